@@ -1,0 +1,79 @@
+"""ctypes binding of libgridinterp.so (include/gridinterp.h).  Fails loudly: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgridinterp.so")
+
+GI_OK, GI_ERR_BAD_ARG, GI_ERR_NO_DEVICE, GI_ERR_OOM, GI_ERR_CUDA = 0, 1, 2, 3, 4
+GI_ERR_ITER_CAP, GI_ERR_TOO_FEW_POINTS, GI_ERR_BAD_INDEX, GI_ERR_HALO = 5, 6, 7, 8
+GI_HOST, GI_DEVICE = 0, 1
+GI_POINTS_ROWMAJOR, GI_TOPO_ROWMAJOR, GI_FIELD_ROWMAJOR, GI_KD_REFERENCE_VISITS = 1, 2, 4, 8
+
+_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+
+# name -> argtypes; every symbol include/gridinterp.h declares (tests/test_abi.py checks the two agree)
+SIGNATURES = {
+    "gi_version": ([], _i),
+    "gi_last_error": ([], C.c_char_p),
+    "gi_device_count": ([], _i),
+    "gi_set_device": ([_i], _i),
+    "gi_host_alloc": ([C.c_uint64], _vp),
+    "gi_host_free": ([_vp], None),
+    "gi_stream_status": ([_vp], _i),
+    "gi_set_profiling": ([_i], None),
+    "gi_last_timings": ([_vp, _i], _i),
+    "gi_last_timing_name": ([_i], C.c_char_p),
+    "gi_release_workspace": ([], None),
+    "gi_bilinear_f64": ([_vp, _i, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _vp], _i),
+    "gi_bilinear_f32": ([_vp, _i, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _vp], _i),
+    "gi_idw_kdtree_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp], _i),
+    "gi_idw_esrg_nearest_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _d, _i, _vp, _i, _i, _vp], _i),
+    "gi_barycentric_interpolation_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp], _i),
+    "gi_barycentric_interpolation_ex_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i,
+                                             _vp, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
+    "gi_idw_kdtree_ex_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
+    "gi_idw_esrg_nearest_ex_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _d, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i,
+                                    _vp], _i),
+    "gi_kd_build_f64": ([_vp, _i, _vp, _i, _i, _vp], _i),
+    "gi_esrg_assign_points_to_cells_f64": ([_vp, _i, _vp, _i, _vp, _i, _d, _vp, _vp, _i, _i, _vp], _i),
+    "gi_fill_nearest_neighbour_f64": ([_vp, _i, _i, _vp, _vp, _i, _i, _vp], _i),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libgridinterp.so (building it with nvcc if the in-tree binary is missing or stale)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH) or os.environ.get("GI_REBUILD"):
+            from . import build as _build
+            _build.build()
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing and could not be built: the CUDA extension is required "
+                              "(there is no CPU fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError = ABI mismatch: fail loudly
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().gi_last_error().decode()
+
+
+def check(status: int, what: str) -> None:
+    if status == GI_OK:
+        return
+    msg = f"{what}: {last_error()} (gi_status {status})"
+    if status == GI_ERR_BAD_ARG:
+        raise ValueError(msg)
+    if status == GI_ERR_OOM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)

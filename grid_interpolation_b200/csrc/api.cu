@@ -1,0 +1,545 @@
+// api.cu -- the C ABI of include/gridinterp.h: argument checks, host <-> device staging for GI_HOST calls,
+// per-stream status words, phase timers.  No interpolation arithmetic lives here.
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "kernels.cuh"
+
+namespace gi {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string t_error;
+void set_error(const std::string& msg) { t_error = msg; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  cudaGetLastError();  // clear the sticky-less error state
+  const char* base = strrchr(file, '/');
+  t_error = std::string(what) + " failed: " + cudaGetErrorString(e) + " (" + (base ? base + 1 : file) + ":" +
+            std::to_string(line) + ")";
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError)
+    return GI_ERR_NO_DEVICE;
+  if (e == cudaErrorMemoryAllocation) return GI_ERR_OOM;
+  return GI_ERR_CUDA;
+}
+
+static std::mutex g_mutex;
+static bool g_pool_configured[64] = {};
+
+int ensure_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: libgridinterp has no CPU fallback");
+    return GI_ERR_NO_DEVICE;
+  }
+  int dev = 0;
+  GI_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (dev < 64 && !g_pool_configured[dev]) {
+    cudaMemPool_t pool;
+    GI_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;  // keep freed scratch cached in the pool between calls
+    GI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    g_pool_configured[dev] = true;
+  }
+  return GI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-(device, stream) status slots
+// ---------------------------------------------------------------------------------------------
+static std::map<std::pair<int, cudaStream_t>, StatusSlot> g_slots;
+
+__global__ void flush_status_kernel(int* dev, volatile int* host) {
+  const int v = *dev;
+  if (v) {
+    if (v > *host) *host = v;
+    *dev = 0;
+  }
+}
+
+int get_status_slot(cudaStream_t s, StatusSlot* out) {
+  int dev = 0;
+  GI_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_mutex);
+  auto key = std::make_pair(dev, s);
+  auto it = g_slots.find(key);
+  if (it == g_slots.end()) {
+    StatusSlot slot;
+    GI_CUDA(cudaMalloc(&slot.dev, sizeof(int)));
+    GI_CUDA(cudaMemset(slot.dev, 0, sizeof(int)));
+    GI_CUDA(cudaHostAlloc(&slot.host, sizeof(int), cudaHostAllocMapped));
+    *slot.host = 0;
+    GI_CUDA(cudaHostGetDevicePointer(&slot.host_dev, slot.host, 0));
+    it = g_slots.emplace(key, slot).first;
+  }
+  *out = it->second;
+  return GI_OK;
+}
+
+int flush_status(cudaStream_t s, const StatusSlot& slot) {
+  flush_status_kernel<<<1, 1, 0, s>>>(slot.dev, slot.host_dev);
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+
+static const char* status_message(int st) {
+  switch (st) {
+    case GI_ERR_ITER_CAP: return "iteration cap hit on the device (walk cycle on a non-Delaunay mesh, or a fully masked grid)";
+    case GI_ERR_TOO_FEW_POINTS: return "fewer source points than num_neighbours";
+    case GI_ERR_BAD_INDEX: return "simplices / neighbours contain an id out of range";
+    case GI_ERR_HALO: return "hull fill needs rows beyond the supplied halo";
+    default: return "device-side error";
+  }
+}
+
+int read_status(cudaStream_t s, bool synchronize) {
+  if (synchronize) GI_CUDA(cudaStreamSynchronize(s));
+  int dev = 0;
+  GI_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_mutex);
+  auto it = g_slots.find(std::make_pair(dev, s));
+  if (it == g_slots.end()) return GI_OK;
+  const int st = *it->second.host;
+  *it->second.host = 0;
+  if (st != GI_OK) set_error(status_message(st));
+  return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase timers
+// ---------------------------------------------------------------------------------------------
+static bool g_profiling = false;
+void set_profiling(bool on) { g_profiling = on; }
+bool profiling() { return g_profiling; }
+
+struct Recorder {
+  std::vector<std::string> names;
+  std::vector<cudaEvent_t> events;  // events[i] opens phase i; the last event closes the last phase
+  int depth = 0;
+  void reset() {
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+    events.clear();
+    names.clear();
+  }
+  void stamp(cudaStream_t s) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) {
+      cudaEventRecord(e, s);
+      events.push_back(e);
+    }
+  }
+};
+static thread_local Recorder t_rec;
+
+Phases::Phases(cudaStream_t s) : stream_(s), on_(g_profiling) {
+  if (!on_) return;
+  if (t_rec.depth == 0) t_rec.reset();
+  ++t_rec.depth;
+}
+void Phases::mark(const char* name) {
+  if (!on_) return;
+  t_rec.names.push_back(name);
+  t_rec.stamp(stream_);
+}
+void Phases::finish() {
+  if (!on_) return;
+  on_ = false;
+  if (--t_rec.depth == 0) t_rec.stamp(stream_);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host staging helpers
+// ---------------------------------------------------------------------------------------------
+static thread_local cudaStream_t t_host_stream = nullptr;
+static int host_stream(cudaStream_t* out) {
+  if (!t_host_stream) GI_CUDA(cudaStreamCreateWithFlags(&t_host_stream, cudaStreamNonBlocking));
+  *out = t_host_stream;
+  return GI_OK;
+}
+
+template <class T>
+static int to_device(Scratch& scr, const T* host, size_t count, T** dev) {
+  GI_TRY(scr.alloc(dev, count));
+  if (count) GI_CUDA(cudaMemcpyAsync(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice, scr.stream()));
+  return GI_OK;
+}
+template <class T>
+static int to_host(Scratch& scr, T* host, const T* dev, size_t count) {
+  if (host && count) GI_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, scr.stream()));
+  return GI_OK;
+}
+template <class T>
+static int out_device(Scratch& scr, T* host, size_t count, T** dev) {  // device twin of an optional host output
+  *dev = nullptr;
+  if (host) GI_TRY(scr.alloc(dev, count));
+  return GI_OK;
+}
+
+static bool valid_flags(int flags) {
+  return (flags & ~(GI_POINTS_ROWMAJOR | GI_TOPO_ROWMAJOR | GI_FIELD_ROWMAJOR | GI_KD_REFERENCE_VISITS)) == 0;
+}
+#define GI_CHECK_COMMON()                                                 \
+  GI_REQUIRE(valid_flags(flags), "unknown bits in flags");                \
+  GI_REQUIRE(mem == GI_HOST || mem == GI_DEVICE, "mem must be GI_HOST or GI_DEVICE")
+
+// ---------------------------------------------------------------------------------------------
+// typed implementations behind the C symbols
+// ---------------------------------------------------------------------------------------------
+template <class R>
+static int bilinear_api(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* data_in, const R* points,
+                        int64_t n, R* data_ip, int flags, int mem, void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(x_axis && y_axis && data_in && (n == 0 || (points && data_ip)), "null pointer");
+  GI_REQUIRE(len_x >= 2 && len_y >= 2 && n >= 0, "bad dimensions");
+  if (mem == GI_DEVICE)
+    return bilinear_device<R>(x_axis, len_x, y_axis, len_y, data_in, points, n, data_ip, flags, (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("h2d");
+  R *dx, *dy, *dd, *dp, *dout;
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  GI_TRY(to_device(scr, data_in, (size_t)len_x * len_y, &dd));
+  GI_TRY(to_device(scr, points, (size_t)2 * n, &dp));
+  GI_TRY(scr.alloc(&dout, (size_t)n));
+  GI_TRY(bilinear_device<R>(dx, len_x, dy, len_y, dd, dp, n, dout, flags, st));
+  ph.mark("d2h");
+  GI_TRY(to_host(scr, data_ip, dout, (size_t)n));
+  ph.finish();
+  GI_CUDA(cudaStreamSynchronize(st));
+  return GI_OK;
+}
+
+template <class R>
+static int barycentric_api(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                           const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
+                           int num_tri, int row_begin, int row_end, int halo, R* data_ip, int32_t* tri_out,
+                           uint8_t* mask_out, int64_t* fill_src, int64_t* counters, int flags, int mem,
+                           void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(points && data_in && x_axis && y_axis && simplices && neighbours && data_ip, "null pointer");
+  GI_REQUIRE(num_points >= 3 && num_tri >= 1 && len_x >= 1 && len_y >= 1, "bad dimensions");
+  GI_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= len_y && halo >= 0, "bad row band");
+  if (mem == GI_DEVICE)
+    return barycentric_device<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
+                                 num_tri, row_begin, row_end, halo, data_ip, tri_out, mask_out, fill_src,
+                                 counters, flags, (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("h2d");
+  const size_t band = (size_t)(row_end - row_begin) * len_x;
+  R *dp, *dd, *dx, *dy, *dout;
+  int32_t *ds, *dn, *dtri;
+  uint8_t* dmask;
+  int64_t *dsrc, *dcnt;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, data_in, (size_t)num_points, &dd));
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  GI_TRY(to_device(scr, simplices, (size_t)3 * num_tri, &ds));
+  GI_TRY(to_device(scr, neighbours, (size_t)3 * num_tri, &dn));
+  GI_TRY(scr.alloc(&dout, band));
+  GI_TRY(out_device(scr, tri_out, band, &dtri));
+  GI_TRY(out_device(scr, mask_out, band, &dmask));
+  GI_TRY(out_device(scr, fill_src, band, &dsrc));
+  GI_TRY(out_device(scr, counters, 4, &dcnt));
+  GI_TRY(barycentric_device<R>(dp, num_points, dd, dx, len_x, dy, len_y, ds, dn, num_tri, row_begin, row_end, halo,
+                               dout, dtri, dmask, dsrc, dcnt, flags, st));
+  ph.mark("d2h");
+  GI_TRY(to_host(scr, data_ip, dout, band));
+  GI_TRY(to_host(scr, tri_out, dtri, band));
+  GI_TRY(to_host(scr, mask_out, dmask, band));
+  GI_TRY(to_host(scr, fill_src, dsrc, band));
+  GI_TRY(to_host(scr, counters, dcnt, 4));
+  ph.finish();
+  return read_status(st, true);
+}
+
+template <class R>
+static int fill_api(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* fill_src, int flags, int mem,
+                    void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(mask && data_ip && len_x >= 1 && len_y >= 1, "bad arguments");
+  if (mem == GI_DEVICE) return fill_device<R>(mask, len_x, len_y, data_ip, fill_src, flags, (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  const size_t n = (size_t)len_x * len_y;
+  uint8_t* dm; R* dd; int64_t* dsrc;
+  GI_TRY(to_device(scr, mask, n, &dm));
+  GI_TRY(to_device(scr, data_ip, n, &dd));
+  GI_TRY(out_device(scr, fill_src, n, &dsrc));
+  GI_TRY(fill_device<R>(dm, len_x, len_y, dd, dsrc, flags, st));
+  GI_TRY(to_host(scr, data_ip, dd, n));
+  GI_TRY(to_host(scr, fill_src, dsrc, n));
+  return read_status(st, true);
+}
+
+template <class R>
+static int kdtree_api(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                      const R* y_axis, int len_y, int k, int row_begin, int row_end, R* data_ip,
+                      int32_t* nn_index, R* nn_dist2, int64_t* counters, int flags, int mem, void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(points && data_in && x_axis && y_axis && data_ip, "null pointer");
+  GI_REQUIRE(num_points >= 1 && len_x >= 1 && len_y >= 1 && k >= 1, "bad dimensions");
+  GI_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= len_y, "bad row band");
+  if (mem == GI_DEVICE)
+    return kdtree_device<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, k, row_begin, row_end,
+                            data_ip, nn_index, nn_dist2, counters, flags, (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("h2d");
+  const size_t band = (size_t)(row_end - row_begin) * len_x;
+  R *dp, *dd, *dx, *dy, *dout, *dd2;
+  int32_t* dnn;
+  int64_t* dcnt;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, data_in, (size_t)num_points, &dd));
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  GI_TRY(scr.alloc(&dout, band));
+  GI_TRY(out_device(scr, nn_index, band * k, &dnn));
+  GI_TRY(out_device(scr, nn_dist2, band * k, &dd2));
+  GI_TRY(out_device(scr, counters, 4, &dcnt));
+  GI_TRY(kdtree_device<R>(dp, num_points, dd, dx, len_x, dy, len_y, k, row_begin, row_end, dout, dnn, dd2, dcnt,
+                          flags, st));
+  ph.mark("d2h");
+  GI_TRY(to_host(scr, data_ip, dout, band));
+  GI_TRY(to_host(scr, nn_index, dnn, band * k));
+  GI_TRY(to_host(scr, nn_dist2, dd2, band * k));
+  GI_TRY(to_host(scr, counters, dcnt, 4));
+  ph.finish();
+  return read_status(st, true);
+}
+
+template <class R>
+static int esrg_api(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+                    int len_y, R grid_spac, int k, int row_begin, int row_end, R* data_ip, int32_t* nn_index,
+                    R* nn_dist2, int64_t* counters, int flags, int mem, void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(points && data_in && x_axis && y_axis && data_ip, "null pointer");
+  GI_REQUIRE(num_points >= 1 && len_x >= 1 && len_y >= 1 && k >= 1, "bad dimensions");
+  GI_REQUIRE(grid_spac > R(0), "grid_spac must be positive");
+  GI_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= len_y, "bad row band");
+  if (num_points < k) {
+    set_error("fewer source points than num_neighbours (the reference loops forever, query_esrg.f90:178)");
+    return GI_ERR_TOO_FEW_POINTS;
+  }
+  if (mem == GI_DEVICE)
+    return esrg_device<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, k, row_begin,
+                          row_end, data_ip, nn_index, nn_dist2, counters, flags, (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("h2d");
+  const size_t band = (size_t)(row_end - row_begin) * len_x;
+  R *dp, *dd, *dx, *dy, *dout, *dd2;
+  int32_t* dnn;
+  int64_t* dcnt;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, data_in, (size_t)num_points, &dd));
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  GI_TRY(scr.alloc(&dout, band));
+  GI_TRY(out_device(scr, nn_index, band * k, &dnn));
+  GI_TRY(out_device(scr, nn_dist2, band * k, &dd2));
+  GI_TRY(out_device(scr, counters, 4, &dcnt));
+  GI_TRY(esrg_device<R>(dp, num_points, dd, dx, len_x, dy, len_y, grid_spac, k, row_begin, row_end, dout, dnn, dd2,
+                        dcnt, flags, st));
+  ph.mark("d2h");
+  GI_TRY(to_host(scr, data_ip, dout, band));
+  GI_TRY(to_host(scr, nn_index, dnn, band * k));
+  GI_TRY(to_host(scr, nn_dist2, dd2, band * k));
+  GI_TRY(to_host(scr, counters, dcnt, 4));
+  ph.finish();
+  return read_status(st, true);
+}
+
+template <class R>
+static int kd_build_api(const R* points, int num_points, int32_t* order, int flags, int mem, void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(points && order && num_points >= 1, "bad arguments");
+  if (mem == GI_DEVICE) return kd_build_device<R>(points, num_points, order, flags, (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  R* dp; int32_t* dord;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(scr.alloc(&dord, (size_t)num_points));
+  GI_TRY(kd_build_device<R>(dp, num_points, dord, flags, st));
+  GI_TRY(to_host(scr, order, dord, (size_t)num_points));
+  return read_status(st, true);
+}
+
+template <class R>
+static int esrg_bin_api(const R* points, int num_points, const R* x_axis, int len_x, const R* y_axis, int len_y,
+                        R grid_spac, int32_t* index_of_pts, int32_t* indptr, int flags, int mem, void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(points && x_axis && y_axis && index_of_pts && indptr, "null pointer");
+  GI_REQUIRE(num_points >= 1 && len_x >= 1 && len_y >= 1 && grid_spac > R(0), "bad dimensions");
+  if (mem == GI_DEVICE)
+    return esrg_bin_device<R>(points, num_points, x_axis, len_x, y_axis, len_y, grid_spac, index_of_pts, indptr,
+                              flags, (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  const size_t cells = (size_t)len_x * len_y;
+  R *dp, *dx, *dy; int32_t *didx, *dptr;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  GI_TRY(scr.alloc(&didx, (size_t)num_points));
+  GI_TRY(scr.alloc(&dptr, cells + 1));
+  GI_TRY(esrg_bin_device<R>(dp, num_points, dx, len_x, dy, len_y, grid_spac, didx, dptr, flags, st));
+  GI_TRY(to_host(scr, index_of_pts, didx, (size_t)num_points));
+  GI_TRY(to_host(scr, indptr, dptr, cells + 1));
+  return read_status(st, true);
+}
+
+}  // namespace gi
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+using namespace gi;
+#define GI_API extern "C" __attribute__((visibility("default")))
+
+GI_API int gi_version(void) { return GI_VERSION; }
+GI_API const char* gi_last_error(void) { return t_error.c_str(); }
+GI_API int gi_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+GI_API int gi_set_device(int device) { GI_CUDA(cudaSetDevice(device)); return GI_OK; }
+GI_API void* gi_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaHostAlloc failed");
+    return nullptr;
+  }
+  return p;
+}
+GI_API void gi_host_free(void* p) { if (p) cudaFreeHost(p); }
+GI_API int gi_stream_status(void* stream) { return read_status((cudaStream_t)stream, true); }
+GI_API void gi_set_profiling(int on) { set_profiling(on != 0); }
+GI_API int gi_last_timings(double* ms, int capacity) {
+  Recorder& r = t_rec;
+  if (r.events.size() < 2) return 0;
+  cudaEventSynchronize(r.events.back());
+  const int n = (int)std::min(r.names.size(), r.events.size() - 1);
+  for (int i = 0; i < n && i < capacity; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.events[i], r.events[i + 1]);
+    ms[i] = t;
+  }
+  return n;
+}
+GI_API const char* gi_last_timing_name(int i) {
+  return (i >= 0 && i < (int)t_rec.names.size()) ? t_rec.names[i].c_str() : "";
+}
+GI_API void gi_release_workspace(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    cudaDeviceSynchronize();
+    cudaMemPoolTrimTo(pool, 0);
+  }
+}
+
+GI_API int gi_bilinear_f64(const double* x_axis, int len_x, const double* y_axis, int len_y, const double* data_in,
+                           const double* points, int64_t num_points, double* data_ip, int flags, int mem,
+                           void* stream) {
+  return bilinear_api<double>(x_axis, len_x, y_axis, len_y, data_in, points, num_points, data_ip, flags, mem, stream);
+}
+GI_API int gi_bilinear_f32(const float* x_axis, int len_x, const float* y_axis, int len_y, const float* data_in,
+                           const float* points, int64_t num_points, float* data_ip, int flags, int mem,
+                           void* stream) {
+  return bilinear_api<float>(x_axis, len_x, y_axis, len_y, data_in, points, num_points, data_ip, flags, mem, stream);
+}
+
+GI_API int gi_idw_kdtree_f64(const double* points, int num_points, const double* data_in, const double* x_axis,
+                             int len_x, const double* y_axis, int len_y, int num_neighbours, double* data_ip,
+                             int flags, int mem, void* stream) {
+  return kdtree_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, num_neighbours, 0, len_y,
+                            data_ip, nullptr, nullptr, nullptr, flags, mem, stream);
+}
+GI_API int gi_idw_kdtree_ex_f64(const double* points, int num_points, const double* data_in, const double* x_axis,
+                                int len_x, const double* y_axis, int len_y, int num_neighbours, int row_begin,
+                                int row_end, double* data_ip, int32_t* nn_index, double* nn_dist2,
+                                int64_t* counters, int flags, int mem, void* stream) {
+  return kdtree_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, num_neighbours, row_begin,
+                            row_end, data_ip, nn_index, nn_dist2, counters, flags, mem, stream);
+}
+
+GI_API int gi_idw_esrg_nearest_f64(const double* points, int num_points, const double* data_in,
+                                   const double* x_axis, int len_x, const double* y_axis, int len_y,
+                                   double grid_spac, int num_neighbours, double* data_ip, int flags, int mem,
+                                   void* stream) {
+  return esrg_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, num_neighbours, 0,
+                          len_y, data_ip, nullptr, nullptr, nullptr, flags, mem, stream);
+}
+GI_API int gi_idw_esrg_nearest_ex_f64(const double* points, int num_points, const double* data_in,
+                                      const double* x_axis, int len_x, const double* y_axis, int len_y,
+                                      double grid_spac, int num_neighbours, int row_begin, int row_end,
+                                      double* data_ip, int32_t* nn_index, double* nn_dist2, int64_t* counters,
+                                      int flags, int mem, void* stream) {
+  return esrg_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, num_neighbours,
+                          row_begin, row_end, data_ip, nn_index, nn_dist2, counters, flags, mem, stream);
+}
+
+GI_API int gi_barycentric_interpolation_f64(const double* points, int num_points, const double* data_in,
+                                            const double* x_axis, int len_x, const double* y_axis, int len_y,
+                                            const int32_t* simplices, const int32_t* neighbours,
+                                            int num_triangles, double* data_ip, int flags, int mem,
+                                            void* stream) {
+  return barycentric_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
+                                 num_triangles, 0, len_y, 0, data_ip, nullptr, nullptr, nullptr, nullptr, flags,
+                                 mem, stream);
+}
+GI_API int gi_barycentric_interpolation_ex_f64(const double* points, int num_points, const double* data_in,
+                                               const double* x_axis, int len_x, const double* y_axis, int len_y,
+                                               const int32_t* simplices, const int32_t* neighbours,
+                                               int num_triangles, int row_begin, int row_end, int halo,
+                                               double* data_ip, int32_t* tri_out, uint8_t* mask_out,
+                                               int64_t* fill_src, int64_t* counters, int flags, int mem,
+                                               void* stream) {
+  return barycentric_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
+                                 num_triangles, row_begin, row_end, halo, data_ip, tri_out, mask_out, fill_src,
+                                 counters, flags, mem, stream);
+}
+
+GI_API int gi_kd_build_f64(const double* points, int num_points, int32_t* order, int flags, int mem, void* stream) {
+  return kd_build_api<double>(points, num_points, order, flags, mem, stream);
+}
+GI_API int gi_esrg_assign_points_to_cells_f64(const double* points, int num_points, const double* x_axis,
+                                              int len_x, const double* y_axis, int len_y, double grid_spac,
+                                              int32_t* index_of_pts, int32_t* indptr, int flags, int mem,
+                                              void* stream) {
+  return esrg_bin_api<double>(points, num_points, x_axis, len_x, y_axis, len_y, grid_spac, index_of_pts, indptr,
+                              flags, mem, stream);
+}
+GI_API int gi_fill_nearest_neighbour_f64(const uint8_t* mask_outside, int len_x, int len_y, double* data_ip,
+                                         int64_t* fill_src, int flags, int mem, void* stream) {
+  return fill_api<double>(mask_outside, len_x, len_y, data_ip, fill_src, flags, mem, stream);
+}

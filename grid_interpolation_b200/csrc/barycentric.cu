@@ -1,0 +1,491 @@
+// barycentric.cu -- triangle mesh -> regular grid: visibility walk + barycentric weights + hull fill.
+//
+// Replaces (reference file:line):
+//   interpolation.f90:298-416   barycentric_interpolation (operator)
+//   triangle_walk.f90:24-84     find_triangle (visibility walk)
+//   triangle_walk.f90:140-153   triangle_point_outside (orientation predicate, margin -1e-10)
+//   triangle_walk.f90:90-132    fill_nearest_neighbour (nearest unmasked cell in index space)
+//
+// B200 design (not a port):
+//   1. pack_mesh_kernel  gathers every triangle's 3 vertices + 3 neighbour ids into ONE 64-byte record
+//      (two 32 B sectors) and its 3 nodal values into a 32-byte record, so that a walk step is a single
+//      aligned 64 B load instead of 3 index loads + 6 scattered coordinate loads.  The same pass bins one
+//      triangle id per 16x16-target cell (atomicMin -> deterministic) into a seed grid.
+//   2. walk_kernel       one thread per target column, chained down a strip of rows: the triangle found
+//      for row r seeds row r+1 (the reference chains along a grid row in the same way, interpolation.f90:
+//      366-373, but restarts every row from one global start triangle; here the first row of a strip is
+//      seeded from the seed grid).  The found triangle is path-independent outside the 1e-10 margin band
+//      (SURVEY 0.7), so the seeding changes the iteration count, not the result.  A warp covers 32
+//      consecutive targets of the contiguous output axis -> 256 B coalesced stores; outside-hull flags go
+//      into a 1-bit-per-target mask written with one ballot per warp row.
+//   3. fill_kernel       one warp per mask word, one lane per masked cell: exact ring search over the bit
+//      mask with the reference's tie-break (smallest squared index distance, then smallest row, then
+//      smallest column).
+//
+// All index decisions (orientation signs, first failing edge) use the reference's expression order with
+// FMA contraction disabled (-fmad=false), so they are bit-identical to the oracle's.
+#include "kernels.cuh"
+
+namespace gi {
+
+namespace {
+
+constexpr int kSeedCell = 16;      // targets per seed-grid cell edge
+constexpr int kWalkThreads = 128;  // one CTA = 128 columns x kWalkRows rows
+constexpr int kWalkRows = 32;
+
+template <class R> struct alignas(16) TriGeom {  // f64: 64 B = 2 sectors
+  R x1, y1, x2, y2, x3, y3;
+  int n1, n2, n3;  // neighbour opposite vertex 1/2/3, 0-based, -1 = hull edge
+  int pad;
+};
+template <class R> struct alignas(16) TriVals {  // f64: 32 B = 1 sector
+  R d1, d2, d3, pad;
+};
+template <class R> struct SeedGrid {
+  R x0, y0, inv_cell_x, inv_cell_y;
+  int ncx, ncy;
+};
+
+template <class R>
+__global__ void seed_setup_kernel(const R* x_axis, int len_x, const R* y_axis, int len_y, SeedGrid<R>* sg) {
+  SeedGrid<R> s;
+  s.ncx = (len_x + kSeedCell - 1) / kSeedCell;
+  s.ncy = (len_y + kSeedCell - 1) / kSeedCell;
+  s.x0 = x_axis[0];
+  s.y0 = y_axis[0];
+  const R ex = x_axis[len_x - 1] - x_axis[0], ey = y_axis[len_y - 1] - y_axis[0];
+  s.inv_cell_x = (len_x > 1 && ex > R(0)) ? R(len_x - 1) / ex / R(kSeedCell) : R(0);
+  s.inv_cell_y = (len_y > 1 && ey > R(0)) ? R(len_y - 1) / ey / R(kSeedCell) : R(0);
+  *sg = s;
+}
+
+template <class R>
+__global__ void __launch_bounds__(256)
+pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, TopoView nbr, int num_points,
+                 int num_tri, TriGeom<R>* __restrict__ geom, TriVals<R>* __restrict__ vals,
+                 int* __restrict__ seed, const SeedGrid<R>* __restrict__ sgp, int* __restrict__ status) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_tri) return;
+  const SeedGrid<R> sg = *sgp;
+  int a = simp(t, 0), b = simp(t, 1), c = simp(t, 2);
+  int n1 = nbr(t, 0), n2 = nbr(t, 1), n3 = nbr(t, 2);
+  const bool bad = (unsigned)(a - 1) >= (unsigned)num_points || (unsigned)(b - 1) >= (unsigned)num_points ||
+                   (unsigned)(c - 1) >= (unsigned)num_points || (unsigned)n1 > (unsigned)num_tri ||
+                   (unsigned)n2 > (unsigned)num_tri || (unsigned)n3 > (unsigned)num_tri;
+  if (bad) {  // reference: out-of-bounds read.  Here: error status, record made harmless.
+    raise_status(status, GI_ERR_BAD_INDEX);
+    a = b = c = 1;
+    n1 = n2 = n3 = 0;
+  }
+  TriGeom<R> g;
+  g.x1 = pts.x(a - 1); g.y1 = pts.y(a - 1);
+  g.x2 = pts.x(b - 1); g.y2 = pts.y(b - 1);
+  g.x3 = pts.x(c - 1); g.y3 = pts.y(c - 1);
+  g.n1 = n1 - 1; g.n2 = n2 - 1; g.n3 = n3 - 1;
+  g.pad = 0;
+  geom[t] = g;
+  TriVals<R> v;
+  v.d1 = __ldg(data + (a - 1)); v.d2 = __ldg(data + (b - 1)); v.d3 = __ldg(data + (c - 1));
+  v.pad = R(0);
+  vals[t] = v;
+  if (bad) return;
+  // seed grid: cell of the centroid under a uniform-axis approximation (a heuristic: it only has to be near)
+  const R cx = (g.x1 + g.x2 + g.x3) / R(3), cy = (g.y1 + g.y2 + g.y3) / R(3);
+  const R fx = (cx - sg.x0) * sg.inv_cell_x, fy = (cy - sg.y0) * sg.inv_cell_y;
+  if (fx >= R(0) && fy >= R(0) && fx < R(sg.ncx) && fy < R(sg.ncy))
+    atomicMin(seed + (int)fy * sg.ncx + (int)fx, t);
+}
+
+// Seed triangle for grid target (ix, iy): the cell's own entry, else the nearest non-empty cell within 3
+// rings, else triangle 0.  Any valid triangle is a correct seed.
+__device__ __forceinline__ int seed_lookup(const int* __restrict__ seed, int ncx, int ncy, int ix, int iy,
+                                           int num_tri) {
+  const int cx = ix / kSeedCell, cy = iy / kSeedCell;
+  int s = __ldg(seed + cy * ncx + cx);
+  if (s < num_tri) return s;
+  for (int r = 1; r <= 3; ++r)
+    for (int dy = -r; dy <= r; ++dy)
+      for (int dx = -r; dx <= r; ++dx) {
+        if (max(abs(dx), abs(dy)) != r) continue;
+        const int x = cx + dx, y = cy + dy;
+        if (x < 0 || y < 0 || x >= ncx || y >= ncy) continue;
+        s = __ldg(seed + y * ncx + x);
+        if (s < num_tri) return s;
+      }
+  return 0;
+}
+
+// triangle_walk.f90:24-84 + :140-153.  Returns the triangle the walk ends in and leaves its record in g;
+// inside=false if the walk left through a hull edge (tri is then the last valid triangle, the reference's
+// ind_tri_pre).
+template <class R>
+__device__ __forceinline__ int walk(const TriGeom<R>* __restrict__ geom, int tri, R tx, R ty, int iter_cap,
+                                    bool& inside, int& iters, TriGeom<R>& g, int* status) {
+  const R margin = Consts<R>::margin();
+  inside = true;
+  int it = 0;
+  for (;;) {
+    ++it;
+    g = geom[tri];
+    // edges (v1,v2), (v2,v3), (v3,v1); cross = (x2-x1)*(py-y1) - (y2-y1)*(px-x1)   (:149-150)
+    const R c1 = (g.x2 - g.x1) * (ty - g.y1) - (g.y2 - g.y1) * (tx - g.x1);
+    const R c2 = (g.x3 - g.x2) * (ty - g.y2) - (g.y3 - g.y2) * (tx - g.x2);
+    const R c3 = (g.x1 - g.x3) * (ty - g.y3) - (g.y1 - g.y3) * (tx - g.x3);
+    int nxt;
+    // first failing edge wins (:57-60); edge i -> neighbour opposite vertex i-1 (wrap) (:66-71)
+    if (c1 < margin) nxt = g.n3;
+    else if (c2 < margin) nxt = g.n1;
+    else if (c3 < margin) nxt = g.n2;
+    else break;
+    if (nxt < 0) { inside = false; break; }  // :74-80
+    tri = nxt;
+    if (it >= iter_cap) { raise_status(status, GI_ERR_ITER_CAP); inside = false; break; }
+  }
+  iters = it;
+  return tri;
+}
+
+// interpolation.f90:385-398, same operation order.
+template <class R>
+__device__ __forceinline__ R barycentric_value(const TriGeom<R>& g, const TriVals<R>& v, R tx, R ty) {
+  const R denom = (g.y2 - g.y3) * (g.x1 - g.x3) + (g.x3 - g.x2) * (g.y1 - g.y3);
+  const R w1 = ((g.y2 - g.y3) * (tx - g.x3) + (g.x3 - g.x2) * (ty - g.y3)) / denom;
+  const R w2 = ((g.y3 - g.y1) * (tx - g.x3) + (g.x1 - g.x3) * (ty - g.y3)) / denom;
+  const R w3 = R(1) - w1 - w2;
+  return v.d1 * w1 + v.d2 * w2 + v.d3 * w3;
+}
+
+template <class R> struct WalkArgs {
+  TargetWindow<R> win;   // walked window E (band + halo)
+  int bf0, bf1, bs0, bs1;  // band B inside E: the part that is written to `out`
+  const TriGeom<R>* geom;
+  const TriVals<R>* vals;
+  const int* seed;
+  int ncx, ncy, num_tri, iter_cap;
+  R* out;               // band-shaped: (bs1-bs0) slow rows of (bf1-bf0)
+  int32_t* tri_out;     // optional, band-shaped
+  uint32_t* mask_words; // E-shaped bit mask: ((nf+31)/32) words per slow row
+  int64_t* counters;
+  int* status;
+};
+
+template <class R>
+__global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkArgs<R> a) {
+  const TargetWindow<R>& w = a.win;
+  const int lane_f = blockIdx.x * kWalkThreads + threadIdx.x;
+  const int f = w.f0 + lane_f;
+  const bool active = f < w.f1;
+  const int srow0 = w.s0 + blockIdx.y * kWalkRows;
+  const int srow1 = min(srow0 + kWalkRows, w.s1);
+  const R tf = active ? __ldg(w.fast_axis + f) : R(0);
+  const int wpr = (w.nf() + 31) >> 5;  // mask words per slow row
+  const bool f_in_band = active && f >= a.bf0 && f < a.bf1;
+
+  int tri = 0;
+  if (active) {
+    const int ix = w.fast_is_y ? srow0 : f, iy = w.fast_is_y ? f : srow0;
+    tri = seed_lookup(a.seed, a.ncx, a.ncy, ix, iy, a.num_tri);
+  }
+  long long iters_sum = 0;
+  for (int s = srow0; s < srow1; ++s) {
+    const R ts = __ldg(w.slow_axis + s);
+    const R tx = w.fast_is_y ? ts : tf, ty = w.fast_is_y ? tf : ts;
+    bool inside = true;
+    if (active) {
+      TriGeom<R> g;
+      int iters;
+      tri = walk(a.geom, tri, tx, ty, a.iter_cap, inside, iters, g, a.status);
+      iters_sum += iters;
+      if (f_in_band && s >= a.bs0 && s < a.bs1) {
+        const int64_t o = (int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0);
+        if (inside) {
+          const TriVals<R> v = a.vals[tri];
+          a.out[o] = barycentric_value(g, v, tx, ty);
+        }
+        if (a.tri_out) a.tri_out[o] = tri + 1;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, active && !inside);
+    if ((threadIdx.x & 31) == 0 && (lane_f >> 5) < wpr)
+      a.mask_words[(int64_t)(s - w.s0) * wpr + (lane_f >> 5)] = m;
+  }
+  // one atomic per warp for the iteration counter (iters_tot, interpolation.f90:374)
+  for (int off = 16; off > 0; off >>= 1) iters_sum += __shfl_down_sync(0xffffffffu, iters_sum, off);
+  if ((threadIdx.x & 31) == 0 && iters_sum)
+    atomicAdd((unsigned long long*)a.counters, (unsigned long long)iters_sum);
+}
+
+// ---------------------------------------------------------------------------------------------
+// hull fill (triangle_walk.f90:90-132) on the bit mask of the walked window
+// ---------------------------------------------------------------------------------------------
+template <class R> struct FillArgs {
+  TargetWindow<R> win;  // window E covered by the bit mask
+  const uint32_t* mask_words;
+  int bf0, bf1, bs0, bs1;  // band B inside E (cells to fill, and where `out` lives)
+  R* out;
+  int64_t* fill_src;  // optional, band-shaped
+  int64_t* counters;  // [1] += masked cells, [2] = max level
+  int len_x, len_y;
+  // to recompute the value of a source cell that lies in the halo (outside the band); geom == nullptr for
+  // the standalone fill (no halo there)
+  const TriGeom<R>* geom;
+  const TriVals<R>* vals;
+  const int* seed;
+  int ncx, ncy, num_tri, iter_cap;
+  int* status;
+};
+
+template <class R>
+__device__ __forceinline__ int fill_cell_state(const FillArgs<R>& a, int wpr, int iy, int ix) {
+  // 0 = unmasked (valid source), 1 = masked, 2 = outside the walked window (unknown)
+  const int f = a.win.fast_is_y ? iy : ix, s = a.win.fast_is_y ? ix : iy;
+  if (f < a.win.f0 || f >= a.win.f1 || s < a.win.s0 || s >= a.win.s1) return 2;
+  const int lf = f - a.win.f0;
+  const uint32_t wd = __ldg(a.mask_words + (int64_t)(s - a.win.s0) * wpr + (lf >> 5));
+  return (wd >> (lf & 31)) & 1u;
+}
+
+__device__ __forceinline__ int isqrt_floor(int v) {  // floor(sqrt(v)) for v >= 0
+  int r = (int)sqrtf((float)v);
+  while (r * r > v) --r;
+  while ((r + 1) * (r + 1) <= v) ++r;
+  return r;
+}
+
+template <class R>
+__global__ void __launch_bounds__(128) fill_kernel(const FillArgs<R> a) {
+  const int nf = a.win.nf(), wpr = (nf + 31) >> 5;
+  const int64_t num_words = (int64_t)wpr * a.win.ns();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t num_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int level_max = 0;
+  long long masked = 0;
+  const int level_cap = a.len_x + a.len_y;
+  for (int64_t wi = warp0; wi < num_words; wi += num_warps) {
+    const uint32_t wd = __ldg(a.mask_words + wi);
+    if (wd == 0) continue;
+    const int s = a.win.s0 + (int)(wi / wpr), f = a.win.f0 + (int)(wi % wpr) * 32 + lane;
+    if (!((wd >> lane) & 1u)) continue;
+    if (f < a.bf0 || f >= a.bf1 || s < a.bs0 || s >= a.bs1) continue;  // halo cell: not ours to fill
+    ++masked;
+    const int iy = a.win.fast_is_y ? f : s, ix = a.win.fast_is_y ? s : f;
+    int best_i = -1, best_j = -1, level = 0;
+    bool unknown = false;
+    while (best_i < 0 && !unknown) {
+      ++level;                                                     // :110
+      if (level > level_cap) { raise_status(a.status, GI_ERR_ITER_CAP); break; }
+      // annulus (L-0.5)^2 <= d2 < (L+0.5)^2 over integers: L*L-L < d2 <= L*L+L   (:111-112,117-118)
+      const int lo = level * level - level, hi = level * level + level;
+      int best_d2 = 0x7fffffff;
+      for (int di = -level; di <= level; ++di) {                   // rows ascending (:113)
+        const int i2 = iy + di;
+        if (i2 < 0 || i2 >= a.len_y) continue;
+        const int rem_hi = hi - di * di;
+        if (rem_hi < 0) continue;
+        const int dj_max = isqrt_floor(rem_hi);
+        const int rem_lo = lo - di * di;                           // need dj*dj > rem_lo
+        const int dj_min = rem_lo < 0 ? 0 : isqrt_floor(rem_lo) + 1;
+        for (int pass = 0; pass < 2; ++pass) {                     // columns ascending (:114)
+          for (int k = (pass == 0 ? dj_max : dj_min); pass == 0 ? k >= dj_min : k <= dj_max;
+               k += (pass == 0 ? -1 : 1)) {
+            if (pass == 1 && k == 0) continue;                     // dj = 0 handled in pass 0
+            const int j2 = ix + (pass == 0 ? -k : k);
+            if (j2 < 0 || j2 >= a.len_x) continue;
+            const int st = fill_cell_state(a, wpr, i2, j2);
+            if (st == 2) { unknown = true; continue; }
+            if (st == 0) {
+              const int d2 = di * di + k * k;
+              if (d2 < best_d2) { best_d2 = d2; best_i = i2; best_j = j2; }  // strict '<' (:119)
+            }
+          }
+        }
+      }
+      // a level is only trustworthy if none of its annulus cells was outside the walked window
+      if (unknown) { raise_status(a.status, GI_ERR_HALO); best_i = -1; }
+    }
+    level_max = max(level_max, level);
+    if (best_i < 0) continue;
+    const int sf = a.win.fast_is_y ? best_i : best_j, ss = a.win.fast_is_y ? best_j : best_i;
+    R v;
+    if (sf >= a.bf0 && sf < a.bf1 && ss >= a.bs0 && ss < a.bs1) {
+      v = a.out[(int64_t)(ss - a.bs0) * (a.bf1 - a.bf0) + (sf - a.bf0)];
+    } else {  // source cell lies in the halo: recompute its (deterministic) value
+      const R tx = __ldg((a.win.fast_is_y ? a.win.slow_axis : a.win.fast_axis) + best_j);
+      const R ty = __ldg((a.win.fast_is_y ? a.win.fast_axis : a.win.slow_axis) + best_i);
+      bool inside; int iters; TriGeom<R> g;
+      const int tri = walk(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, best_j, best_i, a.num_tri), tx, ty,
+                           a.iter_cap, inside, iters, g, a.status);
+      v = barycentric_value(g, a.vals[tri], tx, ty);
+    }
+    const int64_t o = (int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0);
+    a.out[o] = v;                                                  // :121
+    if (a.fill_src) a.fill_src[o] = (int64_t)best_i * a.len_x + best_j;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    masked += __shfl_down_sync(0xffffffffu, masked, off);
+    level_max = max(level_max, __shfl_down_sync(0xffffffffu, level_max, off));
+  }
+  if (lane == 0) {
+    if (masked) atomicAdd((unsigned long long*)(a.counters + 1), (unsigned long long)masked);
+    if (level_max) atomicMax((unsigned long long*)(a.counters + 2), (unsigned long long)level_max);
+  }
+}
+
+__global__ void expand_mask_kernel(const uint32_t* __restrict__ mask_words, int wpr, int e_f0, int e_s0,
+                                   int bf0, int bf1, int bs0, int bs1, uint8_t* __restrict__ mask_out,
+                                   int64_t* __restrict__ fill_src) {
+  const int bnf = bf1 - bf0;
+  const int64_t n = (int64_t)bnf * (bs1 - bs0);
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const int s = bs0 + (int)(o / bnf), f = bf0 + (int)(o % bnf);
+    const int lf = f - e_f0;
+    const uint32_t wd = mask_words[(int64_t)(s - e_s0) * wpr + (lf >> 5)];
+    if (mask_out) mask_out[o] = (wd >> (lf & 31)) & 1u;
+    if (fill_src) fill_src[o] = -1;
+  }
+}
+
+// standalone fill on a caller-supplied byte mask: pack it into the bit mask first
+__global__ void bytes_to_bits_kernel(const uint8_t* __restrict__ mask, int nf, int wpr,
+                                     uint32_t* __restrict__ words) {
+  const int lane_f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  const bool m = lane_f < nf && mask[(int64_t)s * nf + lane_f] != 0;
+  const unsigned b = __ballot_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && (lane_f >> 5) < wpr) words[(int64_t)s * wpr + (lane_f >> 5)] = b;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host-side orchestration (device pointers in, work enqueued on `st`)
+// ---------------------------------------------------------------------------------------------
+template <class R>
+int barycentric_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                       const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
+                       int num_tri, int row_begin, int row_end, int halo, R* data_ip, int32_t* tri_out,
+                       uint8_t* mask_out, int64_t* fill_src, int64_t* counters_out, int flags,
+                       cudaStream_t st) {
+  GI_REQUIRE(num_points >= 3 && num_tri >= 1, "need at least 3 points and 1 triangle");
+  GI_REQUIRE(len_x >= 1 && len_y >= 1, "empty axis");
+  GI_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= len_y, "row band out of range");
+  GI_REQUIRE(halo >= 0, "negative halo");
+  GI_TRY(ensure_device());
+  if (row_begin == row_end) return GI_OK;
+  StatusSlot slot;
+  GI_TRY(get_status_slot(st, &slot));
+  Scratch scr(st);
+  Phases ph(st);
+
+  // ---- 1. pack the mesh ---------------------------------------------------------------------
+  ph.mark("pack_mesh");
+  TriGeom<R>* geom; TriVals<R>* vals; SeedGrid<R>* sg; int* seed; int64_t* counters;
+  GI_TRY(scr.alloc(&geom, (size_t)num_tri));
+  GI_TRY(scr.alloc(&vals, (size_t)num_tri));
+  GI_TRY(scr.alloc(&sg, 1));
+  const int ncx = (len_x + kSeedCell - 1) / kSeedCell, ncy = (len_y + kSeedCell - 1) / kSeedCell;
+  GI_TRY(scr.alloc(&seed, (size_t)ncx * ncy));
+  GI_TRY(scr.alloc(&counters, 4));
+  GI_CUDA(cudaMemsetAsync(seed, 0x7f, sizeof(int) * (size_t)ncx * ncy, st));
+  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4, st));
+  seed_setup_kernel<R><<<1, 1, 0, st>>>(x_axis, len_x, y_axis, len_y, sg);
+  pack_mesh_kernel<R><<<div_up(num_tri, 256), 256, 0, st>>>(
+      points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR), data_in,
+      topo_t3(simplices, num_tri, flags & GI_TOPO_ROWMAJOR), topo_t3(neighbours, num_tri, flags & GI_TOPO_ROWMAJOR),
+      num_points, num_tri, geom, vals, seed, sg, slot.dev);
+  GI_CUDA(cudaGetLastError());
+
+  // ---- 2. walk + barycentric over the band plus halo rows -------------------------------------
+  ph.mark("walk");
+  const int e0 = max(0, row_begin - halo), e1 = min(len_y, row_end + halo);
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  WalkArgs<R> wa;
+  if (rowmajor) {  // fast axis = x, slow = y
+    wa.win = TargetWindow<R>{x_axis, y_axis, len_x, len_y, 0, len_x, e0, e1, 0};
+    wa.bf0 = 0; wa.bf1 = len_x; wa.bs0 = row_begin; wa.bs1 = row_end;
+  } else {         // column-major field: fast axis = y, slow = x
+    wa.win = TargetWindow<R>{y_axis, x_axis, len_y, len_x, e0, e1, 0, len_x, 1};
+    wa.bf0 = row_begin; wa.bf1 = row_end; wa.bs0 = 0; wa.bs1 = len_x;
+  }
+  const int nf = wa.win.nf(), ns = wa.win.ns(), wpr = (nf + 31) >> 5;
+  uint32_t* mask_words;
+  GI_TRY(scr.alloc(&mask_words, (size_t)wpr * ns));
+  wa.geom = geom; wa.vals = vals; wa.seed = seed; wa.ncx = ncx; wa.ncy = ncy; wa.num_tri = num_tri;
+  wa.iter_cap = num_tri + 16;
+  wa.out = data_ip; wa.tri_out = tri_out; wa.mask_words = mask_words; wa.counters = counters;
+  wa.status = slot.dev;
+  {
+    dim3 grid(div_up(nf, kWalkThreads), div_up(ns, kWalkRows));
+    GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
+    walk_kernel<R><<<grid, kWalkThreads, 0, st>>>(wa);
+    GI_CUDA(cudaGetLastError());
+  }
+  if (mask_out || fill_src) {
+    expand_mask_kernel<<<kNumSMs * 8, 256, 0, st>>>(mask_words, wpr, wa.win.f0, wa.win.s0, wa.bf0, wa.bf1, wa.bs0,
+                                                   wa.bs1, mask_out, fill_src);
+    GI_CUDA(cudaGetLastError());
+  }
+
+  // ---- 3. hull fill ---------------------------------------------------------------------------
+  ph.mark("fill");
+  FillArgs<R> fa;
+  fa.win = wa.win; fa.mask_words = mask_words;
+  fa.bf0 = wa.bf0; fa.bf1 = wa.bf1; fa.bs0 = wa.bs0; fa.bs1 = wa.bs1;
+  fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters; fa.len_x = len_x; fa.len_y = len_y;
+  fa.geom = geom; fa.vals = vals; fa.seed = seed; fa.ncx = ncx; fa.ncy = ncy; fa.num_tri = num_tri;
+  fa.iter_cap = wa.iter_cap; fa.status = slot.dev;
+  fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
+  GI_CUDA(cudaGetLastError());
+  ph.finish();
+
+  if (counters_out)
+    GI_CUDA(cudaMemcpyAsync(counters_out, counters, sizeof(int64_t) * 4, cudaMemcpyDeviceToDevice, st));
+  GI_TRY(flush_status(st, slot));
+  return GI_OK;
+}
+
+template <class R>
+int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* fill_src, int flags,
+                cudaStream_t st) {
+  GI_REQUIRE(len_x >= 1 && len_y >= 1, "empty grid");
+  GI_TRY(ensure_device());
+  StatusSlot slot;
+  GI_TRY(get_status_slot(st, &slot));
+  Scratch scr(st);
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  FillArgs<R> fa;
+  fa.win = rowmajor ? TargetWindow<R>{nullptr, nullptr, len_x, len_y, 0, len_x, 0, len_y, 0}
+                    : TargetWindow<R>{nullptr, nullptr, len_y, len_x, 0, len_y, 0, len_x, 1};
+  const int nf = fa.win.nf(), ns = fa.win.ns(), wpr = (nf + 31) >> 5;
+  uint32_t* words; int64_t* counters;
+  GI_TRY(scr.alloc(&words, (size_t)wpr * ns));
+  GI_TRY(scr.alloc(&counters, 4));
+  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4, st));
+  GI_REQUIRE(ns <= 65535, "grid too large for the standalone fill");
+  bytes_to_bits_kernel<<<dim3(div_up(nf, 128), ns), 128, 0, st>>>(mask, nf, wpr, words);
+  GI_CUDA(cudaGetLastError());
+  if (fill_src) {
+    expand_mask_kernel<<<kNumSMs * 8, 256, 0, st>>>(words, wpr, 0, 0, 0, nf, 0, ns, nullptr, fill_src);
+    GI_CUDA(cudaGetLastError());
+  }
+  fa.mask_words = words; fa.bf0 = 0; fa.bf1 = nf; fa.bs0 = 0; fa.bs1 = ns;
+  fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters; fa.len_x = len_x; fa.len_y = len_y;
+  fa.geom = nullptr; fa.vals = nullptr; fa.seed = nullptr; fa.ncx = fa.ncy = fa.num_tri = fa.iter_cap = 0;
+  fa.status = slot.dev;
+  fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
+  GI_CUDA(cudaGetLastError());
+  GI_TRY(flush_status(st, slot));
+  return GI_OK;
+}
+
+#define GI_INSTANTIATE(R)                                                                                  \
+  template int barycentric_device<R>(const R*, int, const R*, const R*, int, const R*, int, const int32_t*, \
+                                     const int32_t*, int, int, int, int, R*, int32_t*, uint8_t*, int64_t*,  \
+                                     int64_t*, int, cudaStream_t);                                          \
+  template int fill_device<R>(const uint8_t*, int, int, R*, int64_t*, int, cudaStream_t);
+GI_INSTANTIATE(double)
+GI_INSTANTIATE(float)
+
+}  // namespace gi

@@ -1,0 +1,130 @@
+// bilinear.cu -- regular grid -> scattered points (interpolation.f90:20-100).
+//
+// One thread handles kPts points strided by the CTA size, so the coordinate loads and the result store
+// are fully coalesced and the 4 x kPts dependent field gathers of a thread are all in flight together
+// (the kernel is bound by random 32 B-sector gathers from a field far larger than L2).  The field is
+// addressed through (stride_y, stride_x), so the reference's column-major data_in(len_y,len_x) and numpy's
+// row-major layout are read in place.
+//
+// Bit parity: dx_inv / dy_inv are the reference's SERIAL running sums of axis differences
+// (interpolation.f90:49-58) -- floating-point addition is not associative, so the sum is done by a single
+// thread per axis in the reference's order; weights and the final sum follow interpolation.f90:81-93 with
+// FMA contraction disabled.
+#include "kernels.cuh"
+
+namespace gi {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPts = 4;
+
+// interpolation.f90:49-58.  Block 0: x axis, block 1: y axis.  The CTA stages the axis through shared
+// memory in coalesced chunks; thread 0 accumulates in the reference's order.
+template <class R>
+__global__ void __launch_bounds__(256) axis_inv_spacing_kernel(const R* __restrict__ x_axis, int len_x,
+                                                               const R* __restrict__ y_axis, int len_y,
+                                                               R* __restrict__ inv) {
+  __shared__ R buf[2049];
+  const R* axis = blockIdx.x == 0 ? x_axis : y_axis;
+  const int len = blockIdx.x == 0 ? len_x : len_y;
+  R delta = R(0);
+  for (int base = 0; base < len - 1; base += 2048) {
+    const int cnt = min(2048, len - 1 - base);  // differences in this chunk; needs cnt + 1 values
+    __syncthreads();
+    for (int i = threadIdx.x; i <= cnt; i += blockDim.x) buf[i] = axis[base + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll 8
+      for (int i = 0; i < cnt; ++i) delta = delta + (buf[i + 1] - buf[i]);
+    }
+  }
+  if (threadIdx.x == 0) inv[blockIdx.x] = R(1) / (delta / R(len - 1));
+}
+
+template <class R>
+__global__ void __launch_bounds__(kThreads)
+bilinear_kernel(const R* __restrict__ x_axis, int len_x, const R* __restrict__ y_axis, int len_y,
+                const R* __restrict__ data, int64_t sy, int64_t sx, PointsView<R> pts, int64_t n,
+                const R* __restrict__ inv, R* __restrict__ out) {
+  const R dx_inv = __ldg(inv), dy_inv = __ldg(inv + 1);
+  const R x_first = __ldg(x_axis), y_first = __ldg(y_axis);
+  const R scale = dx_inv * dy_inv;                                        // :93
+  const int64_t base = (int64_t)blockIdx.x * (kThreads * kPts) + threadIdx.x;
+  R px[kPts], py[kPts];
+  int ix[kPts], iy[kPts];
+  bool ok[kPts];
+#pragma unroll
+  for (int j = 0; j < kPts; ++j) {
+    const int64_t i = base + (int64_t)j * kThreads;
+    if (i < n) { px[j] = pts.x(i); py[j] = pts.y(i); }
+    else { px[j] = x_first; py[j] = y_first; }
+  }
+#pragma unroll
+  for (int j = 0; j < kPts; ++j) {
+    const R fx = floor((px[j] - x_first) * dx_inv);                       // :67
+    const R fy = floor((py[j] - y_first) * dy_inv);                       // :73
+    // 1 <= ind < len in the reference's 1-based terms (:68,:74); NaN fails every comparison
+    ok[j] = fx >= R(0) && fx < R(len_x - 1) && fy >= R(0) && fy < R(len_y - 1);
+    ix[j] = ok[j] ? (int)fx : 0;
+    iy[j] = ok[j] ? (int)fy : 0;
+  }
+  R d11[kPts], d12[kPts], d21[kPts], d22[kPts], xa[kPts], xb[kPts], ya[kPts], yb[kPts];
+#pragma unroll
+  for (int j = 0; j < kPts; ++j) {
+    const bool two = len_x > 1 && len_y > 1;
+    const R* p = data + (int64_t)iy[j] * sy + (int64_t)ix[j] * sx;
+    d11[j] = __ldg(p);                                                    // data_in(ind_y,   ind_x)
+    d12[j] = two ? __ldg(p + sy) : R(0);                                  // data_in(ind_y+1, ind_x)
+    d21[j] = two ? __ldg(p + sx) : R(0);                                  // data_in(ind_y,   ind_x+1)
+    d22[j] = two ? __ldg(p + sy + sx) : R(0);                             // data_in(ind_y+1, ind_x+1)
+    xa[j] = __ldg(x_axis + ix[j]); xb[j] = two ? __ldg(x_axis + ix[j] + 1) : xa[j];
+    ya[j] = __ldg(y_axis + iy[j]); yb[j] = two ? __ldg(y_axis + iy[j] + 1) : ya[j];
+  }
+#pragma unroll
+  for (int j = 0; j < kPts; ++j) {
+    const int64_t i = base + (int64_t)j * kThreads;
+    if (i >= n) continue;
+    const R w11 = (xb[j] - px[j]) * (yb[j] - py[j]);                      // :81-88
+    const R w12 = (xb[j] - px[j]) * (py[j] - ya[j]);
+    const R w21 = (px[j] - xa[j]) * (yb[j] - py[j]);
+    const R w22 = (px[j] - xa[j]) * (py[j] - ya[j]);
+    const R v = (w11 * d11[j] + w12 * d12[j] + w21 * d21[j] + w22 * d22[j]) * scale;  // :90-93
+    out[i] = ok[j] ? v : Consts<R>::ofb();                                // :44,:69,:75
+  }
+}
+
+}  // namespace
+
+template <class R>
+int bilinear_device(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* data_in, const R* points,
+                    int64_t num_points, R* data_ip, int flags, cudaStream_t st) {
+  GI_REQUIRE(len_x >= 2 && len_y >= 2, "axes need at least 2 nodes");
+  GI_REQUIRE(num_points >= 0, "negative num_points");
+  GI_TRY(ensure_device());
+  if (num_points == 0) return GI_OK;
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("axis_spacing");
+  R* inv;
+  GI_TRY(scr.alloc(&inv, 2));
+  axis_inv_spacing_kernel<R><<<2, 256, 0, st>>>(x_axis, len_x, y_axis, len_y, inv);
+  GI_CUDA(cudaGetLastError());
+  ph.mark("bilinear");
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  const int64_t sy = rowmajor ? len_x : 1, sx = rowmajor ? 1 : len_y;
+  const int64_t blocks = (num_points + kThreads * kPts - 1) / (kThreads * kPts);
+  GI_REQUIRE(blocks <= 0x7fffffffLL, "too many points for one launch");
+  bilinear_kernel<R><<<(unsigned)blocks, kThreads, 0, st>>>(
+      x_axis, len_x, y_axis, len_y, data_in, sy, sx, points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR),
+      num_points, inv, data_ip);
+  GI_CUDA(cudaGetLastError());
+  ph.finish();
+  return GI_OK;
+}
+
+template int bilinear_device<double>(const double*, int, const double*, int, const double*, const double*, int64_t,
+                                     double*, int, cudaStream_t);
+template int bilinear_device<float>(const float*, int, const float*, int, const float*, const float*, int64_t,
+                                    float*, int, cudaStream_t);
+
+}  // namespace gi

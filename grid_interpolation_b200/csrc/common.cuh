@@ -1,0 +1,172 @@
+// common.cuh -- shared plumbing of libgridinterp: status codes, stream-ordered scratch memory,
+// per-stream device status words, phase timers and the stride-generic array views that let every
+// kernel read the reference's Fortran layouts and numpy's C layouts without a transposition pass.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/gridinterp.h"
+
+namespace gi {
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define GI_CUDA(call)                                                    \
+  do {                                                                   \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess) return gi::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+#define GI_TRY(call)                 \
+  do {                               \
+    int s__ = (call);                \
+    if (s__ != GI_OK) return s__;    \
+  } while (0)
+#define GI_REQUIRE(cond, msg)                   \
+  do {                                          \
+    if (!(cond)) {                              \
+      gi::set_error(std::string("bad argument: ") + msg); \
+      return GI_ERR_BAD_ARG;                    \
+    }                                           \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// kind-dependent constants of the reference (default-kind REAL literals)
+// ---------------------------------------------------------------------------------------------
+template <class R> struct Consts;
+template <> struct Consts<double> {
+  __host__ __device__ static double tiny_e4() { return 2.2250738585072014e-308 * 1e4; }  // TINY(1.0)*1e4
+  __host__ __device__ static double huge() { return 1.7976931348623157e308; }            // HUGE(1.0)
+  __host__ __device__ static double sentinel() { return 1.0e6; }                         // interpolation.f90:159
+  __host__ __device__ static double margin() { return -1e-10; }                          // triangle_walk.f90:148
+  __host__ __device__ static double ofb() { return -9999.0; }                            // interpolation.f90:44
+};
+template <> struct Consts<float> {
+  __host__ __device__ static float tiny_e4() { return 1.17549435e-38f * 1e4f; }
+  __host__ __device__ static float huge() { return 3.40282347e38f; }
+  __host__ __device__ static float sentinel() { return 1.0e6f; }
+  __host__ __device__ static float margin() { return -1e-10f; }
+  __host__ __device__ static float ofb() { return -9999.0f; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// stride-generic views
+// ---------------------------------------------------------------------------------------------
+template <class R> struct PointsView {  // x(i) = base[i*stride], y(i) = base[i*stride + yoff]
+  const R* base;
+  int64_t stride, yoff;
+  __device__ __forceinline__ R x(int64_t i) const { return __ldg(base + i * stride); }
+  __device__ __forceinline__ R y(int64_t i) const { return __ldg(base + i * stride + yoff); }
+};
+// (n,2) array: Fortran order = SoA, C order = interleaved
+template <class R> inline PointsView<R> points_n2(const R* p, int64_t n, bool rowmajor) {
+  return rowmajor ? PointsView<R>{p, 2, 1} : PointsView<R>{p, 1, n};
+}
+// (2,n) array (idw_kdtree): Fortran order = interleaved, C order = SoA
+template <class R> inline PointsView<R> points_2n(const R* p, int64_t n, bool rowmajor) {
+  return rowmajor ? PointsView<R>{p, 1, n} : PointsView<R>{p, 2, 1};
+}
+struct TopoView {  // a(t,c) = base[t*st + c*sc], t 0-based triangle, c in 0..2
+  const int32_t* base;
+  int64_t st, sc;
+  __device__ __forceinline__ int operator()(int64_t t, int c) const { return __ldg(base + t * st + c * sc); }
+};
+inline TopoView topo_t3(const int32_t* p, int64_t t, bool rowmajor) {
+  return rowmajor ? TopoView{p, 3, 1} : TopoView{p, 1, t};
+}
+
+// A rectangular window of grid targets addressed by (fast, slow) indices: `fast` runs along the axis
+// that is contiguous in the output field.  Row-major field: fast = x; column-major: fast = y.
+template <class R> struct TargetWindow {
+  const R* fast_axis;  // device pointer, full axis
+  const R* slow_axis;
+  int nf_full, ns_full;  // full grid extents along fast / slow
+  int f0, f1, s0, s1;    // window [f0,f1) x [s0,s1)
+  int fast_is_y;         // 1: fast axis = y (column-major field), 0: fast axis = x
+  __host__ __device__ int nf() const { return f1 - f0; }
+  __host__ __device__ int ns() const { return s1 - s0; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// stream-ordered scratch memory (cudaMallocAsync pool, cached between calls)
+// ---------------------------------------------------------------------------------------------
+int ensure_device();  // validates that a CUDA device exists; configures the mem pool once per device
+
+class Scratch {
+ public:
+  explicit Scratch(cudaStream_t s) : stream_(s) {}
+  ~Scratch() { release(); }
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  template <class T> int alloc(T** out, size_t count) {
+    void* p = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(&p, bytes, stream_);
+    if (e != cudaSuccess) {
+      *out = nullptr;
+      if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        set_error("out of device memory allocating " + std::to_string(bytes) + " bytes");
+        return GI_ERR_OOM;
+      }
+      return cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+    }
+    ptrs_.push_back(p);
+    *out = static_cast<T*>(p);
+    return GI_OK;
+  }
+  void release() {
+    for (void* p : ptrs_) cudaFreeAsync(p, stream_);
+    ptrs_.clear();
+  }
+  cudaStream_t stream() const { return stream_; }
+
+ private:
+  cudaStream_t stream_;
+  std::vector<void*> ptrs_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-stream status word: kernels raise it with atomicMax, flush_status() forwards it to a pinned
+// host slot at the end of every call; gi_stream_status() synchronises and reads the slot.
+// ---------------------------------------------------------------------------------------------
+struct StatusSlot {
+  int* dev;        // device word
+  int* host;       // pinned, mapped
+  int* host_dev;   // device alias of host
+};
+int get_status_slot(cudaStream_t s, StatusSlot* out);
+int flush_status(cudaStream_t s, const StatusSlot& slot);
+int read_status(cudaStream_t s, bool synchronize);
+
+__device__ __forceinline__ void raise_status(int* status, int code) { atomicMax(status, code); }
+
+// ---------------------------------------------------------------------------------------------
+// phase timers (CUDA events on the launching stream)
+// ---------------------------------------------------------------------------------------------
+class Phases {
+ public:
+  explicit Phases(cudaStream_t s);
+  ~Phases() { finish(); }
+  void mark(const char* name);  // closes the previous phase, opens `name`
+  void finish();                // closes the last phase; results are resolved lazily
+ private:
+  cudaStream_t stream_;
+  bool on_;
+};
+void set_profiling(bool on);
+bool profiling();
+
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace gi

@@ -1,0 +1,403 @@
+// kdtree.cu -- IDW from scattered points to a regular grid with the k-d tree k-nearest-neighbour search.
+//
+// Replaces (reference file:line):
+//   interpolation.f90:107-194   idw_kdtree (operator + IDW weights)
+//   kd_tree.f90:30-155          build_kd_tree / build_kd_tree_sub / partition_iter
+//   kd_tree.f90:161-251         nearest_neighbours / insert_neighbour / distance_squared
+//
+// B200 design (not a port):
+//   build   The reference's tree is canonical for distinct coordinates (node = element of rank (n+1)/2
+//           along axis depth mod 2, kd_tree.f90:45,54-68), so it is built here without any
+//           recursion or pointers: both coordinate orders are sorted once (hand-written bitonic network,
+//           shared-memory stages for spans <= 2048) and the tree is then produced level by level -- in
+//           every segment the axis-sorted list already has the median in place, and the other list is
+//           stably partitioned around it with one device-wide prefix sum per level.  The result is an
+//           IMPLICIT tree: the node of segment [lo,hi) is element lo+(hi-lo+1)/2-1 of one array, its
+//           subtrees are the two sub-segments.  Coordinate ties are ordered by point id (the reference's
+//           quickselect order for ties depends on its swap history -- documented divergence).
+//   query   one thread per grid target, explicit stack of deferred far branches (depth <= 32),
+//           register-resident sorted top-k (topk.cuh).  The far branch is taken iff
+//           abs(diff) < max d2 -- the reference's rule, which compares a distance with a squared distance
+//           (kd_tree.f90:191,198) and must be reproduced for index parity -- AND diff*diff < max d2.  The
+//           second condition only skips subtrees in which every point has d2 >= diff*diff >= max d2, i.e.
+//           none could be inserted (insertion needs d2 < max d2, which only shrinks), so the neighbour
+//           list after the skipped visit is bit-identical to the reference's; it cuts node visits ~14x when
+//           the k-th d2 is > 1.  GI_KD_REFERENCE_VISITS turns it off (visit-count parity with the oracle).
+#include "kernels.cuh"
+#include "scan.cuh"
+#include "topk.cuh"
+
+namespace gi {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// bitonic sort of (key, id) pairs, ascending, n2 = power of two
+// ---------------------------------------------------------------------------------------------
+struct KeyId {
+  unsigned long long key;
+  int id;
+};
+__device__ __forceinline__ bool key_less(const KeyId& a, const KeyId& b) {
+  return a.key < b.key || (a.key == b.key && a.id < b.id);
+}
+__device__ __forceinline__ unsigned long long order_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+constexpr int kSortTile = 2048;
+
+__device__ __forceinline__ void cmp_swap(KeyId& a, KeyId& b, bool ascending) {
+  if (key_less(b, a) == ascending) { const KeyId t = a; a = b; b = t; }
+}
+
+// all stages with span <= kSortTile for the sub-sequences k_begin..k_end (k = size of the bitonic runs)
+__global__ void __launch_bounds__(kSortTile / 2)
+bitonic_shared_kernel(unsigned long long* __restrict__ keys, int* __restrict__ ids, int k_begin, int k_end) {
+  __shared__ unsigned long long sk[kSortTile];
+  __shared__ int si[kSortTile];
+  const int base = blockIdx.x * kSortTile;
+  for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) { sk[i] = keys[base + i]; si[i] = ids[base + i]; }
+  __syncthreads();
+  for (int k = k_begin; k <= k_end; k <<= 1) {
+    for (int j = min(k >> 1, kSortTile >> 1); j > 0; j >>= 1) {
+      const int t = threadIdx.x;
+      const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
+      const int p = i | j;
+      const bool asc = (((base + i) & k) == 0);
+      KeyId a{sk[i], si[i]}, b{sk[p], si[p]};
+      cmp_swap(a, b, asc);
+      sk[i] = a.key; si[i] = a.id; sk[p] = b.key; si[p] = b.id;
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) { keys[base + i] = sk[i]; ids[base + i] = si[i]; }
+}
+
+__global__ void __launch_bounds__(256)
+bitonic_global_kernel(unsigned long long* __restrict__ keys, int* __restrict__ ids, int n2, int k, int j) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (n2 >> 1)) return;
+  const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+  const int p = i | j;
+  const bool asc = ((i & k) == 0);
+  KeyId a{keys[i], ids[i]}, b{keys[p], ids[p]};
+  if (key_less(b, a) == asc) { keys[i] = b.key; ids[i] = b.id; keys[p] = a.key; ids[p] = a.id; }
+}
+
+template <class R>
+__global__ void __launch_bounds__(256)
+sort_keys_kernel(PointsView<R> pts, int n, int n2, int axis, unsigned long long* __restrict__ keys,
+                 int* __restrict__ ids) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  if (i < n) {
+    keys[i] = order_key((double)(axis == 0 ? pts.x(i) : pts.y(i)));
+    ids[i] = i;
+  } else {  // padding sorts last
+    keys[i] = ~0ull;
+    ids[i] = 0x7fffffff;
+  }
+}
+
+int bitonic_sort(unsigned long long* keys, int* ids, int n2, cudaStream_t st) {
+  if (n2 <= kSortTile) {
+    // a single tile: pad handled by caller (n2 >= kSortTile always, see below)
+  }
+  const int tiles = n2 / kSortTile;
+  bitonic_shared_kernel<<<tiles, kSortTile / 2, 0, st>>>(keys, ids, 2, kSortTile);
+  for (int k = kSortTile << 1; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j >= kSortTile; j >>= 1)
+      bitonic_global_kernel<<<div_up(n2 >> 1, 256), 256, 0, st>>>(keys, ids, n2, k, j);
+    bitonic_shared_kernel<<<tiles, kSortTile / 2, 0, st>>>(keys, ids, k, k);
+  }
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// level-synchronous canonical build
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+kd_init_kernel(const int* __restrict__ list_x, const int* __restrict__ list_y, int n, int* __restrict__ pos_x,
+               int* __restrict__ pos_y, int* __restrict__ seg_lo, int* __restrict__ seg_hi) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  pos_x[list_x[p]] = p;
+  pos_y[list_y[p]] = p;
+  seg_lo[p] = 0;
+  seg_hi[p] = n;
+}
+
+// flag[p] = 1 iff the point at position p of the OTHER list belongs to the left part of its segment
+__global__ void __launch_bounds__(256)
+kd_flag_kernel(const int* __restrict__ other, const int* __restrict__ pos_split, const int* __restrict__ seg_lo,
+               const int* __restrict__ seg_hi, int n, int* __restrict__ flag) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int lo = seg_lo[p];
+  int f = 0;
+  if (lo >= 0) {
+    const int hi = seg_hi[p];
+    const int m = lo + ((hi - lo + 1) >> 1) - 1;  // ind_median = (num_points + 1) / 2   (kd_tree.f90:54)
+    f = pos_split[other[p]] < m ? 1 : 0;
+  }
+  flag[p] = f;
+}
+
+__global__ void __launch_bounds__(256)
+kd_partition_kernel(const int* __restrict__ split, const int* __restrict__ other, const int* __restrict__ pos_split,
+                    const int* __restrict__ pos_other, const int* __restrict__ seg_lo,
+                    const int* __restrict__ seg_hi, const int* __restrict__ scan, int n,
+                    int* __restrict__ other_new, int* __restrict__ pos_other_new, int* __restrict__ seg_lo_new,
+                    int* __restrict__ seg_hi_new) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int lo = seg_lo[p];
+  const int pt = other[p];
+  if (lo < 0) {  // position already holds a finished node
+    other_new[p] = pt;
+    pos_other_new[pt] = p;
+    seg_lo_new[p] = -1;
+    seg_hi_new[p] = -1;
+    return;
+  }
+  const int hi = seg_hi[p];
+  const int m = lo + ((hi - lo + 1) >> 1) - 1;
+  const int ps = pos_split[pt];
+  const int left_before = scan[p] - scan[lo];
+  int newp;
+  if (ps < m) newp = lo + left_before;                       // left subtree keeps its relative order
+  else if (ps == m) newp = m;                                // the node
+  else {
+    const int node_pos = pos_other[split[m]];
+    newp = m + 1 + ((p - lo) - left_before - (node_pos < p ? 1 : 0));
+  }
+  other_new[newp] = pt;
+  pos_other_new[pt] = newp;
+  // the segment bookkeeping is per POSITION
+  if (p < m) { seg_lo_new[p] = lo; seg_hi_new[p] = m; }
+  else if (p == m) { seg_lo_new[p] = -1; seg_hi_new[p] = -1; }
+  else { seg_lo_new[p] = m + 1; seg_hi_new[p] = hi; }
+}
+
+template <class R> struct alignas(16) XY { R x, y; };
+
+template <class R>
+__global__ void __launch_bounds__(256)
+kd_gather_kernel(PointsView<R> pts, const R* __restrict__ data, const int* __restrict__ order, int n,
+                 XY<R>* __restrict__ nodes, R* __restrict__ nval, int* __restrict__ order_out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int i = order[p];
+  if (nodes) { XY<R> v; v.x = pts.x(i); v.y = pts.y(i); nodes[p] = v; }
+  if (nval) nval[p] = __ldg(data + i);
+  if (order_out) order_out[p] = i + 1;
+}
+
+// builds the implicit tree; *order_dev (n ints, 0-based point ids in tree order) lives in scr
+template <class R>
+int kd_build(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
+  cudaStream_t st = scr.stream();
+  int n2 = kSortTile;
+  while (n2 < n) n2 <<= 1;
+  unsigned long long* keys;
+  int *list[2], *pos[2], *list_new, *pos_new, *seg_lo, *seg_hi, *seg_lo_new, *seg_hi_new, *flag;
+  GI_TRY(scr.alloc(&keys, (size_t)n2));
+  GI_TRY(scr.alloc(&list[0], (size_t)n2));
+  GI_TRY(scr.alloc(&list[1], (size_t)n2));
+  GI_TRY(scr.alloc(&pos[0], (size_t)n));
+  GI_TRY(scr.alloc(&pos[1], (size_t)n));
+  GI_TRY(scr.alloc(&list_new, (size_t)n));
+  GI_TRY(scr.alloc(&pos_new, (size_t)n));
+  GI_TRY(scr.alloc(&seg_lo, (size_t)n));
+  GI_TRY(scr.alloc(&seg_hi, (size_t)n));
+  GI_TRY(scr.alloc(&seg_lo_new, (size_t)n));
+  GI_TRY(scr.alloc(&seg_hi_new, (size_t)n));
+  GI_TRY(scr.alloc(&flag, (size_t)n));
+  for (int axis = 0; axis < 2; ++axis) {
+    sort_keys_kernel<R><<<div_up(n2, 256), 256, 0, st>>>(pv, n, n2, axis, keys, list[axis]);
+    GI_TRY(bitonic_sort(keys, list[axis], n2, st));
+  }
+  const int blocks = div_up(n, 256);
+  kd_init_kernel<<<blocks, 256, 0, st>>>(list[0], list[1], n, pos[0], pos[1], seg_lo, seg_hi);
+  int levels = 0;
+  while ((1ll << levels) <= (long long)n) ++levels;  // floor(log2 n) + 1
+  for (int d = 0; d < levels; ++d) {
+    const int ax = d & 1, ot = ax ^ 1;  // axis = mod(depth, 2)   (kd_tree.f90:45)
+    kd_flag_kernel<<<blocks, 256, 0, st>>>(list[ot], pos[ax], seg_lo, seg_hi, n, flag);
+    GI_TRY(exclusive_scan_i32(scr, flag, flag, n));
+    kd_partition_kernel<<<blocks, 256, 0, st>>>(list[ax], list[ot], pos[ax], pos[ot], seg_lo, seg_hi, flag, n,
+                                                list_new, pos_new, seg_lo_new, seg_hi_new);
+    std::swap(list[ot], list_new);
+    std::swap(pos[ot], pos_new);
+    std::swap(seg_lo, seg_lo_new);
+    std::swap(seg_hi, seg_hi_new);
+  }
+  GI_CUDA(cudaGetLastError());
+  *order_dev = list[0];  // both lists are identical once every position is a node
+  return GI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// query + IDW
+// ---------------------------------------------------------------------------------------------
+template <class R> struct KdArgs {
+  TargetWindow<R> win;
+  const XY<R>* nodes;  // coordinates in implicit-tree order
+  const R* nval;       // values in tree order
+  const int* order;    // 0-based point id per tree position
+  int n, k;
+  R* out;
+  int32_t* nn_index;   // optional (window, k), 1-based ids, 0 = slot never filled
+  R* nn_dist2;         // optional
+  int64_t* counters;   // [0] node visits
+  int* status;
+};
+
+template <class R, int KC, bool REFVISITS>
+__global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
+  const TargetWindow<R>& w = a.win;
+  const int f = w.f0 + blockIdx.x * 32 + (threadIdx.x & 31);
+  const int s = w.s0 + blockIdx.y * 4 + (threadIdx.x >> 5);
+  const bool active = f < w.f1 && s < w.s1;
+  long long visits = 0;
+  if (active) {
+    const int ix = w.fast_is_y ? s : f, iy = w.fast_is_y ? f : s;
+    const R tx = __ldg((w.fast_is_y ? w.slow_axis : w.fast_axis) + ix);   // interpolation.f90:158
+    const R ty = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
+    TopK<R, KC> tk;
+    tk.init(a.k, Consts<R>::sentinel(), -1);                              // :159
+    int st_lo[32], st_hi[32], st_depth[32];
+    R st_diff[32];
+    int sp = 0;
+    int lo = 0, hi = a.n, depth = 0;
+    for (;;) {
+      while (lo < hi) {                                                   // kd_tree.f90:174
+        const int m = lo + ((hi - lo + 1) >> 1) - 1;
+        const XY<R> nd = a.nodes[m];
+        const R ddx = nd.x - tx, ddy = nd.y - ty;
+        const R d2 = ddx * ddx + ddy * ddy;                               // :177,:249
+        if (d2 < tk.dlast) tk.template insert<false>(d2, m);              // :222-236
+        ++visits;
+        const R diff = (depth & 1) ? ty - nd.y : tx - nd.x;               // :183-184
+        int flo, fhi;
+        if (diff < R(0)) { flo = m + 1; fhi = hi; hi = m; }               // :188 near = left
+        else { flo = lo; fhi = m; lo = m + 1; }                           // :195 near = right
+        ++depth;
+        if (flo < fhi && sp < 32) {
+          st_lo[sp] = flo; st_hi[sp] = fhi; st_depth[sp] = depth; st_diff[sp] = fabs(diff);
+          ++sp;
+        }
+      }
+      bool got = false;
+      while (sp > 0) {
+        --sp;
+        const R ad = st_diff[sp];
+        // :191,:198 the reference's rule; second term: provably state-preserving skip (see file header)
+        if (ad < tk.dlast && (REFVISITS || ad * ad < tk.dlast)) {
+          lo = st_lo[sp]; hi = st_hi[sp]; depth = st_depth[sp];
+          got = true;
+          break;
+        }
+      }
+      if (!got) break;
+    }
+    // IDW (interpolation.f90:164-178)
+    const int64_t o = (int64_t)(s - w.s0) * w.nf() + (f - w.f0);
+    R numerator = R(0), denominator = R(0), first_val = R(0), first_d2 = R(0);
+#pragma unroll
+    for (int i = 0; i < KC; ++i) {
+      if (i < a.k) {
+        const int pos = tk.id[i];
+        const R dist = sqrt(tk.d[i]);
+        const R v = pos >= 0 ? __ldg(a.nval + pos) : R(0);  // unfilled slot: uninitialised read in the reference
+        if (i == 0) { first_val = v; first_d2 = tk.d[i]; }
+        numerator = numerator + (v / dist);
+        denominator = denominator + (R(1) / dist);
+        if (a.nn_index) a.nn_index[o * a.k + i] = pos >= 0 ? __ldg(a.order + pos) + 1 : 0;
+        if (a.nn_dist2) a.nn_dist2[o * a.k + i] = tk.d[i];
+      }
+    }
+    a.out[o] = (sqrt(first_d2) <= Consts<R>::tiny_e4()) ? first_val : numerator / denominator;
+  }
+  if (a.counters) {
+    for (int off = 16; off > 0; off >>= 1) visits += __shfl_down_sync(0xffffffffu, visits, off);
+    if ((threadIdx.x & 31) == 0 && visits) atomicAdd((unsigned long long*)a.counters, (unsigned long long)visits);
+  }
+}
+
+template <class R, int KC>
+void launch_query(const KdArgs<R>& a, bool refvisits, dim3 grid, cudaStream_t st) {
+  if (refvisits) kd_query_kernel<R, KC, true><<<grid, 128, 0, st>>>(a);
+  else kd_query_kernel<R, KC, false><<<grid, 128, 0, st>>>(a);
+}
+
+}  // namespace
+
+template <class R>
+int kdtree_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                  const R* y_axis, int len_y, int k, int row_begin, int row_end, R* data_ip,
+                  int32_t* nn_index, R* nn_dist2, int64_t* counters_out, int flags, cudaStream_t st) {
+  GI_REQUIRE(k >= 1 && k <= 32, "num_neighbours must be in 1..32");
+  GI_TRY(ensure_device());
+  if (row_begin == row_end) return GI_OK;
+  StatusSlot slot;
+  GI_TRY(get_status_slot(st, &slot));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("kd_build");
+  const PointsView<R> pv = points_2n(points, num_points, flags & GI_POINTS_ROWMAJOR);
+  int* order;
+  GI_TRY(kd_build<R>(scr, pv, num_points, &order));
+  XY<R>* nodes; R* nval; int64_t* counters;
+  GI_TRY(scr.alloc(&nodes, (size_t)num_points));
+  GI_TRY(scr.alloc(&nval, (size_t)num_points));
+  GI_TRY(scr.alloc(&counters, 4));
+  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4, st));
+  kd_gather_kernel<R><<<div_up(num_points, 256), 256, 0, st>>>(pv, data_in, order, num_points, nodes, nval, nullptr);
+  GI_CUDA(cudaGetLastError());
+  ph.mark("kd_query");
+  KdArgs<R> a;
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  a.win = rowmajor ? TargetWindow<R>{x_axis, y_axis, len_x, len_y, 0, len_x, row_begin, row_end, 0}
+                   : TargetWindow<R>{y_axis, x_axis, len_y, len_x, row_begin, row_end, 0, len_x, 1};
+  a.nodes = nodes; a.nval = nval; a.order = order; a.n = num_points; a.k = k;
+  a.out = data_ip; a.nn_index = nn_index; a.nn_dist2 = nn_dist2;
+  a.counters = counters_out ? counters : nullptr; a.status = slot.dev;
+  dim3 grid(div_up(a.win.nf(), 32), div_up(a.win.ns(), 4));
+  GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
+  const bool refvisits = flags & GI_KD_REFERENCE_VISITS;
+  if (k <= 4) launch_query<R, 4>(a, refvisits, grid, st);
+  else if (k <= 8) launch_query<R, 8>(a, refvisits, grid, st);
+  else if (k <= 16) launch_query<R, 16>(a, refvisits, grid, st);
+  else launch_query<R, 32>(a, refvisits, grid, st);
+  GI_CUDA(cudaGetLastError());
+  ph.finish();
+  if (counters_out)
+    GI_CUDA(cudaMemcpyAsync(counters_out, counters, sizeof(int64_t) * 4, cudaMemcpyDeviceToDevice, st));
+  GI_TRY(flush_status(st, slot));
+  return GI_OK;
+}
+
+template <class R>
+int kd_build_device(const R* points, int num_points, int32_t* order_out, int flags, cudaStream_t st) {
+  GI_TRY(ensure_device());
+  Scratch scr(st);
+  const PointsView<R> pv = points_2n(points, num_points, flags & GI_POINTS_ROWMAJOR);
+  int* order;
+  GI_TRY(kd_build<R>(scr, pv, num_points, &order));
+  kd_gather_kernel<R><<<div_up(num_points, 256), 256, 0, st>>>(pv, nullptr, order, num_points, nullptr, nullptr,
+                                                               order_out);
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+
+#define GI_INSTANTIATE(R)                                                                                       \
+  template int kdtree_device<R>(const R*, int, const R*, const R*, int, const R*, int, int, int, int, R*, int32_t*, \
+                                R*, int64_t*, int, cudaStream_t);                                               \
+  template int kd_build_device<R>(const R*, int, int32_t*, int, cudaStream_t);
+GI_INSTANTIATE(double)
+GI_INSTANTIATE(float)
+
+}  // namespace gi

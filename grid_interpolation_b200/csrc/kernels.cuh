@@ -1,0 +1,41 @@
+// kernels.cuh -- device-level entry points (device pointers in, work enqueued on a stream).
+// api.cu wraps these into the C ABI of include/gridinterp.h (host / device memory variants).
+#pragma once
+#include "common.cuh"
+
+namespace gi {
+
+// bilinear.cu -- interpolation.f90:20-100
+template <class R>
+int bilinear_device(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* data_in, const R* points,
+                    int64_t num_points, R* data_ip, int flags, cudaStream_t st);
+
+// barycentric.cu -- interpolation.f90:298-416 + triangle_walk.f90
+// counters (device, optional): int64[4] = walk iterations, masked cells, max fill level, fix-ups
+template <class R>
+int barycentric_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                       const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
+                       int num_tri, int row_begin, int row_end, int halo, R* data_ip, int32_t* tri_out,
+                       uint8_t* mask_out, int64_t* fill_src, int64_t* counters, int flags, cudaStream_t st);
+template <class R>
+int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* fill_src, int flags,
+                cudaStream_t st);
+
+// esrg.cu -- interpolation.f90:201-288 + query_esrg.f90
+template <class R>
+int esrg_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+                int len_y, R grid_spac, int k, int row_begin, int row_end, R* data_ip, int32_t* nn_index,
+                R* nn_dist2, int64_t* counters, int flags, cudaStream_t st);
+template <class R>
+int esrg_bin_device(const R* points, int num_points, const R* x_axis, int len_x, const R* y_axis, int len_y,
+                    R grid_spac, int32_t* index_of_pts, int32_t* indptr, int flags, cudaStream_t st);
+
+// kdtree.cu -- interpolation.f90:107-194 + kd_tree.f90
+template <class R>
+int kdtree_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                  const R* y_axis, int len_y, int k, int row_begin, int row_end, R* data_ip,
+                  int32_t* nn_index, R* nn_dist2, int64_t* counters, int flags, cudaStream_t st);
+template <class R>
+int kd_build_device(const R* points, int num_points, int32_t* order, int flags, cudaStream_t st);
+
+}  // namespace gi

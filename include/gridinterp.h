@@ -1,0 +1,187 @@
+/* gridinterp.h -- C ABI of libgridinterp.so (CUDA, sm_100a)
+ *
+ * Drop-in boundary for the hot path of ChristianSteger/grid_interpolation: point
+ * location + interpolation for every target point.  Each entry point below
+ * replaces one Fortran module procedure that the reference's f2py binding calls;
+ * the reference interface is cited as file:line (paths relative to the reference
+ * checkout).  Argument meaning follows the Fortran dummies; the dimensions f2py
+ * hides (intent(hide)) are explicit here.  No CUDA / torch types appear in any
+ * signature: plain pointers, sizes, ints.
+ *
+ * Memory space (`mem`)
+ *   GI_HOST    every pointer is host memory; the call copies in, computes on the
+ *              current CUDA device, copies out and returns when the result is in
+ *              the caller's buffer (pinned buffers -- gi_host_alloc -- make the
+ *              copies run at full PCIe speed).  `stream` is ignored.
+ *   GI_DEVICE  every pointer is device memory of the current device (e.g. the
+ *              data_ptr() of a torch CUDA tensor); the work is enqueued on
+ *              `stream` (a cudaStream_t passed as void*, NULL = default stream)
+ *              and the call returns without waiting.  Errors detected on the
+ *              device (iteration caps, invalid ids) are collected per stream:
+ *              gi_stream_status() synchronises and returns them.
+ *
+ * Layouts (`flags`)
+ *   0 means "exactly the reference's memory layout": every 2-D array is Fortran
+ *   column-major as the f2py wrapper hands it to the Fortran --
+ *       points(num_points,2) = x[0..n) then y[0..n)      (bilinear, esrg, barycentric)
+ *       points(2,num_points) = x0,y0,x1,y1,...           (idw_kdtree, interpolation.f90:111)
+ *       simplices/neighbours(num_triangles,3) = 3 columns of num_triangles
+ *       data_in/data_ip(len_y,len_x): element (iy,ix) at iy + ix*len_y
+ *   The GI_*_ROWMAJOR bits select the C-order (numpy default) alternative for one
+ *   group of arguments so that no host-side transposition is ever needed.  All
+ *   kernels are stride-generic: both layouts run at the same speed.
+ *
+ * Index conventions are the reference's: simplices / neighbours are 1-based,
+ * neighbour 0 = no neighbour (interpolation.f90:338, test_interpolation.py:199-201).
+ * Debug outputs return 1-based ids as the Fortran variables hold them; 0 = none.
+ *
+ * Every function returns a gi_status; gi_last_error() gives the message of the
+ * last failure on the calling thread.
+ */
+#ifndef GRIDINTERP_H
+#define GRIDINTERP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GI_VERSION 100
+
+typedef enum {
+  GI_OK = 0,
+  GI_ERR_BAD_ARG = 1,        /* shape / pointer / flag error (f2py raises ValueError before the call) */
+  GI_ERR_NO_DEVICE = 2,      /* no usable CUDA device: there is NO CPU fallback */
+  GI_ERR_OOM = 3,
+  GI_ERR_CUDA = 4,           /* CUDA runtime error, see gi_last_error() */
+  GI_ERR_ITER_CAP = 5,       /* walk / ring search exceeded its cap (reference: infinite loop) */
+  GI_ERR_TOO_FEW_POINTS = 6, /* fewer than num_neighbours points (reference: infinite loop, query_esrg.f90:178) */
+  GI_ERR_BAD_INDEX = 7,      /* simplices / neighbours id out of range (reference: out-of-bounds read) */
+  GI_ERR_HALO = 8            /* row-band call: hull fill needs rows beyond the supplied halo */
+} gi_status;
+
+#define GI_HOST 0
+#define GI_DEVICE 1
+
+#define GI_POINTS_ROWMAJOR 1 /* points array is C-order instead of Fortran order */
+#define GI_TOPO_ROWMAJOR 2   /* simplices / neighbours are C-order (num_triangles,3) */
+#define GI_FIELD_ROWMAJOR 4  /* data_in (bilinear) / data_ip (grid outputs): element (iy,ix) at iy*len_x + ix */
+#define GI_KD_REFERENCE_VISITS 8 /* idw_kdtree: visit exactly the nodes the reference visits (debug: makes the
+                                    visit counter comparable).  Default: additionally skip far subtrees with
+                                    diff*diff >= max d2, which provably cannot change the neighbour list. */
+
+/* ---- library / device management ------------------------------------------------------------ */
+int gi_version(void);
+const char* gi_last_error(void);
+int gi_device_count(void);
+int gi_set_device(int device);
+/* Pinned host memory for GI_HOST calls (page-locked: H2D / D2H at full PCIe rate). */
+void* gi_host_alloc(uint64_t bytes);
+void gi_host_free(void* p);
+/* cudaStreamSynchronize(stream) + the first device-side error recorded on it since the last call. */
+int gi_stream_status(void* stream);
+/* Phase profiling: when on, every call records CUDA events around its phases (H2D, pack, walk, fill, ...)
+ * on the stream it runs on.  gi_last_timings() synchronises on the last event of the last call made by
+ * this thread and returns the number of phases; ms[i] is the device time of phase i and
+ * gi_last_timing_name(i) its name. */
+void gi_set_profiling(int on);
+int gi_last_timings(double* ms, int capacity);
+const char* gi_last_timing_name(int i);
+/* Return cached scratch memory of the current device to the driver. */
+void gi_release_workspace(void);
+
+/* ---- the four drop-in entry points ---------------------------------------------------------- */
+
+/* interpolation.f90:20-100  SUBROUTINE bilinear(x_axis, len_x, y_axis, len_y, data_in, points,
+ * num_points, data_ip): regular grid -> scattered points.  Out-of-grid points get -9999.0
+ * (interpolation.f90:44,68-78; the reference then reads out of bounds, here the point is skipped). */
+int gi_bilinear_f64(const double* x_axis, int len_x, const double* y_axis, int len_y,
+                    const double* data_in, const double* points, int64_t num_points, double* data_ip,
+                    int flags, int mem, void* stream);
+int gi_bilinear_f32(const float* x_axis, int len_x, const float* y_axis, int len_y, const float* data_in,
+                    const float* points, int64_t num_points, float* data_ip, int flags, int mem,
+                    void* stream);
+
+/* interpolation.f90:107-194  SUBROUTINE idw_kdtree(points, num_points, data_in, x_axis, len_x, y_axis,
+ * len_y, num_neighbours, data_ip) with kd_tree.f90:30-240 (build + kNN query, including the reference's
+ * prune rule |diff| < max d2, kd_tree.f90:191,198, and the 1.0e6 sentinel, interpolation.f90:159). */
+int gi_idw_kdtree_f64(const double* points, int num_points, const double* data_in, const double* x_axis,
+                      int len_x, const double* y_axis, int len_y, int num_neighbours, double* data_ip,
+                      int flags, int mem, void* stream);
+
+/* interpolation.f90:201-288  SUBROUTINE idw_esrg_nearest(points, num_points, data_in, x_axis, len_x,
+ * y_axis, len_y, grid_spac, num_neighbours, data_ip) with query_esrg.f90:23-249 (cell binning + ring
+ * search; no fixed 1000-entry candidate buffers). */
+int gi_idw_esrg_nearest_f64(const double* points, int num_points, const double* data_in,
+                            const double* x_axis, int len_x, const double* y_axis, int len_y,
+                            double grid_spac, int num_neighbours, double* data_ip, int flags, int mem,
+                            void* stream);
+
+/* interpolation.f90:298-416  SUBROUTINE barycentric_interpolation(points, num_points, data_in, x_axis,
+ * len_x, y_axis, len_y, simplices, neighbours, num_triangles, data_ip) with triangle_walk.f90:24-153
+ * (visibility walk, orientation predicate with the -1e-10 margin, nearest-inside-cell hull fill). */
+int gi_barycentric_interpolation_f64(const double* points, int num_points, const double* data_in,
+                                     const double* x_axis, int len_x, const double* y_axis, int len_y,
+                                     const int32_t* simplices, const int32_t* neighbours,
+                                     int num_triangles, double* data_ip, int flags, int mem, void* stream);
+
+/* ---- extended forms: row bands (multi-GPU sharding) + the indices the reference keeps internal -- */
+
+/* Rows [row_begin, row_end) of the (len_y, len_x) output only; data_ip then holds just that band,
+ * shape (row_end-row_begin, len_x) in the layout `flags` selects.  Optional outputs (NULL to skip), same
+ * band shape and layout as data_ip unless stated:
+ *   tri_out   triangle the walk ended in (find_triangle's ind_tri, triangle_walk.f90:32), 1-based
+ *   mask_out  1 where the target is outside the convex hull (mask_outside, interpolation.f90:334,400)
+ *   fill_src  for masked cells the 0-based row-major id iy*len_x+ix of the source cell chosen by
+ *             fill_nearest_neighbour (triangle_walk.f90:115-123); -1 elsewhere
+ *   counters  int64[4]: walk iterations total (iters_tot, interpolation.f90:374), masked cells,
+ *             max fill level, targets resolved by the ambiguity fix-up pass
+ * `halo` = extra rows walked on each side of the band so that the hull fill sees neighbouring bands'
+ * cells; GI_ERR_HALO if a fill needed more. */
+int gi_barycentric_interpolation_ex_f64(const double* points, int num_points, const double* data_in,
+                                        const double* x_axis, int len_x, const double* y_axis, int len_y,
+                                        const int32_t* simplices, const int32_t* neighbours,
+                                        int num_triangles, int row_begin, int row_end, int halo,
+                                        double* data_ip, int32_t* tri_out, uint8_t* mask_out,
+                                        int64_t* fill_src, int64_t* counters, int flags, int mem,
+                                        void* stream);
+
+/* nn_index (band rows, len_x, k): 1-based ids in ascending-distance order as neighbours_index /
+ * index_nn hold them (kd_tree.f90:236, query_esrg.f90:168), k fastest; nn_dist2 squared distances
+ * (kd: neighbours(3,:), esrg: dist_sq_nn).  counters int64[4]: node visits (kd) or cells scanned (esrg),
+ * max ring level, overflow re-scans, unused. */
+int gi_idw_kdtree_ex_f64(const double* points, int num_points, const double* data_in,
+                         const double* x_axis, int len_x, const double* y_axis, int len_y,
+                         int num_neighbours, int row_begin, int row_end, double* data_ip,
+                         int32_t* nn_index, double* nn_dist2, int64_t* counters, int flags, int mem,
+                         void* stream);
+int gi_idw_esrg_nearest_ex_f64(const double* points, int num_points, const double* data_in,
+                               const double* x_axis, int len_x, const double* y_axis, int len_y,
+                               double grid_spac, int num_neighbours, int row_begin, int row_end,
+                               double* data_ip, int32_t* nn_index, double* nn_dist2, int64_t* counters,
+                               int flags, int mem, void* stream);
+
+/* ---- parity / debug exports for the search structures ----------------------------------------- */
+
+/* kd_tree.f90:30-95: the canonical balanced tree (node = rank (n+1)/2 element along axis depth mod 2)
+ * as an implicit array: order[] (num_points, 1-based point ids) lists the points so that the node of any
+ * segment [lo,hi) is element lo+(hi-lo+1)/2-1, left subtree [lo,m), right subtree (m,hi). */
+int gi_kd_build_f64(const double* points, int num_points, int32_t* order, int flags, int mem, void* stream);
+
+/* query_esrg.f90:23-91 assign_points_to_cells: index_of_pts (num_points, 1-based, stable inside a cell),
+ * indptr (len_y*len_x + 1, 0-based offsets, CSR order ind_y outer / ind_x inner as query_esrg.f90:63-68). */
+int gi_esrg_assign_points_to_cells_f64(const double* points, int num_points, const double* x_axis, int len_x,
+                                       const double* y_axis, int len_y, double grid_spac,
+                                       int32_t* index_of_pts, int32_t* indptr, int flags, int mem,
+                                       void* stream);
+
+/* triangle_walk.f90:90-132 fill_nearest_neighbour on a caller-supplied mask (uint8, 1 = masked) and
+ * field, both (len_y, len_x) in the layout `flags` selects; data is filled in place. */
+int gi_fill_nearest_neighbour_f64(const uint8_t* mask_outside, int len_x, int len_y, double* data_ip,
+                                  int64_t* fill_src, int flags, int mem, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIDINTERP_H */

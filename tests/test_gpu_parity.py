@@ -1,0 +1,278 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Everything goes through the C ABI via the
+reference-facing Python layer and is compared with the CPU oracle on the same inputs:
+indices bit-exact, float64 values bit-exact (both sides evaluate the reference's expressions without FMA
+contraction), plus the committed golden vectors of the reference's own Python twins."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from grid_interpolation_b200 import interpolation as ip  # noqa: E402
+from grid_interpolation_b200 import workloads  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+RTOL = 1e-12  # north_star: FP64 values within 1e-12 relative (we additionally assert bit equality)
+
+
+def assert_values(got, want):
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=0)
+    assert np.array_equal(np.asarray(got), np.asarray(want)), "values are within 1e-12 but not bit-identical"
+
+
+# ------------------------------------------------------------------------------------------ bilinear
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_bilinear_c1(c1, order):
+    field = orc.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, c1.num_nn)
+    want = orc.bilinear(c1.x_axis, c1.y_axis, field, c1.points)
+    data = np.ascontiguousarray(field) if order == "C" else np.asfortranarray(field)
+    pts = np.ascontiguousarray(c1.points) if order == "C" else np.asfortranarray(c1.points)
+    got = ip.bilinear(c1.x_axis, c1.y_axis, data, pts)
+    assert got.shape == (c1.points.shape[0],)
+    assert_values(got, want)
+
+
+def test_bilinear_random_nonuniform_and_oob():
+    rng = np.random.default_rng(0)
+    x = np.cumsum(rng.uniform(0.5, 1.5, 301)); y = np.cumsum(rng.uniform(0.2, 0.4, 157)) - 7.0
+    field = rng.normal(size=(157, 301))
+    pts = np.stack([rng.uniform(x[0] - 5, x[-1] + 5, 20011), rng.uniform(y[0] - 2, y[-1] + 2, 20011)], 1)
+    pts[:3] = [[np.nan, 0.0], [x[0], y[0]], [x[-1], y[-1]]]
+    want = orc.bilinear(x, y, field, pts)
+    got = ip.bilinear(x, y, field, pts)
+    assert (want == -9999.0).sum() > 100
+    assert_values(got, want)
+
+
+def test_bilinear_empty_and_tiny():
+    x, y = np.array([0.0, 1.0]), np.array([0.0, 2.0])
+    f = np.array([[1.0, 2.0], [3.0, 4.0]])
+    assert ip.bilinear(x, y, f, np.zeros((0, 2))).shape == (0,)
+    assert_values(ip.bilinear(x, y, f, np.array([[0.25, 0.5]])), orc.bilinear(x, y, f, np.array([[0.25, 0.5]])))
+
+
+# --------------------------------------------------------------------------------------- barycentric
+@pytest.mark.parametrize("order", ["F", "C"])
+def test_barycentric_c1(c1, order):
+    want, w = orc.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                            c1.neighbours, debug=True)
+    got, g = ip.barycentric_interpolation_ex(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                             c1.neighbours, order=order, debug=True)
+    assert got.shape == want.shape == (79, 132)
+    assert got.flags.f_contiguous if order == "F" else got.flags.c_contiguous
+    assert np.array_equal(g.mask, w.mask) and g.masked == 433
+    ins = ~w.mask
+    assert np.array_equal(g.tri[ins], w.tri[ins])              # found triangle ids, bit-exact
+    assert np.array_equal(g.fill_src, w.fill_src)              # hull-fill sources incl. tie-breaks
+    assert g.fill_level_max == w.fill_level_max == 3
+    assert_values(got, want)
+    # plain entry point, Fortran-ordered inputs exactly as test_interpolation.py:192-204 passes them
+    plain = ip.barycentric_interpolation(np.asfortranarray(c1.points), c1.data_pts, c1.x_axis, c1.y_axis,
+                                         np.asfortranarray(c1.simplices), np.asfortranarray(c1.neighbours))
+    assert_values(plain, want)
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_barycentric_golden_twin(golden_dir, case):
+    z = np.load(os.path.join(golden_dir, "walk_twin.npz"))
+    g = lambda k: z[f"{case}_{k}"]
+    got, dbg = ip.barycentric_interpolation_ex(g("points"), g("data_pts"), g("x_axis"), g("y_axis"),
+                                               g("simplices") + 1, g("neighbours") + 1, debug=True)
+    inside = g("inside")
+    assert np.array_equal(~dbg.mask, inside)
+    assert np.array_equal(dbg.tri[inside] - 1, g("tri")[inside])
+    assert np.array_equal(got, g("data_filled"))
+
+
+def test_barycentric_row_bands_with_halo(c1):
+    want = orc.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                         c1.neighbours)
+    ly = c1.y_axis.size
+    for order in ("C", "F"):
+        parts = []
+        for r0, r1 in [(0, 20), (20, 41), (41, 42), (42, ly)]:
+            parts.append(ip.barycentric_interpolation_ex(c1.points, c1.data_pts, c1.x_axis, c1.y_axis,
+                                                         c1.simplices, c1.neighbours, rows=(r0, r1), halo=4,
+                                                         order=order))
+        assert_values(np.concatenate(parts, 0), want)
+    # a band whose fill needs rows outside the walked window must say so instead of returning wrong cells
+    with pytest.raises(RuntimeError, match="halo"):
+        ip.barycentric_interpolation_ex(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                        c1.neighbours, rows=(0, 2), halo=0)
+
+
+def test_barycentric_bad_topology_is_reported(c1):
+    bad = c1.simplices.copy(); bad[7, 1] = c1.points.shape[0] + 5
+    with pytest.raises(RuntimeError, match="out of range"):
+        ip.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, bad, c1.neighbours)
+
+
+def test_fill_standalone_matches_oracle():
+    rng = np.random.default_rng(5)
+    mask = rng.random((61, 83)) < 0.55
+    mask[20:45, 30:70] = True          # a big hole: deep levels
+    mask[0, 0] = False
+    data = rng.normal(size=mask.shape)
+    want, wsrc, lvl = orc.fill_nearest_neighbour(mask, data)
+    got, gsrc = ip.fill_nearest_neighbour(mask, data)
+    assert lvl >= 10
+    assert np.array_equal(gsrc, wsrc)
+    assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------- esrg
+@pytest.mark.parametrize("order", ["F", "C"])
+@pytest.mark.parametrize("k", [6, 8, 1, 13])
+def test_esrg_c1(c1, order, k):
+    want, w = orc.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, k, debug=True)
+    got, g = ip.idw_esrg_nearest_ex(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, k, order=order,
+                                    debug=True)
+    assert np.array_equal(g.nn_index, np.moveaxis(w.nn_index, 0, -1))     # neighbour ids in order, bit-exact
+    assert np.array_equal(np.sqrt(g.nn_dist2), np.moveaxis(w.nn_dist, 0, -1))
+    assert g.level_max == w.level_max
+    assert_values(got, want)
+
+
+def test_esrg_golden_twin(golden_dir):
+    z = np.load(os.path.join(golden_dir, "esrg_twin.npz"))
+    for case in "abc":
+        g = lambda k: z[f"{case}_{k}"]
+        pts = g("points")
+        data = np.cos(pts[:, 0]) + pts[:, 1]
+        k = int(g("k"))
+        _, dbg = ip.idw_esrg_nearest_ex(pts, data, g("x_axis"), g("y_axis"), float(g("grid_spac")), k, debug=True)
+        assert np.array_equal(dbg.nn_index - 1, g("nn_index"))
+        idx, ptr = ip.assign_points_to_cells(pts, g("x_axis"), g("y_axis"), float(g("grid_spac")))
+        assert np.array_equal(idx - 1, g("index_of_pts"))
+        assert np.array_equal(ptr[:-1].reshape(g("indptr").shape), g("indptr"))
+
+
+def test_esrg_clustered_overflows_candidate_list():
+    """Dense clusters: thousands of points per cell -> the reference's 1000-entry lists would overflow
+    (query_esrg.f90:119-121); the list-free fallback must still give the oracle's (growable-list) answer."""
+    rng = np.random.default_rng(11)
+    x = np.arange(40.0); y = np.arange(30.0)
+    pts = np.concatenate([rng.normal([10.2, 11.7], 0.6, (4000, 2)), rng.uniform([0, 0], [39, 29], (300, 2))])
+    data = np.sin(pts[:, 0]) * pts[:, 1]
+    want, w = orc.idw_esrg_nearest(pts, data, x, y, 1.0, 8, debug=True)
+    got, g = ip.idw_esrg_nearest_ex(pts, data, x, y, 1.0, 8, debug=True)
+    assert w.list_max > 1000 and g.list_overflows > 0
+    assert np.array_equal(g.nn_index, np.moveaxis(w.nn_index, 0, -1))
+    assert_values(got, want)
+
+
+def test_esrg_ties_on_lattice():
+    """Points on a lattice: many exactly equal distances -> exercises the tie order (new point goes before
+    equal ones, boundary tie keeps the earlier one; query_esrg.f90:163-168) and the stable cell order."""
+    gx, gy = np.meshgrid(np.arange(0.0, 12.0, 0.5), np.arange(0.0, 9.0, 0.5))
+    pts = np.stack([gx.ravel(), gy.ravel()], 1)
+    rng = np.random.default_rng(3)
+    pts = pts[rng.permutation(pts.shape[0])]
+    data = rng.normal(size=pts.shape[0])
+    x = np.arange(12.0); y = np.arange(9.0)
+    want, w = orc.idw_esrg_nearest(pts, data, x, y, 1.0, 7, debug=True)
+    got, g = ip.idw_esrg_nearest_ex(pts, data, x, y, 1.0, 7, debug=True)
+    assert np.array_equal(g.nn_index, np.moveaxis(w.nn_index, 0, -1))
+    assert_values(got, want)     # includes the "extremely close neighbour" branch (distance 0)
+
+
+def test_esrg_too_few_points():
+    with pytest.raises(RuntimeError, match="fewer"):
+        ip.idw_esrg_nearest(np.random.rand(3, 2), np.zeros(3), np.arange(4.0), np.arange(4.0), 1.0, 5)
+
+
+# ------------------------------------------------------------------------------------------- k-d tree
+def test_kd_build_is_canonical(c1):
+    order = ip.kd_build(np.ascontiguousarray(c1.points.T)) - 1
+    ref = orc.kd_build(c1.points.T)
+
+    def walk(node, lo, hi):     # oracle pointer tree vs implicit array
+        if node < 0:
+            assert lo == hi
+            return
+        m = lo + (hi - lo + 1) // 2 - 1
+        assert order[m] == ref.index[node] - 1
+        walk(ref.left[node], lo, m)
+        walk(ref.right[node], m + 1, hi)
+
+    walk(ref.root, 0, order.size)
+
+
+@pytest.mark.parametrize("scale", [1.0, 10.0, 0.3])
+@pytest.mark.parametrize("k", [6, 8])
+def test_kdtree_c1(c1, scale, k):
+    """scale 1.0 / 0.3: k-th d2 < 1 -> the reference's prune rule is too eager and the sets are NOT the exact
+    kNN; they must still equal the oracle's bit for bit.  scale 10: exact regime."""
+    pts = np.asfortranarray(c1.points.T * scale)
+    xa, ya = c1.x_axis * scale, c1.y_axis * scale
+    want, w = orc.idw_kdtree(pts, c1.data_pts, xa, ya, k, debug=True)
+    got, g = ip.idw_kdtree_ex(pts, c1.data_pts, xa, ya, k, debug=True)
+    assert np.array_equal(g.nn_index, np.moveaxis(w.nn_index, 0, -1))
+    assert np.array_equal(g.nn_dist2, np.moveaxis(w.nn_dist2, 0, -1))
+    assert_values(got, want)
+    assert g.visits <= w.visits
+    # with the extra (state-preserving) prune switched off the traversal visits exactly the reference's nodes
+    got2, g2 = ip.idw_kdtree_ex(pts, c1.data_pts, xa, ya, k, debug=True, reference_visits=True, order="C")
+    assert g2.visits == w.visits
+    assert np.array_equal(g2.nn_index, np.moveaxis(w.nn_index, 0, -1))
+    assert_values(got2, want)
+
+
+def test_kdtree_sentinel_far_points():
+    """Neighbours with d2 >= 1e6 are never found (interpolation.f90:159, kd_tree.f90:222-223)."""
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(0, 5000.0, (2, 300))
+    data = rng.normal(size=300)
+    x = np.linspace(0, 5000.0, 23); y = np.linspace(0, 5000.0, 17)
+    want, w = orc.idw_kdtree(pts, data, x, y, 8, debug=True)
+    got, g = ip.idw_kdtree_ex(pts, data, x, y, 8, debug=True)
+    assert (w.nn_index == 0).any()
+    assert np.array_equal(g.nn_index, np.moveaxis(w.nn_index, 0, -1))
+    assert_values(got, want)
+
+
+# ------------------------------------------------------------------------------- torch device buffers
+def test_torch_device_path(c1):
+    import torch
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    want = orc.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                         c1.neighbours)
+    got = ip.barycentric_interpolation(t(c1.points), t(c1.data_pts), t(c1.x_axis), t(c1.y_axis),
+                                       t(c1.simplices), t(c1.neighbours), order="C")
+    assert got.is_cuda and tuple(got.shape) == want.shape
+    assert_values(got.cpu().numpy(), want)
+    back = ip.bilinear(t(c1.x_axis), t(c1.y_axis), got, t(c1.points))
+    assert_values(back.cpu().numpy(), orc.bilinear(c1.x_axis, c1.y_axis, want, c1.points))
+    e = ip.idw_esrg_nearest(t(c1.points), t(c1.data_pts), t(c1.x_axis), t(c1.y_axis), c1.grid_spac, 6)
+    assert_values(e.cpu().numpy(), orc.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis,
+                                                        c1.grid_spac, 6))
+    kd = ip.idw_kdtree(t(c1.points).t(), t(c1.data_pts), t(c1.x_axis), t(c1.y_axis), 6)
+    assert_values(kd.cpu().numpy(), orc.idw_kdtree(c1.points.T, c1.data_pts, c1.x_axis, c1.y_axis, 6))
+
+
+# --------------------------------------------------------------- larger, size-independent properties
+def test_medium_mesh_matches_oracle_and_properties():
+    """200k-point mesh on a 1024^2 grid (the oracle still finishes in seconds)."""
+    rng = np.random.default_rng(4)
+    n, grid = 200_000, 1024
+    pts = rng.uniform(0.0, grid - 1.0, (n, 2))
+    simp, nbr = workloads.delaunay(pts)
+    data = workloads.sin_mountains(pts[:, 0] * 0.02, pts[:, 1] * 0.02)
+    axis = np.arange(float(grid))
+    want, w = orc.barycentric_interpolation(pts, data, axis, axis, simp, nbr, debug=True)
+    got, g = ip.barycentric_interpolation_ex(pts, data, axis, axis, simp, nbr, debug=True, order="C")
+    ins = ~w.mask
+    assert np.array_equal(g.mask, w.mask)
+    assert np.array_equal(g.tri[ins], w.tri[ins])
+    assert_values(got, want)
+    # linearity in the data: interp(a*d1 + d2) is affine in the nodal values -> a linear field is reproduced
+    lin = 3.0 * pts[:, 0] - 2.0 * pts[:, 1] + 5.0
+    out = ip.barycentric_interpolation(pts, lin, axis, axis, simp, nbr, order="C")
+    xx, yy = np.meshgrid(axis, axis)
+    np.testing.assert_allclose(out[ins], (3.0 * xx - 2.0 * yy + 5.0)[ins], rtol=0, atol=1e-7)
+    # bilinear back at the grid nodes themselves is the identity
+    nodes = np.stack([xx[:-1, :-1].ravel(), yy[:-1, :-1].ravel()], 1)
+    back = ip.bilinear(axis, axis, got, nodes)
+    assert np.array_equal(back, got[:-1, :-1].ravel())
