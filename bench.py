@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the grid_interpolation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c2|c3|c5]
+                    [--scaling weak|strong] [--scale F]
+
+Default workload = BASELINE.json's headline config C4: barycentric interpolation via the triangle walk from a
+synthetic ~10 M-triangle Delaunay mesh (5 M uniform points, scipy/Qhull, cached under $GI_CACHE) to a
+16384 x 16384 regular grid, hull fill included.  One "step" = one complete barycentric_interpolation call
+(mesh packing + seed grid + walk/barycentric + hull fill), stateless like the reference's routine.
+
+  value   target points/s, inputs and output resident in HBM, timed on the device with CUDA events around
+          exactly K steps after W warm-up steps (max over ranks).
+  e2e     the same metric through the reference-facing Python call with HOST (pinned) buffers: every step
+          copies the mesh in and the field out inside the timed region.
+  roofline  the walk kernel: algorithmic bytes (9.34 B/target for C4) / its CUDA-event duration,
+          against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle (C++/OpenMP restatement of the Fortran, see oracle/) on the host cores of this
+          box, on a bounded sample of the same workload (evenly strided grid rows), rank 0 / N=1 only.
+
+Multi-GPU (torchrun, one rank per GPU): targets are sharded in contiguous row bands, the mesh is replicated,
+no data-path collective.  --scaling weak (default): every rank computes one 16384-row band of a
+16384 x (16384*N) grid laid over the same mesh extent (per-GPU work fixed; N=1 is exactly C4).
+--scaling strong: the fixed 16384 x 16384 grid is split into N bands (BASELINE.json's literal C4 sharding).
+
+--impl reference times the reference's own CPU algorithm (the oracle port; the Fortran cannot be compiled in
+this image: no gfortran) with all host threads on the same config, each step a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from grid_interpolation_b200 import workloads  # noqa: E402
+
+ALG_BYTES = {"c2": 9.43, "c3": 11.58, "c4": 9.34, "c5": 45.48}       # SURVEY.md section 8(d), FP64 + int32
+KERNELS_PER_STEP = {"c4": 5, "c2": None, "c3": None, "c5": 2}          # our kernel launches per step (c2/c3: computed)
+DOMINANT = {"c4": "walk", "c5": "bilinear", "c3": "esrg_query", "c2": "kd_query"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; <1 is not the headline)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_c4(args, rank, world, dist):
+    """(mesh workload, y_axis of the whole job, row band of this rank)."""
+    n = max(int(5_000_000 * args.scale ** 2), 1000)
+    grid = max(int(16384 * args.scale) // 128 * 128, 128)
+    if world > 1:  # rank 0 triangulates (about a minute at full size) and caches; the others load the cache
+        if rank == 0:
+            w = workloads.c4(n, grid)
+        dist.barrier()
+        if rank != 0:
+            w = workloads.c4(n, grid)
+    else:
+        w = workloads.c4(n, grid)
+    if args.scaling == "weak":
+        y_axis = np.arange(grid * world, dtype=np.float64) / world   # same extent, N x the rows
+        band = (rank * grid, (rank + 1) * grid)
+    else:
+        y_axis = w.y_axis
+        band = (rank * grid // world, (rank + 1) * grid // world)
+    return w, y_axis, band, grid
+
+
+def cpu_sample_c4(w, y_axis, seconds, threads=None):
+    """Oracle barycentric on evenly strided grid rows of the same job: every row pays the reference's
+    restart-from-the-start-triangle walk exactly as in the full run.  Returns (targets/s, description)."""
+    from oracle import oracle as orc
+    if threads:
+        orc.set_num_threads(threads)
+    cores = orc.get_max_threads()
+    pts_f = np.asfortranarray(w.points); simp_f = np.asfortranarray(w.simplices); nbr_f = np.asfortranarray(w.neighbours)
+
+    def run(rows):
+        ys = np.ascontiguousarray(y_axis[:: max(len(y_axis) // rows, 1)][:rows])
+        t0 = time.perf_counter()
+        orc.barycentric_interpolation(pts_f, w.data_pts, w.x_axis, ys, simp_f, nbr_f)
+        return ys.size * w.x_axis.size, time.perf_counter() - t0
+
+    rows = max(2 * cores, 16)
+    tg, dt = run(rows)                                   # calibration
+    rate = tg / dt
+    rows2 = int(min(len(y_axis), max(rows, rate * seconds / w.x_axis.size)))
+    rows2 = max(rows2 // cores * cores, cores)
+    tg, dt = run(rows2)
+    return tg / dt, cores, f"{rows2} evenly strided rows x {w.x_axis.size} columns of the job's grid ({tg} targets, {dt:.1f} s)"
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.workload != "c4":
+        sys.path.insert(0, os.path.join(ROOT, "bench"))
+        import bench_extra
+        return bench_extra.run(args, rank, world, local_rank)
+
+    # ---------------------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        w, y_axis, band, grid = make_c4(args, 0, 1, None)
+        if args.scaling == "weak":
+            y_axis = np.arange(grid * args.gpus, dtype=np.float64) / args.gpus
+        vals = []
+        desc = ""
+        per_step = max(args.cpu_seconds, 5.0)
+        for i in range(args.warmup + args.steps):
+            v, cores, desc = cpu_sample_c4(w, y_axis, per_step if i >= args.warmup else 2.0)
+            if i >= args.warmup:
+                vals.append(v)
+            per_step = min(per_step, 150.0 / max(args.steps, 1))
+        value = float(np.mean(vals))
+        tg = w.x_axis.size * (band[1] - band[0]) * args.gpus
+        print(json.dumps({
+            "metric": "target points interpolated/sec", "value": value, "unit": "targets/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"C4 barycentric via triangle walk: {w.simplices.shape[0]} triangles -> "
+                                   f"{w.x_axis.size} x {len(y_axis)} grid (bounded row sample per step)"},
+            "cpu_baseline": {"value": value, "unit": "targets/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": "targets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
+        return 0
+
+    # ---------------------------------------------------------------------------- our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    from grid_interpolation_b200 import interpolation as ip
+    from grid_interpolation_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w, y_axis, band, grid = make_c4(args, rank, world, dist if world > 1 else None)
+    rows = band[1] - band[0]
+    len_x = w.x_axis.size
+    targets_rank = rows * len_x
+    halo = 8 if world > 1 else 0
+
+    # device-resident inputs in the caller's (numpy C-order) layout
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    d_pts, d_val, d_x, d_y = t(w.points), t(w.data_pts), t(w.x_axis), t(y_axis)
+    d_simp, d_nbr = t(w.simplices), t(w.neighbours)
+    d_out = torch.empty((rows, len_x), dtype=torch.float64, device=dev)
+
+    def step_dev():
+        ip.barycentric_interpolation_ex(d_pts, d_val, d_x, d_y, d_simp, d_nbr, rows=band, halo=halo, out=d_out,
+                                        sync=False)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sync_all()
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().gi_stream_status(stream), "warm-up")
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ip.set_profiling(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record()
+    sync_all()
+    phases = ip.last_timings()
+    ip.set_profiling(False)
+    clk = clocks.stop() if rank == 0 else None
+    _lib.check(_lib.lib().gi_stream_status(stream), "timed steps")
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = targets_rank * world * args.steps / (ms_total * 1e-3)
+
+    # per-phase device time (this rank), averaged over the timed steps
+    agg = {}
+    for name, v in phases:
+        agg.setdefault(name, []).append(v)
+    phase_ms = {k: float(np.mean(v)) for k, v in agg.items()}
+    walk_ms = phase_ms.get("walk")
+
+    # ------------------------------------------------------------------ e2e: host buffers through the public API
+    e2e = None
+    if not args.no_e2e:
+        h_pts, h_val = ip.pinned_copy(w.points), ip.pinned_copy(w.data_pts)
+        h_x, h_y = ip.pinned_copy(w.x_axis), ip.pinned_copy(y_axis)
+        h_simp, h_nbr = ip.pinned_copy(w.simplices), ip.pinned_copy(w.neighbours)
+        h_out = ip.pinned_empty((rows, len_x), np.float64, "C")
+
+        def step_host():
+            ip.barycentric_interpolation_ex(h_pts, h_val, h_x, h_y, h_simp, h_nbr, rows=band, halo=halo, out=h_out)
+
+        e_steps = max(2, min(args.steps, 5))
+        step_host()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            step_host()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = sum(a.nbytes for a in (h_pts, h_val, h_x, h_y, h_simp, h_nbr))
+        e2e = {"value": targets_rank * world * e_steps / float(dt.item()), "unit": "targets/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_out.nbytes), "steps": e_steps,
+               "note": "per rank; pinned host buffers; H2D + pack + walk + fill + D2H inside the timed region"}
+        # the host path must agree with the device path bit for bit
+        assert np.array_equal(h_out, d_out.cpu().numpy()), "host-path result differs from device-path result"
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    alg = ALG_BYTES["c4"] * targets_rank
+    roof = None
+    if walk_ms:
+        achieved = alg / (walk_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "walk_kernel_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "walk_kernel<double>", "kernel_ms": walk_ms, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, desc = cpu_sample_c4(w, y_axis, args.cpu_seconds)
+        cpu = {"value": v, "unit": "targets/s", "cores": cores, "kind": "port", "sample": desc}
+
+    out = {
+        "metric": "target points interpolated/sec", "value": value, "unit": "targets/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "impl": "ours",
+        "config": {"workload": f"C4 barycentric via triangle walk + hull fill: {w.points.shape[0]} points / "
+                               f"{w.simplices.shape[0]} triangles (scipy Delaunay, default_rng(4)) -> "
+                               f"{len_x} x {len(y_axis)} regular grid, {world} row band(s) of {rows} rows",
+                   "l2": "inputs (0.36 GB) and output (2.1 GB) per step exceed the 126 MB L2; no explicit flush",
+                   "layout": "numpy C-order inputs and output, consumed in place (no transposition)",
+                   "scale": args.scale},
+        "phase_ms": phase_ms, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk,
+        "gpu_launches": KERNELS_PER_STEP["c4"] * args.steps,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

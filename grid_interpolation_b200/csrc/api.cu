@@ -113,7 +113,6 @@ int read_status(cudaStream_t s, bool synchronize) {
 // phase timers
 // ---------------------------------------------------------------------------------------------
 static bool g_profiling = false;
-void set_profiling(bool on) { g_profiling = on; }
 bool profiling() { return g_profiling; }
 
 struct Recorder {
@@ -134,10 +133,15 @@ struct Recorder {
   }
 };
 static thread_local Recorder t_rec;
+// Switching profiling on starts a fresh recording on the calling thread; phases of every later call are
+// appended until it is switched on again (so a benchmark can time K steps without a per-step sync).
+void set_profiling(bool on) {
+  g_profiling = on;
+  if (on) t_rec.reset();
+}
 
 Phases::Phases(cudaStream_t s) : stream_(s), on_(g_profiling) {
   if (!on_) return;
-  if (t_rec.depth == 0) t_rec.reset();
   ++t_rec.depth;
 }
 void Phases::mark(const char* name) {
@@ -148,7 +152,10 @@ void Phases::mark(const char* name) {
 void Phases::finish() {
   if (!on_) return;
   on_ = false;
-  if (--t_rec.depth == 0) t_rec.stamp(stream_);
+  if (--t_rec.depth == 0) {  // closing stamp of the call: recorded as an unnamed pseudo-phase
+    t_rec.names.push_back("");
+    t_rec.stamp(stream_);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -443,13 +450,14 @@ GI_API void gi_host_free(void* p) { if (p) cudaFreeHost(p); }
 GI_API int gi_stream_status(void* stream) { return read_status((cudaStream_t)stream, true); }
 GI_API void gi_set_profiling(int on) { set_profiling(on != 0); }
 GI_API int gi_last_timings(double* ms, int capacity) {
+  // names[i] opens at events[i]; "" entries are call-closing stamps (reported with 0 ms so indices line up)
   Recorder& r = t_rec;
   if (r.events.size() < 2) return 0;
   cudaEventSynchronize(r.events.back());
-  const int n = (int)std::min(r.names.size(), r.events.size() - 1);
+  const int n = (int)std::min(r.names.size(), r.events.size());
   for (int i = 0; i < n && i < capacity; ++i) {
     float t = 0.f;
-    cudaEventElapsedTime(&t, r.events[i], r.events[i + 1]);
+    if (!r.names[i].empty() && i + 1 < (int)r.events.size()) cudaEventElapsedTime(&t, r.events[i], r.events[i + 1]);
     ms[i] = t;
   }
   return n;

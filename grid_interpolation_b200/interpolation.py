@@ -463,11 +463,12 @@ def set_profiling(on: bool) -> None:
     lib().gi_set_profiling(1 if on else 0)
 
 
-def last_timings():
-    """[(phase name, device milliseconds)] of the last call on this thread (needs set_profiling(True))."""
-    buf = (C.c_double * 32)()
-    n = lib().gi_last_timings(buf, 32)
-    return [(lib().gi_last_timing_name(i).decode(), buf[i]) for i in range(min(n, 32))]
+def last_timings(capacity=8192):
+    """[(phase name, device milliseconds)] of every call made by this thread since set_profiling(True)."""
+    buf = (C.c_double * capacity)()
+    n = lib().gi_last_timings(buf, capacity)
+    res = [(lib().gi_last_timing_name(i).decode(), buf[i]) for i in range(min(n, capacity))]
+    return [(name, ms) for name, ms in res if name]
 
 
 def _moveaxis(a, src, dst):

@@ -81,10 +81,11 @@ void* gi_host_alloc(uint64_t bytes);
 void gi_host_free(void* p);
 /* cudaStreamSynchronize(stream) + the first device-side error recorded on it since the last call. */
 int gi_stream_status(void* stream);
-/* Phase profiling: when on, every call records CUDA events around its phases (H2D, pack, walk, fill, ...)
- * on the stream it runs on.  gi_last_timings() synchronises on the last event of the last call made by
- * this thread and returns the number of phases; ms[i] is the device time of phase i and
- * gi_last_timing_name(i) its name. */
+/* Phase profiling: gi_set_profiling(1) starts a fresh recording on the calling thread; from then on every
+ * call made by that thread records CUDA events around its phases (h2d, pack_mesh, walk, fill, d2h, ...) on
+ * the stream it runs on, without synchronising.  gi_last_timings() waits for the last recorded event and
+ * returns the number of entries since the recording started; ms[i] is the device time of entry i and
+ * gi_last_timing_name(i) its phase name ("" marks the end of one call, 0 ms). */
 void gi_set_profiling(int on);
 int gi_last_timings(double* ms, int capacity);
 const char* gi_last_timing_name(int i);
