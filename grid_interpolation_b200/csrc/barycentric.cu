@@ -7,23 +7,29 @@
 //   triangle_walk.f90:90-132    fill_nearest_neighbour (nearest unmasked cell in index space)
 //
 // B200 design (not a port):
-//   1. pack_mesh_kernel  gathers every triangle's 3 vertices + 3 neighbour ids into ONE 64-byte record
-//      (two 32 B sectors) and its 3 nodal values into a 32-byte record, so that a walk step is a single
-//      aligned 64 B load instead of 3 index loads + 6 scattered coordinate loads.  The same pass bins one
-//      triangle id per 16x16-target cell (atomicMin -> deterministic) into a seed grid.
-//   2. walk_kernel       one thread per target column, chained down a strip of rows: the triangle found
-//      for row r seeds row r+1 (the reference chains along a grid row in the same way, interpolation.f90:
-//      366-373, but restarts every row from one global start triangle; here the first row of a strip is
-//      seeded from the seed grid).  The found triangle is path-independent outside the 1e-10 margin band
-//      (SURVEY 0.7), so the seeding changes the iteration count, not the result.  A warp covers 32
-//      consecutive targets of the contiguous output axis -> 256 B coalesced stores; outside-hull flags go
-//      into a 1-bit-per-target mask written with one ballot per warp row.
-//   3. fill_kernel       one warp per mask word, one lane per masked cell: exact ring search over the bit
-//      mask with the reference's tie-break (smallest squared index distance, then smallest row, then
-//      smallest column).
+//   1. pack_mesh_kernel    gathers every triangle into two aligned records: a 64 B WALK record (3 vertices +
+//      3 neighbour ids = two 32 B sectors, so a walk step is one aligned load instead of 3 index loads + 6
+//      scattered coordinate loads) and a 96 B EVALUATION record (everything of interpolation.f90:385-398 that
+//      depends on the triangle only, including the refined reciprocal of the denominator).  The same pass
+//      bins one triangle id per 16x16-target cell (atomicMin -> deterministic) into a seed grid.
+//   2. locate_eval_kernel  a CTA owns 128 columns x 32 rows of targets.  Phase 1 (locate): one thread per
+//      column walks down the rows; the triangle found for row r seeds row r+1 (the reference chains along a
+//      grid row in the same way, interpolation.f90:366-373, but restarts every row from one global start
+//      triangle; here the first row of a strip is seeded from the seed grid).  The found triangle is
+//      path-independent outside the 1e-10 margin band, so the seeding changes the iteration
+//      count, not the result.  Lanes are decoupled (each runs its own test / move loop) and keep the
+//      (triangle, column)-invariant half of every orientation product in registers, so a target in the same
+//      triangle as the one above it costs no memory access.  Phase 2 (evaluate): row-synchronous, uniform,
+//      128 consecutive doubles per row stored coalesced; outside-hull flags go into a 1-bit-per-target mask
+//      (one ballot per warp row) and the non-zero mask words into a compact work list.
+//   3. fill_kernel         one warp per non-zero mask word, one lane per masked cell: exact ring search over
+//      the bit mask with the reference's tie-break (smallest squared index distance, then smallest row,
+//      then smallest column).
 //
-// All index decisions (orientation signs, first failing edge) use the reference's expression order with
-// FMA contraction disabled (-fmad=false), so they are bit-identical to the oracle's.
+// All index decisions (orientation signs, first failing edge) and all values use the reference's operations
+// in the reference's order with FMA contraction disabled (-fmad=false): bit-identical to the oracle.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace gi {
@@ -31,21 +37,66 @@ namespace gi {
 namespace {
 
 constexpr int kSeedCell = 16;      // targets per seed-grid cell edge
-constexpr int kWalkThreads = 128;  // one CTA = 128 columns x kWalkRows rows
-constexpr int kWalkRows = 32;
+constexpr int kWalkThreads = 128;  // columns per CTA
 
 template <class R> struct alignas(16) TriGeom {  // f64: 64 B = 2 sectors
   R x1, y1, x2, y2, x3, y3;
   int n1, n2, n3;  // neighbour opposite vertex 1/2/3, 0-based, -1 = hull edge
   int pad;
 };
-template <class R> struct alignas(16) TriVals {  // f64: 32 B = 1 sector
-  R d1, d2, d3, pad;
+// Everything the barycentric value needs that depends on the triangle only (interpolation.f90:385-398):
+// A = y2-y3, B = x3-x2, C = y3-y1, D = x1-x3, denom = A*D + B*(y1-y3), r2 = refined reciprocal of denom
+// (see DivRcp), nodal values d1..d3.  f64: 96 B = 3 sectors.
+template <class R> struct alignas(16) EvalRec {
+  R x3, y3, A, B, C, D, denom, r2, d1, d2, d3, pad;
 };
 template <class R> struct SeedGrid {
   R x0, y0, inv_cell_x, inv_cell_y;
   int ncx, ncy;
 };
+
+// ---------------------------------------------------------------------------------------------
+// IEEE-exact division with a reusable reciprocal.
+//
+// nvcc expands a double-precision `n / d` into: seed r0 = MUFU.RCP64H(d) (low word 1), two Newton steps
+// -> r2, then q0 = n*r2, rem = fma(-d,q0,n), q = fma(r2,rem,q0), plus a range check that diverts
+// denormal / huge operands to a slow path (SASS of this file, round-1 notes in DESIGN.md).  r2 depends only
+// on d, and both barycentric quotients of a target -- and of every other target in the same triangle --
+// share d = denom (interpolation.f90:385-394).  DivRcp reproduces that instruction sequence verbatim, so
+// quotient() returns the correctly rounded IEEE quotient, bit-identical to the `/` operator (and so to the
+// oracle); operands outside the fast path's range take the `/` operator itself.
+// ---------------------------------------------------------------------------------------------
+template <class R> struct DivRcp;
+template <> struct DivRcp<double> {
+  double d, r2;
+  __device__ __forceinline__ void set(double denom) {
+    d = denom;
+    double seed;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(denom));
+    const double r0 = __hiloint2double(__double2hiint(seed), 1);
+    double e = __fma_rn(-d, r0, 1.0);
+    e = __fma_rn(e, e, e);
+    const double r1 = __fma_rn(r0, e, r0);
+    const double e2 = __fma_rn(-d, r1, 1.0);
+    r2 = __fma_rn(r1, e2, r1);
+  }
+  __device__ __forceinline__ double quotient(double n) const {
+    const double q0 = __dmul_rn(n, r2);
+    const double rem = __fma_rn(-d, q0, n);
+    const double q = __fma_rn(r2, rem, q0);
+    // nvcc's own guards: numerator exponent not tiny; quotient normal and finite (high words viewed as f32)
+    const float nh = __int_as_float(__double2hiint(n));
+    const float qh = __fmaf_rn(0.0f, __int_as_float(__double2hiint(d)), __int_as_float(__double2hiint(q)));
+    if (fabsf(nh) >= 6.5827683646048100446e-37f && fabsf(qh) > 1.469367938527859385e-39f) return q;
+    return n / d;
+  }
+};
+template <> struct DivRcp<float> {
+  float d, r2;
+  __device__ __forceinline__ void set(float denom) { d = denom; r2 = 0.f; }
+  __device__ __forceinline__ float quotient(float n) const { return n / d; }
+};
+
 
 template <class R>
 __global__ void seed_setup_kernel(const R* x_axis, int len_x, const R* y_axis, int len_y, SeedGrid<R>* sg) {
@@ -63,7 +114,7 @@ __global__ void seed_setup_kernel(const R* x_axis, int len_x, const R* y_axis, i
 template <class R>
 __global__ void __launch_bounds__(256)
 pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, TopoView nbr, int num_points,
-                 int num_tri, TriGeom<R>* __restrict__ geom, TriVals<R>* __restrict__ vals,
+                 int num_tri, TriGeom<R>* __restrict__ geom, EvalRec<R>* __restrict__ vals,
                  int* __restrict__ seed, const SeedGrid<R>* __restrict__ sgp, int* __restrict__ status) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= num_tri) return;
@@ -85,7 +136,13 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
   g.n1 = n1 - 1; g.n2 = n2 - 1; g.n3 = n3 - 1;
   g.pad = 0;
   geom[t] = g;
-  TriVals<R> v;
+  EvalRec<R> v;
+  v.x3 = g.x3; v.y3 = g.y3;
+  v.A = g.y2 - g.y3; v.B = g.x3 - g.x2; v.C = g.y3 - g.y1; v.D = g.x1 - g.x3;
+  v.denom = v.A * v.D + v.B * (g.y1 - g.y3);
+  DivRcp<R> dv;
+  dv.set(v.denom);
+  v.r2 = dv.r2;
   v.d1 = __ldg(data + (a - 1)); v.d2 = __ldg(data + (b - 1)); v.d3 = __ldg(data + (c - 1));
   v.pad = R(0);
   vals[t] = v;
@@ -146,12 +203,14 @@ __device__ __forceinline__ int walk(const TriGeom<R>* __restrict__ geom, int tri
   return tri;
 }
 
-// interpolation.f90:385-398, same operation order.
+// interpolation.f90:385-398, same operation order; the two divisions share the triangle's reciprocal.
 template <class R>
-__device__ __forceinline__ R barycentric_value(const TriGeom<R>& g, const TriVals<R>& v, R tx, R ty) {
-  const R denom = (g.y2 - g.y3) * (g.x1 - g.x3) + (g.x3 - g.x2) * (g.y1 - g.y3);
-  const R w1 = ((g.y2 - g.y3) * (tx - g.x3) + (g.x3 - g.x2) * (ty - g.y3)) / denom;
-  const R w2 = ((g.y3 - g.y1) * (tx - g.x3) + (g.x1 - g.x3) * (ty - g.y3)) / denom;
+__device__ __forceinline__ R eval_value(const EvalRec<R>& v, R tx, R ty) {
+  const R u = tx - v.x3, t = ty - v.y3;
+  DivRcp<R> dv;
+  dv.d = v.denom; dv.r2 = v.r2;
+  const R w1 = dv.quotient(v.A * u + v.B * t);
+  const R w2 = dv.quotient(v.C * u + v.D * t);
   const R w3 = R(1) - w1 - w2;
   return v.d1 * w1 + v.d2 * w2 + v.d3 * w3;
 }
@@ -160,60 +219,130 @@ template <class R> struct WalkArgs {
   TargetWindow<R> win;   // walked window E (band + halo)
   int bf0, bf1, bs0, bs1;  // band B inside E: the part that is written to `out`
   const TriGeom<R>* geom;
-  const TriVals<R>* vals;
+  const EvalRec<R>* vals;
   const int* seed;
   int ncx, ncy, num_tri, iter_cap;
   R* out;               // band-shaped: (bs1-bs0) slow rows of (bf1-bf0)
   int32_t* tri_out;     // optional, band-shaped
   uint32_t* mask_words; // E-shaped bit mask: ((nf+31)/32) words per slow row
-  int64_t* counters;
+  int* nz_words;        // compact list of the mask words that are non-zero (work list of the hull fill)
+  int64_t* counters;    // [0] walk iterations [1] masked cells [2] max fill level [3] fix-ups [4] #nz_words
   int* status;
 };
 
-template <class R>
-__global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkArgs<R> a) {
+// ---------------------------------------------------------------------------------------------
+// The production kernel: locate, then evaluate.
+//
+// ncu on the first two versions (profiles/r01_*): a fused "walk + interpolate per target" loop has three
+// divergent regions (orientation test / move to the neighbour / barycentric value) and ran with 18-21 of 32
+// lanes active, 6 warps per scheduler and 53-63 % issue utilisation.  Splitting it makes both halves SIMT
+// friendly:
+//   phase 1 (locate)   every lane walks its own column down the strip, decoupled from the other lanes: one
+//                      loop whose body is "test the cached triangle; then either record the triangle id for
+//                      this row and go to the next row, or load the neighbouring triangle's 64 B record".
+//                      Only 9 doubles of per-(triangle, column) state stay in registers.  The ids go into a
+//                      shared-memory tile (int32, ~id = left through a hull edge).
+//   phase 2 (evaluate) row-synchronous and uniform: every lane reads its triangle's 96 B evaluation record
+//                      (L1/L2 resident, written by pack_mesh_kernel) and computes the value with two
+//                      shared-reciprocal divisions; 128 consecutive doubles per row are stored coalesced and
+//                      the outside-hull bits come from one ballot per warp row.
+// ---------------------------------------------------------------------------------------------
+template <class R, bool FY, int ROWS, int MINB>
+__global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const WalkArgs<R> a) {
+  __shared__ int stri[ROWS][kWalkThreads];
+  __shared__ R saxis[ROWS];
   const TargetWindow<R>& w = a.win;
-  const int lane_f = blockIdx.x * kWalkThreads + threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int lane_f = blockIdx.x * kWalkThreads + tid;
   const int f = w.f0 + lane_f;
   const bool active = f < w.f1;
-  const int srow0 = w.s0 + blockIdx.y * kWalkRows;
-  const int srow1 = min(srow0 + kWalkRows, w.s1);
-  const R tf = active ? __ldg(w.fast_axis + f) : R(0);
-  const int wpr = (w.nf() + 31) >> 5;  // mask words per slow row
-  const bool f_in_band = active && f >= a.bf0 && f < a.bf1;
+  const int srow0 = w.s0 + blockIdx.y * ROWS;
+  const int nrows = min(ROWS, w.s1 - srow0);
+  if (tid < nrows) saxis[tid] = __ldg(w.slow_axis + srow0 + tid);
+  __syncthreads();
+  const R cf = active ? __ldg(w.fast_axis + f) : R(0);
+  const R margin = Consts<R>::margin();
 
-  int tri = 0;
-  if (active) {
-    const int ix = w.fast_is_y ? srow0 : f, iy = w.fast_is_y ? f : srow0;
-    tri = seed_lookup(a.seed, a.ncx, a.ncy, ix, iy, a.num_tri);
-  }
+  // ---- phase 1: locate -------------------------------------------------------------------------
   long long iters_sum = 0;
-  for (int s = srow0; s < srow1; ++s) {
-    const R ts = __ldg(w.slow_axis + s);
-    const R tx = w.fast_is_y ? ts : tf, ty = w.fast_is_y ? tf : ts;
-    bool inside = true;
-    if (active) {
-      TriGeom<R> g;
-      int iters;
-      tri = walk(a.geom, tri, tx, ty, a.iter_cap, inside, iters, g, a.status);
-      iters_sum += iters;
-      if (f_in_band && s >= a.bs0 && s < a.bs1) {
-        const int64_t o = (int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0);
-        if (inside) {
-          const TriVals<R> v = a.vals[tri];
-          a.out[o] = barycentric_value(g, v, tx, ty);
-        }
-        if (a.tri_out) a.tri_out[o] = tri + 1;
+  if (active) {
+    int tri, n1, n2, n3;
+    R m1, m2, m3, p1, p2, p3, k1, k2, k3;
+    auto enter = [&](int t) {  // make `t` the current triangle: one 64 B load + 12 flops
+      tri = t;
+      const TriGeom<R> g = a.geom[t];
+      n1 = g.n1; n2 = g.n2; n3 = g.n3;
+      const R ex1 = g.x2 - g.x1, ey1 = g.y2 - g.y1;   // edge (v1,v2)
+      const R ex2 = g.x3 - g.x2, ey2 = g.y3 - g.y2;   // edge (v2,v3)
+      const R ex3 = g.x1 - g.x3, ey3 = g.y1 - g.y3;   // edge (v3,v1)
+      if (!FY) {
+        m1 = ex1; m2 = ex2; m3 = ex3; p1 = g.y1; p2 = g.y2; p3 = g.y3;
+        k1 = ey1 * (cf - g.x1); k2 = ey2 * (cf - g.x2); k3 = ey3 * (cf - g.x3);
+      } else {
+        m1 = ey1; m2 = ey2; m3 = ey3; p1 = g.x1; p2 = g.x2; p3 = g.x3;
+        k1 = ex1 * (cf - g.y1); k2 = ex2 * (cf - g.y2); k3 = ex3 * (cf - g.y3);
       }
+    };
+    const int ix = FY ? srow0 : f, iy = FY ? f : srow0;
+    enter(seed_lookup(a.seed, a.ncx, a.ncy, ix, iy, a.num_tri));
+    int r = 0, it = 0, iters = 0;
+    while (r < nrows) {
+      const R cv = saxis[r];
+      // cross_i = (x_b-x_a)*(ty-y_a) - (y_b-y_a)*(tx-x_a)   (triangle_walk.f90:149-150) evaluated as
+      // m_i*(cv-p_i) - k_i (fast axis x: m = x_b-x_a, p = y_a, k = (y_b-y_a)*(tx-x_a)) or k_i - m_i*(cv-p_i)
+      // (fast axis y): the reference's operations in the reference's order, with the product that does not
+      // depend on the row computed once per (triangle, column) -- the rounded results are identical
+      const R t1 = cv - p1, t2 = cv - p2, t3 = cv - p3;
+      const R x1 = FY ? k1 - m1 * t1 : m1 * t1 - k1;
+      const R x2 = FY ? k2 - m2 * t2 : m2 * t2 - k2;
+      const R x3 = FY ? k3 - m3 * t3 : m3 * t3 - k3;
+      ++it;
+      // first failing edge wins (:57-60); edge i -> neighbour opposite vertex i-1 (wrap) (:66-71)
+      const bool o1 = x1 < margin, o2 = x2 < margin, o3 = x3 < margin;
+      const bool outside = o1 | o2 | o3;
+      const int nxt = o1 ? n3 : (o2 ? n1 : n2);
+      if (outside && nxt >= 0) {
+        if (it < a.iter_cap) { enter(nxt); continue; }
+        raise_status(a.status, GI_ERR_ITER_CAP);
+      }
+      // resolved: inside `tri`, or outside the hull (:74-80: the last valid triangle is kept)
+      stri[r][tid] = outside ? ~tri : tri;
+      iters += it;
+      it = 0;
+      ++r;
+    }
+    iters_sum = iters;
+  }
+  __syncthreads();
+
+  // ---- phase 2: evaluate -----------------------------------------------------------------------
+  const bool f_in_band = active && f >= a.bf0 && f < a.bf1;
+  const int wpr = (w.nf() + 31) >> 5;
+  const int bnf = a.bf1 - a.bf0;
+#pragma unroll 2
+  for (int r = 0; r < nrows; ++r) {
+    const int s = srow0 + r;
+    const int t = active ? stri[r][tid] : 0;
+    const bool inside = t >= 0;
+    if (f_in_band && s >= a.bs0 && s < a.bs1) {
+      const int64_t o = (int64_t)(s - a.bs0) * bnf + (f - a.bf0);
+      if (inside) {
+        const EvalRec<R> v = a.vals[t];
+        const R cv = saxis[r];
+        a.out[o] = eval_value(v, FY ? cv : cf, FY ? cf : cv);
+      }
+      if (a.tri_out) a.tri_out[o] = (inside ? t : ~t) + 1;
     }
     const unsigned m = __ballot_sync(0xffffffffu, active && !inside);
-    if ((threadIdx.x & 31) == 0 && (lane_f >> 5) < wpr)
-      a.mask_words[(int64_t)(s - w.s0) * wpr + (lane_f >> 5)] = m;
+    if (lane == 0 && (lane_f >> 5) < wpr) {
+      const int64_t wi = (int64_t)(s - w.s0) * wpr + (lane_f >> 5);
+      a.mask_words[wi] = m;
+      if (m) a.nz_words[atomicAdd((unsigned long long*)(a.counters + 4), 1ull)] = (int)wi;
+    }
   }
   // one atomic per warp for the iteration counter (iters_tot, interpolation.f90:374)
   for (int off = 16; off > 0; off >>= 1) iters_sum += __shfl_down_sync(0xffffffffu, iters_sum, off);
-  if ((threadIdx.x & 31) == 0 && iters_sum)
-    atomicAdd((unsigned long long*)a.counters, (unsigned long long)iters_sum);
+  if (lane == 0 && iters_sum) atomicAdd((unsigned long long*)a.counters, (unsigned long long)iters_sum);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -222,15 +351,16 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const WalkArgs<R> a)
 template <class R> struct FillArgs {
   TargetWindow<R> win;  // window E covered by the bit mask
   const uint32_t* mask_words;
+  const int* nz_words;     // indices of the non-zero mask words, counters[4] of them
   int bf0, bf1, bs0, bs1;  // band B inside E (cells to fill, and where `out` lives)
   R* out;
   int64_t* fill_src;  // optional, band-shaped
-  int64_t* counters;  // [1] += masked cells, [2] = max level
+  int64_t* counters;  // [1] += masked cells, [2] = max level, [4] = number of nz_words
   int len_x, len_y;
   // to recompute the value of a source cell that lies in the halo (outside the band); geom == nullptr for
   // the standalone fill (no halo there)
   const TriGeom<R>* geom;
-  const TriVals<R>* vals;
+  const EvalRec<R>* vals;
   const int* seed;
   int ncx, ncy, num_tri, iter_cap;
   int* status;
@@ -256,16 +386,16 @@ __device__ __forceinline__ int isqrt_floor(int v) {  // floor(sqrt(v)) for v >= 
 template <class R>
 __global__ void __launch_bounds__(128) fill_kernel(const FillArgs<R> a) {
   const int nf = a.win.nf(), wpr = (nf + 31) >> 5;
-  const int64_t num_words = (int64_t)wpr * a.win.ns();
+  const int64_t num_words = a.counters[4];
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t num_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   int level_max = 0;
   long long masked = 0;
   const int level_cap = a.len_x + a.len_y;
-  for (int64_t wi = warp0; wi < num_words; wi += num_warps) {
+  for (int64_t li = warp0; li < num_words; li += num_warps) {
+    const int64_t wi = a.nz_words[li];
     const uint32_t wd = __ldg(a.mask_words + wi);
-    if (wd == 0) continue;
     const int s = a.win.s0 + (int)(wi / wpr), f = a.win.f0 + (int)(wi % wpr) * 32 + lane;
     if (!((wd >> lane) & 1u)) continue;
     if (f < a.bf0 || f >= a.bf1 || s < a.bs0 || s >= a.bs1) continue;  // halo cell: not ours to fill
@@ -317,7 +447,7 @@ __global__ void __launch_bounds__(128) fill_kernel(const FillArgs<R> a) {
       bool inside; int iters; TriGeom<R> g;
       const int tri = walk(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, best_j, best_i, a.num_tri), tx, ty,
                            a.iter_cap, inside, iters, g, a.status);
-      v = barycentric_value(g, a.vals[tri], tx, ty);
+      v = eval_value(a.vals[tri], tx, ty);
     }
     const int64_t o = (int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0);
     a.out[o] = v;                                                  // :121
@@ -349,12 +479,17 @@ __global__ void expand_mask_kernel(const uint32_t* __restrict__ mask_words, int 
 
 // standalone fill on a caller-supplied byte mask: pack it into the bit mask first
 __global__ void bytes_to_bits_kernel(const uint8_t* __restrict__ mask, int nf, int wpr,
-                                     uint32_t* __restrict__ words) {
+                                     uint32_t* __restrict__ words, int* __restrict__ nz_words,
+                                     int64_t* __restrict__ counters) {
   const int lane_f = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = blockIdx.y;
   const bool m = lane_f < nf && mask[(int64_t)s * nf + lane_f] != 0;
   const unsigned b = __ballot_sync(0xffffffffu, m);
-  if ((threadIdx.x & 31) == 0 && (lane_f >> 5) < wpr) words[(int64_t)s * wpr + (lane_f >> 5)] = b;
+  if ((threadIdx.x & 31) == 0 && (lane_f >> 5) < wpr) {
+    const int64_t wi = (int64_t)s * wpr + (lane_f >> 5);
+    words[wi] = b;
+    if (b) nz_words[atomicAdd((unsigned long long*)(counters + 4), 1ull)] = (int)wi;
+  }
 }
 
 }  // namespace
@@ -381,15 +516,15 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
 
   // ---- 1. pack the mesh ---------------------------------------------------------------------
   ph.mark("pack_mesh");
-  TriGeom<R>* geom; TriVals<R>* vals; SeedGrid<R>* sg; int* seed; int64_t* counters;
+  TriGeom<R>* geom; EvalRec<R>* vals; SeedGrid<R>* sg; int* seed; int64_t* counters; int* nz_words;
   GI_TRY(scr.alloc(&geom, (size_t)num_tri));
   GI_TRY(scr.alloc(&vals, (size_t)num_tri));
   GI_TRY(scr.alloc(&sg, 1));
   const int ncx = (len_x + kSeedCell - 1) / kSeedCell, ncy = (len_y + kSeedCell - 1) / kSeedCell;
   GI_TRY(scr.alloc(&seed, (size_t)ncx * ncy));
-  GI_TRY(scr.alloc(&counters, 4));
+  GI_TRY(scr.alloc(&counters, 8));
   GI_CUDA(cudaMemsetAsync(seed, 0x7f, sizeof(int) * (size_t)ncx * ncy, st));
-  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4, st));
+  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 8, st));
   seed_setup_kernel<R><<<1, 1, 0, st>>>(x_axis, len_x, y_axis, len_y, sg);
   pack_mesh_kernel<R><<<div_up(num_tri, 256), 256, 0, st>>>(
       points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR), data_in,
@@ -411,15 +546,24 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
   }
   const int nf = wa.win.nf(), ns = wa.win.ns(), wpr = (nf + 31) >> 5;
   uint32_t* mask_words;
+  GI_REQUIRE((int64_t)wpr * ns < (int64_t)0x7fffffff, "window too large");
   GI_TRY(scr.alloc(&mask_words, (size_t)wpr * ns));
+  GI_TRY(scr.alloc(&nz_words, (size_t)wpr * ns));
+  wa.nz_words = nz_words;
   wa.geom = geom; wa.vals = vals; wa.seed = seed; wa.ncx = ncx; wa.ncy = ncy; wa.num_tri = num_tri;
   wa.iter_cap = num_tri + 16;
   wa.out = data_ip; wa.tri_out = tri_out; wa.mask_words = mask_words; wa.counters = counters;
   wa.status = slot.dev;
   {
-    dim3 grid(div_up(nf, kWalkThreads), div_up(ns, kWalkRows));
-    GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
-    walk_kernel<R><<<grid, kWalkThreads, 0, st>>>(wa);
+    {
+      // 128 columns x 32 rows per CTA, >= 8 CTAs per SM (64 registers): the best of the variants measured in
+      // round 1 (profiles/r01_walk_variants.md)
+      constexpr int kRows = 32;
+      dim3 grid(div_up(nf, kWalkThreads), div_up(ns, kRows));
+      GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
+      if (rowmajor) locate_eval_kernel<R, false, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
+      else locate_eval_kernel<R, true, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
+    }
     GI_CUDA(cudaGetLastError());
   }
   if (mask_out || fill_src) {
@@ -431,7 +575,7 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
   // ---- 3. hull fill ---------------------------------------------------------------------------
   ph.mark("fill");
   FillArgs<R> fa;
-  fa.win = wa.win; fa.mask_words = mask_words;
+  fa.win = wa.win; fa.mask_words = mask_words; fa.nz_words = nz_words;
   fa.bf0 = wa.bf0; fa.bf1 = wa.bf1; fa.bs0 = wa.bs0; fa.bs1 = wa.bs1;
   fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters; fa.len_x = len_x; fa.len_y = len_y;
   fa.geom = geom; fa.vals = vals; fa.seed = seed; fa.ncx = ncx; fa.ncy = ncy; fa.num_tri = num_tri;
@@ -459,18 +603,19 @@ int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* 
   fa.win = rowmajor ? TargetWindow<R>{nullptr, nullptr, len_x, len_y, 0, len_x, 0, len_y, 0}
                     : TargetWindow<R>{nullptr, nullptr, len_y, len_x, 0, len_y, 0, len_x, 1};
   const int nf = fa.win.nf(), ns = fa.win.ns(), wpr = (nf + 31) >> 5;
-  uint32_t* words; int64_t* counters;
+  uint32_t* words; int64_t* counters; int* nz_words;
   GI_TRY(scr.alloc(&words, (size_t)wpr * ns));
-  GI_TRY(scr.alloc(&counters, 4));
-  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4, st));
+  GI_TRY(scr.alloc(&nz_words, (size_t)wpr * ns));
+  GI_TRY(scr.alloc(&counters, 8));
+  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 8, st));
   GI_REQUIRE(ns <= 65535, "grid too large for the standalone fill");
-  bytes_to_bits_kernel<<<dim3(div_up(nf, 128), ns), 128, 0, st>>>(mask, nf, wpr, words);
+  bytes_to_bits_kernel<<<dim3(div_up(nf, 128), ns), 128, 0, st>>>(mask, nf, wpr, words, nz_words, counters);
   GI_CUDA(cudaGetLastError());
   if (fill_src) {
     expand_mask_kernel<<<kNumSMs * 8, 256, 0, st>>>(words, wpr, 0, 0, 0, nf, 0, ns, nullptr, fill_src);
     GI_CUDA(cudaGetLastError());
   }
-  fa.mask_words = words; fa.bf0 = 0; fa.bf1 = nf; fa.bs0 = 0; fa.bs1 = ns;
+  fa.mask_words = words; fa.nz_words = nz_words; fa.bf0 = 0; fa.bf1 = nf; fa.bs0 = 0; fa.bs1 = ns;
   fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters; fa.len_x = len_x; fa.len_y = len_y;
   fa.geom = nullptr; fa.vals = nullptr; fa.seed = nullptr; fa.ncx = fa.ncy = fa.num_tri = fa.iter_cap = 0;
   fa.status = slot.dev;

@@ -75,10 +75,11 @@ def test_no_silent_cpu_fallback():
 
 
 def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package may import, link or call it."""
     pkg = os.path.join(ROOT, "grid_interpolation_b200")
+    bad = re.compile(r"import\s+oracle|from\s+oracle|from\s+\.\.?oracle|liboracle|orc_[a-z_]+\s*\(|oracle[/\\]")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in text.replace("the oracle", "").replace("oracle's", "") or f in (), \
-                    f"{f} mentions the oracle"
+                assert not bad.search(text), f"{f} references the oracle"
