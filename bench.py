@@ -304,7 +304,7 @@ def main():
         except Exception:
             pass
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "walk_kernel<double>", "kernel_ms": walk_ms, "peak_source": peak_src,
+                "traffic": traffic, "kernel": "locate_eval_kernel<double>", "kernel_ms": walk_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg}
 
     cpu = None

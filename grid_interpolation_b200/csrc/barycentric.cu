@@ -7,11 +7,10 @@
 //   triangle_walk.f90:90-132    fill_nearest_neighbour (nearest unmasked cell in index space)
 //
 // B200 design (not a port):
-//   1. pack_mesh_kernel    gathers every triangle into two aligned records: a 64 B WALK record (3 vertices +
-//      3 neighbour ids = two 32 B sectors, so a walk step is one aligned load instead of 3 index loads + 6
-//      scattered coordinate loads) and a 96 B EVALUATION record (everything of interpolation.f90:385-398 that
-//      depends on the triangle only, including the refined reciprocal of the denominator).  The same pass
-//      bins one triangle id per 16x16-target cell (atomicMin -> deterministic) into a seed grid.
+//   1. pack_mesh_kernel    gathers every triangle into ONE aligned 96 B record: sectors 0-1 hold the 3 vertices +
+//      3 neighbour ids (a walk step is two 256-bit loads instead of 3 index loads + 6 scattered coordinate
+//      loads), sector 2 the 3 nodal values.  The same pass bins one triangle id per 16x16-target cell
+//      (atomicMin -> deterministic) into a seed grid.
 //   2. locate_eval_kernel  a CTA owns 128 columns x 32 rows of targets.  Phase 1 (locate): one thread per
 //      column walks down the rows; the triangle found for row r seeds row r+1 (the reference chains along a
 //      grid row in the same way, interpolation.f90:366-373, but restarts every row from one global start
@@ -19,17 +18,17 @@
 //      path-independent outside the 1e-10 margin band, so the seeding changes the iteration
 //      count, not the result.  Lanes are decoupled (each runs its own test / move loop) and keep the
 //      (triangle, column)-invariant half of every orientation product in registers, so a target in the same
-//      triangle as the one above it costs no memory access.  Phase 2 (evaluate): row-synchronous, uniform,
-//      128 consecutive doubles per row stored coalesced; outside-hull flags go into a 1-bit-per-target mask
-//      (one ballot per warp row) and the non-zero mask words into a compact work list.
+//      triangle as the one above it costs no memory access.  Phase 2 (evaluate): row-synchronous; the record
+//      (L1-resident after phase 1) is re-read only when the column enters another triangle, the two
+//      quotients of interpolation.f90:387-394 share one refined reciprocal, 128 consecutive doubles per row
+//      are stored coalesced; outside-hull flags go into a 1-bit-per-target mask (one ballot per warp row)
+//      and the non-zero mask words into a compact work list.
 //   3. fill_kernel         one warp per non-zero mask word, one lane per masked cell: exact ring search over
 //      the bit mask with the reference's tie-break (smallest squared index distance, then smallest row,
 //      then smallest column).
 //
 // All index decisions (orientation signs, first failing edge) and all values use the reference's operations
 // in the reference's order with FMA contraction disabled (-fmad=false): bit-identical to the oracle.
-#include <cstdlib>
-
 #include "kernels.cuh"
 
 namespace gi {
@@ -39,21 +38,47 @@ namespace {
 constexpr int kSeedCell = 16;      // targets per seed-grid cell edge
 constexpr int kWalkThreads = 128;  // columns per CTA
 
-template <class R> struct alignas(16) TriGeom {  // f64: 64 B = 2 sectors
+// One record per triangle, f64: 96 B = 3 sectors, 32 B aligned.  Sectors 0-1 are what a walk step needs (3
+// vertices + 3 neighbour ids), sector 2 holds the nodal values for the barycentric value.
+template <class R> struct alignas(sizeof(R) == 8 ? 32 : 16) TriGeom {
   R x1, y1, x2, y2, x3, y3;
   int n1, n2, n3;  // neighbour opposite vertex 1/2/3, 0-based, -1 = hull edge
   int pad;
-};
-// Everything the barycentric value needs that depends on the triangle only (interpolation.f90:385-398):
-// A = y2-y3, B = x3-x2, C = y3-y1, D = x1-x3, denom = A*D + B*(y1-y3), r2 = refined reciprocal of denom
-// (see DivRcp), nodal values d1..d3.  f64: 96 B = 3 sectors.
-template <class R> struct alignas(16) EvalRec {
-  R x3, y3, A, B, C, D, denom, r2, d1, d2, d3, pad;
+  R d1, d2, d3, padv;
 };
 template <class R> struct SeedGrid {
   R x0, y0, inv_cell_x, inv_cell_y;
   int ncx, ncy;
 };
+
+// Record loads.  The kernels below are bound by L1 data-pipe wavefronts (ncu: l1tex__data_pipe_lsu_wavefronts
+// 75 % of peak with 128-bit loads): every lane fetches its own record, so one warp-wide load costs one wavefront
+// per distinct cache line.  sm_100 has 256-bit global loads (LDG.E.ENL2.256): a 64 B walk record is 2 loads
+// instead of 4, a 96 B evaluation record 3 instead of 6.
+__device__ __forceinline__ void ld256(const void* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+// walk part (sectors 0-1) of a record
+__device__ __forceinline__ void load_walk(const TriGeom<double>* p, TriGeom<double>& g) {
+  double n12, w;
+  ld256(p, g.x1, g.y1, g.x2, g.y2);
+  ld256(reinterpret_cast<const char*>(p) + 32, g.x3, g.y3, n12, w);
+  g.n1 = __double2loint(n12); g.n2 = __double2hiint(n12);
+  g.n3 = __double2loint(w); g.pad = 0;
+}
+__device__ __forceinline__ void load_walk(const TriGeom<float>* p, TriGeom<float>& g) { g = *p; }
+// nodal values (sector 2)
+__device__ __forceinline__ void load_values(const TriGeom<double>* p, TriGeom<double>& g) {
+  ld256(reinterpret_cast<const char*>(p) + 64, g.d1, g.d2, g.d3, g.padv);
+}
+__device__ __forceinline__ void load_values(const TriGeom<float>*, TriGeom<float>&) {}
+// Fire-and-forget load of sector 2: the registers are never read, so nothing waits on it, but the sector is in
+// L1 when phase 2 asks for it a few thousand cycles later (prefetch.global.L1 had no measurable effect).
+__device__ __forceinline__ void touch_values(const TriGeom<double>* p) {
+  double a, b, c, d;
+  ld256(reinterpret_cast<const char*>(p) + 64, a, b, c, d);
+}
+__device__ __forceinline__ void touch_values(const TriGeom<float>*) {}
 
 // ---------------------------------------------------------------------------------------------
 // IEEE-exact division with a reusable reciprocal.
@@ -61,8 +86,8 @@ template <class R> struct SeedGrid {
 // nvcc expands a double-precision `n / d` into: seed r0 = MUFU.RCP64H(d) (low word 1), two Newton steps
 // -> r2, then q0 = n*r2, rem = fma(-d,q0,n), q = fma(r2,rem,q0), plus a range check that diverts
 // denormal / huge operands to a slow path (SASS of this file, round-1 notes in DESIGN.md).  r2 depends only
-// on d, and both barycentric quotients of a target -- and of every other target in the same triangle --
-// share d = denom (interpolation.f90:385-394).  DivRcp reproduces that instruction sequence verbatim, so
+// on d, and both barycentric quotients of a target -- and of every later target of the column in the same
+// triangle -- share d = denom (interpolation.f90:385-394).  DivRcp reproduces that instruction sequence verbatim, so
 // quotient() returns the correctly rounded IEEE quotient, bit-identical to the `/` operator (and so to the
 // oracle); operands outside the fast path's range take the `/` operator itself.
 // ---------------------------------------------------------------------------------------------
@@ -114,8 +139,7 @@ __global__ void seed_setup_kernel(const R* x_axis, int len_x, const R* y_axis, i
 template <class R>
 __global__ void __launch_bounds__(256)
 pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, TopoView nbr, int num_points,
-                 int num_tri, TriGeom<R>* __restrict__ geom, EvalRec<R>* __restrict__ vals,
-                 int* __restrict__ seed, const SeedGrid<R>* __restrict__ sgp, int* __restrict__ status) {
+                 int num_tri, TriGeom<R>* __restrict__ geom, int* __restrict__ seed, const SeedGrid<R>* __restrict__ sgp, int* __restrict__ status) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= num_tri) return;
   const SeedGrid<R> sg = *sgp;
@@ -135,17 +159,9 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
   g.x3 = pts.x(c - 1); g.y3 = pts.y(c - 1);
   g.n1 = n1 - 1; g.n2 = n2 - 1; g.n3 = n3 - 1;
   g.pad = 0;
+  g.d1 = __ldg(data + (a - 1)); g.d2 = __ldg(data + (b - 1)); g.d3 = __ldg(data + (c - 1));
+  g.padv = R(0);
   geom[t] = g;
-  EvalRec<R> v;
-  v.x3 = g.x3; v.y3 = g.y3;
-  v.A = g.y2 - g.y3; v.B = g.x3 - g.x2; v.C = g.y3 - g.y1; v.D = g.x1 - g.x3;
-  v.denom = v.A * v.D + v.B * (g.y1 - g.y3);
-  DivRcp<R> dv;
-  dv.set(v.denom);
-  v.r2 = dv.r2;
-  v.d1 = __ldg(data + (a - 1)); v.d2 = __ldg(data + (b - 1)); v.d3 = __ldg(data + (c - 1));
-  v.pad = R(0);
-  vals[t] = v;
   if (bad) return;
   // seed grid: cell of the centroid under a uniform-axis approximation (a heuristic: it only has to be near)
   const R cx = (g.x1 + g.x2 + g.x3) / R(3), cy = (g.y1 + g.y2 + g.y3) / R(3);
@@ -203,23 +219,23 @@ __device__ __forceinline__ int walk(const TriGeom<R>* __restrict__ geom, int tri
   return tri;
 }
 
-// interpolation.f90:385-398, same operation order; the two divisions share the triangle's reciprocal.
+// interpolation.f90:385-398, same operation order; the two divisions share the reciprocal of denom.
 template <class R>
-__device__ __forceinline__ R eval_value(const EvalRec<R>& v, R tx, R ty) {
-  const R u = tx - v.x3, t = ty - v.y3;
+__device__ __forceinline__ R eval_value(const TriGeom<R>& g, R tx, R ty) {
+  const R A = g.y2 - g.y3, B = g.x3 - g.x2, C = g.y3 - g.y1, D = g.x1 - g.x3;
   DivRcp<R> dv;
-  dv.d = v.denom; dv.r2 = v.r2;
-  const R w1 = dv.quotient(v.A * u + v.B * t);
-  const R w2 = dv.quotient(v.C * u + v.D * t);
+  dv.set(A * D + B * (g.y1 - g.y3));
+  const R u = tx - g.x3, t = ty - g.y3;
+  const R w1 = dv.quotient(A * u + B * t);
+  const R w2 = dv.quotient(C * u + D * t);
   const R w3 = R(1) - w1 - w2;
-  return v.d1 * w1 + v.d2 * w2 + v.d3 * w3;
+  return g.d1 * w1 + g.d2 * w2 + g.d3 * w3;
 }
 
 template <class R> struct WalkArgs {
   TargetWindow<R> win;   // walked window E (band + halo)
   int bf0, bf1, bs0, bs1;  // band B inside E: the part that is written to `out`
   const TriGeom<R>* geom;
-  const EvalRec<R>* vals;
   const int* seed;
   int ncx, ncy, num_tri, iter_cap;
   R* out;               // band-shaped: (bs1-bs0) slow rows of (bf1-bf0)
@@ -268,9 +284,12 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   if (active) {
     int tri, n1, n2, n3;
     R m1, m2, m3, p1, p2, p3, k1, k2, k3;
+    bool fresh;  // no target resolved in `tri` yet
     auto enter = [&](int t) {  // make `t` the current triangle: one 64 B load + 12 flops
       tri = t;
-      const TriGeom<R> g = a.geom[t];
+      fresh = true;
+      TriGeom<R> g;
+      load_walk(a.geom + t, g);
       n1 = g.n1; n2 = g.n2; n3 = g.n3;
       const R ex1 = g.x2 - g.x1, ey1 = g.y2 - g.y1;   // edge (v1,v2)
       const R ex2 = g.x3 - g.x2, ey2 = g.y3 - g.y2;   // edge (v2,v3)
@@ -306,6 +325,10 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
         raise_status(a.status, GI_ERR_ITER_CAP);
       }
       // resolved: inside `tri`, or outside the hull (:74-80: the last valid triangle is kept)
+      if (fresh && !outside) {  // phase 2 will want this triangle's nodal values: pull the sector into L1 now
+        touch_values(a.geom + tri);
+        fresh = false;
+      }
       stri[r][tid] = outside ? ~tri : tri;
       iters += it;
       it = 0;
@@ -316,10 +339,16 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   __syncthreads();
 
   // ---- phase 2: evaluate -----------------------------------------------------------------------
+  // Row-synchronous.  The evaluation record is fetched only when the column enters another triangle (about one
+  // row in four); what depends on (triangle, column) only -- A*(tx-x3), C*(tx-x3) for fast axis x -- is kept in
+  // registers, the row-dependent half of interpolation.f90:387-394 is evaluated per target.
   const bool f_in_band = active && f >= a.bf0 && f < a.bf1;
   const int wpr = (w.nf() + 31) >> 5;
   const int bnf = a.bf1 - a.bf0;
-#pragma unroll 2
+  int cur = -1;
+  R c1 = 0, q1 = 0, c2 = 0, q2 = 0, p3 = 0, d1 = 0, d2 = 0, d3 = 0;
+  DivRcp<R> dv;
+  dv.d = R(1); dv.r2 = R(1);
   for (int r = 0; r < nrows; ++r) {
     const int s = srow0 + r;
     const int t = active ? stri[r][tid] : 0;
@@ -327,9 +356,23 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
     if (f_in_band && s >= a.bs0 && s < a.bs1) {
       const int64_t o = (int64_t)(s - a.bs0) * bnf + (f - a.bf0);
       if (inside) {
-        const EvalRec<R> v = a.vals[t];
-        const R cv = saxis[r];
-        a.out[o] = eval_value(v, FY ? cv : cf, FY ? cf : cv);
+        if (t != cur) {  // records were touched by phase 1: L1 hits
+          TriGeom<R> g;
+          load_walk(a.geom + t, g);
+          load_values(a.geom + t, g);
+          cur = t;
+          const R A = g.y2 - g.y3, B = g.x3 - g.x2, C = g.y3 - g.y1, D = g.x1 - g.x3;
+          dv.set(A * D + B * (g.y1 - g.y3));                        // denom (:385-386)
+          d1 = g.d1; d2 = g.d2; d3 = g.d3;
+          if (!FY) { const R u = cf - g.x3; c1 = A * u; q1 = B; c2 = C * u; q2 = D; p3 = g.y3; }
+          else { const R u = cf - g.y3; c1 = B * u; q1 = A; c2 = D * u; q2 = C; p3 = g.x3; }
+        }
+        // w1 = (A*(tx-x3) + B*(ty-y3))/denom, w2 = (C*(tx-x3) + D*(ty-y3))/denom   (:387-394); the sum commutes
+        const R t3 = saxis[r] - p3;
+        const R w1 = dv.quotient(FY ? q1 * t3 + c1 : c1 + q1 * t3);
+        const R w2 = dv.quotient(FY ? q2 * t3 + c2 : c2 + q2 * t3);
+        const R w3 = R(1) - w1 - w2;
+        a.out[o] = d1 * w1 + d2 * w2 + d3 * w3;                   // :396-398
       }
       if (a.tri_out) a.tri_out[o] = (inside ? t : ~t) + 1;
     }
@@ -360,7 +403,6 @@ template <class R> struct FillArgs {
   // to recompute the value of a source cell that lies in the halo (outside the band); geom == nullptr for
   // the standalone fill (no halo there)
   const TriGeom<R>* geom;
-  const EvalRec<R>* vals;
   const int* seed;
   int ncx, ncy, num_tri, iter_cap;
   int* status;
@@ -447,7 +489,7 @@ __global__ void __launch_bounds__(128) fill_kernel(const FillArgs<R> a) {
       bool inside; int iters; TriGeom<R> g;
       const int tri = walk(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, best_j, best_i, a.num_tri), tx, ty,
                            a.iter_cap, inside, iters, g, a.status);
-      v = eval_value(a.vals[tri], tx, ty);
+      v = eval_value(g, tx, ty);
     }
     const int64_t o = (int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0);
     a.out[o] = v;                                                  // :121
@@ -516,9 +558,8 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
 
   // ---- 1. pack the mesh ---------------------------------------------------------------------
   ph.mark("pack_mesh");
-  TriGeom<R>* geom; EvalRec<R>* vals; SeedGrid<R>* sg; int* seed; int64_t* counters; int* nz_words;
+  TriGeom<R>* geom; SeedGrid<R>* sg; int* seed; int64_t* counters; int* nz_words;
   GI_TRY(scr.alloc(&geom, (size_t)num_tri));
-  GI_TRY(scr.alloc(&vals, (size_t)num_tri));
   GI_TRY(scr.alloc(&sg, 1));
   const int ncx = (len_x + kSeedCell - 1) / kSeedCell, ncy = (len_y + kSeedCell - 1) / kSeedCell;
   GI_TRY(scr.alloc(&seed, (size_t)ncx * ncy));
@@ -529,7 +570,7 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
   pack_mesh_kernel<R><<<div_up(num_tri, 256), 256, 0, st>>>(
       points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR), data_in,
       topo_t3(simplices, num_tri, flags & GI_TOPO_ROWMAJOR), topo_t3(neighbours, num_tri, flags & GI_TOPO_ROWMAJOR),
-      num_points, num_tri, geom, vals, seed, sg, slot.dev);
+      num_points, num_tri, geom, seed, sg, slot.dev);
   GI_CUDA(cudaGetLastError());
 
   // ---- 2. walk + barycentric over the band plus halo rows -------------------------------------
@@ -550,22 +591,20 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
   GI_TRY(scr.alloc(&mask_words, (size_t)wpr * ns));
   GI_TRY(scr.alloc(&nz_words, (size_t)wpr * ns));
   wa.nz_words = nz_words;
-  wa.geom = geom; wa.vals = vals; wa.seed = seed; wa.ncx = ncx; wa.ncy = ncy; wa.num_tri = num_tri;
+  wa.geom = geom; wa.seed = seed; wa.ncx = ncx; wa.ncy = ncy; wa.num_tri = num_tri;
   wa.iter_cap = num_tri + 16;
   wa.out = data_ip; wa.tri_out = tri_out; wa.mask_words = mask_words; wa.counters = counters;
   wa.status = slot.dev;
   {
-    {
-      // 128 columns x 32 rows per CTA, >= 8 CTAs per SM (64 registers): the best of the variants measured in
-      // round 1 (profiles/r01_walk_variants.md)
+      // 128 columns x 32 rows per CTA, 64 registers, >= 8 CTAs per SM: the best of the shapes measured in round 1
+      // (profiles/r01_walk_variants.md)
       constexpr int kRows = 32;
       dim3 grid(div_up(nf, kWalkThreads), div_up(ns, kRows));
       GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
       if (rowmajor) locate_eval_kernel<R, false, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
       else locate_eval_kernel<R, true, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
+      GI_CUDA(cudaGetLastError());
     }
-    GI_CUDA(cudaGetLastError());
-  }
   if (mask_out || fill_src) {
     expand_mask_kernel<<<kNumSMs * 8, 256, 0, st>>>(mask_words, wpr, wa.win.f0, wa.win.s0, wa.bf0, wa.bf1, wa.bs0,
                                                    wa.bs1, mask_out, fill_src);
@@ -578,7 +617,7 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
   fa.win = wa.win; fa.mask_words = mask_words; fa.nz_words = nz_words;
   fa.bf0 = wa.bf0; fa.bf1 = wa.bf1; fa.bs0 = wa.bs0; fa.bs1 = wa.bs1;
   fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters; fa.len_x = len_x; fa.len_y = len_y;
-  fa.geom = geom; fa.vals = vals; fa.seed = seed; fa.ncx = ncx; fa.ncy = ncy; fa.num_tri = num_tri;
+  fa.geom = geom; fa.seed = seed; fa.ncx = ncx; fa.ncy = ncy; fa.num_tri = num_tri;
   fa.iter_cap = wa.iter_cap; fa.status = slot.dev;
   fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
   GI_CUDA(cudaGetLastError());
@@ -617,7 +656,7 @@ int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* 
   }
   fa.mask_words = words; fa.nz_words = nz_words; fa.bf0 = 0; fa.bf1 = nf; fa.bs0 = 0; fa.bs1 = ns;
   fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters; fa.len_x = len_x; fa.len_y = len_y;
-  fa.geom = nullptr; fa.vals = nullptr; fa.seed = nullptr; fa.ncx = fa.ncy = fa.num_tri = fa.iter_cap = 0;
+  fa.geom = nullptr; fa.seed = nullptr; fa.ncx = fa.ncy = fa.num_tri = fa.iter_cap = 0;
   fa.status = slot.dev;
   fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
   GI_CUDA(cudaGetLastError());
