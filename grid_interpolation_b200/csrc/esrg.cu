@@ -15,13 +15,20 @@
 //             atomic scatter is not, so cells holding more than one point are insertion-sorted afterwards.
 //             Coordinates, values and ids are then gathered into cell order so the query reads them
 //             contiguously.
-//   query     one thread per grid target, register-resident top-k (topk.cuh).  A frame's top and bottom
-//             rows are contiguous in the CSR (key = iy*len_x + ix), so each costs two offset reads and one
-//             contiguous run of points.  The reference's two fixed 1000-entry candidate lists
-//             (query_esrg.f90:119-121) become one small in-place deferred list per thread; when it
-//             overflows the thread switches to an exact list-free mode that re-scans the inner frames with
-//             the predicate "was deferred at the previous level" (d2 > r2_prev), which reproduces the
-//             reference's processing order and therefore its tie behaviour for any point density.
+//   query     one thread per grid target, two kernels:
+//             esrg_fast_kernel   The reference's result is "the k smallest d2 among the points of the
+//               (2L+1)^2 window, L = first level at which k points lie within r_L = spac*(L+1/2)"
+//               (query_esrg.f90:141,159-169,178-181); its candidate lists only decide the order
+//               among EQUAL d2.  So the fast kernel keeps no list at all: it scans frame after frame, keeps
+//               the k smallest d2 seen in registers and stops when the k-th is <= r_L^2.  A frame's top and
+//               bottom rows are contiguous runs of the CSR (key = iy*len_x + ix).  Whenever a candidate's d2
+//               equals a kept one (the only case in which processing order matters) the target is handed to
+//             esrg_query_kernel  which follows the reference's processing order exactly (carried candidates
+//               first, then the frame in scan order, ties inserted before equal entries).  The reference's
+//               two fixed 1000-entry candidate lists (query_esrg.f90:119-121) are one small in-place
+//               deferred list per thread; when it overflows the thread switches to a list-free mode that
+//               re-scans the inner frames with the predicate "was deferred at the previous level"
+//               (d2 > r2_prev), which yields the same order for any point density.
 #include "kernels.cuh"
 #include "scan.cuh"
 #include "topk.cuh"
@@ -108,16 +115,22 @@ template <class R> struct EsrgArgs {
   R* out;                 // window-shaped
   int32_t* nn_index;      // optional (window, k)
   R* nn_dist2;            // optional
-  int64_t* counters;      // [0] cells scanned, [1] max level, [2] list overflows
+  int64_t* counters;      // [0] cells scanned, [1] max level, [2] list overflows, [3] targets sent to the exact kernel
   int* status;
+  int* todo;              // window-linear ids of the targets the exact kernel must do (filled by the fast kernel)
+  int64_t* todo_count;
+  int all_exact;          // debug: the fast kernel hands every target over
+  int stats;              // update counters[0..2] (debug: one atomic per target)
 };
 
 template <class R, int KC>
 __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
   const TargetWindow<R>& w = a.win;
-  const int f = w.f0 + blockIdx.x * 32 + (threadIdx.x & 31);
-  const int s = w.s0 + blockIdx.y * 4 + (threadIdx.x >> 5);
-  if (f >= w.f1 || s >= w.s1) return;
+  const int64_t n_todo = *a.todo_count;
+  for (int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; li < n_todo; li += (int64_t)gridDim.x * blockDim.x) {
+  const int lin = a.todo[li];
+  const int f = w.f0 + lin % w.nf();
+  const int s = w.s0 + lin / w.nf();
   const int ix = w.fast_is_y ? s : f, iy = w.fast_is_y ? f : s;
   const int len_x = a.len_x, len_y = a.len_y;
   const R cx = __ldg((w.fast_is_y ? w.slow_axis : w.fast_axis) + ix);     // query_esrg.f90:133-134
@@ -230,11 +243,280 @@ __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
   }
   a.out[o] = (first_dist <= Consts<R>::tiny_e4()) ? first_val : numerator / denominator;
 
-  if (a.counters) {
+  if (a.stats) {
     atomicAdd((unsigned long long*)a.counters, (unsigned long long)cells_scanned);
     atomicMax((unsigned long long*)(a.counters + 1), (unsigned long long)level);
     if (overflows) atomicAdd((unsigned long long*)(a.counters + 2), (unsigned long long)overflows);
   }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast kernel (see file header)
+// ---------------------------------------------------------------------------------------------
+template <class R, int KC>
+__global__ void __launch_bounds__(128) esrg_fast_kernel(const EsrgArgs<R> a) {
+  const TargetWindow<R>& w = a.win;
+  const int f = w.f0 + blockIdx.x * 32 + (threadIdx.x & 31);
+  const int s = w.s0 + blockIdx.y * 4 + (threadIdx.x >> 5);
+  if (f >= w.f1 || s >= w.s1) return;
+  const int lin = (s - w.s0) * w.nf() + (f - w.f0);
+  if (a.all_exact) { a.todo[atomicAdd((unsigned long long*)a.todo_count, 1ull)] = lin; return; }
+  const int ix = w.fast_is_y ? s : f, iy = w.fast_is_y ? f : s;
+  const int len_x = a.len_x, len_y = a.len_y, k = a.k;
+  const R cx = __ldg((w.fast_is_y ? w.slow_axis : w.fast_axis) + ix);     // query_esrg.f90:133-134
+  const R cy = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
+
+  // the k smallest d2 seen so far, unsorted; dmax = largest of them (HUGE until k points were seen)
+  R d[KC];
+  int id[KC];
+#pragma unroll
+  for (int j = 0; j < KC; ++j) { d[j] = Consts<R>::huge(); id[j] = -1; }
+  R dmax = Consts<R>::huge();
+  int jmax = 0;
+  bool tie = false;
+
+  auto scan_run = [&](int p0, int p1) {
+    for (int p = p0; p < p1; ++p) {
+      const XY<R> q = a.sxy[p];
+      const R ddx = cx - q.x, ddy = cy - q.y;
+      const R d2 = ddx * ddx + ddy * ddy;                                 // :147-148
+      if (d2 < dmax) {
+        R m = R(-1);
+        int jm = 0;
+#pragma unroll
+        for (int j = 0; j < KC; ++j) {
+          if (j < k) {
+            if (j == jmax) { d[j] = d2; id[j] = p; }
+            else tie |= (d[j] == d2);
+            if (d[j] > m) { m = d[j]; jm = j; }
+          }
+        }
+        dmax = m; jmax = jm;
+      } else {
+        tie |= (d2 == dmax);
+      }
+    }
+  };
+  auto cell_start = [&](int c) { return c > 0 ? __ldg(a.table + c - 1) : 0; };
+
+  int level = 0;
+  long long cells_scanned = 0;
+  const int level_cap = len_x + len_y;
+  for (;;) {
+    if (level == 0) {
+      const int c = iy * len_x + ix;
+      scan_run(cell_start(c), __ldg(a.table + c));
+      ++cells_scanned;
+    } else {
+      const int jlo = max(ix - level, 0), jhi = min(ix + level, len_x - 1);
+      for (int i = -level; i <= level; ++i) {
+        const int iy2 = iy + i;
+        if (iy2 < 0 || iy2 >= len_y) continue;
+        const int row = iy2 * len_x;
+        if (i == -level || i == level) {                                  // a full row of the frame: one run
+          scan_run(cell_start(row + jlo), __ldg(a.table + row + jhi));
+          cells_scanned += jhi - jlo + 1;
+        } else {                                                          // its two end cells
+          if (ix - level >= 0) { const int c = row + ix - level; scan_run(cell_start(c), __ldg(a.table + c)); ++cells_scanned; }
+          if (ix + level < len_x) { const int c = row + ix + level; scan_run(cell_start(c), __ldg(a.table + c)); ++cells_scanned; }
+        }
+      }
+    }
+    const R rad = a.spac * (R(level) + R(0.5));                           // :141,:181
+    if (!(dmax > rad * rad)) break;                                       // k points within r_L: :178,:243
+    ++level;
+    if (level > level_cap) { raise_status(a.status, GI_ERR_TOO_FEW_POINTS); break; }
+  }
+  if (tie) {  // equal distances: the reference's processing order decides -> exact kernel
+    a.todo[atomicAdd((unsigned long long*)a.todo_count, 1ull)] = lin;
+    return;
+  }
+  // ascending d2 (odd-even transposition network; unused slots hold HUGE and stay at the end)
+#pragma unroll
+  for (int round = 0; round < KC; ++round) {
+#pragma unroll
+    for (int j = (round & 1); j + 1 < KC; j += 2) {
+      if (d[j + 1] < d[j]) {
+        const R td = d[j]; d[j] = d[j + 1]; d[j + 1] = td;
+        const int ti = id[j]; id[j] = id[j + 1]; id[j + 1] = ti;
+      }
+    }
+  }
+  // IDW (interpolation.f90:260-274): distances are square-rooted first (query_esrg.f90:247)
+  const int64_t o = lin;
+  R numerator = R(0), denominator = R(0), first_val = R(0), first_dist = R(0);
+#pragma unroll
+  for (int i = 0; i < KC; ++i) {
+    if (i < k) {
+      const int pos = id[i];
+      const R dist = sqrt(d[i]);
+      const R v = pos >= 0 ? __ldg(a.sval + pos) : R(0);
+      if (i == 0) { first_val = v; first_dist = dist; }
+      numerator = numerator + (v / dist);
+      denominator = denominator + (R(1) / dist);
+      if (a.nn_index) a.nn_index[o * k + i] = pos >= 0 ? __ldg(a.sid + pos) : -1;
+      if (a.nn_dist2) a.nn_dist2[o * k + i] = d[i];
+    }
+  }
+  a.out[o] = (first_dist <= Consts<R>::tiny_e4()) ? first_val : numerator / denominator;
+  if (a.stats) {
+    atomicAdd((unsigned long long*)a.counters, (unsigned long long)cells_scanned);
+    atomicMax((unsigned long long*)(a.counters + 1), (unsigned long long)level);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile kernel: the production path for k <= 16
+//
+// ncu on the per-thread kernels above: 440 warp instructions per target at 7.6 of 32 lanes active -- every lane
+// runs its own cell loops with its own trip counts.  Here a WARP owns a tile of 8 x 4 targets (8 along the
+// contiguous output axis) and works in lock step:
+//   1. stage   the points of the tile's halo rectangle (tile grown by H cells on every side; one CSR run per
+//              grid row, one lane per run) are copied to shared memory;
+//   2. scan    every lane computes its d2 to every staged point (shared-memory broadcast, no divergence) and
+//              appends those within r_H = spac*(H+1/2) -- the radius its own (2H+1)^2 window is guaranteed to
+//              cover -- to a per-lane candidate list in shared memory;
+//   3. grow    lanes with fewer than k candidates make the warp repeat 1-2 with H+2 (rare: H starts at the
+//              level where the mean density gives ~1.5k+6 points within r_H);
+//   4. select  k+1 rounds of minimum extraction give the neighbours in ascending order (the order of the
+//              reference's IDW sums); equal distances among them, or a full list, send the target to the
+//              exact kernel.
+// The result is the exact k nearest neighbours, which is what the reference computes (see esrg_fast_kernel).
+// ---------------------------------------------------------------------------------------------
+constexpr int kStageCap = 160;    // staged points per warp and chunk
+constexpr int kTileWarps = 2;
+
+// kTileCap = candidate slots per lane (32 for k <= 8, 48 for k <= 16)
+template <class R, int kTileCap>
+__global__ void __launch_bounds__(32 * kTileWarps, 12) esrg_tile_kernel(const EsrgArgs<R> a, int h0) {
+  __shared__ XY<R> s_xy[kTileWarps][kStageCap];
+  __shared__ int s_pos[kTileWarps][kStageCap];
+  __shared__ R s_d2[kTileWarps][kTileCap][32];
+  __shared__ int s_id[kTileWarps][kTileCap][32];
+  const TargetWindow<R>& w = a.win;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int len_x = a.len_x, len_y = a.len_y, k = a.k;
+  // tile origin in (fast, slow); 8 lanes along fast, 4 along slow
+  const int tiles_f = (w.nf() + 7) >> 3;
+  const int tile = blockIdx.x * kTileWarps + wid;
+  const int tf0 = w.f0 + (tile % tiles_f) * 8, ts0 = w.s0 + (tile / tiles_f) * 4;
+  if (ts0 >= w.s1) return;  // whole warp
+  const int f = tf0 + (lane & 7), s = ts0 + (lane >> 3);
+  const bool active = f < w.f1 && s < w.s1;
+  const int lin = (s - w.s0) * w.nf() + (f - w.f0);
+  if (a.all_exact) {
+    if (active) a.todo[atomicAdd((unsigned long long*)a.todo_count, 1ull)] = lin;
+    return;
+  }
+  const int fa = min(f, w.f1 - 1), sa = min(s, w.s1 - 1);  // inactive lanes shadow a valid target
+  const int ix = w.fast_is_y ? sa : fa, iy = w.fast_is_y ? fa : sa;
+  const R cx = __ldg((w.fast_is_y ? w.slow_axis : w.fast_axis) + ix);     // query_esrg.f90:133-134
+  const R cy = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
+  // tile extent in grid cells
+  const int f_hi = min(tf0 + 7, w.f1 - 1), s_hi = min(ts0 + 3, w.s1 - 1);
+  const int tx0 = w.fast_is_y ? ts0 : tf0, tx1 = w.fast_is_y ? s_hi : f_hi;
+  const int ty0 = w.fast_is_y ? tf0 : ts0, ty1 = w.fast_is_y ? f_hi : s_hi;
+
+  int cnt = 0;
+  bool done = !active, hand_over = false;
+  int H = h0;
+  const int level_cap = len_x + len_y;
+  for (;;) {
+    const R rad = a.spac * (R(H) + R(0.5));                               // :141,:181
+    const R r2 = rad * rad;
+    if (!done) cnt = 0;
+    // ---- 1. stage: one CSR run per grid row of the halo rectangle ----------------------------------
+    const int rx0 = max(tx0 - H, 0), rx1 = min(tx1 + H, len_x - 1);
+    const int ry0 = max(ty0 - H, 0), ry1 = min(ty1 + H, len_y - 1);
+    const int nrows = ry1 - ry0 + 1;
+    for (int rbase = 0; rbase < nrows; rbase += 32) {
+      int p0 = 0, n = 0;
+      if (rbase + lane < nrows) {
+        const int row = (ry0 + rbase + lane) * len_x;
+        const int c0 = row + rx0;
+        p0 = c0 > 0 ? __ldg(a.table + c0 - 1) : 0;
+        n = __ldg(a.table + row + rx1) - p0;
+      }
+      int off = n;  // inclusive warp scan
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, off, d);
+        if (lane >= d) off += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, off, 31);
+      off -= n;
+      for (int cbase = 0; cbase < total; cbase += kStageCap) {
+        __syncwarp();
+        // copy the part of this lane's run that falls into the chunk [cbase, cbase + kStageCap)
+        const int lo = max(off, cbase), hi = min(off + n, cbase + kStageCap);
+        for (int i = lo; i < hi; ++i) {
+          s_xy[wid][i - cbase] = a.sxy[p0 + (i - off)];
+          s_pos[wid][i - cbase] = p0 + (i - off);
+        }
+        __syncwarp();
+        // ---- 2. scan ------------------------------------------------------------------------------
+        const int m = min(total - cbase, kStageCap);
+        if (!done) {
+          for (int i = 0; i < m; ++i) {
+            const XY<R> q = s_xy[wid][i];
+            const R ddx = cx - q.x, ddy = cy - q.y;
+            const R d2 = ddx * ddx + ddy * ddy;                           // :147-148
+            if (!(d2 > r2)) {
+              if (cnt < kTileCap) { s_d2[wid][cnt][lane] = d2; s_id[wid][cnt][lane] = s_pos[wid][i]; }
+              ++cnt;
+            }
+          }
+        }
+      }
+    }
+    // ---- 3. grow? ---------------------------------------------------------------------------------
+    if (!done) {
+      if (cnt > kTileCap) { hand_over = true; done = true; }              // dense cluster: exact kernel
+      else if (cnt >= k) done = true;                                     // :178,:243
+    }
+    if (__all_sync(0xffffffffu, done)) break;
+    H += 2;
+    if (H > level_cap) { raise_status(a.status, GI_ERR_TOO_FEW_POINTS); break; }
+  }
+  // ---- 4. select ------------------------------------------------------------------------------------
+  const int n_list = hand_over ? 0 : min(cnt, kTileCap);
+  int cmax = n_list;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
+  R numerator = R(0), denominator = R(0), first_val = R(0), first_dist = R(0), prev = R(-1);
+  bool tie = false;
+  for (int round = 0; round <= k; ++round) {
+    R best = Consts<R>::huge();
+    int be = -1;
+#pragma unroll 4
+    for (int e = 0; e < cmax; ++e) {
+      const R v = s_d2[wid][e][lane];
+      if (e < n_list && v < best) { best = v; be = e; }
+    }
+    if (be < 0) break;  // (only when fewer than k+1 candidates: the whole list has been taken)
+    tie |= (best == prev);
+    prev = best;
+    if (round == k) break;
+    const int pos = s_id[wid][be][lane];
+    s_d2[wid][be][lane] = Consts<R>::huge();
+    // IDW (interpolation.f90:260-274): distances are square-rooted first (query_esrg.f90:247)
+    const R dist = sqrt(best);
+    const R v = __ldg(a.sval + pos);
+    if (round == 0) { first_val = v; first_dist = dist; }
+    numerator = numerator + (v / dist);
+    denominator = denominator + (R(1) / dist);
+    if (active && !hand_over) {
+      if (a.nn_index) a.nn_index[(int64_t)lin * k + round] = __ldg(a.sid + pos);
+      if (a.nn_dist2) a.nn_dist2[(int64_t)lin * k + round] = best;
+    }
+  }
+  if (!active) return;
+  if (hand_over || tie) {  // equal distances (the reference's candidate order decides) or a full list
+    a.todo[atomicAdd((unsigned long long*)a.todo_count, 1ull)] = lin;
+    return;
+  }
+  a.out[lin] = (first_dist <= Consts<R>::tiny_e4()) ? first_val : numerator / denominator;
 }
 
 template <class R> struct Binned {
@@ -298,13 +580,34 @@ int esrg_device(const R* points, int num_points, const R* data_in, const R* x_ax
   a.table = b.table; a.sxy = b.sxy; a.sval = b.sval; a.sid = b.sid;
   a.len_x = len_x; a.len_y = len_y; a.k = k; a.spac = grid_spac;
   a.out = data_ip; a.nn_index = nn_index; a.nn_dist2 = nn_dist2;
-  a.counters = counters_out ? counters : nullptr; a.status = slot.dev;
+  a.counters = counters; a.stats = counters_out ? 1 : 0; a.status = slot.dev;
   dim3 grid(div_up(a.win.nf(), 32), div_up(a.win.ns(), 4));
   GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
-  if (k <= 4) esrg_query_kernel<R, 4><<<grid, 128, 0, st>>>(a);
-  else if (k <= 8) esrg_query_kernel<R, 8><<<grid, 128, 0, st>>>(a);
-  else if (k <= 16) esrg_query_kernel<R, 16><<<grid, 128, 0, st>>>(a);
-  else esrg_query_kernel<R, 32><<<grid, 128, 0, st>>>(a);
+  const int64_t ntargets = (int64_t)a.win.nf() * a.win.ns();
+  GI_REQUIRE(ntargets < (int64_t)0x7fffffff, "window has more than 2^31 targets");
+  GI_TRY(scr.alloc(&a.todo, (size_t)ntargets));
+  a.todo_count = counters + 3;
+  a.all_exact = (flags & GI_ESRG_REFERENCE_ORDER) ? 1 : 0;
+  if (k <= 16) {
+    // first halo level: where the mean point density puts about 1.5k+6 points within r_H = spac*(H+1/2), so
+    // that all 32 lanes of a tile find k of them in the first pass with high probability (Poisson tail)
+    const double density = (double)num_points / ((double)len_x * (double)len_y);
+    int h0 = 1;
+    while (h0 < 12 && 3.141592653589793 * (h0 + 0.5) * (h0 + 0.5) * density < 1.5 * k + 6.0) ++h0;
+    const int64_t tiles = (int64_t)div_up(a.win.nf(), 8) * div_up(a.win.ns(), 4);
+    const unsigned tg = (unsigned)div_up(tiles, kTileWarps);
+    if (k <= 8) esrg_tile_kernel<R, 32><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
+    else esrg_tile_kernel<R, 48><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
+  } else {
+    esrg_fast_kernel<R, 32><<<grid, 128, 0, st>>>(a);
+  }
+  GI_CUDA(cudaGetLastError());
+  ph.mark("esrg_exact_ties");
+  const int eg = kNumSMs * 8;
+  if (k <= 4) esrg_query_kernel<R, 4><<<eg, 128, 0, st>>>(a);
+  else if (k <= 8) esrg_query_kernel<R, 8><<<eg, 128, 0, st>>>(a);
+  else if (k <= 16) esrg_query_kernel<R, 16><<<eg, 128, 0, st>>>(a);
+  else esrg_query_kernel<R, 32><<<eg, 128, 0, st>>>(a);
   GI_CUDA(cudaGetLastError());
   ph.finish();
   if (counters_out)

@@ -336,7 +336,7 @@ def idw_kdtree(points, data_in, x_axis, y_axis, num_neighbours, **kw):
 
 
 def idw_esrg_nearest_ex(points, data_in, x_axis, y_axis, grid_spac, num_neighbours, *, rows=None, order="F",
-                        debug=False, out=None, sync=True):
+                        debug=False, reference_order=False, out=None, sync=True):
     """idw_esrg_nearest on a row band; debug=True also returns neighbour ids / d2 / counters."""
     with _Call(points) as c:
         x, y, p, d, n = _grid_common(c, points, data_in, x_axis, y_axis, "n2")
@@ -345,6 +345,7 @@ def idw_esrg_nearest_ex(points, data_in, x_axis, y_axis, grid_spac, num_neighbou
         k = int(num_neighbours)
         res, res_ptr, rowmajor = _use_out(c, out, (r1 - r0, len_x), _F64, order)
         flags = (GI_FIELD_ROWMAJOR if rowmajor else 0) | (GI_POINTS_ROWMAJOR if p.rowmajor else 0)
+        flags |= _lib.GI_ESRG_REFERENCE_ORDER if reference_order else 0
         nn = d2 = cnt = None
         nn_ptr = d2_ptr = cnt_ptr = None
         if debug:
@@ -360,7 +361,7 @@ def idw_esrg_nearest_ex(points, data_in, x_axis, y_axis, grid_spac, num_neighbou
         if not rowmajor:
             nn, d2 = _moveaxis(nn, 0, -1), _moveaxis(d2, 0, -1)
         return res, SimpleNamespace(nn_index=nn, nn_dist2=d2, cells_scanned=int(cnt[0]), level_max=int(cnt[1]),
-                                    list_overflows=int(cnt[2]))
+                                    list_overflows=int(cnt[2]), exact_order_targets=int(cnt[3]))
 
 
 def idw_esrg_nearest(points, data_in, x_axis, y_axis, grid_spac, num_neighbours, **kw):

@@ -67,6 +67,9 @@ typedef enum {
 #define GI_POINTS_ROWMAJOR 1 /* points array is C-order instead of Fortran order */
 #define GI_TOPO_ROWMAJOR 2   /* simplices / neighbours are C-order (num_triangles,3) */
 #define GI_FIELD_ROWMAJOR 4  /* data_in (bilinear) / data_ip (grid outputs): element (iy,ix) at iy*len_x + ix */
+#define GI_ESRG_REFERENCE_ORDER 16 /* idw_esrg_nearest: process every target in the reference's candidate order
+                                      (debug).  Default: only targets with exactly equal neighbour distances,
+                                      the only case in which that order changes the result. */
 #define GI_KD_REFERENCE_VISITS 8 /* idw_kdtree: visit exactly the nodes the reference visits (debug: makes the
                                     visit counter comparable).  Default: additionally skip far subtrees with
                                     diff*diff >= max d2, which provably cannot change the neighbour list. */
@@ -151,7 +154,7 @@ int gi_barycentric_interpolation_ex_f64(const double* points, int num_points, co
 /* nn_index (band rows, len_x, k): 1-based ids in ascending-distance order as neighbours_index /
  * index_nn hold them (kd_tree.f90:236, query_esrg.f90:168), k fastest; nn_dist2 squared distances
  * (kd: neighbours(3,:), esrg: dist_sq_nn).  counters int64[4]: node visits (kd) or cells scanned (esrg),
- * max ring level, overflow re-scans, unused. */
+ * max ring level, candidate-list overflows, targets resolved in the reference's candidate order (ties). */
 int gi_idw_kdtree_ex_f64(const double* points, int num_points, const double* data_in,
                          const double* x_axis, int len_x, const double* y_axis, int len_y,
                          int num_neighbours, int row_begin, int row_end, double* data_ip,

@@ -130,8 +130,16 @@ def test_esrg_c1(c1, order, k):
                                     debug=True)
     assert np.array_equal(g.nn_index, np.moveaxis(w.nn_index, 0, -1))     # neighbour ids in order, bit-exact
     assert np.array_equal(np.sqrt(g.nn_dist2), np.moveaxis(w.nn_dist, 0, -1))
-    assert g.level_max == w.level_max
     assert_values(got, want)
+    # random FP64 inputs have no equal distances: only a handful of targets with an overfull candidate list
+    # (local density far above the mean) are handed to the exact-order kernel
+    assert g.exact_order_targets <= got.size // 50
+    # the kernel that follows the reference's candidate order, forced on every target
+    got2, g2 = ip.idw_esrg_nearest_ex(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, k, order=order,
+                                      debug=True, reference_order=True)
+    assert g2.exact_order_targets == got.size and g2.level_max == w.level_max
+    assert np.array_equal(g2.nn_index, np.moveaxis(w.nn_index, 0, -1))
+    assert_values(got2, want)
 
 
 def test_esrg_golden_twin(golden_dir):
@@ -157,9 +165,13 @@ def test_esrg_clustered_overflows_candidate_list():
     data = np.sin(pts[:, 0]) * pts[:, 1]
     want, w = orc.idw_esrg_nearest(pts, data, x, y, 1.0, 8, debug=True)
     got, g = ip.idw_esrg_nearest_ex(pts, data, x, y, 1.0, 8, debug=True)
-    assert w.list_max > 1000 and g.list_overflows > 0
+    assert w.list_max > 1000
     assert np.array_equal(g.nn_index, np.moveaxis(w.nn_index, 0, -1))
     assert_values(got, want)
+    got2, g2 = ip.idw_esrg_nearest_ex(pts, data, x, y, 1.0, 8, debug=True, reference_order=True)
+    assert g2.list_overflows > 0                # the deferred list overflowed -> list-free re-scan mode
+    assert np.array_equal(g2.nn_index, np.moveaxis(w.nn_index, 0, -1))
+    assert_values(got2, want)
 
 
 def test_esrg_ties_on_lattice():
@@ -173,6 +185,7 @@ def test_esrg_ties_on_lattice():
     x = np.arange(12.0); y = np.arange(9.0)
     want, w = orc.idw_esrg_nearest(pts, data, x, y, 1.0, 7, debug=True)
     got, g = ip.idw_esrg_nearest_ex(pts, data, x, y, 1.0, 7, debug=True)
+    assert g.exact_order_targets > got.size // 2   # ties everywhere: resolved in the reference's candidate order
     assert np.array_equal(g.nn_index, np.moveaxis(w.nn_index, 0, -1))
     assert_values(got, want)     # includes the "extremely close neighbour" branch (distance 0)
 
