@@ -135,7 +135,8 @@ def make_c4(args, rank, world, dist):
 
 def cpu_sample_c4(w, y_axis, seconds, threads=None):
     """Oracle barycentric on evenly strided grid rows of the same job: every row pays the reference's
-    restart-from-the-start-triangle walk exactly as in the full run.  Returns (targets/s, description)."""
+    restart-from-the-start-triangle walk exactly as in the full run.  The sample grows until it takes about
+    `seconds` or covers the whole grid.  Returns (targets/s, threads, description)."""
     from oracle import oracle as orc
     if threads:
         orc.set_num_threads(threads)
@@ -146,15 +147,16 @@ def cpu_sample_c4(w, y_axis, seconds, threads=None):
         ys = np.ascontiguousarray(y_axis[:: max(len(y_axis) // rows, 1)][:rows])
         t0 = time.perf_counter()
         orc.barycentric_interpolation(pts_f, w.data_pts, w.x_axis, ys, simp_f, nbr_f)
-        return ys.size * w.x_axis.size, time.perf_counter() - t0
+        return ys.size, ys.size * w.x_axis.size, time.perf_counter() - t0
 
-    rows = max(2 * cores, 16)
-    tg, dt = run(rows)                                   # calibration
-    rate = tg / dt
-    rows2 = int(min(len(y_axis), max(rows, rate * seconds / w.x_axis.size)))
-    rows2 = max(rows2 // cores * cores, cores)
-    tg, dt = run(rows2)
-    return tg / dt, cores, f"{rows2} evenly strided rows x {w.x_axis.size} columns of the job's grid ({tg} targets, {dt:.1f} s)"
+    rows = max(8 * cores, 64)
+    while True:
+        nrows, tg, dt = run(min(rows, len(y_axis)))
+        if dt >= 0.5 * seconds or nrows >= len(y_axis):
+            break
+        rows = int(min(len(y_axis), max(2 * rows, rows * 0.8 * seconds / max(dt, 1e-3))))
+    return tg / dt, cores, (f"{nrows} evenly strided rows x {w.x_axis.size} columns of the job's grid "
+                            f"({tg} targets, {dt:.1f} s; the whole grid when it takes less than the budget)")
 
 
 def main():

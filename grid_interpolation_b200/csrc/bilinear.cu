@@ -2,7 +2,9 @@
 //
 // One thread handles kPts points strided by the CTA size, so the coordinate loads and the result store
 // are fully coalesced and the 4 x kPts dependent field gathers of a thread are all in flight together
-// (the kernel is bound by random 32 B-sector gathers from a field far larger than L2).  The field is
+// (the kernel is bound by random gathers from a field far larger than L2: ncu shows 8.7 DRAM sectors read per
+// point -- L2 fetches more than the touched sector -- at 46 % of peak DRAM throughput;
+// cudaLimitMaxL2FetchGranularity = 32 had no effect on B200).  The field is
 // addressed through (stride_y, stride_x), so the reference's column-major data_in(len_y,len_x) and numpy's
 // row-major layout are read in place.
 //
@@ -71,14 +73,13 @@ bilinear_kernel(const R* __restrict__ x_axis, int len_x, const R* __restrict__ y
   R d11[kPts], d12[kPts], d21[kPts], d22[kPts], xa[kPts], xb[kPts], ya[kPts], yb[kPts];
 #pragma unroll
   for (int j = 0; j < kPts; ++j) {
-    const bool two = len_x > 1 && len_y > 1;
-    const R* p = data + (int64_t)iy[j] * sy + (int64_t)ix[j] * sx;
+    const R* p = data + (int64_t)iy[j] * sy + (int64_t)ix[j] * sx;       // ix <= len_x-2, iy <= len_y-2
     d11[j] = __ldg(p);                                                    // data_in(ind_y,   ind_x)
-    d12[j] = two ? __ldg(p + sy) : R(0);                                  // data_in(ind_y+1, ind_x)
-    d21[j] = two ? __ldg(p + sx) : R(0);                                  // data_in(ind_y,   ind_x+1)
-    d22[j] = two ? __ldg(p + sy + sx) : R(0);                             // data_in(ind_y+1, ind_x+1)
-    xa[j] = __ldg(x_axis + ix[j]); xb[j] = two ? __ldg(x_axis + ix[j] + 1) : xa[j];
-    ya[j] = __ldg(y_axis + iy[j]); yb[j] = two ? __ldg(y_axis + iy[j] + 1) : ya[j];
+    d12[j] = __ldg(p + sy);                                               // data_in(ind_y+1, ind_x)
+    d21[j] = __ldg(p + sx);                                               // data_in(ind_y,   ind_x+1)
+    d22[j] = __ldg(p + sy + sx);                                          // data_in(ind_y+1, ind_x+1)
+    xa[j] = __ldg(x_axis + ix[j]); xb[j] = __ldg(x_axis + ix[j] + 1);
+    ya[j] = __ldg(y_axis + iy[j]); yb[j] = __ldg(y_axis + iy[j] + 1);
   }
 #pragma unroll
   for (int j = 0; j < kPts; ++j) {

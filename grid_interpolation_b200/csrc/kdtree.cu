@@ -255,11 +255,19 @@ template <class R> struct KdArgs {
   int* status;
 };
 
+template <class R> struct alignas(16) StackEntry {
+  int lo, hi;
+  R adiff;  // |diff| of the parent; sign bit = parity of the subtree's depth
+};
+
 template <class R, int KC, bool REFVISITS>
 __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
   const TargetWindow<R>& w = a.win;
-  const int f = w.f0 + blockIdx.x * 32 + (threadIdx.x & 31);
-  const int s = w.s0 + blockIdx.y * 4 + (threadIdx.x >> 5);
+  // a warp owns a compact 8 x 4 patch of targets (8 along the contiguous output axis): neighbouring targets
+  // descend through the same nodes, which keeps the 32 traversals as coherent as a per-thread walk can be
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = w.f0 + blockIdx.x * 32 + wid * 8 + (lane & 7);
+  const int s = w.s0 + blockIdx.y * 4 + (lane >> 3);
   const bool active = f < w.f1 && s < w.s1;
   long long visits = 0;
   if (active) {
@@ -268,8 +276,8 @@ __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
     const R ty = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
     TopK<R, KC> tk;
     tk.init(a.k, Consts<R>::sentinel(), -1);                              // :159
-    int st_lo[32], st_hi[32], st_depth[32];
-    R st_diff[32];
+    // deferred far branches: one 16 B entry each (segment + |diff|; the depth parity rides in the sign bit)
+    StackEntry<R> stack[32];
     int sp = 0;
     int lo = 0, hi = a.n, depth = 0;
     for (;;) {
@@ -286,17 +294,20 @@ __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
         else { flo = lo; fhi = m; lo = m + 1; }                           // :195 near = right
         ++depth;
         if (flo < fhi && sp < 32) {
-          st_lo[sp] = flo; st_hi[sp] = fhi; st_depth[sp] = depth; st_diff[sp] = fabs(diff);
-          ++sp;
+          StackEntry<R> e;
+          e.lo = flo; e.hi = fhi;
+          e.adiff = (depth & 1) ? -fabs(diff) : fabs(diff);
+          stack[sp++] = e;
         }
       }
       bool got = false;
       while (sp > 0) {
-        --sp;
-        const R ad = st_diff[sp];
+        const StackEntry<R> e = stack[--sp];
+        const R ad = fabs(e.adiff);
         // :191,:198 the reference's rule; second term: provably state-preserving skip (see file header)
         if (ad < tk.dlast && (REFVISITS || ad * ad < tk.dlast)) {
-          lo = st_lo[sp]; hi = st_hi[sp]; depth = st_depth[sp];
+          lo = e.lo; hi = e.hi;
+          depth = signbit(e.adiff) ? 1 : 0;  // only the parity of the depth is ever used
           got = true;
           break;
         }
