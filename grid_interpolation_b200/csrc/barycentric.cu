@@ -29,6 +29,8 @@
 //
 // All index decisions (orientation signs, first failing edge) and all values use the reference's operations
 // in the reference's order with FMA contraction disabled (-fmad=false): bit-identical to the oracle.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace gi {
@@ -232,6 +234,36 @@ __device__ __forceinline__ R eval_value(const TriGeom<R>& g, R tx, R ty) {
   return g.d1 * w1 + g.d2 * w2 + g.d3 * w3;
 }
 
+// |cross| below this (twice the reference's margin) means "within the margin band of an edge"
+template <class R> __device__ __forceinline__ R kAmbBand() { return R(2e-10); }
+
+// walk() that also reports whether the accepting (or hull-exit) test was inside the margin band
+template <class R>
+__device__ __forceinline__ int walk_checked(const TriGeom<R>* __restrict__ geom, int tri, R tx, R ty, int iter_cap,
+                                            bool& inside, bool& amb, int* status) {
+  const R margin = Consts<R>::margin();
+  inside = true;
+  int it = 0;
+  for (;;) {
+    ++it;
+    TriGeom<R> g;
+    load_walk(geom + tri, g);
+    const R c1 = (g.x2 - g.x1) * (ty - g.y1) - (g.y2 - g.y1) * (tx - g.x1);
+    const R c2 = (g.x3 - g.x2) * (ty - g.y2) - (g.y3 - g.y2) * (tx - g.x2);
+    const R c3 = (g.x1 - g.x3) * (ty - g.y3) - (g.y1 - g.y3) * (tx - g.x3);
+    int nxt;
+    R cf;
+    if (c1 < margin) { nxt = g.n3; cf = c1; }
+    else if (c2 < margin) { nxt = g.n1; cf = c2; }
+    else if (c3 < margin) { nxt = g.n2; cf = c3; }
+    else { amb = fmin(fmin(c1, c2), c3) < kAmbBand<R>(); break; }
+    if (nxt < 0) { inside = false; amb = cf > -kAmbBand<R>(); break; }
+    tri = nxt;
+    if (it >= iter_cap) { raise_status(status, GI_ERR_ITER_CAP); inside = false; amb = false; break; }
+  }
+  return tri;
+}
+
 template <class R> struct WalkArgs {
   TargetWindow<R> win;   // walked window E (band + halo)
   int bf0, bf1, bs0, bs1;  // band B inside E: the part that is written to `out`
@@ -243,6 +275,9 @@ template <class R> struct WalkArgs {
   uint32_t* mask_words; // E-shaped bit mask: ((nf+31)/32) words per slow row
   int* nz_words;        // compact list of the mask words that are non-zero (work list of the hull fill)
   int64_t* counters;    // [0] walk iterations [1] masked cells [2] max fill level [3] fix-ups [4] #nz_words
+                        // [5] #ambiguous targets flagged [6],[7] start-triangle reduction scratch
+  int* amb_list;        // E-linear ids of the targets inside the margin band of an edge (see fixup_kernel)
+  int amb_cap;
   int* status;
 };
 
@@ -324,7 +359,14 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
         if (it < a.iter_cap) { enter(nxt); continue; }
         raise_status(a.status, GI_ERR_ITER_CAP);
       }
-      // resolved: inside `tri`, or outside the hull (:74-80: the last valid triangle is kept)
+      // resolved: inside `tri`, or outside the hull (:74-80: the last valid triangle is kept).
+      // A target within the margin band of an edge is accepted by both adjacent triangles and which one the
+      // reference returns depends on its walk path: flag it for fixup_kernel.
+      // (any |cross| below twice the margin: a superset of the truly ambiguous cases, three compares)
+      if (fabs(x1) < kAmbBand<R>() || fabs(x2) < kAmbBand<R>() || fabs(x3) < kAmbBand<R>()) {
+        const unsigned long long slot = atomicAdd((unsigned long long*)(a.counters + 5), 1ull);
+        if (slot < (unsigned long long)a.amb_cap) a.amb_list[slot] = (srow0 + r - w.s0) * w.nf() + lane_f;
+      }
       if (fresh && !outside) {  // phase 2 will want this triangle's nodal values: pull the sector into L1 now
         touch_values(a.geom + tri);
         fresh = false;
@@ -386,6 +428,109 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   // one atomic per warp for the iteration counter (iters_tot, interpolation.f90:374)
   for (int off = 16; off > 0; off >>= 1) iters_sum += __shfl_down_sync(0xffffffffu, iters_sum, off);
   if (lane == 0 && iters_sum) atomicAdd((unsigned long long*)a.counters, (unsigned long long)iters_sum);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ambiguity fix-up.  A target within 1e-10 (cross-product units) of a mesh edge passes the orientation test of
+// both adjacent triangles (triangle_walk.f90:148-151); the reference returns whichever its own walk reaches
+// first -- it walks along the grid row from the triangle found for the previous column, every row starting at
+// ind_tri_start (interpolation.f90:342-355,365-373).  For random meshes this concerns about one target in 1e10,
+// for meshes with grid-aligned edges (structured triangulations) it concerns many.  The flagged targets are
+// re-located here by following the reference's path: back up along the row to the nearest column whose triangle
+// is unambiguous (any walk finds that one), or to column 0 and the reference's start triangle, then walk forward
+// column by column.
+// ---------------------------------------------------------------------------------------------
+template <class R>
+__global__ void start_tri_setup_kernel(const R* __restrict__ y_axis, int len_y, int64_t* counters, R* opt_y) {
+  if (counters[5] == 0) return;
+  R sum = R(0);
+  for (int i = 0; i < len_y; ++i) sum = sum + y_axis[i];                  // SUM(y_axis), interpolation.f90:345
+  *opt_y = sum / R(len_y);
+  counters[6] = (int64_t)0x7fffffffffffffffll;
+  counters[7] = (int64_t)0x7fffffffffffffffll;
+}
+
+template <class R>
+__device__ __forceinline__ unsigned long long start_tri_dist(const TriGeom<R>* geom, int i, R opt_x, R opt_y) {
+  TriGeom<R> g;
+  load_walk(geom + i, g);
+  const R cx = ((g.x1 + g.x2) + g.x3) / R(3), cy = ((g.y1 + g.y2) + g.y3) / R(3);   // :348-349
+  const double d = (double)((cx - opt_x) * (cx - opt_x) + (cy - opt_y) * (cy - opt_y));  // :350
+  return (unsigned long long)__double_as_longlong(d);  // non-negative doubles order like their bit patterns
+}
+
+// pass 0: minimum distance; pass 1: smallest index attaining it (strict '<' keeps the first, :351-354)
+template <class R>
+__global__ void __launch_bounds__(256)
+start_tri_kernel(const TriGeom<R>* __restrict__ geom, int n_search, const R* __restrict__ x_axis,
+                 const R* __restrict__ opt_y, int64_t* counters, int pass) {
+  if (counters[5] == 0) return;
+  const R ox = __ldg(x_axis), oy = *opt_y;
+  unsigned long long best = ~0ull;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_search; i += gridDim.x * blockDim.x) {
+    const unsigned long long d = start_tri_dist(geom, i, ox, oy);
+    if (pass == 0) best = min(best, d);
+    else if (d == (unsigned long long)counters[6]) best = min(best, (unsigned long long)i);
+  }
+  for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+  if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin((unsigned long long*)(counters + 6 + pass), best);
+}
+
+constexpr int kMaxBackup = 256;
+
+template <class R>
+__global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len_x, int len_y) {
+  const TargetWindow<R>& w = a.win;
+  const int64_t n = min(a.counters[5], (int64_t)a.amb_cap);
+  const int nf = w.nf(), wpr = (nf + 31) >> 5;
+  const R* x_axis = w.fast_is_y ? w.slow_axis : w.fast_axis;
+  const R* y_axis = w.fast_is_y ? w.fast_axis : w.slow_axis;
+  for (int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; li < n; li += (int64_t)gridDim.x * blockDim.x) {
+    const int lin = a.amb_list[li];
+    const int s = w.s0 + lin / nf, f = w.f0 + lin % nf;
+    const int ix = w.fast_is_y ? s : f, iy = w.fast_is_y ? f : s;
+    const R ty = __ldg(y_axis + iy);
+    // back up to the nearest column of this row whose triangle does not depend on the path
+    int tri = -1, j0 = -1;
+    const int j_stop = max(ix - kMaxBackup, 0);
+    for (int j = ix - 1; j >= j_stop; --j) {
+      bool inside, amb;
+      const int t = walk_checked(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, j, iy, a.num_tri), __ldg(x_axis + j), ty,
+                                 a.iter_cap, inside, amb, a.status);
+      if (inside && !amb) { tri = t; j0 = j; break; }
+    }
+    if (tri < 0) {
+      // no path-independent column within kMaxBackup: only column 0 (the reference's ind_tri_start, :366) is
+      // another certain starting point; otherwise the target keeps the triangle phase 1 found (a whole row
+      // running along mesh edges for more than kMaxBackup columns -- values agree to rounding either way)
+      if (j_stop > 0) continue;
+      tri = (int)a.counters[7];
+    }
+    // forward along the row exactly as the reference does (:367-373)
+    bool inside = true, amb;
+    for (int j = j0 + 1; j <= ix; ++j)
+      tri = walk_checked(a.geom, tri, __ldg(x_axis + j), ty, a.iter_cap, inside, amb, a.status);
+    // publish
+    if (f >= a.bf0 && f < a.bf1 && s >= a.bs0 && s < a.bs1) {
+      const int64_t o = (int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0);
+      if (inside) {
+        TriGeom<R> g;
+        load_walk(a.geom + tri, g);
+        load_values(a.geom + tri, g);
+        a.out[o] = eval_value(g, __ldg(x_axis + ix), ty);
+      }
+      if (a.tri_out) a.tri_out[o] = tri + 1;
+    }
+    const int lf = f - w.f0;
+    uint32_t* word = a.mask_words + (int64_t)(s - w.s0) * wpr + (lf >> 5);
+    const uint32_t bit = 1u << (lf & 31);
+    if (inside) {
+      atomicAnd(word, ~bit);
+    } else if (atomicOr(word, bit) == 0u) {  // the word was not on the fill's work list yet
+      a.nz_words[atomicAdd((unsigned long long*)(a.counters + 4), 1ull)] = (int)((int64_t)(s - w.s0) * wpr + (lf >> 5));
+    }
+    atomicAdd((unsigned long long*)(a.counters + 3), 1ull);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -591,6 +736,8 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
   GI_TRY(scr.alloc(&mask_words, (size_t)wpr * ns));
   GI_TRY(scr.alloc(&nz_words, (size_t)wpr * ns));
   wa.nz_words = nz_words;
+  wa.amb_cap = (int)std::min<int64_t>((int64_t)nf * ns, (int64_t)1 << 22);
+  GI_TRY(scr.alloc(&wa.amb_list, (size_t)wa.amb_cap));
   wa.geom = geom; wa.seed = seed; wa.ncx = ncx; wa.ncy = ncy; wa.num_tri = num_tri;
   wa.iter_cap = num_tri + 16;
   wa.out = data_ip; wa.tri_out = tri_out; wa.mask_words = mask_words; wa.counters = counters;
@@ -605,6 +752,17 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
       else locate_eval_kernel<R, true, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
       GI_CUDA(cudaGetLastError());
     }
+  // ---- 2b. targets inside the margin band of an edge: follow the reference's own path (normally none) --
+  {
+    R* opt_y;
+    GI_TRY(scr.alloc(&opt_y, 1));
+    const int n_search = std::min(num_points, num_tri);  // the reference searches triangles 1..num_points (:347)
+    start_tri_setup_kernel<R><<<1, 1, 0, st>>>(y_axis, len_y, counters, opt_y);
+    start_tri_kernel<R><<<kNumSMs * 4, 256, 0, st>>>(geom, n_search, x_axis, opt_y, counters, 0);
+    start_tri_kernel<R><<<kNumSMs * 4, 256, 0, st>>>(geom, n_search, x_axis, opt_y, counters, 1);
+    fixup_kernel<R><<<kNumSMs * 2, 128, 0, st>>>(wa, len_x, len_y);
+    GI_CUDA(cudaGetLastError());
+  }
   if (mask_out || fill_src) {
     expand_mask_kernel<<<kNumSMs * 8, 256, 0, st>>>(mask_words, wpr, wa.win.f0, wa.win.s0, wa.bf0, wa.bf1, wa.bs0,
                                                    wa.bs1, mask_out, fill_src);

@@ -61,7 +61,7 @@ def test_barycentric_c1(c1, order):
                                              c1.neighbours, order=order, debug=True)
     assert got.shape == want.shape == (79, 132)
     assert got.flags.f_contiguous if order == "F" else got.flags.c_contiguous
-    assert np.array_equal(g.mask, w.mask) and g.masked == 433
+    assert np.array_equal(g.mask, w.mask) and g.masked == 433 and g.fixups == 0
     ins = ~w.mask
     assert np.array_equal(g.tri[ins], w.tri[ins])              # found triangle ids, bit-exact
     assert np.array_equal(g.fill_src, w.fill_src)              # hull-fill sources incl. tie-breaks
@@ -100,6 +100,30 @@ def test_barycentric_row_bands_with_halo(c1):
     with pytest.raises(RuntimeError, match="halo"):
         ip.barycentric_interpolation_ex(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
                                         c1.neighbours, rows=(0, 2), halo=0)
+
+
+def test_barycentric_targets_on_mesh_edges():
+    """Structured mesh, grid nodes exactly on mesh vertices and edges: such targets pass the orientation test of
+    two (or more) triangles and the reference returns the one its row-wise walk reaches first
+    (triangle_walk.f90:148-151, interpolation.f90:365-373).  The fix-up pass must reproduce that choice."""
+    gx, gy = np.meshgrid(np.arange(0.0, 12.0), np.arange(0.0, 9.0))
+    pts = np.stack([gx.ravel(), gy.ravel()], 1)
+    simp, nbr = workloads.delaunay(pts)
+    a = pts[simp - 1]
+    area = 0.5 * ((a[:, 1, 0] - a[:, 0, 0]) * (a[:, 2, 1] - a[:, 0, 1]) - (a[:, 1, 1] - a[:, 0, 1]) * (a[:, 2, 0] - a[:, 0, 0]))
+    keep = area > 1e-9                          # Qhull may emit flat triangles for co-circular lattice points
+    assert keep.all(), "degenerate triangles in the lattice triangulation"
+    data = np.sin(pts[:, 0]) + 0.3 * pts[:, 1] ** 2
+    x = np.arange(-0.5, 12.0, 0.5); y = np.arange(-0.5, 9.0, 0.25)
+    want, w = orc.barycentric_interpolation(pts, data, x, y, simp, nbr, debug=True)
+    for order in ("C", "F"):
+        got, g = ip.barycentric_interpolation_ex(pts, data, x, y, simp, nbr, debug=True, order=order)
+        assert g.fixups > 100                   # many targets sit on edges / vertices
+        assert np.array_equal(g.mask, w.mask)
+        ins = ~w.mask
+        assert np.array_equal(g.tri[ins], w.tri[ins])
+        assert np.array_equal(g.fill_src, w.fill_src)
+        assert_values(got, want)
 
 
 def test_barycentric_bad_topology_is_reported(c1):
