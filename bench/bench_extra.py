@@ -163,7 +163,8 @@ def run(args, rank, world, local_rank):
                       ip.pinned_copy(w.y_axis))
             step_host = lambda: ip.idw_esrg_nearest_ex(*h_args, 1.0, k, rows=band, out=h_out)
             cells = grid * grid
-            launches = 1 + (3 if cells > 4096 else 1) + (2 if cells > 4096 * 4096 else 0) + 3 + 1 + 1
+            # key/count, scan (1, 3 or 5 kernels), scatter, sort cells, gather, tile query, exact-order query, flush
+            launches = 1 + (1 if cells <= 4096 else (3 if cells <= 4096 * 4096 else 5)) + 3 + 2 + 1
             dominant = "esrg_query"
 
     def sync_all():
