@@ -13,7 +13,7 @@ GI_HOST, GI_DEVICE = 0, 1
 GI_POINTS_ROWMAJOR, GI_TOPO_ROWMAJOR, GI_FIELD_ROWMAJOR, GI_KD_REFERENCE_VISITS = 1, 2, 4, 8
 GI_ESRG_REFERENCE_ORDER = 16
 
-_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+_vp, _i, _i64, _d, _f = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float
 
 # name -> argtypes; every symbol include/gridinterp.h declares (tests/test_abi.py checks the two agree)
 SIGNATURES = {
@@ -28,20 +28,22 @@ SIGNATURES = {
     "gi_last_timings": ([_vp, _i], _i),
     "gi_last_timing_name": ([_i], C.c_char_p),
     "gi_release_workspace": ([], None),
-    "gi_bilinear_f64": ([_vp, _i, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _vp], _i),
-    "gi_bilinear_f32": ([_vp, _i, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _vp], _i),
-    "gi_idw_kdtree_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp], _i),
-    "gi_idw_esrg_nearest_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _d, _i, _vp, _i, _i, _vp], _i),
-    "gi_barycentric_interpolation_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp], _i),
-    "gi_barycentric_interpolation_ex_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i,
-                                             _vp, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
-    "gi_idw_kdtree_ex_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
-    "gi_idw_esrg_nearest_ex_f64": ([_vp, _i, _vp, _vp, _i, _vp, _i, _d, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i,
-                                    _vp], _i),
-    "gi_kd_build_f64": ([_vp, _i, _vp, _i, _i, _vp], _i),
-    "gi_esrg_assign_points_to_cells_f64": ([_vp, _i, _vp, _i, _vp, _i, _d, _vp, _vp, _i, _i, _vp], _i),
-    "gi_fill_nearest_neighbour_f64": ([_vp, _i, _i, _vp, _vp, _i, _i, _vp], _i),
 }
+for _suf, _real in (("f64", _d), ("f32", _f)):
+    SIGNATURES.update({
+        f"gi_bilinear_{_suf}": ([_vp, _i, _vp, _i, _vp, _vp, _i64, _vp, _i, _i, _vp], _i),
+        f"gi_idw_kdtree_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp], _i),
+        f"gi_idw_esrg_nearest_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _real, _i, _vp, _i, _i, _vp], _i),
+        f"gi_barycentric_interpolation_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp], _i),
+        f"gi_barycentric_interpolation_ex_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i,
+                                                     _vp, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
+        f"gi_idw_kdtree_ex_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
+        f"gi_idw_esrg_nearest_ex_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _real, _i, _i, _i, _vp, _vp, _vp, _vp,
+                                            _i, _i, _vp], _i),
+        f"gi_kd_build_{_suf}": ([_vp, _i, _vp, _i, _i, _vp], _i),
+        f"gi_esrg_assign_points_to_cells_{_suf}": ([_vp, _i, _vp, _i, _vp, _i, _real, _vp, _vp, _i, _i, _vp], _i),
+        f"gi_fill_nearest_neighbour_{_suf}": ([_vp, _i, _i, _vp, _vp, _i, _i, _vp], _i),
+    })
 
 _lib = None
 

@@ -475,79 +475,70 @@ GI_API void gi_release_workspace(void) {
   }
 }
 
-GI_API int gi_bilinear_f64(const double* x_axis, int len_x, const double* y_axis, int len_y, const double* data_in,
-                           const double* points, int64_t num_points, double* data_ip, int flags, int mem,
-                           void* stream) {
-  return bilinear_api<double>(x_axis, len_x, y_axis, len_y, data_in, points, num_points, data_ip, flags, mem, stream);
-}
-GI_API int gi_bilinear_f32(const float* x_axis, int len_x, const float* y_axis, int len_y, const float* data_in,
-                           const float* points, int64_t num_points, float* data_ip, int flags, int mem,
-                           void* stream) {
-  return bilinear_api<float>(x_axis, len_x, y_axis, len_y, data_in, points, num_points, data_ip, flags, mem, stream);
-}
+// Every entry point exists for both real kinds: _f64 is the graded path (the reference built with
+// -fdefault-real-8), _f32 reproduces the shipped single-precision numerics.
+#define GI_DEFINE_ENTRY_POINTS(SUF, R)                                                                              \
+  GI_API int gi_bilinear_##SUF(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* data_in,           \
+                               const R* points, int64_t num_points, R* data_ip, int flags, int mem, void* stream) { \
+    return bilinear_api<R>(x_axis, len_x, y_axis, len_y, data_in, points, num_points, data_ip, flags, mem, stream); \
+  }                                                                                                                 \
+  GI_API int gi_idw_kdtree_##SUF(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,    \
+                                 const R* y_axis, int len_y, int num_neighbours, R* data_ip, int flags, int mem,   \
+                                 void* stream) {                                                                    \
+    return kdtree_api<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, num_neighbours, 0, len_y,      \
+                         data_ip, nullptr, nullptr, nullptr, flags, mem, stream);                                  \
+  }                                                                                                                 \
+  GI_API int gi_idw_kdtree_ex_##SUF(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, \
+                                    const R* y_axis, int len_y, int num_neighbours, int row_begin, int row_end,    \
+                                    R* data_ip, int32_t* nn_index, R* nn_dist2, int64_t* counters, int flags,      \
+                                    int mem, void* stream) {                                                       \
+    return kdtree_api<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, num_neighbours, row_begin,     \
+                         row_end, data_ip, nn_index, nn_dist2, counters, flags, mem, stream);                      \
+  }                                                                                                                 \
+  GI_API int gi_idw_esrg_nearest_##SUF(const R* points, int num_points, const R* data_in, const R* x_axis,         \
+                                       int len_x, const R* y_axis, int len_y, R grid_spac, int num_neighbours,     \
+                                       R* data_ip, int flags, int mem, void* stream) {                             \
+    return esrg_api<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, num_neighbours, 0,    \
+                       len_y, data_ip, nullptr, nullptr, nullptr, flags, mem, stream);                             \
+  }                                                                                                                 \
+  GI_API int gi_idw_esrg_nearest_ex_##SUF(const R* points, int num_points, const R* data_in, const R* x_axis,      \
+                                          int len_x, const R* y_axis, int len_y, R grid_spac, int num_neighbours,  \
+                                          int row_begin, int row_end, R* data_ip, int32_t* nn_index, R* nn_dist2,  \
+                                          int64_t* counters, int flags, int mem, void* stream) {                   \
+    return esrg_api<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, num_neighbours,       \
+                       row_begin, row_end, data_ip, nn_index, nn_dist2, counters, flags, mem, stream);             \
+  }                                                                                                                 \
+  GI_API int gi_barycentric_interpolation_##SUF(const R* points, int num_points, const R* data_in,                 \
+                                                const R* x_axis, int len_x, const R* y_axis, int len_y,            \
+                                                const int32_t* simplices, const int32_t* neighbours,               \
+                                                int num_triangles, R* data_ip, int flags, int mem, void* stream) { \
+    return barycentric_api<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,    \
+                              num_triangles, 0, len_y, 0, data_ip, nullptr, nullptr, nullptr, nullptr, flags, mem, \
+                              stream);                                                                              \
+  }                                                                                                                 \
+  GI_API int gi_barycentric_interpolation_ex_##SUF(                                                                 \
+      const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis, int len_y,   \
+      const int32_t* simplices, const int32_t* neighbours, int num_triangles, int row_begin, int row_end,          \
+      int halo, R* data_ip, int32_t* tri_out, uint8_t* mask_out, int64_t* fill_src, int64_t* counters, int flags,  \
+      int mem, void* stream) {                                                                                      \
+    return barycentric_api<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,    \
+                              num_triangles, row_begin, row_end, halo, data_ip, tri_out, mask_out, fill_src,       \
+                              counters, flags, mem, stream);                                                       \
+  }                                                                                                                 \
+  GI_API int gi_kd_build_##SUF(const R* points, int num_points, int32_t* order, int flags, int mem,                \
+                               void* stream) {                                                                      \
+    return kd_build_api<R>(points, num_points, order, flags, mem, stream);                                         \
+  }                                                                                                                 \
+  GI_API int gi_esrg_assign_points_to_cells_##SUF(const R* points, int num_points, const R* x_axis, int len_x,     \
+                                                  const R* y_axis, int len_y, R grid_spac, int32_t* index_of_pts,  \
+                                                  int32_t* indptr, int flags, int mem, void* stream) {             \
+    return esrg_bin_api<R>(points, num_points, x_axis, len_x, y_axis, len_y, grid_spac, index_of_pts, indptr,      \
+                           flags, mem, stream);                                                                     \
+  }                                                                                                                 \
+  GI_API int gi_fill_nearest_neighbour_##SUF(const uint8_t* mask_outside, int len_x, int len_y, R* data_ip,        \
+                                             int64_t* fill_src, int flags, int mem, void* stream) {                \
+    return fill_api<R>(mask_outside, len_x, len_y, data_ip, fill_src, flags, mem, stream);                         \
+  }
 
-GI_API int gi_idw_kdtree_f64(const double* points, int num_points, const double* data_in, const double* x_axis,
-                             int len_x, const double* y_axis, int len_y, int num_neighbours, double* data_ip,
-                             int flags, int mem, void* stream) {
-  return kdtree_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, num_neighbours, 0, len_y,
-                            data_ip, nullptr, nullptr, nullptr, flags, mem, stream);
-}
-GI_API int gi_idw_kdtree_ex_f64(const double* points, int num_points, const double* data_in, const double* x_axis,
-                                int len_x, const double* y_axis, int len_y, int num_neighbours, int row_begin,
-                                int row_end, double* data_ip, int32_t* nn_index, double* nn_dist2,
-                                int64_t* counters, int flags, int mem, void* stream) {
-  return kdtree_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, num_neighbours, row_begin,
-                            row_end, data_ip, nn_index, nn_dist2, counters, flags, mem, stream);
-}
-
-GI_API int gi_idw_esrg_nearest_f64(const double* points, int num_points, const double* data_in,
-                                   const double* x_axis, int len_x, const double* y_axis, int len_y,
-                                   double grid_spac, int num_neighbours, double* data_ip, int flags, int mem,
-                                   void* stream) {
-  return esrg_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, num_neighbours, 0,
-                          len_y, data_ip, nullptr, nullptr, nullptr, flags, mem, stream);
-}
-GI_API int gi_idw_esrg_nearest_ex_f64(const double* points, int num_points, const double* data_in,
-                                      const double* x_axis, int len_x, const double* y_axis, int len_y,
-                                      double grid_spac, int num_neighbours, int row_begin, int row_end,
-                                      double* data_ip, int32_t* nn_index, double* nn_dist2, int64_t* counters,
-                                      int flags, int mem, void* stream) {
-  return esrg_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, num_neighbours,
-                          row_begin, row_end, data_ip, nn_index, nn_dist2, counters, flags, mem, stream);
-}
-
-GI_API int gi_barycentric_interpolation_f64(const double* points, int num_points, const double* data_in,
-                                            const double* x_axis, int len_x, const double* y_axis, int len_y,
-                                            const int32_t* simplices, const int32_t* neighbours,
-                                            int num_triangles, double* data_ip, int flags, int mem,
-                                            void* stream) {
-  return barycentric_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
-                                 num_triangles, 0, len_y, 0, data_ip, nullptr, nullptr, nullptr, nullptr, flags,
-                                 mem, stream);
-}
-GI_API int gi_barycentric_interpolation_ex_f64(const double* points, int num_points, const double* data_in,
-                                               const double* x_axis, int len_x, const double* y_axis, int len_y,
-                                               const int32_t* simplices, const int32_t* neighbours,
-                                               int num_triangles, int row_begin, int row_end, int halo,
-                                               double* data_ip, int32_t* tri_out, uint8_t* mask_out,
-                                               int64_t* fill_src, int64_t* counters, int flags, int mem,
-                                               void* stream) {
-  return barycentric_api<double>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
-                                 num_triangles, row_begin, row_end, halo, data_ip, tri_out, mask_out, fill_src,
-                                 counters, flags, mem, stream);
-}
-
-GI_API int gi_kd_build_f64(const double* points, int num_points, int32_t* order, int flags, int mem, void* stream) {
-  return kd_build_api<double>(points, num_points, order, flags, mem, stream);
-}
-GI_API int gi_esrg_assign_points_to_cells_f64(const double* points, int num_points, const double* x_axis,
-                                              int len_x, const double* y_axis, int len_y, double grid_spac,
-                                              int32_t* index_of_pts, int32_t* indptr, int flags, int mem,
-                                              void* stream) {
-  return esrg_bin_api<double>(points, num_points, x_axis, len_x, y_axis, len_y, grid_spac, index_of_pts, indptr,
-                              flags, mem, stream);
-}
-GI_API int gi_fill_nearest_neighbour_f64(const uint8_t* mask_outside, int len_x, int len_y, double* data_ip,
-                                         int64_t* fill_src, int flags, int mem, void* stream) {
-  return fill_api<double>(mask_outside, len_x, len_y, data_ip, fill_src, flags, mem, stream);
-}
+GI_DEFINE_ENTRY_POINTS(f64, double)
+GI_DEFINE_ENTRY_POINTS(f32, float)

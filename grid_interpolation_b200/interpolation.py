@@ -41,6 +41,16 @@ __all__ = ["bilinear", "idw_kdtree", "idw_esrg_nearest", "barycentric_interpolat
 _F64 = np.dtype(np.float64)
 
 
+def _real(dtype):
+    """(numpy dtype, C-symbol suffix) of the arithmetic kind: float64 (graded) or float32 (as shipped)."""
+    dt = np.dtype(dtype)
+    if dt == np.float64:
+        return dt, "f64"
+    if dt == np.float32:
+        return dt, "f32"
+    raise ValueError("dtype must be float64 or float32")
+
+
 # -------------------------------------------------------------------------------------------------
 # pinned host buffers (page-locked: H2D / D2H at PCIe rate), cached because cudaHostAlloc is slow
 # -------------------------------------------------------------------------------------------------
@@ -200,8 +210,9 @@ class _Call:
         _require_device()
         if self.torch:
             import torch
-            tdtype = {np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32,
-                      np.dtype(np.uint8): torch.uint8, np.dtype(np.int64): torch.int64}[np.dtype(dtype)]
+            tdtype = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+                      np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8,
+                      np.dtype(np.int64): torch.int64}[np.dtype(dtype)]
             if order == "F" and len(shape) > 1:
                 t = torch.empty(tuple(reversed(shape)), dtype=tdtype, device=self.device)
                 view = t.permute(*reversed(range(len(shape))))
@@ -256,31 +267,32 @@ def _use_out(call, out, shape, dtype, order):
 # -------------------------------------------------------------------------------------------------
 # the four drop-in entry points
 # -------------------------------------------------------------------------------------------------
-def bilinear(x_axis, y_axis, data_in, points, *, out=None, sync=True):
+def bilinear(x_axis, y_axis, data_in, points, *, dtype=np.float64, out=None, sync=True):
     """Regular grid -> scattered points (interpolation.f90:20-100).
 
     data_in has shape (len_y, len_x), points (num_points, 2); returns data_ip (num_points,).  Points outside
     [x_axis[0], x_axis[-1]) x [y_axis[0], y_axis[-1]) get -9999.0 (interpolation.f90:44,68-78).
     """
+    rt, suf = _real(dtype)
     with _Call(data_in) as c:
-        x = c.arg(x_axis, _F64, 1, "x_axis"); y = c.arg(y_axis, _F64, 1, "y_axis")
-        d = c.arg(data_in, _F64, 2, "data_in"); p = c.arg(points, _F64, 2, "points")
+        x = c.arg(x_axis, rt, 1, "x_axis"); y = c.arg(y_axis, rt, 1, "y_axis")
+        d = c.arg(data_in, rt, 2, "data_in"); p = c.arg(points, rt, 2, "points")
         len_x, len_y = x.shape[0], y.shape[0]
         if d.shape != (len_y, len_x):
             raise ValueError(f"data_in must have shape (len_y, len_x) = {(len_y, len_x)}, got {d.shape}")
         if p.shape[1] != 2:
             raise ValueError(f"points must have shape (num_points, 2), got {p.shape}")
         n = p.shape[0]
-        res, res_ptr, _ = _use_out(c, out, (n,), _F64, "C")
+        res, res_ptr, _ = _use_out(c, out, (n,), rt, "C")
         flags = (GI_FIELD_ROWMAJOR if d.rowmajor else 0) | (GI_POINTS_ROWMAJOR if p.rowmajor else 0)
-        st = lib().gi_bilinear_f64(x.ptr, len_x, y.ptr, len_y, d.ptr, p.ptr, n, res_ptr, flags, c.mem, c.stream)
+        st = getattr(lib(), "gi_bilinear_" + suf)(x.ptr, len_x, y.ptr, len_y, d.ptr, p.ptr, n, res_ptr, flags, c.mem, c.stream)
         c.finish(st, "bilinear", sync)
         return res
 
 
-def _grid_common(c, points, data_in, x_axis, y_axis, points_shape):
-    x = c.arg(x_axis, _F64, 1, "x_axis"); y = c.arg(y_axis, _F64, 1, "y_axis")
-    p = c.arg(points, _F64, 2, "points"); d = c.arg(data_in, _F64, 1, "data_in")
+def _grid_common(c, points, data_in, x_axis, y_axis, points_shape, rt=_F64):
+    x = c.arg(x_axis, rt, 1, "x_axis"); y = c.arg(y_axis, rt, 1, "y_axis")
+    p = c.arg(points, rt, 2, "points"); d = c.arg(data_in, rt, 1, "data_in")
     if points_shape == "n2":
         if p.shape[1] != 2:
             raise ValueError(f"points must have shape (num_points, 2), got {p.shape}")
@@ -302,14 +314,15 @@ def _band(rows, len_y):
 
 
 def idw_kdtree_ex(points, data_in, x_axis, y_axis, num_neighbours, *, rows=None, order="F", debug=False,
-                  reference_visits=False, out=None, sync=True):
+                  reference_visits=False, dtype=np.float64, out=None, sync=True):
     """idw_kdtree on the row band ``rows=(begin, end)``; debug=True also returns neighbour ids / d2 / visits."""
+    rt, suf = _real(dtype)
     with _Call(points) as c:
-        x, y, p, d, n = _grid_common(c, points, data_in, x_axis, y_axis, "2n")
+        x, y, p, d, n = _grid_common(c, points, data_in, x_axis, y_axis, "2n", rt)
         len_x, len_y = x.shape[0], y.shape[0]
         r0, r1 = _band(rows, len_y)
         k = int(num_neighbours)
-        res, res_ptr, rowmajor = _use_out(c, out, (r1 - r0, len_x), _F64, order)
+        res, res_ptr, rowmajor = _use_out(c, out, (r1 - r0, len_x), rt, order)
         flags = (GI_FIELD_ROWMAJOR if rowmajor else 0) | (GI_POINTS_ROWMAJOR if p.rowmajor else 0)
         flags |= GI_KD_REFERENCE_VISITS if reference_visits else 0
         nn = d2 = cnt = None
@@ -317,9 +330,9 @@ def idw_kdtree_ex(points, data_in, x_axis, y_axis, num_neighbours, *, rows=None,
         if debug:
             shp = (r1 - r0, len_x, k) if rowmajor else (k, r1 - r0, len_x)
             nn, nn_ptr, _ = c.out(shp, np.int32, "C" if rowmajor else "F")
-            d2, d2_ptr, _ = c.out(shp, _F64, "C" if rowmajor else "F")
+            d2, d2_ptr, _ = c.out(shp, rt, "C" if rowmajor else "F")
             cnt, cnt_ptr, _ = c.out((4,), np.int64, "C")
-        st = lib().gi_idw_kdtree_ex_f64(p.ptr, n, d.ptr, x.ptr, len_x, y.ptr, len_y, k, r0, r1, res_ptr, nn_ptr,
+        st = getattr(lib(), "gi_idw_kdtree_ex_" + suf)(p.ptr, n, d.ptr, x.ptr, len_x, y.ptr, len_y, k, r0, r1, res_ptr, nn_ptr,
                                         d2_ptr, cnt_ptr, flags, c.mem, c.stream)
         c.finish(st, "idw_kdtree", sync)
         if not debug:
@@ -336,14 +349,15 @@ def idw_kdtree(points, data_in, x_axis, y_axis, num_neighbours, **kw):
 
 
 def idw_esrg_nearest_ex(points, data_in, x_axis, y_axis, grid_spac, num_neighbours, *, rows=None, order="F",
-                        debug=False, reference_order=False, out=None, sync=True):
+                        debug=False, reference_order=False, dtype=np.float64, out=None, sync=True):
     """idw_esrg_nearest on a row band; debug=True also returns neighbour ids / d2 / counters."""
+    rt, suf = _real(dtype)
     with _Call(points) as c:
-        x, y, p, d, n = _grid_common(c, points, data_in, x_axis, y_axis, "n2")
+        x, y, p, d, n = _grid_common(c, points, data_in, x_axis, y_axis, "n2", rt)
         len_x, len_y = x.shape[0], y.shape[0]
         r0, r1 = _band(rows, len_y)
         k = int(num_neighbours)
-        res, res_ptr, rowmajor = _use_out(c, out, (r1 - r0, len_x), _F64, order)
+        res, res_ptr, rowmajor = _use_out(c, out, (r1 - r0, len_x), rt, order)
         flags = (GI_FIELD_ROWMAJOR if rowmajor else 0) | (GI_POINTS_ROWMAJOR if p.rowmajor else 0)
         flags |= _lib.GI_ESRG_REFERENCE_ORDER if reference_order else 0
         nn = d2 = cnt = None
@@ -351,9 +365,9 @@ def idw_esrg_nearest_ex(points, data_in, x_axis, y_axis, grid_spac, num_neighbou
         if debug:
             shp = (r1 - r0, len_x, k) if rowmajor else (k, r1 - r0, len_x)
             nn, nn_ptr, _ = c.out(shp, np.int32, "C" if rowmajor else "F")
-            d2, d2_ptr, _ = c.out(shp, _F64, "C" if rowmajor else "F")
+            d2, d2_ptr, _ = c.out(shp, rt, "C" if rowmajor else "F")
             cnt, cnt_ptr, _ = c.out((4,), np.int64, "C")
-        st = lib().gi_idw_esrg_nearest_ex_f64(p.ptr, n, d.ptr, x.ptr, len_x, y.ptr, len_y, float(grid_spac), k,
+        st = getattr(lib(), "gi_idw_esrg_nearest_ex_" + suf)(p.ptr, n, d.ptr, x.ptr, len_x, y.ptr, len_y, float(grid_spac), k,
                                               r0, r1, res_ptr, nn_ptr, d2_ptr, cnt_ptr, flags, c.mem, c.stream)
         c.finish(st, "idw_esrg_nearest", sync)
         if not debug:
@@ -371,11 +385,12 @@ def idw_esrg_nearest(points, data_in, x_axis, y_axis, grid_spac, num_neighbours,
 
 
 def barycentric_interpolation_ex(points, data_in, x_axis, y_axis, simplices, neighbours, *, rows=None, halo=0,
-                                 order="F", debug=False, out=None, sync=True):
+                                 order="F", debug=False, dtype=np.float64, out=None, sync=True):
     """barycentric_interpolation on a row band (+ ``halo`` rows for the hull fill); debug=True also returns
     triangle ids (1-based), the outside-hull mask, fill sources and counters."""
+    rt, suf = _real(dtype)
     with _Call(points) as c:
-        x, y, p, d, n = _grid_common(c, points, data_in, x_axis, y_axis, "n2")
+        x, y, p, d, n = _grid_common(c, points, data_in, x_axis, y_axis, "n2", rt)
         s = c.arg(simplices, np.dtype(np.int32), 2, "simplices")
         nb = c.arg(neighbours, np.dtype(np.int32), 2, "neighbours")
         t = s.shape[0]
@@ -387,7 +402,7 @@ def barycentric_interpolation_ex(points, data_in, x_axis, y_axis, simplices, nei
             nb = c.arg(_reorder(nb.keep, s.rowmajor), np.dtype(np.int32), 2, "neighbours")
         len_x, len_y = x.shape[0], y.shape[0]
         r0, r1 = _band(rows, len_y)
-        res, res_ptr, rowmajor = _use_out(c, out, (r1 - r0, len_x), _F64, order)
+        res, res_ptr, rowmajor = _use_out(c, out, (r1 - r0, len_x), rt, order)
         flags = ((GI_FIELD_ROWMAJOR if rowmajor else 0) | (GI_POINTS_ROWMAJOR if p.rowmajor else 0)
                  | (GI_TOPO_ROWMAJOR if s.rowmajor else 0))
         tri = mask = src = cnt = None
@@ -398,7 +413,7 @@ def barycentric_interpolation_ex(points, data_in, x_axis, y_axis, simplices, nei
             mask, mask_ptr, _ = c.out((r1 - r0, len_x), np.uint8, o)
             src, src_ptr, _ = c.out((r1 - r0, len_x), np.int64, o)
             cnt, cnt_ptr, _ = c.out((4,), np.int64, "C")
-        st = lib().gi_barycentric_interpolation_ex_f64(p.ptr, n, d.ptr, x.ptr, len_x, y.ptr, len_y, s.ptr, nb.ptr,
+        st = getattr(lib(), "gi_barycentric_interpolation_ex_" + suf)(p.ptr, n, d.ptr, x.ptr, len_x, y.ptr, len_y, s.ptr, nb.ptr,
                                                        t, r0, r1, int(halo), res_ptr, tri_ptr, mask_ptr, src_ptr,
                                                        cnt_ptr, flags, c.mem, c.stream)
         c.finish(st, "barycentric_interpolation", sync)

@@ -185,6 +185,39 @@ int gi_esrg_assign_points_to_cells_f64(const double* points, int num_points, con
 int gi_fill_nearest_neighbour_f64(const uint8_t* mask_outside, int len_x, int len_y, double* data_ip,
                                   int64_t* fill_src, int flags, int mem, void* stream);
 
+/* ---- single precision (the reference as shipped: every REAL is default kind) ------------- */
+/* Same entry points, argument meaning and flags with float instead of double (grid_spac included). */
+int gi_idw_kdtree_f32(const float* points, int num_points, const float* data_in, const float* x_axis, int len_x,
+                      const float* y_axis, int len_y, int num_neighbours, float* data_ip, int flags, int mem,
+                      void* stream);
+int gi_idw_esrg_nearest_f32(const float* points, int num_points, const float* data_in, const float* x_axis,
+                            int len_x, const float* y_axis, int len_y, float grid_spac, int num_neighbours,
+                            float* data_ip, int flags, int mem, void* stream);
+int gi_barycentric_interpolation_f32(const float* points, int num_points, const float* data_in,
+                                     const float* x_axis, int len_x, const float* y_axis, int len_y,
+                                     const int32_t* simplices, const int32_t* neighbours, int num_triangles,
+                                     float* data_ip, int flags, int mem, void* stream);
+int gi_barycentric_interpolation_ex_f32(const float* points, int num_points, const float* data_in,
+                                        const float* x_axis, int len_x, const float* y_axis, int len_y,
+                                        const int32_t* simplices, const int32_t* neighbours, int num_triangles,
+                                        int row_begin, int row_end, int halo, float* data_ip, int32_t* tri_out,
+                                        uint8_t* mask_out, int64_t* fill_src, int64_t* counters, int flags,
+                                        int mem, void* stream);
+int gi_idw_kdtree_ex_f32(const float* points, int num_points, const float* data_in, const float* x_axis,
+                         int len_x, const float* y_axis, int len_y, int num_neighbours, int row_begin,
+                         int row_end, float* data_ip, int32_t* nn_index, float* nn_dist2, int64_t* counters,
+                         int flags, int mem, void* stream);
+int gi_idw_esrg_nearest_ex_f32(const float* points, int num_points, const float* data_in, const float* x_axis,
+                               int len_x, const float* y_axis, int len_y, float grid_spac, int num_neighbours,
+                               int row_begin, int row_end, float* data_ip, int32_t* nn_index, float* nn_dist2,
+                               int64_t* counters, int flags, int mem, void* stream);
+int gi_kd_build_f32(const float* points, int num_points, int32_t* order, int flags, int mem, void* stream);
+int gi_esrg_assign_points_to_cells_f32(const float* points, int num_points, const float* x_axis, int len_x,
+                                       const float* y_axis, int len_y, float grid_spac, int32_t* index_of_pts,
+                                       int32_t* indptr, int flags, int mem, void* stream);
+int gi_fill_nearest_neighbour_f32(const uint8_t* mask_outside, int len_x, int len_y, float* data_ip,
+                                  int64_t* fill_src, int flags, int mem, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -313,3 +313,30 @@ def test_medium_mesh_matches_oracle_and_properties():
     nodes = np.stack([xx[:-1, :-1].ravel(), yy[:-1, :-1].ravel()], 1)
     back = ip.bilinear(axis, axis, got, nodes)
     assert np.array_equal(back, got[:-1, :-1].ravel())
+
+
+# ------------------------------------------------------------- single precision (the shipped numerics)
+def test_f32_entry_points_match_f32_oracle(c1):
+    """The reference as shipped is single precision: the _f32 entry points must reproduce the f32
+    oracle bit for bit (same operations, IEEE single division / sqrt, no FMA contraction)."""
+    f = np.float32
+    pts, dat, xa, ya = c1.points.astype(f), c1.data_pts.astype(f), c1.x_axis.astype(f), c1.y_axis.astype(f)
+    # barycentric: the f32 margin (-1e-10f) and f32 cross products decide the triangles
+    want, w = orc.barycentric_interpolation(pts, dat, xa, ya, c1.simplices, c1.neighbours, dtype=f, debug=True)
+    got, g = ip.barycentric_interpolation_ex(pts, dat, xa, ya, c1.simplices, c1.neighbours, dtype=f, debug=True)
+    assert got.dtype == f and np.array_equal(g.mask, w.mask)
+    ins = ~w.mask
+    assert np.array_equal(g.tri[ins], w.tri[ins])
+    assert np.array_equal(got, want)
+    # esrg / k-d tree
+    spac = f(c1.grid_spac)
+    want_e, we = orc.idw_esrg_nearest(pts, dat, xa, ya, spac, 6, dtype=f, debug=True)
+    got_e, ge = ip.idw_esrg_nearest_ex(pts, dat, xa, ya, spac, 6, dtype=f, debug=True)
+    assert np.array_equal(ge.nn_index, np.moveaxis(we.nn_index, 0, -1)) and np.array_equal(got_e, want_e)
+    want_k, wk = orc.idw_kdtree(pts.T, dat, xa, ya, 6, dtype=f, debug=True)
+    got_k, gk = ip.idw_kdtree_ex(pts.T, dat, xa, ya, 6, dtype=f, debug=True)
+    assert np.array_equal(gk.nn_index, np.moveaxis(wk.nn_index, 0, -1)) and np.array_equal(got_k, want_k)
+    # bilinear
+    want_b = orc.bilinear(xa, ya, want_e, pts, dtype=f)
+    got_b = ip.bilinear(xa, ya, got_e, pts, dtype=f)
+    assert got_b.dtype == f and np.array_equal(got_b, want_b)
