@@ -1,0 +1,110 @@
+"""Edge cases of the four entry points against the oracle (GPU): tiny / degenerate sizes, k at its limits,
+empty bands, points outside the grid, mostly-masked fields."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from grid_interpolation_b200 import interpolation as ip  # noqa: E402
+from grid_interpolation_b200 import workloads  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+def same(a, b):
+    assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_single_triangle_mostly_outside():
+    pts = np.array([[2.0, 1.0], [9.0, 2.5], [4.0, 8.0]])
+    simp = np.array([[1, 2, 3]], np.int32); nbr = np.zeros((1, 3), np.int32)
+    data = np.array([1.0, -2.0, 5.0])
+    x = np.linspace(0.0, 12.0, 37); y = np.linspace(-3.0, 11.0, 29)
+    want, w = orc.barycentric_interpolation(pts, data, x, y, simp, nbr, debug=True)
+    got, g = ip.barycentric_interpolation_ex(pts, data, x, y, simp, nbr, debug=True)
+    assert w.mask.mean() > 0.7 and w.fill_level_max >= 8
+    same(g.mask, w.mask); same(g.fill_src, w.fill_src); same(got, want)
+
+
+def test_grid_entirely_outside_the_mesh_reports_instead_of_hanging():
+    pts = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+    simp = np.array([[1, 2, 3]], np.int32); nbr = np.zeros((1, 3), np.int32)
+    x = np.linspace(5.0, 6.0, 4); y = np.linspace(5.0, 6.0, 3)
+    with pytest.raises(RuntimeError, match="cap"):       # reference: fill_nearest_neighbour loops forever
+        ip.barycentric_interpolation(pts, np.ones(3), x, y, simp, nbr)
+
+
+def test_one_by_one_grid_and_empty_band(c1):
+    x = c1.x_axis[40:41]; y = c1.y_axis[30:31]
+    same(ip.barycentric_interpolation(c1.points, c1.data_pts, x, y, c1.simplices, c1.neighbours),
+         orc.barycentric_interpolation(c1.points, c1.data_pts, x, y, c1.simplices, c1.neighbours))
+    same(ip.idw_esrg_nearest(c1.points, c1.data_pts, x, y, c1.grid_spac, 6),
+         orc.idw_esrg_nearest(c1.points, c1.data_pts, x, y, c1.grid_spac, 6))
+    same(ip.idw_kdtree(c1.points.T, c1.data_pts, x, y, 6), orc.idw_kdtree(c1.points.T, c1.data_pts, x, y, 6))
+    empty = ip.idw_esrg_nearest_ex(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, 6, rows=(7, 7))
+    assert empty.shape == (0, c1.x_axis.size)
+
+
+@pytest.mark.parametrize("k", [1, 2, 16, 17, 32])
+def test_k_limits(c1, k):
+    sub = slice(0, 600)
+    pts, dat = c1.points[sub], c1.data_pts[sub]
+    x, y = c1.x_axis[::3], c1.y_axis[::3]
+    spac = c1.grid_spac * 3
+    want, w = orc.idw_esrg_nearest(pts, dat, x, y, spac, k, debug=True)
+    got, g = ip.idw_esrg_nearest_ex(pts, dat, x, y, spac, k, debug=True)
+    same(g.nn_index, np.moveaxis(w.nn_index, 0, -1)); same(got, want)
+    want, w = orc.idw_kdtree(pts.T, dat, x, y, k, debug=True)
+    got, g = ip.idw_kdtree_ex(pts.T, dat, x, y, k, debug=True)
+    same(g.nn_index, np.moveaxis(w.nn_index, 0, -1)); same(got, want)
+
+
+def test_k_above_32_is_rejected(c1):
+    with pytest.raises(ValueError):
+        ip.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, 33)
+    with pytest.raises(ValueError):
+        ip.idw_kdtree(c1.points.T, c1.data_pts, c1.x_axis, c1.y_axis, 33)
+
+
+def test_esrg_exactly_k_points_and_points_outside_grid():
+    rng = np.random.default_rng(8)
+    pts = rng.uniform(-4.0, 14.0, (8, 2))           # several outside the 10 x 7 grid -> clamped cells
+    dat = rng.normal(size=8)
+    x = np.arange(10.0); y = np.arange(7.0)
+    want, w = orc.idw_esrg_nearest(pts, dat, x, y, 1.0, 8, debug=True)
+    got, g = ip.idw_esrg_nearest_ex(pts, dat, x, y, 1.0, 8, debug=True)
+    same(g.nn_index, np.moveaxis(w.nn_index, 0, -1)); same(got, want)
+    idx, ptr = ip.assign_points_to_cells(pts, x, y, 1.0)
+    oi, op, _ = orc.assign_points_to_cells(pts, x, y, 1.0)
+    same(idx, oi); same(ptr[:-1].reshape(7, 10) + 1, op)
+
+
+def test_kdtree_fewer_points_than_k():
+    """Slots that never fill keep the sentinel distance and an undefined id in the reference
+    (interpolation.f90:151,159); both sides define id 0 / value 0 for them."""
+    rng = np.random.default_rng(9)
+    pts = rng.uniform(0.0, 5.0, (2, 3)); dat = rng.normal(size=3)
+    x = np.linspace(0, 5, 6); y = np.linspace(0, 5, 5)
+    want, w = orc.idw_kdtree(pts, dat, x, y, 5, debug=True)
+    got, g = ip.idw_kdtree_ex(pts, dat, x, y, 5, debug=True)
+    assert (w.nn_index == 0).any()
+    same(g.nn_index, np.moveaxis(w.nn_index, 0, -1)); same(got, want)
+
+
+def test_bilinear_two_node_axes_and_boundaries():
+    x = np.array([1.0, 3.0]); y = np.array([-1.0, 0.5])
+    f = np.array([[1.0, 2.0], [3.0, 5.0]])
+    pts = np.array([[1.0, -1.0], [2.9999999, 0.4999999], [3.0, 0.0], [2.0, 0.5], [0.999, 0.0], [2.0, -0.25]])
+    same(ip.bilinear(x, y, f, pts), orc.bilinear(x, y, f, pts))
+
+
+def test_non_contiguous_and_integer_inputs_are_converted_like_f2py(c1):
+    pts = np.asfortranarray(c1.points)[::2]                       # strided view
+    dat = c1.data_pts[::2]
+    simp, nbr = workloads.delaunay(np.ascontiguousarray(pts))
+    want = orc.barycentric_interpolation(pts, dat, c1.x_axis, c1.y_axis, simp, nbr)
+    got = ip.barycentric_interpolation(pts, dat.astype(np.float32).astype(np.float64), list(c1.x_axis), c1.y_axis,
+                                       simp.astype(np.int64), nbr.astype(np.int64))
+    want2 = orc.barycentric_interpolation(pts, dat.astype(np.float32).astype(np.float64), c1.x_axis, c1.y_axis,
+                                          simp, nbr)
+    same(got, want2)
+    assert want.shape == got.shape
