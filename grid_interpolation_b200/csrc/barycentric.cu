@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   R c1 = 0, q1 = 0, c2 = 0, q2 = 0, p3 = 0, d1 = 0, d2 = 0, d3 = 0;
   DivRcp<R> dv;
   dv.d = R(1); dv.r2 = R(1);
+#pragma unroll 2
   for (int r = 0; r < nrows; ++r) {
     const int s = srow0 + r;
     const int t = active ? stri[r][tid] : 0;

@@ -260,7 +260,9 @@ template <class R> struct alignas(16) StackEntry {
   R adiff;  // |diff| of the parent; sign bit = parity of the subtree's depth
 };
 
-template <class R, int KC, bool REFVISITS>
+// PRUNE: 0 = reference rule + state-preserving skip (default), 1 = reference rule only (visit-count parity),
+// 2 = exact rule diff*diff < max d2 (extension: exact kNN)
+template <class R, int KC, int PRUNE>
 __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
   const TargetWindow<R>& w = a.win;
   // a warp owns a compact 8 x 4 patch of targets (8 along the contiguous output axis): neighbouring targets
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
         const StackEntry<R> e = stack[--sp];
         const R ad = fabs(e.adiff);
         // :191,:198 the reference's rule; second term: provably state-preserving skip (see file header)
-        if (ad < tk.dlast && (REFVISITS || ad * ad < tk.dlast)) {
+        if (PRUNE == 2 ? ad * ad < tk.dlast : (ad < tk.dlast && (PRUNE == 1 || ad * ad < tk.dlast))) {
           lo = e.lo; hi = e.hi;
           depth = signbit(e.adiff) ? 1 : 0;  // only the parity of the depth is ever used
           got = true;
@@ -339,9 +341,10 @@ __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
 }
 
 template <class R, int KC>
-void launch_query(const KdArgs<R>& a, bool refvisits, dim3 grid, cudaStream_t st) {
-  if (refvisits) kd_query_kernel<R, KC, true><<<grid, 128, 0, st>>>(a);
-  else kd_query_kernel<R, KC, false><<<grid, 128, 0, st>>>(a);
+void launch_query(const KdArgs<R>& a, int prune, dim3 grid, cudaStream_t st) {
+  if (prune == 2) kd_query_kernel<R, KC, 2><<<grid, 128, 0, st>>>(a);
+  else if (prune == 1) kd_query_kernel<R, KC, 1><<<grid, 128, 0, st>>>(a);
+  else kd_query_kernel<R, KC, 0><<<grid, 128, 0, st>>>(a);
 }
 
 }  // namespace
@@ -378,11 +381,11 @@ int kdtree_device(const R* points, int num_points, const R* data_in, const R* x_
   a.counters = counters_out ? counters : nullptr; a.status = slot.dev;
   dim3 grid(div_up(a.win.nf(), 32), div_up(a.win.ns(), 4));
   GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
-  const bool refvisits = flags & GI_KD_REFERENCE_VISITS;
-  if (k <= 4) launch_query<R, 4>(a, refvisits, grid, st);
-  else if (k <= 8) launch_query<R, 8>(a, refvisits, grid, st);
-  else if (k <= 16) launch_query<R, 16>(a, refvisits, grid, st);
-  else launch_query<R, 32>(a, refvisits, grid, st);
+  const int prune = (flags & GI_KD_EXACT_PRUNE) ? 2 : ((flags & GI_KD_REFERENCE_VISITS) ? 1 : 0);
+  if (k <= 4) launch_query<R, 4>(a, prune, grid, st);
+  else if (k <= 8) launch_query<R, 8>(a, prune, grid, st);
+  else if (k <= 16) launch_query<R, 16>(a, prune, grid, st);
+  else launch_query<R, 32>(a, prune, grid, st);
   GI_CUDA(cudaGetLastError());
   ph.finish();
   if (counters_out)

@@ -314,8 +314,9 @@ def _band(rows, len_y):
 
 
 def idw_kdtree_ex(points, data_in, x_axis, y_axis, num_neighbours, *, rows=None, order="F", debug=False,
-                  reference_visits=False, dtype=np.float64, out=None, sync=True):
-    """idw_kdtree on the row band ``rows=(begin, end)``; debug=True also returns neighbour ids / d2 / visits."""
+                  reference_visits=False, exact_prune=False, dtype=np.float64, out=None, sync=True):
+    """idw_kdtree on the row band ``rows=(begin, end)``; debug=True also returns neighbour ids / d2 / visits.
+    ``exact_prune=True`` (extension) replaces the reference's prune rule by the geometrically correct one."""
     rt, suf = _real(dtype)
     with _Call(points) as c:
         x, y, p, d, n = _grid_common(c, points, data_in, x_axis, y_axis, "2n", rt)
@@ -325,6 +326,7 @@ def idw_kdtree_ex(points, data_in, x_axis, y_axis, num_neighbours, *, rows=None,
         res, res_ptr, rowmajor = _use_out(c, out, (r1 - r0, len_x), rt, order)
         flags = (GI_FIELD_ROWMAJOR if rowmajor else 0) | (GI_POINTS_ROWMAJOR if p.rowmajor else 0)
         flags |= GI_KD_REFERENCE_VISITS if reference_visits else 0
+        flags |= _lib.GI_KD_EXACT_PRUNE if exact_prune else 0
         nn = d2 = cnt = None
         nn_ptr = d2_ptr = cnt_ptr = None
         if debug:

@@ -67,6 +67,10 @@ typedef enum {
 #define GI_POINTS_ROWMAJOR 1 /* points array is C-order instead of Fortran order */
 #define GI_TOPO_ROWMAJOR 2   /* simplices / neighbours are C-order (num_triangles,3) */
 #define GI_FIELD_ROWMAJOR 4  /* data_in (bilinear) / data_ip (grid outputs): element (iy,ix) at iy*len_x + ix */
+#define GI_KD_EXACT_PRUNE 32 /* idw_kdtree: prune the far subtree iff diff*diff >= max d2 (the geometrically correct
+                               rule) instead of the reference's abs(diff) >= max d2 -> exact k nearest neighbours
+                               even where the k-th d2 is < 1.  An extension (the reference README's to-do list);
+                               results then differ from the reference's wherever its rule is too eager. */
 #define GI_ESRG_REFERENCE_ORDER 16 /* idw_esrg_nearest: process every target in the reference's candidate order
                                       (debug).  Default: only targets with exactly equal neighbour distances,
                                       the only case in which that order changes the result. */
