@@ -94,6 +94,111 @@ bilinear_kernel(const R* __restrict__ x_axis, int len_x, const R* __restrict__ y
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sector-load variant (f64).  A micro-benchmark (bench/gather_probe.cu) shows that random gathers from a field
+// far larger than L2 run at a fixed ~50 G load requests/s on B200 whatever the load flavour or row pitch --
+// the limit is the number of outstanding L1 misses per SM, not DRAM bytes.  So the kernel minimises REQUESTS:
+// the two field values that are adjacent in memory come from ONE aligned 256-bit load of their 32 B sector
+// (plus one scalar load in the 1-in-4 case that the pair straddles two sectors), and the axis pairs likewise:
+// 5 requests per point instead of 8.  Needs a 32 B aligned field whose contiguous extent is a multiple of 4.
+// `fast` = the unit-stride axis of the field (x for row-major, y for column-major).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld_sector(const double* p, double (&v)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+// v = the aligned sector holding element i; returns elements i and i+1 (the latter from `next` if i % 4 == 3)
+__device__ __forceinline__ void pick_pair(const double (&v)[4], int o, double next, double& e0, double& e1) {
+  e0 = o == 0 ? v[0] : (o == 1 ? v[1] : (o == 2 ? v[2] : v[3]));
+  e1 = o == 0 ? v[1] : (o == 1 ? v[2] : (o == 2 ? v[3] : next));
+}
+
+constexpr int kVecPts = 2;
+
+template <bool ROWMAJOR>
+__global__ void __launch_bounds__(kThreads)
+bilinear_sector_kernel(const double* __restrict__ x_axis, int len_x, const double* __restrict__ y_axis, int len_y,
+                       const double* __restrict__ data, PointsView<double> pts, int64_t n,
+                       const double* __restrict__ inv, double* __restrict__ out) {
+  const double dx_inv = __ldg(inv), dy_inv = __ldg(inv + 1);
+  const double x_first = __ldg(x_axis), y_first = __ldg(y_axis);
+  const double scale = dx_inv * dy_inv;                                   // :93
+  const int64_t pitch = ROWMAJOR ? len_x : len_y;                         // elements between two fast-axis runs
+  const int64_t base = (int64_t)blockIdx.x * (kThreads * kVecPts) + threadIdx.x;
+  double px[kVecPts], py[kVecPts];
+  int ix[kVecPts], iy[kVecPts];
+  bool ok[kVecPts];
+#pragma unroll
+  for (int j = 0; j < kVecPts; ++j) {
+    const int64_t i = base + (int64_t)j * kThreads;
+    if (i < n) { px[j] = pts.x(i); py[j] = pts.y(i); }
+    else { px[j] = x_first; py[j] = y_first; }
+    const double fx = floor((px[j] - x_first) * dx_inv);                  // :67
+    const double fy = floor((py[j] - y_first) * dy_inv);                  // :73
+    ok[j] = fx >= 0.0 && fx < double(len_x - 1) && fy >= 0.0 && fy < double(len_y - 1);
+    ix[j] = ok[j] ? (int)fx : 0;
+    iy[j] = ok[j] ? (int)fy : 0;
+  }
+  double fa[kVecPts][4], fb[kVecPts][4], xs[kVecPts][4], ys[kVecPts][4], fan[kVecPts], fbn[kVecPts], xn[kVecPts],
+      yn[kVecPts];
+#pragma unroll
+  for (int j = 0; j < kVecPts; ++j) {  // issue every load of every point before the first use
+    const int fi = ROWMAJOR ? ix[j] : iy[j], si = ROWMAJOR ? iy[j] : ix[j];
+    const double* p = data + (int64_t)si * pitch + (fi & ~3);
+    ld_sector(p, fa[j]);
+    ld_sector(p + pitch, fb[j]);
+    ld_sector(x_axis + (ix[j] & ~3), xs[j]);
+    ld_sector(y_axis + (iy[j] & ~3), ys[j]);
+    fan[j] = (fi & 3) == 3 ? __ldg(p + 4) : 0.0;
+    fbn[j] = (fi & 3) == 3 ? __ldg(p + pitch + 4) : 0.0;
+    xn[j] = (ix[j] & 3) == 3 ? __ldg(x_axis + ix[j] + 1) : 0.0;
+    yn[j] = (iy[j] & 3) == 3 ? __ldg(y_axis + iy[j] + 1) : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < kVecPts; ++j) {
+    const int64_t i = base + (int64_t)j * kThreads;
+    if (i >= n) continue;
+    const int fi = ROWMAJOR ? ix[j] : iy[j];
+    double a0, a1, b0, b1, xa, xb, ya, yb;
+    pick_pair(fa[j], fi & 3, fan[j], a0, a1);
+    pick_pair(fb[j], fi & 3, fbn[j], b0, b1);
+    pick_pair(xs[j], ix[j] & 3, xn[j], xa, xb);
+    pick_pair(ys[j], iy[j] & 3, yn[j], ya, yb);
+    // data_in(ind_y, ind_x), (ind_y+1, ind_x), (ind_y, ind_x+1), (ind_y+1, ind_x+1)
+    const double d11 = a0, d12 = ROWMAJOR ? b0 : a1, d21 = ROWMAJOR ? a1 : b0, d22 = b1;
+    const double w11 = (xb - px[j]) * (yb - py[j]);                       // :81-88
+    const double w12 = (xb - px[j]) * (py[j] - ya);
+    const double w21 = (px[j] - xa) * (yb - py[j]);
+    const double w22 = (px[j] - xa) * (py[j] - ya);
+    const double v = (w11 * d11 + w12 * d12 + w21 * d21 + w22 * d22) * scale;  // :90-93
+    out[i] = ok[j] ? v : Consts<double>::ofb();                           // :44,:69,:75
+  }
+}
+
+template <class R> struct SectorPath {
+  static bool launch(const R*, int, const R*, int, const R*, PointsView<R>, int64_t, const R*, R*, bool,
+                     cudaStream_t) { return false; }
+};
+template <> struct SectorPath<double> {
+  static bool launch(const double* x_axis, int len_x, const double* y_axis, int len_y, const double* data,
+                     PointsView<double> pv, int64_t n, const double* inv, double* out, bool rowmajor,
+                     cudaStream_t st) {
+    const int64_t pitch = rowmajor ? len_x : len_y;
+    // aligned sector loads must stay inside the arrays: 32 B aligned bases, extents that are multiples of 4
+    if ((reinterpret_cast<uintptr_t>(data) & 31) || (reinterpret_cast<uintptr_t>(x_axis) & 31) ||
+        (reinterpret_cast<uintptr_t>(y_axis) & 31) || (pitch & 3) || (len_x & 3) || (len_y & 3))
+      return false;
+    const int64_t blocks = (n + kThreads * kVecPts - 1) / (kThreads * kVecPts);
+    if (blocks > 0x7fffffffLL) return false;
+    if (rowmajor)
+      bilinear_sector_kernel<true><<<(unsigned)blocks, kThreads, 0, st>>>(x_axis, len_x, y_axis, len_y, data, pv, n,
+                                                                        inv, out);
+    else
+      bilinear_sector_kernel<false><<<(unsigned)blocks, kThreads, 0, st>>>(x_axis, len_x, y_axis, len_y, data, pv,
+                                                                         n, inv, out);
+    return true;
+  }
+};
+
 }  // namespace
 
 template <class R>
@@ -113,11 +218,13 @@ int bilinear_device(const R* x_axis, int len_x, const R* y_axis, int len_y, cons
   ph.mark("bilinear");
   const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
   const int64_t sy = rowmajor ? len_x : 1, sx = rowmajor ? 1 : len_y;
-  const int64_t blocks = (num_points + kThreads * kPts - 1) / (kThreads * kPts);
-  GI_REQUIRE(blocks <= 0x7fffffffLL, "too many points for one launch");
-  bilinear_kernel<R><<<(unsigned)blocks, kThreads, 0, st>>>(
-      x_axis, len_x, y_axis, len_y, data_in, sy, sx, points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR),
-      num_points, inv, data_ip);
+  const PointsView<R> pv = points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR);
+  if (!SectorPath<R>::launch(x_axis, len_x, y_axis, len_y, data_in, pv, num_points, inv, data_ip, rowmajor, st)) {
+    const int64_t blocks = (num_points + kThreads * kPts - 1) / (kThreads * kPts);
+    GI_REQUIRE(blocks <= 0x7fffffffLL, "too many points for one launch");
+    bilinear_kernel<R><<<(unsigned)blocks, kThreads, 0, st>>>(x_axis, len_x, y_axis, len_y, data_in, sy, sx, pv,
+                                                             num_points, inv, data_ip);
+  }
   GI_CUDA(cudaGetLastError());
   ph.finish();
   return GI_OK;

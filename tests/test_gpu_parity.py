@@ -357,3 +357,18 @@ def test_kdtree_exact_prune_extension(c1):
     # ... and it differs from the reference rule on this geometry (~53 % of the targets)
     _, gr = ip.idw_kdtree_ex(c1.points.T, c1.data_pts, c1.x_axis, c1.y_axis, k, debug=True, order="C")
     assert (np.sort(gr.nn_index, -1) != np.sort(g.nn_index, -1)).any(-1).mean() > 0.4
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_bilinear_sector_load_path(order):
+    """Axes whose lengths are multiples of 4 take the 256-bit sector-load kernel (bilinear.cu); it must agree with
+    the scalar kernel's oracle bit for bit, including points in every position modulo 4 and out-of-grid points."""
+    rng = np.random.default_rng(12)
+    x = np.cumsum(rng.uniform(0.5, 1.5, 64)); y = np.cumsum(rng.uniform(0.2, 0.4, 48)) - 3.0
+    field = rng.normal(size=(48, 64))
+    pts = np.stack([rng.uniform(x[0] - 1, x[-1] + 1, 50021), rng.uniform(y[0] - 1, y[-1] + 1, 50021)], 1)
+    pts[:4] = [[x[0], y[0]], [x[-1], y[-1]], [np.nextafter(x[-1], 0), np.nextafter(y[-1], 0)], [np.nan, 1.0]]
+    want = orc.bilinear(x, y, field, pts)
+    f = np.ascontiguousarray(field) if order == "C" else np.asfortranarray(field)
+    p = np.ascontiguousarray(pts) if order == "C" else np.asfortranarray(pts)
+    assert_values(ip.bilinear(x, y, f, p), want)
