@@ -20,7 +20,7 @@ out = torch.empty((grid, grid), dtype=torch.float64, device=dev)
 ref = None
 for order in ("C",):
     for v in variants:
-        os.environ["GI_WALK_VARIANT"] = str(v)
+        os.environ["GI_WALK_VARIANT"] = str(v)  # (the kernel no longer has variants; kept for re-use)
         for _ in range(3):
             ip.barycentric_interpolation_ex(*args, out=out, sync=False)
         torch.cuda.synchronize()
