@@ -125,26 +125,30 @@ template <> struct DivRcp<float> {
 };
 
 
+// seed-grid geometry from the axes (a uniform-axis approximation: seeds only have to be near)
 template <class R>
-__global__ void seed_setup_kernel(const R* x_axis, int len_x, const R* y_axis, int len_y, SeedGrid<R>* sg) {
+__device__ __forceinline__ SeedGrid<R> seed_grid_of(const R* __restrict__ x_axis, int len_x,
+                                                    const R* __restrict__ y_axis, int len_y) {
   SeedGrid<R> s;
   s.ncx = (len_x + kSeedCell - 1) / kSeedCell;
   s.ncy = (len_y + kSeedCell - 1) / kSeedCell;
-  s.x0 = x_axis[0];
-  s.y0 = y_axis[0];
-  const R ex = x_axis[len_x - 1] - x_axis[0], ey = y_axis[len_y - 1] - y_axis[0];
+  s.x0 = __ldg(x_axis);
+  s.y0 = __ldg(y_axis);
+  const R ex = __ldg(x_axis + len_x - 1) - s.x0, ey = __ldg(y_axis + len_y - 1) - s.y0;
   s.inv_cell_x = (len_x > 1 && ex > R(0)) ? R(len_x - 1) / ex / R(kSeedCell) : R(0);
   s.inv_cell_y = (len_y > 1 && ey > R(0)) ? R(len_y - 1) / ey / R(kSeedCell) : R(0);
-  *sg = s;
+  return s;
 }
 
 template <class R>
 __global__ void __launch_bounds__(256)
 pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, TopoView nbr, int num_points,
-                 int num_tri, TriGeom<R>* __restrict__ geom, int* __restrict__ seed, const SeedGrid<R>* __restrict__ sgp, int* __restrict__ status) {
+                 int num_tri, TriGeom<R>* __restrict__ geom, int* __restrict__ seed,
+                 const R* __restrict__ x_axis, int len_x, const R* __restrict__ y_axis, int len_y,
+                 int* __restrict__ status) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= num_tri) return;
-  const SeedGrid<R> sg = *sgp;
+  const SeedGrid<R> sg = seed_grid_of(x_axis, len_x, y_axis, len_y);
   int a = simp(t, 0), b = simp(t, 1), c = simp(t, 2);
   int n1 = nbr(t, 0), n2 = nbr(t, 1), n3 = nbr(t, 2);
   const bool bad = (unsigned)(a - 1) >= (unsigned)num_points || (unsigned)(b - 1) >= (unsigned)num_points ||
@@ -442,16 +446,6 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
 // column by column.
 // ---------------------------------------------------------------------------------------------
 template <class R>
-__global__ void start_tri_setup_kernel(const R* __restrict__ y_axis, int len_y, int64_t* counters, R* opt_y) {
-  if (counters[5] == 0) return;
-  R sum = R(0);
-  for (int i = 0; i < len_y; ++i) sum = sum + y_axis[i];                  // SUM(y_axis), interpolation.f90:345
-  *opt_y = sum / R(len_y);
-  counters[6] = (int64_t)0x7fffffffffffffffll;
-  counters[7] = (int64_t)0x7fffffffffffffffll;
-}
-
-template <class R>
 __device__ __forceinline__ unsigned long long start_tri_dist(const TriGeom<R>* geom, int i, R opt_x, R opt_y) {
   TriGeom<R> g;
   load_walk(geom + i, g);
@@ -460,21 +454,40 @@ __device__ __forceinline__ unsigned long long start_tri_dist(const TriGeom<R>* g
   return (unsigned long long)__double_as_longlong(d);  // non-negative doubles order like their bit patterns
 }
 
-// pass 0: minimum distance; pass 1: smallest index attaining it (strict '<' keeps the first, :351-354)
+// The reference's ind_tri_start (interpolation.f90:342-355): arg-min of the centroid distance to
+// (x_axis(1), SUM(y_axis)/len_y) over the first min(num_points, num_triangles) triangles, first minimum wins.
+// One CTA, and only when a target was flagged (it returns at once otherwise): the result is needed only by
+// fix-ups that reach column 0.
 template <class R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 start_tri_kernel(const TriGeom<R>* __restrict__ geom, int n_search, const R* __restrict__ x_axis,
-                 const R* __restrict__ opt_y, int64_t* counters, int pass) {
+                 const R* __restrict__ y_axis, int len_y, int64_t* counters) {
   if (counters[5] == 0) return;
-  const R ox = __ldg(x_axis), oy = *opt_y;
-  unsigned long long best = ~0ull;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_search; i += gridDim.x * blockDim.x) {
-    const unsigned long long d = start_tri_dist(geom, i, ox, oy);
-    if (pass == 0) best = min(best, d);
-    else if (d == (unsigned long long)counters[6]) best = min(best, (unsigned long long)i);
+  __shared__ R s_opt_y;
+  __shared__ unsigned long long s_best;
+  if (threadIdx.x == 0) {
+    R sum = R(0);
+    for (int i = 0; i < len_y; ++i) sum = sum + y_axis[i];                // SUM(y_axis), :345 (serial order)
+    s_opt_y = sum / R(len_y);
   }
-  for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
-  if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin((unsigned long long*)(counters + 6 + pass), best);
+  const R ox = __ldg(x_axis);
+  for (int pass = 0; pass < 2; ++pass) {  // 0: minimum distance, 1: smallest index attaining it (strict '<', :351)
+    const unsigned long long dmin = pass ? s_best : 0ull;
+    __syncthreads();
+    if (threadIdx.x == 0) s_best = ~0ull;
+    __syncthreads();
+    const R oy = s_opt_y;
+    unsigned long long best = ~0ull;
+    for (int i = threadIdx.x; i < n_search; i += blockDim.x) {
+      const unsigned long long d = start_tri_dist(geom, i, ox, oy);
+      if (pass == 0) best = min(best, d);
+      else if (d == dmin) best = min(best, (unsigned long long)i);
+    }
+    for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if ((threadIdx.x & 31) == 0) atomicMin(&s_best, best);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counters[7] = (int64_t)s_best;
 }
 
 constexpr int kMaxBackup = 256;
@@ -704,19 +717,17 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
 
   // ---- 1. pack the mesh ---------------------------------------------------------------------
   ph.mark("pack_mesh");
-  TriGeom<R>* geom; SeedGrid<R>* sg; int* seed; int64_t* counters; int* nz_words;
+  TriGeom<R>* geom; int* seed; int64_t* counters; int* nz_words;
   GI_TRY(scr.alloc(&geom, (size_t)num_tri));
-  GI_TRY(scr.alloc(&sg, 1));
   const int ncx = (len_x + kSeedCell - 1) / kSeedCell, ncy = (len_y + kSeedCell - 1) / kSeedCell;
   GI_TRY(scr.alloc(&seed, (size_t)ncx * ncy));
   GI_TRY(scr.alloc(&counters, 8));
   GI_CUDA(cudaMemsetAsync(seed, 0x7f, sizeof(int) * (size_t)ncx * ncy, st));
   GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 8, st));
-  seed_setup_kernel<R><<<1, 1, 0, st>>>(x_axis, len_x, y_axis, len_y, sg);
   pack_mesh_kernel<R><<<div_up(num_tri, 256), 256, 0, st>>>(
       points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR), data_in,
       topo_t3(simplices, num_tri, flags & GI_TOPO_ROWMAJOR), topo_t3(neighbours, num_tri, flags & GI_TOPO_ROWMAJOR),
-      num_points, num_tri, geom, seed, sg, slot.dev);
+      num_points, num_tri, geom, seed, x_axis, len_x, y_axis, len_y, slot.dev);
   GI_CUDA(cudaGetLastError());
 
   // ---- 2. walk + barycentric over the band plus halo rows -------------------------------------
@@ -755,12 +766,8 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
     }
   // ---- 2b. targets inside the margin band of an edge: follow the reference's own path (normally none) --
   {
-    R* opt_y;
-    GI_TRY(scr.alloc(&opt_y, 1));
     const int n_search = std::min(num_points, num_tri);  // the reference searches triangles 1..num_points (:347)
-    start_tri_setup_kernel<R><<<1, 1, 0, st>>>(y_axis, len_y, counters, opt_y);
-    start_tri_kernel<R><<<kNumSMs * 4, 256, 0, st>>>(geom, n_search, x_axis, opt_y, counters, 0);
-    start_tri_kernel<R><<<kNumSMs * 4, 256, 0, st>>>(geom, n_search, x_axis, opt_y, counters, 1);
+    start_tri_kernel<R><<<1, 1024, 0, st>>>(geom, n_search, x_axis, y_axis, len_y, counters);
     fixup_kernel<R><<<kNumSMs * 2, 128, 0, st>>>(wa, len_x, len_y);
     GI_CUDA(cudaGetLastError());
   }
