@@ -93,6 +93,9 @@ __device__ __forceinline__ void touch_values(const TriGeom<float>*) {}
 // quotient() returns the correctly rounded IEEE quotient, bit-identical to the `/` operator (and so to the
 // oracle); operands outside the fast path's range take the `/` operator itself.
 // ---------------------------------------------------------------------------------------------
+// out of line on purpose: inlined, nvcc if-converts the rare fallback and computes BOTH divisions for every target
+__device__ __noinline__ double ieee_div_slow(double n, double d) { return n / d; }
+
 template <class R> struct DivRcp;
 template <> struct DivRcp<double> {
   double d, r2;
@@ -115,14 +118,33 @@ template <> struct DivRcp<double> {
     const float nh = __int_as_float(__double2hiint(n));
     const float qh = __fmaf_rn(0.0f, __int_as_float(__double2hiint(d)), __int_as_float(__double2hiint(q)));
     if (fabsf(nh) >= 6.5827683646048100446e-37f && fabsf(qh) > 1.469367938527859385e-39f) return q;
-    return n / d;
+    return ieee_div_slow(n, d);
   }
 };
+// both quotients of a target with ONE guard branch
+__device__ __forceinline__ void quotient_pair(const DivRcp<double>& dv, double n1, double n2, double& q1,
+                                              double& q2) {
+  const double a0 = __dmul_rn(n1, dv.r2), b0 = __dmul_rn(n2, dv.r2);
+  const double a = __fma_rn(dv.r2, __fma_rn(-dv.d, a0, n1), a0);
+  const double b = __fma_rn(dv.r2, __fma_rn(-dv.d, b0, n2), b0);
+  const float dh = __int_as_float(__double2hiint(dv.d));
+  const float ah = __fmaf_rn(0.0f, dh, __int_as_float(__double2hiint(a)));
+  const float bh = __fmaf_rn(0.0f, dh, __int_as_float(__double2hiint(b)));
+  const bool ok = fabsf(__int_as_float(__double2hiint(n1))) >= 6.5827683646048100446e-37f &&
+                  fabsf(__int_as_float(__double2hiint(n2))) >= 6.5827683646048100446e-37f &&
+                  fabsf(ah) > 1.469367938527859385e-39f && fabsf(bh) > 1.469367938527859385e-39f;
+  if (ok) { q1 = a; q2 = b; }
+  else { q1 = dv.quotient(n1); q2 = dv.quotient(n2); }
+}
+template <class R> struct DivRcp;
 template <> struct DivRcp<float> {
   float d, r2;
   __device__ __forceinline__ void set(float denom) { d = denom; r2 = 0.f; }
   __device__ __forceinline__ float quotient(float n) const { return n / d; }
 };
+__device__ __forceinline__ void quotient_pair(const DivRcp<float>& dv, float n1, float n2, float& q1, float& q2) {
+  q1 = n1 / dv.d; q2 = n2 / dv.d;
+}
 
 
 // seed-grid geometry from the axes (a uniform-axis approximation: seeds only have to be near)
@@ -240,6 +262,10 @@ __device__ __forceinline__ R eval_value(const TriGeom<R>& g, R tx, R ty) {
 
 // |cross| below this (twice the reference's margin) means "within the margin band of an edge"
 template <class R> __device__ __forceinline__ R kAmbBand() { return R(2e-10); }
+// Cheap superset test for the hot loop: compares the high word of |x| only (2e-10 = 0x3DEB7CDF'D9D7BDBB), i.e.
+// |x| < 2.0000003e-10, with two integer instructions instead of FP64-pipe min / compare sequences.
+__device__ __forceinline__ bool in_amb_band(double x) { return (__double2hiint(x) & 0x7fffffff) < 0x3DEB7CE0; }
+__device__ __forceinline__ bool in_amb_band(float x) { return fabsf(x) < 2e-10f; }
 
 // walk() that also reports whether the accepting (or hull-exit) test was inside the margin band
 template <class R>
@@ -367,7 +393,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
       // A target within the margin band of an edge is accepted by both adjacent triangles and which one the
       // reference returns depends on its walk path: flag it for fixup_kernel.
       // (any |cross| below twice the margin: a superset of the truly ambiguous cases, three compares)
-      if (fabs(x1) < kAmbBand<R>() || fabs(x2) < kAmbBand<R>() || fabs(x3) < kAmbBand<R>()) {
+      if (in_amb_band(x1) | in_amb_band(x2) | in_amb_band(x3)) {
         const unsigned long long slot = atomicAdd((unsigned long long*)(a.counters + 5), 1ull);
         if (slot < (unsigned long long)a.amb_cap) a.amb_list[slot] = (srow0 + r - w.s0) * w.nf() + lane_f;
       }
@@ -391,7 +417,9 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   const bool f_in_band = active && f >= a.bf0 && f < a.bf1;
   const int wpr = (w.nf() + 31) >> 5;
   const int bnf = a.bf1 - a.bf0;
+  static_assert(ROWS <= 32, "one lane per row keeps that row's mask word");
   int cur = -1;
+  unsigned my_mask = 0;
   R c1 = 0, q1 = 0, c2 = 0, q2 = 0, p3 = 0, d1 = 0, d2 = 0, d3 = 0;
   DivRcp<R> dv;
   dv.d = R(1); dv.r2 = R(1);
@@ -416,19 +444,20 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
         }
         // w1 = (A*(tx-x3) + B*(ty-y3))/denom, w2 = (C*(tx-x3) + D*(ty-y3))/denom   (:387-394); the sum commutes
         const R t3 = saxis[r] - p3;
-        const R w1 = dv.quotient(FY ? q1 * t3 + c1 : c1 + q1 * t3);
-        const R w2 = dv.quotient(FY ? q2 * t3 + c2 : c2 + q2 * t3);
+        R w1, w2;
+        quotient_pair(dv, FY ? q1 * t3 + c1 : c1 + q1 * t3, FY ? q2 * t3 + c2 : c2 + q2 * t3, w1, w2);
         const R w3 = R(1) - w1 - w2;
         a.out[o] = d1 * w1 + d2 * w2 + d3 * w3;                   // :396-398
       }
       if (a.tri_out) a.tri_out[o] = (inside ? t : ~t) + 1;
     }
     const unsigned m = __ballot_sync(0xffffffffu, active && !inside);
-    if (lane == 0 && (lane_f >> 5) < wpr) {
-      const int64_t wi = (int64_t)(s - w.s0) * wpr + (lane_f >> 5);
-      a.mask_words[wi] = m;
-      if (m) a.nz_words[atomicAdd((unsigned long long*)(a.counters + 4), 1ull)] = (int)wi;
-    }
+    if (lane == r) my_mask = m;  // lane r keeps the word of row r (ROWS <= 32)
+  }
+  if (lane < nrows && (lane_f >> 5) < wpr) {
+    const int64_t wi = (int64_t)(srow0 + lane - w.s0) * wpr + (lane_f >> 5);
+    a.mask_words[wi] = my_mask;
+    if (my_mask) a.nz_words[atomicAdd((unsigned long long*)(a.counters + 4), 1ull)] = (int)wi;
   }
   // one atomic per warp for the iteration counter (iters_tot, interpolation.f90:374)
   for (int off = 16; off > 0; off >>= 1) iters_sum += __shfl_down_sync(0xffffffffu, iters_sum, off);
