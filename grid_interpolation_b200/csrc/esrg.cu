@@ -229,16 +229,16 @@ __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
   const int64_t o = (int64_t)(s - w.s0) * w.nf() + (f - w.f0);
   R numerator = R(0), denominator = R(0), first_val = R(0), first_dist = R(0);
 #pragma unroll
-  for (int i = 0; i < KC; ++i) {
-    if (i < a.k) {
-      const int pos = tk.id[i];
-      const R dist = sqrt(tk.d[i]);
+  for (int j = 0; j < KC; ++j) {
+    if (j >= tk.base) {  // rank j - tk.base of the list (topk.cuh)
+      const int pos = tk.id[j];
+      const R dist = sqrt(tk.d[j]);
       const R v = pos >= 0 ? __ldg(a.sval + pos) : R(0);
-      if (i == 0) { first_val = v; first_dist = dist; }
+      if (j == tk.base) { first_val = v; first_dist = dist; }
       numerator = numerator + (v / dist);
       denominator = denominator + (R(1) / dist);
-      if (a.nn_index) a.nn_index[o * a.k + i] = pos >= 0 ? __ldg(a.sid + pos) : -1;
-      if (a.nn_dist2) a.nn_dist2[o * a.k + i] = tk.d[i];
+      if (a.nn_index) a.nn_index[o * a.k + (j - tk.base)] = pos >= 0 ? __ldg(a.sid + pos) : -1;
+      if (a.nn_dist2) a.nn_dist2[o * a.k + (j - tk.base)] = tk.d[j];
     }
   }
   a.out[o] = (first_dist <= Consts<R>::tiny_e4()) ? first_val : numerator / denominator;
@@ -373,27 +373,36 @@ __global__ void __launch_bounds__(128) esrg_fast_kernel(const EsrgArgs<R> a) {
 // runs its own cell loops with its own trip counts.  Here a WARP owns a tile of 8 x 4 targets (8 along the
 // contiguous output axis) and works in lock step:
 //   1. stage   the points of the tile's halo rectangle (tile grown by H cells on every side; one CSR run per
-//              grid row, one lane per run) are copied to shared memory;
+//              grid row, one lane per run) are copied to shared memory (at most 255 of them);
 //   2. scan    every lane computes its d2 to every staged point (shared-memory broadcast, no divergence) and
-//              appends those within r_H = spac*(H+1/2) -- the radius its own (2H+1)^2 window is guaranteed to
-//              cover -- to a per-lane candidate list in shared memory;
-//   3. grow    lanes with fewer than k candidates make the warp repeat 1-2 with H+2 (rare: H starts at the
-//              level where the mean density gives ~1.5k+6 points within r_H);
-//   4. select  k+1 rounds of minimum extraction give the neighbours in ascending order (the order of the
-//              reference's IDW sums); equal distances among them, or a full list, send the target to the
-//              exact kernel.
+//              feeds a 32-bit KEY into a branch-free min/max ladder that keeps its k+1 smallest keys in
+//              registers.  key = (fixed-point d2) << 8 | staged index, or 0xffffffff beyond r_H =
+//              spac*(H+1/2), the radius the lane's own (2H+1)^2 window is guaranteed to cover.  The fixed-point
+//              value is the low mantissa word of d2 + 2^(e+52) -- a MONOTONE function of d2 with 2^-23 r_H^2
+//              resolution -- so the ladder costs two integer min/max per slot and carries no payload;
+//   3. grow    if a lane found fewer than k points within r_H the warp repeats 1-2 with H+2 (rare: H starts
+//              at the level where the mean density gives ~1.5k+6 points within r_H);
+//   4. resolve monotonicity makes the k smallest keys the k nearest points in ascending order provided the
+//              fixed-point values of the k+1 smallest keys are pairwise different; then the exact d2 of the k
+//              winners is recomputed from the staged coordinates (same expression, same bits) and the IDW sum
+//              is taken in that order.  Equal fixed-point values (exact ties, where the reference's candidate
+//              order decides, or distances closer than the resolution: ~1e-5 of the targets) and tiles with
+//              more than 255 staged points send the target to the exact kernel.
 // The result is the exact k nearest neighbours, which is what the reference computes (see esrg_fast_kernel).
+// The first tile version kept per-lane candidate lists in shared memory and selected with k+1 minimum-
+// extraction passes: 112 warp instructions per target, 31 KB of shared memory per 2 warps (15.1 ms at C3).
 // ---------------------------------------------------------------------------------------------
-constexpr int kStageCap = 160;    // staged points per warp and chunk
-constexpr int kTileWarps = 2;
+constexpr int kStageCap = 255;  // staged points per tile: the staged index is the low byte of a key
+constexpr int kTileWarps = 4;
 
-// kTileCap = candidate slots per lane (32 for k <= 8, 48 for k <= 16)
-template <class R, int kTileCap>
-__global__ void __launch_bounds__(32 * kTileWarps, 12) esrg_tile_kernel(const EsrgArgs<R> a, int h0) {
-  __shared__ XY<R> s_xy[kTileWarps][kStageCap];
-  __shared__ int s_pos[kTileWarps][kStageCap];
-  __shared__ R s_d2[kTileWarps][kTileCap][32];
-  __shared__ int s_id[kTileWarps][kTileCap][32];
+__device__ __forceinline__ unsigned lo_word(double x) { return (unsigned)__double2loint(x); }
+
+// KS = key slots = largest supported k + 1.  The live k+1 slots are the TOP ones (slots below hold 0 and stay
+// 0), so the k-th and (k+1)-th smallest keys sit in the compile-time slots KS-2 and KS-1 for every run-time k.
+template <class R, int KS>
+__global__ void __launch_bounds__(32 * kTileWarps) esrg_tile_kernel(const EsrgArgs<R> a, int h0) {
+  __shared__ XY<R> s_xy[kTileWarps][kStageCap + 1];
+  __shared__ int s_pos[kTileWarps][kStageCap + 1];
   const TargetWindow<R>& w = a.win;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int len_x = a.len_x, len_y = a.len_y, k = a.k;
@@ -418,101 +427,92 @@ __global__ void __launch_bounds__(32 * kTileWarps, 12) esrg_tile_kernel(const Es
   const int tx0 = w.fast_is_y ? ts0 : tf0, tx1 = w.fast_is_y ? s_hi : f_hi;
   const int ty0 = w.fast_is_y ? tf0 : ts0, ty1 = w.fast_is_y ? f_hi : s_hi;
 
-  int cnt = 0;
-  bool done = !active, hand_over = false;
+  const int base = KS - 1 - k;  // first live slot
+  unsigned key[KS];
+  bool hand_over = false;
   int H = h0;
   const int level_cap = len_x + len_y;
   for (;;) {
     const R rad = a.spac * (R(H) + R(0.5));                               // :141,:181
     const R r2 = rad * rad;
-    if (!done) cnt = 0;
+    // 2^(e+52) with r2 < 2^(e+23): d2 <= r2 maps to a fixed-point value below 2^23
+    const int r2_exp = (__double2hiint((double)r2) >> 20) & 0x7ff;        // biased exponent of r2 (> 0)
+    const double magic = __hiloint2double(min(r2_exp + 30, 2046) << 20, 0);
     // ---- 1. stage: one CSR run per grid row of the halo rectangle ----------------------------------
     const int rx0 = max(tx0 - H, 0), rx1 = min(tx1 + H, len_x - 1);
     const int ry0 = max(ty0 - H, 0), ry1 = min(ty1 + H, len_y - 1);
     const int nrows = ry1 - ry0 + 1;
-    for (int rbase = 0; rbase < nrows; rbase += 32) {
-      int p0 = 0, n = 0;
-      if (rbase + lane < nrows) {
-        const int row = (ry0 + rbase + lane) * len_x;
-        const int c0 = row + rx0;
-        p0 = c0 > 0 ? __ldg(a.table + c0 - 1) : 0;
-        n = __ldg(a.table + row + rx1) - p0;
-      }
-      int off = n;  // inclusive warp scan
+    int p0 = 0, n = 0;
+    if (lane < nrows) {
+      const int row = (ry0 + lane) * len_x;
+      const int c0 = row + rx0;
+      p0 = c0 > 0 ? __ldg(a.table + c0 - 1) : 0;
+      n = __ldg(a.table + row + rx1) - p0;
+    }
+    int off = n;  // inclusive warp scan
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, off, d);
-        if (lane >= d) off += t;
-      }
-      const int total = __shfl_sync(0xffffffffu, off, 31);
-      off -= n;
-      for (int cbase = 0; cbase < total; cbase += kStageCap) {
-        __syncwarp();
-        // copy the part of this lane's run that falls into the chunk [cbase, cbase + kStageCap)
-        const int lo = max(off, cbase), hi = min(off + n, cbase + kStageCap);
-        for (int i = lo; i < hi; ++i) {
-          s_xy[wid][i - cbase] = a.sxy[p0 + (i - off)];
-          s_pos[wid][i - cbase] = p0 + (i - off);
-        }
-        __syncwarp();
-        // ---- 2. scan ------------------------------------------------------------------------------
-        const int m = min(total - cbase, kStageCap);
-        if (!done) {
-          for (int i = 0; i < m; ++i) {
-            const XY<R> q = s_xy[wid][i];
-            const R ddx = cx - q.x, ddy = cy - q.y;
-            const R d2 = ddx * ddx + ddy * ddy;                           // :147-148
-            if (!(d2 > r2)) {
-              if (cnt < kTileCap) { s_d2[wid][cnt][lane] = d2; s_id[wid][cnt][lane] = s_pos[wid][i]; }
-              ++cnt;
-            }
-          }
-        }
-      }
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, off, d);
+      if (lane >= d) off += t;
     }
-    // ---- 3. grow? ---------------------------------------------------------------------------------
-    if (!done) {
-      if (cnt > kTileCap) { hand_over = true; done = true; }              // dense cluster: exact kernel
-      else if (cnt >= k) done = true;                                     // :178,:243
+    const int total = __shfl_sync(0xffffffffu, off, 31);
+    off -= n;
+    if (nrows > 32 || total > kStageCap) { hand_over = true; break; }     // dense cluster: exact kernel
+    __syncwarp();
+    for (int i = 0; i < n; ++i) {
+      s_xy[wid][off + i] = a.sxy[p0 + i];
+      s_pos[wid][off + i] = p0 + i;
     }
-    if (__all_sync(0xffffffffu, done)) break;
+    __syncwarp();
+    // ---- 2. scan ------------------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < KS; ++j) key[j] = j >= base ? 0xffffffffu : 0u;
+#pragma unroll 2
+    for (int i = 0; i < total; ++i) {
+      const XY<R> q = s_xy[wid][i];
+      const R ddx = cx - q.x, ddy = cy - q.y;
+      const R d2 = ddx * ddx + ddy * ddy;                                 // :147-148
+      const unsigned fix = lo_word((double)d2 + magic);
+      const unsigned c = d2 > r2 ? 0xffffffffu : (fix << 8) + (unsigned)i;
+#pragma unroll
+      for (int j = KS - 1; j >= 1; --j) key[j] = min(key[j], max(key[j - 1], c));
+      key[0] = min(key[0], c);  // (slot 0 is live only when k + 1 == KS)
+    }
+    // ---- 3. grow? -----------------------------------------------------------------------------------
+    if (__all_sync(0xffffffffu, key[KS - 2] != 0xffffffffu)) break;       // k points within r_H: :178,:243
     H += 2;
-    if (H > level_cap) { raise_status(a.status, GI_ERR_TOO_FEW_POINTS); break; }
+    if (H > level_cap) { raise_status(a.status, GI_ERR_TOO_FEW_POINTS); hand_over = true; break; }
   }
-  // ---- 4. select ------------------------------------------------------------------------------------
-  const int n_list = hand_over ? 0 : min(cnt, kTileCap);
-  int cmax = n_list;
+  if (hand_over) {
+    if (active) a.todo[atomicAdd((unsigned long long*)a.todo_count, 1ull)] = lin;
+    return;
+  }
+  // ---- 4. resolve -----------------------------------------------------------------------------------
+  bool ambiguous = false;
+  R numerator = R(0), denominator = R(0), first_val = R(0), first_dist = R(0);
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
-  R numerator = R(0), denominator = R(0), first_val = R(0), first_dist = R(0), prev = R(-1);
-  bool tie = false;
-  for (int round = 0; round <= k; ++round) {
-    R best = Consts<R>::huge();
-    int be = -1;
-#pragma unroll 4
-    for (int e = 0; e < cmax; ++e) {
-      const R v = s_d2[wid][e][lane];
-      if (e < n_list && v < best) { best = v; be = e; }
-    }
-    if (be < 0) break;  // (only when fewer than k+1 candidates: the whole list has been taken)
-    tie |= (best == prev);
-    prev = best;
-    if (round == k) break;
-    const int pos = s_id[wid][be][lane];
-    s_d2[wid][be][lane] = Consts<R>::huge();
-    // IDW (interpolation.f90:260-274): distances are square-rooted first (query_esrg.f90:247)
-    const R dist = sqrt(best);
-    const R v = __ldg(a.sval + pos);
-    if (round == 0) { first_val = v; first_dist = dist; }
-    numerator = numerator + (v / dist);
-    denominator = denominator + (R(1) / dist);
-    if (active && !hand_over) {
-      if (a.nn_index) a.nn_index[(int64_t)lin * k + round] = __ldg(a.sid + pos);
-      if (a.nn_dist2) a.nn_dist2[(int64_t)lin * k + round] = best;
+  for (int j = 0; j < KS - 1; ++j) {
+    if (j >= base) {
+      ambiguous |= (key[j] >> 8) == (key[j + 1] >> 8);
+      const int e = key[j] & 0xff;
+      const XY<R> q = s_xy[wid][e];
+      const int pos = s_pos[wid][e];
+      const R ddx = cx - q.x, ddy = cy - q.y;
+      const R d2 = ddx * ddx + ddy * ddy;                                 // :147-148
+      // IDW (interpolation.f90:260-274): distances are square-rooted first (query_esrg.f90:247)
+      const R dist = sqrt(d2);
+      const R v = __ldg(a.sval + pos);
+      if (j == base) { first_val = v; first_dist = dist; }
+      numerator = numerator + (v / dist);
+      denominator = denominator + (R(1) / dist);
+      if (active) {  // (overwritten by the exact kernel if the target turns out to be ambiguous)
+        if (a.nn_index) a.nn_index[(int64_t)lin * k + (j - base)] = __ldg(a.sid + pos);
+        if (a.nn_dist2) a.nn_dist2[(int64_t)lin * k + (j - base)] = d2;
+      }
     }
   }
   if (!active) return;
-  if (hand_over || tie) {  // equal distances (the reference's candidate order decides) or a full list
+  if (ambiguous) {  // equal (fixed-point) distances: the reference's candidate order may decide
     a.todo[atomicAdd((unsigned long long*)a.todo_count, 1ull)] = lin;
     return;
   }
@@ -588,16 +588,18 @@ int esrg_device(const R* points, int num_points, const R* data_in, const R* x_ax
   GI_TRY(scr.alloc(&a.todo, (size_t)ntargets));
   a.todo_count = counters + 3;
   a.all_exact = (flags & GI_ESRG_REFERENCE_ORDER) ? 1 : 0;
-  if (k <= 16) {
-    // first halo level: where the mean point density puts about 1.5k+6 points within r_H = spac*(H+1/2), so
-    // that all 32 lanes of a tile find k of them in the first pass with high probability (Poisson tail)
-    const double density = (double)num_points / ((double)len_x * (double)len_y);
-    int h0 = 1;
-    while (h0 < 12 && 3.141592653589793 * (h0 + 0.5) * (h0 + 0.5) * density < 1.5 * k + 6.0) ++h0;
+  // first halo level: where the mean point density puts about 1.5k+6 points within r_H = spac*(H+1/2), so
+  // that all 32 lanes of a tile find k of them in the first pass with high probability (Poisson tail)
+  const double density = (double)num_points / ((double)len_x * (double)len_y);
+  int h0 = 1;
+  while (h0 < 12 && 3.141592653589793 * (h0 + 0.5) * (h0 + 0.5) * density < 1.5 * k + 6.0) ++h0;
+  // the tile kernel stages at most 255 points per tile; very dense inputs go straight to the per-thread kernel
+  const bool tiles_fit = (8.0 + 2 * h0) * (4.0 + 2 * h0) * density < 0.6 * kStageCap;
+  if (k <= 16 && tiles_fit) {
     const int64_t tiles = (int64_t)div_up(a.win.nf(), 8) * div_up(a.win.ns(), 4);
     const unsigned tg = (unsigned)div_up(tiles, kTileWarps);
-    if (k <= 8) esrg_tile_kernel<R, 32><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
-    else esrg_tile_kernel<R, 48><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
+    if (k <= 8) esrg_tile_kernel<R, 9><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
+    else esrg_tile_kernel<R, 17><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
   } else {
     esrg_fast_kernel<R, 32><<<grid, 128, 0, st>>>(a);
   }

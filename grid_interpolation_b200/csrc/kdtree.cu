@@ -257,11 +257,41 @@ template <class R> struct KdArgs {
 
 template <class R> struct alignas(16) StackEntry {
   int lo, hi;
-  R adiff;  // |diff| of the parent; sign bit = parity of the subtree's depth
+  R key;  // what the prune rule compares with max d2 (see prune_key); sign bit = parity of the subtree's depth
 };
 
 // PRUNE: 0 = reference rule + state-preserving skip (default), 1 = reference rule only (visit-count parity),
-// 2 = exact rule diff*diff < max d2 (extension: exact kNN)
+// 2 = exact rule diff*diff < max d2 (extension: exact kNN).
+// The far branch behind a split at distance ad = |diff| is visited iff prune_key(ad) < max d2:
+//   1: ad < max d2                              (kd_tree.f90:191,198)
+//   2: ad*ad < max d2
+//   0: ad < max d2 AND ad*ad < max d2  <=>  max(ad, ad*ad) < max d2, and max(ad, ad*ad) is ad*ad iff ad >= 1
+// sign-bit helpers on the integer pipe (fabs / negation of a double are FP64-pipe DADDs otherwise)
+__device__ __forceinline__ double clear_sign(double x) {
+  return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
+}
+__device__ __forceinline__ float clear_sign(float x) { return __int_as_float(__float_as_int(x) & 0x7fffffff); }
+__device__ __forceinline__ double or_sign(double x, unsigned sign) {
+  return __hiloint2double(__double2hiint(x) | (int)sign, __double2loint(x));
+}
+__device__ __forceinline__ float or_sign(float x, unsigned sign) { return __int_as_float(__float_as_int(x) | (int)sign); }
+__device__ __forceinline__ unsigned sign_of(double x) { return (unsigned)__double2hiint(x) & 0x80000000u; }
+__device__ __forceinline__ unsigned sign_of(float x) { return (unsigned)__float_as_int(x) & 0x80000000u; }
+__device__ __forceinline__ bool at_least_one(double ad) { return __double2hiint(ad) >= 0x3ff00000; }  // ad >= 0
+__device__ __forceinline__ bool at_least_one(float ad) { return ad >= 1.0f; }
+
+template <class R, int PRUNE> __device__ __forceinline__ R prune_key(R ad) {
+  if (PRUNE == 1) return ad;
+  if (PRUNE == 2) return ad * ad;
+  return at_least_one(ad) ? ad * ad : ad;
+}
+
+// ncu on the first version (profiles/r01_kd_query_ncu.csv): 513 warp instructions per target at 12 of 32 lanes
+// active -- a "descend to a leaf, then pop" loop nest makes every lane wait for the longest descent of its warp
+// in every round, and the position-counting insertion cost ~110 instructions.  This version is one flat loop
+// whose body is "pop if the current segment is empty; visit one node": lanes advance independently and meet
+// again at every node visit.  Far branches that the prune rule already rejects when they are created are never
+// pushed (max d2 only shrinks, so the rejection is final), which removes most stack traffic.
 template <class R, int KC, int PRUNE>
 __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
   const TargetWindow<R>& w = a.win;
@@ -271,72 +301,73 @@ __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
   const int f = w.f0 + blockIdx.x * 32 + wid * 8 + (lane & 7);
   const int s = w.s0 + blockIdx.y * 4 + (lane >> 3);
   const bool active = f < w.f1 && s < w.s1;
-  long long visits = 0;
+  unsigned visits = 0;
   if (active) {
     const int ix = w.fast_is_y ? s : f, iy = w.fast_is_y ? f : s;
     const R tx = __ldg((w.fast_is_y ? w.slow_axis : w.fast_axis) + ix);   // interpolation.f90:158
     const R ty = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
     TopK<R, KC> tk;
     tk.init(a.k, Consts<R>::sentinel(), -1);                              // :159
-    // deferred far branches: one 16 B entry each (segment + |diff|; the depth parity rides in the sign bit)
-    StackEntry<R> stack[32];
+    StackEntry<R> stack[32];  // deferred far branches, at most one per tree level
     int sp = 0;
-    int lo = 0, hi = a.n, depth = 0;
+    int lo = 0, hi = a.n;
+    unsigned odd = 0u;  // 0x80000000 at odd depth, else 0: axis = mod(depth, 2)   (kd_tree.f90:45)
     for (;;) {
-      while (lo < hi) {                                                   // kd_tree.f90:174
-        const int m = lo + ((hi - lo + 1) >> 1) - 1;
-        const XY<R> nd = a.nodes[m];
-        const R ddx = nd.x - tx, ddy = nd.y - ty;
-        const R d2 = ddx * ddx + ddy * ddy;                               // :177,:249
-        if (d2 < tk.dlast) tk.template insert<false>(d2, m);              // :222-236
-        ++visits;
-        const R diff = (depth & 1) ? ty - nd.y : tx - nd.x;               // :183-184
-        int flo, fhi;
-        if (diff < R(0)) { flo = m + 1; fhi = hi; hi = m; }               // :188 near = left
-        else { flo = lo; fhi = m; lo = m + 1; }                           // :195 near = right
-        ++depth;
-        if (flo < fhi && sp < 32) {
-          StackEntry<R> e;
-          e.lo = flo; e.hi = fhi;
-          e.adiff = (depth & 1) ? -fabs(diff) : fabs(diff);
-          stack[sp++] = e;
+      if (lo >= hi) {                                                     // :174 -- back up to a deferred branch
+        bool got = false;
+        while (sp > 0) {
+          const StackEntry<R> e = stack[--sp];
+          if (fabs(e.key) < tk.dlast) {                                   // :191,:198 (see prune_key)
+            lo = e.lo; hi = e.hi;
+            odd = sign_of(e.key);
+            got = true;
+            break;
+          }
         }
+        if (!got) break;
       }
-      bool got = false;
-      while (sp > 0) {
-        const StackEntry<R> e = stack[--sp];
-        const R ad = fabs(e.adiff);
-        // :191,:198 the reference's rule; second term: provably state-preserving skip (see file header)
-        if (PRUNE == 2 ? ad * ad < tk.dlast : (ad < tk.dlast && (PRUNE == 1 || ad * ad < tk.dlast))) {
-          lo = e.lo; hi = e.hi;
-          depth = signbit(e.adiff) ? 1 : 0;  // only the parity of the depth is ever used
-          got = true;
-          break;
-        }
+      const int m = lo + ((hi - lo + 1) >> 1) - 1;
+      const XY<R> nd = a.nodes[m];
+      const R ddx = nd.x - tx, ddy = nd.y - ty;
+      const R d2 = ddx * ddx + ddy * ddy;                                 // :177,:249
+      if (d2 < tk.dlast) tk.template insert<false>(d2, m);                // :222-236
+      ++visits;
+      // diff = t(axis) - node(axis) (:183-184) is exactly -(node - t): reuse the difference computed for d2
+      const R nmt = odd ? ddy : ddx;
+      int flo, fhi;
+      if (nmt > R(0)) { flo = m + 1; fhi = hi; hi = m; }                  // :188 diff < 0: near = left
+      else { flo = lo; fhi = m; lo = m + 1; }                             // :195 near = right
+      odd ^= 0x80000000u;
+      const R key = prune_key<R, PRUNE>(clear_sign(nmt));
+      if (flo < fhi && key < tk.dlast && sp < 32) {
+        StackEntry<R> e;
+        e.lo = flo; e.hi = fhi;
+        e.key = or_sign(key, odd);
+        stack[sp++] = e;
       }
-      if (!got) break;
     }
-    // IDW (interpolation.f90:164-178)
+    // IDW (interpolation.f90:164-178); rank i of the list lives in slot tk.base + i
     const int64_t o = (int64_t)(s - w.s0) * w.nf() + (f - w.f0);
     R numerator = R(0), denominator = R(0), first_val = R(0), first_d2 = R(0);
 #pragma unroll
-    for (int i = 0; i < KC; ++i) {
-      if (i < a.k) {
-        const int pos = tk.id[i];
-        const R dist = sqrt(tk.d[i]);
+    for (int j = 0; j < KC; ++j) {
+      if (j >= tk.base) {
+        const int pos = tk.id[j];
+        const R dist = sqrt(tk.d[j]);
         const R v = pos >= 0 ? __ldg(a.nval + pos) : R(0);  // unfilled slot: uninitialised read in the reference
-        if (i == 0) { first_val = v; first_d2 = tk.d[i]; }
+        if (j == tk.base) { first_val = v; first_d2 = tk.d[j]; }
         numerator = numerator + (v / dist);
         denominator = denominator + (R(1) / dist);
-        if (a.nn_index) a.nn_index[o * a.k + i] = pos >= 0 ? __ldg(a.order + pos) + 1 : 0;
-        if (a.nn_dist2) a.nn_dist2[o * a.k + i] = tk.d[i];
+        if (a.nn_index) a.nn_index[o * a.k + (j - tk.base)] = pos >= 0 ? __ldg(a.order + pos) + 1 : 0;
+        if (a.nn_dist2) a.nn_dist2[o * a.k + (j - tk.base)] = tk.d[j];
       }
     }
     a.out[o] = (sqrt(first_d2) <= Consts<R>::tiny_e4()) ? first_val : numerator / denominator;
   }
   if (a.counters) {
-    for (int off = 16; off > 0; off >>= 1) visits += __shfl_down_sync(0xffffffffu, visits, off);
-    if ((threadIdx.x & 31) == 0 && visits) atomicAdd((unsigned long long*)a.counters, (unsigned long long)visits);
+    unsigned long long v = visits;
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd((unsigned long long*)a.counters, v);
   }
 }
 

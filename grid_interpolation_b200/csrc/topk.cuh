@@ -11,31 +11,36 @@
 namespace gi {
 
 template <class R, int KC> struct TopK {
+  // The k live entries occupy the TOP k slots, d[KC-k .. KC-1]; the slots below hold -1, which no squared
+  // distance sorts before, so they are inert.  That makes the k-th entry the compile-time slot KC-1 for every
+  // run-time k: a run-time slot (d[k-1]) would turn the arrays into local memory.
   R d[KC];
   int id[KC];
-  R dlast;  // d[k-1]
-  int k;
+  R dlast;   // the k-th smallest so far = d[KC-1]
+  int base;  // KC - k: slot of the smallest entry
 
-  __device__ __forceinline__ void init(int k_, R d_init, int id_init) {
-    k = k_;
+  __device__ __forceinline__ void init(int k, R d_init, int id_init) {
+    base = KC - k;
 #pragma unroll
-    for (int i = 0; i < KC; ++i) { d[i] = d_init; id[i] = id_init; }
+    for (int i = 0; i < KC; ++i) { d[i] = i >= base ? d_init : R(-1); id[i] = id_init; }
     dlast = d_init;
   }
-  // precondition: d2 < dlast
+  // precondition: d2 < dlast.
+  // One predicate per slot, before(j) = "the new entry sorts before d[j]"; d[] is ascending, so before() is
+  // monotone in j and slot j either takes its left neighbour (before(j-1)), the new entry (before(j) only) or
+  // keeps its value: one compare + predicated moves per slot, no position counting.
   template <bool BEFORE_EQUAL> __device__ __forceinline__ void insert(R d2, int idx) {
-    int pos = 0;
+    bool below = true;  // before(KC-1) is the precondition
 #pragma unroll
-    for (int j = 0; j < KC; ++j) pos += (j < k && (BEFORE_EQUAL ? d[j] < d2 : d[j] <= d2)) ? 1 : 0;
-#pragma unroll
-    for (int i = KC - 1; i >= 1; --i)
-      if (i < k && i > pos) { d[i] = d[i - 1]; id[i] = id[i - 1]; }
-#pragma unroll
-    for (int i = 0; i < KC; ++i)
-      if (i == pos) { d[i] = d2; id[i] = idx; }
-#pragma unroll
-    for (int i = 0; i < KC; ++i)
-      if (i == k - 1) dlast = d[i];
+    for (int j = KC - 1; j >= 1; --j) {
+      const bool lower = BEFORE_EQUAL ? d2 <= d[j - 1] : d2 < d[j - 1];
+      d[j] = lower ? d[j - 1] : (below ? d2 : d[j]);  // selects, not branches: ptxas turns the if/else form
+      id[j] = lower ? id[j - 1] : (below ? idx : id[j]);  // into 3x as many register moves
+      below = lower;
+    }
+    d[0] = below ? d2 : d[0];
+    id[0] = below ? idx : id[0];
+    dlast = d[KC - 1];
   }
 };
 
