@@ -29,6 +29,8 @@
 //               deferred list per thread; when it overflows the thread switches to a list-free mode that
 //               re-scans the inner frames with the predicate "was deferred at the previous level"
 //               (d2 > r2_prev), which yields the same order for any point density.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "scan.cuh"
 #include "topk.cuh"
@@ -400,7 +402,7 @@ __device__ __forceinline__ unsigned lo_word(double x) { return (unsigned)__doubl
 // KS = key slots = largest supported k + 1.  The live k+1 slots are the TOP ones (slots below hold 0 and stay
 // 0), so the k-th and (k+1)-th smallest keys sit in the compile-time slots KS-2 and KS-1 for every run-time k.
 template <class R, int KS>
-__global__ void __launch_bounds__(32 * kTileWarps) esrg_tile_kernel(const EsrgArgs<R> a, int h0) {
+__global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const EsrgArgs<R> a, int h0) {
   __shared__ XY<R> s_xy[kTileWarps][kStageCap + 1];
   __shared__ int s_pos[kTileWarps][kStageCap + 1];
   const TargetWindow<R>& w = a.win;
@@ -593,6 +595,9 @@ int esrg_device(const R* points, int num_points, const R* data_in, const R* x_ax
   const double density = (double)num_points / ((double)len_x * (double)len_y);
   int h0 = 1;
   while (h0 < 12 && 3.141592653589793 * (h0 + 0.5) * (h0 + 0.5) * density < 1.5 * k + 6.0) ++h0;
+#ifdef GI_TUNING
+  if (const char* e = getenv("GI_ESRG_H0")) h0 = atoi(e);
+#endif
   // the tile kernel stages at most 255 points per tile; very dense inputs go straight to the per-thread kernel
   const bool tiles_fit = (8.0 + 2 * h0) * (4.0 + 2 * h0) * density < 0.6 * kStageCap;
   if (k <= 16 && tiles_fit) {

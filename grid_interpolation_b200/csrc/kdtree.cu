@@ -308,7 +308,10 @@ __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
     const R ty = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
     TopK<R, KC> tk;
     tk.init(a.k, Consts<R>::sentinel(), -1);                              // :159
-    StackEntry<R> stack[32];  // deferred far branches, at most one per tree level
+    // Deferred far branches, at most one per tree level.  Measured alternatives (profiles/r01_kd_esrg_variants.md):
+    // top entry kept in registers +16 %, 48 registers for 10 CTAs/SM +8 % (spills), two entries per back-up
+    // round -1 %.
+    StackEntry<R> stack[32];
     int sp = 0;
     int lo = 0, hi = a.n;
     unsigned odd = 0u;  // 0x80000000 at odd depth, else 0: axis = mod(depth, 2)   (kd_tree.f90:45)
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
         bool got = false;
         while (sp > 0) {
           const StackEntry<R> e = stack[--sp];
-          if (fabs(e.key) < tk.dlast) {                                   // :191,:198 (see prune_key)
+          if (clear_sign(e.key) < tk.dlast) {                             // :191,:198 (see prune_key)
             lo = e.lo; hi = e.hi;
             odd = sign_of(e.key);
             got = true;
