@@ -26,6 +26,7 @@ SIGNATURES = {
     "gi_host_free": ([_vp], None),
     "gi_stream_status": ([_vp], _i),
     "gi_set_profiling": ([_i], None),
+    "gi_set_pipeline_band_bytes": ([C.c_uint64], None),
     "gi_last_timings": ([_vp, _i], _i),
     "gi_last_timing_name": ([_i], C.c_char_p),
     "gi_release_workspace": ([], None),

@@ -161,28 +161,28 @@ void Phases::finish() {
 // ---------------------------------------------------------------------------------------------
 // host staging helpers
 // ---------------------------------------------------------------------------------------------
-static thread_local cudaStream_t t_host_stream = nullptr;
-static int host_stream(cudaStream_t* out) {
-  if (!t_host_stream) GI_CUDA(cudaStreamCreateWithFlags(&t_host_stream, cudaStreamNonBlocking));
-  *out = t_host_stream;
-  return GI_OK;
-}
+static int64_t g_band_bytes = (int64_t)32 << 20;
+int64_t pipeline_band_bytes() { return g_band_bytes; }
 
-template <class T>
-static int to_device(Scratch& scr, const T* host, size_t count, T** dev) {
-  GI_TRY(scr.alloc(dev, count));
-  if (count) GI_CUDA(cudaMemcpyAsync(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice, scr.stream()));
+static thread_local HostPipe t_pipe;
+int host_pipe(HostPipe** out) {
+  HostPipe& p = t_pipe;
+  if (!p.compute) {
+    GI_CUDA(cudaStreamCreateWithFlags(&p.compute, cudaStreamNonBlocking));
+    GI_CUDA(cudaStreamCreateWithFlags(&p.copy_in, cudaStreamNonBlocking));
+    GI_CUDA(cudaStreamCreateWithFlags(&p.copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxBands; ++i) {
+      GI_CUDA(cudaEventCreateWithFlags(&p.computed[i], cudaEventDisableTiming));
+      GI_CUDA(cudaEventCreateWithFlags(&p.arrived[i], cudaEventDisableTiming));
+    }
+  }
+  *out = &p;
   return GI_OK;
 }
-template <class T>
-static int to_host(Scratch& scr, T* host, const T* dev, size_t count) {
-  if (host && count) GI_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, scr.stream()));
-  return GI_OK;
-}
-template <class T>
-static int out_device(Scratch& scr, T* host, size_t count, T** dev) {  // device twin of an optional host output
-  *dev = nullptr;
-  if (host) GI_TRY(scr.alloc(dev, count));
+static int host_stream(cudaStream_t* out) {
+  HostPipe* p;
+  GI_TRY(host_pipe(&p));
+  *out = p->compute;
   return GI_OK;
 }
 
@@ -204,24 +204,7 @@ static int bilinear_api(const R* x_axis, int len_x, const R* y_axis, int len_y, 
   GI_REQUIRE(len_x >= 2 && len_y >= 2 && n >= 0, "bad dimensions");
   if (mem == GI_DEVICE)
     return bilinear_device<R>(x_axis, len_x, y_axis, len_y, data_in, points, n, data_ip, flags, (cudaStream_t)stream);
-  GI_TRY(ensure_device());
-  cudaStream_t st;
-  GI_TRY(host_stream(&st));
-  Scratch scr(st);
-  Phases ph(st);
-  ph.mark("h2d");
-  R *dx, *dy, *dd, *dp, *dout;
-  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
-  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
-  GI_TRY(to_device(scr, data_in, (size_t)len_x * len_y, &dd));
-  GI_TRY(to_device(scr, points, (size_t)2 * n, &dp));
-  GI_TRY(scr.alloc(&dout, (size_t)n));
-  GI_TRY(bilinear_device<R>(dx, len_x, dy, len_y, dd, dp, n, dout, flags, st));
-  ph.mark("d2h");
-  GI_TRY(to_host(scr, data_ip, dout, (size_t)n));
-  ph.finish();
-  GI_CUDA(cudaStreamSynchronize(st));
-  return GI_OK;
+  return bilinear_host<R>(x_axis, len_x, y_axis, len_y, data_in, points, n, data_ip, flags);
 }
 
 template <class R>
@@ -238,6 +221,9 @@ static int barycentric_api(const R* points, int num_points, const R* data_in, co
     return barycentric_device<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
                                  num_tri, row_begin, row_end, halo, data_ip, tri_out, mask_out, fill_src,
                                  counters, flags, (cudaStream_t)stream);
+  if (row_begin == 0 && row_end == len_y && !tri_out && !mask_out && !fill_src && !counters)
+    return barycentric_host<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
+                               num_tri, data_ip, flags);
   GI_TRY(ensure_device());
   cudaStream_t st;
   GI_TRY(host_stream(&st));
@@ -263,11 +249,11 @@ static int barycentric_api(const R* points, int num_points, const R* data_in, co
   GI_TRY(barycentric_device<R>(dp, num_points, dd, dx, len_x, dy, len_y, ds, dn, num_tri, row_begin, row_end, halo,
                                dout, dtri, dmask, dsrc, dcnt, flags, st));
   ph.mark("d2h");
-  GI_TRY(to_host(scr, data_ip, dout, band));
-  GI_TRY(to_host(scr, tri_out, dtri, band));
-  GI_TRY(to_host(scr, mask_out, dmask, band));
-  GI_TRY(to_host(scr, fill_src, dsrc, band));
-  GI_TRY(to_host(scr, counters, dcnt, 4));
+  GI_TRY(to_host(st, data_ip, dout, band));
+  GI_TRY(to_host(st, tri_out, dtri, band));
+  GI_TRY(to_host(st, mask_out, dmask, band));
+  GI_TRY(to_host(st, fill_src, dsrc, band));
+  GI_TRY(to_host(st, counters, dcnt, 4));
   ph.finish();
   return read_status(st, true);
 }
@@ -288,8 +274,8 @@ static int fill_api(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64
   GI_TRY(to_device(scr, data_ip, n, &dd));
   GI_TRY(out_device(scr, fill_src, n, &dsrc));
   GI_TRY(fill_device<R>(dm, len_x, len_y, dd, dsrc, flags, st));
-  GI_TRY(to_host(scr, data_ip, dd, n));
-  GI_TRY(to_host(scr, fill_src, dsrc, n));
+  GI_TRY(to_host(st, data_ip, dd, n));
+  GI_TRY(to_host(st, fill_src, dsrc, n));
   return read_status(st, true);
 }
 
@@ -304,6 +290,9 @@ static int kdtree_api(const R* points, int num_points, const R* data_in, const R
   if (mem == GI_DEVICE)
     return kdtree_device<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, k, row_begin, row_end,
                             data_ip, nn_index, nn_dist2, counters, flags, (cudaStream_t)stream);
+  if (!nn_index && !nn_dist2 && !counters)
+    return kdtree_host<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, k, row_begin, row_end, data_ip,
+                          flags);
   GI_TRY(ensure_device());
   cudaStream_t st;
   GI_TRY(host_stream(&st));
@@ -325,10 +314,10 @@ static int kdtree_api(const R* points, int num_points, const R* data_in, const R
   GI_TRY(kdtree_device<R>(dp, num_points, dd, dx, len_x, dy, len_y, k, row_begin, row_end, dout, dnn, dd2, dcnt,
                           flags, st));
   ph.mark("d2h");
-  GI_TRY(to_host(scr, data_ip, dout, band));
-  GI_TRY(to_host(scr, nn_index, dnn, band * k));
-  GI_TRY(to_host(scr, nn_dist2, dd2, band * k));
-  GI_TRY(to_host(scr, counters, dcnt, 4));
+  GI_TRY(to_host(st, data_ip, dout, band));
+  GI_TRY(to_host(st, nn_index, dnn, band * k));
+  GI_TRY(to_host(st, nn_dist2, dd2, band * k));
+  GI_TRY(to_host(st, counters, dcnt, 4));
   ph.finish();
   return read_status(st, true);
 }
@@ -349,6 +338,9 @@ static int esrg_api(const R* points, int num_points, const R* data_in, const R* 
   if (mem == GI_DEVICE)
     return esrg_device<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, k, row_begin,
                           row_end, data_ip, nn_index, nn_dist2, counters, flags, (cudaStream_t)stream);
+  if (!nn_index && !nn_dist2 && !counters)
+    return esrg_host<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, k, row_begin, row_end,
+                        data_ip, flags);
   GI_TRY(ensure_device());
   cudaStream_t st;
   GI_TRY(host_stream(&st));
@@ -370,10 +362,10 @@ static int esrg_api(const R* points, int num_points, const R* data_in, const R* 
   GI_TRY(esrg_device<R>(dp, num_points, dd, dx, len_x, dy, len_y, grid_spac, k, row_begin, row_end, dout, dnn, dd2,
                         dcnt, flags, st));
   ph.mark("d2h");
-  GI_TRY(to_host(scr, data_ip, dout, band));
-  GI_TRY(to_host(scr, nn_index, dnn, band * k));
-  GI_TRY(to_host(scr, nn_dist2, dd2, band * k));
-  GI_TRY(to_host(scr, counters, dcnt, 4));
+  GI_TRY(to_host(st, data_ip, dout, band));
+  GI_TRY(to_host(st, nn_index, dnn, band * k));
+  GI_TRY(to_host(st, nn_dist2, dd2, band * k));
+  GI_TRY(to_host(st, counters, dcnt, 4));
   ph.finish();
   return read_status(st, true);
 }
@@ -391,7 +383,7 @@ static int kd_build_api(const R* points, int num_points, int32_t* order, int fla
   GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
   GI_TRY(scr.alloc(&dord, (size_t)num_points));
   GI_TRY(kd_build_device<R>(dp, num_points, dord, flags, st));
-  GI_TRY(to_host(scr, order, dord, (size_t)num_points));
+  GI_TRY(to_host(st, order, dord, (size_t)num_points));
   return read_status(st, true);
 }
 
@@ -416,8 +408,8 @@ static int esrg_bin_api(const R* points, int num_points, const R* x_axis, int le
   GI_TRY(scr.alloc(&didx, (size_t)num_points));
   GI_TRY(scr.alloc(&dptr, cells + 1));
   GI_TRY(esrg_bin_device<R>(dp, num_points, dx, len_x, dy, len_y, grid_spac, didx, dptr, flags, st));
-  GI_TRY(to_host(scr, index_of_pts, didx, (size_t)num_points));
-  GI_TRY(to_host(scr, indptr, dptr, cells + 1));
+  GI_TRY(to_host(st, index_of_pts, didx, (size_t)num_points));
+  GI_TRY(to_host(st, indptr, dptr, cells + 1));
   return read_status(st, true);
 }
 
@@ -449,6 +441,7 @@ GI_API void* gi_host_alloc(uint64_t bytes) {
 GI_API void gi_host_free(void* p) { if (p) cudaFreeHost(p); }
 GI_API int gi_stream_status(void* stream) { return read_status((cudaStream_t)stream, true); }
 GI_API void gi_set_profiling(int on) { set_profiling(on != 0); }
+GI_API void gi_set_pipeline_band_bytes(uint64_t bytes) { g_band_bytes = bytes ? (int64_t)bytes : ((int64_t)32 << 20); }
 GI_API int gi_last_timings(double* ms, int capacity) {
   // names[i] opens at events[i]; "" entries are call-closing stamps (reported with 0 ms so indices line up)
   Recorder& r = t_rec;

@@ -519,7 +519,9 @@ template <class R> struct FillArgs {
   TargetWindow<R> win;  // window E covered by the bit mask
   const uint32_t* mask_words;
   const int* nz_words;     // indices of the non-zero mask words, counters[4] of them
-  int bf0, bf1, bs0, bs1;  // band B inside E (cells to fill, and where `out` lives)
+  int bf0, bf1, bs0, bs1;  // band B inside E: the cells to fill
+  int vf0, vf1, vs0, vs1;  // V, B <= V: the cells whose final value can be read from `out` (out is V-shaped)
+  int64_t nz_shift;        // added to the entries of nz_words (they may be relative to another window origin)
   R* out;
   int64_t* fill_src;  // optional, band-shaped
   int64_t* counters;  // [1] += masked cells, [2] = max level, [4] = number of nz_words
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(128) fill_kernel(const FillArgs<R> a) {
   long long masked = 0;
   const int level_cap = a.len_x + a.len_y;
   for (int64_t li = warp0; li < num_words; li += num_warps) {
-    const int64_t wi = a.nz_words[li];
+    const int64_t wi = a.nz_words[li] + a.nz_shift;
     const uint32_t wd = __ldg(a.mask_words + wi);
     const int s = a.win.s0 + (int)(wi / wpr), f = a.win.f0 + (int)(wi % wpr) * 32 + lane;
     if (!((wd >> lane) & 1u)) continue;
@@ -605,8 +607,8 @@ __global__ void __launch_bounds__(128) fill_kernel(const FillArgs<R> a) {
     if (best_i < 0) continue;
     const int sf = a.win.fast_is_y ? best_i : best_j, ss = a.win.fast_is_y ? best_j : best_i;
     R v;
-    if (sf >= a.bf0 && sf < a.bf1 && ss >= a.bs0 && ss < a.bs1) {
-      v = a.out[(int64_t)(ss - a.bs0) * (a.bf1 - a.bf0) + (sf - a.bf0)];
+    if (sf >= a.vf0 && sf < a.vf1 && ss >= a.vs0 && ss < a.vs1) {
+      v = a.out[(int64_t)(ss - a.vs0) * (a.vf1 - a.vf0) + (sf - a.vf0)];
     } else {  // source cell lies in the halo: recompute its (deterministic) value
       const R tx = __ldg((a.win.fast_is_y ? a.win.slow_axis : a.win.fast_axis) + best_j);
       const R ty = __ldg((a.win.fast_is_y ? a.win.fast_axis : a.win.slow_axis) + best_i);
@@ -615,9 +617,9 @@ __global__ void __launch_bounds__(128) fill_kernel(const FillArgs<R> a) {
                            a.iter_cap, inside, iters, g, a.status);
       v = eval_value(g, tx, ty);
     }
-    const int64_t o = (int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0);
-    a.out[o] = v;                                                  // :121
-    if (a.fill_src) a.fill_src[o] = (int64_t)best_i * a.len_x + best_j;
+    a.out[(int64_t)(s - a.vs0) * (a.vf1 - a.vf0) + (f - a.vf0)] = v;  // :121
+    if (a.fill_src)
+      a.fill_src[(int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0)] = (int64_t)best_i * a.len_x + best_j;
   }
   for (int off = 16; off > 0; off >>= 1) {
     masked += __shfl_down_sync(0xffffffffu, masked, off);
@@ -658,6 +660,60 @@ __global__ void bytes_to_bits_kernel(const uint8_t* __restrict__ mask, int nf, i
   }
 }
 
+template <class R> struct PackedMesh {
+  TriGeom<R>* geom;
+  int* seed;
+  int ncx, ncy, num_tri;
+};
+
+// 1. pack the mesh (device pointers; records and seed grid live in `scr`)
+template <class R>
+int bary_pack(Scratch& scr, const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+              const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours, int num_tri, int flags,
+              int* status, PackedMesh<R>* pm) {
+  cudaStream_t st = scr.stream();
+  GI_TRY(scr.alloc(&pm->geom, (size_t)num_tri));
+  pm->ncx = (len_x + kSeedCell - 1) / kSeedCell;
+  pm->ncy = (len_y + kSeedCell - 1) / kSeedCell;
+  pm->num_tri = num_tri;
+  GI_TRY(scr.alloc(&pm->seed, (size_t)pm->ncx * pm->ncy));
+  GI_CUDA(cudaMemsetAsync(pm->seed, 0x7f, sizeof(int) * (size_t)pm->ncx * pm->ncy, st));
+  pack_mesh_kernel<R><<<div_up(num_tri, 256), 256, 0, st>>>(
+      points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR), data_in,
+      topo_t3(simplices, num_tri, flags & GI_TOPO_ROWMAJOR), topo_t3(neighbours, num_tri, flags & GI_TOPO_ROWMAJOR),
+      num_points, num_tri, pm->geom, pm->seed, x_axis, len_x, y_axis, len_y, status);
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+
+// 2. + 2b. locate / evaluate / fix-up over the window wa.win (mask words, work list and counters as set in wa)
+template <class R>
+int bary_walk(const WalkArgs<R>& wa, const PackedMesh<R>& pm, const R* x_axis, const R* y_axis, int len_x, int len_y,
+              int num_points, cudaStream_t st) {
+  const int nf = wa.win.nf(), ns = wa.win.ns();
+  // 128 columns x 32 rows per CTA, 64 registers, >= 8 CTAs per SM: the best of the shapes measured in round 1
+  // (profiles/r01_walk_variants.md)
+  constexpr int kRows = 32;
+  dim3 grid(div_up(nf, kWalkThreads), div_up(ns, kRows));
+  GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
+  if (!wa.win.fast_is_y) locate_eval_kernel<R, false, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
+  else locate_eval_kernel<R, true, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
+  GI_CUDA(cudaGetLastError());
+  // targets inside the margin band of an edge: follow the reference's own path (normally none)
+  const int n_search = std::min(num_points, pm.num_tri);  // the reference searches triangles 1..num_points (:347)
+  start_tri_kernel<R><<<1, 1024, 0, st>>>(pm.geom, n_search, x_axis, y_axis, len_y, wa.counters);
+  fixup_kernel<R><<<kNumSMs * 2, 128, 0, st>>>(wa, len_x, len_y);
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+
+template <class R> void fill_from_walk(FillArgs<R>& fa, const WalkArgs<R>& wa, const PackedMesh<R>& pm, int len_x,
+                                       int len_y) {
+  fa.len_x = len_x; fa.len_y = len_y;
+  fa.geom = pm.geom; fa.seed = pm.seed; fa.ncx = pm.ncx; fa.ncy = pm.ncy; fa.num_tri = pm.num_tri;
+  fa.iter_cap = wa.iter_cap; fa.status = wa.status;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -682,18 +738,12 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
 
   // ---- 1. pack the mesh ---------------------------------------------------------------------
   ph.mark("pack_mesh");
-  TriGeom<R>* geom; int* seed; int64_t* counters; int* nz_words;
-  GI_TRY(scr.alloc(&geom, (size_t)num_tri));
-  const int ncx = (len_x + kSeedCell - 1) / kSeedCell, ncy = (len_y + kSeedCell - 1) / kSeedCell;
-  GI_TRY(scr.alloc(&seed, (size_t)ncx * ncy));
+  PackedMesh<R> pm;
+  GI_TRY(bary_pack<R>(scr, points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours, num_tri,
+                      flags, slot.dev, &pm));
+  int64_t* counters; int* nz_words;
   GI_TRY(scr.alloc(&counters, 8));
-  GI_CUDA(cudaMemsetAsync(seed, 0x7f, sizeof(int) * (size_t)ncx * ncy, st));
   GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 8, st));
-  pack_mesh_kernel<R><<<div_up(num_tri, 256), 256, 0, st>>>(
-      points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR), data_in,
-      topo_t3(simplices, num_tri, flags & GI_TOPO_ROWMAJOR), topo_t3(neighbours, num_tri, flags & GI_TOPO_ROWMAJOR),
-      num_points, num_tri, geom, seed, x_axis, len_x, y_axis, len_y, slot.dev);
-  GI_CUDA(cudaGetLastError());
 
   // ---- 2. walk + barycentric over the band plus halo rows -------------------------------------
   ph.mark("walk");
@@ -715,27 +765,11 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
   wa.nz_words = nz_words;
   wa.amb_cap = (int)std::min<int64_t>((int64_t)nf * ns, (int64_t)1 << 22);
   GI_TRY(scr.alloc(&wa.amb_list, (size_t)wa.amb_cap));
-  wa.geom = geom; wa.seed = seed; wa.ncx = ncx; wa.ncy = ncy; wa.num_tri = num_tri;
+  wa.geom = pm.geom; wa.seed = pm.seed; wa.ncx = pm.ncx; wa.ncy = pm.ncy; wa.num_tri = num_tri;
   wa.iter_cap = num_tri + 16;
   wa.out = data_ip; wa.tri_out = tri_out; wa.mask_words = mask_words; wa.counters = counters;
   wa.status = slot.dev;
-  {
-      // 128 columns x 32 rows per CTA, 64 registers, >= 8 CTAs per SM: the best of the shapes measured in round 1
-      // (profiles/r01_walk_variants.md)
-      constexpr int kRows = 32;
-      dim3 grid(div_up(nf, kWalkThreads), div_up(ns, kRows));
-      GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
-      if (rowmajor) locate_eval_kernel<R, false, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
-      else locate_eval_kernel<R, true, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
-      GI_CUDA(cudaGetLastError());
-    }
-  // ---- 2b. targets inside the margin band of an edge: follow the reference's own path (normally none) --
-  {
-    const int n_search = std::min(num_points, num_tri);  // the reference searches triangles 1..num_points (:347)
-    start_tri_kernel<R><<<1, 1024, 0, st>>>(geom, n_search, x_axis, y_axis, len_y, counters);
-    fixup_kernel<R><<<kNumSMs * 2, 128, 0, st>>>(wa, len_x, len_y);
-    GI_CUDA(cudaGetLastError());
-  }
+  GI_TRY(bary_walk<R>(wa, pm, x_axis, y_axis, len_x, len_y, num_points, st));
   if (mask_out || fill_src) {
     expand_mask_kernel<<<kNumSMs * 8, 256, 0, st>>>(mask_words, wpr, wa.win.f0, wa.win.s0, wa.bf0, wa.bf1, wa.bs0,
                                                    wa.bs1, mask_out, fill_src);
@@ -745,11 +779,11 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
   // ---- 3. hull fill ---------------------------------------------------------------------------
   ph.mark("fill");
   FillArgs<R> fa;
-  fa.win = wa.win; fa.mask_words = mask_words; fa.nz_words = nz_words;
+  fa.win = wa.win; fa.mask_words = mask_words; fa.nz_words = nz_words; fa.nz_shift = 0;
   fa.bf0 = wa.bf0; fa.bf1 = wa.bf1; fa.bs0 = wa.bs0; fa.bs1 = wa.bs1;
-  fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters; fa.len_x = len_x; fa.len_y = len_y;
-  fa.geom = geom; fa.seed = seed; fa.ncx = ncx; fa.ncy = ncy; fa.num_tri = num_tri;
-  fa.iter_cap = wa.iter_cap; fa.status = slot.dev;
+  fa.vf0 = wa.bf0; fa.vf1 = wa.bf1; fa.vs0 = wa.bs0; fa.vs1 = wa.bs1;
+  fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters;
+  fill_from_walk(fa, wa, pm, len_x, len_y);
   fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
   GI_CUDA(cudaGetLastError());
   ph.finish();
@@ -758,6 +792,112 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
     GI_CUDA(cudaMemcpyAsync(counters_out, counters, sizeof(int64_t) * 4, cudaMemcpyDeviceToDevice, st));
   GI_TRY(flush_status(st, slot));
   return GI_OK;
+}
+
+// GI_HOST form of the whole-grid call without debug outputs.  The mesh is packed once; the grid is cut into
+// bands along the axis that is not contiguous in memory; band b is located / evaluated, then band b-1 is hull-
+// filled (its fill may look into bands b-2 .. b, all walked by then) and copied back on a second stream while
+// band b+1 is being walked.  Nothing is computed twice.  A fill that would have to look further than one band
+// away (GI_ERR_HALO) makes the call start over with a single band.
+template <class R>
+int barycentric_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+                     int len_y, const int32_t* simplices, const int32_t* neighbours, int num_tri, R* data_ip,
+                     int flags) {
+  GI_REQUIRE(num_points >= 3 && num_tri >= 1, "need at least 3 points and 1 triangle");
+  GI_REQUIRE(len_x >= 1 && len_y >= 1, "empty axis");
+  GI_TRY(ensure_device());
+  HostPipe* pipe;
+  GI_TRY(host_pipe(&pipe));
+  cudaStream_t st = pipe->compute;
+  StatusSlot slot;
+  GI_TRY(get_status_slot(st, &slot));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("h2d");
+  R *dp, *dd, *dx, *dy, *dout;
+  int32_t *ds, *dn;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, data_in, (size_t)num_points, &dd));
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  GI_TRY(to_device(scr, simplices, (size_t)3 * num_tri, &ds));
+  GI_TRY(to_device(scr, neighbours, (size_t)3 * num_tri, &dn));
+  GI_TRY(scr.alloc(&dout, (size_t)len_x * len_y));
+  ph.mark("pack_mesh");
+  PackedMesh<R> pm;
+  GI_TRY(bary_pack<R>(scr, dp, num_points, dd, dx, len_x, dy, len_y, ds, dn, num_tri, flags, slot.dev, &pm));
+
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  const int nfast = rowmajor ? len_x : len_y, nslow = rowmajor ? len_y : len_x;
+  const int wpr = (nfast + 31) >> 5;
+  GI_REQUIRE((int64_t)wpr * nslow < (int64_t)0x7fffffff, "grid too large");
+  uint32_t* mask_words; int* nz_words; int64_t* counters; int* amb_list;
+  GI_TRY(scr.alloc(&mask_words, (size_t)wpr * nslow));
+  GI_TRY(scr.alloc(&nz_words, (size_t)wpr * nslow));
+  GI_TRY(scr.alloc(&counters, (size_t)8 * kMaxBands));
+  const int amb_cap = (int)std::min<int64_t>((int64_t)nfast * nslow, (int64_t)1 << 22);
+  GI_TRY(scr.alloc(&amb_list, (size_t)amb_cap));  // shared by the bands: band b's fix-up runs before band b+1's walk
+
+  int nb = plan_bands(nslow, (int64_t)len_x * len_y * sizeof(R));
+  ph.mark("walk");
+  for (;;) {
+    GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 8 * kMaxBands, st));
+    int64_t start[kMaxBands + 1];
+    for (int b = 0; b < nb; ++b) {
+      int64_t e;
+      band_range(0, nslow, nb, b, 32, &start[b], &e);
+      start[b + 1] = e;
+    }
+    auto window = [&](int64_t s0, int64_t s1) {
+      return rowmajor ? TargetWindow<R>{dx, dy, len_x, len_y, 0, len_x, (int)s0, (int)s1, 0}
+                      : TargetWindow<R>{dy, dx, len_y, len_x, 0, len_y, (int)s0, (int)s1, 1};
+    };
+    WalkArgs<R> was[kMaxBands];
+    auto fill_band = [&](int b) -> int {
+      const int64_t e0 = start[b > 0 ? b - 1 : 0], e1 = start[b + 1 < nb ? b + 2 : nb];
+      FillArgs<R> fa;
+      fa.win = window(e0, e1);
+      fa.mask_words = mask_words + e0 * wpr;
+      fa.nz_words = nz_words + start[b] * wpr;
+      fa.nz_shift = (start[b] - e0) * wpr;
+      fa.bf0 = 0; fa.bf1 = nfast; fa.bs0 = (int)start[b]; fa.bs1 = (int)start[b + 1];
+      fa.vf0 = 0; fa.vf1 = nfast; fa.vs0 = 0; fa.vs1 = (int)e1;  // everything walked so far holds final values
+      fa.out = dout; fa.fill_src = nullptr; fa.counters = counters + 8 * b;
+      fill_from_walk(fa, was[b], pm, len_x, len_y);
+      fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
+      GI_CUDA(cudaGetLastError());
+      GI_CUDA(cudaEventRecord(pipe->computed[b], st));
+      GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
+      const int64_t o = start[b] * nfast, cnt = (start[b + 1] - start[b]) * nfast;
+      return to_host(pipe->copy_out, data_ip + o, dout + o, (size_t)cnt);
+    };
+    for (int b = 0; b < nb; ++b) {
+      if (start[b] < start[b + 1]) {
+        WalkArgs<R>& wa = was[b];
+        wa.win = window(start[b], start[b + 1]);
+        wa.bf0 = 0; wa.bf1 = nfast; wa.bs0 = (int)start[b]; wa.bs1 = (int)start[b + 1];
+        wa.geom = pm.geom; wa.seed = pm.seed; wa.ncx = pm.ncx; wa.ncy = pm.ncy; wa.num_tri = num_tri;
+        wa.iter_cap = num_tri + 16;
+        wa.out = dout + start[b] * nfast; wa.tri_out = nullptr;
+        wa.mask_words = mask_words + start[b] * wpr; wa.nz_words = nz_words + start[b] * wpr;
+        wa.counters = counters + 8 * b;
+        wa.amb_list = amb_list; wa.amb_cap = amb_cap;
+        wa.status = slot.dev;
+        GI_TRY(bary_walk<R>(wa, pm, dx, dy, len_x, len_y, num_points, st));
+      }
+      if (b > 0 && start[b - 1] < start[b]) GI_TRY(fill_band(b - 1));
+    }
+    if (start[nb - 1] < start[nb]) GI_TRY(fill_band(nb - 1));
+    GI_TRY(flush_status(st, slot));
+    GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
+    const int status = read_status(st, true);
+    if (status == GI_ERR_HALO && nb > 1) {  // a hull fill reached beyond the neighbouring band: one band sees all
+      nb = 1;
+      continue;
+    }
+    ph.finish();
+    return status;
+  }
 }
 
 template <class R>
@@ -785,7 +925,8 @@ int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* 
     expand_mask_kernel<<<kNumSMs * 8, 256, 0, st>>>(words, wpr, 0, 0, 0, nf, 0, ns, nullptr, fill_src);
     GI_CUDA(cudaGetLastError());
   }
-  fa.mask_words = words; fa.nz_words = nz_words; fa.bf0 = 0; fa.bf1 = nf; fa.bs0 = 0; fa.bs1 = ns;
+  fa.mask_words = words; fa.nz_words = nz_words; fa.nz_shift = 0; fa.bf0 = 0; fa.bf1 = nf; fa.bs0 = 0; fa.bs1 = ns;
+  fa.vf0 = 0; fa.vf1 = nf; fa.vs0 = 0; fa.vs1 = ns;
   fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters; fa.len_x = len_x; fa.len_y = len_y;
   fa.geom = nullptr; fa.seed = nullptr; fa.ncx = fa.ncy = fa.num_tri = fa.iter_cap = 0;
   fa.status = slot.dev;
@@ -799,7 +940,9 @@ int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* 
   template int barycentric_device<R>(const R*, int, const R*, const R*, int, const R*, int, const int32_t*, \
                                      const int32_t*, int, int, int, int, R*, int32_t*, uint8_t*, int64_t*,  \
                                      int64_t*, int, cudaStream_t);                                          \
-  template int fill_device<R>(const uint8_t*, int, int, R*, int64_t*, int, cudaStream_t);
+  template int fill_device<R>(const uint8_t*, int, int, R*, int64_t*, int, cudaStream_t);                   \
+  template int barycentric_host<R>(const R*, int, const R*, const R*, int, const R*, int, const int32_t*,   \
+                                   const int32_t*, int, R*, int);
 GI_INSTANTIATE(double)
 GI_INSTANTIATE(float)
 

@@ -201,6 +201,27 @@ template <> struct SectorPath<double> {
 
 }  // namespace
 
+namespace {
+
+// the per-point part: `pv` / `out` address the chunk, `inv` holds the two mean-spacing inverses
+template <class R>
+int bilinear_points(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* data_in, PointsView<R> pv,
+                    int64_t num_points, const R* inv, R* out, int flags, cudaStream_t st) {
+  if (num_points == 0) return GI_OK;
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  const int64_t sy = rowmajor ? len_x : 1, sx = rowmajor ? 1 : len_y;
+  if (!SectorPath<R>::launch(x_axis, len_x, y_axis, len_y, data_in, pv, num_points, inv, out, rowmajor, st)) {
+    const int64_t blocks = (num_points + kThreads * kPts - 1) / (kThreads * kPts);
+    GI_REQUIRE(blocks <= 0x7fffffffLL, "too many points for one launch");
+    bilinear_kernel<R><<<(unsigned)blocks, kThreads, 0, st>>>(x_axis, len_x, y_axis, len_y, data_in, sy, sx, pv,
+                                                             num_points, inv, out);
+  }
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+
+}  // namespace
+
 template <class R>
 int bilinear_device(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* data_in, const R* points,
                     int64_t num_points, R* data_ip, int flags, cudaStream_t st) {
@@ -216,17 +237,66 @@ int bilinear_device(const R* x_axis, int len_x, const R* y_axis, int len_y, cons
   axis_inv_spacing_kernel<R><<<2, 256, 0, st>>>(x_axis, len_x, y_axis, len_y, inv);
   GI_CUDA(cudaGetLastError());
   ph.mark("bilinear");
-  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
-  const int64_t sy = rowmajor ? len_x : 1, sx = rowmajor ? 1 : len_y;
-  const PointsView<R> pv = points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR);
-  if (!SectorPath<R>::launch(x_axis, len_x, y_axis, len_y, data_in, pv, num_points, inv, data_ip, rowmajor, st)) {
-    const int64_t blocks = (num_points + kThreads * kPts - 1) / (kThreads * kPts);
-    GI_REQUIRE(blocks <= 0x7fffffffLL, "too many points for one launch");
-    bilinear_kernel<R><<<(unsigned)blocks, kThreads, 0, st>>>(x_axis, len_x, y_axis, len_y, data_in, sy, sx, pv,
-                                                             num_points, inv, data_ip);
-  }
-  GI_CUDA(cudaGetLastError());
+  GI_TRY(bilinear_points<R>(x_axis, len_x, y_axis, len_y, data_in, points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR),
+                            num_points, inv, data_ip, flags, st));
   ph.finish();
+  return GI_OK;
+}
+
+// GI_HOST form: the field goes in first; the points then stream through in chunks -- chunk c+1 is copied in and
+// chunk c-1's results are copied out (opposite PCIe direction) while chunk c is interpolated (common.cuh).
+template <class R>
+int bilinear_host(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* data_in, const R* points,
+                  int64_t num_points, R* data_ip, int flags) {
+  GI_REQUIRE(len_x >= 2 && len_y >= 2, "axes need at least 2 nodes");
+  GI_REQUIRE(num_points >= 0, "negative num_points");
+  GI_TRY(ensure_device());
+  if (num_points == 0) return GI_OK;
+  HostPipe* pipe;
+  GI_TRY(host_pipe(&pipe));
+  cudaStream_t st = pipe->compute;
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("h2d");
+  R *dx, *dy, *dd, *dp, *dout, *inv;
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  GI_TRY(scr.alloc(&dp, (size_t)2 * num_points));
+  GI_TRY(scr.alloc(&dout, (size_t)num_points));
+  GI_TRY(scr.alloc(&inv, 2));
+  axis_inv_spacing_kernel<R><<<2, 256, 0, st>>>(dx, len_x, dy, len_y, inv);
+  GI_CUDA(cudaGetLastError());
+  // the allocations above are ordered on the compute stream: the copy-in stream may touch them after this event
+  GI_CUDA(cudaEventRecord(pipe->computed[0], st));
+  GI_CUDA(cudaStreamWaitEvent(pipe->copy_in, pipe->computed[0], 0));
+  GI_TRY(to_device(scr, data_in, (size_t)len_x * len_y, &dd));  // (compute stream, overlaps the first point chunks)
+  ph.mark("bilinear");
+  const bool interleaved = flags & GI_POINTS_ROWMAJOR;
+  const int nc = plan_bands(num_points, (int64_t)num_points * 3 * sizeof(R));
+  for (int c = 0; c < nc; ++c) {
+    int64_t c0, c1;
+    band_range(0, num_points, nc, c, 4096, &c0, &c1);
+    if (c0 >= c1) continue;
+    const size_t cnt = (size_t)(c1 - c0);
+    if (interleaved) {
+      GI_CUDA(cudaMemcpyAsync(dp + 2 * c0, points + 2 * c0, 2 * cnt * sizeof(R), cudaMemcpyHostToDevice, pipe->copy_in));
+    } else {
+      GI_CUDA(cudaMemcpyAsync(dp + c0, points + c0, cnt * sizeof(R), cudaMemcpyHostToDevice, pipe->copy_in));
+      GI_CUDA(cudaMemcpyAsync(dp + num_points + c0, points + num_points + c0, cnt * sizeof(R), cudaMemcpyHostToDevice,
+                              pipe->copy_in));
+    }
+    GI_CUDA(cudaEventRecord(pipe->arrived[c], pipe->copy_in));
+    GI_CUDA(cudaStreamWaitEvent(st, pipe->arrived[c], 0));
+    const PointsView<R> pv = interleaved ? PointsView<R>{dp + 2 * c0, 2, 1} : PointsView<R>{dp + c0, 1, num_points};
+    GI_TRY(bilinear_points<R>(dx, len_x, dy, len_y, dd, pv, (int64_t)cnt, inv, dout + c0, flags, st));
+    GI_CUDA(cudaEventRecord(pipe->computed[c], st));
+    GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[c], 0));
+    GI_TRY(to_host(pipe->copy_out, data_ip + c0, dout + c0, cnt));
+  }
+  ph.finish();
+  GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
+  GI_CUDA(cudaStreamSynchronize(pipe->copy_in));
+  GI_CUDA(cudaStreamSynchronize(st));
   return GI_OK;
 }
 
@@ -234,5 +304,9 @@ template int bilinear_device<double>(const double*, int, const double*, int, con
                                      double*, int, cudaStream_t);
 template int bilinear_device<float>(const float*, int, const float*, int, const float*, const float*, int64_t,
                                     float*, int, cudaStream_t);
+template int bilinear_host<double>(const double*, int, const double*, int, const double*, const double*, int64_t,
+                                   double*, int);
+template int bilinear_host<float>(const float*, int, const float*, int, const float*, const float*, int64_t, float*,
+                                  int);
 
 }  // namespace gi

@@ -554,6 +554,56 @@ int esrg_bin(Scratch& scr, const R* points, int n, const R* data_in, const R* x_
   return GI_OK;
 }
 
+// query + IDW for the targets rows [row0,row1) x columns [col0,col1); `out` (and nn_*) are window-shaped.
+// counters: device int64[4], zeroed by the caller (slot 3 is the exact-order work counter of THIS call).
+template <class R>
+int esrg_query_window(Scratch& scr, const Binned<R>& b, int num_points, const R* x_axis, int len_x, const R* y_axis,
+                      int len_y, R grid_spac, int k, int row0, int row1, int col0, int col1, R* out,
+                      int32_t* nn_index, R* nn_dist2, int64_t* counters, bool stats, int flags, int* status,
+                      Phases* ph) {
+  if (row0 >= row1 || col0 >= col1) return GI_OK;
+  cudaStream_t st = scr.stream();
+  EsrgArgs<R> a;
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  a.win = rowmajor ? TargetWindow<R>{x_axis, y_axis, len_x, len_y, col0, col1, row0, row1, 0}
+                   : TargetWindow<R>{y_axis, x_axis, len_y, len_x, row0, row1, col0, col1, 1};
+  a.table = b.table; a.sxy = b.sxy; a.sval = b.sval; a.sid = b.sid;
+  a.len_x = len_x; a.len_y = len_y; a.k = k; a.spac = grid_spac;
+  a.out = out; a.nn_index = nn_index; a.nn_dist2 = nn_dist2;
+  a.counters = counters; a.stats = stats ? 1 : 0; a.status = status;
+  dim3 grid(div_up(a.win.nf(), 32), div_up(a.win.ns(), 4));
+  GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
+  const int64_t ntargets = (int64_t)a.win.nf() * a.win.ns();
+  GI_REQUIRE(ntargets < (int64_t)0x7fffffff, "window has more than 2^31 targets");
+  GI_TRY(scr.alloc(&a.todo, (size_t)ntargets));
+  a.todo_count = counters + 3;
+  a.all_exact = (flags & GI_ESRG_REFERENCE_ORDER) ? 1 : 0;
+  // first halo level: where the mean point density puts about 1.5k+6 points within r_H = spac*(H+1/2), so
+  // that all 32 lanes of a tile find k of them in the first pass with high probability (Poisson tail)
+  const double density = (double)num_points / ((double)len_x * (double)len_y);
+  int h0 = 1;
+  while (h0 < 12 && 3.141592653589793 * (h0 + 0.5) * (h0 + 0.5) * density < 1.5 * k + 6.0) ++h0;
+  // the tile kernel stages at most 255 points per tile; very dense inputs go straight to the per-thread kernel
+  const bool tiles_fit = (8.0 + 2 * h0) * (4.0 + 2 * h0) * density < 0.6 * kStageCap;
+  if (k <= 16 && tiles_fit) {
+    const int64_t tiles = (int64_t)div_up(a.win.nf(), 8) * div_up(a.win.ns(), 4);
+    const unsigned tg = (unsigned)div_up(tiles, kTileWarps);
+    if (k <= 8) esrg_tile_kernel<R, 9><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
+    else esrg_tile_kernel<R, 17><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
+  } else {
+    esrg_fast_kernel<R, 32><<<grid, 128, 0, st>>>(a);
+  }
+  GI_CUDA(cudaGetLastError());
+  if (ph) ph->mark("esrg_exact_ties");
+  const int eg = kNumSMs * 8;
+  if (k <= 4) esrg_query_kernel<R, 4><<<eg, 128, 0, st>>>(a);
+  else if (k <= 8) esrg_query_kernel<R, 8><<<eg, 128, 0, st>>>(a);
+  else if (k <= 16) esrg_query_kernel<R, 16><<<eg, 128, 0, st>>>(a);
+  else esrg_query_kernel<R, 32><<<eg, 128, 0, st>>>(a);
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+
 }  // namespace
 
 template <class R>
@@ -575,52 +625,72 @@ int esrg_device(const R* points, int num_points, const R* data_in, const R* x_ax
   int64_t* counters;
   GI_TRY(scr.alloc(&counters, 4));
   GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4, st));
-  EsrgArgs<R> a;
-  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
-  a.win = rowmajor ? TargetWindow<R>{x_axis, y_axis, len_x, len_y, 0, len_x, row_begin, row_end, 0}
-                   : TargetWindow<R>{y_axis, x_axis, len_y, len_x, row_begin, row_end, 0, len_x, 1};
-  a.table = b.table; a.sxy = b.sxy; a.sval = b.sval; a.sid = b.sid;
-  a.len_x = len_x; a.len_y = len_y; a.k = k; a.spac = grid_spac;
-  a.out = data_ip; a.nn_index = nn_index; a.nn_dist2 = nn_dist2;
-  a.counters = counters; a.stats = counters_out ? 1 : 0; a.status = slot.dev;
-  dim3 grid(div_up(a.win.nf(), 32), div_up(a.win.ns(), 4));
-  GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
-  const int64_t ntargets = (int64_t)a.win.nf() * a.win.ns();
-  GI_REQUIRE(ntargets < (int64_t)0x7fffffff, "window has more than 2^31 targets");
-  GI_TRY(scr.alloc(&a.todo, (size_t)ntargets));
-  a.todo_count = counters + 3;
-  a.all_exact = (flags & GI_ESRG_REFERENCE_ORDER) ? 1 : 0;
-  // first halo level: where the mean point density puts about 1.5k+6 points within r_H = spac*(H+1/2), so
-  // that all 32 lanes of a tile find k of them in the first pass with high probability (Poisson tail)
-  const double density = (double)num_points / ((double)len_x * (double)len_y);
-  int h0 = 1;
-  while (h0 < 12 && 3.141592653589793 * (h0 + 0.5) * (h0 + 0.5) * density < 1.5 * k + 6.0) ++h0;
-#ifdef GI_TUNING
-  if (const char* e = getenv("GI_ESRG_H0")) h0 = atoi(e);
-#endif
-  // the tile kernel stages at most 255 points per tile; very dense inputs go straight to the per-thread kernel
-  const bool tiles_fit = (8.0 + 2 * h0) * (4.0 + 2 * h0) * density < 0.6 * kStageCap;
-  if (k <= 16 && tiles_fit) {
-    const int64_t tiles = (int64_t)div_up(a.win.nf(), 8) * div_up(a.win.ns(), 4);
-    const unsigned tg = (unsigned)div_up(tiles, kTileWarps);
-    if (k <= 8) esrg_tile_kernel<R, 9><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
-    else esrg_tile_kernel<R, 17><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
-  } else {
-    esrg_fast_kernel<R, 32><<<grid, 128, 0, st>>>(a);
-  }
-  GI_CUDA(cudaGetLastError());
-  ph.mark("esrg_exact_ties");
-  const int eg = kNumSMs * 8;
-  if (k <= 4) esrg_query_kernel<R, 4><<<eg, 128, 0, st>>>(a);
-  else if (k <= 8) esrg_query_kernel<R, 8><<<eg, 128, 0, st>>>(a);
-  else if (k <= 16) esrg_query_kernel<R, 16><<<eg, 128, 0, st>>>(a);
-  else esrg_query_kernel<R, 32><<<eg, 128, 0, st>>>(a);
-  GI_CUDA(cudaGetLastError());
+  GI_TRY(esrg_query_window<R>(scr, b, num_points, x_axis, len_x, y_axis, len_y, grid_spac, k, row_begin, row_end, 0,
+                              len_x, data_ip, nn_index, nn_dist2, counters, counters_out != nullptr, flags, slot.dev,
+                              &ph));
   ph.finish();
   if (counters_out)
     GI_CUDA(cudaMemcpyAsync(counters_out, counters, sizeof(int64_t) * 4, cudaMemcpyDeviceToDevice, st));
   GI_TRY(flush_status(st, slot));
   return GI_OK;
+}
+
+// GI_HOST form without debug outputs: inputs in, points binned once, output bands computed and copied back in a
+// pipeline (common.cuh).
+template <class R>
+int esrg_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+              int len_y, R grid_spac, int k, int row_begin, int row_end, R* data_ip, int flags) {
+  GI_REQUIRE(k >= 1 && k <= 32, "num_neighbours must be in 1..32");
+  GI_REQUIRE(num_points >= k, "fewer points than num_neighbours");
+  GI_TRY(ensure_device());
+  if (row_begin == row_end) return GI_OK;
+  HostPipe* pipe;
+  GI_TRY(host_pipe(&pipe));
+  cudaStream_t st = pipe->compute;
+  StatusSlot slot;
+  GI_TRY(get_status_slot(st, &slot));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("h2d");
+  R *dp, *dd, *dx, *dy, *dout;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, data_in, (size_t)num_points, &dd));
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  const int nrows = row_end - row_begin;
+  GI_TRY(scr.alloc(&dout, (size_t)nrows * len_x));
+  ph.mark("esrg_bin");
+  Binned<R> bins;
+  GI_TRY(esrg_bin(scr, dp, num_points, dd, dx, len_x, dy, len_y, grid_spac, flags, &bins));
+  ph.mark("esrg_query");
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  const int64_t lo = rowmajor ? row_begin : 0, hi = rowmajor ? row_end : len_x;
+  const int64_t line = rowmajor ? len_x : nrows;
+  const int nb = plan_bands(hi - lo, (int64_t)nrows * len_x * sizeof(R));
+  int64_t* counters;
+  GI_TRY(scr.alloc(&counters, (size_t)4 * nb));
+  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4 * nb, st));
+  for (int b = 0; b < nb; ++b) {
+    int64_t b0, b1;
+    band_range(lo, hi, nb, b, 4, &b0, &b1);
+    if (b0 >= b1) continue;
+    R* band_out = dout + (b0 - lo) * line;
+    if (rowmajor)
+      GI_TRY(esrg_query_window<R>(scr, bins, num_points, dx, len_x, dy, len_y, grid_spac, k, (int)b0, (int)b1, 0,
+                                  len_x, band_out, nullptr, nullptr, counters + 4 * b, false, flags, slot.dev,
+                                  nullptr));
+    else
+      GI_TRY(esrg_query_window<R>(scr, bins, num_points, dx, len_x, dy, len_y, grid_spac, k, row_begin, row_end,
+                                  (int)b0, (int)b1, band_out, nullptr, nullptr, counters + 4 * b, false, flags,
+                                  slot.dev, nullptr));
+    GI_CUDA(cudaEventRecord(pipe->computed[b], st));
+    GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
+    GI_TRY(to_host(pipe->copy_out, data_ip + (b0 - lo) * line, band_out, (size_t)((b1 - b0) * line)));
+  }
+  ph.finish();
+  GI_TRY(flush_status(st, slot));
+  GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
+  return read_status(st, true);
 }
 
 template <class R>
@@ -640,7 +710,8 @@ int esrg_bin_device(const R* points, int num_points, const R* x_axis, int len_x,
   template int esrg_device<R>(const R*, int, const R*, const R*, int, const R*, int, R, int, int, int, R*, int32_t*, \
                               R*, int64_t*, int, cudaStream_t);                                                  \
   template int esrg_bin_device<R>(const R*, int, const R*, int, const R*, int, R, int32_t*, int32_t*, int,        \
-                                  cudaStream_t);
+                                  cudaStream_t);                                                                  \
+  template int esrg_host<R>(const R*, int, const R*, const R*, int, const R*, int, R, int, int, int, R*, int);
 GI_INSTANTIATE(double)
 GI_INSTANTIATE(float)
 

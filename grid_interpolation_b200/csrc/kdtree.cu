@@ -381,6 +381,51 @@ void launch_query(const KdArgs<R>& a, int prune, dim3 grid, cudaStream_t st) {
   else kd_query_kernel<R, KC, 0><<<grid, 128, 0, st>>>(a);
 }
 
+// build + gather: the implicit tree as the query reads it (lives in `scr`)
+template <class R> struct KdTreeDev {
+  XY<R>* nodes;
+  R* nval;
+  int* order;
+  int n;
+};
+template <class R>
+int kd_prepare(Scratch& scr, const R* points, int num_points, const R* data_in, int flags, KdTreeDev<R>* t) {
+  cudaStream_t st = scr.stream();
+  const PointsView<R> pv = points_2n(points, num_points, flags & GI_POINTS_ROWMAJOR);
+  GI_TRY(kd_build<R>(scr, pv, num_points, &t->order));
+  GI_TRY(scr.alloc(&t->nodes, (size_t)num_points));
+  GI_TRY(scr.alloc(&t->nval, (size_t)num_points));
+  t->n = num_points;
+  kd_gather_kernel<R><<<div_up(num_points, 256), 256, 0, st>>>(pv, data_in, t->order, num_points, t->nodes, t->nval,
+                                                               nullptr);
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+
+// query + IDW for the targets rows [row0,row1) x columns [col0,col1); `out` (and nn_*) are window-shaped
+template <class R>
+int kd_query_window(const KdTreeDev<R>& t, const R* x_axis, int len_x, const R* y_axis, int len_y, int k, int row0,
+                    int row1, int col0, int col1, R* out, int32_t* nn_index, R* nn_dist2, int64_t* counters,
+                    int flags, int* status, cudaStream_t st) {
+  if (row0 >= row1 || col0 >= col1) return GI_OK;
+  KdArgs<R> a;
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  a.win = rowmajor ? TargetWindow<R>{x_axis, y_axis, len_x, len_y, col0, col1, row0, row1, 0}
+                   : TargetWindow<R>{y_axis, x_axis, len_y, len_x, row0, row1, col0, col1, 1};
+  a.nodes = t.nodes; a.nval = t.nval; a.order = t.order; a.n = t.n; a.k = k;
+  a.out = out; a.nn_index = nn_index; a.nn_dist2 = nn_dist2;
+  a.counters = counters; a.status = status;
+  dim3 grid(div_up(a.win.nf(), 32), div_up(a.win.ns(), 4));
+  GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
+  const int prune = (flags & GI_KD_EXACT_PRUNE) ? 2 : ((flags & GI_KD_REFERENCE_VISITS) ? 1 : 0);
+  if (k <= 4) launch_query<R, 4>(a, prune, grid, st);
+  else if (k <= 8) launch_query<R, 8>(a, prune, grid, st);
+  else if (k <= 16) launch_query<R, 16>(a, prune, grid, st);
+  else launch_query<R, 32>(a, prune, grid, st);
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+
 }  // namespace
 
 template <class R>
@@ -395,37 +440,74 @@ int kdtree_device(const R* points, int num_points, const R* data_in, const R* x_
   Scratch scr(st);
   Phases ph(st);
   ph.mark("kd_build");
-  const PointsView<R> pv = points_2n(points, num_points, flags & GI_POINTS_ROWMAJOR);
-  int* order;
-  GI_TRY(kd_build<R>(scr, pv, num_points, &order));
-  XY<R>* nodes; R* nval; int64_t* counters;
-  GI_TRY(scr.alloc(&nodes, (size_t)num_points));
-  GI_TRY(scr.alloc(&nval, (size_t)num_points));
-  GI_TRY(scr.alloc(&counters, 4));
-  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4, st));
-  kd_gather_kernel<R><<<div_up(num_points, 256), 256, 0, st>>>(pv, data_in, order, num_points, nodes, nval, nullptr);
-  GI_CUDA(cudaGetLastError());
+  KdTreeDev<R> tree;
+  GI_TRY(kd_prepare<R>(scr, points, num_points, data_in, flags, &tree));
+  int64_t* counters = nullptr;
+  if (counters_out) {
+    GI_TRY(scr.alloc(&counters, 4));
+    GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4, st));
+  }
   ph.mark("kd_query");
-  KdArgs<R> a;
-  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
-  a.win = rowmajor ? TargetWindow<R>{x_axis, y_axis, len_x, len_y, 0, len_x, row_begin, row_end, 0}
-                   : TargetWindow<R>{y_axis, x_axis, len_y, len_x, row_begin, row_end, 0, len_x, 1};
-  a.nodes = nodes; a.nval = nval; a.order = order; a.n = num_points; a.k = k;
-  a.out = data_ip; a.nn_index = nn_index; a.nn_dist2 = nn_dist2;
-  a.counters = counters_out ? counters : nullptr; a.status = slot.dev;
-  dim3 grid(div_up(a.win.nf(), 32), div_up(a.win.ns(), 4));
-  GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
-  const int prune = (flags & GI_KD_EXACT_PRUNE) ? 2 : ((flags & GI_KD_REFERENCE_VISITS) ? 1 : 0);
-  if (k <= 4) launch_query<R, 4>(a, prune, grid, st);
-  else if (k <= 8) launch_query<R, 8>(a, prune, grid, st);
-  else if (k <= 16) launch_query<R, 16>(a, prune, grid, st);
-  else launch_query<R, 32>(a, prune, grid, st);
-  GI_CUDA(cudaGetLastError());
+  GI_TRY(kd_query_window<R>(tree, x_axis, len_x, y_axis, len_y, k, row_begin, row_end, 0, len_x, data_ip, nn_index,
+                            nn_dist2, counters, flags, slot.dev, st));
   ph.finish();
   if (counters_out)
     GI_CUDA(cudaMemcpyAsync(counters_out, counters, sizeof(int64_t) * 4, cudaMemcpyDeviceToDevice, st));
   GI_TRY(flush_status(st, slot));
   return GI_OK;
+}
+
+// GI_HOST form without debug outputs: inputs in, tree built once, output bands computed and copied back in a
+// pipeline (common.cuh).  host pointers in, synchronous.
+template <class R>
+int kdtree_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+                int len_y, int k, int row_begin, int row_end, R* data_ip, int flags) {
+  GI_REQUIRE(k >= 1 && k <= 32, "num_neighbours must be in 1..32");
+  GI_TRY(ensure_device());
+  if (row_begin == row_end) return GI_OK;
+  HostPipe* pipe;
+  GI_TRY(host_pipe(&pipe));
+  cudaStream_t st = pipe->compute;
+  StatusSlot slot;
+  GI_TRY(get_status_slot(st, &slot));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("h2d");
+  R *dp, *dd, *dx, *dy, *dout;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, data_in, (size_t)num_points, &dd));
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  const int nrows = row_end - row_begin;
+  GI_TRY(scr.alloc(&dout, (size_t)nrows * len_x));
+  ph.mark("kd_build");
+  KdTreeDev<R> tree;
+  GI_TRY(kd_prepare<R>(scr, dp, num_points, dd, flags, &tree));
+  ph.mark("kd_query");
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  // bands along the axis that is NOT contiguous in memory: each band is one contiguous piece of the output
+  const int64_t lo = rowmajor ? row_begin : 0, hi = rowmajor ? row_end : len_x;
+  const int64_t line = rowmajor ? len_x : nrows;  // elements per unit of the banded axis
+  const int nb = plan_bands(hi - lo, (int64_t)nrows * len_x * sizeof(R));
+  for (int b = 0; b < nb; ++b) {
+    int64_t b0, b1;
+    band_range(lo, hi, nb, b, 4, &b0, &b1);
+    if (b0 >= b1) continue;
+    R* band_out = dout + (b0 - lo) * line;
+    if (rowmajor)
+      GI_TRY(kd_query_window<R>(tree, dx, len_x, dy, len_y, k, (int)b0, (int)b1, 0, len_x, band_out, nullptr, nullptr,
+                                nullptr, flags, slot.dev, st));
+    else
+      GI_TRY(kd_query_window<R>(tree, dx, len_x, dy, len_y, k, row_begin, row_end, (int)b0, (int)b1, band_out,
+                                nullptr, nullptr, nullptr, flags, slot.dev, st));
+    GI_CUDA(cudaEventRecord(pipe->computed[b], st));
+    GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
+    GI_TRY(to_host(pipe->copy_out, data_ip + (b0 - lo) * line, band_out, (size_t)((b1 - b0) * line)));
+  }
+  ph.finish();
+  GI_TRY(flush_status(st, slot));
+  GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
+  return read_status(st, true);
 }
 
 template <class R>
@@ -444,7 +526,8 @@ int kd_build_device(const R* points, int num_points, int32_t* order_out, int fla
 #define GI_INSTANTIATE(R)                                                                                       \
   template int kdtree_device<R>(const R*, int, const R*, const R*, int, const R*, int, int, int, int, R*, int32_t*, \
                                 R*, int64_t*, int, cudaStream_t);                                               \
-  template int kd_build_device<R>(const R*, int, int32_t*, int, cudaStream_t);
+  template int kd_build_device<R>(const R*, int, int32_t*, int, cudaStream_t);                                  \
+  template int kdtree_host<R>(const R*, int, const R*, const R*, int, const R*, int, int, int, int, R*, int);
 GI_INSTANTIATE(double)
 GI_INSTANTIATE(float)
 

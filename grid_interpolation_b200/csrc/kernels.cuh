@@ -38,4 +38,21 @@ int kdtree_device(const R* points, int num_points, const R* data_in, const R* x_
 template <class R>
 int kd_build_device(const R* points, int num_points, int32_t* order, int flags, cudaStream_t st);
 
+// GI_HOST forms of the four operators (host pointers in, synchronous): copies and compute are pipelined over
+// output bands / point chunks (common.cuh, HostPipe).  No debug outputs; api.cu falls back to "copy in, *_device,
+// copy out" when those are requested.
+template <class R>
+int kdtree_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+                int len_y, int k, int row_begin, int row_end, R* data_ip, int flags);
+template <class R>
+int bilinear_host(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* data_in, const R* points,
+                  int64_t num_points, R* data_ip, int flags);
+template <class R>
+int barycentric_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+                     int len_y, const int32_t* simplices, const int32_t* neighbours, int num_tri, R* data_ip,
+                     int flags);
+template <class R>
+int esrg_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+              int len_y, R grid_spac, int k, int row_begin, int row_end, R* data_ip, int flags);
+
 }  // namespace gi

@@ -36,7 +36,7 @@ from ._lib import (GI_DEVICE, GI_FIELD_ROWMAJOR, GI_HOST, GI_KD_REFERENCE_VISITS
 __all__ = ["bilinear", "idw_kdtree", "idw_esrg_nearest", "barycentric_interpolation",
            "barycentric_interpolation_ex", "idw_kdtree_ex", "idw_esrg_nearest_ex", "kd_build",
            "assign_points_to_cells", "fill_nearest_neighbour", "pinned_empty", "pinned_copy",
-           "set_profiling", "last_timings"]
+           "set_profiling", "set_pipeline_band_bytes", "last_timings"]
 
 _F64 = np.dtype(np.float64)
 
@@ -479,6 +479,12 @@ def fill_nearest_neighbour(mask_outside, data_ip):
 
 def set_profiling(on: bool) -> None:
     lib().gi_set_profiling(1 if on else 0)
+
+
+def set_pipeline_band_bytes(nbytes: int) -> None:
+    """Granularity of the copy / compute pipeline of host (numpy) calls: bytes of output per band (0 = default
+    32 MB).  Results do not depend on it."""
+    lib().gi_set_pipeline_band_bytes(int(nbytes))
 
 
 def last_timings(capacity=8192):

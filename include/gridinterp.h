@@ -96,6 +96,11 @@ int gi_stream_status(void* stream);
 void gi_set_profiling(int on);
 int gi_last_timings(double* ms, int capacity);
 const char* gi_last_timing_name(int i);
+/* GI_HOST calls overlap their PCIe copies with the kernels: the grid operators compute and copy back their
+ * output in bands along the axis that is not contiguous in memory, bilinear streams its points through in
+ * chunks (results are identical to a one-shot call).  A band / chunk holds about `bytes` of output (default
+ * 32 MB, at most 16 bands per call); 0 restores the default.  Process-wide tuning knob. */
+void gi_set_pipeline_band_bytes(uint64_t bytes);
 /* Return cached scratch memory of the current device to the driver. */
 void gi_release_workspace(void);
 
