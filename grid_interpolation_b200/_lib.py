@@ -30,6 +30,7 @@ SIGNATURES = {
     "gi_last_timings": ([_vp, _i], _i),
     "gi_last_timing_name": ([_i], C.c_char_p),
     "gi_release_workspace": ([], None),
+    "gi_plan_destroy": ([_vp], None),
 }
 for _suf, _real in (("f64", _d), ("f32", _f)):
     SIGNATURES.update({
@@ -42,6 +43,10 @@ for _suf, _real in (("f64", _d), ("f32", _f)):
         f"gi_idw_kdtree_ex_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
         f"gi_idw_esrg_nearest_ex_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _real, _i, _i, _i, _vp, _vp, _vp, _vp,
                                             _i, _i, _vp], _i),
+        f"gi_barycentric_plan_create_{_suf}": ([_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),
+        f"gi_idw_kdtree_plan_create_{_suf}": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),
+        f"gi_idw_esrg_plan_create_{_suf}": ([_vp, _i, _vp, _i, _vp, _i, _real, _i, _i, _i, _i, _i, _vp, _vp], _i),
+        f"gi_plan_execute_{_suf}": ([_vp, _vp, _vp, _i, _vp], _i),
         f"gi_kd_build_{_suf}": ([_vp, _i, _vp, _i, _i, _vp], _i),
         f"gi_esrg_assign_points_to_cells_{_suf}": ([_vp, _i, _vp, _i, _vp, _i, _real, _vp, _vp, _i, _i, _vp], _i),
         f"gi_fill_nearest_neighbour_{_suf}": ([_vp, _i, _i, _vp, _vp, _i, _i, _vp], _i),

@@ -468,6 +468,36 @@ GI_API void gi_release_workspace(void) {
   }
 }
 
+// ---- plans --------------------------------------------------------------------------------------
+struct gi_plan { PlanBase* impl; };
+static int plan_wrap(int status, PlanBase* impl, gi_plan** out) {
+  if (status != GI_OK) { delete impl; return status; }
+  *out = new gi_plan{impl};
+  return GI_OK;
+}
+template <class R>
+static int plan_execute(gi_plan* plan, const R* data_in, R* data_ip, int mem, void* stream) {
+  GI_REQUIRE(plan && plan->impl && data_in && data_ip, "null pointer");
+  GI_REQUIRE(mem == GI_HOST || mem == GI_DEVICE, "mem must be GI_HOST or GI_DEVICE");
+  GI_REQUIRE(plan->impl->real_bytes == (int)sizeof(R), "plan was created for the other real kind");
+  int dev = -1;
+  GI_CUDA(cudaGetDevice(&dev));
+  GI_REQUIRE(dev == plan->impl->device, "plan belongs to another device");
+  return plan->impl->execute(data_in, data_ip, mem, (cudaStream_t)stream);
+}
+GI_API void gi_plan_destroy(gi_plan* plan) {
+  if (!plan) return;
+  delete plan->impl;
+  delete plan;
+}
+#define GI_PLAN_CHECK()                                                                          \
+  GI_CHECK_COMMON();                                                                             \
+  GI_REQUIRE(plan && points && x_axis && y_axis, "null pointer");                                \
+  GI_REQUIRE(num_points >= 1 && len_x >= 1 && len_y >= 1, "bad dimensions");                     \
+  GI_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= len_y, "bad row band");         \
+  *plan = nullptr;                                                                               \
+  PlanBase* impl = nullptr
+
 // Every entry point exists for both real kinds: _f64 is the graded path (the reference built with
 // -fdefault-real-8), _f32 reproduces the shipped single-precision numerics.
 #define GI_DEFINE_ENTRY_POINTS(SUF, R)                                                                              \
@@ -517,6 +547,44 @@ GI_API void gi_release_workspace(void) {
     return barycentric_api<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,    \
                               num_triangles, row_begin, row_end, halo, data_ip, tri_out, mask_out, fill_src,       \
                               counters, flags, mem, stream);                                                       \
+  }                                                                                                                 \
+  GI_API int gi_barycentric_plan_create_##SUF(const R* points, int num_points, const R* x_axis, int len_x,         \
+                                              const R* y_axis, int len_y, const int32_t* simplices,                \
+                                              const int32_t* neighbours, int num_triangles, int row_begin,         \
+                                              int row_end, int halo, int flags, int mem, void* stream,             \
+                                              gi_plan** plan) {                                                    \
+    GI_PLAN_CHECK();                                                                                                \
+    GI_REQUIRE(simplices && neighbours && num_points >= 3 && num_triangles >= 1 && halo >= 0, "bad arguments");    \
+    const int st = barycentric_plan_create<R>(points, num_points, x_axis, len_x, y_axis, len_y, simplices,         \
+                                              neighbours, num_triangles, row_begin, row_end, halo, flags, mem,     \
+                                              (cudaStream_t)stream, &impl);                                        \
+    return plan_wrap(st, impl, plan);                                                                               \
+  }                                                                                                                 \
+  GI_API int gi_idw_kdtree_plan_create_##SUF(const R* points, int num_points, const R* x_axis, int len_x,          \
+                                             const R* y_axis, int len_y, int num_neighbours, int row_begin,        \
+                                             int row_end, int flags, int mem, void* stream, gi_plan** plan) {      \
+    GI_PLAN_CHECK();                                                                                                \
+    const int st = kdtree_plan_create<R>(points, num_points, x_axis, len_x, y_axis, len_y, num_neighbours,         \
+                                         row_begin, row_end, flags, mem, (cudaStream_t)stream, &impl);             \
+    return plan_wrap(st, impl, plan);                                                                               \
+  }                                                                                                                 \
+  GI_API int gi_idw_esrg_plan_create_##SUF(const R* points, int num_points, const R* x_axis, int len_x,            \
+                                           const R* y_axis, int len_y, R grid_spac, int num_neighbours,            \
+                                           int row_begin, int row_end, int flags, int mem, void* stream,           \
+                                           gi_plan** plan) {                                                       \
+    GI_PLAN_CHECK();                                                                                                \
+    GI_REQUIRE(grid_spac > R(0), "grid_spac must be positive");                                                     \
+    if (num_points < num_neighbours) {                                                                              \
+      set_error("fewer source points than num_neighbours (the reference loops forever, query_esrg.f90:178)");      \
+      return GI_ERR_TOO_FEW_POINTS;                                                                                 \
+    }                                                                                                               \
+    const int st = esrg_plan_create<R>(points, num_points, x_axis, len_x, y_axis, len_y, grid_spac,                \
+                                       num_neighbours, row_begin, row_end, flags, mem, (cudaStream_t)stream,       \
+                                       &impl);                                                                      \
+    return plan_wrap(st, impl, plan);                                                                               \
+  }                                                                                                                 \
+  GI_API int gi_plan_execute_##SUF(gi_plan* plan, const R* data_in, R* data_ip, int mem, void* stream) {           \
+    return plan_execute<R>(plan, data_in, data_ip, mem, stream);                                                   \
   }                                                                                                                 \
   GI_API int gi_kd_build_##SUF(const R* points, int num_points, int32_t* order, int flags, int mem,                \
                                void* stream) {                                                                      \

@@ -30,6 +30,7 @@
 // All index decisions (orientation signs, first failing edge) and all values use the reference's operations
 // in the reference's order with FMA contraction disabled (-fmad=false): bit-identical to the oracle.
 #include <algorithm>
+#include <memory>
 
 #include "ieee_div.cuh"
 #include "kernels.cuh"
@@ -132,6 +133,19 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
   const R fx = (cx - sg.x0) * sg.inv_cell_x, fy = (cy - sg.y0) * sg.inv_cell_y;
   if (fx >= R(0) && fy >= R(0) && fx < R(sg.ncx) && fy < R(sg.ncy))
     atomicMin(seed + (int)fy * sg.ncx + (int)fx, t);
+}
+
+// plans: new nodal values into sector 2 of the existing records (ids were validated by pack_mesh_kernel)
+template <class R>
+__global__ void __launch_bounds__(256)
+pack_values_kernel(const R* __restrict__ data, TopoView simp, int num_points, int num_tri, TriGeom<R>* __restrict__ geom) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_tri) return;
+  int a = simp(t, 0), b = simp(t, 1), c = simp(t, 2);
+  if ((unsigned)(a - 1) >= (unsigned)num_points || (unsigned)(b - 1) >= (unsigned)num_points ||
+      (unsigned)(c - 1) >= (unsigned)num_points)
+    a = b = c = 1;
+  geom[t].d1 = __ldg(data + (a - 1)); geom[t].d2 = __ldg(data + (b - 1)); geom[t].d3 = __ldg(data + (c - 1));
 }
 
 // Seed triangle for grid target (ix, iy): the cell's own entry, else the nearest non-empty cell within 3
@@ -714,39 +728,19 @@ template <class R> void fill_from_walk(FillArgs<R>& fa, const WalkArgs<R>& wa, c
   fa.iter_cap = wa.iter_cap; fa.status = wa.status;
 }
 
-}  // namespace
-
-// ---------------------------------------------------------------------------------------------
-// host-side orchestration (device pointers in, work enqueued on `st`)
-// ---------------------------------------------------------------------------------------------
+// 2. + 3. for the row band [row_begin,row_end) with `halo` extra rows walked on each side, on a packed mesh
 template <class R>
-int barycentric_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
-                       const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
-                       int num_tri, int row_begin, int row_end, int halo, R* data_ip, int32_t* tri_out,
-                       uint8_t* mask_out, int64_t* fill_src, int64_t* counters_out, int flags,
-                       cudaStream_t st) {
-  GI_REQUIRE(num_points >= 3 && num_tri >= 1, "need at least 3 points and 1 triangle");
-  GI_REQUIRE(len_x >= 1 && len_y >= 1, "empty axis");
-  GI_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= len_y, "row band out of range");
-  GI_REQUIRE(halo >= 0, "negative halo");
-  GI_TRY(ensure_device());
-  if (row_begin == row_end) return GI_OK;
-  StatusSlot slot;
-  GI_TRY(get_status_slot(st, &slot));
-  Scratch scr(st);
-  Phases ph(st);
-
-  // ---- 1. pack the mesh ---------------------------------------------------------------------
-  ph.mark("pack_mesh");
-  PackedMesh<R> pm;
-  GI_TRY(bary_pack<R>(scr, points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours, num_tri,
-                      flags, slot.dev, &pm));
+int bary_run_window(Scratch& scr, const PackedMesh<R>& pm, const R* x_axis, int len_x, const R* y_axis, int len_y,
+                    int num_points, int row_begin, int row_end, int halo, R* data_ip, int32_t* tri_out,
+                    uint8_t* mask_out, int64_t* fill_src, int64_t* counters_out, int flags, const StatusSlot& slot,
+                    cudaStream_t st, Phases* ph) {
+  const int num_tri = pm.num_tri;
   int64_t* counters; int* nz_words;
   GI_TRY(scr.alloc(&counters, 8));
   GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 8, st));
 
   // ---- 2. walk + barycentric over the band plus halo rows -------------------------------------
-  ph.mark("walk");
+  ph->mark("walk");
   const int e0 = max(0, row_begin - halo), e1 = min(len_y, row_end + halo);
   const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
   WalkArgs<R> wa;
@@ -777,7 +771,7 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
   }
 
   // ---- 3. hull fill ---------------------------------------------------------------------------
-  ph.mark("fill");
+  ph->mark("fill");
   FillArgs<R> fa;
   fa.win = wa.win; fa.mask_words = mask_words; fa.nz_words = nz_words; fa.nz_shift = 0;
   fa.bf0 = wa.bf0; fa.bf1 = wa.bf1; fa.bs0 = wa.bs0; fa.bs1 = wa.bs1;
@@ -786,47 +780,57 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
   fill_from_walk(fa, wa, pm, len_x, len_y);
   fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
   GI_CUDA(cudaGetLastError());
-  ph.finish();
-
   if (counters_out)
     GI_CUDA(cudaMemcpyAsync(counters_out, counters, sizeof(int64_t) * 4, cudaMemcpyDeviceToDevice, st));
-  GI_TRY(flush_status(st, slot));
   return GI_OK;
 }
 
-// GI_HOST form of the whole-grid call without debug outputs.  The mesh is packed once; the grid is cut into
-// bands along the axis that is not contiguous in memory; band b is located / evaluated, then band b-1 is hull-
-// filled (its fill may look into bands b-2 .. b, all walked by then) and copied back on a second stream while
-// band b+1 is being walked.  Nothing is computed twice.  A fill that would have to look further than one band
-// away (GI_ERR_HALO) makes the call start over with a single band.
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host-side orchestration (device pointers in, work enqueued on `st`)
+// ---------------------------------------------------------------------------------------------
 template <class R>
-int barycentric_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
-                     int len_y, const int32_t* simplices, const int32_t* neighbours, int num_tri, R* data_ip,
-                     int flags) {
+int barycentric_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                       const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
+                       int num_tri, int row_begin, int row_end, int halo, R* data_ip, int32_t* tri_out,
+                       uint8_t* mask_out, int64_t* fill_src, int64_t* counters_out, int flags,
+                       cudaStream_t st) {
   GI_REQUIRE(num_points >= 3 && num_tri >= 1, "need at least 3 points and 1 triangle");
   GI_REQUIRE(len_x >= 1 && len_y >= 1, "empty axis");
+  GI_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= len_y, "row band out of range");
+  GI_REQUIRE(halo >= 0, "negative halo");
   GI_TRY(ensure_device());
-  HostPipe* pipe;
-  GI_TRY(host_pipe(&pipe));
-  cudaStream_t st = pipe->compute;
+  if (row_begin == row_end) return GI_OK;
   StatusSlot slot;
   GI_TRY(get_status_slot(st, &slot));
   Scratch scr(st);
   Phases ph(st);
-  ph.mark("h2d");
-  R *dp, *dd, *dx, *dy, *dout;
-  int32_t *ds, *dn;
-  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
-  GI_TRY(to_device(scr, data_in, (size_t)num_points, &dd));
-  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
-  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
-  GI_TRY(to_device(scr, simplices, (size_t)3 * num_tri, &ds));
-  GI_TRY(to_device(scr, neighbours, (size_t)3 * num_tri, &dn));
-  GI_TRY(scr.alloc(&dout, (size_t)len_x * len_y));
+
+  // ---- 1. pack the mesh ---------------------------------------------------------------------
   ph.mark("pack_mesh");
   PackedMesh<R> pm;
-  GI_TRY(bary_pack<R>(scr, dp, num_points, dd, dx, len_x, dy, len_y, ds, dn, num_tri, flags, slot.dev, &pm));
+  GI_TRY(bary_pack<R>(scr, points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours, num_tri,
+                      flags, slot.dev, &pm));
+  GI_TRY(bary_run_window<R>(scr, pm, x_axis, len_x, y_axis, len_y, num_points, row_begin, row_end, halo, data_ip,
+                            tri_out, mask_out, fill_src, counters_out, flags, slot, st, &ph));
+  ph.finish();
+  GI_TRY(flush_status(st, slot));
+  return GI_OK;
+}
 
+namespace {
+// Whole grid, mesh already packed: the grid is cut into bands along the axis that is not contiguous in memory;
+// band b is located / evaluated, then band b-1 is hull-filled (its fill may look into bands b-2 .. b, all walked
+// by then) and copied back on a second stream while band b+1 is being walked.  Nothing is computed twice.  A
+// fill that would have to look further than one band away (GI_ERR_HALO) makes the run start over with a single
+// band.  dout is the device twin of data_ip (host), both (len_y, len_x) in the layout `flags` selects.
+// Returns the status of the run (synchronous).
+template <class R>
+int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const R* dx, int len_x, const R* dy,
+                    int len_y, int num_points, R* dout, R* data_ip, int flags, const StatusSlot& slot) {
+  cudaStream_t st = pipe->compute;
+  const int num_tri = pm.num_tri;
   const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
   const int nfast = rowmajor ? len_x : len_y, nslow = rowmajor ? len_y : len_x;
   const int wpr = (nfast + 31) >> 5;
@@ -839,7 +843,6 @@ int barycentric_host(const R* points, int num_points, const R* data_in, const R*
   GI_TRY(scr.alloc(&amb_list, (size_t)amb_cap));  // shared by the bands: band b's fix-up runs before band b+1's walk
 
   int nb = plan_bands(nslow, (int64_t)len_x * len_y * sizeof(R));
-  ph.mark("walk");
   for (;;) {
     GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 8 * kMaxBands, st));
     int64_t start[kMaxBands + 1];
@@ -895,9 +898,143 @@ int barycentric_host(const R* points, int num_points, const R* data_in, const R*
       nb = 1;
       continue;
     }
-    ph.finish();
     return status;
   }
+}
+}  // namespace
+
+// GI_HOST form of the whole-grid call without debug outputs: inputs in, mesh packed once, banded run.
+template <class R>
+int barycentric_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+                     int len_y, const int32_t* simplices, const int32_t* neighbours, int num_tri, R* data_ip,
+                     int flags) {
+  GI_REQUIRE(num_points >= 3 && num_tri >= 1, "need at least 3 points and 1 triangle");
+  GI_REQUIRE(len_x >= 1 && len_y >= 1, "empty axis");
+  GI_TRY(ensure_device());
+  HostPipe* pipe;
+  GI_TRY(host_pipe(&pipe));
+  cudaStream_t st = pipe->compute;
+  StatusSlot slot;
+  GI_TRY(get_status_slot(st, &slot));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("h2d");
+  R *dp, *dd, *dx, *dy, *dout;
+  int32_t *ds, *dn;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, data_in, (size_t)num_points, &dd));
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  GI_TRY(to_device(scr, simplices, (size_t)3 * num_tri, &ds));
+  GI_TRY(to_device(scr, neighbours, (size_t)3 * num_tri, &dn));
+  GI_TRY(scr.alloc(&dout, (size_t)len_x * len_y));
+  ph.mark("pack_mesh");
+  PackedMesh<R> pm;
+  GI_TRY(bary_pack<R>(scr, dp, num_points, dd, dx, len_x, dy, len_y, ds, dn, num_tri, flags, slot.dev, &pm));
+  ph.mark("walk");
+  const int status = bary_run_banded<R>(pipe, scr, pm, dx, len_x, dy, len_y, num_points, dout, data_ip, flags, slot);
+  ph.finish();
+  return status;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: packed mesh + target grid resident on the device, one execute() per field of nodal values
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <class R> struct BaryPlan : PlanBase {
+  Scratch keep{nullptr, true};
+  PackedMesh<R> pm;
+  R *dx, *dy;
+  int32_t* simp;  // device copy of simplices (for new nodal values)
+  int num_points, len_x, len_y, row_begin, row_end, halo, flags;
+
+  int execute(const void* data_in_v, void* data_ip_v, int mem, cudaStream_t st_in) override {
+    const R* data_in = static_cast<const R*>(data_in_v);
+    R* data_ip = static_cast<R*>(data_ip_v);
+    if (row_begin == row_end) return GI_OK;
+    HostPipe* pipe = nullptr;
+    cudaStream_t st = st_in;
+    if (mem == GI_HOST) { GI_TRY(host_pipe(&pipe)); st = pipe->compute; }
+    StatusSlot slot;
+    GI_TRY(get_status_slot(st, &slot));
+    Scratch scr(st);
+    Phases ph(st);
+    const R* dd = data_in;
+    R* dout = data_ip;
+    const size_t band = (size_t)(row_end - row_begin) * len_x;
+    if (mem == GI_HOST) {
+      ph.mark("h2d");
+      R* tmp;
+      GI_TRY(to_device(scr, data_in, (size_t)num_points, &tmp));
+      dd = tmp;
+      GI_TRY(scr.alloc(&dout, band));
+    }
+    ph.mark("pack_values");
+    pack_values_kernel<R><<<div_up(pm.num_tri, 256), 256, 0, st>>>(dd, topo_t3(simp, pm.num_tri, flags & GI_TOPO_ROWMAJOR),
+                                                                  num_points, pm.num_tri, pm.geom);
+    GI_CUDA(cudaGetLastError());
+    ph.mark("walk");
+    if (mem == GI_HOST && row_begin == 0 && row_end == len_y) {
+      const int status = bary_run_banded<R>(pipe, scr, pm, dx, len_x, dy, len_y, num_points, dout, data_ip, flags, slot);
+      ph.finish();
+      return status;
+    }
+    GI_TRY(bary_run_window<R>(scr, pm, dx, len_x, dy, len_y, num_points, row_begin, row_end, halo, dout, nullptr,
+                              nullptr, nullptr, nullptr, flags, slot, st, &ph));
+    ph.finish();
+    GI_TRY(flush_status(st, slot));
+    if (mem == GI_HOST) {
+      GI_TRY(to_host(st, data_ip, dout, band));
+      return read_status(st, true);
+    }
+    return GI_OK;
+  }
+};
+}  // namespace
+
+template <class R>
+int barycentric_plan_create(const R* points, int num_points, const R* x_axis, int len_x, const R* y_axis, int len_y,
+                            const int32_t* simplices, const int32_t* neighbours, int num_tri, int row_begin,
+                            int row_end, int halo, int flags, int mem, cudaStream_t st_in, PlanBase** out) {
+  GI_REQUIRE(num_points >= 3 && num_tri >= 1, "need at least 3 points and 1 triangle");
+  GI_REQUIRE(len_x >= 1 && len_y >= 1, "empty axis");
+  GI_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= len_y && halo >= 0, "bad row band");
+  GI_TRY(ensure_device());
+  cudaStream_t st = st_in;
+  if (mem == GI_HOST) { HostPipe* pipe; GI_TRY(host_pipe(&pipe)); st = pipe->compute; }
+  StatusSlot slot;
+  GI_TRY(get_status_slot(st, &slot));
+  std::unique_ptr<BaryPlan<R>> plan(new BaryPlan<R>());
+  plan->real_bytes = sizeof(R);
+  GI_CUDA(cudaGetDevice(&plan->device));
+  plan->num_points = num_points; plan->len_x = len_x; plan->len_y = len_y;
+  plan->row_begin = row_begin; plan->row_end = row_end; plan->halo = halo; plan->flags = flags;
+  Scratch tmp(st);
+  const cudaMemcpyKind kind = mem == GI_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  GI_TRY(plan->keep.alloc(&plan->dx, (size_t)len_x));
+  GI_TRY(plan->keep.alloc(&plan->dy, (size_t)len_y));
+  GI_TRY(plan->keep.alloc(&plan->simp, (size_t)3 * num_tri));
+  GI_CUDA(cudaMemcpyAsync(plan->dx, x_axis, sizeof(R) * (size_t)len_x, kind, st));
+  GI_CUDA(cudaMemcpyAsync(plan->dy, y_axis, sizeof(R) * (size_t)len_y, kind, st));
+  GI_CUDA(cudaMemcpyAsync(plan->simp, simplices, sizeof(int32_t) * (size_t)3 * num_tri, kind, st));
+  const R* dp = points;
+  const int32_t* dn = neighbours;
+  R* zeros;  // nodal values are supplied by execute(): pack with zeros
+  GI_TRY(tmp.alloc(&zeros, (size_t)num_points));
+  GI_CUDA(cudaMemsetAsync(zeros, 0, sizeof(R) * (size_t)num_points, st));
+  if (mem == GI_HOST) {
+    R* t; int32_t* tn;
+    GI_TRY(to_device(tmp, points, (size_t)2 * num_points, &t));
+    GI_TRY(to_device(tmp, neighbours, (size_t)3 * num_tri, &tn));
+    dp = t; dn = tn;
+  }
+  GI_TRY(bary_pack<R>(plan->keep, dp, num_points, zeros, plan->dx, len_x, plan->dy, len_y, plan->simp, dn, num_tri,
+                      flags, slot.dev, &plan->pm));
+  GI_TRY(flush_status(st, slot));
+  const int status = read_status(st, true);  // invalid ids are reported at creation
+  if (status != GI_OK) return status;
+  *out = plan.release();
+  return GI_OK;
 }
 
 template <class R>
@@ -942,7 +1079,10 @@ int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* 
                                      int64_t*, int, cudaStream_t);                                          \
   template int fill_device<R>(const uint8_t*, int, int, R*, int64_t*, int, cudaStream_t);                   \
   template int barycentric_host<R>(const R*, int, const R*, const R*, int, const R*, int, const int32_t*,   \
-                                   const int32_t*, int, R*, int);
+                                   const int32_t*, int, R*, int);                                           \
+  template int barycentric_plan_create<R>(const R*, int, const R*, int, const R*, int, const int32_t*,      \
+                                          const int32_t*, int, int, int, int, int, int, cudaStream_t,       \
+                                          PlanBase**);
 GI_INSTANTIATE(double)
 GI_INSTANTIATE(float)
 

@@ -103,7 +103,8 @@ int ensure_device();  // validates that a CUDA device exists; configures the mem
 
 class Scratch {
  public:
-  explicit Scratch(cudaStream_t s) : stream_(s) {}
+  // persistent = true: plain cudaMalloc / cudaFree, for memory that outlives the call and its stream (plans)
+  explicit Scratch(cudaStream_t s, bool persistent = false) : stream_(s), persistent_(persistent) {}
   ~Scratch() { release(); }
   Scratch(const Scratch&) = delete;
   Scratch& operator=(const Scratch&) = delete;
@@ -111,7 +112,7 @@ class Scratch {
     void* p = nullptr;
     size_t bytes = count * sizeof(T);
     if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMallocAsync(&p, bytes, stream_);
+    cudaError_t e = persistent_ ? cudaMalloc(&p, bytes) : cudaMallocAsync(&p, bytes, stream_);
     if (e != cudaSuccess) {
       *out = nullptr;
       if (e == cudaErrorMemoryAllocation) {
@@ -126,13 +127,17 @@ class Scratch {
     return GI_OK;
   }
   void release() {
-    for (void* p : ptrs_) cudaFreeAsync(p, stream_);
+    for (void* p : ptrs_) {
+      if (persistent_) cudaFree(p);
+      else cudaFreeAsync(p, stream_);
+    }
     ptrs_.clear();
   }
   cudaStream_t stream() const { return stream_; }
 
  private:
   cudaStream_t stream_;
+  bool persistent_;
   std::vector<void*> ptrs_;
 };
 
@@ -199,6 +204,17 @@ inline void band_range(int64_t lo, int64_t hi, int nb, int b, int64_t align, int
   *b0 = lo + per * b < hi ? lo + per * b : hi;
   *b1 = *b0 + per < hi ? *b0 + per : hi;
 }
+
+// A plan (gi_plan): search structure / packed mesh + target grid resident on the device; execute() interpolates
+// one field of nodal values.  One implementation per operator (kdtree.cu, esrg.cu, barycentric.cu).
+struct PlanBase {
+  int real_bytes = 8;  // sizeof(R) of the plan
+  int device = 0;
+  virtual ~PlanBase() {}
+  // data_in (num_points) -> data_ip (band rows, len_x) in the layout fixed at creation; mem / stream as in the
+  // one-shot calls
+  virtual int execute(const void* data_in, void* data_ip, int mem, cudaStream_t st) = 0;
+};
 
 template <class T> int to_device(Scratch& scr, const T* host, size_t count, T** dev) {
   GI_TRY(scr.alloc(dev, count));

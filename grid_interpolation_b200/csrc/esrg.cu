@@ -30,6 +30,7 @@
 //               re-scans the inner frames with the predicate "was deferred at the previous level"
 //               (d2 > r2_prev), which yields the same order for any point density.
 #include <cstdlib>
+#include <memory>
 
 #include "kernels.cuh"
 #include "scan.cuh"
@@ -96,8 +97,7 @@ esrg_gather_kernel(PointsView<R> pts, const R* __restrict__ data, const int* __r
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const int i = sid[p] - 1;
-  XY<R> v; v.x = pts.x(i); v.y = pts.y(i);
-  sxy[p] = v;
+  if (sxy) { XY<R> v; v.x = pts.x(i); v.y = pts.y(i); sxy[p] = v; }
   if (sval) sval[p] = __ldg(data + i);
 }
 
@@ -530,28 +530,33 @@ template <class R> struct Binned {
 };
 
 template <class R>
-int esrg_bin(Scratch& scr, const R* points, int n, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
-             int len_y, R spac, int flags, Binned<R>* b) {
-  cudaStream_t st = scr.stream();
+int esrg_bin(Scratch& keep, Scratch& tmp, const R* points, int n, const R* data_in, const R* x_axis, int len_x,
+             const R* y_axis, int len_y, R spac, int flags, bool want_values, Binned<R>* b) {
+  cudaStream_t st = tmp.stream();
   const int64_t cells = (int64_t)len_x * len_y;
   GI_REQUIRE(cells < (int64_t)0x7fffffff, "grid has more than 2^31 cells");
-  GI_TRY(scr.alloc(&b->table, (size_t)cells));
-  GI_TRY(scr.alloc(&b->keys, (size_t)n));
-  GI_TRY(scr.alloc(&b->sid, (size_t)n));
-  GI_TRY(scr.alloc(&b->sxy, (size_t)n));
+  GI_TRY(keep.alloc(&b->table, (size_t)cells));
+  GI_TRY(tmp.alloc(&b->keys, (size_t)n));
+  GI_TRY(keep.alloc(&b->sid, (size_t)n));
+  GI_TRY(keep.alloc(&b->sxy, (size_t)n));
   b->sval = nullptr;
-  if (data_in) GI_TRY(scr.alloc(&b->sval, (size_t)n));
+  if (want_values) GI_TRY(keep.alloc(&b->sval, (size_t)n));
   GI_CUDA(cudaMemsetAsync(b->table, 0, sizeof(int) * (size_t)cells, st));
   const PointsView<R> pv = points_n2(points, n, flags & GI_POINTS_ROWMAJOR);
   const int blocks = div_up(n, 256);
   esrg_key_count_kernel<R><<<blocks, 256, 0, st>>>(pv, n, x_axis, len_x, y_axis, len_y, spac, b->keys, b->table);
   GI_CUDA(cudaGetLastError());
-  GI_TRY(exclusive_scan_i32(scr, b->table, b->table, cells));
+  GI_TRY(exclusive_scan_i32(tmp, b->table, b->table, cells));
   esrg_scatter_kernel<<<blocks, 256, 0, st>>>(b->keys, n, b->table, b->sid);
   esrg_sort_cells_kernel<<<blocks, 256, 0, st>>>(b->keys, n, b->table, b->sid);
-  esrg_gather_kernel<R><<<blocks, 256, 0, st>>>(pv, data_in, b->sid, n, b->sxy, b->sval);
+  esrg_gather_kernel<R><<<blocks, 256, 0, st>>>(pv, data_in, b->sid, n, b->sxy, data_in ? b->sval : nullptr);
   GI_CUDA(cudaGetLastError());
   return GI_OK;
+}
+template <class R>
+int esrg_bin(Scratch& scr, const R* points, int n, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+             int len_y, R spac, int flags, Binned<R>* b) {
+  return esrg_bin<R>(scr, scr, points, n, data_in, x_axis, len_x, y_axis, len_y, spac, flags, data_in != nullptr, b);
 }
 
 // query + IDW for the targets rows [row0,row1) x columns [col0,col1); `out` (and nn_*) are window-shaped.
@@ -635,6 +640,44 @@ int esrg_device(const R* points, int num_points, const R* data_in, const R* x_ax
   return GI_OK;
 }
 
+namespace {
+// output bands computed on the compute stream and copied back on the copy stream (common.cuh)
+template <class R>
+int esrg_run_banded(HostPipe* pipe, Scratch& scr, const Binned<R>& bins, int num_points, const R* dx, int len_x,
+                    const R* dy, int len_y, R grid_spac, int k, int row_begin, int row_end, R* dout, R* data_ip,
+                    int flags, const StatusSlot& slot) {
+  cudaStream_t st = pipe->compute;
+  const int nrows = row_end - row_begin;
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  const int64_t lo = rowmajor ? row_begin : 0, hi = rowmajor ? row_end : len_x;
+  const int64_t line = rowmajor ? len_x : nrows;
+  const int nb = plan_bands(hi - lo, (int64_t)nrows * len_x * sizeof(R));
+  int64_t* counters;
+  GI_TRY(scr.alloc(&counters, (size_t)4 * nb));
+  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4 * nb, st));
+  for (int b = 0; b < nb; ++b) {
+    int64_t b0, b1;
+    band_range(lo, hi, nb, b, 4, &b0, &b1);
+    if (b0 >= b1) continue;
+    R* band_out = dout + (b0 - lo) * line;
+    if (rowmajor)
+      GI_TRY(esrg_query_window<R>(scr, bins, num_points, dx, len_x, dy, len_y, grid_spac, k, (int)b0, (int)b1, 0,
+                                  len_x, band_out, nullptr, nullptr, counters + 4 * b, false, flags, slot.dev,
+                                  nullptr));
+    else
+      GI_TRY(esrg_query_window<R>(scr, bins, num_points, dx, len_x, dy, len_y, grid_spac, k, row_begin, row_end,
+                                  (int)b0, (int)b1, band_out, nullptr, nullptr, counters + 4 * b, false, flags,
+                                  slot.dev, nullptr));
+    GI_CUDA(cudaEventRecord(pipe->computed[b], st));
+    GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
+    GI_TRY(to_host(pipe->copy_out, data_ip + (b0 - lo) * line, band_out, (size_t)((b1 - b0) * line)));
+  }
+  GI_TRY(flush_status(st, slot));
+  GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
+  return GI_OK;
+}
+}  // namespace
+
 // GI_HOST form without debug outputs: inputs in, points binned once, output bands computed and copied back in a
 // pipeline (common.cuh).
 template <class R>
@@ -663,34 +706,96 @@ int esrg_host(const R* points, int num_points, const R* data_in, const R* x_axis
   Binned<R> bins;
   GI_TRY(esrg_bin(scr, dp, num_points, dd, dx, len_x, dy, len_y, grid_spac, flags, &bins));
   ph.mark("esrg_query");
-  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
-  const int64_t lo = rowmajor ? row_begin : 0, hi = rowmajor ? row_end : len_x;
-  const int64_t line = rowmajor ? len_x : nrows;
-  const int nb = plan_bands(hi - lo, (int64_t)nrows * len_x * sizeof(R));
-  int64_t* counters;
-  GI_TRY(scr.alloc(&counters, (size_t)4 * nb));
-  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4 * nb, st));
-  for (int b = 0; b < nb; ++b) {
-    int64_t b0, b1;
-    band_range(lo, hi, nb, b, 4, &b0, &b1);
-    if (b0 >= b1) continue;
-    R* band_out = dout + (b0 - lo) * line;
-    if (rowmajor)
-      GI_TRY(esrg_query_window<R>(scr, bins, num_points, dx, len_x, dy, len_y, grid_spac, k, (int)b0, (int)b1, 0,
-                                  len_x, band_out, nullptr, nullptr, counters + 4 * b, false, flags, slot.dev,
-                                  nullptr));
-    else
-      GI_TRY(esrg_query_window<R>(scr, bins, num_points, dx, len_x, dy, len_y, grid_spac, k, row_begin, row_end,
-                                  (int)b0, (int)b1, band_out, nullptr, nullptr, counters + 4 * b, false, flags,
-                                  slot.dev, nullptr));
-    GI_CUDA(cudaEventRecord(pipe->computed[b], st));
-    GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
-    GI_TRY(to_host(pipe->copy_out, data_ip + (b0 - lo) * line, band_out, (size_t)((b1 - b0) * line)));
-  }
+  GI_TRY(esrg_run_banded<R>(pipe, scr, bins, num_points, dx, len_x, dy, len_y, grid_spac, k, row_begin, row_end, dout,
+                            data_ip, flags, slot));
   ph.finish();
-  GI_TRY(flush_status(st, slot));
-  GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
   return read_status(st, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: binned points + target grid resident on the device, one execute() per field of nodal values
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <class R> struct EsrgPlan : PlanBase {
+  Scratch keep{nullptr, true};
+  Binned<R> bins;
+  R *dx, *dy;
+  R spac;
+  int num_points, len_x, len_y, k, row_begin, row_end, flags;
+
+  int execute(const void* data_in_v, void* data_ip_v, int mem, cudaStream_t st_in) override {
+    const R* data_in = static_cast<const R*>(data_in_v);
+    R* data_ip = static_cast<R*>(data_ip_v);
+    if (row_begin == row_end) return GI_OK;
+    HostPipe* pipe = nullptr;
+    cudaStream_t st = st_in;
+    if (mem == GI_HOST) { GI_TRY(host_pipe(&pipe)); st = pipe->compute; }
+    StatusSlot slot;
+    GI_TRY(get_status_slot(st, &slot));
+    Scratch scr(st);
+    Phases ph(st);
+    const R* dd = data_in;
+    R* dout = data_ip;
+    if (mem == GI_HOST) {
+      ph.mark("h2d");
+      R* tmp;
+      GI_TRY(to_device(scr, data_in, (size_t)num_points, &tmp));
+      dd = tmp;
+      GI_TRY(scr.alloc(&dout, (size_t)(row_end - row_begin) * len_x));
+    }
+    ph.mark("esrg_values");
+    esrg_gather_kernel<R><<<div_up(num_points, 256), 256, 0, st>>>(PointsView<R>{nullptr, 0, 0}, dd, bins.sid,
+                                                                  num_points, nullptr, bins.sval);
+    GI_CUDA(cudaGetLastError());
+    ph.mark("esrg_query");
+    if (mem == GI_HOST) {
+      GI_TRY(esrg_run_banded<R>(pipe, scr, bins, num_points, dx, len_x, dy, len_y, spac, k, row_begin, row_end, dout,
+                                data_ip, flags, slot));
+      ph.finish();
+      return read_status(st, true);
+    }
+    int64_t* counters;
+    GI_TRY(scr.alloc(&counters, 4));
+    GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4, st));
+    GI_TRY(esrg_query_window<R>(scr, bins, num_points, dx, len_x, dy, len_y, spac, k, row_begin, row_end, 0, len_x,
+                                dout, nullptr, nullptr, counters, false, flags, slot.dev, nullptr));
+    ph.finish();
+    return flush_status(st, slot);
+  }
+};
+}  // namespace
+
+template <class R>
+int esrg_plan_create(const R* points, int num_points, const R* x_axis, int len_x, const R* y_axis, int len_y,
+                     R grid_spac, int k, int row_begin, int row_end, int flags, int mem, cudaStream_t st_in,
+                     PlanBase** out) {
+  GI_REQUIRE(k >= 1 && k <= 32, "num_neighbours must be in 1..32");
+  GI_REQUIRE(num_points >= k, "fewer points than num_neighbours");
+  GI_TRY(ensure_device());
+  cudaStream_t st = st_in;
+  if (mem == GI_HOST) { HostPipe* pipe; GI_TRY(host_pipe(&pipe)); st = pipe->compute; }
+  std::unique_ptr<EsrgPlan<R>> plan(new EsrgPlan<R>());
+  plan->real_bytes = sizeof(R);
+  GI_CUDA(cudaGetDevice(&plan->device));
+  plan->num_points = num_points; plan->len_x = len_x; plan->len_y = len_y; plan->k = k; plan->spac = grid_spac;
+  plan->row_begin = row_begin; plan->row_end = row_end; plan->flags = flags;
+  Scratch tmp(st);
+  const R* dp = points;
+  GI_TRY(plan->keep.alloc(&plan->dx, (size_t)len_x));
+  GI_TRY(plan->keep.alloc(&plan->dy, (size_t)len_y));
+  const cudaMemcpyKind kind = mem == GI_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  GI_CUDA(cudaMemcpyAsync(plan->dx, x_axis, sizeof(R) * (size_t)len_x, kind, st));
+  GI_CUDA(cudaMemcpyAsync(plan->dy, y_axis, sizeof(R) * (size_t)len_y, kind, st));
+  if (mem == GI_HOST) {
+    R* t;
+    GI_TRY(to_device(tmp, points, (size_t)2 * num_points, &t));
+    dp = t;
+  }
+  GI_TRY(esrg_bin<R>(plan->keep, tmp, dp, num_points, (const R*)nullptr, plan->dx, len_x, plan->dy, len_y, grid_spac,
+                     flags, true, &plan->bins));
+  GI_CUDA(cudaStreamSynchronize(st));  // the plan may be used from any stream afterwards
+  *out = plan.release();
+  return GI_OK;
 }
 
 template <class R>
@@ -711,7 +816,9 @@ int esrg_bin_device(const R* points, int num_points, const R* x_axis, int len_x,
                               R*, int64_t*, int, cudaStream_t);                                                  \
   template int esrg_bin_device<R>(const R*, int, const R*, int, const R*, int, R, int32_t*, int32_t*, int,        \
                                   cudaStream_t);                                                                  \
-  template int esrg_host<R>(const R*, int, const R*, const R*, int, const R*, int, R, int, int, int, R*, int);
+  template int esrg_host<R>(const R*, int, const R*, const R*, int, const R*, int, R, int, int, int, R*, int);  \
+  template int esrg_plan_create<R>(const R*, int, const R*, int, const R*, int, R, int, int, int, int, int,       \
+                                   cudaStream_t, PlanBase**);
 GI_INSTANTIATE(double)
 GI_INSTANTIATE(float)
 

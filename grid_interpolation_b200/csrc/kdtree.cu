@@ -23,6 +23,8 @@
 //           none could be inserted (insertion needs d2 < max d2, which only shrinks), so the neighbour
 //           list after the skipped visit is bit-identical to the reference's; it cuts node visits ~14x when
 //           the k-th d2 is > 1.  GI_KD_REFERENCE_VISITS turns it off (visit-count parity with the oracle).
+#include <memory>
+
 #include "kernels.cuh"
 #include "scan.cuh"
 #include "topk.cuh"
@@ -389,17 +391,24 @@ template <class R> struct KdTreeDev {
   int n;
 };
 template <class R>
-int kd_prepare(Scratch& scr, const R* points, int num_points, const R* data_in, int flags, KdTreeDev<R>* t) {
-  cudaStream_t st = scr.stream();
+int kd_prepare(Scratch& keep, Scratch& tmp, const R* points, int num_points, const R* data_in, int flags,
+               KdTreeDev<R>* t) {
+  cudaStream_t st = tmp.stream();
   const PointsView<R> pv = points_2n(points, num_points, flags & GI_POINTS_ROWMAJOR);
-  GI_TRY(kd_build<R>(scr, pv, num_points, &t->order));
-  GI_TRY(scr.alloc(&t->nodes, (size_t)num_points));
-  GI_TRY(scr.alloc(&t->nval, (size_t)num_points));
+  int* order_tmp;
+  GI_TRY(kd_build<R>(tmp, pv, num_points, &order_tmp));
+  GI_TRY(keep.alloc(&t->order, (size_t)num_points));
+  GI_CUDA(cudaMemcpyAsync(t->order, order_tmp, sizeof(int) * (size_t)num_points, cudaMemcpyDeviceToDevice, st));
+  GI_TRY(keep.alloc(&t->nodes, (size_t)num_points));
+  GI_TRY(keep.alloc(&t->nval, (size_t)num_points));
   t->n = num_points;
-  kd_gather_kernel<R><<<div_up(num_points, 256), 256, 0, st>>>(pv, data_in, t->order, num_points, t->nodes, t->nval,
-                                                               nullptr);
+  kd_gather_kernel<R><<<div_up(num_points, 256), 256, 0, st>>>(pv, data_in, t->order, num_points, t->nodes,
+                                                               data_in ? t->nval : nullptr, nullptr);
   GI_CUDA(cudaGetLastError());
   return GI_OK;
+}
+template <class R> int kd_prepare(Scratch& scr, const R* points, int n, const R* data_in, int flags, KdTreeDev<R>* t) {
+  return kd_prepare<R>(scr, scr, points, n, data_in, flags, t);
 }
 
 // query + IDW for the targets rows [row0,row1) x columns [col0,col1); `out` (and nn_*) are window-shaped
@@ -457,6 +466,40 @@ int kdtree_device(const R* points, int num_points, const R* data_in, const R* x_
   return GI_OK;
 }
 
+namespace {
+// output bands computed on the compute stream and copied back on the copy stream (common.cuh); dout is the
+// device twin of data_ip (host), both shaped (row_end-row_begin, len_x) in the layout `flags` selects
+template <class R>
+int kd_run_banded(HostPipe* pipe, const KdTreeDev<R>& tree, const R* dx, int len_x, const R* dy, int len_y, int k,
+                  int row_begin, int row_end, R* dout, R* data_ip, int flags, const StatusSlot& slot) {
+  cudaStream_t st = pipe->compute;
+  const int nrows = row_end - row_begin;
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  // bands along the axis that is NOT contiguous in memory: each band is one contiguous piece of the output
+  const int64_t lo = rowmajor ? row_begin : 0, hi = rowmajor ? row_end : len_x;
+  const int64_t line = rowmajor ? len_x : nrows;  // elements per unit of the banded axis
+  const int nb = plan_bands(hi - lo, (int64_t)nrows * len_x * sizeof(R));
+  for (int b = 0; b < nb; ++b) {
+    int64_t b0, b1;
+    band_range(lo, hi, nb, b, 4, &b0, &b1);
+    if (b0 >= b1) continue;
+    R* band_out = dout + (b0 - lo) * line;
+    if (rowmajor)
+      GI_TRY(kd_query_window<R>(tree, dx, len_x, dy, len_y, k, (int)b0, (int)b1, 0, len_x, band_out, nullptr, nullptr,
+                                nullptr, flags, slot.dev, st));
+    else
+      GI_TRY(kd_query_window<R>(tree, dx, len_x, dy, len_y, k, row_begin, row_end, (int)b0, (int)b1, band_out,
+                                nullptr, nullptr, nullptr, flags, slot.dev, st));
+    GI_CUDA(cudaEventRecord(pipe->computed[b], st));
+    GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
+    GI_TRY(to_host(pipe->copy_out, data_ip + (b0 - lo) * line, band_out, (size_t)((b1 - b0) * line)));
+  }
+  GI_TRY(flush_status(st, slot));
+  GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
+  return GI_OK;
+}
+}  // namespace
+
 // GI_HOST form without debug outputs: inputs in, tree built once, output bands computed and copied back in a
 // pipeline (common.cuh).  host pointers in, synchronous.
 template <class R>
@@ -484,30 +527,87 @@ int kdtree_host(const R* points, int num_points, const R* data_in, const R* x_ax
   KdTreeDev<R> tree;
   GI_TRY(kd_prepare<R>(scr, dp, num_points, dd, flags, &tree));
   ph.mark("kd_query");
-  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
-  // bands along the axis that is NOT contiguous in memory: each band is one contiguous piece of the output
-  const int64_t lo = rowmajor ? row_begin : 0, hi = rowmajor ? row_end : len_x;
-  const int64_t line = rowmajor ? len_x : nrows;  // elements per unit of the banded axis
-  const int nb = plan_bands(hi - lo, (int64_t)nrows * len_x * sizeof(R));
-  for (int b = 0; b < nb; ++b) {
-    int64_t b0, b1;
-    band_range(lo, hi, nb, b, 4, &b0, &b1);
-    if (b0 >= b1) continue;
-    R* band_out = dout + (b0 - lo) * line;
-    if (rowmajor)
-      GI_TRY(kd_query_window<R>(tree, dx, len_x, dy, len_y, k, (int)b0, (int)b1, 0, len_x, band_out, nullptr, nullptr,
-                                nullptr, flags, slot.dev, st));
-    else
-      GI_TRY(kd_query_window<R>(tree, dx, len_x, dy, len_y, k, row_begin, row_end, (int)b0, (int)b1, band_out,
-                                nullptr, nullptr, nullptr, flags, slot.dev, st));
-    GI_CUDA(cudaEventRecord(pipe->computed[b], st));
-    GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
-    GI_TRY(to_host(pipe->copy_out, data_ip + (b0 - lo) * line, band_out, (size_t)((b1 - b0) * line)));
-  }
+  GI_TRY(kd_run_banded<R>(pipe, tree, dx, len_x, dy, len_y, k, row_begin, row_end, dout, data_ip, flags, slot));
   ph.finish();
-  GI_TRY(flush_status(st, slot));
-  GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
   return read_status(st, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: tree + target grid resident on the device, one execute() per field of nodal values
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <class R> struct KdPlan : PlanBase {
+  Scratch keep{nullptr, true};
+  KdTreeDev<R> tree;
+  R *dx, *dy;
+  int len_x, len_y, k, row_begin, row_end, flags;
+
+  int execute(const void* data_in_v, void* data_ip_v, int mem, cudaStream_t st_in) override {
+    const R* data_in = static_cast<const R*>(data_in_v);
+    R* data_ip = static_cast<R*>(data_ip_v);
+    if (row_begin == row_end) return GI_OK;
+    HostPipe* pipe = nullptr;
+    cudaStream_t st = st_in;
+    if (mem == GI_HOST) { GI_TRY(host_pipe(&pipe)); st = pipe->compute; }
+    StatusSlot slot;
+    GI_TRY(get_status_slot(st, &slot));
+    Scratch scr(st);
+    Phases ph(st);
+    const R* dd = data_in;
+    R* dout = data_ip;
+    if (mem == GI_HOST) {
+      ph.mark("h2d");
+      R* tmp;
+      GI_TRY(to_device(scr, data_in, (size_t)tree.n, &tmp));
+      dd = tmp;
+      GI_TRY(scr.alloc(&dout, (size_t)(row_end - row_begin) * len_x));
+    }
+    ph.mark("kd_values");
+    kd_gather_kernel<R><<<div_up(tree.n, 256), 256, 0, st>>>(PointsView<R>{nullptr, 0, 0}, dd, tree.order, tree.n, nullptr,
+                                                            tree.nval, nullptr);
+    GI_CUDA(cudaGetLastError());
+    ph.mark("kd_query");
+    if (mem == GI_HOST) {
+      GI_TRY(kd_run_banded<R>(pipe, tree, dx, len_x, dy, len_y, k, row_begin, row_end, dout, data_ip, flags, slot));
+      ph.finish();
+      return read_status(st, true);
+    }
+    GI_TRY(kd_query_window<R>(tree, dx, len_x, dy, len_y, k, row_begin, row_end, 0, len_x, dout, nullptr, nullptr,
+                              nullptr, flags, slot.dev, st));
+    ph.finish();
+    return flush_status(st, slot);
+  }
+};
+}  // namespace
+
+template <class R>
+int kdtree_plan_create(const R* points, int num_points, const R* x_axis, int len_x, const R* y_axis, int len_y, int k,
+                       int row_begin, int row_end, int flags, int mem, cudaStream_t st_in, PlanBase** out) {
+  GI_REQUIRE(k >= 1 && k <= 32, "num_neighbours must be in 1..32");
+  GI_TRY(ensure_device());
+  cudaStream_t st = st_in;
+  if (mem == GI_HOST) { HostPipe* pipe; GI_TRY(host_pipe(&pipe)); st = pipe->compute; }
+  std::unique_ptr<KdPlan<R>> plan(new KdPlan<R>());
+  plan->real_bytes = sizeof(R);
+  GI_CUDA(cudaGetDevice(&plan->device));
+  plan->len_x = len_x; plan->len_y = len_y; plan->k = k; plan->row_begin = row_begin; plan->row_end = row_end;
+  plan->flags = flags;
+  Scratch tmp(st);
+  const R* dp = points;
+  GI_TRY(plan->keep.alloc(&plan->dx, (size_t)len_x));
+  GI_TRY(plan->keep.alloc(&plan->dy, (size_t)len_y));
+  const cudaMemcpyKind kind = mem == GI_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  GI_CUDA(cudaMemcpyAsync(plan->dx, x_axis, sizeof(R) * (size_t)len_x, kind, st));
+  GI_CUDA(cudaMemcpyAsync(plan->dy, y_axis, sizeof(R) * (size_t)len_y, kind, st));
+  if (mem == GI_HOST) {
+    R* t;
+    GI_TRY(to_device(tmp, points, (size_t)2 * num_points, &t));
+    dp = t;
+  }
+  GI_TRY(kd_prepare<R>(plan->keep, tmp, dp, num_points, (const R*)nullptr, flags, &plan->tree));
+  GI_CUDA(cudaStreamSynchronize(st));  // the plan may be used from any stream afterwards
+  *out = plan.release();
+  return GI_OK;
 }
 
 template <class R>
@@ -527,7 +627,9 @@ int kd_build_device(const R* points, int num_points, int32_t* order_out, int fla
   template int kdtree_device<R>(const R*, int, const R*, const R*, int, const R*, int, int, int, int, R*, int32_t*, \
                                 R*, int64_t*, int, cudaStream_t);                                               \
   template int kd_build_device<R>(const R*, int, int32_t*, int, cudaStream_t);                                  \
-  template int kdtree_host<R>(const R*, int, const R*, const R*, int, const R*, int, int, int, int, R*, int);
+  template int kdtree_host<R>(const R*, int, const R*, const R*, int, const R*, int, int, int, int, R*, int);    \
+  template int kdtree_plan_create<R>(const R*, int, const R*, int, const R*, int, int, int, int, int, int,       \
+                                     cudaStream_t, PlanBase**);
 GI_INSTANTIATE(double)
 GI_INSTANTIATE(float)
 

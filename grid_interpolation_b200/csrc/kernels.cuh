@@ -55,4 +55,17 @@ template <class R>
 int esrg_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
               int len_y, R grid_spac, int k, int row_begin, int row_end, R* data_ip, int flags);
 
+// plans (gi_plan): geometry + target grid prepared once, execute() per field of nodal values
+template <class R>
+int barycentric_plan_create(const R* points, int num_points, const R* x_axis, int len_x, const R* y_axis, int len_y,
+                            const int32_t* simplices, const int32_t* neighbours, int num_tri, int row_begin,
+                            int row_end, int halo, int flags, int mem, cudaStream_t st, PlanBase** out);
+template <class R>
+int kdtree_plan_create(const R* points, int num_points, const R* x_axis, int len_x, const R* y_axis, int len_y, int k,
+                       int row_begin, int row_end, int flags, int mem, cudaStream_t st, PlanBase** out);
+template <class R>
+int esrg_plan_create(const R* points, int num_points, const R* x_axis, int len_x, const R* y_axis, int len_y,
+                     R grid_spac, int k, int row_begin, int row_end, int flags, int mem, cudaStream_t st,
+                     PlanBase** out);
+
 }  // namespace gi

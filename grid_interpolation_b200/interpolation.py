@@ -36,7 +36,7 @@ from ._lib import (GI_DEVICE, GI_FIELD_ROWMAJOR, GI_HOST, GI_KD_REFERENCE_VISITS
 __all__ = ["bilinear", "idw_kdtree", "idw_esrg_nearest", "barycentric_interpolation",
            "barycentric_interpolation_ex", "idw_kdtree_ex", "idw_esrg_nearest_ex", "kd_build",
            "assign_points_to_cells", "fill_nearest_neighbour", "pinned_empty", "pinned_copy",
-           "set_profiling", "set_pipeline_band_bytes", "last_timings"]
+           "set_profiling", "set_pipeline_band_bytes", "last_timings", "BarycentricPlan", "KdTreePlan", "EsrgPlan"]
 
 _F64 = np.dtype(np.float64)
 
@@ -430,6 +430,128 @@ def barycentric_interpolation(points, data_in, x_axis, y_axis, simplices, neighb
     (interpolation.f90:298-416).  simplices / neighbours (num_triangles, 3) are 1-based, neighbour 0 = none
     (test_interpolation.py:199-201).  Returns data_ip (len_y, len_x)."""
     return barycentric_interpolation_ex(points, data_in, x_axis, y_axis, simplices, neighbours, **kw)
+
+
+# -------------------------------------------------------------------------------------------------
+# plans: geometry + target grid prepared once on the device, one call per field of nodal values
+# -------------------------------------------------------------------------------------------------
+class _Plan:
+    """Base of the three plan classes (gi_plan of gridinterp.h).  ``plan(data_in)`` returns data_ip with the
+    shape / memory order fixed at creation; numpy in -> numpy out (pinned), torch CUDA tensor in -> torch out on
+    the current stream.  Results are identical to the one-shot call on the same inputs."""
+
+    def __init__(self):
+        self._handle = C.c_void_p()
+        self._suf = "f64"
+        self._rt = _F64
+        self._n = 0
+        self._shape = (0, 0)
+        self._order = "F"
+
+    def _create(self, name, call, args):
+        _require_device()
+        st = getattr(lib(), name + "_" + self._suf)(*args, call.mem, call.stream, C.byref(self._handle))
+        check(st, name)
+
+    def __call__(self, data_in, *, out=None, sync=True):
+        if not self._handle:
+            raise RuntimeError("plan has been closed")
+        with _Call(data_in) as c:
+            d = c.arg(data_in, self._rt, 1, "data_in")
+            if d.shape != (self._n,):
+                raise ValueError(f"data_in must have shape (num_points,) = ({self._n},), got {d.shape}")
+            res, res_ptr, rowmajor = _use_out(c, out, self._shape, self._rt, self._order)
+            if rowmajor != (self._order == "C") and min(self._shape) > 1:
+                raise ValueError(f"out must be {self._order}-contiguous (the plan's layout)")
+            st = getattr(lib(), "gi_plan_execute_" + self._suf)(self._handle, d.ptr, res_ptr, c.mem, c.stream)
+            c.finish(st, type(self).__name__, sync)
+            return res
+
+    def close(self):
+        if self._handle:
+            lib().gi_plan_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _plan_geometry(plan, c, points, x_axis, y_axis, points_shape, rows, order, dtype):
+    plan._rt, plan._suf = _real(dtype)
+    x = c.arg(x_axis, plan._rt, 1, "x_axis"); y = c.arg(y_axis, plan._rt, 1, "y_axis")
+    p = c.arg(points, plan._rt, 2, "points")
+    if points_shape == "n2":
+        if p.shape[1] != 2:
+            raise ValueError(f"points must have shape (num_points, 2), got {p.shape}")
+        plan._n = p.shape[0]
+    else:
+        if p.shape[0] != 2:
+            raise ValueError(f"points must have shape (2, num_points), got {p.shape}")
+        plan._n = p.shape[1]
+    if order not in ("C", "F"):
+        raise ValueError("order must be 'C' or 'F'")
+    r0, r1 = _band(rows, y.shape[0])
+    plan._shape, plan._order = (r1 - r0, x.shape[0]), order
+    flags = (GI_FIELD_ROWMAJOR if order == "C" else 0) | (GI_POINTS_ROWMAJOR if p.rowmajor else 0)
+    return x, y, p, r0, r1, flags
+
+
+class BarycentricPlan(_Plan):
+    """barycentric_interpolation with the mesh packed once: ``plan = BarycentricPlan(points, x_axis, y_axis,
+    simplices, neighbours); field = plan(data_in)``."""
+
+    def __init__(self, points, x_axis, y_axis, simplices, neighbours, *, rows=None, halo=0, order="F",
+                 dtype=np.float64):
+        super().__init__()
+        with _Call(points) as c:
+            x, y, p, r0, r1, flags = _plan_geometry(self, c, points, x_axis, y_axis, "n2", rows, order, dtype)
+            s = c.arg(simplices, np.dtype(np.int32), 2, "simplices")
+            nb = c.arg(neighbours, np.dtype(np.int32), 2, "neighbours")
+            t = s.shape[0]
+            if s.shape != (t, 3) or nb.shape != (t, 3):
+                raise ValueError("simplices and neighbours must both have shape (num_triangles, 3)")
+            if s.rowmajor != nb.rowmajor:
+                nb = c.arg(_reorder(nb.keep, s.rowmajor), np.dtype(np.int32), 2, "neighbours")
+            flags |= GI_TOPO_ROWMAJOR if s.rowmajor else 0
+            self._create("gi_barycentric_plan_create", c,
+                         (p.ptr, self._n, x.ptr, x.shape[0], y.ptr, y.shape[0], s.ptr, nb.ptr, t, r0, r1, int(halo), flags))
+
+
+class KdTreePlan(_Plan):
+    """idw_kdtree with the tree built once: ``plan = KdTreePlan(points, x_axis, y_axis, num_neighbours)``
+    (points (2, num_points) as in idw_kdtree)."""
+
+    def __init__(self, points, x_axis, y_axis, num_neighbours, *, rows=None, order="F", exact_prune=False,
+                 dtype=np.float64):
+        super().__init__()
+        with _Call(points) as c:
+            x, y, p, r0, r1, flags = _plan_geometry(self, c, points, x_axis, y_axis, "2n", rows, order, dtype)
+            flags |= _lib.GI_KD_EXACT_PRUNE if exact_prune else 0
+            self._create("gi_idw_kdtree_plan_create", c,
+                         (p.ptr, self._n, x.ptr, x.shape[0], y.ptr, y.shape[0], int(num_neighbours), r0, r1, flags))
+
+
+class EsrgPlan(_Plan):
+    """idw_esrg_nearest with the points binned once: ``plan = EsrgPlan(points, x_axis, y_axis, grid_spac,
+    num_neighbours)``."""
+
+    def __init__(self, points, x_axis, y_axis, grid_spac, num_neighbours, *, rows=None, order="F", dtype=np.float64):
+        super().__init__()
+        with _Call(points) as c:
+            x, y, p, r0, r1, flags = _plan_geometry(self, c, points, x_axis, y_axis, "n2", rows, order, dtype)
+            self._create("gi_idw_esrg_plan_create", c,
+                         (p.ptr, self._n, x.ptr, x.shape[0], y.ptr, y.shape[0], float(grid_spac), int(num_neighbours),
+                          r0, r1, flags))
 
 
 # -------------------------------------------------------------------------------------------------

@@ -175,6 +175,31 @@ int gi_idw_esrg_nearest_ex_f64(const double* points, int num_points, const doubl
                                double* data_ip, int32_t* nn_index, double* nn_dist2, int64_t* counters,
                                int flags, int mem, void* stream);
 
+/* ---- plans: geometry prepared once, many fields ------------------------------------------------- */
+
+/* The reference rebuilds its search structure in every call (interpolation.f90:139,235-239; the start-triangle
+ * search :342-355).  A plan keeps what depends on the geometry only -- the packed triangle records + seed grid,
+ * the k-d tree, or the cell list -- together with the target grid (axes, row band, layout flags) on the device;
+ * gi_plan_execute_* then interpolates one field of nodal values `data_in` (num_points) into `data_ip`
+ * (row_end-row_begin, len_x), with results identical to the one-shot call on the same inputs.
+ * `mem` / `stream` of create describe points / axes / topology, those of execute describe data_in / data_ip
+ * (a GI_HOST execute pipelines its copies like the one-shot calls).  A plan belongs to the device that was
+ * current at creation and serves one execute at a time.  Extension: no counterpart in the
+ * reference's f2py module. */
+typedef struct gi_plan gi_plan;
+int gi_barycentric_plan_create_f64(const double* points, int num_points, const double* x_axis, int len_x,
+                                   const double* y_axis, int len_y, const int32_t* simplices,
+                                   const int32_t* neighbours, int num_triangles, int row_begin, int row_end,
+                                   int halo, int flags, int mem, void* stream, gi_plan** plan);
+int gi_idw_kdtree_plan_create_f64(const double* points, int num_points, const double* x_axis, int len_x,
+                                  const double* y_axis, int len_y, int num_neighbours, int row_begin,
+                                  int row_end, int flags, int mem, void* stream, gi_plan** plan);
+int gi_idw_esrg_plan_create_f64(const double* points, int num_points, const double* x_axis, int len_x,
+                                const double* y_axis, int len_y, double grid_spac, int num_neighbours,
+                                int row_begin, int row_end, int flags, int mem, void* stream, gi_plan** plan);
+int gi_plan_execute_f64(gi_plan* plan, const double* data_in, double* data_ip, int mem, void* stream);
+void gi_plan_destroy(gi_plan* plan);
+
 /* ---- parity / debug exports for the search structures ----------------------------------------- */
 
 /* kd_tree.f90:30-95: the canonical balanced tree (node = rank (n+1)/2 element along axis depth mod 2)
@@ -220,6 +245,17 @@ int gi_idw_esrg_nearest_ex_f32(const float* points, int num_points, const float*
                                int len_x, const float* y_axis, int len_y, float grid_spac, int num_neighbours,
                                int row_begin, int row_end, float* data_ip, int32_t* nn_index, float* nn_dist2,
                                int64_t* counters, int flags, int mem, void* stream);
+int gi_barycentric_plan_create_f32(const float* points, int num_points, const float* x_axis, int len_x,
+                                   const float* y_axis, int len_y, const int32_t* simplices,
+                                   const int32_t* neighbours, int num_triangles, int row_begin, int row_end,
+                                   int halo, int flags, int mem, void* stream, gi_plan** plan);
+int gi_idw_kdtree_plan_create_f32(const float* points, int num_points, const float* x_axis, int len_x,
+                                  const float* y_axis, int len_y, int num_neighbours, int row_begin, int row_end,
+                                  int flags, int mem, void* stream, gi_plan** plan);
+int gi_idw_esrg_plan_create_f32(const float* points, int num_points, const float* x_axis, int len_x,
+                                const float* y_axis, int len_y, float grid_spac, int num_neighbours, int row_begin,
+                                int row_end, int flags, int mem, void* stream, gi_plan** plan);
+int gi_plan_execute_f32(gi_plan* plan, const float* data_in, float* data_ip, int mem, void* stream);
 int gi_kd_build_f32(const float* points, int num_points, int32_t* order, int flags, int mem, void* stream);
 int gi_esrg_assign_points_to_cells_f32(const float* points, int num_points, const float* x_axis, int len_x,
                                        const float* y_axis, int len_y, float grid_spac, int32_t* index_of_pts,
