@@ -221,9 +221,9 @@ static int barycentric_api(const R* points, int num_points, const R* data_in, co
     return barycentric_device<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
                                  num_tri, row_begin, row_end, halo, data_ip, tri_out, mask_out, fill_src,
                                  counters, flags, (cudaStream_t)stream);
-  if (row_begin == 0 && row_end == len_y && !tri_out && !mask_out && !fill_src && !counters)
+  if (!tri_out && !mask_out && !fill_src && !counters)
     return barycentric_host<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
-                               num_tri, data_ip, flags);
+                               num_tri, row_begin, row_end, halo, data_ip, flags);
   GI_TRY(ensure_device());
   cudaStream_t st;
   GI_TRY(host_stream(&st));

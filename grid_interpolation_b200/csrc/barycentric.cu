@@ -820,21 +820,28 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
 }
 
 namespace {
-// Whole grid, mesh already packed: the grid is cut into bands along the axis that is not contiguous in memory;
-// band b is located / evaluated, then band b-1 is hull-filled (its fill may look into bands b-2 .. b, all walked
-// by then) and copied back on a second stream while band b+1 is being walked.  Nothing is computed twice.  A
-// fill that would have to look further than one band away (GI_ERR_HALO) makes the run start over with a single
-// band.  dout is the device twin of data_ip (host), both (len_y, len_x) in the layout `flags` selects.
-// Returns the status of the run (synchronous).
+// Row band [row_begin,row_end) (+ `halo` rows walked on each side) on a packed mesh: the walked window is cut
+// into sub-bands along the axis that is not contiguous in memory; sub-band b is located / evaluated, then
+// sub-band b-1 is hull-filled (its fill may look into sub-bands b-2 .. b, all walked by then) and copied back on
+// a second stream while sub-band b+1 is being walked.  Nothing is computed twice.  A fill that would have to
+// look further than one sub-band away (GI_ERR_HALO) makes the run start over with a single band (where
+// GI_ERR_HALO then means what it says: the caller's halo is too small).  dout is the device twin of data_ip
+// (host), both (row_end-row_begin, len_x) in the layout `flags` selects.  Returns the status (synchronous).
 template <class R>
 int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const R* dx, int len_x, const R* dy,
-                    int len_y, int num_points, R* dout, R* data_ip, int flags, const StatusSlot& slot) {
+                    int len_y, int num_points, int row_begin, int row_end, int halo, R* dout, R* data_ip, int flags,
+                    const StatusSlot& slot) {
   cudaStream_t st = pipe->compute;
   const int num_tri = pm.num_tri;
   const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
-  const int nfast = rowmajor ? len_x : len_y, nslow = rowmajor ? len_y : len_x;
+  const int e0 = max(0, row_begin - halo), e1 = min(len_y, row_end + halo);
+  // walked window E and written band B in (fast, slow) coordinates
+  const int ef0 = rowmajor ? 0 : e0, ef1 = rowmajor ? len_x : e1, es0 = rowmajor ? e0 : 0, es1 = rowmajor ? e1 : len_x;
+  const int bf0 = rowmajor ? 0 : row_begin, bf1 = rowmajor ? len_x : row_end;
+  const int bs0 = rowmajor ? row_begin : 0, bs1 = rowmajor ? row_end : len_x;
+  const int nfast = ef1 - ef0, nslow = es1 - es0, bnf = bf1 - bf0;
   const int wpr = (nfast + 31) >> 5;
-  GI_REQUIRE((int64_t)wpr * nslow < (int64_t)0x7fffffff, "grid too large");
+  GI_REQUIRE((int64_t)wpr * nslow < (int64_t)0x7fffffff, "window too large");
   uint32_t* mask_words; int* nz_words; int64_t* counters; int* amb_list;
   GI_TRY(scr.alloc(&mask_words, (size_t)wpr * nslow));
   GI_TRY(scr.alloc(&nz_words, (size_t)wpr * nslow));
@@ -842,47 +849,53 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
   const int amb_cap = (int)std::min<int64_t>((int64_t)nfast * nslow, (int64_t)1 << 22);
   GI_TRY(scr.alloc(&amb_list, (size_t)amb_cap));  // shared by the bands: band b's fix-up runs before band b+1's walk
 
-  int nb = plan_bands(nslow, (int64_t)len_x * len_y * sizeof(R));
+  int nb = plan_bands(nslow, (int64_t)(row_end - row_begin) * len_x * sizeof(R));
   for (;;) {
     GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 8 * kMaxBands, st));
-    int64_t start[kMaxBands + 1];
+    int64_t start[kMaxBands + 1];  // sub-band b = slow indices [start[b], start[b+1])
     for (int b = 0; b < nb; ++b) {
       int64_t e;
-      band_range(0, nslow, nb, b, 32, &start[b], &e);
+      band_range(es0, es1, nb, b, 32, &start[b], &e);
       start[b + 1] = e;
     }
     auto window = [&](int64_t s0, int64_t s1) {
-      return rowmajor ? TargetWindow<R>{dx, dy, len_x, len_y, 0, len_x, (int)s0, (int)s1, 0}
-                      : TargetWindow<R>{dy, dx, len_y, len_x, 0, len_y, (int)s0, (int)s1, 1};
+      return rowmajor ? TargetWindow<R>{dx, dy, len_x, len_y, ef0, ef1, (int)s0, (int)s1, 0}
+                      : TargetWindow<R>{dy, dx, len_y, len_x, ef0, ef1, (int)s0, (int)s1, 1};
     };
+    // the part of sub-band b that belongs to the band (empty for pure halo pieces)
+    auto band_lo = [&](int b) { return (int)std::min<int64_t>(std::max<int64_t>(start[b], bs0), bs1); };
+    auto band_hi = [&](int b) { return (int)std::max<int64_t>(std::min<int64_t>(start[b + 1], bs1), band_lo(b)); };
     WalkArgs<R> was[kMaxBands];
     auto fill_band = [&](int b) -> int {
-      const int64_t e0 = start[b > 0 ? b - 1 : 0], e1 = start[b + 1 < nb ? b + 2 : nb];
+      const int lo = band_lo(b), hi = band_hi(b);
+      if (lo >= hi) return GI_OK;
+      const int64_t f0 = start[b > 0 ? b - 1 : 0], f1 = start[b + 1 < nb ? b + 2 : nb];
       FillArgs<R> fa;
-      fa.win = window(e0, e1);
-      fa.mask_words = mask_words + e0 * wpr;
-      fa.nz_words = nz_words + start[b] * wpr;
-      fa.nz_shift = (start[b] - e0) * wpr;
-      fa.bf0 = 0; fa.bf1 = nfast; fa.bs0 = (int)start[b]; fa.bs1 = (int)start[b + 1];
-      fa.vf0 = 0; fa.vf1 = nfast; fa.vs0 = 0; fa.vs1 = (int)e1;  // everything walked so far holds final values
+      fa.win = window(f0, f1);
+      fa.mask_words = mask_words + (f0 - es0) * wpr;
+      fa.nz_words = nz_words + (start[b] - es0) * wpr;
+      fa.nz_shift = (start[b] - f0) * wpr;
+      fa.bf0 = bf0; fa.bf1 = bf1; fa.bs0 = lo; fa.bs1 = hi;
+      // every band cell walked so far holds its final value
+      fa.vf0 = bf0; fa.vf1 = bf1; fa.vs0 = bs0; fa.vs1 = (int)std::max<int64_t>(std::min<int64_t>(f1, bs1), bs0);
       fa.out = dout; fa.fill_src = nullptr; fa.counters = counters + 8 * b;
       fill_from_walk(fa, was[b], pm, len_x, len_y);
       fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
       GI_CUDA(cudaGetLastError());
       GI_CUDA(cudaEventRecord(pipe->computed[b], st));
       GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
-      const int64_t o = start[b] * nfast, cnt = (start[b + 1] - start[b]) * nfast;
+      const int64_t o = (int64_t)(lo - bs0) * bnf, cnt = (int64_t)(hi - lo) * bnf;
       return to_host(pipe->copy_out, data_ip + o, dout + o, (size_t)cnt);
     };
     for (int b = 0; b < nb; ++b) {
       if (start[b] < start[b + 1]) {
         WalkArgs<R>& wa = was[b];
         wa.win = window(start[b], start[b + 1]);
-        wa.bf0 = 0; wa.bf1 = nfast; wa.bs0 = (int)start[b]; wa.bs1 = (int)start[b + 1];
+        wa.bf0 = bf0; wa.bf1 = bf1; wa.bs0 = band_lo(b); wa.bs1 = band_hi(b);
         wa.geom = pm.geom; wa.seed = pm.seed; wa.ncx = pm.ncx; wa.ncy = pm.ncy; wa.num_tri = num_tri;
         wa.iter_cap = num_tri + 16;
-        wa.out = dout + start[b] * nfast; wa.tri_out = nullptr;
-        wa.mask_words = mask_words + start[b] * wpr; wa.nz_words = nz_words + start[b] * wpr;
+        wa.out = dout + (int64_t)(wa.bs0 - bs0) * bnf; wa.tri_out = nullptr;
+        wa.mask_words = mask_words + (start[b] - es0) * wpr; wa.nz_words = nz_words + (start[b] - es0) * wpr;
         wa.counters = counters + 8 * b;
         wa.amb_list = amb_list; wa.amb_cap = amb_cap;
         wa.status = slot.dev;
@@ -903,14 +916,16 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
 }
 }  // namespace
 
-// GI_HOST form of the whole-grid call without debug outputs: inputs in, mesh packed once, banded run.
+// GI_HOST form without debug outputs: inputs in, mesh packed once, banded run.
 template <class R>
 int barycentric_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
-                     int len_y, const int32_t* simplices, const int32_t* neighbours, int num_tri, R* data_ip,
-                     int flags) {
+                     int len_y, const int32_t* simplices, const int32_t* neighbours, int num_tri, int row_begin,
+                     int row_end, int halo, R* data_ip, int flags) {
   GI_REQUIRE(num_points >= 3 && num_tri >= 1, "need at least 3 points and 1 triangle");
   GI_REQUIRE(len_x >= 1 && len_y >= 1, "empty axis");
+  GI_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= len_y && halo >= 0, "bad row band");
   GI_TRY(ensure_device());
+  if (row_begin == row_end) return GI_OK;
   HostPipe* pipe;
   GI_TRY(host_pipe(&pipe));
   cudaStream_t st = pipe->compute;
@@ -927,12 +942,13 @@ int barycentric_host(const R* points, int num_points, const R* data_in, const R*
   GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
   GI_TRY(to_device(scr, simplices, (size_t)3 * num_tri, &ds));
   GI_TRY(to_device(scr, neighbours, (size_t)3 * num_tri, &dn));
-  GI_TRY(scr.alloc(&dout, (size_t)len_x * len_y));
+  GI_TRY(scr.alloc(&dout, (size_t)len_x * (row_end - row_begin)));
   ph.mark("pack_mesh");
   PackedMesh<R> pm;
   GI_TRY(bary_pack<R>(scr, dp, num_points, dd, dx, len_x, dy, len_y, ds, dn, num_tri, flags, slot.dev, &pm));
   ph.mark("walk");
-  const int status = bary_run_banded<R>(pipe, scr, pm, dx, len_x, dy, len_y, num_points, dout, data_ip, flags, slot);
+  const int status = bary_run_banded<R>(pipe, scr, pm, dx, len_x, dy, len_y, num_points, row_begin, row_end, halo,
+                                        dout, data_ip, flags, slot);
   ph.finish();
   return status;
 }
@@ -974,20 +990,16 @@ template <class R> struct BaryPlan : PlanBase {
                                                                   num_points, pm.num_tri, pm.geom);
     GI_CUDA(cudaGetLastError());
     ph.mark("walk");
-    if (mem == GI_HOST && row_begin == 0 && row_end == len_y) {
-      const int status = bary_run_banded<R>(pipe, scr, pm, dx, len_x, dy, len_y, num_points, dout, data_ip, flags, slot);
+    if (mem == GI_HOST) {
+      const int status = bary_run_banded<R>(pipe, scr, pm, dx, len_x, dy, len_y, num_points, row_begin, row_end, halo,
+                                            dout, data_ip, flags, slot);
       ph.finish();
       return status;
     }
     GI_TRY(bary_run_window<R>(scr, pm, dx, len_x, dy, len_y, num_points, row_begin, row_end, halo, dout, nullptr,
                               nullptr, nullptr, nullptr, flags, slot, st, &ph));
     ph.finish();
-    GI_TRY(flush_status(st, slot));
-    if (mem == GI_HOST) {
-      GI_TRY(to_host(st, data_ip, dout, band));
-      return read_status(st, true);
-    }
-    return GI_OK;
+    return flush_status(st, slot);
   }
 };
 }  // namespace
@@ -1079,7 +1091,7 @@ int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* 
                                      int64_t*, int, cudaStream_t);                                          \
   template int fill_device<R>(const uint8_t*, int, int, R*, int64_t*, int, cudaStream_t);                   \
   template int barycentric_host<R>(const R*, int, const R*, const R*, int, const R*, int, const int32_t*,   \
-                                   const int32_t*, int, R*, int);                                           \
+                                   const int32_t*, int, int, int, int, R*, int);                            \
   template int barycentric_plan_create<R>(const R*, int, const R*, int, const R*, int, const int32_t*,      \
                                           const int32_t*, int, int, int, int, int, int, cudaStream_t,       \
                                           PlanBase**);

@@ -49,8 +49,8 @@ int bilinear_host(const R* x_axis, int len_x, const R* y_axis, int len_y, const 
                   int64_t num_points, R* data_ip, int flags);
 template <class R>
 int barycentric_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
-                     int len_y, const int32_t* simplices, const int32_t* neighbours, int num_tri, R* data_ip,
-                     int flags);
+                     int len_y, const int32_t* simplices, const int32_t* neighbours, int num_tri, int row_begin,
+                     int row_end, int halo, R* data_ip, int flags);
 template <class R>
 int esrg_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
               int len_y, R grid_spac, int k, int row_begin, int row_end, R* data_ip, int flags);

@@ -43,6 +43,19 @@ def test_row_band_calls_are_banded_too(c1, tiny_bands):
          orc.idw_kdtree(c1.points.T, c1.data_pts, c1.x_axis, c1.y_axis, 8)[rows[0]:rows[1]])
 
 
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_barycentric_row_band_with_halo_is_banded_too(c1, tiny_bands, order):
+    """multi-GPU style call (row band + halo rows) through the host path: sub-bands include pure halo pieces"""
+    want = orc.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices, c1.neighbours)
+    for rows, halo in (((0, 40), 8), ((33, 79), 8), ((20, 45), 40)):
+        got = ip.barycentric_interpolation_ex(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                              c1.neighbours, rows=rows, halo=halo, order=order)
+        same(got, want[rows[0]:rows[1]])
+    with pytest.raises(RuntimeError, match="halo"):      # a halo that is too small is still reported
+        ip.barycentric_interpolation_ex(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices, c1.neighbours,
+                                        rows=(0, 2), halo=0, order=order)
+
+
 def test_fill_deeper_than_a_band_restarts_with_one_band(tiny_bands):
     """A hull fill that has to look further than the neighbouring band (GI_ERR_HALO inside) must not leak out:
     the call starts over with a single band and returns the oracle's field."""
