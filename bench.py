@@ -260,6 +260,28 @@ def main():
     phase_ms = {k: float(np.mean(v)) for k, v in agg.items()}
     walk_ms = phase_ms.get("walk")
 
+    # ------------------------------------------------------------------ steady state with a plan (extension)
+    plan = ip.BarycentricPlan(d_pts, d_x, d_y, d_simp, d_nbr, rows=band, halo=halo, order="C")
+    p_out = torch.empty_like(d_out)
+    for _ in range(3):
+        plan(d_val, out=p_out, sync=False)
+    sync_all()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(args.steps):
+        plan(d_val, out=p_out, sync=False)
+    pe1.record()
+    sync_all()
+    pms = torch.tensor([pe0.elapsed_time(pe1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pms, op=dist.ReduceOp.MAX)
+    assert torch.equal(p_out, d_out), "plan result differs from the one-shot result"
+    plan_line = {"ms_per_step": float(pms.item()) / args.steps,
+                 "value": targets_rank * world * args.steps / (float(pms.item()) * 1e-3), "unit": "targets/s",
+                 "note": "mesh packed once (BarycentricPlan), one execute per step; not the headline"}
+    plan.close()
+    del p_out
+
     # ------------------------------------------------------------------ e2e: host buffers through the public API
     e2e = None
     if not args.no_e2e:
@@ -284,7 +306,8 @@ def main():
         h2d = sum(a.nbytes for a in (h_pts, h_val, h_x, h_y, h_simp, h_nbr))
         e2e = {"value": targets_rank * world * e_steps / float(dt.item()), "unit": "targets/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_out.nbytes), "steps": e_steps,
-               "note": "per rank; pinned host buffers; H2D + pack + walk + fill + D2H inside the timed region"}
+               "note": "pinned host buffers; H2D + pack + walk + fill + D2H inside the timed region; the call "
+                       "copies output bands back while the next band is computed"}
         # the host path must agree with the device path bit for bit
         assert np.array_equal(h_out, d_out.cpu().numpy()), "host-path result differs from device-path result"
 
@@ -325,7 +348,7 @@ def main():
                    "l2": "inputs (0.36 GB) and output (2.1 GB) per step exceed the 126 MB L2; no explicit flush",
                    "layout": "numpy C-order inputs and output, consumed in place (no transposition)",
                    "scale": args.scale},
-        "phase_ms": phase_ms, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk,
+        "phase_ms": phase_ms, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "plan": plan_line, "clocks": clk,
         "gpu_launches": KERNELS_PER_STEP["c4"] * args.steps,
     }
     print(json.dumps(out))
