@@ -119,9 +119,9 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
     n1 = n2 = n3 = 0;
   }
   TriGeom<R> g;
-  g.x1 = pts.x(a - 1); g.y1 = pts.y(a - 1);
-  g.x2 = pts.x(b - 1); g.y2 = pts.y(b - 1);
-  g.x3 = pts.x(c - 1); g.y3 = pts.y(c - 1);
+  pts.xy(a - 1, g.x1, g.y1);
+  pts.xy(b - 1, g.x2, g.y2);
+  pts.xy(c - 1, g.x3, g.y3);
   g.n1 = n1 - 1; g.n2 = n2 - 1; g.n3 = n3 - 1;
   g.pad = 0;
   g.d1 = __ldg(data + (a - 1)); g.d2 = __ldg(data + (b - 1)); g.d3 = __ldg(data + (c - 1));

@@ -66,6 +66,20 @@ template <class R> struct PointsView {  // x(i) = base[i*stride], y(i) = base[i*
   int64_t stride, yoff;
   __device__ __forceinline__ R x(int64_t i) const { return __ldg(base + i * stride); }
   __device__ __forceinline__ R y(int64_t i) const { return __ldg(base + i * stride + yoff); }
+  // both coordinates of one point: a single 2*sizeof(R) load when the layout is interleaved (and aligned)
+  __device__ __forceinline__ void xy(int64_t i, R& px, R& py) const {
+    if (stride == 2 && yoff == 1 && (reinterpret_cast<uintptr_t>(base) & (2 * sizeof(R) - 1)) == 0) {
+      if (sizeof(R) == 8) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(base) + i);
+        px = (R)v.x; py = (R)v.y;
+      } else {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(base) + i);
+        px = (R)v.x; py = (R)v.y;
+      }
+    } else {
+      px = x(i); py = y(i);
+    }
+  }
 };
 // (n,2) array: Fortran order = SoA, C order = interleaved
 template <class R> inline PointsView<R> points_n2(const R* p, int64_t n, bool rowmajor) {
