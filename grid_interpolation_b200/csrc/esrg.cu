@@ -377,11 +377,13 @@ __global__ void __launch_bounds__(128) esrg_fast_kernel(const EsrgArgs<R> a) {
 //   1. stage   the points of the tile's halo rectangle (tile grown by H cells on every side; one CSR run per
 //              grid row, one lane per run) are copied to shared memory (at most 255 of them);
 //   2. scan    every lane computes its d2 to every staged point (shared-memory broadcast, no divergence) and
-//              feeds a 32-bit KEY into a branch-free min/max ladder that keeps its k+1 smallest keys in
-//              registers.  key = (fixed-point d2) << 8 | staged index, or 0xffffffff beyond r_H =
+//              turns it into a 32-bit KEY = (fixed-point d2) << 8 | staged index, or 0xffffffff beyond r_H =
 //              spac*(H+1/2), the radius the lane's own (2H+1)^2 window is guaranteed to cover.  The fixed-point
 //              value is the low mantissa word of d2 + 2^(e+52) -- a MONOTONE function of d2 with 2^-23 r_H^2
-//              resolution -- so the ladder costs two integer min/max per slot and carries no payload;
+//              resolution.  Keys carry no payload, so keeping the k+1 smallest is pure integer min/max in
+//              registers: candidates are taken in batches of 8 (16 for k > 8), a batch is sorted by a
+//              19-comparator network and merged into the kept keys by one bitonic merge (10 min/max per
+//              candidate; an insertion ladder, the previous form, needs 17);
 //   3. grow    if a lane found fewer than k points within r_H the warp repeats 1-2 with H+2 (rare: H starts
 //              at the level where the mean density gives ~1.5k+6 points within r_H);
 //   4. resolve monotonicity makes the k smallest keys the k nearest points in ascending order provided the
@@ -399,9 +401,58 @@ constexpr int kTileWarps = 4;
 
 __device__ __forceinline__ unsigned lo_word(double x) { return (unsigned)__double2loint(x); }
 
-// KS = key slots = largest supported k + 1.  The live k+1 slots are the TOP ones (slots below hold 0 and stay
-// 0), so the k-th and (k+1)-th smallest keys sit in the compile-time slots KS-2 and KS-1 for every run-time k.
-template <class R, int KS>
+// Key selection networks (registers only, fully unrolled; validated with the 0-1 principle).
+#define GI_CE(x, y) { const unsigned lo__ = min(x, y), hi__ = max(x, y); x = lo__; y = hi__; }
+// ascending sort of M keys: Batcher's 19-comparator odd-even merge sort for M = 8, a bitonic network otherwise
+template <int M> __device__ __forceinline__ void sort_keys(unsigned (&b)[M]) {
+  if (M == 8) {
+    GI_CE(b[0], b[1]) GI_CE(b[2], b[3]) GI_CE(b[4], b[5]) GI_CE(b[6], b[7])
+    GI_CE(b[0], b[2]) GI_CE(b[1], b[3]) GI_CE(b[4], b[6]) GI_CE(b[5], b[7])
+    GI_CE(b[1], b[2]) GI_CE(b[5], b[6])
+    GI_CE(b[0], b[4]) GI_CE(b[1], b[5]) GI_CE(b[2], b[6]) GI_CE(b[3], b[7])
+    GI_CE(b[2], b[4]) GI_CE(b[3], b[5])
+    GI_CE(b[1], b[2]) GI_CE(b[3], b[4]) GI_CE(b[5], b[6])
+  } else {
+#pragma unroll
+    for (int k = 2; k <= M; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+          const int l = i ^ j;
+          if (l > i) {
+            if ((i & k) == 0) { GI_CE(b[i], b[l]) } else { GI_CE(b[l], b[i]) }
+          }
+        }
+      }
+    }
+  }
+}
+// a[] (ascending) <- the M smallest of a[] and b[] (both ascending), ascending; next <- min(next, the other M):
+// min(a[i], b[M-1-i]) is the lower half of the union as a bitonic sequence, one bitonic merge sorts it
+template <int M> __device__ __forceinline__ void merge_keys(unsigned (&a)[M], const unsigned (&b)[M], unsigned& next) {
+  unsigned hi[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    const unsigned x = a[i], y = b[M - 1 - i];
+    a[i] = min(x, y);
+    hi[i] = max(x, y);
+  }
+#pragma unroll
+  for (int i = 0; i < M; i += 2) next = __vimin3_u32(next, hi[i], hi[i + 1]);
+#pragma unroll
+  for (int j = M >> 1; j > 0; j >>= 1) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      const int l = i ^ j;
+      if (l > i) GI_CE(a[i], a[l])
+    }
+  }
+}
+
+// M = largest supported k.  The k live slots of key[] are the TOP ones (slots below hold 0 and stay 0), so the
+// k-th smallest key sits in the compile-time slot M-1 for every run-time k; `next` is the (k+1)-th smallest.
+template <class R, int M>
 __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const EsrgArgs<R> a, int h0) {
   __shared__ XY<R> s_xy[kTileWarps][kStageCap + 1];
   __shared__ int s_pos[kTileWarps][kStageCap + 1];
@@ -429,8 +480,9 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
   const int tx0 = w.fast_is_y ? ts0 : tf0, tx1 = w.fast_is_y ? s_hi : f_hi;
   const int ty0 = w.fast_is_y ? tf0 : ts0, ty1 = w.fast_is_y ? f_hi : s_hi;
 
-  const int base = KS - 1 - k;  // first live slot
-  unsigned key[KS];
+  const int base = M - k;  // first live slot
+  unsigned key[M];
+  unsigned next = 0xffffffffu;
   bool hand_over = false;
   int H = h0;
   const int level_cap = len_x + len_y;
@@ -468,20 +520,33 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
     __syncwarp();
     // ---- 2. scan ------------------------------------------------------------------------------------
 #pragma unroll
-    for (int j = 0; j < KS; ++j) key[j] = j >= base ? 0xffffffffu : 0u;
-#pragma unroll 2
-    for (int i = 0; i < total; ++i) {
+    for (int j = 0; j < M; ++j) key[j] = j >= base ? 0xffffffffu : 0u;
+    next = 0xffffffffu;
+    auto key_of = [&](int i) -> unsigned {
       const XY<R> q = s_xy[wid][i];
       const R ddx = cx - q.x, ddy = cy - q.y;
       const R d2 = ddx * ddx + ddy * ddy;                                 // :147-148
       const unsigned fix = lo_word((double)d2 + magic);
-      const unsigned c = d2 > r2 ? 0xffffffffu : (fix << 8) + (unsigned)i;
+      return d2 > r2 ? 0xffffffffu : (fix << 8) + (unsigned)i;
+    };
+    // batches of M candidates: sort the batch (network), merge it into the kept keys (one bitonic merge)
+    int i0 = 0;
+    for (; i0 + M <= total; i0 += M) {
+      unsigned b[M];
 #pragma unroll
-      for (int j = KS - 1; j >= 1; --j) key[j] = min(key[j], max(key[j - 1], c));
-      key[0] = min(key[0], c);  // (slot 0 is live only when k + 1 == KS)
+      for (int u = 0; u < M; ++u) b[u] = key_of(i0 + u);
+      sort_keys<M>(b);
+      merge_keys<M>(key, b, next);
+    }
+    if (i0 < total) {  // ragged last batch (total is warp-uniform)
+      unsigned b[M];
+#pragma unroll
+      for (int u = 0; u < M; ++u) b[u] = i0 + u < total ? key_of(i0 + u) : 0xffffffffu;
+      sort_keys<M>(b);
+      merge_keys<M>(key, b, next);
     }
     // ---- 3. grow? -----------------------------------------------------------------------------------
-    if (__all_sync(0xffffffffu, key[KS - 2] != 0xffffffffu)) break;       // k points within r_H: :178,:243
+    if (__all_sync(0xffffffffu, key[M - 1] != 0xffffffffu)) break;        // k points within r_H: :178,:243
     H += 2;
     if (H > level_cap) { raise_status(a.status, GI_ERR_TOO_FEW_POINTS); hand_over = true; break; }
   }
@@ -493,9 +558,9 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
   bool ambiguous = false;
   R numerator = R(0), denominator = R(0), first_val = R(0), first_dist = R(0);
 #pragma unroll
-  for (int j = 0; j < KS - 1; ++j) {
+  for (int j = 0; j < M; ++j) {
     if (j >= base) {
-      ambiguous |= (key[j] >> 8) == (key[j + 1] >> 8);
+      ambiguous |= (key[j] >> 8) == ((j + 1 < M ? key[j + 1 < M ? j + 1 : j] : next) >> 8);
       const int e = key[j] & 0xff;
       const XY<R> q = s_xy[wid][e];
       const int pos = s_pos[wid][e];
@@ -593,8 +658,8 @@ int esrg_query_window(Scratch& scr, const Binned<R>& b, int num_points, const R*
   if (k <= 16 && tiles_fit) {
     const int64_t tiles = (int64_t)div_up(a.win.nf(), 8) * div_up(a.win.ns(), 4);
     const unsigned tg = (unsigned)div_up(tiles, kTileWarps);
-    if (k <= 8) esrg_tile_kernel<R, 9><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
-    else esrg_tile_kernel<R, 17><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
+    if (k <= 8) esrg_tile_kernel<R, 8><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
+    else esrg_tile_kernel<R, 16><<<tg, 32 * kTileWarps, 0, st>>>(a, h0);
   } else {
     esrg_fast_kernel<R, 32><<<grid, 128, 0, st>>>(a);
   }
