@@ -7,14 +7,15 @@
 //   query_esrg.f90:97-249       nearest_neighbours_esrg (ring-expanding exact kNN from the cell centre)
 //
 // B200 design (not a port):
-//   binning   one pass computes each point's cell key and a histogram (atomics into ONE int32 table of
-//             len_y*len_x entries), an in-place exclusive scan turns it into offsets, a second pass scatters
-//             the point ids with atomicAdd on the same table -- which leaves the table holding the END
-//             offset of every cell (start(c) = table[c-1]), so no second 268 MB table is needed at 8192^2.
-//             The reference's fill is stable (ascending point id inside a cell, query_esrg.f90:72-89); the
-//             atomic scatter is not, so cells holding more than one point are insertion-sorted afterwards.
-//             Coordinates, values and ids are then gathered into cell order so the query reads them
-//             contiguously.
+//   binning   each point's cell key (iy*len_x + ix, the reference's CSR order) is computed once and the points
+//             are sorted by it with a stable LSD radix sort (radix.cuh; 4 passes for 2^26 cells) -- stable, so
+//             the points of a cell stay in ascending id order exactly like the reference's fill
+//             (query_esrg.f90:72-89).  ONE int32 table of len_y*len_x entries then receives the END offset of
+//             every cell (start(c) = table[c-1]): the thread of sorted position p writes p+1 into the cells
+//             key[p] .. key[p+1]-1, long empty stretches cooperatively by the warp.  Coordinates, values and ids
+//             are gathered into cell order so the query reads them contiguously.  (The first version counted
+//             with 10 M atomics into the table, scanned all 67 M cells and scattered with atomics again:
+//             1.75 ms at C3.)
 //   query     one thread per grid target, two kernels:
 //             esrg_fast_kernel   The reference's result is "the k smallest d2 among the points of the
 //               (2L+1)^2 window, L = first level at which k points lie within r_L = spac*(L+1/2)"
@@ -33,7 +34,7 @@
 #include <memory>
 
 #include "kernels.cuh"
-#include "scan.cuh"
+#include "radix.cuh"
 #include "topk.cuh"
 
 namespace gi {
@@ -51,54 +52,67 @@ template <class R> __device__ __forceinline__ int cell_index(R p, R axis0, R spa
 
 template <class R>
 __global__ void __launch_bounds__(256)
-esrg_key_count_kernel(PointsView<R> pts, int n, const R* __restrict__ x_axis, int len_x,
-                      const R* __restrict__ y_axis, int len_y, R spac, int* __restrict__ keys,
-                      int* __restrict__ table) {
+esrg_key_kernel(PointsView<R> pts, int n, const R* __restrict__ x_axis, int len_x, const R* __restrict__ y_axis,
+                int len_y, R spac, unsigned* __restrict__ keys, int* __restrict__ ids) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int ix = cell_index(pts.x(i), __ldg(x_axis), spac, len_x);
   const int iy = cell_index(pts.y(i), __ldg(y_axis), spac, len_y);
-  const int key = iy * len_x + ix;  // CSR order: ind_y outer, ind_x inner (query_esrg.f90:63-68)
-  keys[i] = key;
-  atomicAdd(table + key, 1);
+  keys[i] = (unsigned)(iy * len_x + ix);  // CSR order: ind_y outer, ind_x inner (query_esrg.f90:63-68)
+  ids[i] = i;
 }
 
+// table[c] = number of points with key <= c (the END offset of cell c), from the sorted keys: position p owns the
+// cells key[p] .. key[p+1]-1 (the last position up to the last cell, position 0 also the cells before key[0])
 __global__ void __launch_bounds__(256)
-esrg_scatter_kernel(const int* __restrict__ keys, int n, int* __restrict__ table, int* __restrict__ sid) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int slot = atomicAdd(table + keys[i], 1);  // table[c] ends as the END offset of cell c
-  sid[slot] = i + 1;                               // 1-based ids like index_of_pts
-}
-
-// restore the reference's stable order inside every cell that holds more than one point
-__global__ void __launch_bounds__(256)
-esrg_sort_cells_kernel(const int* __restrict__ keys, int n, const int* __restrict__ table, int* __restrict__ sid) {
+esrg_table_kernel(const unsigned* __restrict__ keys, int n, int64_t cells, int* __restrict__ table) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  const int key = keys[sid[p] - 1];
-  const int start = key > 0 ? table[key - 1] : 0;
-  if (start != p) return;
-  const int end = table[key];
-  for (int i = start + 1; i < end; ++i) {
-    const int v = sid[i];
-    int j = i - 1;
-    while (j >= start && sid[j] > v) { sid[j + 1] = sid[j]; --j; }
-    sid[j + 1] = v;
+  const int lane = threadIdx.x & 31;
+  // every lane fills table[c0..c1) with val: short stretches by the lane itself, long ones (empty regions of the
+  // grid) by the whole warp
+  auto fill = [&](int64_t c0, int64_t c1, int val) {
+    constexpr int kOwn = 8;
+    const int64_t own_end = c0 + kOwn < c1 ? c0 + kOwn : c1;
+    for (int64_t c = c0; c < own_end; ++c) table[c] = val;
+    unsigned long_ones = __ballot_sync(0xffffffffu, c1 > own_end);
+    while (long_ones) {
+      const int src = __ffs(long_ones) - 1;
+      long_ones &= long_ones - 1;
+      const int64_t b0 = __shfl_sync(0xffffffffu, own_end, src), b1 = __shfl_sync(0xffffffffu, c1, src);
+      const int v = __shfl_sync(0xffffffffu, val, src);
+      for (int64_t c = b0 + lane; c < b1; c += 32) table[c] = v;
+    }
+  };
+  int64_t c0 = 0, c1 = 0;
+  if (p < n) {
+    c0 = keys[p];
+    c1 = p + 1 < n ? (int64_t)keys[p + 1] : cells;
   }
+  if (blockIdx.x == 0 && threadIdx.x < 32) fill(0, p == 0 ? c0 : 0, 0);  // the cells before the first point
+  fill(c0, c1, p + 1);
 }
 
 template <class R> struct alignas(16) XY { R x, y; };
 
+// order[p] = 0-based id of the point at cell-order position p; sid_out (optional) receives the 1-based ids
 template <class R>
 __global__ void __launch_bounds__(256)
-esrg_gather_kernel(PointsView<R> pts, const R* __restrict__ data, const int* __restrict__ sid, int n,
-                   XY<R>* __restrict__ sxy, R* __restrict__ sval) {
+esrg_gather_kernel(PointsView<R> pts, const R* __restrict__ data, const int* __restrict__ order, int n,
+                   XY<R>* __restrict__ sxy, R* __restrict__ sval, int* __restrict__ sid_out) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  const int i = sid[p] - 1;
-  if (sxy) { XY<R> v; v.x = pts.x(i); v.y = pts.y(i); sxy[p] = v; }
+  const int i = order[p];
+  if (sxy) { XY<R> v; pts.xy(i, v.x, v.y); sxy[p] = v; }
   if (sval) sval[p] = __ldg(data + i);
+  if (sid_out) sid_out[p] = i + 1;  // 1-based ids like index_of_pts
+}
+
+// plans: new nodal values into cell order (sid holds the 1-based ids)
+template <class R>
+__global__ void __launch_bounds__(256)
+esrg_values_kernel(const R* __restrict__ data, const int* __restrict__ sid, int n, R* __restrict__ sval) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) sval[p] = __ldg(data + sid[p] - 1);
 }
 
 __global__ void esrg_export_indptr_kernel(const int* __restrict__ table, int64_t cells, int* __restrict__ indptr) {
@@ -589,7 +603,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
 template <class R> struct Binned {
   int* table;
   int* sid;
-  int* keys;
   XY<R>* sxy;
   R* sval;
 };
@@ -601,20 +614,27 @@ int esrg_bin(Scratch& keep, Scratch& tmp, const R* points, int n, const R* data_
   const int64_t cells = (int64_t)len_x * len_y;
   GI_REQUIRE(cells < (int64_t)0x7fffffff, "grid has more than 2^31 cells");
   GI_TRY(keep.alloc(&b->table, (size_t)cells));
-  GI_TRY(tmp.alloc(&b->keys, (size_t)n));
   GI_TRY(keep.alloc(&b->sid, (size_t)n));
   GI_TRY(keep.alloc(&b->sxy, (size_t)n));
   b->sval = nullptr;
   if (want_values) GI_TRY(keep.alloc(&b->sval, (size_t)n));
-  GI_CUDA(cudaMemsetAsync(b->table, 0, sizeof(int) * (size_t)cells, st));
+  unsigned *keys, *keys_tmp, *keys_sorted;
+  int *ids, *ids_tmp, *ids_sorted, *hist;
+  GI_TRY(tmp.alloc(&keys, (size_t)n));
+  GI_TRY(tmp.alloc(&keys_tmp, (size_t)n));
+  GI_TRY(tmp.alloc(&ids, (size_t)n));
+  GI_TRY(tmp.alloc(&ids_tmp, (size_t)n));
+  GI_TRY(tmp.alloc(&hist, radix_hist_size(n)));
   const PointsView<R> pv = points_n2(points, n, flags & GI_POINTS_ROWMAJOR);
   const int blocks = div_up(n, 256);
-  esrg_key_count_kernel<R><<<blocks, 256, 0, st>>>(pv, n, x_axis, len_x, y_axis, len_y, spac, b->keys, b->table);
+  esrg_key_kernel<R><<<blocks, 256, 0, st>>>(pv, n, x_axis, len_x, y_axis, len_y, spac, keys, ids);
   GI_CUDA(cudaGetLastError());
-  GI_TRY(exclusive_scan_i32(tmp, b->table, b->table, cells));
-  esrg_scatter_kernel<<<blocks, 256, 0, st>>>(b->keys, n, b->table, b->sid);
-  esrg_sort_cells_kernel<<<blocks, 256, 0, st>>>(b->keys, n, b->table, b->sid);
-  esrg_gather_kernel<R><<<blocks, 256, 0, st>>>(pv, data_in, b->sid, n, b->sxy, data_in ? b->sval : nullptr);
+  int passes = 1;
+  while (passes < 4 && (cells - 1) >> (8 * passes)) ++passes;
+  GI_TRY(radix_sort<unsigned>(keys, ids, keys_tmp, ids_tmp, hist, n, passes, st, &keys_sorted, &ids_sorted));
+  esrg_table_kernel<<<blocks, 256, 0, st>>>(keys_sorted, n, cells, b->table);
+  esrg_gather_kernel<R><<<blocks, 256, 0, st>>>(pv, data_in, ids_sorted, n, b->sxy, data_in ? b->sval : nullptr,
+                                                b->sid);
   GI_CUDA(cudaGetLastError());
   return GI_OK;
 }
@@ -809,8 +829,7 @@ template <class R> struct EsrgPlan : PlanBase {
       GI_TRY(scr.alloc(&dout, (size_t)(row_end - row_begin) * len_x));
     }
     ph.mark("esrg_values");
-    esrg_gather_kernel<R><<<div_up(num_points, 256), 256, 0, st>>>(PointsView<R>{nullptr, 0, 0}, dd, bins.sid,
-                                                                  num_points, nullptr, bins.sval);
+    esrg_values_kernel<R><<<div_up(num_points, 256), 256, 0, st>>>(dd, bins.sid, num_points, bins.sval);
     GI_CUDA(cudaGetLastError());
     ph.mark("esrg_query");
     if (mem == GI_HOST) {

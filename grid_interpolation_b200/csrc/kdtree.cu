@@ -26,6 +26,7 @@
 #include <memory>
 
 #include "kernels.cuh"
+#include "radix.cuh"
 #include "scan.cuh"
 #include "topk.cuh"
 
@@ -33,19 +34,14 @@ namespace gi {
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// stable LSD radix sort of (64-bit key, id) pairs, ascending: 8 passes of 8 bits, 3 launches per pass
-// (per-tile digit histogram, per-digit scan over the tiles, stable scatter).  The first version used
-// a bitonic network (56 launches per sort, 0.65 ms for 1 M points: launch-bound).
+// sort keys: both coordinate orders are produced by radix.cuh's stable sort on an order-preserving 64-bit image
+// of the coordinate (ties end up in id order).  The first version used a bitonic network: 56 launches per sort,
+// 0.65 ms for 1 M points, launch-bound.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long order_key(double v) {
   const unsigned long long b = (unsigned long long)__double_as_longlong(v);
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
-
-constexpr int kRadix = 256;
-constexpr int kSortThreads = 256;
-constexpr int kSortChunks = 16;
-constexpr int kSortTile = kSortThreads * kSortChunks;  // 4096 elements per block
 
 template <class R>
 __global__ void __launch_bounds__(256)
@@ -54,129 +50,6 @@ sort_keys_kernel(PointsView<R> pts, int n, int axis, unsigned long long* __restr
   if (i >= n) return;
   keys[i] = order_key((double)(axis == 0 ? pts.x(i) : pts.y(i)));
   ids[i] = i;
-}
-
-// hist[d * tiles + tile] = number of keys of the tile with digit d
-__global__ void __launch_bounds__(kSortThreads)
-radix_hist_kernel(const unsigned long long* __restrict__ keys, int n, int shift, int* __restrict__ hist, int tiles) {
-  __shared__ int h[kRadix];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  const int base = blockIdx.x * kSortTile;
-#pragma unroll 4
-  for (int c = 0; c < kSortChunks; ++c) {
-    const int i = base + c * kSortThreads + threadIdx.x;
-    if (i < n) atomicAdd(&h[(int)((keys[i] >> shift) & (kRadix - 1))], 1);
-  }
-  __syncthreads();
-  hist[threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
-}
-
-// one block per digit: exclusive scan of its row hist[d][0..tiles) in place, row total to digit_total[d]
-__global__ void __launch_bounds__(256)
-radix_scan_kernel(int* __restrict__ hist, int tiles, int* __restrict__ digit_total) {
-  __shared__ int warp_sums[8];
-  int* row = hist + (size_t)blockIdx.x * tiles;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int carry = 0;
-  for (int t0 = 0; t0 < tiles; t0 += 256) {
-    const int t = t0 + threadIdx.x;
-    const int v = t < tiles ? row[t] : 0;
-    int inc = v;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, inc, off);
-      if (lane >= off) inc += u;
-    }
-    if (lane == 31) warp_sums[wid] = inc;
-    __syncthreads();
-    int wbase = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const int x = warp_sums[w];
-      if (w < wid) wbase += x;
-      tot += x;
-    }
-    if (t < tiles) row[t] = carry + wbase + inc - v;
-    carry += tot;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) digit_total[blockIdx.x] = carry;
-}
-
-// stable scatter: an element's position = global offset of (digit, tile) + its rank among the tile's earlier
-// elements with the same digit (chunks in order; inside a chunk warps in order, lanes in order)
-__global__ void __launch_bounds__(kSortThreads)
-radix_scatter_kernel(const unsigned long long* __restrict__ keys_in, const int* __restrict__ ids_in,
-                     unsigned long long* __restrict__ keys_out, int* __restrict__ ids_out, int n, int shift,
-                     const int* __restrict__ offs, const int* __restrict__ digit_total, int tiles) {
-  __shared__ int base[kRadix];
-  __shared__ int warp_cnt[kSortThreads / 32][kRadix];
-  __shared__ int wsum[kSortThreads / 32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  {  // base[d] = (number of keys with a smaller digit) + (keys with digit d in earlier tiles)
-    const int v = digit_total[threadIdx.x];
-    int inc = v;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, inc, off);
-      if (lane >= off) inc += u;
-    }
-    if (lane == 31) wsum[wid] = inc;
-    __syncthreads();
-    int wbase = 0;
-#pragma unroll
-    for (int w = 0; w < kSortThreads / 32; ++w)
-      if (w < wid) wbase += wsum[w];
-    base[threadIdx.x] = wbase + inc - v + offs[threadIdx.x * tiles + blockIdx.x];
-  }
-#pragma unroll
-  for (int w = 0; w < kSortThreads / 32; ++w) warp_cnt[w][threadIdx.x] = 0;
-  __syncthreads();
-  const int tile0 = blockIdx.x * kSortTile;
-  for (int c = 0; c < kSortChunks; ++c) {
-    const int i = tile0 + c * kSortThreads + threadIdx.x;
-    const bool valid = i < n;
-    unsigned long long key = 0;
-    int id = 0, d = 0;
-    if (valid) { key = keys_in[i]; id = ids_in[i]; d = (int)((key >> shift) & (kRadix - 1)); }
-    // lanes of this warp with the same digit (invalid lanes only exist at the very end: give them no peers)
-    const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : kRadix + lane) & __ballot_sync(0xffffffffu, valid);
-    const int rank = __popc(peers & ((1u << lane) - 1u));
-    if (valid && rank == 0) warp_cnt[wid][d] = __popc(peers);
-    __syncthreads();
-    int pos = 0;
-    if (valid) {
-      pos = base[d] + rank;
-      for (int w = 0; w < wid; ++w) pos += warp_cnt[w][d];
-    }
-    __syncthreads();
-    {  // digit = threadIdx.x: advance its base by this chunk's count and clear the per-warp counters
-      int tot = 0;
-#pragma unroll
-      for (int w = 0; w < kSortThreads / 32; ++w) { tot += warp_cnt[w][threadIdx.x]; warp_cnt[w][threadIdx.x] = 0; }
-      base[threadIdx.x] += tot;
-    }
-    __syncthreads();
-    if (valid) { keys_out[pos] = key; ids_out[pos] = id; }
-  }
-}
-
-// sorts (keys, ids) in place; keys_tmp / ids_tmp are scratch of the same size, hist holds 256 * (tiles + 1) ints
-int radix_sort(unsigned long long* keys, int* ids, unsigned long long* keys_tmp, int* ids_tmp, int* hist, int n,
-               cudaStream_t st) {
-  const int tiles = div_up(n, kSortTile);
-  for (int pass = 0; pass < 8; ++pass) {
-    const int shift = 8 * pass;
-    radix_hist_kernel<<<tiles, kSortThreads, 0, st>>>(keys, n, shift, hist, tiles);
-    radix_scan_kernel<<<kRadix, 256, 0, st>>>(hist, tiles, hist + (size_t)kRadix * tiles);
-    radix_scatter_kernel<<<tiles, kSortThreads, 0, st>>>(keys, ids, keys_tmp, ids_tmp, n, shift, hist,
-                                                        hist + (size_t)kRadix * tiles, tiles);
-    std::swap(keys, keys_tmp);
-    std::swap(ids, ids_tmp);
-  }
-  GI_CUDA(cudaGetLastError());
-  return GI_OK;  // 8 passes: the result is back in the caller's keys / ids
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -268,7 +141,7 @@ int kd_build(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
   GI_TRY(scr.alloc(&keys, (size_t)n));
   GI_TRY(scr.alloc(&keys_tmp, (size_t)n));
   GI_TRY(scr.alloc(&ids_tmp, (size_t)n));
-  GI_TRY(scr.alloc(&hist, (size_t)kRadix * (div_up(n, kSortTile) + 1)));
+  GI_TRY(scr.alloc(&hist, radix_hist_size(n)));
   GI_TRY(scr.alloc(&list[0], (size_t)n));
   GI_TRY(scr.alloc(&list[1], (size_t)n));
   GI_TRY(scr.alloc(&pos[0], (size_t)n));
@@ -282,7 +155,8 @@ int kd_build(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
   GI_TRY(scr.alloc(&flag, (size_t)n));
   for (int axis = 0; axis < 2; ++axis) {
     sort_keys_kernel<R><<<div_up(n, 256), 256, 0, st>>>(pv, n, axis, keys, list[axis]);
-    GI_TRY(radix_sort(keys, list[axis], keys_tmp, ids_tmp, hist, n, st));
+    unsigned long long* k_sorted; int* l_sorted;  // 8 passes: back in keys / list[axis]
+    GI_TRY(radix_sort<unsigned long long>(keys, list[axis], keys_tmp, ids_tmp, hist, n, 8, st, &k_sorted, &l_sorted));
   }
   const int blocks = div_up(n, 256);
   kd_init_kernel<<<blocks, 256, 0, st>>>(list[0], list[1], n, pos[0], pos[1], seg_lo, seg_hi);
