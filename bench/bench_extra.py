@@ -17,20 +17,8 @@ from grid_interpolation_b200 import workloads  # noqa: E402
 
 
 def _kd_launches(n):
-    """Kernel launches of one idw_kdtree call (mirrors kdtree.cu: bitonic network + level-synchronous build)."""
-    tile = 2048
-    n2 = tile
-    while n2 < n:
-        n2 *= 2
-    sort = 1 + 1  # keys + first shared pass
-    k = tile * 2
-    while k <= n2:
-        j = k // 2
-        while j >= tile:
-            sort += 1
-            j //= 2
-        sort += 1
-        k *= 2
+    """Kernel launches of one idw_kdtree call (mirrors kdtree.cu: two radix sorts + level-synchronous build)."""
+    sort = 1 + 8 * 3  # keys + 8 passes x (histogram, scan, scatter)
     levels = 0
     while (1 << levels) <= n:
         levels += 1
@@ -163,8 +151,11 @@ def run(args, rank, world, local_rank):
                       ip.pinned_copy(w.y_axis))
             step_host = lambda: ip.idw_esrg_nearest_ex(*h_args, 1.0, k, rows=band, out=h_out)
             cells = grid * grid
-            # key/count, scan (1, 3 or 5 kernels), scatter, sort cells, gather, tile query, exact-order query, flush
-            launches = 1 + (1 if cells <= 4096 else (3 if cells <= 4096 * 4096 else 5)) + 3 + 2 + 1
+            passes = 1
+            while passes < 4 and (cells - 1) >> (8 * passes):
+                passes += 1
+            # keys, radix passes x (histogram, scan, scatter), table, gather, tile query, exact-order query, flush
+            launches = 1 + 3 * passes + 2 + 2 + 1
             dominant = "esrg_query"
 
     def sync_all():
