@@ -76,6 +76,15 @@ __device__ __forceinline__ void load_values(const TriGeom<double>* p, TriGeom<do
   ld256(reinterpret_cast<const char*>(p) + 64, g.d1, g.d2, g.d3, g.padv);
 }
 __device__ __forceinline__ void load_values(const TriGeom<float>*, TriGeom<float>&) {}
+// sector 2 as ONE full-sector store (three 8 B stores at a 96 B stride make the L2 merge partial sectors)
+__device__ __forceinline__ void store_values(TriGeom<double>* p, double d1, double d2, double d3) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<char*>(p) + 64), "d"(d1), "d"(d2), "d"(d3),
+               "d"(0.0)
+               : "memory");
+}
+__device__ __forceinline__ void store_values(TriGeom<float>* p, float d1, float d2, float d3) {
+  p->d1 = d1; p->d2 = d2; p->d3 = d3;
+}
 // Fire-and-forget load of sector 2: the registers are never read, so nothing waits on it, but the sector is in
 // L1 when phase 2 asks for it a few thousand cycles later (prefetch.global.L1 had no measurable effect).
 __device__ __forceinline__ void touch_values(const TriGeom<double>* p) {
@@ -145,7 +154,7 @@ pack_values_kernel(const R* __restrict__ data, TopoView simp, int num_points, in
   if ((unsigned)(a - 1) >= (unsigned)num_points || (unsigned)(b - 1) >= (unsigned)num_points ||
       (unsigned)(c - 1) >= (unsigned)num_points)
     a = b = c = 1;
-  geom[t].d1 = __ldg(data + (a - 1)); geom[t].d2 = __ldg(data + (b - 1)); geom[t].d3 = __ldg(data + (c - 1));
+  store_values(geom + t, __ldg(data + (a - 1)), __ldg(data + (b - 1)), __ldg(data + (c - 1)));
 }
 
 // Seed triangle for grid target (ix, iy): the cell's own entry, else the nearest non-empty cell within 3

@@ -30,7 +30,6 @@
 //               deferred list per thread; when it overflows the thread switches to a list-free mode that
 //               re-scans the inner frames with the predicate "was deferred at the previous level"
 //               (d2 > r2_prev), which yields the same order for any point density.
-#include <cstdlib>
 #include <memory>
 
 #include "kernels.cuh"

@@ -1,0 +1,56 @@
+"""The search-structure builds on their own (GPU): radix-sort based k-d tree build and esrg cell binning at sizes
+around the sort's tile / warp boundaries, with duplicate keys, empty regions and clamped points."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from grid_interpolation_b200 import interpolation as ip  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+def same(a, b):
+    assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def check_tree(points_2n):
+    order = ip.kd_build(np.ascontiguousarray(points_2n)) - 1
+    ref = orc.kd_build(points_2n)
+    stack = [(ref.root, 0, order.size)]
+    while stack:                                   # oracle pointer tree vs implicit array (kd_tree.f90:54-68)
+        node, lo, hi = stack.pop()
+        if node < 0:
+            assert lo == hi
+            continue
+        m = lo + (hi - lo + 1) // 2 - 1
+        assert order[m] == ref.index[node] - 1
+        stack.append((ref.left[node], lo, m)); stack.append((ref.right[node], m + 1, hi))
+    assert sorted(order.tolist()) == list(range(order.size))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 511, 513, 4095, 4096, 4097, 8193, 100_003])
+def test_kd_build_sizes(n):
+    rng = np.random.default_rng(n)
+    check_tree(rng.uniform(-50.0, 1000.0, (2, n)))
+
+
+def test_kd_build_negative_and_tiny_coordinates():
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([rng.normal(0.0, 1e-200, (2, 700)), rng.normal(0.0, 1e200, (2, 700)),
+                          rng.uniform(-1.0, 1.0, (2, 700))], axis=1)
+    check_tree(pts)
+
+
+@pytest.mark.parametrize("n,lx,ly", [(1, 5, 4), (40, 3, 3), (4097, 64, 48), (20_000, 300, 200), (9_000, 1500, 1100)])
+def test_esrg_binning_sizes(n, lx, ly):
+    """dense (many points per cell), sparse (long empty stretches of the table) and clamped points"""
+    rng = np.random.default_rng(n + lx)
+    x = np.arange(float(lx)); y = np.arange(float(ly))
+    pts = np.column_stack([rng.uniform(-3.0, lx + 2.0, n), rng.uniform(-3.0, ly + 2.0, n)])
+    if n > 1000:                                   # a tight cluster and a big hole
+        pts[: n // 3] = rng.normal([lx * 0.8, ly * 0.2], 0.7, (n // 3, 2))
+    idx, ptr = ip.assign_points_to_cells(pts, x, y, 1.0)
+    oi, op, _ = orc.assign_points_to_cells(pts, x, y, 1.0)
+    same(idx, oi)
+    same(ptr[:-1].reshape(ly, lx) + 1, op)
+    assert ptr[-1] == n
