@@ -1,0 +1,93 @@
+"""Size-independent properties at (or near) BASELINE.json's full sizes, where the CPU oracle would take minutes (GPU).
+
+  C2 full size   k-d tree IDW == cell-list IDW bit for bit (unit spacing: the reference's prune rule is exact
+                 there), neighbour sets == scipy cKDTree on a sample, values inside the data range
+  C3 (1/2 edge)  device path == host (pipelined) path == plan, checksums; row bands concatenate to the field
+  C4 (1/4 edge)  a linear field is reproduced inside the hull, hull fill only copies existing values,
+                 host path == device path == plan, band-split run == one-shot run
+  C5 (1/4 edge)  bilinear of a linear field is exact to rounding, chunked host path == device path
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from grid_interpolation_b200 import interpolation as ip  # noqa: E402
+from grid_interpolation_b200 import workloads  # noqa: E402
+
+
+def dev(a):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+
+
+def test_c2_full_size_kdtree_equals_cell_list_and_scipy():
+    from scipy.spatial import cKDTree
+    w = workloads.c2()                                                 # 1 M points -> 4096 x 4096, k = 8
+    k = 8
+    kd = ip.idw_kdtree(dev(w.points).t(), dev(w.data_pts), dev(w.x_axis), dev(w.y_axis), k, order="C")
+    es = ip.idw_esrg_nearest(dev(w.points), dev(w.data_pts), dev(w.x_axis), dev(w.y_axis), 1.0, k, order="C")
+    kd, es = kd.cpu().numpy(), es.cpu().numpy()
+    assert np.array_equal(kd, es), "k-d tree and cell-list IDW differ although both are exact kNN here"
+    assert kd.min() >= w.data_pts.min() and kd.max() <= w.data_pts.max()      # a convex combination
+    # neighbour ids of a band of rows against scipy (exact kNN, ascending distance)
+    rows = (2000, 2016)
+    _, g = ip.idw_kdtree_ex(w.points.T, w.data_pts, w.x_axis, w.y_axis, k, rows=rows, order="C", debug=True)
+    xx, yy = np.meshgrid(w.x_axis, w.y_axis[rows[0]:rows[1]])
+    d, idx = cKDTree(w.points).query(np.stack([xx.ravel(), yy.ravel()], 1), k=k)
+    assert np.array_equal(g.nn_index.reshape(-1, k) - 1, idx)
+    np.testing.assert_allclose(np.sqrt(g.nn_dist2.reshape(-1, k)), d, rtol=1e-13, atol=0)
+
+
+def test_c3_half_edge_paths_agree():
+    w = workloads.c3(2_500_000, 4096)
+    k = 8
+    one = ip.idw_esrg_nearest(dev(w.points), dev(w.data_pts), dev(w.x_axis), dev(w.y_axis), 1.0, k, order="C").cpu().numpy()
+    host = ip.idw_esrg_nearest(w.points, w.data_pts, w.x_axis, w.y_axis, 1.0, k, order="C")      # 4 bands of 32 MB
+    assert np.array_equal(one, host)
+    with ip.EsrgPlan(dev(w.points), dev(w.x_axis), dev(w.y_axis), 1.0, k, order="C") as plan:
+        assert np.array_equal(plan(dev(w.data_pts)).cpu().numpy(), one)
+    parts = [ip.idw_esrg_nearest_ex(w.points, w.data_pts, w.x_axis, w.y_axis, 1.0, k, rows=r, order="C")
+             for r in ((0, 1000), (1000, 1001), (1001, 4096))]
+    assert np.array_equal(np.concatenate(parts, 0), one)
+    assert np.isfinite(one).all() and one.min() >= w.data_pts.min() and one.max() <= w.data_pts.max()
+
+
+def test_c4_quarter_edge_properties():
+    n, grid = 312_500, 4096
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(100.0, grid - 101.0, (n, 2))                     # leaves a ring outside the hull to fill
+    simp, nbr = workloads.delaunay(pts)
+    axis = np.arange(float(grid))
+    lin = 3.0 * pts[:, 0] - 2.0 * pts[:, 1] + 5.0
+    out, g = ip.barycentric_interpolation_ex(pts, lin, axis, axis, simp, nbr, order="C", debug=True)
+    ins = ~g.mask
+    assert ins.mean() > 0.85 and g.mask.any()
+    xx, yy = np.meshgrid(axis, axis)
+    np.testing.assert_allclose(out[ins], (3.0 * xx - 2.0 * yy + 5.0)[ins], rtol=0, atol=2e-8)
+    # hull fill: every masked cell holds the value of its (unmasked) source cell
+    src = g.fill_src[g.mask]
+    assert (src >= 0).all() and not g.mask.ravel()[src].any()
+    assert np.array_equal(out[g.mask], out.ravel()[src])
+    # the three ways to run it agree bit for bit
+    d = [dev(a) for a in (pts, lin, axis, axis, simp, nbr)]
+    device = ip.barycentric_interpolation(*d, order="C").cpu().numpy()
+    assert np.array_equal(device, out)
+    assert np.array_equal(ip.barycentric_interpolation(pts, lin, axis, axis, simp, nbr, order="C"), out)   # 4 bands
+    with ip.BarycentricPlan(d[0], d[2], d[3], d[4], d[5], order="C") as plan:
+        assert np.array_equal(plan(d[1]).cpu().numpy(), out)
+    halves = [ip.barycentric_interpolation_ex(pts, lin, axis, axis, simp, nbr, rows=r, halo=160, order="C")
+              for r in ((0, 2048), (2048, 4096))]
+    assert np.array_equal(np.concatenate(halves, 0), out)
+
+
+def test_c5_quarter_edge_bilinear_linear_field():
+    grid, n = 4096, 6_250_000
+    axis = np.arange(float(grid))
+    xx, yy = np.meshgrid(axis, axis)
+    field = 0.5 * xx - 0.25 * yy + 7.0
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(0.0, grid - 1.0, (n, 2))
+    got = ip.bilinear(axis, axis, field, pts)                           # host path: 4 chunks
+    np.testing.assert_allclose(got, 0.5 * pts[:, 0] - 0.25 * pts[:, 1] + 7.0, rtol=0, atol=1e-9)
+    assert np.array_equal(ip.bilinear(dev(axis), dev(axis), dev(field), dev(pts)).cpu().numpy(), got)
