@@ -91,3 +91,28 @@ def test_c5_quarter_edge_bilinear_linear_field():
     got = ip.bilinear(axis, axis, field, pts)                           # host path: 4 chunks
     np.testing.assert_allclose(got, 0.5 * pts[:, 0] - 0.25 * pts[:, 1] + 7.0, rtol=0, atol=1e-9)
     assert np.array_equal(ip.bilinear(dev(axis), dev(axis), dev(field), dev(pts)).cpu().numpy(), got)
+
+
+@pytest.mark.parametrize("order,dims", [("C", (3008, 3008)), ("F", (3008, 3008)), ("C", (3001, 3003))])
+def test_bilinear_large_field_device_path_equals_host_path(order, dims):
+    """A field larger than half the L2 with 2.6 M points, non-uniform axes, out-of-grid points, both memory orders,
+    sector-load and scalar kernels, f64 and f32: device call == chunked host call, bit for bit."""
+    ly, lx = dims
+    rng = np.random.default_rng(lx + ly)
+    x = np.cumsum(rng.uniform(0.9, 1.1, lx)); y = np.cumsum(rng.uniform(0.9, 1.1, ly))
+    field = np.asarray(rng.normal(size=(ly, lx)), order=order)
+    n = 2_600_000
+    pts = np.column_stack([rng.uniform(x[0] - 20, x[-1] + 20, n), rng.uniform(y[0] - 20, y[-1] + 20, n)])
+    import torch
+    d_field = dev(field) if order == "C" else dev(field.T).t()
+    got = ip.bilinear(dev(x), dev(y), d_field, dev(pts)).cpu().numpy()
+    want = ip.bilinear(x, y, field, pts)
+    assert (want == -9999.0).any()
+    assert np.array_equal(got, want)
+    # f32 variant (scalar kernel) through the same pass
+    got32 = ip.bilinear(dev(x.astype(np.float32)), dev(y.astype(np.float32)),
+                        dev(field.astype(np.float32)) if order == "C" else dev(field.astype(np.float32).T).t(),
+                        dev(pts.astype(np.float32)), dtype=np.float32).cpu().numpy()
+    want32 = ip.bilinear(x.astype(np.float32), y.astype(np.float32), field.astype(np.float32),
+                         pts.astype(np.float32), dtype=np.float32)
+    assert np.array_equal(got32, want32)
