@@ -623,7 +623,7 @@ int esrg_bin(Scratch& keep, Scratch& tmp, const R* points, int n, const R* data_
   GI_TRY(tmp.alloc(&keys_tmp, (size_t)n));
   GI_TRY(tmp.alloc(&ids, (size_t)n));
   GI_TRY(tmp.alloc(&ids_tmp, (size_t)n));
-  GI_TRY(tmp.alloc(&hist, radix_hist_size(n)));
+  GI_TRY(tmp.alloc(&hist, radix_hist_size<unsigned>(n)));
   const PointsView<R> pv = points_n2(points, n, flags & GI_POINTS_ROWMAJOR);
   const int blocks = div_up(n, 256);
   esrg_key_kernel<R><<<blocks, 256, 0, st>>>(pv, n, x_axis, len_x, y_axis, len_y, spac, keys, ids);

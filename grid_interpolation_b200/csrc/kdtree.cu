@@ -141,7 +141,7 @@ int kd_build(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
   GI_TRY(scr.alloc(&keys, (size_t)n));
   GI_TRY(scr.alloc(&keys_tmp, (size_t)n));
   GI_TRY(scr.alloc(&ids_tmp, (size_t)n));
-  GI_TRY(scr.alloc(&hist, radix_hist_size(n)));
+  GI_TRY(scr.alloc(&hist, radix_hist_size<unsigned long long>(n)));
   GI_TRY(scr.alloc(&list[0], (size_t)n));
   GI_TRY(scr.alloc(&list[1], (size_t)n));
   GI_TRY(scr.alloc(&pos[0], (size_t)n));
