@@ -43,7 +43,20 @@ __global__ void __launch_bounds__(256) axis_inv_spacing_kernel(const R* __restri
   if (threadIdx.x == 0) inv[blockIdx.x] = R(1) / (delta / R(len - 1));
 }
 
-template <class R>
+// GI_BILINEAR_SEARCH_AXES (extension): the cell is found by bisection on the axis values instead of the
+// reference's mean-spacing formula (interpolation.f90:49-58,67,73), which is only right for equally spaced axes.
+// Returns the largest i in [0, len-2] with axis[i] <= p, or -1 if p is outside [axis[0], axis[len-1]).
+template <class R> __device__ __forceinline__ int axis_cell(const R* __restrict__ axis, int len, R p) {
+  if (!(p >= __ldg(axis)) || !(p < __ldg(axis + len - 1))) return -1;  // also NaN
+  int lo = 0, hi = len - 1;  // axis[lo] <= p < axis[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(axis + mid) <= p) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <class R, bool SEARCH>
 __global__ void __launch_bounds__(kThreads)
 bilinear_kernel(const R* __restrict__ x_axis, int len_x, const R* __restrict__ y_axis, int len_y,
                 const R* __restrict__ data, int64_t sy, int64_t sx, PointsView<R> pts, int64_t n,
@@ -63,12 +76,19 @@ bilinear_kernel(const R* __restrict__ x_axis, int len_x, const R* __restrict__ y
   }
 #pragma unroll
   for (int j = 0; j < kPts; ++j) {
-    const R fx = floor((px[j] - x_first) * dx_inv);                       // :67
-    const R fy = floor((py[j] - y_first) * dy_inv);                       // :73
-    // 1 <= ind < len in the reference's 1-based terms (:68,:74); NaN fails every comparison
-    ok[j] = fx >= R(0) && fx < R(len_x - 1) && fy >= R(0) && fy < R(len_y - 1);
-    ix[j] = ok[j] ? (int)fx : 0;
-    iy[j] = ok[j] ? (int)fy : 0;
+    if (SEARCH) {
+      const int cx = axis_cell(x_axis, len_x, px[j]), cy = axis_cell(y_axis, len_y, py[j]);
+      ok[j] = cx >= 0 && cy >= 0;
+      ix[j] = ok[j] ? cx : 0;
+      iy[j] = ok[j] ? cy : 0;
+    } else {
+      const R fx = floor((px[j] - x_first) * dx_inv);                     // :67
+      const R fy = floor((py[j] - y_first) * dy_inv);                     // :73
+      // 1 <= ind < len in the reference's 1-based terms (:68,:74); NaN fails every comparison
+      ok[j] = fx >= R(0) && fx < R(len_x - 1) && fy >= R(0) && fy < R(len_y - 1);
+      ix[j] = ok[j] ? (int)fx : 0;
+      iy[j] = ok[j] ? (int)fy : 0;
+    }
   }
   R d11[kPts], d12[kPts], d21[kPts], d22[kPts], xa[kPts], xb[kPts], ya[kPts], yb[kPts];
 #pragma unroll
@@ -114,7 +134,7 @@ __device__ __forceinline__ void pick_pair(const double (&v)[4], int o, double ne
 
 constexpr int kVecPts = 2;
 
-template <bool ROWMAJOR>
+template <bool ROWMAJOR, bool SEARCH>
 __global__ void __launch_bounds__(kThreads)
 bilinear_sector_kernel(const double* __restrict__ x_axis, int len_x, const double* __restrict__ y_axis, int len_y,
                        const double* __restrict__ data, PointsView<double> pts, int64_t n,
@@ -132,11 +152,18 @@ bilinear_sector_kernel(const double* __restrict__ x_axis, int len_x, const doubl
     const int64_t i = base + (int64_t)j * kThreads;
     if (i < n) { px[j] = pts.x(i); py[j] = pts.y(i); }
     else { px[j] = x_first; py[j] = y_first; }
-    const double fx = floor((px[j] - x_first) * dx_inv);                  // :67
-    const double fy = floor((py[j] - y_first) * dy_inv);                  // :73
-    ok[j] = fx >= 0.0 && fx < double(len_x - 1) && fy >= 0.0 && fy < double(len_y - 1);
-    ix[j] = ok[j] ? (int)fx : 0;
-    iy[j] = ok[j] ? (int)fy : 0;
+    if (SEARCH) {
+      const int cx = axis_cell(x_axis, len_x, px[j]), cy = axis_cell(y_axis, len_y, py[j]);
+      ok[j] = cx >= 0 && cy >= 0;
+      ix[j] = ok[j] ? cx : 0;
+      iy[j] = ok[j] ? cy : 0;
+    } else {
+      const double fx = floor((px[j] - x_first) * dx_inv);                // :67
+      const double fy = floor((py[j] - y_first) * dy_inv);                // :73
+      ok[j] = fx >= 0.0 && fx < double(len_x - 1) && fy >= 0.0 && fy < double(len_y - 1);
+      ix[j] = ok[j] ? (int)fx : 0;
+      iy[j] = ok[j] ? (int)fy : 0;
+    }
   }
   double fa[kVecPts][4], fb[kVecPts][4], xs[kVecPts][4], ys[kVecPts][4], fan[kVecPts], fbn[kVecPts], xn[kVecPts],
       yn[kVecPts];
@@ -175,12 +202,12 @@ bilinear_sector_kernel(const double* __restrict__ x_axis, int len_x, const doubl
 }
 
 template <class R> struct SectorPath {
-  static bool launch(const R*, int, const R*, int, const R*, PointsView<R>, int64_t, const R*, R*, bool,
+  static bool launch(const R*, int, const R*, int, const R*, PointsView<R>, int64_t, const R*, R*, bool, bool,
                      cudaStream_t) { return false; }
 };
 template <> struct SectorPath<double> {
   static bool launch(const double* x_axis, int len_x, const double* y_axis, int len_y, const double* data,
-                     PointsView<double> pv, int64_t n, const double* inv, double* out, bool rowmajor,
+                     PointsView<double> pv, int64_t n, const double* inv, double* out, bool rowmajor, bool search,
                      cudaStream_t st) {
     const int64_t pitch = rowmajor ? len_x : len_y;
     // aligned sector loads must stay inside the arrays: 32 B aligned bases, extents that are multiples of 4
@@ -189,12 +216,12 @@ template <> struct SectorPath<double> {
       return false;
     const int64_t blocks = (n + kThreads * kVecPts - 1) / (kThreads * kVecPts);
     if (blocks > 0x7fffffffLL) return false;
-    if (rowmajor)
-      bilinear_sector_kernel<true><<<(unsigned)blocks, kThreads, 0, st>>>(x_axis, len_x, y_axis, len_y, data, pv, n,
-                                                                        inv, out);
-    else
-      bilinear_sector_kernel<false><<<(unsigned)blocks, kThreads, 0, st>>>(x_axis, len_x, y_axis, len_y, data, pv,
-                                                                         n, inv, out);
+#define GI_LAUNCH_SECTOR(RM, SE)                                                                              \
+  bilinear_sector_kernel<RM, SE><<<(unsigned)blocks, kThreads, 0, st>>>(x_axis, len_x, y_axis, len_y, data, pv, n, \
+                                                                      inv, out)
+    if (rowmajor) { if (search) GI_LAUNCH_SECTOR(true, true); else GI_LAUNCH_SECTOR(true, false); }
+    else { if (search) GI_LAUNCH_SECTOR(false, true); else GI_LAUNCH_SECTOR(false, false); }
+#undef GI_LAUNCH_SECTOR
     return true;
   }
 };
@@ -210,11 +237,16 @@ int bilinear_points(const R* x_axis, int len_x, const R* y_axis, int len_y, cons
   if (num_points == 0) return GI_OK;
   const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
   const int64_t sy = rowmajor ? len_x : 1, sx = rowmajor ? 1 : len_y;
-  if (!SectorPath<R>::launch(x_axis, len_x, y_axis, len_y, data_in, pv, num_points, inv, out, rowmajor, st)) {
+  const bool search = flags & GI_BILINEAR_SEARCH_AXES;
+  if (!SectorPath<R>::launch(x_axis, len_x, y_axis, len_y, data_in, pv, num_points, inv, out, rowmajor, search, st)) {
     const int64_t blocks = (num_points + kThreads * kPts - 1) / (kThreads * kPts);
     GI_REQUIRE(blocks <= 0x7fffffffLL, "too many points for one launch");
-    bilinear_kernel<R><<<(unsigned)blocks, kThreads, 0, st>>>(x_axis, len_x, y_axis, len_y, data_in, sy, sx, pv,
-                                                             num_points, inv, out);
+    if (search)
+      bilinear_kernel<R, true><<<(unsigned)blocks, kThreads, 0, st>>>(x_axis, len_x, y_axis, len_y, data_in, sy, sx,
+                                                                     pv, num_points, inv, out);
+    else
+      bilinear_kernel<R, false><<<(unsigned)blocks, kThreads, 0, st>>>(x_axis, len_x, y_axis, len_y, data_in, sy, sx,
+                                                                      pv, num_points, inv, out);
   }
   GI_CUDA(cudaGetLastError());
   return GI_OK;

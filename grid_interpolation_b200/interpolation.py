@@ -267,11 +267,13 @@ def _use_out(call, out, shape, dtype, order):
 # -------------------------------------------------------------------------------------------------
 # the four drop-in entry points
 # -------------------------------------------------------------------------------------------------
-def bilinear(x_axis, y_axis, data_in, points, *, dtype=np.float64, out=None, sync=True):
+def bilinear(x_axis, y_axis, data_in, points, *, search_axes=False, dtype=np.float64, out=None, sync=True):
     """Regular grid -> scattered points (interpolation.f90:20-100).
 
     data_in has shape (len_y, len_x), points (num_points, 2); returns data_ip (num_points,).  Points outside
     [x_axis[0], x_axis[-1]) x [y_axis[0], y_axis[-1]) get -9999.0 (interpolation.f90:44,68-78).
+    ``search_axes=True`` (extension) finds the cell by bisection on the axis values, which is also right for axes
+    that are not equally spaced (the reference assumes they are, interpolation.f90:49-58).
     """
     rt, suf = _real(dtype)
     with _Call(data_in) as c:
@@ -285,6 +287,7 @@ def bilinear(x_axis, y_axis, data_in, points, *, dtype=np.float64, out=None, syn
         n = p.shape[0]
         res, res_ptr, _ = _use_out(c, out, (n,), rt, "C")
         flags = (GI_FIELD_ROWMAJOR if d.rowmajor else 0) | (GI_POINTS_ROWMAJOR if p.rowmajor else 0)
+        flags |= _lib.GI_BILINEAR_SEARCH_AXES if search_axes else 0
         st = getattr(lib(), "gi_bilinear_" + suf)(x.ptr, len_x, y.ptr, len_y, d.ptr, p.ptr, n, res_ptr, flags, c.mem, c.stream)
         c.finish(st, "bilinear", sync)
         return res

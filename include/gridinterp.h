@@ -71,6 +71,10 @@ typedef enum {
                                rule) instead of the reference's abs(diff) >= max d2 -> exact k nearest neighbours
                                even where the k-th d2 is < 1.  An extension (the reference README's to-do list);
                                results then differ from the reference's wherever its rule is too eager. */
+#define GI_BILINEAR_SEARCH_AXES 64 /* bilinear: find the cell by bisection on the axis values instead of the
+                                      reference's mean-spacing formula (interpolation.f90:49-58,67,73), which is
+                                      only right for equally spaced axes.  An extension: results differ
+                                      from the reference's wherever its formula picks the wrong cell. */
 #define GI_ESRG_REFERENCE_ORDER 16 /* idw_esrg_nearest: process every target in the reference's candidate order
                                       (debug).  Default: only targets with exactly equal neighbour distances,
                                       the only case in which that order changes the result. */

@@ -108,3 +108,29 @@ def test_non_contiguous_and_integer_inputs_are_converted_like_f2py(c1):
                                           simp, nbr)
     same(got, want2)
     assert want.shape == got.shape
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_bilinear_search_axes_extension(order):
+    """search_axes=True (extension): bisection on the axis values -> correct on non-uniform axes, where
+    the reference's mean-spacing formula picks wrong cells; checked against scipy."""
+    from scipy.interpolate import RegularGridInterpolator
+    rng = np.random.default_rng(21)
+    x = np.cumsum(rng.uniform(0.2, 3.0, 60)); y = np.cumsum(rng.uniform(0.2, 3.0, 44))     # strongly non-uniform
+    field = np.asarray(rng.normal(size=(44, 60)), order=order)
+    n = 20_000
+    pts = np.column_stack([rng.uniform(x[0] - 1, x[-1] + 1, n), rng.uniform(y[0] - 1, y[-1] + 1, n)])
+    got = ip.bilinear(x, y, field, pts, search_axes=True)
+    inside = (pts[:, 0] >= x[0]) & (pts[:, 0] < x[-1]) & (pts[:, 1] >= y[0]) & (pts[:, 1] < y[-1])
+    assert np.array_equal(got[~inside], np.full((~inside).sum(), -9999.0))
+    want = RegularGridInterpolator((y, x), field)(pts[inside][:, ::-1])
+    # the reference divides by the MEAN spacings (interpolation.f90:93): rescale to the true cell area
+    ix = np.searchsorted(x, pts[inside, 0], side="right") - 1; iy = np.searchsorted(y, pts[inside, 1], side="right") - 1
+    mean_area = ((x[-1] - x[0]) / (x.size - 1)) * ((y[-1] - y[0]) / (y.size - 1))
+    scale = mean_area / ((x[ix + 1] - x[ix]) * (y[iy + 1] - y[iy]))
+    np.testing.assert_allclose(got[inside] * scale, want, rtol=1e-9, atol=1e-11)
+    # on equally spaced axes both cell rules agree (up to points that sit on a node to within rounding)
+    xu = np.linspace(0.0, 59.0, 60); yu = np.linspace(0.0, 43.0, 44)
+    p2 = np.column_stack([rng.uniform(0, 59, n), rng.uniform(0, 43, n)])
+    np.testing.assert_allclose(ip.bilinear(xu, yu, field, p2, search_axes=True), ip.bilinear(xu, yu, field, p2),
+                               rtol=1e-12, atol=1e-12)
