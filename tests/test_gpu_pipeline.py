@@ -87,3 +87,38 @@ def test_default_band_size_is_restored(c1):
     """(sanity) with the default 32 MB bands the small cases run as one band and still match."""
     same(ip.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, 6),
          orc.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, 6))
+
+
+def test_host_calls_from_concurrent_threads(c1):
+    """ctypes releases the GIL (like f2py's `threadsafe`, interpolation.f90:30,118,213,311): four host threads run
+    the four operators at once, each on its own thread-local pipeline, and every result matches the oracle."""
+    import threading
+    want_b = orc.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices, c1.neighbours)
+    want_e = orc.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, 6)
+    want_k = orc.idw_kdtree(c1.points.T, c1.data_pts, c1.x_axis, c1.y_axis, 6)
+    want_l = orc.bilinear(c1.x_axis, c1.y_axis, want_e, c1.points)
+    jobs = {
+        "bary": (lambda: ip.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                                      c1.neighbours), want_b),
+        "esrg": (lambda: ip.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, 6), want_e),
+        "kd": (lambda: ip.idw_kdtree(c1.points.T, c1.data_pts, c1.x_axis, c1.y_axis, 6), want_k),
+        "bil": (lambda: ip.bilinear(c1.x_axis, c1.y_axis, want_e, c1.points), want_l),
+    }
+    errors = []
+
+    def worker(name):
+        fn, want = jobs[name]
+        try:
+            for _ in range(25):
+                if not np.array_equal(fn(), want):
+                    errors.append(f"{name}: result differs")
+                    return
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"{name}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(n,)) for n in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
