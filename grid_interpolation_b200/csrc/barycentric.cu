@@ -891,10 +891,12 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
       fill_from_walk(fa, was[b], pm, len_x, len_y);
       fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
       GI_CUDA(cudaGetLastError());
-      GI_CUDA(cudaEventRecord(pipe->computed[b], st));
-      GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
+      if (nb > 1) {  // (a single band needs no second stream: small calls are latency-bound)
+        GI_CUDA(cudaEventRecord(pipe->computed[b], st));
+        GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
+      }
       const int64_t o = (int64_t)(lo - bs0) * bnf, cnt = (int64_t)(hi - lo) * bnf;
-      return to_host(pipe->copy_out, data_ip + o, dout + o, (size_t)cnt);
+      return to_host(nb > 1 ? pipe->copy_out : st, data_ip + o, dout + o, (size_t)cnt);
     };
     for (int b = 0; b < nb; ++b) {
       if (start[b] < start[b + 1]) {
@@ -914,7 +916,7 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
     }
     if (start[nb - 1] < start[nb]) GI_TRY(fill_band(nb - 1));
     GI_TRY(flush_status(st, slot));
-    GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
+    if (nb > 1) GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
     const int status = read_status(st, true);
     if (status == GI_ERR_HALO && nb > 1) {  // a hull fill reached beyond the neighbouring band: one band sees all
       nb = 1;

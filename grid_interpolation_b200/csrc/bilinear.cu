@@ -298,36 +298,45 @@ int bilinear_host(const R* x_axis, int len_x, const R* y_axis, int len_y, const 
   GI_TRY(scr.alloc(&inv, 2));
   axis_inv_spacing_kernel<R><<<2, 256, 0, st>>>(dx, len_x, dy, len_y, inv);
   GI_CUDA(cudaGetLastError());
-  // the allocations above are ordered on the compute stream: the copy-in stream may touch them after this event
-  GI_CUDA(cudaEventRecord(pipe->computed[0], st));
-  GI_CUDA(cudaStreamWaitEvent(pipe->copy_in, pipe->computed[0], 0));
-  GI_TRY(to_device(scr, data_in, (size_t)len_x * len_y, &dd));  // (compute stream, overlaps the first point chunks)
   ph.mark("bilinear");
   const bool interleaved = flags & GI_POINTS_ROWMAJOR;
   const int nc = plan_bands(num_points, (int64_t)num_points * 3 * sizeof(R));
+  // a single chunk needs no extra streams (small calls are latency-bound)
+  cudaStream_t cin = nc > 1 ? pipe->copy_in : st, cout = nc > 1 ? pipe->copy_out : st;
+  if (nc > 1) {  // the allocations above are ordered on the compute stream: the copy-in stream waits for them
+    GI_CUDA(cudaEventRecord(pipe->computed[0], st));
+    GI_CUDA(cudaStreamWaitEvent(cin, pipe->computed[0], 0));
+  }
+  GI_TRY(to_device(scr, data_in, (size_t)len_x * len_y, &dd));  // (compute stream, overlaps the first point chunks)
   for (int c = 0; c < nc; ++c) {
     int64_t c0, c1;
     band_range(0, num_points, nc, c, 4096, &c0, &c1);
     if (c0 >= c1) continue;
     const size_t cnt = (size_t)(c1 - c0);
     if (interleaved) {
-      GI_CUDA(cudaMemcpyAsync(dp + 2 * c0, points + 2 * c0, 2 * cnt * sizeof(R), cudaMemcpyHostToDevice, pipe->copy_in));
+      GI_CUDA(cudaMemcpyAsync(dp + 2 * c0, points + 2 * c0, 2 * cnt * sizeof(R), cudaMemcpyHostToDevice, cin));
     } else {
-      GI_CUDA(cudaMemcpyAsync(dp + c0, points + c0, cnt * sizeof(R), cudaMemcpyHostToDevice, pipe->copy_in));
+      GI_CUDA(cudaMemcpyAsync(dp + c0, points + c0, cnt * sizeof(R), cudaMemcpyHostToDevice, cin));
       GI_CUDA(cudaMemcpyAsync(dp + num_points + c0, points + num_points + c0, cnt * sizeof(R), cudaMemcpyHostToDevice,
-                              pipe->copy_in));
+                              cin));
     }
-    GI_CUDA(cudaEventRecord(pipe->arrived[c], pipe->copy_in));
-    GI_CUDA(cudaStreamWaitEvent(st, pipe->arrived[c], 0));
+    if (nc > 1) {
+      GI_CUDA(cudaEventRecord(pipe->arrived[c], cin));
+      GI_CUDA(cudaStreamWaitEvent(st, pipe->arrived[c], 0));
+    }
     const PointsView<R> pv = interleaved ? PointsView<R>{dp + 2 * c0, 2, 1} : PointsView<R>{dp + c0, 1, num_points};
     GI_TRY(bilinear_points<R>(dx, len_x, dy, len_y, dd, pv, (int64_t)cnt, inv, dout + c0, flags, st));
-    GI_CUDA(cudaEventRecord(pipe->computed[c], st));
-    GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[c], 0));
-    GI_TRY(to_host(pipe->copy_out, data_ip + c0, dout + c0, cnt));
+    if (nc > 1) {
+      GI_CUDA(cudaEventRecord(pipe->computed[c], st));
+      GI_CUDA(cudaStreamWaitEvent(cout, pipe->computed[c], 0));
+    }
+    GI_TRY(to_host(cout, data_ip + c0, dout + c0, cnt));
   }
   ph.finish();
-  GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
-  GI_CUDA(cudaStreamSynchronize(pipe->copy_in));
+  if (nc > 1) {
+    GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
+    GI_CUDA(cudaStreamSynchronize(pipe->copy_in));
+  }
   GI_CUDA(cudaStreamSynchronize(st));
   return GI_OK;
 }

@@ -752,12 +752,14 @@ int esrg_run_banded(HostPipe* pipe, Scratch& scr, const Binned<R>& bins, int num
       GI_TRY(esrg_query_window<R>(scr, bins, num_points, dx, len_x, dy, len_y, grid_spac, k, row_begin, row_end,
                                   (int)b0, (int)b1, band_out, nullptr, nullptr, counters + 4 * b, false, flags,
                                   slot.dev, nullptr));
-    GI_CUDA(cudaEventRecord(pipe->computed[b], st));
-    GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
-    GI_TRY(to_host(pipe->copy_out, data_ip + (b0 - lo) * line, band_out, (size_t)((b1 - b0) * line)));
+    if (nb > 1) {  // (a single band needs no second stream: small calls are latency-bound)
+      GI_CUDA(cudaEventRecord(pipe->computed[b], st));
+      GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
+    }
+    GI_TRY(to_host(nb > 1 ? pipe->copy_out : st, data_ip + (b0 - lo) * line, band_out, (size_t)((b1 - b0) * line)));
   }
   GI_TRY(flush_status(st, slot));
-  GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
+  if (nb > 1) GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
   return GI_OK;
 }
 }  // namespace

@@ -427,12 +427,14 @@ int kd_run_banded(HostPipe* pipe, const KdTreeDev<R>& tree, const R* dx, int len
     else
       GI_TRY(kd_query_window<R>(tree, dx, len_x, dy, len_y, k, row_begin, row_end, (int)b0, (int)b1, band_out,
                                 nullptr, nullptr, nullptr, flags, slot.dev, st));
-    GI_CUDA(cudaEventRecord(pipe->computed[b], st));
-    GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
-    GI_TRY(to_host(pipe->copy_out, data_ip + (b0 - lo) * line, band_out, (size_t)((b1 - b0) * line)));
+    if (nb > 1) {  // (a single band needs no second stream: small calls are latency-bound)
+      GI_CUDA(cudaEventRecord(pipe->computed[b], st));
+      GI_CUDA(cudaStreamWaitEvent(pipe->copy_out, pipe->computed[b], 0));
+    }
+    GI_TRY(to_host(nb > 1 ? pipe->copy_out : st, data_ip + (b0 - lo) * line, band_out, (size_t)((b1 - b0) * line)));
   }
   GI_TRY(flush_status(st, slot));
-  GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
+  if (nb > 1) GI_CUDA(cudaStreamSynchronize(pipe->copy_out));
   return GI_OK;
 }
 }  // namespace
