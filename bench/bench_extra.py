@@ -22,7 +22,7 @@ def _kd_launches(n):
     levels = 0
     while (1 << levels) <= n:
         levels += 1
-    scan = 1 if n <= 4096 else (3 if n <= 4096 * 4096 else 5)
+    scan = 1 if n <= 16 * 4096 else (3 if n <= 16 * 4096 * 4096 else 5)
     return 2 * sort + 1 + levels * (2 + scan) + 1 + 1 + 1  # init, levels, gather, query, flush
 
 

@@ -65,6 +65,32 @@ scan_tile_kernel(const int* in, int* out, int64_t n, const int* __restrict__ off
   }
 }
 
+// up to kScanSmallTiles tiles by ONE block with a running carry: one launch instead of three for small inputs,
+// which are launch-latency-bound (the k-d build scans once per tree level)
+constexpr int kScanSmallTiles = 16;
+static __global__ void __launch_bounds__(kScanThreads)
+scan_small_kernel(const int* in, int* out, int64_t n) {
+  int carry = 0;
+  for (int64_t t0 = 0; t0 < n; t0 += kScanTile) {
+    const int64_t base = t0 + (int64_t)threadIdx.x * kScanPerThread;
+    int v[kScanPerThread];
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; ++i) {
+      v[i] = (base + i < n) ? in[base + i] : 0;
+      acc += v[i];
+    }
+    int total;
+    int run = block_exclusive_scan_256(acc, &total) + carry;
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; ++i) {
+      if (base + i < n) out[base + i] = run;
+      run += v[i];
+    }
+    carry += total;
+  }
+}
+
 // exclusive scan of in[0..n) into out[0..n); tile sums live in scratch memory
 inline int exclusive_scan_i32(Scratch& scr, const int* in, int* out, int64_t n) {
   cudaStream_t st = scr.stream();
@@ -72,6 +98,11 @@ inline int exclusive_scan_i32(Scratch& scr, const int* in, int* out, int64_t n) 
   const int64_t tiles = (n + kScanTile - 1) / kScanTile;
   if (tiles == 1) {
     scan_tile_kernel<<<1, kScanThreads, 0, st>>>(in, out, n, nullptr);
+    GI_CUDA(cudaGetLastError());
+    return GI_OK;
+  }
+  if (tiles <= kScanSmallTiles) {
+    scan_small_kernel<<<1, kScanThreads, 0, st>>>(in, out, n);
     GI_CUDA(cudaGetLastError());
     return GI_OK;
   }
