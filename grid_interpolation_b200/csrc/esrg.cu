@@ -11,8 +11,8 @@
 //             are sorted by it with a stable LSD radix sort (radix.cuh; 4 passes for 2^26 cells) -- stable, so
 //             the points of a cell stay in ascending id order exactly like the reference's fill
 //             (query_esrg.f90:72-89).  ONE int32 table of len_y*len_x entries then receives the END offset of
-//             every cell (start(c) = table[c-1]): the thread of sorted position p writes p+1 into the cells
-//             key[p] .. key[p+1]-1, long empty stretches cooperatively by the warp.  Coordinates, values and ids
+//             every cell (start(c) = table[c-1]): a warp writes the contiguous cell range its 32 sorted positions
+//             own, 32 consecutive cells at a time (esrg_table_kernel).  Coordinates, values and ids
 //             are gathered into cell order so the query reads them contiguously.  (The first version counted
 //             with 10 M atomics into the table, scanned all 67 M cells and scattered with atomics again:
 //             1.75 ms at C3.)
@@ -61,34 +61,32 @@ esrg_key_kernel(PointsView<R> pts, int n, const R* __restrict__ x_axis, int len_
   ids[i] = i;
 }
 
-// table[c] = number of points with key <= c (the END offset of cell c), from the sorted keys: position p owns the
-// cells key[p] .. key[p+1]-1 (the last position up to the last cell, position 0 also the cells before key[0])
+// table[c] = number of points with key <= c (the END offset of cell c), from the sorted keys.  The 32 positions
+// p0..p0+31 of a warp own the contiguous cell range [key[p0], key[p0+32]) (from cell 0 for the first warp, up to
+// `cells` for the last): the lanes write it 32 consecutive cells at a time, and the value of cell c is
+// p0 + (number of the warp's keys <= c), found by bisection over the lanes' keys with shuffles.  Fully coalesced
+// whatever the gaps between occupied cells (a thread-per-point fill wrote 27 B-strided words: 1 TB/s).
 __global__ void __launch_bounds__(256)
-esrg_table_kernel(const unsigned* __restrict__ keys, int n, int64_t cells, int* __restrict__ table) {
+esrg_table_kernel(const unsigned* __restrict__ keys, int n, long long cells, int* __restrict__ table) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  // every lane fills table[c0..c1) with val: short stretches by the lane itself, long ones (empty regions of the
-  // grid) by the whole warp
-  auto fill = [&](int64_t c0, int64_t c1, int val) {
-    constexpr int kOwn = 8;
-    const int64_t own_end = c0 + kOwn < c1 ? c0 + kOwn : c1;
-    for (int64_t c = c0; c < own_end; ++c) table[c] = val;
-    unsigned long_ones = __ballot_sync(0xffffffffu, c1 > own_end);
-    while (long_ones) {
-      const int src = __ffs(long_ones) - 1;
-      long_ones &= long_ones - 1;
-      const int64_t b0 = __shfl_sync(0xffffffffu, own_end, src), b1 = __shfl_sync(0xffffffffu, c1, src);
-      const int v = __shfl_sync(0xffffffffu, val, src);
-      for (int64_t c = b0 + lane; c < b1; c += 32) table[c] = v;
+  const int p0 = p - lane;
+  if (p0 >= n) return;  // whole warp
+  const long long key = p < n ? (long long)keys[p] : cells;  // non-decreasing over the lanes
+  const long long begin = p0 == 0 ? 0 : __shfl_sync(0xffffffffu, key, 0);
+  const long long end = p0 + 32 < n ? (long long)keys[p0 + 32] : cells;
+  for (long long c = begin + lane; __any_sync(0xffffffffu, c < end); c += 32) {
+    int lo = 0, hi = 32;  // first lane whose key is > c
+#pragma unroll
+    for (int step = 0; step < 6; ++step) {
+      const int mid = (lo + hi) >> 1;
+      const long long v = __shfl_sync(0xffffffffu, key, mid & 31);
+      if (lo < hi) {
+        if (v <= c) lo = mid + 1; else hi = mid;
+      }
     }
-  };
-  int64_t c0 = 0, c1 = 0;
-  if (p < n) {
-    c0 = keys[p];
-    c1 = p + 1 < n ? (int64_t)keys[p + 1] : cells;
+    if (c < end) table[c] = p0 + lo;
   }
-  if (blockIdx.x == 0 && threadIdx.x < 32) fill(0, p == 0 ? c0 : 0, 0);  // the cells before the first point
-  fill(c0, c1, p + 1);
 }
 
 template <class R> struct alignas(16) XY { R x, y; };
@@ -631,7 +629,7 @@ int esrg_bin(Scratch& keep, Scratch& tmp, const R* points, int n, const R* data_
   int passes = 1;
   while (passes < 4 && (cells - 1) >> (8 * passes)) ++passes;
   GI_TRY(radix_sort<unsigned>(keys, ids, keys_tmp, ids_tmp, hist, n, passes, st, &keys_sorted, &ids_sorted));
-  esrg_table_kernel<<<blocks, 256, 0, st>>>(keys_sorted, n, cells, b->table);
+  esrg_table_kernel<<<blocks, 256, 0, st>>>(keys_sorted, n, (long long)cells, b->table);
   esrg_gather_kernel<R><<<blocks, 256, 0, st>>>(pv, data_in, ids_sorted, n, b->sxy, data_in ? b->sval : nullptr,
                                                 b->sid);
   GI_CUDA(cudaGetLastError());
