@@ -16,14 +16,19 @@
 //             are gathered into cell order so the query reads them contiguously.  (The first version counted
 //             with 10 M atomics into the table, scanned all 67 M cells and scattered with atomics again:
 //             1.75 ms at C3.)
-//   query     one thread per grid target, two kernels:
-//             esrg_fast_kernel   The reference's result is "the k smallest d2 among the points of the
-//               (2L+1)^2 window, L = first level at which k points lie within r_L = spac*(L+1/2)"
-//               (query_esrg.f90:141,159-169,178-181); its candidate lists only decide the order
-//               among EQUAL d2.  So the fast kernel keeps no list at all: it scans frame after frame, keeps
-//               the k smallest d2 seen in registers and stops when the k-th is <= r_L^2.  A frame's top and
-//               bottom rows are contiguous runs of the CSR (key = iy*len_x + ix).  Whenever a candidate's d2
-//               equals a kept one (the only case in which processing order matters) the target is handed to
+//   query     three kernels:
+//             esrg_tile_kernel   (production, k <= 16) a warp owns 8 x 4 targets, stages the points of the
+//               tile's halo rectangle in shared memory and every lane selects its k+1 smallest 32-bit
+//               monotone keys with comparator networks -- see the comment above the kernel.
+//             esrg_fast_kernel   (k > 16, or more points per tile than can be staged) one thread per target.
+//               The reference's result is "the k smallest d2 among the points of the (2L+1)^2 window, L =
+//               first level at which k points lie within r_L = spac*(L+1/2)" (query_esrg.f90:141,159-169,
+//               178-181); its candidate lists only decide the order among EQUAL d2.  So this
+//               kernel keeps no list at all: it scans frame after frame, keeps the k smallest d2 seen in
+//               registers and stops when the k-th is <= r_L^2.  A frame's top and bottom rows are contiguous
+//               runs of the CSR (key = iy*len_x + ix).
+//             Whenever equal d2 (the only case in which the processing order matters) or ambiguous keys turn
+//             up, the target is handed to
 //             esrg_query_kernel  which follows the reference's processing order exactly (carried candidates
 //               first, then the frame in scan order, ties inserted before equal entries).  The reference's
 //               two fixed 1000-entry candidate lists (query_esrg.f90:119-121) are one small in-place
