@@ -28,14 +28,17 @@
 // reassociation) -- see oracle/Makefile.
 //
 // Parity pinning status (see DESIGN.md "Oracle"):
-//   * esrg kNN / cell binning, triangle walk, barycentric weights, hull fill:
-//     pinned against the reference's own executable Python twins
-//     (development/idw_interp_esrg_dev.py, development/triangle_walk_dev.py)
-//     through tests/golden/*.npz generated by tests/golden/make_golden.py.
-//   * k-d tree build/query and bilinear: the reference holds no golden vector,
-//     assertion or Python twin for them and no Fortran compiler exists in the
-//     build image -> "parity unpinned" by reference output; pinned only by
-//     line fidelity and by scipy cross-checks (tests/test_oracle_scipy.py).
+//   * ALL FOUR entry points and their search primitives (k-d tree build / query incl. the approximate prune
+//     regime, esrg cell binning / ring kNN, triangle walk + barycentric weights + hull fill, bilinear): pinned
+//     against the reference's own Fortran source, executed unmodified by oracle/f90interp.py (a small
+//     interpreter for the Fortran 90 subset the reference uses; no Fortran compiler exists in the build image)
+//     through tests/golden/f90_f64.npz / f90_f32.npz written by tests/golden/make_golden_f90.py --
+//     bit-identical indices and values in double and single precision (tests/test_oracle_f90_golden.py).
+//   * esrg kNN / cell binning, triangle walk, barycentric weights, hull fill: additionally pinned against the
+//     reference's own executable Python twins (development/idw_interp_esrg_dev.py,
+//     development/triangle_walk_dev.py) through tests/golden/{esrg,walk}_twin.npz (tests/golden/make_golden.py).
+//   * The interpreter is ours (it implements Fortran semantics, nothing about interpolation; its own semantics are
+//     unit-tested in tests/test_f90interp.py); a gfortran build of the reference would replace it as oracle/_ref.
 //
 // Defined divergences from the reference (each is UB or a hang there):
 //   * bilinear out-of-bounds: reference writes -9999.0 then falls through
