@@ -55,6 +55,17 @@ def c1(num_points=5000, seed=33):
                            num_nn=6, area_min=float(area_tri.min()))
 
 
+def digest(w):
+    """SHA-256 of a C1-style workload's inputs.  Golden fixtures that store outputs only keep this beside them; the
+    tests rebuild the seeded inputs and compare digests first, so an input mismatch cannot pass for a parity failure."""
+    import hashlib
+    h = hashlib.sha256()
+    for a in (w.points, w.data_pts, w.x_axis, w.y_axis, w.simplices, w.neighbours):
+        a = np.asarray(a)
+        h.update(np.ascontiguousarray(a.astype(np.int64) if a.dtype.kind in "iu" else a).tobytes())
+    return h.hexdigest()
+
+
 def _z(x, y, extent):
     s = 20.9 / extent
     return sin_mountains(x * s, y * s)

@@ -16,6 +16,7 @@ them bit for bit and tests/test_gpu_parity.py the CUDA library.
 Run in the build container only (needs /root/reference); takes about two minutes:
 
     python tests/golden/make_golden_f90.py        # rewrites tests/golden/f90_f64.npz, f90_f32.npz
+    python tests/golden/make_golden_f90.py --c1   # the reference's own 5 000-point case (fields only, ~10 min)
 """
 import os
 import sys
@@ -134,5 +135,41 @@ def main():
         print(f"{path}: {len(out)} arrays, {itp.calls} procedure calls interpreted")
 
 
+def c1_full():
+    """The reference's own test case at its own size (test_interpolation.py:54-93 with 5 000 points -> 132 x 79 grid,
+    num_nn = 6): the four fields only, double precision.  About ten minutes of interpretation."""
+    src = [open(os.path.join(REF, f)).read() for f in FILES]
+    R = np.float64
+    itp = Interpreter(src, R)
+    w = workloads.c1()
+    pts = farr(w.points, R); dat = w.data_pts.astype(R); x = w.x_axis.astype(R); y = w.y_axis.astype(R)
+    simp = farr(w.simplices, np.int64); nbr = farr(w.neighbours, np.int64)
+    out = {}
+    f = np.zeros((y.size, x.size), dtype=R, order="F")
+    itp.call("barycentric_interpolation", pts, pts.shape[0], dat, x, x.size, y, y.size, simp, nbr, simp.shape[0], f)
+    out["bary_field"] = f.copy()
+    print("barycentric done", itp.calls, flush=True)
+    f = np.zeros((y.size, x.size), dtype=R, order="F")
+    itp.call("idw_esrg_nearest", pts, pts.shape[0], dat, x, x.size, y, y.size, R(w.grid_spac), 6, f)
+    out["esrg_field"] = f.copy()
+    print("esrg done", itp.calls, flush=True)
+    f = np.zeros((y.size, x.size), dtype=R, order="F")
+    itp.call("idw_kdtree", farr(w.points.T, R), pts.shape[0], dat, x, x.size, y, y.size, 6, f)
+    out["kd_field"] = f.copy()
+    print("kd done", itp.calls, flush=True)
+    inside = ((w.points[:, 0] >= w.x_axis[0]) & (w.points[:, 0] < w.x_axis[-1]) &
+              (w.points[:, 1] >= w.y_axis[0]) & (w.points[:, 1] < w.y_axis[-1]))
+    bp = farr(w.points[inside], R)
+    res = np.zeros(bp.shape[0], R)
+    itp.call("bilinear", x, x.size, y, y.size, out["bary_field"], bp, bp.shape[0], res)
+    out.update(bil_inside=inside, bil_values=res, inputs_sha256=np.array(workloads.digest(w)))
+    path = os.path.join(HERE, "f90_c1_f64.npz")
+    np.savez_compressed(path, **out)
+    print(f"{path}: {itp.calls} procedure calls interpreted")
+
+
 if __name__ == "__main__":
-    main()
+    if "--c1" in sys.argv:
+        c1_full()
+    else:
+        main()

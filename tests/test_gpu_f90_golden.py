@@ -63,3 +63,17 @@ def test_barycentric(g, order):
     with ip.BarycentricPlan(z["points"], z["x_axis"], z["y_axis"], z["simplices"], z["neighbours"], order=order,
                             dtype=R) as plan:
         same(plan(z["data"]), z["bary_field"])
+
+
+def test_reference_test_case_at_full_size(golden_dir):
+    """The reference's own test case at its own size (test_interpolation.py:54-93: 5 000 points -> 132 x 79 grid,
+    num_nn = 6) against the Fortran source interpreted end to end (make_golden_f90.py --c1)."""
+    from grid_interpolation_b200 import workloads
+    z = np.load(os.path.join(golden_dir, "f90_c1_f64.npz"))
+    w = workloads.c1()
+    assert workloads.digest(w) == str(z["inputs_sha256"]), "seeded inputs differ from the ones the vectors were made from"
+    same(ip.barycentric_interpolation(w.points, w.data_pts, w.x_axis, w.y_axis, w.simplices, w.neighbours),
+         z["bary_field"])
+    same(ip.idw_esrg_nearest(w.points, w.data_pts, w.x_axis, w.y_axis, w.grid_spac, 6), z["esrg_field"])
+    same(ip.idw_kdtree(w.points.T, w.data_pts, w.x_axis, w.y_axis, 6), z["kd_field"])
+    same(ip.bilinear(w.x_axis, w.y_axis, z["bary_field"], w.points[z["bil_inside"]]), z["bil_values"])

@@ -60,3 +60,17 @@ def test_barycentric_matches_fortran_source(g):
     z, R = g
     same(orc.barycentric_interpolation(z["points"], z["data"], z["x_axis"], z["y_axis"], z["simplices"],
                                        z["neighbours"], dtype=R), z["bary_field"])
+
+
+def test_reference_test_case_at_full_size(golden_dir):
+    """The reference's own test case at its own size (test_interpolation.py:54-93: 5 000 points -> 132 x 79 grid,
+    num_nn = 6), Fortran source interpreted end to end (make_golden_f90.py --c1): the four fields bit for bit."""
+    from grid_interpolation_b200 import workloads
+    z = np.load(os.path.join(golden_dir, "f90_c1_f64.npz"))
+    w = workloads.c1()
+    assert workloads.digest(w) == str(z["inputs_sha256"]), "seeded inputs differ from the ones the vectors were made from"
+    same(orc.barycentric_interpolation(w.points, w.data_pts, w.x_axis, w.y_axis, w.simplices, w.neighbours),
+         z["bary_field"])
+    same(orc.idw_esrg_nearest(w.points, w.data_pts, w.x_axis, w.y_axis, w.grid_spac, 6), z["esrg_field"])
+    same(orc.idw_kdtree(w.points.T, w.data_pts, w.x_axis, w.y_axis, 6), z["kd_field"])
+    same(orc.bilinear(w.x_axis, w.y_axis, z["bary_field"], w.points[z["bil_inside"]]), z["bil_values"])
