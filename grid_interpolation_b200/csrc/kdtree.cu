@@ -13,8 +13,9 @@
 //           every segment the axis-sorted list already has the median in place, and the other list is
 //           stably partitioned around it with one device-wide prefix sum per level.  The result is an
 //           IMPLICIT tree: the node of segment [lo,hi) is element lo+(hi-lo+1)/2-1 of one array, its
-//           subtrees are the two sub-segments.  Coordinate ties are ordered by point id (the reference's
-//           quickselect order for ties depends on its swap history -- documented divergence).
+//           subtrees are the two sub-segments.  With tied coordinates the reference's tree depends on its
+//           quickselect's swap history instead: the build detects ties and evaluates the reference's Lomuto
+//           passes in parallel (kd_build_faithful below) -- same tree, node by node.
 //   query   one thread per grid target, explicit stack of deferred far branches (depth <= 32),
 //           register-resident sorted top-k (topk.cuh).  The far branch is taken iff
 //           abs(diff) < max d2 -- the reference's rule, which compares a distance with a squared distance
@@ -132,11 +133,220 @@ kd_gather_kernel(PointsView<R> pts, const R* __restrict__ data, const int* __res
   if (order_out) order_out[p] = i + 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Coordinate ties: the quickselect-faithful build.
+//
+// With tied coordinates the reference's tree is no longer determined by ranks: equal keys stay right of a Lomuto
+// pivot (kd_tree.f90:129), which tied element lands on the median and in which order a child receives its
+// sub-array depend on the swap history of every ancestor's quickselect (kd_tree.f90:97-155).  The tree must
+// then be built the way the reference builds it -- but a Lomuto pass is a deterministic permutation that can be
+// evaluated in parallel:
+//   * the elements < pivot end up at the front in encounter order (stable);
+//   * the elements >= pivot form a FIFO queue in positions [store, i): a later ">=" element is appended at the
+//     back, and every "<" element met after the first ">=" one (position i0) moves the queue's front to its back
+//     (the swap at :131-136).  From i0 on every loop iteration therefore appends exactly one item; item number s
+//     is appended by iteration e = i0 + s and is either the element found there, or -- if that element was "<" --
+//     the item popped by that swap, which is item number t = #("<" in [i0, e)) < s.  The queue finally holds items
+//     T .. P-1 (T = number of pops) in positions store .. hi-1, before the pivot is swapped in at `store` (:141-146).
+//   So the source of every destination follows from one prefix sum F over the "<" flags: walk s -> F[e] - F[i0]
+//   until an iteration with a ">=" element is reached (one hop per time the reference swapped that item).
+// Every unfinished node performs one pass per round (its own [ind_left, ind_right] range, its own axis), nodes
+// whose quickselect has converged hand their two sub-ranges to their children (:64-68), all in the same
+// launches; the array the rounds leave behind is the implicit tree the query reads.  Rounds ~ sum over levels of
+// the passes per quickselect (a few hundred for 1e6 points): ~10x slower than the rank-based build, used only
+// when a tie is detected (or GI_KD_FAITHFUL_BUILD asks for it).
+// ---------------------------------------------------------------------------------------------
+struct alignas(16) KdfNode {
+  int a_lo, a_hi;  // the quickselect's current [ind_left, ind_right] (0-based, inclusive)
+  int n_hi;        // last position of the node's sub-array (its first position is the node's id)
+  int depth;
+};
+
+// position i of the array as the pass sees it, i.e. after pivot and last element were exchanged (:119-124)
+__device__ __forceinline__ int kdf_virt(int i, int pidx, int hi) { return i == pidx ? hi : (i == hi ? pidx : i); }
+
+template <class R>
+__global__ void __launch_bounds__(256)
+kdf_init_kernel(PointsView<R> pts, int n, R* __restrict__ X, R* __restrict__ Y, int* __restrict__ ID,
+                int* __restrict__ nid, KdfNode* __restrict__ nodes) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  X[p] = pts.x(p); Y[p] = pts.y(p); ID[p] = p;
+  nid[p] = 0;
+  if (p == 0) nodes[0] = KdfNode{0, n - 1, n - 1, 0};
+}
+
+template <class R>
+__global__ void __launch_bounds__(256)
+kdf_flag_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __restrict__ nid,
+                const KdfNode* __restrict__ nodes, int n, int* __restrict__ flag) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int f = 0;
+  const int node = nid[p];
+  if (node >= 0) {
+    const KdfNode nd = nodes[node];
+    if (p >= nd.a_lo && p < nd.a_hi) {
+      const R* K = (nd.depth & 1) ? Y : X;                 // axis = mod(depth, 2)   (kd_tree.f90:45)
+      const int pidx = (nd.a_lo + nd.a_hi) >> 1;           // :115
+      f = K[p == pidx ? nd.a_hi : p] < K[pidx] ? 1 : 0;    // :129 (strict)
+    }
+  }
+  flag[p] = f;
+}
+
+// per node: i0 = first position of the pass whose element is not "<" (a_hi if there is none)
+__global__ void __launch_bounds__(256)
+kdf_first_ge_kernel(const int* __restrict__ nid, const KdfNode* __restrict__ nodes, const int* __restrict__ F, int n,
+                    int* __restrict__ first_ge) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int node = nid[p];
+  if (node < 0) return;
+  const KdfNode nd = nodes[node];
+  if (p != nd.a_hi || nd.a_lo == nd.a_hi) return;
+  const int base = F[nd.a_lo] - nd.a_lo;
+  int l = nd.a_lo, r = nd.a_hi;  // largest i with "all of [a_lo, i) are <"
+  while (l < r) {
+    const int mid = (l + r + 1) >> 1;
+    if (F[mid] - mid == base) l = mid; else r = mid - 1;
+  }
+  first_ge[node] = l;
+}
+
+template <class R>
+__global__ void __launch_bounds__(256)
+kdf_pass_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __restrict__ ID, int* __restrict__ nid,
+                const KdfNode* __restrict__ nodes, const int* __restrict__ flag, const int* __restrict__ F,
+                const int* __restrict__ first_ge, int n, R* __restrict__ X2, R* __restrict__ Y2,
+                int* __restrict__ ID2, KdfNode* __restrict__ nodes_next, int* __restrict__ alive) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int node = nid[p];
+  if (node < 0) { X2[p] = X[p]; Y2[p] = Y[p]; ID2[p] = ID[p]; return; }
+  const KdfNode nd = nodes[node];
+  const int lo = nd.a_lo, hi = nd.a_hi;
+  const int k = node + ((nd.n_hi - node + 2) >> 1) - 1;  // ind_median = (num_points + 1) / 2   (:54)
+  bool fin;
+  int nlo = lo, nhi = hi;
+  if (lo == hi) {                                        // :112
+    fin = true;
+    X2[p] = X[p]; Y2[p] = Y[p]; ID2[p] = ID[p];
+  } else {
+    const int base = F[lo];
+    const int store = lo + (F[hi] - base);               // :127-138
+    if (k < store) { fin = false; nhi = store - 1; }     // :149-153
+    else if (k > store) { fin = false; nlo = store + 1; }
+    else fin = true;
+    if (!fin && nlo == nhi) fin = true;                  // the next call would return at :112 (k == nlo)
+    if (p < lo || p > hi) {
+      X2[p] = X[p]; Y2[p] = Y[p]; ID2[p] = ID[p];
+    } else {
+      const int pidx = (lo + hi) >> 1;
+      if (p < hi && flag[p]) {                           // a "<" element: to the front, in encounter order
+        const int src = kdf_virt(p, pidx, hi), dst = lo + (F[p] - base);
+        X2[dst] = X[src]; Y2[dst] = Y[src]; ID2[dst] = ID[src];
+      }
+      if (p >= store) {                                  // destinations of the pivot and of the ">=" queue
+        int src;
+        if (p == store) src = pidx;                      // the pivot (:141-146)
+        else {
+          const int i0 = first_ge[node], f0 = F[i0];
+          int e = (p == hi) ? store : p;                 // the queue's front goes to the end (:141-146)
+          while (flag[e]) e = i0 + (F[e] - f0);
+          src = kdf_virt(e, pidx, hi);
+        }
+        X2[p] = X[src]; Y2[p] = Y[src]; ID2[p] = ID[src];
+      }
+    }
+  }
+  if (p == hi) {  // one thread per node writes the next state(s)
+    if (!fin) { nodes_next[node] = KdfNode{nlo, nhi, nd.n_hi, nd.depth}; *alive = 1; }
+    else {
+      if (k > node) { nodes_next[node] = KdfNode{node, k - 1, k - 1, nd.depth + 1}; *alive = 1; }          // :64-65
+      if (k < nd.n_hi) { nodes_next[k + 1] = KdfNode{k + 1, nd.n_hi, nd.n_hi, nd.depth + 1}; *alive = 1; }  // :66-68
+    }
+  }
+  if (fin) {
+    if (p == k) nid[p] = -1;      // :59-61 the node
+    else if (p > k) nid[p] = k + 1;
+  }
+}
+
+// 1 iff two neighbours of a sorted key list are equal (-0.0 and +0.0 count as equal, as `<` sees them)
+__global__ void __launch_bounds__(256)
+kd_tie_kernel(const unsigned long long* __restrict__ keys, int n, int* __restrict__ tie) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 >= n) return;
+  unsigned long long a = keys[i], b = keys[i + 1];
+  if (a == 0x7fffffffffffffffull) a = 0x8000000000000000ull;
+  if (b == 0x7fffffffffffffffull) b = 0x8000000000000000ull;
+  if (a == b) *tie = 1;
+}
+
+// exclusive scan with caller-provided tile sums (the rounds below scan a few hundred times)
+inline int kdf_scan(const int* in, int* out, int n, int* sums, cudaStream_t st) {
+  const int tiles = div_up(n, kScanTile);
+  if (tiles == 1) scan_tile_kernel<<<1, kScanThreads, 0, st>>>(in, out, n, nullptr);
+  else if (tiles <= kScanSmallTiles) scan_small_kernel<<<1, kScanThreads, 0, st>>>(in, out, n);
+  else {
+    scan_reduce_kernel<<<tiles, kScanThreads, 0, st>>>(in, n, sums);
+    if (tiles <= kScanTile) scan_tile_kernel<<<1, kScanThreads, 0, st>>>(sums, sums, tiles, nullptr);
+    else scan_small_kernel<<<1, kScanThreads, 0, st>>>(sums, sums, tiles);
+    scan_tile_kernel<<<tiles, kScanThreads, 0, st>>>(in, out, n, sums);
+  }
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+
+template <class R>
+int kd_build_faithful(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
+  cudaStream_t st = scr.stream();
+  GI_REQUIRE((int64_t)n <= (int64_t)kScanTile * kScanTile * kScanSmallTiles, "too many points");
+  R *X, *Y, *X2, *Y2;
+  int *ID, *ID2, *nid, *flag, *F, *first_ge, *sums, *alive;
+  KdfNode *nodes, *nodes_next;
+  GI_TRY(scr.alloc(&X, (size_t)n)); GI_TRY(scr.alloc(&Y, (size_t)n)); GI_TRY(scr.alloc(&ID, (size_t)n));
+  GI_TRY(scr.alloc(&X2, (size_t)n)); GI_TRY(scr.alloc(&Y2, (size_t)n)); GI_TRY(scr.alloc(&ID2, (size_t)n));
+  GI_TRY(scr.alloc(&nid, (size_t)n)); GI_TRY(scr.alloc(&flag, (size_t)n)); GI_TRY(scr.alloc(&F, (size_t)n));
+  GI_TRY(scr.alloc(&first_ge, (size_t)n));
+  GI_TRY(scr.alloc(&nodes, (size_t)n)); GI_TRY(scr.alloc(&nodes_next, (size_t)n));
+  GI_TRY(scr.alloc(&sums, (size_t)div_up(n, kScanTile)));
+  GI_TRY(scr.alloc(&alive, 1));
+  const int blocks = div_up(n, 256);
+  kdf_init_kernel<R><<<blocks, 256, 0, st>>>(pv, n, X, Y, ID, nid, nodes);
+  constexpr int kBatch = 8;  // rounds between two looks at the `alive` word
+  for (int64_t round = 0;; round += kBatch) {
+    GI_REQUIRE(round <= 4 * (int64_t)n + 64, "k-d build did not converge");
+    GI_CUDA(cudaMemsetAsync(alive, 0, sizeof(int), st));
+    for (int b = 0; b < kBatch; ++b) {
+      kdf_flag_kernel<R><<<blocks, 256, 0, st>>>(X, Y, nid, nodes, n, flag);
+      GI_TRY(kdf_scan(flag, F, n, sums, st));
+      kdf_first_ge_kernel<<<blocks, 256, 0, st>>>(nid, nodes, F, n, first_ge);
+      if (b == kBatch - 1) GI_CUDA(cudaMemsetAsync(alive, 0, sizeof(int), st));  // what the LAST round leaves
+      kdf_pass_kernel<R><<<blocks, 256, 0, st>>>(X, Y, ID, nid, nodes, flag, F, first_ge, n, X2, Y2, ID2,
+                                                 nodes_next, alive);
+      std::swap(X, X2); std::swap(Y, Y2); std::swap(ID, ID2); std::swap(nodes, nodes_next);
+    }
+    int h_alive = 0;
+    GI_CUDA(cudaMemcpyAsync(&h_alive, alive, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GI_CUDA(cudaStreamSynchronize(st));
+    if (!h_alive) break;
+  }
+  GI_CUDA(cudaGetLastError());
+  *order_dev = ID;
+  return GI_OK;
+}
+
 // builds the implicit tree; *order_dev (n ints, 0-based point ids in tree order) lives in scr
 template <class R>
-int kd_build(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
+int kd_build(Scratch& scr, PointsView<R> pv, int n, int flags, int** order_dev) {
   cudaStream_t st = scr.stream();
+  if (flags & GI_KD_FAITHFUL_BUILD) return kd_build_faithful<R>(scr, pv, n, order_dev);
   unsigned long long *keys, *keys_tmp;
+  int* tie;
+  GI_TRY(scr.alloc(&tie, 1));
+  GI_CUDA(cudaMemsetAsync(tie, 0, sizeof(int), st));
   int *list[2], *pos[2], *list_new, *pos_new, *seg_lo, *seg_hi, *seg_lo_new, *seg_hi_new, *flag, *ids_tmp, *hist;
   GI_TRY(scr.alloc(&keys, (size_t)n));
   GI_TRY(scr.alloc(&keys_tmp, (size_t)n));
@@ -157,7 +367,13 @@ int kd_build(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
     sort_keys_kernel<R><<<div_up(n, 256), 256, 0, st>>>(pv, n, axis, keys, list[axis]);
     unsigned long long* k_sorted; int* l_sorted;  // 8 passes: back in keys / list[axis]
     GI_TRY(radix_sort<unsigned long long>(keys, list[axis], keys_tmp, ids_tmp, hist, n, 8, st, &k_sorted, &l_sorted));
+    kd_tie_kernel<<<div_up(n, 256), 256, 0, st>>>(k_sorted, n, tie);
   }
+  // tied coordinates: the reference's tree depends on its quickselect's swap history (see kd_build_faithful)
+  int h_tie = 0;
+  GI_CUDA(cudaMemcpyAsync(&h_tie, tie, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GI_CUDA(cudaStreamSynchronize(st));
+  if (h_tie) return kd_build_faithful<R>(scr, pv, n, order_dev);
   const int blocks = div_up(n, 256);
   kd_init_kernel<<<blocks, 256, 0, st>>>(list[0], list[1], n, pos[0], pos[1], seg_lo, seg_hi);
   int levels = 0;
@@ -333,7 +549,7 @@ int kd_prepare(Scratch& keep, Scratch& tmp, const R* points, int num_points, con
   cudaStream_t st = tmp.stream();
   const PointsView<R> pv = points_2n(points, num_points, flags & GI_POINTS_ROWMAJOR);
   int* order_tmp;
-  GI_TRY(kd_build<R>(tmp, pv, num_points, &order_tmp));
+  GI_TRY(kd_build<R>(tmp, pv, num_points, flags, &order_tmp));
   GI_TRY(keep.alloc(&t->order, (size_t)num_points));
   GI_CUDA(cudaMemcpyAsync(t->order, order_tmp, sizeof(int) * (size_t)num_points, cudaMemcpyDeviceToDevice, st));
   GI_TRY(keep.alloc(&t->nodes, (size_t)num_points));
@@ -555,7 +771,7 @@ int kd_build_device(const R* points, int num_points, int32_t* order_out, int fla
   Scratch scr(st);
   const PointsView<R> pv = points_2n(points, num_points, flags & GI_POINTS_ROWMAJOR);
   int* order;
-  GI_TRY(kd_build<R>(scr, pv, num_points, &order));
+  GI_TRY(kd_build<R>(scr, pv, num_points, flags, &order));
   kd_gather_kernel<R><<<div_up(num_points, 256), 256, 0, st>>>(pv, nullptr, order, num_points, nullptr, nullptr,
                                                                order_out);
   GI_CUDA(cudaGetLastError());

@@ -560,15 +560,17 @@ class EsrgPlan(_Plan):
 # -------------------------------------------------------------------------------------------------
 # parity / debug exports of the search structures
 # -------------------------------------------------------------------------------------------------
-def kd_build(points):
-    """Implicit canonical k-d tree (kd_tree.f90:30-95): 1-based point ids in tree order (see gridinterp.h)."""
+def kd_build(points, faithful=False):
+    """Implicit k-d tree (kd_tree.f90:30-95): 1-based point ids in tree order (see gridinterp.h).  faithful=True
+    forces the build that evaluates the reference's quickselect passes (chosen automatically when coordinates tie)."""
     with _Call(points) as c:
         p = c.arg(points, _F64, 2, "points")
         if p.shape[0] != 2:
             raise ValueError("points must have shape (2, num_points)")
         n = p.shape[1]
         order, ptr, _ = c.out((n,), np.int32, "C")
-        st = lib().gi_kd_build_f64(p.ptr, n, ptr, GI_POINTS_ROWMAJOR if p.rowmajor else 0, c.mem, c.stream)
+        flags = (GI_POINTS_ROWMAJOR if p.rowmajor else 0) | (_lib.GI_KD_FAITHFUL_BUILD if faithful else 0)
+        st = lib().gi_kd_build_f64(p.ptr, n, ptr, flags, c.mem, c.stream)
         c.finish(st, "kd_build")
         return order
 

@@ -75,6 +75,10 @@ typedef enum {
                                       reference's mean-spacing formula (interpolation.f90:49-58,67,73), which is
                                       only right for equally spaced axes.  An extension: results differ
                                       from the reference's wherever its formula picks the wrong cell. */
+#define GI_KD_FAITHFUL_BUILD 128 /* idw_kdtree / gi_kd_build: build the tree by evaluating the reference's quickselect
+                                    passes (kd_tree.f90:97-155) instead of by ranks.  The two trees are identical
+                                    unless coordinates tie; the library detects ties and switches by itself, the
+                                    flag forces the slower build (debug / tests). */
 #define GI_ESRG_REFERENCE_ORDER 16 /* idw_esrg_nearest: process every target in the reference's candidate order
                                       (debug).  Default: only targets with exactly equal neighbour distances,
                                       the only case in which that order changes the result. */

@@ -130,6 +130,37 @@ def main():
         itp.call("bilinear", xn, xn.size, yn, yn.size, fld, bq, 200, res2)
         out.update(biln_x_axis=xn, biln_y_axis=yn, biln_field=fld, biln_points=bq, biln_values=res2)
 
+        # ---- tie-heavy lattice: points on a spacing-2 lattice (shuffled), targets on the spacing-1 grid over the same
+        # extent + one ring -> targets ON vertices and edges (walk margin / path dependence, triangle_walk.f90:148-151),
+        # exact distance ties (kd_tree.f90:222-231 stable, query_esrg.f90:234-240 new-before-equal), zero distances
+        # (nearest-copy branches interpolation.f90:164-169,260-265), equal split keys (kd_tree.f90:129); then the
+        # same lattice with 20 exact duplicates for the two IDW paths
+        from scipy.spatial import Delaunay
+        gx, gy = np.meshgrid(np.arange(0, 21, 2.0), np.arange(0, 15, 2.0))
+        lp = np.column_stack([gx.ravel(), gy.ravel()])
+        rng = np.random.default_rng(7)
+        lp = lp[rng.permutation(len(lp))]
+        ld = rng.normal(size=len(lp)).astype(R)
+        lx = np.arange(-1.0, 22.0, 1.0).astype(R); ly = np.arange(-1.0, 16.0, 1.0).astype(R)
+        tri = Delaunay(lp)
+        ls = tri.simplices.astype(np.int64) + 1; ln = tri.neighbors.astype(np.int64) + 1
+        f = np.zeros((ly.size, lx.size), dtype=R, order="F")
+        itp.call("barycentric_interpolation", farr(lp, R), len(lp), ld, lx, lx.size, ly, ly.size, farr(ls, np.int64),
+                 farr(ln, np.int64), len(ls), f)
+        out.update(lat_points=farr(lp, R), lat_data=ld, lat_x_axis=lx, lat_y_axis=ly, lat_simplices=ls.astype(np.int32),
+                   lat_neighbours=ln.astype(np.int32), lat_bary_field=f)
+        dp = np.vstack([lp, lp[rng.integers(0, len(lp), 20)]])
+        dd = rng.normal(size=len(dp)).astype(R)
+        out.update(dup_points=farr(dp, R), dup_data=dd)
+        for name, P, D in (("lat", lp, ld), ("dup", dp, dd)):
+            for k in (1, 4, 6):
+                f = np.zeros((ly.size, lx.size), dtype=R, order="F")
+                itp.call("idw_kdtree", farr(P.T, R), len(P), D, lx, lx.size, ly, ly.size, k, f)
+                out[f"{name}_kd_field_k{k}"] = f
+                f = np.zeros((ly.size, lx.size), dtype=R, order="F")
+                itp.call("idw_esrg_nearest", farr(P, R), len(P), D, lx, lx.size, ly, ly.size, R(1.0), k, f)
+                out[f"{name}_esrg_field_k{k}"] = f
+
         path = os.path.join(HERE, f"f90_{tag}.npz")
         np.savez_compressed(path, **out)
         print(f"{path}: {len(out)} arrays, {itp.calls} procedure calls interpreted")

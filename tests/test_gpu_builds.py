@@ -13,8 +13,8 @@ def same(a, b):
     assert np.array_equal(np.asarray(a), np.asarray(b))
 
 
-def check_tree(points_2n):
-    order = ip.kd_build(np.ascontiguousarray(points_2n)) - 1
+def check_tree(points_2n, faithful=False):
+    order = ip.kd_build(np.ascontiguousarray(points_2n), faithful=faithful) - 1
     ref = orc.kd_build(points_2n)
     stack = [(ref.root, 0, order.size)]
     while stack:                                   # oracle pointer tree vs implicit array (kd_tree.f90:54-68)
@@ -38,6 +38,39 @@ def test_kd_build_negative_and_tiny_coordinates():
     rng = np.random.default_rng(3)
     pts = np.concatenate([rng.normal(0.0, 1e-200, (2, 700)), rng.normal(0.0, 1e200, (2, 700)),
                           rng.uniform(-1.0, 1.0, (2, 700))], axis=1)
+    check_tree(pts)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 33, 513, 4097, 100_003])
+def test_kd_build_quickselect_passes_on_distinct_coordinates(n):
+    """the build that evaluates the reference's Lomuto passes in parallel gives the same (canonical) tree"""
+    rng = np.random.default_rng(n)
+    check_tree(rng.uniform(-50.0, 1000.0, (2, n)), faithful=True)
+
+
+@pytest.mark.parametrize("case", ["lattice", "few_values", "all_equal", "one_axis_constant", "duplicates", "zeros",
+                                  "float32_cast"])
+def test_kd_build_tied_coordinates(case):
+    """Tied coordinates: the reference's tree depends on its quickselect's swap history (equal keys stay right of the
+    pivot, kd_tree.f90:129); the library detects the ties and reproduces the passes -- node by node the oracle's tree."""
+    rng = np.random.default_rng(5)
+    if case == "lattice":
+        gx, gy = np.meshgrid(np.arange(0, 61, 2.0), np.arange(0, 45, 2.0))
+        pts = np.stack([gx.ravel(), gy.ravel()])[:, rng.permutation(gx.size)]
+    elif case == "few_values":
+        pts = rng.integers(0, 5, (2, 3000)).astype(np.float64)
+    elif case == "all_equal":
+        pts = np.full((2, 777), 3.25)
+    elif case == "one_axis_constant":
+        pts = np.stack([rng.uniform(0, 9, 2500), np.full(2500, -1.5)])
+    elif case == "duplicates":
+        base = rng.uniform(0.0, 100.0, (2, 5000))
+        pts = np.concatenate([base, base[:, rng.integers(0, 5000, 1500)]], axis=1)[:, rng.permutation(6500)]
+    elif case == "zeros":
+        pts = np.where(rng.uniform(size=(2, 900)) < 0.5, 0.0, -0.0) * np.where(rng.uniform(size=(2, 900)) < 0.1, 1.0, 1.0)
+        pts[:, ::7] = rng.normal(size=pts[:, ::7].shape)
+    else:
+        pts = rng.uniform(0.0, 4095.0, (2, 200_000)).astype(np.float32).astype(np.float64)
     check_tree(pts)
 
 

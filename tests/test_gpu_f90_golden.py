@@ -77,3 +77,19 @@ def test_reference_test_case_at_full_size(golden_dir):
     same(ip.idw_esrg_nearest(w.points, w.data_pts, w.x_axis, w.y_axis, w.grid_spac, 6), z["esrg_field"])
     same(ip.idw_kdtree(w.points.T, w.data_pts, w.x_axis, w.y_axis, 6), z["kd_field"])
     same(ip.bilinear(w.x_axis, w.y_axis, z["bary_field"], w.points[z["bil_inside"]]), z["bil_values"])
+
+
+def test_lattice_ties(g):
+    """Tie-heavy lattice (targets on vertices and edges: the walk's margin band and path dependence; exact distance
+    ties, zero distances, equal split keys) and the same lattice with exact duplicate points."""
+    z, R = g
+    for order in ("F", "C"):
+        same(ip.barycentric_interpolation(z["lat_points"], z["lat_data"], z["lat_x_axis"], z["lat_y_axis"],
+                                          z["lat_simplices"], z["lat_neighbours"], order=order, dtype=R),
+             z["lat_bary_field"])
+    for name in ("lat", "dup"):
+        P, D = z[name + "_points"], z[name + "_data"]
+        for k in (1, 4, 6):
+            same(ip.idw_kdtree(P.T, D, z["lat_x_axis"], z["lat_y_axis"], k, dtype=R), z[f"{name}_kd_field_k{k}"])
+            same(ip.idw_esrg_nearest(P, D, z["lat_x_axis"], z["lat_y_axis"], 1.0, k, dtype=R),
+                 z[f"{name}_esrg_field_k{k}"])

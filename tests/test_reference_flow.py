@@ -10,7 +10,7 @@ from scipy.spatial import KDTree
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("num_points", [5_000, 100_000])
+@pytest.mark.parametrize("num_points", [5_000, 100_000, 500_000])   # 500 000 = the script's default (:54)
 def test_test_interpolation_flow(num_points):
     from interpolation import interpolation as ip_fortran          # test_interpolation.py:27
     from grid_interpolation_b200 import workloads
