@@ -141,6 +141,21 @@ template <class R> struct EsrgArgs {
   int stats;              // update counters[0..2] (debug: one atomic per target)
 };
 
+// Smallest level L >= from whose radius is not exceeded by d2, i.e. the first level at which the reference accepts
+// a deferred point with this d2: NOT (d2 > (spac*(L+0.5))**2), the radius evaluated as the reference does
+// (query_esrg.f90:141,181,230).  Used once a target's frames have left the grid: no cell is added any more and
+// nothing changes until the growing radius reaches the nearest deferred point (points clamped into the border
+// cells from far outside the grid), so the levels in between are skipped instead of iterated.
+template <class R> __device__ __forceinline__ int esrg_level_reaching(R spac, R d2, int from) {
+  const double est = sqrt((double)d2) / (double)spac - 0.5;
+  int L = est > 2.0e9 ? 2000000000 : (est > 0.0 ? (int)est : 0);
+  L = max(L - 1, from);
+  auto r2 = [&](int l) { const R rad = spac * (R(l) + R(0.5)); return rad * rad; };
+  while (L > from && !(d2 > r2(L - 1))) --L;
+  while (d2 > r2(L) && L < 2000000000) ++L;
+  return L;
+}
+
 template <class R, int KC>
 __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
   const TargetWindow<R>& w = a.win;
@@ -166,11 +181,13 @@ __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
   long long cells_scanned = 0;
 
   R radius_sq = R(0), radius_sq_prev = R(0);
+  R dmin_deferred = Consts<R>::huge();  // smallest d2 deferred at the current level
   // One candidate (query_esrg.f90:158-169 / :229-240).  `fresh` = first time this point is seen (frame ==
   // level); otherwise it is a re-scanned inner-frame point that counts only if it was deferred so far.
   auto consider = [&](int pos, R dist_sq, bool fresh) {
     if (!fresh && !(dist_sq > radius_sq_prev)) return;   // already consumed at an earlier level
     if (dist_sq > radius_sq) {                            // defer
+      dmin_deferred = dist_sq < dmin_deferred ? dist_sq : dmin_deferred;
       if (!listfree) {
         if (n_list < kListCap) { list_pos[n_list] = pos; list_d2[n_list] = dist_sq; ++n_list; }
         else { listfree = true; ++overflows; }
@@ -218,14 +235,16 @@ __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
   };
 
   int level = 0;
-  const int level_cap = len_x + len_y;
+  // beyond this level the frame lies outside the grid: every cell has been scanned
+  const int level_full = max(max(ix, len_x - 1 - ix), max(iy, len_y - 1 - iy));
   for (;;) {
     const R rad = a.spac * (R(level) + R(0.5));                           // :141,:181
     radius_sq_prev = radius_sq;
     radius_sq = rad * rad;
+    dmin_deferred = Consts<R>::huge();
     if (listfree) {
       // exact list-free mode: inner frames first (the order the deferred list would have), then the new one
-      for (int l = 0; l < level; ++l) scan_frame(l, false);
+      for (int l = 0; l < min(level, level_full + 1); ++l) scan_frame(l, false);
     } else {
       // carried (deferred) candidates first, compacting in place (:184-185,:227-233)
       const int n_old = n_list;
@@ -233,14 +252,22 @@ __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
       for (int i = 0; i < n_old; ++i) {
         const int pos = list_pos[i];
         const R dist_sq = list_d2[i];
-        if (dist_sq > radius_sq) { list_pos[n_list] = pos; list_d2[n_list] = dist_sq; ++n_list; }
+        if (dist_sq > radius_sq) {
+          list_pos[n_list] = pos; list_d2[n_list] = dist_sq; ++n_list;
+          dmin_deferred = dist_sq < dmin_deferred ? dist_sq : dmin_deferred;
+        }
         else if (dist_sq < tk.dlast) { tk.template insert<true>(dist_sq, pos); found = min(found + 1, a.k); }
       }
     }
-    scan_frame(level, true);
+    if (level <= level_full) scan_frame(level, true);
     if (found == a.k) break;                                              // :178,:243
     ++level;
-    if (level > level_cap) { raise_status(a.status, GI_ERR_TOO_FEW_POINTS); break; }
+    if (level > level_full) {
+      // The reference keeps incrementing the level (:178-181) until the radius reaches its deferred points; the
+      // host checked num_points >= k, so that happens.  (No deferred point at all: NaN coordinates -- stop.)
+      if (!(dmin_deferred < Consts<R>::huge())) { raise_status(a.status, GI_ERR_TOO_FEW_POINTS); break; }
+      level = esrg_level_reaching(a.spac, dmin_deferred, level);
+    }
   }
 
   // IDW (interpolation.f90:260-274): distances are square-rooted first (query_esrg.f90:247)
@@ -320,7 +347,7 @@ __global__ void __launch_bounds__(128) esrg_fast_kernel(const EsrgArgs<R> a) {
 
   int level = 0;
   long long cells_scanned = 0;
-  const int level_cap = len_x + len_y;
+  const int level_full = max(max(ix, len_x - 1 - ix), max(iy, len_y - 1 - iy));  // last frame that touches the grid
   for (;;) {
     if (level == 0) {
       const int c = iy * len_x + ix;
@@ -344,7 +371,10 @@ __global__ void __launch_bounds__(128) esrg_fast_kernel(const EsrgArgs<R> a) {
     const R rad = a.spac * (R(level) + R(0.5));                           // :141,:181
     if (!(dmax > rad * rad)) break;                                       // k points within r_L: :178,:243
     ++level;
-    if (level > level_cap) { raise_status(a.status, GI_ERR_TOO_FEW_POINTS); break; }
+    if (level > level_full) {  // every cell scanned: the k smallest are final, the reference only grows its radius
+      level = esrg_level_reaching(a.spac, dmax, level);
+      break;
+    }
   }
   if (tie) {  // equal distances: the reference's processing order decides -> exact kernel
     a.todo[atomicAdd((unsigned long long*)a.todo_count, 1ull)] = lin;
@@ -501,7 +531,6 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
   unsigned next = 0xffffffffu;
   bool hand_over = false;
   int H = h0;
-  const int level_cap = len_x + len_y;
   for (;;) {
     const R rad = a.spac * (R(H) + R(0.5));                               // :141,:181
     const R r2 = rad * rad;
@@ -563,8 +592,10 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
     }
     // ---- 3. grow? -----------------------------------------------------------------------------------
     if (__all_sync(0xffffffffu, key[M - 1] != 0xffffffffu)) break;        // k points within r_H: :178,:243
+    // the rectangle already holds every point of the grid (neighbours clamped in from far outside): a larger H
+    // adds nothing but radius -- the exact kernel jumps to the level the reference stops at
+    if (rx0 == 0 && ry0 == 0 && rx1 == len_x - 1 && ry1 == len_y - 1) { hand_over = true; break; }
     H += 2;
-    if (H > level_cap) { raise_status(a.status, GI_ERR_TOO_FEW_POINTS); hand_over = true; break; }
   }
   if (hand_over) {
     if (active) a.todo[atomicAdd((unsigned long long*)a.todo_count, 1ull)] = lin;

@@ -423,17 +423,19 @@ int nearest_neighbours_esrg(const Real* points, int num_points, const int* index
 
   while (num_nn_found != num_nn) {                                          // :178
     level = level + 1;                                                      // :180-181
-    if (level > len_x + len_y) return ORC_TOO_FEW_POINTS;                   // reference: infinite loop
+    // (terminates: the caller checked num_points >= num_nn, and every point is in some cell -- points far outside
+    //  the grid are clamped into the border cells and accepted once the radius has grown to them)
     radius_sq = grid_spac * (Real(level) + Real(0.5f));
     radius_sq = radius_sq * radius_sq;
     points_cons = points_cons_next;                                         // :184-185
-    for (int i = -level; i <= level; i += 2 * level)                        // :186-203 (y-axis)
+    const bool frame_in_grid = level <= std::max(len_x, len_y);             // else: every cell index out of range
+    for (int i = -level; frame_in_grid && i <= level; i += 2 * level)       // :186-203 (y-axis)
       for (int j = -level; j <= level; ++j) {
         const int iy = ind_y + i, ix = ind_x + j;
         if (ix < 1 || ix > len_x || iy < 1 || iy > len_y) continue;
         gather_cell(iy, ix);
       }
-    for (int j = -level; j <= level; j += 2 * level)                        // :206-223 (x-axis)
+    for (int j = -level; frame_in_grid && j <= level; j += 2 * level)       // :206-223 (x-axis)
       for (int i = -level + 1; i <= level - 1; ++i) {
         const int iy = ind_y + i, ix = ind_x + j;
         if (ix < 1 || ix > len_x || iy < 1 || iy > len_y) continue;

@@ -161,6 +161,22 @@ def main():
                 itp.call("idw_esrg_nearest", farr(P, R), len(P), D, lx, lx.size, ly, ly.size, R(1.0), k, f)
                 out[f"{name}_esrg_field_k{k}"] = f
 
+        # ---- a small grid among far-away points (sparse stations around a local grid): most points are clamped into
+        # the border cells (query_esrg.f90:44-57) and the ring search keeps growing its radius after its frames have
+        # left the grid (:178-181) until it reaches them
+        rng = np.random.default_rng(48)
+        fx = (-4.75 + np.arange(5)).astype(R); fy = (2.5 + np.arange(7)).astype(R)
+        fp = np.column_stack([rng.uniform(-17.0, 11.0, 14), rng.uniform(-15.0, 27.0, 14)]).astype(R)
+        fd = rng.normal(size=14).astype(R)
+        out.update(far_points=farr(fp, R), far_data=fd, far_x_axis=fx, far_y_axis=fy)
+        for k in (1, 7, 13):
+            f = np.zeros((fy.size, fx.size), dtype=R, order="F")
+            itp.call("idw_esrg_nearest", farr(fp, R), 14, fd, fx, fx.size, fy, fy.size, R(1.0), k, f)
+            out[f"far_esrg_field_k{k}"] = f
+            f = np.zeros((fy.size, fx.size), dtype=R, order="F")
+            itp.call("idw_kdtree", farr(fp.T, R), 14, fd, fx, fx.size, fy, fy.size, k, f)
+            out[f"far_kd_field_k{k}"] = f
+
         path = os.path.join(HERE, f"f90_{tag}.npz")
         np.savez_compressed(path, **out)
         print(f"{path}: {len(out)} arrays, {itp.calls} procedure calls interpreted")

@@ -78,6 +78,49 @@ def test_esrg_exactly_k_points_and_points_outside_grid():
     same(idx, oi); same(ptr[:-1].reshape(7, 10) + 1, op)
 
 
+def _far_case(k, spread):
+    rng = np.random.default_rng(int(spread) + k)
+    x = 100.0 + 0.5 * np.arange(40.0); y = -7.0 + 0.5 * np.arange(30.0)
+    pts = np.column_stack([x.mean() + rng.uniform(-1, 1, 300) * 20.0 * spread,
+                           y.mean() + rng.uniform(-1, 1, 300) * 15.0 * spread])
+    return x, y, pts, rng.normal(size=300)
+
+
+@pytest.mark.parametrize("k", [3, 8, 14, 20, 32])
+@pytest.mark.parametrize("spread", [3.0, 40.0])
+def test_esrg_points_far_outside_the_grid(k, spread):
+    """Sparse points around a small grid: most are clamped into the border cells and are accepted only when the
+    search radius has grown far beyond the grid (query_esrg.f90:178-181 keeps incrementing the level).  Tile kernel
+    (k <= 16), per-thread kernel (k > 16) and the reference-order kernel; neighbour ids and max level included."""
+    x, y, pts, dat = _far_case(k, spread)
+    want, w = orc.idw_esrg_nearest(pts, dat, x, y, 0.5, k, debug=True)
+    for ref_order in (False, True):
+        got, g = ip.idw_esrg_nearest_ex(pts, dat, x, y, 0.5, k, debug=True, reference_order=ref_order)
+        same(g.nn_index, np.moveaxis(w.nn_index, 0, -1)); same(got, want)
+        if ref_order:
+            assert g.level_max == w.level_max
+
+
+@pytest.mark.parametrize("k", [8, 20])
+def test_esrg_points_extremely_far_outside_the_grid(k):
+    """~1e6 ring levels between the grid and the points: the levels are skipped, not iterated.  (The line-faithful
+    oracle would iterate them, so the check is a brute-force exact kNN with the reference's IDW expression.)"""
+    x, y, pts, dat = _far_case(k, 3.0e4)
+    xx, yy = np.meshgrid(x, y)
+    d2 = (xx[..., None] - pts[:, 0]) ** 2 + (yy[..., None] - pts[:, 1]) ** 2       # query_esrg.f90:147-148
+    nn = np.argsort(d2, axis=-1, kind="stable")[..., :k]
+    dist = np.sqrt(np.take_along_axis(d2, nn, -1))
+    num = np.zeros_like(xx); den = np.zeros_like(xx)
+    for i in range(k):                                                              # interpolation.f90:267-273
+        num = num + dat[nn[..., i]] / dist[..., i]
+        den = den + 1.0 / dist[..., i]
+    for ref_order in (False, True):
+        got, g = ip.idw_esrg_nearest_ex(pts, dat, x, y, 0.5, k, debug=True, reference_order=ref_order)
+        same(g.nn_index, nn + 1); same(got, num / den)
+        if ref_order:
+            assert g.level_max > 100_000
+
+
 def test_kdtree_fewer_points_than_k():
     """Slots that never fill keep the sentinel distance and an undefined id in the reference
     (interpolation.f90:151,159); both sides define id 0 / value 0 for them."""

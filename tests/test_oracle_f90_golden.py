@@ -88,3 +88,14 @@ def test_lattice_ties_match_fortran_source(g):
             same(orc.idw_kdtree(P.T, D, z["lat_x_axis"], z["lat_y_axis"], k, dtype=R), z[f"{name}_kd_field_k{k}"])
             same(orc.idw_esrg_nearest(P, D, z["lat_x_axis"], z["lat_y_axis"], 1.0, k, dtype=R),
                  z[f"{name}_esrg_field_k{k}"])
+
+
+def test_far_away_points_match_fortran_source(g):
+    """A small grid among far-away points: they are clamped into the border cells and the ring search grows its radius
+    long after its frames have left the grid (query_esrg.f90:44-57,178-181)."""
+    z, R = g
+    for k in (1, 7, 13):
+        same(orc.idw_esrg_nearest(z["far_points"], z["far_data"], z["far_x_axis"], z["far_y_axis"], 1.0, k, dtype=R),
+             z[f"far_esrg_field_k{k}"])
+        same(orc.idw_kdtree(z["far_points"].T, z["far_data"], z["far_x_axis"], z["far_y_axis"], k, dtype=R),
+             z[f"far_kd_field_k{k}"])
