@@ -99,11 +99,13 @@ template <class R> struct alignas(16) XY { R x, y; };
 // order[p] = 0-based id of the point at cell-order position p; sid_out (optional) receives the 1-based ids
 template <class R>
 __global__ void __launch_bounds__(256)
-esrg_gather_kernel(PointsView<R> pts, const R* __restrict__ data, const int* __restrict__ order, int n,
-                   XY<R>* __restrict__ sxy, R* __restrict__ sval, int* __restrict__ sid_out) {
+esrg_gather_kernel(PointsView<R> pts, const R* __restrict__ data, const int* __restrict__ order,
+                   const unsigned* __restrict__ keys_sorted, int n, XY<R>* __restrict__ sxy, R* __restrict__ sval,
+                   int* __restrict__ sid_out, unsigned* __restrict__ scell) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const int i = order[p];
+  if (scell) scell[p] = keys_sorted[p];
   if (sxy) { XY<R> v; pts.xy(i, v.x, v.y); sxy[p] = v; }
   if (sval) sval[p] = __ldg(data + i);
   if (sid_out) sid_out[p] = i + 1;  // 1-based ids like index_of_pts
@@ -128,6 +130,7 @@ template <class R> struct EsrgArgs {
   const XY<R>* sxy;       // coordinates in cell order
   const R* sval;          // values in cell order
   const int* sid;         // 1-based point ids in cell order
+  const unsigned* scell;  // cell (iy*len_x + ix) of every point in cell order
   int len_x, len_y, k;
   R spac;
   R* out;                 // window-shaped
@@ -421,7 +424,7 @@ __global__ void __launch_bounds__(128) esrg_fast_kernel(const EsrgArgs<R> a) {
 // runs its own cell loops with its own trip counts.  Here a WARP owns a tile of 8 x 4 targets (8 along the
 // contiguous output axis) and works in lock step:
 //   1. stage   the points of the tile's halo rectangle (tile grown by H cells on every side; one CSR run per
-//              grid row, one lane per run) are copied to shared memory (at most 255 of them);
+//              grid row, one lane per run) are copied to shared memory (at most 223 of them);
 //   2. scan    every lane computes its d2 to every staged point (shared-memory broadcast, no divergence) and
 //              turns it into a 32-bit KEY = (fixed-point d2) << 8 | staged index, or 0xffffffff beyond r_H =
 //              spac*(H+1/2), the radius the lane's own (2H+1)^2 window is guaranteed to cover.  The fixed-point
@@ -437,12 +440,13 @@ __global__ void __launch_bounds__(128) esrg_fast_kernel(const EsrgArgs<R> a) {
 //              winners is recomputed from the staged coordinates (same expression, same bits) and the IDW sum
 //              is taken in that order.  Equal fixed-point values (exact ties, where the reference's candidate
 //              order decides, or distances closer than the resolution: ~1e-5 of the targets) and tiles with
-//              more than 255 staged points send the target to the exact kernel.
+//              more than 223 staged points send the target to the exact kernel.
 // The result is the exact k nearest neighbours, which is what the reference computes (see esrg_fast_kernel).
 // The first tile version kept per-lane candidate lists in shared memory and selected with k+1 minimum-
 // extraction passes: 112 warp instructions per target, 31 KB of shared memory per 2 warps (15.1 ms at C3).
 // ---------------------------------------------------------------------------------------------
-constexpr int kStageCap = 255;  // staged points per tile: the staged index is the low byte of a key
+constexpr int kStageCap = 223;  // staged points per tile: the staged index is the low byte of a key; 224 x (16 + 4 + 2) B
+                                // per warp keeps 10 CTAs of 4 warps on an SM
 constexpr int kTileWarps = 4;
 
 __device__ __forceinline__ unsigned lo_word(double x) { return (unsigned)__double2loint(x); }
@@ -499,8 +503,13 @@ template <int M> __device__ __forceinline__ void merge_keys(unsigned (&a)[M], co
 // M = largest supported k.  The k live slots of key[] are the TOP ones (slots below hold 0 and stay 0), so the
 // k-th smallest key sits in the compile-time slot M-1 for every run-time k; `next` is the (k+1)-th smallest.
 template <class R, int M>
-__global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const EsrgArgs<R> a, int h0) {
+#ifndef GI_ESRG_TILE_MINB
+#define GI_ESRG_TILE_MINB 10
+#endif
+__global__ void __launch_bounds__(32 * kTileWarps, GI_ESRG_TILE_MINB) esrg_tile_kernel(const EsrgArgs<R> a, int h0) {
   __shared__ XY<R> s_xy[kTileWarps][kStageCap + 1];
+  __shared__ unsigned short s_cell[kTileWarps][kStageCap + 1];  // cell of a staged point inside the halo rectangle:
+                                                                // column - rx0 (low byte), row - ry0 (high byte)
   __shared__ int s_pos[kTileWarps][kStageCap + 1];
   const TargetWindow<R>& w = a.win;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -531,6 +540,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
   unsigned next = 0xffffffffu;
   bool hand_over = false;
   int H = h0;
+  unsigned tcell = 0;  // the target's own cell inside the halo rectangle, packed like s_cell
   for (;;) {
     const R rad = a.spac * (R(H) + R(0.5));                               // :141,:181
     const R r2 = rad * rad;
@@ -538,12 +548,13 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
     const int r2_exp = (__double2hiint((double)r2) >> 20) & 0x7ff;        // biased exponent of r2 (> 0)
     const double magic = __hiloint2double(min(r2_exp + 30, 2046) << 20, 0);
     // ---- 1. stage: one CSR run per grid row of the halo rectangle ----------------------------------
-    const int rx0 = max(tx0 - H, 0), rx1 = min(tx1 + H, len_x - 1);
-    const int ry0 = max(ty0 - H, 0), ry1 = min(ty1 + H, len_y - 1);
-    const int nrows = ry1 - ry0 + 1;
+    const int rx0 = max(tx0 - H, 0), ry0 = max(ty0 - H, 0);
+    tcell = (unsigned)(ix - rx0) | ((unsigned)(iy - ry0) << 8);
+    const int rx1 = min(tx1 + H, len_x - 1), ry1 = min(ty1 + H, len_y - 1);
+    const int nrows = ry1 - ry0 + 1, ncols = rx1 - rx0 + 1;
+    const int row = (ry0 + min(lane, nrows - 1)) * len_x;
     int p0 = 0, n = 0;
     if (lane < nrows) {
-      const int row = (ry0 + lane) * len_x;
       const int c0 = row + rx0;
       p0 = c0 > 0 ? __ldg(a.table + c0 - 1) : 0;
       n = __ldg(a.table + row + rx1) - p0;
@@ -556,11 +567,12 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
     }
     const int total = __shfl_sync(0xffffffffu, off, 31);
     off -= n;
-    if (nrows > 32 || total > kStageCap) { hand_over = true; break; }     // dense cluster: exact kernel
+    if (nrows > 32 || ncols > 255 || total > kStageCap) { hand_over = true; break; }  // dense cluster: exact kernel
     __syncwarp();
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n; ++i) {  // every staged point remembers its cell inside the rectangle (see 4.)
       s_xy[wid][off + i] = a.sxy[p0 + i];
       s_pos[wid][off + i] = p0 + i;
+      s_cell[wid][off + i] = (unsigned short)((__ldg(a.scell + p0 + i) - (unsigned)(row + rx0)) | (lane << 8));
     }
     __syncwarp();
     // ---- 2. scan ------------------------------------------------------------------------------------
@@ -602,7 +614,17 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
     return;
   }
   // ---- 4. resolve -----------------------------------------------------------------------------------
+  // The reference stops at the first level L whose (2L+1)^2 window holds k points within r_L and returns the k
+  // nearest of THOSE (query_esrg.f90:178-243); the winners below come from the larger halo rectangle.  They are
+  // the reference's result iff all of them lie inside the window of L* = the first level with r_L^2 >= the k-th
+  // winner's d2 (no fewer than k points are within any smaller radius, and a subset's k smallest that are also the
+  // superset's k smallest are the same points).  In exact arithmetic that always holds -- a point outside the
+  // window is farther away than r_L -- but a point ON a cell border can be binned one cell further out and still
+  // have a rounded distance <= r_L, and axes that are not exactly x(1) + i*spac shift the windows against the
+  // distances; so it is checked, in cell indices, and the rare violations go to the exact kernel.
   bool ambiguous = false;
+  unsigned cheb = 0;  // per byte: max |winner cell - target cell| (columns, rows)
+  R dk2 = R(0);
   R numerator = R(0), denominator = R(0), first_val = R(0), first_dist = R(0);
 #pragma unroll
   for (int j = 0; j < M; ++j) {
@@ -611,8 +633,10 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
       const int e = key[j] & 0xff;
       const XY<R> q = s_xy[wid][e];
       const int pos = s_pos[wid][e];
+      cheb = __vmaxu4(cheb, __vabsdiffu4(s_cell[wid][e], tcell));
       const R ddx = cx - q.x, ddy = cy - q.y;
       const R d2 = ddx * ddx + ddy * ddy;                                 // :147-148
+      if (j == M - 1) dk2 = d2;
       // IDW (interpolation.f90:260-274): distances are square-rooted first (query_esrg.f90:247)
       const R dist = sqrt(d2);
       const R v = __ldg(a.sval + pos);
@@ -625,6 +649,11 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
       }
     }
   }
+  const int reach = (int)max(cheb & 0xffu, cheb >> 8);
+  if (reach > 0) {  // all winners inside the window of L*  <=>  r_(reach-1)^2 < d2 of the k-th winner
+    const R rad = a.spac * (R(reach - 1) + R(0.5));
+    ambiguous |= !(dk2 > rad * rad);
+  }
   if (!active) return;
   if (ambiguous) {  // equal (fixed-point) distances: the reference's candidate order may decide
     a.todo[atomicAdd((unsigned long long*)a.todo_count, 1ull)] = lin;
@@ -636,6 +665,7 @@ __global__ void __launch_bounds__(32 * kTileWarps, 10) esrg_tile_kernel(const Es
 template <class R> struct Binned {
   int* table;
   int* sid;
+  unsigned* scell;
   XY<R>* sxy;
   R* sval;
 };
@@ -648,6 +678,7 @@ int esrg_bin(Scratch& keep, Scratch& tmp, const R* points, int n, const R* data_
   GI_REQUIRE(cells < (int64_t)0x7fffffff, "grid has more than 2^31 cells");
   GI_TRY(keep.alloc(&b->table, (size_t)cells));
   GI_TRY(keep.alloc(&b->sid, (size_t)n));
+  GI_TRY(keep.alloc(&b->scell, (size_t)n));
   GI_TRY(keep.alloc(&b->sxy, (size_t)n));
   b->sval = nullptr;
   if (want_values) GI_TRY(keep.alloc(&b->sval, (size_t)n));
@@ -666,8 +697,8 @@ int esrg_bin(Scratch& keep, Scratch& tmp, const R* points, int n, const R* data_
   while (passes < 4 && (cells - 1) >> (8 * passes)) ++passes;
   GI_TRY(radix_sort<unsigned>(keys, ids, keys_tmp, ids_tmp, hist, n, passes, st, &keys_sorted, &ids_sorted));
   esrg_table_kernel<<<blocks, 256, 0, st>>>(keys_sorted, n, (long long)cells, b->table);
-  esrg_gather_kernel<R><<<blocks, 256, 0, st>>>(pv, data_in, ids_sorted, n, b->sxy, data_in ? b->sval : nullptr,
-                                                b->sid);
+  esrg_gather_kernel<R><<<blocks, 256, 0, st>>>(pv, data_in, ids_sorted, keys_sorted, n, b->sxy,
+                                                data_in ? b->sval : nullptr, b->sid, b->scell);
   GI_CUDA(cudaGetLastError());
   return GI_OK;
 }
@@ -690,7 +721,7 @@ int esrg_query_window(Scratch& scr, const Binned<R>& b, int num_points, const R*
   const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
   a.win = rowmajor ? TargetWindow<R>{x_axis, y_axis, len_x, len_y, col0, col1, row0, row1, 0}
                    : TargetWindow<R>{y_axis, x_axis, len_y, len_x, row0, row1, col0, col1, 1};
-  a.table = b.table; a.sxy = b.sxy; a.sval = b.sval; a.sid = b.sid;
+  a.table = b.table; a.sxy = b.sxy; a.sval = b.sval; a.sid = b.sid; a.scell = b.scell;
   a.len_x = len_x; a.len_y = len_y; a.k = k; a.spac = grid_spac;
   a.out = out; a.nn_index = nn_index; a.nn_dist2 = nn_dist2;
   a.counters = counters; a.stats = stats ? 1 : 0; a.status = status;
@@ -706,7 +737,7 @@ int esrg_query_window(Scratch& scr, const Binned<R>& b, int num_points, const R*
   const double density = (double)num_points / ((double)len_x * (double)len_y);
   int h0 = 1;
   while (h0 < 12 && 3.141592653589793 * (h0 + 0.5) * (h0 + 0.5) * density < 1.5 * k + 6.0) ++h0;
-  // the tile kernel stages at most 255 points per tile; very dense inputs go straight to the per-thread kernel
+  // the tile kernel stages at most kStageCap points per tile; very dense inputs go straight to the per-thread kernel
   const bool tiles_fit = (8.0 + 2 * h0) * (4.0 + 2 * h0) * density < 0.6 * kStageCap;
   if (k <= 16 && tiles_fit) {
     const int64_t tiles = (int64_t)div_up(a.win.nf(), 8) * div_up(a.win.ns(), 4);

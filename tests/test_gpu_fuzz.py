@@ -1,0 +1,81 @@
+"""Differential fuzz of the CUDA library against the oracle (GPU): random small problems of every flavour the
+interpreted Fortran source was fuzzed with against the oracle -- both precisions, odd spacings, clustered points,
+points on grid nodes and cell borders (duplicates, exact ties), points far outside the grid, rounded coordinates,
+k from 1 to num_points -- all four entry points, bit for bit."""
+import numpy as np
+import pytest
+from scipy.spatial import Delaunay
+
+pytestmark = pytest.mark.gpu
+
+from grid_interpolation_b200 import interpolation as ip  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+def same(a, b, what):
+    assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), what
+
+
+def run_trials(seed, trials, n_max, lx_max, ly_max):
+    rng = np.random.default_rng(1000 + seed)
+    for trial in range(trials):
+        R = np.float64 if rng.uniform() < 0.6 else np.float32
+        n = int(rng.integers(3, n_max))
+        mode = int(rng.integers(0, 5))
+        lx = int(rng.integers(2, lx_max)); ly = int(rng.integers(2, ly_max))
+        spac = float(rng.choice([1.0, 0.5, 2.0, 0.37]))
+        x = (rng.uniform(-5, 5) + spac * np.arange(lx)).astype(R); y = (rng.uniform(-5, 5) + spac * np.arange(ly)).astype(R)
+        ex = float(x[-1] - x[0]); ey = float(y[-1] - y[0])
+        if mode == 0:
+            pts = np.column_stack([rng.uniform(x[0] - spac, x[-1] + spac, n), rng.uniform(y[0] - spac, y[-1] + spac, n)])
+        elif mode == 1:       # clustered: hull well inside the grid, deep hull fill
+            pts = np.column_stack([rng.normal(x[0] + ex / 2, ex / 8, n), rng.normal(y[0] + ey / 2, ey / 8, n)])
+        elif mode == 2:       # on grid nodes and cell borders: duplicates, exact ties, zero distances
+            pts = np.column_stack([rng.choice(x, n) + rng.choice([0, 0, spac / 2], n),
+                                   rng.choice(y, n) + rng.choice([0, 0, spac / 2], n)])
+        elif mode == 3:       # mostly far outside the grid
+            pts = np.column_stack([rng.uniform(x[0] - 3 * ex, x[-1] + 3 * ex, n), rng.uniform(y[0] - 3 * ey, y[-1] + 3 * ey, n)])
+        else:                 # rounded coordinates: coordinate ties
+            pts = np.round(np.column_stack([rng.uniform(x[0], x[-1], n), rng.uniform(y[0], y[-1], n)]), 1)
+        pts = pts.astype(R).astype(np.float64)
+        dat = rng.normal(size=n).astype(R)
+        k = int(rng.integers(1, min(n, 9) + 1)) if rng.uniform() < 0.8 else min(n, 32)
+        tag = f"seed {seed} trial {trial}: {R.__name__} mode {mode} n {n} k {k} grid {lx}x{ly} spac {spac}"
+
+        want, w = orc.idw_kdtree(pts.T, dat, x, y, k, dtype=R, debug=True)
+        got, g = ip.idw_kdtree_ex(pts.T, dat, x, y, k, debug=True, dtype=R)
+        same(g.nn_index, np.moveaxis(w.nn_index, 0, -1), "kd ids " + tag); same(got, want, "kd " + tag)
+
+        want, w = orc.idw_esrg_nearest(pts, dat, x, y, spac, k, dtype=R, debug=True)
+        got, g = ip.idw_esrg_nearest_ex(pts, dat, x, y, spac, k, debug=True, dtype=R)
+        same(g.nn_index, np.moveaxis(w.nn_index, 0, -1), "esrg ids " + tag); same(got, want, "esrg " + tag)
+
+        if mode != 2:
+            tri = Delaunay(pts)
+            simp = (tri.simplices + 1).astype(np.int32); nbr = (tri.neighbors + 1).astype(np.int32)
+            # (fewer triangles than points -- tiny or duplicated inputs: the reference's start-triangle loop reads out
+            #  of bounds, interpolation.f90:347; oracle and library both stop at the last triangle)
+            try:
+                want = orc.barycentric_interpolation(pts, dat, x, y, simp, nbr, dtype=R)
+            except RuntimeError:      # no grid node inside the hull: the reference's fill never ends -- both report
+                with pytest.raises(RuntimeError):
+                    ip.barycentric_interpolation(pts, dat, x, y, simp, nbr, dtype=R)
+            else:
+                same(ip.barycentric_interpolation(pts, dat, x, y, simp, nbr, dtype=R), want, "barycentric " + tag)
+
+        fld = np.asfortranarray(rng.normal(size=(ly, lx)).astype(R))
+        q = np.column_stack([rng.uniform(x[0], x[-1] - 1e-3, 60), rng.uniform(y[0], y[-1] - 1e-3, 60)])
+        q[:10, 0] = rng.choice(x[:-1], 10); q[5:15, 1] = rng.choice(y[:-1], 10)
+        q = q.astype(R)
+        same(ip.bilinear(x, y, fld, q, dtype=R), orc.bilinear(x, y, fld, q, dtype=R), "bilinear " + tag)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_small(seed):
+    run_trials(seed, 12, 400, 40, 30)
+
+
+@pytest.mark.parametrize("seed", range(100, 108))
+def test_fuzz_medium(seed):
+    """tens of thousands of points, grids of a few hundred nodes per side: several CTAs / tiles / sort tiles per call"""
+    run_trials(seed, 3, 30_000, 300, 250)
