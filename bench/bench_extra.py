@@ -18,7 +18,7 @@ from grid_interpolation_b200 import workloads  # noqa: E402
 
 def _kd_launches(n):
     """Kernel launches of one idw_kdtree call (mirrors kdtree.cu: two radix sorts + level-synchronous build)."""
-    sort = 1 + 8 * 3  # keys + 8 passes x (histogram, scan, scatter)
+    sort = 1 + 8 * 3 + 1  # keys + 8 passes x (histogram, scan, scatter) + tie detection
     levels = 0
     while (1 << levels) <= n:
         levels += 1
