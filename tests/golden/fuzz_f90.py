@@ -20,7 +20,7 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
     R = np.float64 if rng.uniform()<0.6 else np.float32
     itp=Interpreter(src,R)
     n=int(rng.integers(3,120))
-    mode=rng.integers(0,5)
+    mode=rng.integers(0,6)
     lx=int(rng.integers(2,14)); ly=int(rng.integers(2,12))
     spac=float(rng.choice([1.0,0.5,2.0,0.37]))
     x=(rng.uniform(-5,5)+spac*np.arange(lx)).astype(R); y=(rng.uniform(-5,5)+spac*np.arange(ly)).astype(R)
@@ -29,6 +29,10 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
     elif mode==1: pts=np.column_stack([rng.normal(x[0]+ex/2,ex/8,n),rng.normal(y[0]+ey/2,ey/8,n)])   # clustered, hull inside grid
     elif mode==2: pts=np.column_stack([rng.choice(x,n)+rng.choice([0,0,spac/2],n),rng.choice(y,n)+rng.choice([0,0,spac/2],n)])  # on nodes / cell borders (duplicates)
     elif mode==3: pts=np.column_stack([rng.uniform(x[0]-3*ex,x[-1]+3*ex,n),rng.uniform(y[0]-3*ey,y[-1]+3*ey,n)])  # mostly outside
+    elif mode==5:   # unique lattice nodes / half steps: targets ON vertices and edges (margin band, path dependence)
+        gx,gy=np.meshgrid(x[0]+0.5*spac*np.arange(2*lx-1),y[0]+0.5*spac*np.arange(2*ly-1))
+        allp=np.column_stack([gx.ravel(),gy.ravel()]); sel=rng.permutation(len(allp))[:max(min(n,len(allp)),4)]
+        pts=allp[sel]; n=len(pts)
     else: pts=np.round(np.column_stack([rng.uniform(x[0],x[-1],n),rng.uniform(y[0],y[-1],n)]),1)
     pts=pts.astype(R).astype(np.float64)
     dat=rng.normal(size=n).astype(R)

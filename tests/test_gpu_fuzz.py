@@ -21,7 +21,7 @@ def run_trials(seed, trials, n_max, lx_max, ly_max):
     for trial in range(trials):
         R = np.float64 if rng.uniform() < 0.6 else np.float32
         n = int(rng.integers(3, n_max))
-        mode = int(rng.integers(0, 5))
+        mode = int(rng.integers(0, 6))
         lx = int(rng.integers(2, lx_max)); ly = int(rng.integers(2, ly_max))
         spac = float(rng.choice([1.0, 0.5, 2.0, 0.37]))
         x = (rng.uniform(-5, 5) + spac * np.arange(lx)).astype(R); y = (rng.uniform(-5, 5) + spac * np.arange(ly)).astype(R)
@@ -35,6 +35,10 @@ def run_trials(seed, trials, n_max, lx_max, ly_max):
                                    rng.choice(y, n) + rng.choice([0, 0, spac / 2], n)])
         elif mode == 3:       # mostly far outside the grid
             pts = np.column_stack([rng.uniform(x[0] - 3 * ex, x[-1] + 3 * ex, n), rng.uniform(y[0] - 3 * ey, y[-1] + 3 * ey, n)])
+        elif mode == 5:       # unique lattice nodes / half steps: targets ON vertices and edges (margin band, path dependence)
+            gx, gy = np.meshgrid(x[0] + 0.5 * spac * np.arange(2 * lx - 1), y[0] + 0.5 * spac * np.arange(2 * ly - 1))
+            allp = np.column_stack([gx.ravel(), gy.ravel()])
+            pts = allp[rng.permutation(len(allp))[:max(min(n, len(allp)), 4)]]; n = len(pts)
         else:                 # rounded coordinates: coordinate ties
             pts = np.round(np.column_stack([rng.uniform(x[0], x[-1], n), rng.uniform(y[0], y[-1], n)]), 1)
         pts = pts.astype(R).astype(np.float64)
