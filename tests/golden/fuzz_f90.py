@@ -24,6 +24,8 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
     lx=int(rng.integers(2,14)); ly=int(rng.integers(2,12))
     spac=float(rng.choice([1.0,0.5,2.0,0.37]))
     x=(rng.uniform(-5,5)+spac*np.arange(lx)).astype(R); y=(rng.uniform(-5,5)+spac*np.arange(ly)).astype(R)
+    if rng.uniform()<0.3:   # axes that are not exactly x(1) + i*spac: the ring windows no longer match the radii
+        x=(x+rng.uniform(-0.2,0.2,lx).astype(R)*R(spac)).astype(R); y=(y+rng.uniform(-0.2,0.2,ly).astype(R)*R(spac)).astype(R)
     ex=float(x[-1]-x[0]); ey=float(y[-1]-y[0])
     if mode==0: pts=np.column_stack([rng.uniform(x[0]-spac,x[-1]+spac,n),rng.uniform(y[0]-spac,y[-1]+spac,n)])
     elif mode==1: pts=np.column_stack([rng.normal(x[0]+ex/2,ex/8,n),rng.normal(y[0]+ey/2,ey/8,n)])   # clustered, hull inside grid

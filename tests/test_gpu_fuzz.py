@@ -25,6 +25,9 @@ def run_trials(seed, trials, n_max, lx_max, ly_max):
         lx = int(rng.integers(2, lx_max)); ly = int(rng.integers(2, ly_max))
         spac = float(rng.choice([1.0, 0.5, 2.0, 0.37]))
         x = (rng.uniform(-5, 5) + spac * np.arange(lx)).astype(R); y = (rng.uniform(-5, 5) + spac * np.arange(ly)).astype(R)
+        if rng.uniform() < 0.3:   # axes that are not exactly x(1) + i*spac: the ring windows no longer match the radii
+            x = (x + rng.uniform(-0.2, 0.2, lx).astype(R) * R(spac)).astype(R)
+            y = (y + rng.uniform(-0.2, 0.2, ly).astype(R) * R(spac)).astype(R)
         ex = float(x[-1] - x[0]); ey = float(y[-1] - y[0])
         if mode == 0:
             pts = np.column_stack([rng.uniform(x[0] - spac, x[-1] + spac, n), rng.uniform(y[0] - spac, y[-1] + spac, n)])

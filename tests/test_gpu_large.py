@@ -39,6 +39,30 @@ def test_c2_full_size_kdtree_equals_cell_list_and_scipy():
     np.testing.assert_allclose(np.sqrt(g.nn_dist2.reshape(-1, k)), d, rtol=1e-13, atol=0)
 
 
+def test_c2_single_precision_coordinates_tied_tree_matches_oracle():
+    """C2's 1 M points cast to single precision (what the reference as shipped receives from f2py) tie by the tens of
+    thousands per axis: the tree is the reference's quickselect tree, not the rank-based one -- node by node the
+    oracle's (serial restatement of kd_tree.f90:30-155), and 256 rows of the field equal the oracle's."""
+    from oracle import oracle as orc
+    w = workloads.c2()
+    pts = np.ascontiguousarray(w.points.T.astype(np.float32).astype(np.float64))
+    assert len(np.unique(pts[0])) < pts.shape[1] - 10_000             # really tied
+    order = ip.kd_build(pts) - 1
+    ref = orc.kd_build(pts)
+    stack = [(ref.root, 0, order.size)]
+    while stack:
+        node, lo, hi = stack.pop()
+        if node < 0:
+            assert lo == hi
+            continue
+        m = lo + (hi - lo + 1) // 2 - 1
+        assert order[m] == ref.index[node] - 1
+        stack.append((ref.left[node], lo, m)); stack.append((ref.right[node], m + 1, hi))
+    assert not np.array_equal(order, ip.kd_build(w.points.T.copy()) - 1)
+    x = w.x_axis[:1024]; y = w.y_axis[1500:1756]
+    assert np.array_equal(ip.idw_kdtree(pts, w.data_pts, x, y, 8), orc.idw_kdtree(pts, w.data_pts, x, y, 8))
+
+
 def test_c3_half_edge_paths_agree():
     w = workloads.c3(2_500_000, 4096)
     k = 8
