@@ -24,6 +24,8 @@
 //           none could be inserted (insertion needs d2 < max d2, which only shrinks), so the neighbour
 //           list after the skipped visit is bit-identical to the reference's; it cuts node visits ~14x when
 //           the k-th d2 is > 1.  GI_KD_REFERENCE_VISITS turns it off (visit-count parity with the oracle).
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 
 #include "kernels.cuh"
@@ -331,7 +333,10 @@ int kd_build_faithful(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
     int h_alive = 0;
     GI_CUDA(cudaMemcpyAsync(&h_alive, alive, sizeof(int), cudaMemcpyDeviceToHost, st));
     GI_CUDA(cudaStreamSynchronize(st));
-    if (!h_alive) break;
+    if (!h_alive) {
+      if (getenv("GI_KD_TRACE")) fprintf(stderr, "[gridinterp] quickselect-faithful k-d build: n = %d, %lld rounds\n", n, (long long)(round + kBatch));
+      break;
+    }
   }
   GI_CUDA(cudaGetLastError());
   *order_dev = ID;
