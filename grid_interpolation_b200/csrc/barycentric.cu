@@ -267,6 +267,7 @@ template <class R> struct WalkArgs {
                         // [5] #ambiguous targets flagged [6],[7] start-triangle reduction scratch
   int* amb_list;        // E-linear ids of the targets inside the margin band of an edge (see fixup_kernel)
   int amb_cap;
+  unsigned long long* start_part;  // start_tri_kernel scratch: 2 * kStartBlocks partial results + ticket (zeroed)
   int* status;
 };
 
@@ -443,39 +444,65 @@ __device__ __forceinline__ unsigned long long start_tri_dist(const TriGeom<R>* g
 }
 
 // The reference's ind_tri_start (interpolation.f90:342-355): arg-min of the centroid distance to
-// (x_axis(1), SUM(y_axis)/len_y) over the first min(num_points, num_triangles) triangles, first minimum wins.
-// One CTA, and only when a target was flagged (it returns at once otherwise): the result is needed only by
-// fix-ups that reach column 0.
+// (x_axis(1), SUM(y_axis)/len_y) over the first min(num_points, num_triangles) triangles, first minimum wins, i.e.
+// the lexicographic minimum of (distance, index).  Needed only by fix-ups that reach column 0, so the kernel
+// returns at once unless a target was flagged.  kStartBlocks CTAs each reduce a strided share, the last one to
+// finish (ticket) reduces the partial results.  (The first version was one CTA: 6.4 ms for 5 M triangles
+// whenever anything was flagged -- single-precision C4, structured meshes.)
+constexpr int kStartBlocks = 296;
 template <class R>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 start_tri_kernel(const TriGeom<R>* __restrict__ geom, int n_search, const R* __restrict__ x_axis,
-                 const R* __restrict__ y_axis, int len_y, int64_t* counters) {
+                 const R* __restrict__ y_axis, int len_y, int64_t* counters, unsigned long long* part) {
   if (counters[5] == 0) return;
   __shared__ R s_opt_y;
-  __shared__ unsigned long long s_best;
+  __shared__ unsigned long long s_d[8], s_i[8];
+  __shared__ bool s_last;
   if (threadIdx.x == 0) {
     R sum = R(0);
     for (int i = 0; i < len_y; ++i) sum = sum + y_axis[i];                // SUM(y_axis), :345 (serial order)
     s_opt_y = sum / R(len_y);
   }
-  const R ox = __ldg(x_axis);
-  for (int pass = 0; pass < 2; ++pass) {  // 0: minimum distance, 1: smallest index attaining it (strict '<', :351)
-    const unsigned long long dmin = pass ? s_best : 0ull;
+  __syncthreads();
+  const R ox = __ldg(x_axis), oy = s_opt_y;
+  unsigned long long bd = ~0ull, bi = ~0ull;
+  auto take = [&](unsigned long long d, unsigned long long i) {           // strict '<', first minimum wins (:351)
+    if (d < bd || (d == bd && i < bi)) { bd = d; bi = i; }
+  };
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_search; i += gridDim.x * blockDim.x)
+    take(start_tri_dist(geom, i, ox, oy), (unsigned long long)i);
+  auto block_reduce = [&]() {
+    for (int off = 16; off > 0; off >>= 1)
+      take(__shfl_xor_sync(0xffffffffu, bd, off), __shfl_xor_sync(0xffffffffu, bi, off));
+    if ((threadIdx.x & 31) == 0) { s_d[threadIdx.x >> 5] = bd; s_i[threadIdx.x >> 5] = bi; }
     __syncthreads();
-    if (threadIdx.x == 0) s_best = ~0ull;
-    __syncthreads();
-    const R oy = s_opt_y;
-    unsigned long long best = ~0ull;
-    for (int i = threadIdx.x; i < n_search; i += blockDim.x) {
-      const unsigned long long d = start_tri_dist(geom, i, ox, oy);
-      if (pass == 0) best = min(best, d);
-      else if (d == dmin) best = min(best, (unsigned long long)i);
+    if (threadIdx.x < 32) {
+      bd = threadIdx.x < 8 ? s_d[threadIdx.x] : ~0ull;
+      bi = threadIdx.x < 8 ? s_i[threadIdx.x] : ~0ull;
+      for (int off = 4; off > 0; off >>= 1)
+        take(__shfl_xor_sync(0xffffffffu, bd, off), __shfl_xor_sync(0xffffffffu, bi, off));
     }
-    for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
-    if ((threadIdx.x & 31) == 0) atomicMin(&s_best, best);
-    __syncthreads();
+  };
+  block_reduce();
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = bd; part[2 * blockIdx.x + 1] = bi;
+    __threadfence();
+    s_last = atomicAdd(part + 2 * kStartBlocks, 1ull) == (unsigned long long)gridDim.x - 1;
   }
-  if (threadIdx.x == 0) counters[7] = (int64_t)s_best;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  bd = ~0ull; bi = ~0ull;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+    const volatile unsigned long long* vp = part;
+    take(vp[2 * b], vp[2 * b + 1]);
+  }
+  __syncthreads();
+  block_reduce();
+  if (threadIdx.x == 0) {
+    counters[7] = (int64_t)bi;
+    part[2 * kStartBlocks] = 0ull;  // ticket ready for the next call on this scratch
+  }
 }
 
 constexpr int kMaxBackup = 256;
@@ -724,7 +751,8 @@ int bary_walk(const WalkArgs<R>& wa, const PackedMesh<R>& pm, const R* x_axis, c
   GI_CUDA(cudaGetLastError());
   // targets inside the margin band of an edge: follow the reference's own path (normally none)
   const int n_search = std::min(num_points, pm.num_tri);  // the reference searches triangles 1..num_points (:347)
-  start_tri_kernel<R><<<1, 1024, 0, st>>>(pm.geom, n_search, x_axis, y_axis, len_y, wa.counters);
+  start_tri_kernel<R><<<kStartBlocks, 256, 0, st>>>(pm.geom, n_search, x_axis, y_axis, len_y, wa.counters,
+                                                    wa.start_part);
   fixup_kernel<R><<<kNumSMs * 2, 128, 0, st>>>(wa, len_x, len_y);
   GI_CUDA(cudaGetLastError());
   return GI_OK;
@@ -768,6 +796,8 @@ int bary_run_window(Scratch& scr, const PackedMesh<R>& pm, const R* x_axis, int 
   wa.nz_words = nz_words;
   wa.amb_cap = (int)std::min<int64_t>((int64_t)nf * ns, (int64_t)1 << 22);
   GI_TRY(scr.alloc(&wa.amb_list, (size_t)wa.amb_cap));
+  GI_TRY(scr.alloc(&wa.start_part, (size_t)2 * kStartBlocks + 1));
+  GI_CUDA(cudaMemsetAsync(wa.start_part, 0, sizeof(unsigned long long) * (2 * kStartBlocks + 1), st));
   wa.geom = pm.geom; wa.seed = pm.seed; wa.ncx = pm.ncx; wa.ncy = pm.ncy; wa.num_tri = num_tri;
   wa.iter_cap = num_tri + 16;
   wa.out = data_ip; wa.tri_out = tri_out; wa.mask_words = mask_words; wa.counters = counters;
@@ -857,6 +887,9 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
   GI_TRY(scr.alloc(&counters, (size_t)8 * kMaxBands));
   const int amb_cap = (int)std::min<int64_t>((int64_t)nfast * nslow, (int64_t)1 << 22);
   GI_TRY(scr.alloc(&amb_list, (size_t)amb_cap));  // shared by the bands: band b's fix-up runs before band b+1's walk
+  unsigned long long* start_part;
+  GI_TRY(scr.alloc(&start_part, (size_t)2 * kStartBlocks + 1));
+  GI_CUDA(cudaMemsetAsync(start_part, 0, sizeof(unsigned long long) * (2 * kStartBlocks + 1), st));
 
   int nb = plan_bands(nslow, (int64_t)(row_end - row_begin) * len_x * sizeof(R));
   for (;;) {
@@ -908,7 +941,7 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
         wa.out = dout + (int64_t)(wa.bs0 - bs0) * bnf; wa.tri_out = nullptr;
         wa.mask_words = mask_words + (start[b] - es0) * wpr; wa.nz_words = nz_words + (start[b] - es0) * wpr;
         wa.counters = counters + 8 * b;
-        wa.amb_list = amb_list; wa.amb_cap = amb_cap;
+        wa.amb_list = amb_list; wa.amb_cap = amb_cap; wa.start_part = start_part;
         wa.status = slot.dev;
         GI_TRY(bary_walk<R>(wa, pm, dx, dy, len_x, len_y, num_points, st));
       }
