@@ -44,7 +44,7 @@ sys.path.insert(0, ROOT)
 from grid_interpolation_b200 import workloads  # noqa: E402
 
 ALG_BYTES = {"c2": 9.43, "c3": 11.58, "c4": 9.34, "c5": 45.48}       # SURVEY.md section 8(d), FP64 + int32
-KERNELS_PER_STEP = {"c4": 6, "c2": None, "c3": None, "c5": 2}          # our kernel launches per step (c2/c3: computed)
+KERNELS_PER_STEP = {"c4": 7, "c2": None, "c3": None, "c5": 2}          # our kernel launches per step (c2/c3: computed)
 DOMINANT = {"c4": "walk", "c5": "bilinear", "c3": "esrg_query", "c2": "kd_query"}
 
 

@@ -15,6 +15,7 @@ GI_ESRG_REFERENCE_ORDER = 16
 GI_KD_EXACT_PRUNE = 32
 GI_BILINEAR_SEARCH_AXES = 64
 GI_KD_FAITHFUL_BUILD = 128
+GI_BARY_REFERENCE_ORDER = 256
 
 _vp, _i, _i64, _d, _f = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float
 

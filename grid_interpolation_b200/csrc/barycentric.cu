@@ -32,6 +32,8 @@
 #include <algorithm>
 #include <memory>
 
+#include <cstdlib>
+
 #include "ieee_div.cuh"
 #include "kernels.cuh"
 
@@ -268,6 +270,7 @@ template <class R> struct WalkArgs {
   int* amb_list;        // E-linear ids of the targets inside the margin band of an edge (see fixup_kernel)
   int amb_cap;
   unsigned long long* start_part;  // start_tri_kernel scratch: 2 * kStartBlocks partial results + ticket (zeroed)
+  int reference_rows;   // GI_BARY_REFERENCE_ORDER: locate every target by the reference's row-sequential walk
   int* status;
 };
 
@@ -424,6 +427,30 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   if (lane == 0 && iters_sum) atomicAdd((unsigned long long*)a.counters, (unsigned long long)iters_sum);
 }
 
+// Result of a (re-)located target (f, s): value or mask bit, triangle id, work list of the hull fill.
+template <class R>
+__device__ __forceinline__ void publish_target(const WalkArgs<R>& a, int f, int s, int tri, bool inside, R tx, R ty) {
+  const TargetWindow<R>& w = a.win;
+  if (f >= a.bf0 && f < a.bf1 && s >= a.bs0 && s < a.bs1) {
+    const int64_t o = (int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0);
+    if (inside) {
+      TriGeom<R> g;
+      load_walk(a.geom + tri, g);
+      load_values(a.geom + tri, g);
+      a.out[o] = eval_value(g, tx, ty);
+    }
+    if (a.tri_out) a.tri_out[o] = (inside ? tri : ~tri) + 1;
+  }
+  const int lf = f - w.f0, wpr = (w.nf() + 31) >> 5;
+  uint32_t* word = a.mask_words + (int64_t)(s - w.s0) * wpr + (lf >> 5);
+  const uint32_t bit = 1u << (lf & 31);
+  if (inside) {
+    atomicAnd(word, ~bit);
+  } else if (atomicOr(word, bit) == 0u) {  // the word was not on the fill's work list yet
+    a.nz_words[atomicAdd((unsigned long long*)(a.counters + 4), 1ull)] = (int)((int64_t)(s - w.s0) * wpr + (lf >> 5));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Ambiguity fix-up.  A target within 1e-10 (cross-product units) of a mesh edge passes the orientation test of
 // both adjacent triangles (triangle_walk.f90:148-151); the reference returns whichever its own walk reaches
@@ -453,8 +480,8 @@ constexpr int kStartBlocks = 296;
 template <class R>
 __global__ void __launch_bounds__(256)
 start_tri_kernel(const TriGeom<R>* __restrict__ geom, int n_search, const R* __restrict__ x_axis,
-                 const R* __restrict__ y_axis, int len_y, int64_t* counters, unsigned long long* part) {
-  if (counters[5] == 0) return;
+                 const R* __restrict__ y_axis, int len_y, int64_t* counters, unsigned long long* part, int force) {
+  if (counters[5] == 0 && !force) return;
   __shared__ R s_opt_y;
   __shared__ unsigned long long s_d[8], s_i[8];
   __shared__ bool s_last;
@@ -506,6 +533,12 @@ start_tri_kernel(const TriGeom<R>* __restrict__ geom, int n_search, const R* __r
 }
 
 constexpr int kMaxBackup = 256;
+// entries of the fix-up work list (GI_AMB_CAP shrinks it: tests of the overflow path)
+inline int64_t amb_list_limit() {
+  const char* e = getenv("GI_AMB_CAP");
+  const long long v = e ? atoll(e) : 0;
+  return v > 0 ? (int64_t)v : (int64_t)1 << 22;
+}
 
 template <class R>
 __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len_x, int len_y) {
@@ -539,26 +572,37 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
     bool inside = true, amb;
     for (int j = j0 + 1; j <= ix; ++j)
       tri = walk_checked(a.geom, tri, __ldg(x_axis + j), ty, a.iter_cap, inside, amb, a.status);
-    // publish
-    if (f >= a.bf0 && f < a.bf1 && s >= a.bs0 && s < a.bs1) {
-      const int64_t o = (int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0);
-      if (inside) {
-        TriGeom<R> g;
-        load_walk(a.geom + tri, g);
-        load_values(a.geom + tri, g);
-        a.out[o] = eval_value(g, __ldg(x_axis + ix), ty);
-      }
-      if (a.tri_out) a.tri_out[o] = tri + 1;
-    }
-    const int lf = f - w.f0;
-    uint32_t* word = a.mask_words + (int64_t)(s - w.s0) * wpr + (lf >> 5);
-    const uint32_t bit = 1u << (lf & 31);
-    if (inside) {
-      atomicAnd(word, ~bit);
-    } else if (atomicOr(word, bit) == 0u) {  // the word was not on the fill's work list yet
-      a.nz_words[atomicAdd((unsigned long long*)(a.counters + 4), 1ull)] = (int)((int64_t)(s - w.s0) * wpr + (lf >> 5));
-    }
+    publish_target(a, f, s, tri, inside, __ldg(x_axis + ix), ty);
     atomicAdd((unsigned long long*)(a.counters + 3), 1ull);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The reference's own order: one thread per grid row starts at ind_tri_start and walks the row column by column,
+// every target from the triangle of the previous one (interpolation.f90:362-404).  By construction this finds the
+// reference's triangle for EVERY target, whatever the margin band does -- it is what the fix-up reproduces
+// locally.  It runs (a) when more targets were flagged than the fix-up list holds (a structured mesh whose edges
+// run along the grid lines of a multi-million-node grid), so that nothing is silently left to phase 1's
+// path, and (b) for all targets with GI_BARY_REFERENCE_ORDER (debug).  Rows are independent but each is serial:
+// 16384 threads at C4 size, tens of milliseconds -- a fallback, not the production path.
+// ---------------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(32) row_walk_kernel(const WalkArgs<R> a) {
+  if (!a.reference_rows && a.counters[5] <= (int64_t)a.amb_cap) return;
+  const TargetWindow<R>& w = a.win;
+  const R* x_axis = w.fast_is_y ? w.slow_axis : w.fast_axis;
+  const R* y_axis = w.fast_is_y ? w.fast_axis : w.slow_axis;
+  const int ix0 = w.fast_is_y ? w.s0 : w.f0, ix1 = w.fast_is_y ? w.s1 : w.f1;
+  const int iy0 = w.fast_is_y ? w.f0 : w.s0, iy1 = w.fast_is_y ? w.f1 : w.s1;
+  for (int iy = iy0 + blockIdx.x * blockDim.x + threadIdx.x; iy < iy1; iy += gridDim.x * blockDim.x) {
+    const R ty = __ldg(y_axis + iy);
+    int tri = (int)a.counters[7];                                          // ind_tri = ind_tri_start   (:366)
+    for (int ix = 0; ix < ix1; ++ix) {                                     // :367
+      bool inside, amb;
+      const R tx = __ldg(x_axis + ix);
+      tri = walk_checked(a.geom, tri, tx, ty, a.iter_cap, inside, amb, a.status);   // :372-373
+      if (ix >= ix0) publish_target(a, w.fast_is_y ? iy : ix, w.fast_is_y ? ix : iy, tri, inside, tx, ty);
+    }
   }
 }
 
@@ -752,8 +796,10 @@ int bary_walk(const WalkArgs<R>& wa, const PackedMesh<R>& pm, const R* x_axis, c
   // targets inside the margin band of an edge: follow the reference's own path (normally none)
   const int n_search = std::min(num_points, pm.num_tri);  // the reference searches triangles 1..num_points (:347)
   start_tri_kernel<R><<<kStartBlocks, 256, 0, st>>>(pm.geom, n_search, x_axis, y_axis, len_y, wa.counters,
-                                                    wa.start_part);
+                                                    wa.start_part, wa.reference_rows);
   fixup_kernel<R><<<kNumSMs * 2, 128, 0, st>>>(wa, len_x, len_y);
+  // more flagged targets than the list holds, or GI_BARY_REFERENCE_ORDER: the reference's row-sequential walk
+  row_walk_kernel<R><<<div_up(wa.win.fast_is_y ? nf : ns, 32), 32, 0, st>>>(wa);
   GI_CUDA(cudaGetLastError());
   return GI_OK;
 }
@@ -794,7 +840,8 @@ int bary_run_window(Scratch& scr, const PackedMesh<R>& pm, const R* x_axis, int 
   GI_TRY(scr.alloc(&mask_words, (size_t)wpr * ns));
   GI_TRY(scr.alloc(&nz_words, (size_t)wpr * ns));
   wa.nz_words = nz_words;
-  wa.amb_cap = (int)std::min<int64_t>((int64_t)nf * ns, (int64_t)1 << 22);
+  wa.amb_cap = (int)std::min<int64_t>((int64_t)nf * ns, amb_list_limit());
+  wa.reference_rows = (flags & GI_BARY_REFERENCE_ORDER) ? 1 : 0;
   GI_TRY(scr.alloc(&wa.amb_list, (size_t)wa.amb_cap));
   GI_TRY(scr.alloc(&wa.start_part, (size_t)2 * kStartBlocks + 1));
   GI_CUDA(cudaMemsetAsync(wa.start_part, 0, sizeof(unsigned long long) * (2 * kStartBlocks + 1), st));
@@ -885,7 +932,7 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
   GI_TRY(scr.alloc(&mask_words, (size_t)wpr * nslow));
   GI_TRY(scr.alloc(&nz_words, (size_t)wpr * nslow));
   GI_TRY(scr.alloc(&counters, (size_t)8 * kMaxBands));
-  const int amb_cap = (int)std::min<int64_t>((int64_t)nfast * nslow, (int64_t)1 << 22);
+  const int amb_cap = (int)std::min<int64_t>((int64_t)nfast * nslow, amb_list_limit());
   GI_TRY(scr.alloc(&amb_list, (size_t)amb_cap));  // shared by the bands: band b's fix-up runs before band b+1's walk
   unsigned long long* start_part;
   GI_TRY(scr.alloc(&start_part, (size_t)2 * kStartBlocks + 1));
@@ -942,6 +989,7 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
         wa.mask_words = mask_words + (start[b] - es0) * wpr; wa.nz_words = nz_words + (start[b] - es0) * wpr;
         wa.counters = counters + 8 * b;
         wa.amb_list = amb_list; wa.amb_cap = amb_cap; wa.start_part = start_part;
+        wa.reference_rows = (flags & GI_BARY_REFERENCE_ORDER) ? 1 : 0;
         wa.status = slot.dev;
         GI_TRY(bary_walk<R>(wa, pm, dx, dy, len_x, len_y, num_points, st));
       }

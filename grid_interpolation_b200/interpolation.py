@@ -390,9 +390,11 @@ def idw_esrg_nearest(points, data_in, x_axis, y_axis, grid_spac, num_neighbours,
 
 
 def barycentric_interpolation_ex(points, data_in, x_axis, y_axis, simplices, neighbours, *, rows=None, halo=0,
-                                 order="F", debug=False, dtype=np.float64, out=None, sync=True):
+                                 order="F", debug=False, reference_order=False, dtype=np.float64, out=None,
+                                 sync=True):
     """barycentric_interpolation on a row band (+ ``halo`` rows for the hull fill); debug=True also returns
-    triangle ids (1-based), the outside-hull mask, fill sources and counters."""
+    triangle ids (1-based), the outside-hull mask, fill sources and counters.  reference_order=True locates every
+    target by the reference's own row-sequential walk (debug: slow; the default reproduces its result)."""
     rt, suf = _real(dtype)
     with _Call(points) as c:
         x, y, p, d, n = _grid_common(c, points, data_in, x_axis, y_axis, "n2", rt)
@@ -409,7 +411,7 @@ def barycentric_interpolation_ex(points, data_in, x_axis, y_axis, simplices, nei
         r0, r1 = _band(rows, len_y)
         res, res_ptr, rowmajor = _use_out(c, out, (r1 - r0, len_x), rt, order)
         flags = ((GI_FIELD_ROWMAJOR if rowmajor else 0) | (GI_POINTS_ROWMAJOR if p.rowmajor else 0)
-                 | (GI_TOPO_ROWMAJOR if s.rowmajor else 0))
+                 | (GI_TOPO_ROWMAJOR if s.rowmajor else 0) | (_lib.GI_BARY_REFERENCE_ORDER if reference_order else 0))
         tri = mask = src = cnt = None
         tri_ptr = mask_ptr = src_ptr = cnt_ptr = None
         if debug:

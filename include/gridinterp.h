@@ -79,6 +79,11 @@ typedef enum {
                                     passes (kd_tree.f90:97-155) instead of by ranks.  The two trees are identical
                                     unless coordinates tie; the library detects ties and switches by itself, the
                                     flag forces the slower build (debug / tests). */
+#define GI_BARY_REFERENCE_ORDER 256 /* barycentric_interpolation: locate EVERY target by the reference's own
+                                       row-sequential walk from ind_tri_start (interpolation.f90:362-404; debug:
+                                       one thread per grid row).  Default: only the targets inside the margin
+                                       band of a mesh edge are re-located along that path -- or all of them
+                                       when there are more than the fix-up list holds. */
 #define GI_ESRG_REFERENCE_ORDER 16 /* idw_esrg_nearest: process every target in the reference's candidate order
                                       (debug).  Default: only targets with exactly equal neighbour distances,
                                       the only case in which that order changes the result. */

@@ -126,6 +126,50 @@ def test_barycentric_targets_on_mesh_edges():
         assert_values(got, want)
 
 
+def _lattice_case():
+    gx, gy = np.meshgrid(np.arange(0.0, 12.0), np.arange(0.0, 9.0))
+    pts = np.stack([gx.ravel(), gy.ravel()], 1)
+    simp, nbr = workloads.delaunay(pts)
+    data = np.sin(pts[:, 0]) + 0.3 * pts[:, 1] ** 2
+    return pts, data, np.arange(-0.5, 12.0, 0.5), np.arange(-0.5, 9.0, 0.25), simp, nbr
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_barycentric_reference_order_walk(c1, order):
+    """GI_BARY_REFERENCE_ORDER: one thread per grid row walks the row from ind_tri_start exactly like the reference
+    (interpolation.f90:362-404) -- same triangles (also for targets on edges), mask, fill sources and values, on the
+    reference's own test case, on the lattice mesh, and on a row band with halo."""
+    for pts, data, x, y, simp, nbr in ((c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices, c1.neighbours),
+                                       _lattice_case()):
+        want, w = orc.barycentric_interpolation(pts, data, x, y, simp, nbr, debug=True)
+        got, g = ip.barycentric_interpolation_ex(pts, data, x, y, simp, nbr, debug=True, order=order,
+                                                 reference_order=True)
+        assert np.array_equal(g.mask, w.mask)
+        assert np.array_equal(g.tri[~w.mask], w.tri[~w.mask])
+        assert np.array_equal(g.fill_src, w.fill_src)
+        assert_values(got, want)
+        r0, r1 = 5, y.size - 7
+        band = ip.barycentric_interpolation_ex(pts, data, x, y, simp, nbr, rows=(r0, r1), halo=6, order=order,
+                                               reference_order=True)
+        assert_values(band, want[r0:r1])
+
+
+def test_barycentric_more_flagged_targets_than_the_fixup_list_holds(monkeypatch):
+    """Every lattice target on an edge or vertex is flagged; with a 64-entry fix-up list (GI_AMB_CAP, normally 4 M)
+    the list overflows and the row-sequential walk takes over -- nothing may be left to phase 1's own path."""
+    pts, data, x, y, simp, nbr = _lattice_case()
+    want, w = orc.barycentric_interpolation(pts, data, x, y, simp, nbr, debug=True)
+    monkeypatch.setenv("GI_AMB_CAP", "64")
+    for order in ("C", "F"):
+        got, g = ip.barycentric_interpolation_ex(pts, data, x, y, simp, nbr, debug=True, order=order)
+        assert np.array_equal(g.mask, w.mask)
+        assert np.array_equal(g.tri[~w.mask], w.tri[~w.mask])
+        assert np.array_equal(g.fill_src, w.fill_src)
+        assert_values(got, want)
+        host = ip.barycentric_interpolation(pts, data, x, y, simp, nbr, order=order)      # pipelined host path
+        assert_values(host, want)
+
+
 def test_barycentric_bad_topology_is_reported(c1):
     bad = c1.simplices.copy(); bad[7, 1] = c1.points.shape[0] + 5
     with pytest.raises(RuntimeError, match="out of range"):
