@@ -266,7 +266,8 @@ template <class R> struct WalkArgs {
   uint32_t* mask_words; // E-shaped bit mask: ((nf+31)/32) words per slow row
   int* nz_words;        // compact list of the mask words that are non-zero (work list of the hull fill)
   int64_t* counters;    // [0] walk iterations [1] masked cells [2] max fill level [3] fix-ups [4] #nz_words
-                        // [5] #ambiguous targets flagged [6],[7] start-triangle reduction scratch
+                        // [5] #ambiguous targets flagged [6] a fix-up found no certain column to start from
+                        // [7] the reference's start triangle
   int* amb_list;        // E-linear ids of the targets inside the margin band of an edge (see fixup_kernel)
   int amb_cap;
   unsigned long long* start_part;  // start_tri_kernel scratch: 2 * kStartBlocks partial results + ticket (zeroed)
@@ -562,10 +563,12 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
       if (inside && !amb) { tri = t; j0 = j; break; }
     }
     if (tri < 0) {
-      // no path-independent column within kMaxBackup: only column 0 (the reference's ind_tri_start, :366) is
-      // another certain starting point; otherwise the target keeps the triangle phase 1 found (a whole row
-      // running along mesh edges for more than kMaxBackup columns -- values agree to rounding either way)
-      if (j_stop > 0) continue;
+      // no path-independent column within kMaxBackup (a grid row running along mesh edges): only column 0 (the
+      // reference's ind_tri_start, :366) is another certain starting point
+      if (j_stop > 0) {  // leave it to row_walk_kernel, which redoes the window along the reference's own path
+        a.counters[6] = 1;
+        continue;
+      }
       tri = (int)a.counters[7];
     }
     // forward along the row exactly as the reference does (:367-373)
@@ -588,7 +591,7 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
 // ---------------------------------------------------------------------------------------------
 template <class R>
 __global__ void __launch_bounds__(32) row_walk_kernel(const WalkArgs<R> a) {
-  if (!a.reference_rows && a.counters[5] <= (int64_t)a.amb_cap) return;
+  if (!a.reference_rows && a.counters[5] <= (int64_t)a.amb_cap && a.counters[6] == 0) return;
   const TargetWindow<R>& w = a.win;
   const R* x_axis = w.fast_is_y ? w.slow_axis : w.fast_axis;
   const R* y_axis = w.fast_is_y ? w.fast_axis : w.slow_axis;

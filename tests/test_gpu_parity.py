@@ -170,6 +170,25 @@ def test_barycentric_more_flagged_targets_than_the_fixup_list_holds(monkeypatch)
         assert_values(host, want)
 
 
+def test_barycentric_grid_rows_along_mesh_edges_for_hundreds_of_columns():
+    """A lattice mesh 330 columns wide whose horizontal edges coincide with grid rows: along such a row EVERY target is
+    inside the margin band, so a fix-up finds no path-independent column within its 256-column back-up range; the
+    row-sequential walk then redoes the window along the reference's own path (interpolation.f90:362-404)."""
+    gx, gy = np.meshgrid(np.arange(0.0, 330.0), np.arange(0.0, 6.0))
+    pts = np.stack([gx.ravel(), gy.ravel()], 1)
+    simp, nbr = workloads.delaunay(pts)
+    data = np.cos(0.1 * pts[:, 0]) + 0.2 * pts[:, 1] ** 2
+    x = np.arange(0.0, 329.01, 0.5); y = np.arange(0.0, 5.01, 0.5)
+    want, w = orc.barycentric_interpolation(pts, data, x, y, simp, nbr, debug=True)
+    for order in ("C", "F"):
+        got, g = ip.barycentric_interpolation_ex(pts, data, x, y, simp, nbr, debug=True, order=order)
+        assert np.array_equal(g.mask, w.mask)
+        assert np.array_equal(g.tri[~w.mask], w.tri[~w.mask])
+        assert_values(got, want)
+        with ip.BarycentricPlan(pts, x, y, simp, nbr, order=order) as plan:
+            assert_values(plan(data), want)
+
+
 def test_barycentric_bad_topology_is_reported(c1):
     bad = c1.simplices.copy(); bad[7, 1] = c1.points.shape[0] + 5
     with pytest.raises(RuntimeError, match="out of range"):
