@@ -101,6 +101,10 @@ void* gi_host_alloc(uint64_t bytes);
 void gi_host_free(void* p);
 /* cudaStreamSynchronize(stream) + the first device-side error recorded on it since the last call. */
 int gi_stream_status(void* stream);
+/* Environment variables read by the library (debugging aids, none is needed in production):
+ *   GI_KD_TRACE=1   print the number of rounds of the quickselect-faithful k-d tree build to stderr
+ *   GI_AMB_CAP=n    size of the barycentric fix-up work list (default 4 194 304 targets per window): a smaller
+ *                   value forces the row-sequential fallback that runs when the list overflows (tests) */
 /* Phase profiling: gi_set_profiling(1) starts a fresh recording on the calling thread; from then on every
  * call made by that thread records CUDA events around its phases (h2d, pack_mesh, walk, fill, d2h, ...) on
  * the stream it runs on, without synchronising.  gi_last_timings() waits for the last recorded event and
