@@ -16,6 +16,29 @@ def same(a, b, what):
     assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), what
 
 
+def dev(a, R):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a).astype(R) if np.asarray(a).dtype.kind == "f" else a),
+                           device="cuda:0")
+
+
+def api_variant(vr, R, want, tag, call, plan, ly, halo=None):
+    """The same problem through another door of the API, picked at random: C-ordered output, a plan, device tensors
+    in and out, a row band (with a halo that covers the grid where the operator needs one)."""
+    v = int(vr.integers(0, 4))
+    if v == 0:
+        same(call(order="C"), want, "order=C " + tag)
+    elif v == 1:
+        with plan() as pl:
+            same(pl(pl._fuzz_data), want, "plan " + tag)
+    elif v == 2:
+        same(call(device=True).cpu().numpy(), want, "device tensors " + tag)
+    else:
+        r0 = int(vr.integers(0, ly)); r1 = int(vr.integers(r0, ly + 1))
+        kw = {} if halo is None else {"halo": halo}
+        same(call(rows=(r0, r1), **kw), want[r0:r1], f"rows ({r0},{r1}) " + tag)
+
+
 def run_trials(seed, trials, n_max, lx_max, ly_max):
     rng = np.random.default_rng(1000 + seed)
     for trial in range(trials):
@@ -52,10 +75,29 @@ def run_trials(seed, trials, n_max, lx_max, ly_max):
         want, w = orc.idw_kdtree(pts.T, dat, x, y, k, dtype=R, debug=True)
         got, g = ip.idw_kdtree_ex(pts.T, dat, x, y, k, debug=True, dtype=R)
         same(g.nn_index, np.moveaxis(w.nn_index, 0, -1), "kd ids " + tag); same(got, want, "kd " + tag)
+        vr = np.random.default_rng(77_000 + 1000 * seed + trial)
+
+        def kd_call(device=False, **kw):
+            a = (dev(pts.T, R), dev(dat, R), dev(x, R), dev(y, R)) if device else (pts.T, dat, x, y)
+            return ip.idw_kdtree_ex(*a, k, dtype=R, **kw)
+
+        def kd_plan():
+            pl = ip.KdTreePlan(pts.T, x, y, k, dtype=R); pl._fuzz_data = dat
+            return pl
+        api_variant(vr, R, want, "kd " + tag, kd_call, kd_plan, ly)
 
         want, w = orc.idw_esrg_nearest(pts, dat, x, y, spac, k, dtype=R, debug=True)
         got, g = ip.idw_esrg_nearest_ex(pts, dat, x, y, spac, k, debug=True, dtype=R)
         same(g.nn_index, np.moveaxis(w.nn_index, 0, -1), "esrg ids " + tag); same(got, want, "esrg " + tag)
+
+        def es_call(device=False, **kw):
+            a = (dev(pts, R), dev(dat, R), dev(x, R), dev(y, R)) if device else (pts, dat, x, y)
+            return ip.idw_esrg_nearest_ex(*a, spac, k, dtype=R, **kw)
+
+        def es_plan():
+            pl = ip.EsrgPlan(pts, x, y, spac, k, dtype=R); pl._fuzz_data = dat
+            return pl
+        api_variant(vr, R, want, "esrg " + tag, es_call, es_plan, ly)
 
         if mode != 2:
             tri = Delaunay(pts)
@@ -69,6 +111,16 @@ def run_trials(seed, trials, n_max, lx_max, ly_max):
                     ip.barycentric_interpolation(pts, dat, x, y, simp, nbr, dtype=R)
             else:
                 same(ip.barycentric_interpolation(pts, dat, x, y, simp, nbr, dtype=R), want, "barycentric " + tag)
+
+                def ba_call(device=False, **kw):
+                    a = ((dev(pts, R), dev(dat, R), dev(x, R), dev(y, R), dev(simp, R), dev(nbr, R)) if device
+                         else (pts, dat, x, y, simp, nbr))
+                    return ip.barycentric_interpolation_ex(*a, dtype=R, **kw)
+
+                def ba_plan():
+                    pl = ip.BarycentricPlan(pts, x, y, simp, nbr, dtype=R); pl._fuzz_data = dat
+                    return pl
+                api_variant(vr, R, want, "barycentric " + tag, ba_call, ba_plan, ly, halo=ly)
 
         fld = np.asfortranarray(rng.normal(size=(ly, lx)).astype(R))
         q = np.column_stack([rng.uniform(x[0], x[-1] - 1e-3, 60), rng.uniform(y[0], y[-1] - 1e-3, 60)])
