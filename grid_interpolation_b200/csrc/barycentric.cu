@@ -49,7 +49,7 @@ constexpr int kWalkThreads = 128;  // columns per CTA
 template <class R> struct alignas(sizeof(R) == 8 ? 32 : 16) TriGeom {
   R x1, y1, x2, y2, x3, y3;
   int n1, n2, n3;  // neighbour opposite vertex 1/2/3, 0-based, -1 = hull edge
-  int pad;
+  int pad;         // ambiguity threshold of this triangle (bit pattern, see amb_threshold)
   R d1, d2, d3, padv;
 };
 template <class R> struct SeedGrid {
@@ -70,7 +70,7 @@ __device__ __forceinline__ void load_walk(const TriGeom<double>* p, TriGeom<doub
   ld256(p, g.x1, g.y1, g.x2, g.y2);
   ld256(reinterpret_cast<const char*>(p) + 32, g.x3, g.y3, n12, w);
   g.n1 = __double2loint(n12); g.n2 = __double2hiint(n12);
-  g.n3 = __double2loint(w); g.pad = 0;
+  g.n3 = __double2loint(w); g.pad = __double2hiint(w);
 }
 __device__ __forceinline__ void load_walk(const TriGeom<float>* p, TriGeom<float>& g) { g = *p; }
 // nodal values (sector 2)
@@ -134,7 +134,7 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
   pts.xy(b - 1, g.x2, g.y2);
   pts.xy(c - 1, g.x3, g.y3);
   g.n1 = n1 - 1; g.n2 = n2 - 1; g.n3 = n3 - 1;
-  g.pad = 0;
+  g.pad = amb_threshold(g);
   g.d1 = __ldg(data + (a - 1)); g.d2 = __ldg(data + (b - 1)); g.d3 = __ldg(data + (c - 1));
   g.padv = R(0);
   geom[t] = g;
@@ -221,12 +221,33 @@ __device__ __forceinline__ R eval_value(const TriGeom<R>& g, R tx, R ty) {
   return g.d1 * w1 + g.d2 * w2 + g.d3 * w3;
 }
 
-// |cross| below this (twice the reference's margin) means "within the margin band of an edge"
-template <class R> __device__ __forceinline__ R kAmbBand() { return R(2e-10); }
-// Cheap superset test for the hot loop: compares the high word of |x| only (2e-10 = 0x3DEB7CDF'D9D7BDBB), i.e.
-// |x| < 2.0000003e-10, with two integer instructions instead of FP64-pipe min / compare sequences.
-__device__ __forceinline__ bool in_amb_band(double x) { return (__double2hiint(x) & 0x7fffffff) < 0x3DEB7CE0; }
-__device__ __forceinline__ bool in_amb_band(float x) { return fabsf(x) < 2e-10f; }
+// When is a located target path-dependent?  A target accepted by this triangle (every cross >= -1e-10,
+// triangle_walk.f90:148-151) is ALSO accepted by the neighbour behind edge i iff that neighbour's own evaluation of
+// the shared edge, cross' = -cross + delta, is >= -1e-10, i.e. iff cross <= 1e-10 + delta.  delta is the rounding
+// difference of the two evaluations (different base vertex): each is a difference of two products of coordinate
+// differences, so |delta| <= ~12 eps D^2 with D the longest edge (the target is within D of every vertex).  With
+// double precision and O(1) triangles that is far below the margin; in single precision, or with coordinates in
+// the millions, it is the larger term.  A cross below  T = 2e-10 + 32 eps D^2  therefore marks the target for the
+// fix-up (a superset of the truly ambiguous cases); T depends on the triangle only and travels in the record as
+// the bit pattern the hot loop compares against: the high word of T for double (rounded up), the word for float.
+template <class R> __device__ __forceinline__ int amb_threshold(const TriGeom<R>& g);
+template <> __device__ __forceinline__ int amb_threshold<double>(const TriGeom<double>& g) {
+  const double a = (g.x2 - g.x1) * (g.x2 - g.x1) + (g.y2 - g.y1) * (g.y2 - g.y1);
+  const double b = (g.x3 - g.x2) * (g.x3 - g.x2) + (g.y3 - g.y2) * (g.y3 - g.y2);
+  const double c = (g.x1 - g.x3) * (g.x1 - g.x3) + (g.y1 - g.y3) * (g.y1 - g.y3);
+  const double t = 2e-10 + 32.0 * 1.1102230246251565e-16 * fmax(fmax(a, b), c);
+  return t < 1e300 ? __double2hiint(t) + 1 : 0x7fe00000;
+}
+template <> __device__ __forceinline__ int amb_threshold<float>(const TriGeom<float>& g) {
+  const float a = (g.x2 - g.x1) * (g.x2 - g.x1) + (g.y2 - g.y1) * (g.y2 - g.y1);
+  const float b = (g.x3 - g.x2) * (g.x3 - g.x2) + (g.y3 - g.y2) * (g.y3 - g.y2);
+  const float c = (g.x1 - g.x3) * (g.x1 - g.x3) + (g.y1 - g.y3) * (g.y1 - g.y3);
+  const float t = 2e-10f + 32.0f * 5.9604645e-8f * fmaxf(fmaxf(a, b), c);
+  return t < 1e37f ? __float_as_int(t) + 1 : 0x7f000000;
+}
+// |x| below the triangle's threshold?  Integer compares on the (high) word: two instructions per cross.
+__device__ __forceinline__ bool in_amb_band(double x, int thr) { return (__double2hiint(x) & 0x7fffffff) < thr; }
+__device__ __forceinline__ bool in_amb_band(float x, int thr) { return (__float_as_int(x) & 0x7fffffff) < thr; }
 
 // walk() that also reports whether the accepting (or hull-exit) test was inside the margin band
 template <class R>
@@ -247,8 +268,8 @@ __device__ __forceinline__ int walk_checked(const TriGeom<R>* __restrict__ geom,
     if (c1 < margin) { nxt = g.n3; cf = c1; }
     else if (c2 < margin) { nxt = g.n1; cf = c2; }
     else if (c3 < margin) { nxt = g.n2; cf = c3; }
-    else { amb = fmin(fmin(c1, c2), c3) < kAmbBand<R>(); break; }
-    if (nxt < 0) { inside = false; amb = cf > -kAmbBand<R>(); break; }
+    else { amb = in_amb_band(c1, g.pad) | in_amb_band(c2, g.pad) | in_amb_band(c3, g.pad); break; }
+    if (nxt < 0) { inside = false; amb = in_amb_band(cf, g.pad); break; }
     tri = nxt;
     if (it >= iter_cap) { raise_status(status, GI_ERR_ITER_CAP); inside = false; amb = false; break; }
   }
@@ -272,6 +293,7 @@ template <class R> struct WalkArgs {
   int amb_cap;
   unsigned long long* start_part;  // start_tri_kernel scratch: 2 * kStartBlocks partial results + ticket (zeroed)
   int reference_rows;   // GI_BARY_REFERENCE_ORDER: locate every target by the reference's row-sequential walk
+  int* row_todo;        // [len_y], zeroed: grid rows a fix-up handed to row_walk_kernel
   int* status;
 };
 
@@ -311,7 +333,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   // ---- phase 1: locate -------------------------------------------------------------------------
   long long iters_sum = 0;
   if (active) {
-    int tri, n1, n2, n3;
+    int tri, n1, n2, n3, thr;
     R m1, m2, m3, p1, p2, p3, k1, k2, k3;
     bool fresh;  // no target resolved in `tri` yet
     auto enter = [&](int t) {  // make `t` the current triangle: one 64 B load + 12 flops
@@ -319,7 +341,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
       fresh = true;
       TriGeom<R> g;
       load_walk(a.geom + t, g);
-      n1 = g.n1; n2 = g.n2; n3 = g.n3;
+      n1 = g.n1; n2 = g.n2; n3 = g.n3; thr = g.pad;
       const R ex1 = g.x2 - g.x1, ey1 = g.y2 - g.y1;   // edge (v1,v2)
       const R ex2 = g.x3 - g.x2, ey2 = g.y3 - g.y2;   // edge (v2,v3)
       const R ex3 = g.x1 - g.x3, ey3 = g.y1 - g.y3;   // edge (v3,v1)
@@ -357,7 +379,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
       // A target within the margin band of an edge is accepted by both adjacent triangles and which one the
       // reference returns depends on its walk path: flag it for fixup_kernel.
       // (any |cross| below twice the margin: a superset of the truly ambiguous cases, three compares)
-      if (in_amb_band(x1) | in_amb_band(x2) | in_amb_band(x3)) {
+      if (in_amb_band(x1, thr) | in_amb_band(x2, thr) | in_amb_band(x3, thr)) {
         const unsigned long long slot = atomicAdd((unsigned long long*)(a.counters + 5), 1ull);
         if (slot < (unsigned long long)a.amb_cap) a.amb_list[slot] = (srow0 + r - w.s0) * w.nf() + lane_f;
       }
@@ -565,7 +587,8 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
     if (tri < 0) {
       // no path-independent column within kMaxBackup (a grid row running along mesh edges): only column 0 (the
       // reference's ind_tri_start, :366) is another certain starting point
-      if (j_stop > 0) {  // leave it to row_walk_kernel, which redoes the window along the reference's own path
+      if (j_stop > 0) {  // leave the row to row_walk_kernel, which redoes it along the reference's own path
+        a.row_todo[iy] = 1;
         a.counters[6] = 1;
         continue;
       }
@@ -584,27 +607,49 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
 // The reference's own order: one thread per grid row starts at ind_tri_start and walks the row column by column,
 // every target from the triangle of the previous one (interpolation.f90:362-404).  By construction this finds the
 // reference's triangle for EVERY target, whatever the margin band does -- it is what the fix-up reproduces
-// locally.  It runs (a) when more targets were flagged than the fix-up list holds (a structured mesh whose edges
-// run along the grid lines of a multi-million-node grid), so that nothing is silently left to phase 1's
-// path, and (b) for all targets with GI_BARY_REFERENCE_ORDER (debug).  Rows are independent but each is serial:
+// locally.  It runs (a) for the rows in which a fix-up found no certain column to start from within its back-up
+// range (a grid row along mesh edges, or along the hull: every target of the row is flagged), (b) for the whole
+// window when more targets were flagged than the fix-up list holds (a structured mesh whose edges run along the
+// grid lines of a multi-million-node grid), so that nothing is silently left to phase 1's path, and (c) for
+// all targets with GI_BARY_REFERENCE_ORDER (debug).  Rows are independent but each is serial:
 // 16384 threads at C4 size, tens of milliseconds -- a fallback, not the production path.
 // ---------------------------------------------------------------------------------------------
+constexpr int kRowChunk = 1024;
 template <class R>
 __global__ void __launch_bounds__(32) row_walk_kernel(const WalkArgs<R> a) {
-  if (!a.reference_rows && a.counters[5] <= (int64_t)a.amb_cap && a.counters[6] == 0) return;
+  // one warp per grid row: lane 0 walks a chunk of columns (the chain of dependent walks, nothing else in it),
+  // then all lanes publish the chunk (values, mask bits, work list) in parallel
+  __shared__ int s_tri[kRowChunk];  // found triangle, ~id = left through a hull edge
+  const bool all_rows = a.reference_rows || a.counters[5] > (int64_t)a.amb_cap;
+  if (!all_rows && a.counters[6] == 0) return;
   const TargetWindow<R>& w = a.win;
   const R* x_axis = w.fast_is_y ? w.slow_axis : w.fast_axis;
   const R* y_axis = w.fast_is_y ? w.fast_axis : w.slow_axis;
   const int ix0 = w.fast_is_y ? w.s0 : w.f0, ix1 = w.fast_is_y ? w.s1 : w.f1;
   const int iy0 = w.fast_is_y ? w.f0 : w.s0, iy1 = w.fast_is_y ? w.f1 : w.s1;
-  for (int iy = iy0 + blockIdx.x * blockDim.x + threadIdx.x; iy < iy1; iy += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x;
+  for (int iy = iy0 + blockIdx.x; iy < iy1; iy += gridDim.x) {
+    if (!all_rows && !a.row_todo[iy]) continue;
+    __syncwarp();
+    if (lane == 0) a.row_todo[iy] = 0;
     const R ty = __ldg(y_axis + iy);
     int tri = (int)a.counters[7];                                          // ind_tri = ind_tri_start   (:366)
-    for (int ix = 0; ix < ix1; ++ix) {                                     // :367
-      bool inside, amb;
-      const R tx = __ldg(x_axis + ix);
-      tri = walk_checked(a.geom, tri, tx, ty, a.iter_cap, inside, amb, a.status);   // :372-373
-      if (ix >= ix0) publish_target(a, w.fast_is_y ? iy : ix, w.fast_is_y ? ix : iy, tri, inside, tx, ty);
+    for (int c0 = 0; c0 < ix1; c0 += kRowChunk) {                          // :367
+      const int cn = min(kRowChunk, ix1 - c0);
+      if (lane == 0) {
+        for (int i = 0; i < cn; ++i) {
+          bool inside, amb;
+          tri = walk_checked(a.geom, tri, __ldg(x_axis + c0 + i), ty, a.iter_cap, inside, amb, a.status);  // :372-373
+          s_tri[i] = inside ? tri : ~tri;
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < cn; i += 32) {
+        const int ix = c0 + i, t = s_tri[i];
+        if (ix >= ix0)
+          publish_target(a, w.fast_is_y ? iy : ix, w.fast_is_y ? ix : iy, t >= 0 ? t : ~t, t >= 0, __ldg(x_axis + ix), ty);
+      }
+      __syncwarp();
     }
   }
 }
@@ -802,7 +847,7 @@ int bary_walk(const WalkArgs<R>& wa, const PackedMesh<R>& pm, const R* x_axis, c
                                                     wa.start_part, wa.reference_rows);
   fixup_kernel<R><<<kNumSMs * 2, 128, 0, st>>>(wa, len_x, len_y);
   // more flagged targets than the list holds, or GI_BARY_REFERENCE_ORDER: the reference's row-sequential walk
-  row_walk_kernel<R><<<div_up(wa.win.fast_is_y ? nf : ns, 32), 32, 0, st>>>(wa);
+  row_walk_kernel<R><<<std::min(wa.win.fast_is_y ? nf : ns, 65535), 32, 0, st>>>(wa);
   GI_CUDA(cudaGetLastError());
   return GI_OK;
 }
@@ -848,6 +893,8 @@ int bary_run_window(Scratch& scr, const PackedMesh<R>& pm, const R* x_axis, int 
   GI_TRY(scr.alloc(&wa.amb_list, (size_t)wa.amb_cap));
   GI_TRY(scr.alloc(&wa.start_part, (size_t)2 * kStartBlocks + 1));
   GI_CUDA(cudaMemsetAsync(wa.start_part, 0, sizeof(unsigned long long) * (2 * kStartBlocks + 1), st));
+  GI_TRY(scr.alloc(&wa.row_todo, (size_t)len_y));
+  GI_CUDA(cudaMemsetAsync(wa.row_todo, 0, sizeof(int) * (size_t)len_y, st));
   wa.geom = pm.geom; wa.seed = pm.seed; wa.ncx = pm.ncx; wa.ncy = pm.ncy; wa.num_tri = num_tri;
   wa.iter_cap = num_tri + 16;
   wa.out = data_ip; wa.tri_out = tri_out; wa.mask_words = mask_words; wa.counters = counters;
@@ -940,6 +987,9 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
   unsigned long long* start_part;
   GI_TRY(scr.alloc(&start_part, (size_t)2 * kStartBlocks + 1));
   GI_CUDA(cudaMemsetAsync(start_part, 0, sizeof(unsigned long long) * (2 * kStartBlocks + 1), st));
+  int* row_todo;
+  GI_TRY(scr.alloc(&row_todo, (size_t)len_y));
+  GI_CUDA(cudaMemsetAsync(row_todo, 0, sizeof(int) * (size_t)len_y, st));
 
   int nb = plan_bands(nslow, (int64_t)(row_end - row_begin) * len_x * sizeof(R));
   for (;;) {
@@ -992,7 +1042,7 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
         wa.mask_words = mask_words + (start[b] - es0) * wpr; wa.nz_words = nz_words + (start[b] - es0) * wpr;
         wa.counters = counters + 8 * b;
         wa.amb_list = amb_list; wa.amb_cap = amb_cap; wa.start_part = start_part;
-        wa.reference_rows = (flags & GI_BARY_REFERENCE_ORDER) ? 1 : 0;
+        wa.reference_rows = (flags & GI_BARY_REFERENCE_ORDER) ? 1 : 0; wa.row_todo = row_todo;
         wa.status = slot.dev;
         GI_TRY(bary_walk<R>(wa, pm, dx, dy, len_x, len_y, num_points, st));
       }
