@@ -36,6 +36,10 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
         allp=np.column_stack([gx.ravel(),gy.ravel()]); sel=rng.permutation(len(allp))[:max(min(n,len(allp)),4)]
         pts=allp[sel]; n=len(pts)
     else: pts=np.round(np.column_stack([rng.uniform(x[0],x[-1],n),rng.uniform(y[0],y[-1],n)]),1)
+    if rng.uniform()<0.3:   # another length scale / offset: the walk's margin 1e-10 and the k-d sentinel 1e6 are absolute
+        sc=float(rng.choice([1.0e3,1.0e-3,37.0])); off=rng.uniform(-1.0,1.0,2)*1.0e3*sc
+        x=(x.astype(np.float64)*sc+off[0]).astype(R); y=(y.astype(np.float64)*sc+off[1]).astype(R)
+        pts=pts*sc+off; spac=float(R(spac*sc))
     pts=pts.astype(R).astype(np.float64)
     dat=rng.normal(size=n).astype(R)
     k=int(rng.integers(1,min(n,9)+1)) if rng.uniform()<0.8 else n if n<=32 else 8
@@ -61,7 +65,7 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
                 itp.call("barycentric_interpolation",farr(pts,R),n,dat,x,lx,y,ly,farr(simp,np.int64),farr(nbr,np.int64),len(simp),f)
                 if not np.array_equal(f,o,equal_nan=True): nbad+=1; print("BARY MISMATCH",tag,np.abs(f-o).max(),flush=True)
         fld=farr(rng.normal(size=(ly,lx)),R)
-        q=np.column_stack([rng.uniform(x[0],x[-1]-1e-3,50),rng.uniform(y[0],y[-1]-1e-3,50)])
+        q=np.column_stack([rng.uniform(x[0],x[-1]-1e-3*(x[-1]-x[0]),50),rng.uniform(y[0],y[-1]-1e-3*(y[-1]-y[0]),50)])
         q[:10,0]=rng.choice(x[:-1],10); q[5:15,1]=rng.choice(y[:-1],10)
         res=np.zeros(50,R)
         itp.call("bilinear",x,lx,y,ly,fld,farr(q,R),50,res)

@@ -67,6 +67,10 @@ def run_trials(seed, trials, n_max, lx_max, ly_max):
             pts = allp[rng.permutation(len(allp))[:max(min(n, len(allp)), 4)]]; n = len(pts)
         else:                 # rounded coordinates: coordinate ties
             pts = np.round(np.column_stack([rng.uniform(x[0], x[-1], n), rng.uniform(y[0], y[-1], n)]), 1)
+        if rng.uniform() < 0.3:   # another length scale / offset: the walk's margin 1e-10 and the k-d sentinel 1e6 are absolute
+            sc = float(rng.choice([1.0e3, 1.0e-3, 37.0])); off = rng.uniform(-1.0, 1.0, 2) * 1.0e3 * sc
+            x = (x.astype(np.float64) * sc + off[0]).astype(R); y = (y.astype(np.float64) * sc + off[1]).astype(R)
+            pts = pts * sc + off; spac = float(R(spac * sc))
         pts = pts.astype(R).astype(np.float64)
         dat = rng.normal(size=n).astype(R)
         k = int(rng.integers(1, min(n, 9) + 1)) if rng.uniform() < 0.8 else min(n, 32)
@@ -123,7 +127,8 @@ def run_trials(seed, trials, n_max, lx_max, ly_max):
                 api_variant(vr, R, want, "barycentric " + tag, ba_call, ba_plan, ly, halo=ly)
 
         fld = np.asfortranarray(rng.normal(size=(ly, lx)).astype(R))
-        q = np.column_stack([rng.uniform(x[0], x[-1] - 1e-3, 60), rng.uniform(y[0], y[-1] - 1e-3, 60)])
+        q = np.column_stack([rng.uniform(x[0], x[-1] - 1e-3 * (x[-1] - x[0]), 60),
+                             rng.uniform(y[0], y[-1] - 1e-3 * (y[-1] - y[0]), 60)])
         q[:10, 0] = rng.choice(x[:-1], 10); q[5:15, 1] = rng.choice(y[:-1], 10)
         q = q.astype(R)
         same(ip.bilinear(x, y, fld, q, dtype=R), orc.bilinear(x, y, fld, q, dtype=R), "bilinear " + tag)
