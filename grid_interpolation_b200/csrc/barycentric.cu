@@ -847,7 +847,7 @@ int bary_walk(const WalkArgs<R>& wa, const PackedMesh<R>& pm, const R* x_axis, c
                                                     wa.start_part, wa.reference_rows);
   fixup_kernel<R><<<kNumSMs * 2, 128, 0, st>>>(wa, len_x, len_y);
   // more flagged targets than the list holds, or GI_BARY_REFERENCE_ORDER: the reference's row-sequential walk
-  row_walk_kernel<R><<<std::min(wa.win.fast_is_y ? nf : ns, 65535), 32, 0, st>>>(wa);
+  row_walk_kernel<R><<<std::min(wa.win.fast_is_y ? nf : ns, kNumSMs * 16), 32, 0, st>>>(wa);
   GI_CUDA(cudaGetLastError());
   return GI_OK;
 }
