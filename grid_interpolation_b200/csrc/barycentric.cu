@@ -271,7 +271,7 @@ __device__ __forceinline__ int walk_checked(const TriGeom<R>* __restrict__ geom,
     else { amb = in_amb_band(c1, g.pad) | in_amb_band(c2, g.pad) | in_amb_band(c3, g.pad); break; }
     if (nxt < 0) { inside = false; amb = in_amb_band(cf, g.pad); break; }
     tri = nxt;
-    if (it >= iter_cap) { raise_status(status, GI_ERR_ITER_CAP); inside = false; amb = false; break; }
+    if (it >= iter_cap) { if (status) raise_status(status, GI_ERR_ITER_CAP); inside = false; amb = false; break; }
   }
   return tri;
 }
@@ -615,11 +615,21 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
 // 16384 threads at C4 size, tens of milliseconds -- a fallback, not the production path.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowChunk = 1024;
+constexpr int kRowSpecMaxCols = 50 * 1024;  // speculative form: one int of shared memory per column (200 KB)
+// One warp per grid row.
+//   serial form       lane 0 walks a chunk of columns (the chain of dependent walks, nothing else in it), then all
+//                     lanes publish the chunk (values, mask bits, work list) in parallel.
+//   speculative form  (rows of up to kRowSpecMaxCols columns) the chain is cut into 32 pieces: lane L walks piece
+//                     L from a GUESSED state (the triangle a walk from the seed grid finds for the column before
+//                     the piece) and records the state after every column; then lane 0 repairs the pieces in
+//                     order -- it continues the TRUE chain into piece L only until its state equals the recorded
+//                     one (the state after a column depends on nothing but the state before it and the column,
+//                     so from there on the recorded chain is the true chain).  Exact, and 512 instead of 16 384
+//                     dependent walks per row at C4 size.
 template <class R>
-__global__ void __launch_bounds__(32) row_walk_kernel(const WalkArgs<R> a) {
-  // one warp per grid row: lane 0 walks a chunk of columns (the chain of dependent walks, nothing else in it),
-  // then all lanes publish the chunk (values, mask bits, work list) in parallel
-  __shared__ int s_tri[kRowChunk];  // found triangle, ~id = left through a hull edge
+__global__ void __launch_bounds__(32) row_walk_kernel(const WalkArgs<R> a, int spec_cols) {
+  __shared__ int s_tri[kRowChunk];   // found triangle, ~id = left through a hull edge
+  extern __shared__ int s_state[];   // speculative form: the same per column of the row
   const bool all_rows = a.reference_rows || a.counters[5] > (int64_t)a.amb_cap;
   if (!all_rows && a.counters[6] == 0) return;
   const TargetWindow<R>& w = a.win;
@@ -633,12 +643,47 @@ __global__ void __launch_bounds__(32) row_walk_kernel(const WalkArgs<R> a) {
     __syncwarp();
     if (lane == 0) a.row_todo[iy] = 0;
     const R ty = __ldg(y_axis + iy);
-    int tri = (int)a.counters[7];                                          // ind_tri = ind_tri_start   (:366)
+    const int start = (int)a.counters[7];                                  // ind_tri = ind_tri_start   (:366)
+    bool inside, amb;
+    if (ix1 <= spec_cols && ix1 >= 64) {
+      const int piece = (ix1 + 31) >> 5, c_lo = lane * piece, c_hi = min(c_lo + piece, ix1);
+      if (c_lo < ix1) {
+        int tri = start;
+        if (lane > 0)  // any valid triangle may be guessed; a good guess makes the repair short
+          tri = walk_checked(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, c_lo - 1, iy, a.num_tri), __ldg(x_axis + c_lo - 1),
+                             ty, a.iter_cap, inside, amb, (int*)nullptr);
+        for (int ix = c_lo; ix < c_hi; ++ix) {
+          tri = walk_checked(a.geom, tri, __ldg(x_axis + ix), ty, a.iter_cap, inside, amb, lane ? (int*)nullptr : a.status);
+          s_state[ix] = inside ? tri : ~tri;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        for (int c = piece; c < ix1; c += piece) {
+          const int prev = s_state[c - 1];
+          int tri = prev >= 0 ? prev : ~prev;                              // the true state after column c - 1
+          const int end = min(c + piece, ix1);
+          for (int ix = c; ix < end; ++ix) {
+            tri = walk_checked(a.geom, tri, __ldg(x_axis + ix), ty, a.iter_cap, inside, amb, a.status);   // :372-373
+            const int st = inside ? tri : ~tri;
+            if (st == s_state[ix]) break;                                  // met the recorded chain
+            s_state[ix] = st;
+          }
+        }
+      }
+      __syncwarp();
+      for (int ix = ix0 + lane; ix < ix1; ix += 32) {
+        const int t = s_state[ix];
+        publish_target(a, w.fast_is_y ? iy : ix, w.fast_is_y ? ix : iy, t >= 0 ? t : ~t, t >= 0, __ldg(x_axis + ix), ty);
+      }
+      __syncwarp();
+      continue;
+    }
+    int tri = start;
     for (int c0 = 0; c0 < ix1; c0 += kRowChunk) {                          // :367
       const int cn = min(kRowChunk, ix1 - c0);
       if (lane == 0) {
         for (int i = 0; i < cn; ++i) {
-          bool inside, amb;
           tri = walk_checked(a.geom, tri, __ldg(x_axis + c0 + i), ty, a.iter_cap, inside, amb, a.status);  // :372-373
           s_tri[i] = inside ? tri : ~tri;
         }
@@ -847,7 +892,18 @@ int bary_walk(const WalkArgs<R>& wa, const PackedMesh<R>& pm, const R* x_axis, c
                                                     wa.start_part, wa.reference_rows);
   fixup_kernel<R><<<kNumSMs * 2, 128, 0, st>>>(wa, len_x, len_y);
   // more flagged targets than the list holds, or GI_BARY_REFERENCE_ORDER: the reference's row-sequential walk
-  row_walk_kernel<R><<<std::min(wa.win.fast_is_y ? nf : ns, kNumSMs * 16), 32, 0, st>>>(wa);
+  {
+    const int cols = wa.win.fast_is_y ? wa.win.s1 : wa.win.f1;            // a row is walked from column 0
+    const int spec_cols = cols <= kRowSpecMaxCols ? cols : 0;
+    static bool configured = false;  // (per instantiation; the attribute is idempotent)
+    if (!configured) {
+      GI_CUDA(cudaFuncSetAttribute(row_walk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kRowSpecMaxCols * (int)sizeof(int)));
+      configured = true;
+    }
+    row_walk_kernel<R><<<std::min(wa.win.fast_is_y ? nf : ns, kNumSMs * 16), 32, (size_t)spec_cols * sizeof(int), st>>>(
+        wa, spec_cols);
+  }
   GI_CUDA(cudaGetLastError());
   return GI_OK;
 }
