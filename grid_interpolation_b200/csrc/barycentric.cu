@@ -579,6 +579,13 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
     int tri = -1, j0 = -1;
     const int j_stop = max(ix - kMaxBackup, 0);
     for (int j = ix - 1; j >= j_stop; --j) {
+      // phase 1 has classified column j already: one it found outside the hull cannot be the certain INSIDE start
+      // looked for here (passing over a candidate is always safe; a row outside the hull costs 256 loads, not walks)
+      const int jf = w.fast_is_y ? iy : j, js = w.fast_is_y ? j : iy;
+      if (jf >= w.f0 && jf < w.f1 && js >= w.s0 && js < w.s1) {
+        const uint32_t mw = a.mask_words[(int64_t)(js - w.s0) * wpr + ((jf - w.f0) >> 5)];
+        if ((mw >> ((jf - w.f0) & 31)) & 1u) continue;
+      }
       bool inside, amb;
       const int t = walk_checked(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, j, iy, a.num_tri), __ldg(x_axis + j), ty,
                                  a.iter_cap, inside, amb, a.status);
