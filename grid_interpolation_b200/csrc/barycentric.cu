@@ -902,11 +902,13 @@ int bary_walk(const WalkArgs<R>& wa, const PackedMesh<R>& pm, const R* x_axis, c
   {
     const int cols = wa.win.fast_is_y ? wa.win.s1 : wa.win.f1;            // a row is walked from column 0
     const int spec_cols = cols <= kRowSpecMaxCols ? cols : 0;
-    static bool configured = false;  // (per instantiation; the attribute is idempotent)
-    if (!configured) {
+    static bool configured[64] = {};  // per device (the attribute belongs to the device's copy of the kernel)
+    int dev = 0;
+    GI_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
       GI_CUDA(cudaFuncSetAttribute(row_walk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kRowSpecMaxCols * (int)sizeof(int)));
-      configured = true;
+      if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     row_walk_kernel<R><<<std::min(wa.win.fast_is_y ? nf : ns, kNumSMs * 16), 32, (size_t)spec_cols * sizeof(int), st>>>(
         wa, spec_cols);
