@@ -1,6 +1,6 @@
 """Differential fuzz: the reference's Fortran source (interpreted, oracle/f90interp.py) against the C++ oracle on random
 small problems -- both precisions, odd spacings, clustered / on-node / far-outside / rounded points, k up to num_points.
-Build-container tool (needs /root/reference):   python tests/golden/fuzz_f90.py SEED TRIALS
+Build-container tool (needs /root/reference):   python tests/golden/fuzz_f90.py SEED TRIALS [SIZE]
 Prints one line per mismatch and "done seed S bad N".  tests/test_gpu_fuzz.py runs the same generator on the GPU
 against the oracle."""
 import sys, os, time
@@ -14,14 +14,15 @@ FILES=("kd_tree.f90","query_esrg.f90","triangle_walk.f90","interpolation.f90")
 src=[open(os.path.join(REF,f)).read() for f in FILES]
 def farr(a,dt): return np.asfortranarray(np.asarray(a,dtype=dt))
 seed=int(sys.argv[1]) if len(sys.argv)>1 else 0
+SIZE=int(sys.argv[3]) if len(sys.argv)>3 else 1      # scales the number of points and the grid
 rng=np.random.default_rng(seed)
 nbad=0
 for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
     R = np.float64 if rng.uniform()<0.6 else np.float32
     itp=Interpreter(src,R)
-    n=int(rng.integers(3,120))
+    n=int(rng.integers(3,120*SIZE))
     mode=rng.integers(0,6)
-    lx=int(rng.integers(2,14)); ly=int(rng.integers(2,12))
+    lx=int(rng.integers(2,14*SIZE)); ly=int(rng.integers(2,12*SIZE))
     spac=float(rng.choice([1.0,0.5,2.0,0.37]))
     x=(rng.uniform(-5,5)+spac*np.arange(lx)).astype(R); y=(rng.uniform(-5,5)+spac*np.arange(ly)).astype(R)
     if rng.uniform()<0.3:   # axes that are not exactly x(1) + i*spac: the ring windows no longer match the radii
