@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libgridinterp.so")
 
 GI_OK, GI_ERR_BAD_ARG, GI_ERR_NO_DEVICE, GI_ERR_OOM, GI_ERR_CUDA = 0, 1, 2, 3, 4
 GI_ERR_ITER_CAP, GI_ERR_TOO_FEW_POINTS, GI_ERR_BAD_INDEX, GI_ERR_HALO = 5, 6, 7, 8
+GI_ERR_PACK_WINDOW, GI_ERR_TIMEOUT = 9, 10
 GI_HOST, GI_DEVICE = 0, 1
 GI_POINTS_ROWMAJOR, GI_TOPO_ROWMAJOR, GI_FIELD_ROWMAJOR, GI_KD_REFERENCE_VISITS = 1, 2, 4, 8
 GI_ESRG_REFERENCE_ORDER = 16
@@ -16,6 +17,8 @@ GI_KD_EXACT_PRUNE = 32
 GI_BILINEAR_SEARCH_AXES = 64
 GI_KD_FAITHFUL_BUILD = 128
 GI_BARY_REFERENCE_ORDER = 256
+GI_BARY_BAND_PACK = 512
+GI_MAX_GATHER_FIELDS, GI_PEER_HANDLE_BYTES = 8, 64
 
 _vp, _i, _i64, _d, _f = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float
 
@@ -33,6 +36,14 @@ SIGNATURES = {
     "gi_last_timings": ([_vp, _i], _i),
     "gi_last_timing_name": ([_i], C.c_char_p),
     "gi_release_workspace": ([], None),
+    "gi_set_fixup_list_capacity": ([_i64], None),
+    "gi_peer_alloc": ([C.c_uint64], _vp),
+    "gi_peer_free": ([_vp], None),
+    "gi_peer_export": ([_vp, _vp], _i),
+    "gi_peer_open": ([_vp, _vp], _i),
+    "gi_peer_close": ([_vp], _i),
+    "gi_peer_signal": ([_vp, _i, _i, C.c_uint32, _vp], _i),
+    "gi_peer_wait": ([_vp, _i, C.c_uint32, _d, _vp], _i),
     "gi_plan_destroy": ([_vp], None),
 }
 for _suf, _real in (("f64", _d), ("f32", _f)):
@@ -43,6 +54,8 @@ for _suf, _real in (("f64", _d), ("f32", _f)):
         f"gi_barycentric_interpolation_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp], _i),
         f"gi_barycentric_interpolation_ex_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i,
                                                      _vp, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
+        f"gi_barycentric_interpolation_gather_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i,
+                                                         _vp, _i, _i, _vp], _i),
         f"gi_idw_kdtree_ex_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
         f"gi_idw_esrg_nearest_ex_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _real, _i, _i, _i, _vp, _vp, _vp, _vp,
                                             _i, _i, _vp], _i),
@@ -81,6 +94,14 @@ def last_error() -> str:
     return lib().gi_last_error().decode()
 
 
+class GiError(RuntimeError):
+    """A device-side / runtime failure reported by libgridinterp; ``status`` is the gi_status code."""
+
+    def __init__(self, msg, status):
+        super().__init__(msg)
+        self.status = status
+
+
 def check(status: int, what: str) -> None:
     if status == GI_OK:
         return
@@ -89,4 +110,4 @@ def check(status: int, what: str) -> None:
         raise ValueError(msg)
     if status == GI_ERR_OOM:
         raise MemoryError(msg)
-    raise RuntimeError(msg)
+    raise GiError(msg, status)

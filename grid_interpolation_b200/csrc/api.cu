@@ -92,6 +92,8 @@ static const char* status_message(int st) {
     case GI_ERR_TOO_FEW_POINTS: return "fewer source points than num_neighbours";
     case GI_ERR_BAD_INDEX: return "simplices / neighbours contain an id out of range";
     case GI_ERR_HALO: return "hull fill needs rows beyond the supplied halo";
+    case GI_ERR_PACK_WINDOW: return "a walk left the triangles packed for this row band (GI_BARY_BAND_PACK): retry without the flag";
+    case GI_ERR_TIMEOUT: return "gi_peer_wait timed out: a peer did not signal";
     default: return "device-side error";
   }
 }
@@ -163,6 +165,8 @@ void Phases::finish() {
 // ---------------------------------------------------------------------------------------------
 static int64_t g_band_bytes = (int64_t)32 << 20;
 int64_t pipeline_band_bytes() { return g_band_bytes; }
+static int64_t g_fixup_capacity = (int64_t)1 << 22;
+int64_t fixup_list_capacity() { return g_fixup_capacity; }
 
 static thread_local HostPipe t_pipe;
 int host_pipe(HostPipe** out) {
@@ -187,7 +191,7 @@ static int host_stream(cudaStream_t* out) {
 }
 
 static bool valid_flags(int flags) {
-  return (flags & ~(GI_POINTS_ROWMAJOR | GI_TOPO_ROWMAJOR | GI_FIELD_ROWMAJOR | GI_KD_REFERENCE_VISITS | GI_ESRG_REFERENCE_ORDER | GI_KD_EXACT_PRUNE | GI_BILINEAR_SEARCH_AXES | GI_KD_FAITHFUL_BUILD | GI_BARY_REFERENCE_ORDER)) == 0;
+  return (flags & ~(GI_POINTS_ROWMAJOR | GI_TOPO_ROWMAJOR | GI_FIELD_ROWMAJOR | GI_KD_REFERENCE_VISITS | GI_ESRG_REFERENCE_ORDER | GI_KD_EXACT_PRUNE | GI_BILINEAR_SEARCH_AXES | GI_KD_FAITHFUL_BUILD | GI_BARY_REFERENCE_ORDER | GI_BARY_BAND_PACK)) == 0;
 }
 #define GI_CHECK_COMMON()                                                 \
   GI_REQUIRE(valid_flags(flags), "unknown bits in flags");                \
@@ -256,6 +260,45 @@ static int barycentric_api(const R* points, int num_points, const R* data_in, co
   GI_TRY(to_host(st, counters, dcnt, 4));
   ph.finish();
   return read_status(st, true);
+}
+
+template <class R>
+static int barycentric_gather_api(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                                  const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
+                                  int num_tri, int row_begin, int row_end, int halo, R* const* fields, int num_fields,
+                                  int flags, void* stream) {
+  const int mem = GI_DEVICE;
+  GI_CHECK_COMMON();
+  GI_REQUIRE(points && data_in && x_axis && y_axis && simplices && neighbours && fields, "null pointer");
+  GI_REQUIRE(num_points >= 3 && num_tri >= 1 && len_x >= 1 && len_y >= 1, "bad dimensions");
+  GI_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= len_y && halo >= 0, "bad row band");
+  return barycentric_gather_device<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
+                                      num_tri, row_begin, row_end, halo, fields, num_fields, flags, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer memory + signals: the plumbing of the fused gather (one process per GPU, CUDA IPC)
+// ---------------------------------------------------------------------------------------------
+struct PeerFlagPtrs { uint32_t* p[GI_MAX_GATHER_FIELDS]; int n; };
+__global__ void peer_signal_kernel(PeerFlagPtrs f, int slot, uint32_t value) {
+  const int d = threadIdx.x;
+  if (d >= f.n) return;
+  // results were stored by earlier kernels of this stream (complete at the kernel boundary); the fence orders this
+  // thread's view before the flag travels the same NVLink path
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[d] + slot), "r"(value) : "memory");
+}
+__global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t value, long long timeout_cycles, int* status) {
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t cur;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(flags + i) : "memory");
+    if ((int32_t)(cur - value) >= 0) break;  // wrap-safe "cur >= value"
+    if (clock64() - t0 > timeout_cycles) { raise_status(status, GI_ERR_TIMEOUT); break; }
+    __nanosleep(200);
+  }
 }
 
 template <class R>
@@ -458,6 +501,61 @@ GI_API int gi_last_timings(double* ms, int capacity) {
 GI_API const char* gi_last_timing_name(int i) {
   return (i >= 0 && i < (int)t_rec.names.size()) ? t_rec.names[i].c_str() : "";
 }
+GI_API void gi_set_fixup_list_capacity(int64_t targets) { g_fixup_capacity = targets > 0 ? targets : ((int64_t)1 << 22); }
+
+GI_API void* gi_peer_alloc(uint64_t bytes) {
+  if (ensure_device() != GI_OK) return nullptr;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {  // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+    cudaGetLastError();
+    set_error("cudaMalloc failed in gi_peer_alloc");
+    return nullptr;
+  }
+  cudaMemset(p, 0, bytes ? bytes : 16);
+  return p;
+}
+GI_API void gi_peer_free(void* p) { if (p) cudaFree(p); }
+GI_API int gi_peer_export(void* p, void* handle64) {
+  GI_REQUIRE(p && handle64, "null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == GI_PEER_HANDLE_BYTES, "handle size");
+  cudaIpcMemHandle_t h;
+  GI_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle64, &h, sizeof(h));
+  return GI_OK;
+}
+GI_API int gi_peer_open(const void* handle64, void** p) {
+  GI_REQUIRE(handle64 && p, "null pointer");
+  GI_TRY(ensure_device());
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  GI_CUDA(cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
+  return GI_OK;
+}
+GI_API int gi_peer_close(void* p) {
+  if (p) GI_CUDA(cudaIpcCloseMemHandle(p));
+  return GI_OK;
+}
+GI_API int gi_peer_signal(uint32_t* const* flag_arrays, int num, int slot, uint32_t value, void* stream) {
+  GI_REQUIRE(flag_arrays && num >= 1 && num <= GI_MAX_GATHER_FIELDS && slot >= 0, "bad arguments");
+  PeerFlagPtrs f;
+  f.n = num;
+  for (int d = 0; d < num; ++d) { GI_REQUIRE(flag_arrays[d] != nullptr, "null flag array"); f.p[d] = flag_arrays[d]; }
+  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, slot, value);
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+GI_API int gi_peer_wait(const uint32_t* flags, int num_slots, uint32_t value, double timeout_s, void* stream) {
+  GI_REQUIRE(flags && num_slots >= 1 && num_slots <= 1024, "bad arguments");
+  StatusSlot slot;
+  GI_TRY(get_status_slot((cudaStream_t)stream, &slot));
+  if (!(timeout_s > 0.0) || timeout_s > 30.0) timeout_s = 30.0;  // never an unbounded spin on the device
+  peer_wait_kernel<<<1, (num_slots + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(flags, num_slots, value,
+                                                                             (long long)(timeout_s * 2.0e9), slot.dev);
+  GI_CUDA(cudaGetLastError());
+  GI_TRY(flush_status((cudaStream_t)stream, slot));
+  return GI_OK;
+}
+
 GI_API void gi_release_workspace(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
@@ -547,6 +645,14 @@ GI_API void gi_plan_destroy(gi_plan* plan) {
     return barycentric_api<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,    \
                               num_triangles, row_begin, row_end, halo, data_ip, tri_out, mask_out, fill_src,       \
                               counters, flags, mem, stream);                                                       \
+  }                                                                                                                 \
+  GI_API int gi_barycentric_interpolation_gather_##SUF(                                                             \
+      const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis, int len_y,   \
+      const int32_t* simplices, const int32_t* neighbours, int num_triangles, int row_begin, int row_end,          \
+      int halo, R* const* fields, int num_fields, int flags, void* stream) {                                       \
+    return barycentric_gather_api<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices,         \
+                                     neighbours, num_triangles, row_begin, row_end, halo, fields, num_fields,      \
+                                     flags, stream);                                                                \
   }                                                                                                                 \
   GI_API int gi_barycentric_plan_create_##SUF(const R* points, int num_points, const R* x_axis, int len_x,         \
                                               const R* y_axis, int len_y, const int32_t* simplices,                \

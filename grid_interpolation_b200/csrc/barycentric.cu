@@ -110,14 +110,46 @@ __device__ __forceinline__ SeedGrid<R> seed_grid_of(const R* __restrict__ x_axis
   return s;
 }
 
+// Row-band calls (multi-GPU sharding) need only the triangles near their band.  need_kernel marks the triangles
+// whose y-range meets [y_lo, y_hi] (the walked rows +- a margin): 3 y gathers per triangle from an array that stays
+// L2-resident, no record traffic.  pack_mesh_kernel then skips the others, and a link from a packed triangle to a
+// skipped one becomes kNotPacked: a walk that wants to cross it raises GI_ERR_PACK_WINDOW instead of reading a
+// record that was never written (the caller retries with the whole mesh packed).
+constexpr int kNotPacked = -2;
+template <class R>
+__global__ void __launch_bounds__(256)
+need_kernel(PointsView<R> pts, TopoView simp, int num_points, int num_tri, const R* __restrict__ y_axis, int row_lo,
+            int row_hi, int len_y, uint8_t* __restrict__ need) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_tri) return;
+  // y-range of the packed rows; open towards a grid border so that walks to targets of the first / last rows,
+  // which may lie outside the hull, never meet a skipped triangle on that side
+  const R ya0 = __ldg(y_axis + row_lo), ya1 = __ldg(y_axis + row_hi);
+  const bool up = ya1 >= ya0;
+  const bool open_lo = up ? row_lo == 0 : row_hi == len_y - 1, open_hi = up ? row_hi == len_y - 1 : row_lo == 0;
+  const R y_lo = open_lo ? -Consts<R>::huge() : fmin(ya0, ya1), y_hi = open_hi ? Consts<R>::huge() : fmax(ya0, ya1);
+  const int a = simp(t, 0), b = simp(t, 1), c = simp(t, 2);
+  if ((unsigned)(a - 1) >= (unsigned)num_points || (unsigned)(b - 1) >= (unsigned)num_points ||
+      (unsigned)(c - 1) >= (unsigned)num_points) {
+    need[t] = 1;  // pack_mesh_kernel reports the bad id
+    return;
+  }
+  const R ya = pts.y(a - 1), yb = pts.y(b - 1), yc = pts.y(c - 1);
+  need[t] = (fmax(fmax(ya, yb), yc) >= y_lo && fmin(fmin(ya, yb), yc) <= y_hi) ? 1 : 0;
+}
+
 template <class R>
 __global__ void __launch_bounds__(256)
 pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, TopoView nbr, int num_points,
                  int num_tri, TriGeom<R>* __restrict__ geom, int* __restrict__ seed,
                  const R* __restrict__ x_axis, int len_x, const R* __restrict__ y_axis, int len_y,
-                 int* __restrict__ status) {
+                 const uint8_t* __restrict__ need, int* __restrict__ status) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= num_tri) return;
+  const bool packed = t < num_tri && (!need || need[t]);
+  // fallback seed (seed[ncx*ncy]): the smallest packed triangle id
+  const unsigned pm = __ballot_sync(0xffffffffu, packed);
+  if (pm && (threadIdx.x & 31) == __ffs(pm) - 1) atomicMin(seed + ((len_x + kSeedCell - 1) / kSeedCell) * ((len_y + kSeedCell - 1) / kSeedCell), t);
+  if (!packed) return;
   const SeedGrid<R> sg = seed_grid_of(x_axis, len_x, y_axis, len_y);
   int a = simp(t, 0), b = simp(t, 1), c = simp(t, 2);
   int n1 = nbr(t, 0), n2 = nbr(t, 1), n3 = nbr(t, 2);
@@ -134,6 +166,11 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
   pts.xy(b - 1, g.x2, g.y2);
   pts.xy(c - 1, g.x3, g.y3);
   g.n1 = n1 - 1; g.n2 = n2 - 1; g.n3 = n3 - 1;
+  if (need) {
+    if (n1 > 0 && !need[n1 - 1]) g.n1 = kNotPacked;
+    if (n2 > 0 && !need[n2 - 1]) g.n2 = kNotPacked;
+    if (n3 > 0 && !need[n3 - 1]) g.n3 = kNotPacked;
+  }
   g.pad = amb_threshold(g);
   g.d1 = __ldg(data + (a - 1)); g.d2 = __ldg(data + (b - 1)); g.d3 = __ldg(data + (c - 1));
   g.padv = R(0);
@@ -175,7 +212,8 @@ __device__ __forceinline__ int seed_lookup(const int* __restrict__ seed, int ncx
         s = __ldg(seed + y * ncx + x);
         if (s < num_tri) return s;
       }
-  return 0;
+  s = __ldg(seed + ncx * ncy);  // the smallest packed triangle id
+  return s < num_tri ? s : 0;
 }
 
 // triangle_walk.f90:24-84 + :140-153.  Returns the triangle the walk ends in and leaves its record in g;
@@ -200,7 +238,11 @@ __device__ __forceinline__ int walk(const TriGeom<R>* __restrict__ geom, int tri
     else if (c2 < margin) nxt = g.n1;
     else if (c3 < margin) nxt = g.n2;
     else break;
-    if (nxt < 0) { inside = false; break; }  // :74-80
+    if (nxt < 0) {  // :74-80
+      if (nxt == kNotPacked) raise_status(status, GI_ERR_PACK_WINDOW);
+      inside = false;
+      break;
+    }
     tri = nxt;
     if (it >= iter_cap) { raise_status(status, GI_ERR_ITER_CAP); inside = false; break; }
   }
@@ -269,12 +311,26 @@ __device__ __forceinline__ int walk_checked(const TriGeom<R>* __restrict__ geom,
     else if (c2 < margin) { nxt = g.n1; cf = c2; }
     else if (c3 < margin) { nxt = g.n2; cf = c3; }
     else { amb = in_amb_band(c1, g.pad) | in_amb_band(c2, g.pad) | in_amb_band(c3, g.pad); break; }
-    if (nxt < 0) { inside = false; amb = in_amb_band(cf, g.pad); break; }
+    if (nxt < 0) {
+      if (nxt == kNotPacked && status) raise_status(status, GI_ERR_PACK_WINDOW);
+      inside = false; amb = in_amb_band(cf, g.pad); break;
+    }
     tri = nxt;
     if (it >= iter_cap) { if (status) raise_status(status, GI_ERR_ITER_CAP); inside = false; amb = false; break; }
   }
   return tri;
 }
+
+// Multi-GPU gather fused into the kernels (north_star "final gather of the output field"): every store
+// of a result -- phase 2 of locate_eval_kernel, the fix-up paths, the hull fill -- goes to the local field and to the
+// same element of up to kMaxPeers peer fields over NVLink, so the band arrives at its owners while the rest of
+// the band is still being computed and no separate collective runs afterwards.
+constexpr int kMaxPeers = GI_MAX_GATHER_FIELDS - 1;
+template <class R> struct GatherDest {
+  R* peer[kMaxPeers];
+  int n_peer;
+  int64_t ld;  // 0 = band-shaped contiguous
+};
 
 template <class R> struct WalkArgs {
   TargetWindow<R> win;   // walked window E (band + halo)
@@ -282,7 +338,10 @@ template <class R> struct WalkArgs {
   const TriGeom<R>* geom;
   const int* seed;
   int ncx, ncy, num_tri, iter_cap;
-  R* out;               // band-shaped: (bs1-bs0) slow rows of (bf1-bf0)
+  R* out;               // band-shaped: (bs1-bs0) slow rows of (bf1-bf0), `out_ld` elements from one slow row to the next
+  int64_t out_ld;
+  R* peer_out[kMaxPeers];  // the same band in the fields of other GPUs (peer-mapped device memory), see GatherDest
+  int n_peer;
   int32_t* tri_out;     // optional, band-shaped
   uint32_t* mask_words; // E-shaped bit mask: ((nf+31)/32) words per slow row
   int* nz_words;        // compact list of the mask words that are non-zero (work list of the hull fill)
@@ -375,6 +434,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
         if (it < a.iter_cap) { enter(nxt); continue; }
         raise_status(a.status, GI_ERR_ITER_CAP);
       }
+      if (outside && nxt == kNotPacked) raise_status(a.status, GI_ERR_PACK_WINDOW);  // band-limited pack too tight
       // resolved: inside `tri`, or outside the hull (:74-80: the last valid triangle is kept).
       // A target within the margin band of an edge is accepted by both adjacent triangles and which one the
       // reference returns depends on its walk path: flag it for fixup_kernel.
@@ -416,6 +476,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
     const bool inside = t >= 0;
     if (f_in_band && s >= a.bs0 && s < a.bs1) {
       const int64_t o = (int64_t)(s - a.bs0) * bnf + (f - a.bf0);
+      const int64_t oo = (int64_t)(s - a.bs0) * a.out_ld + (f - a.bf0);
       if (inside) {
         if (t != cur) {  // records were touched by phase 1: L1 hits
           TriGeom<R> g;
@@ -433,7 +494,9 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
         R w1, w2;
         quotient_pair(dv, FY ? q1 * t3 + c1 : c1 + q1 * t3, FY ? q2 * t3 + c2 : c2 + q2 * t3, w1, w2);
         const R w3 = R(1) - w1 - w2;
-        a.out[o] = d1 * w1 + d2 * w2 + d3 * w3;                   // :396-398
+        const R v = d1 * w1 + d2 * w2 + d3 * w3;                   // :396-398
+        a.out[oo] = v;
+        for (int d = 0; d < a.n_peer; ++d) a.peer_out[d][oo] = v;
       }
       if (a.tri_out) a.tri_out[o] = (inside ? t : ~t) + 1;
     }
@@ -460,7 +523,10 @@ __device__ __forceinline__ void publish_target(const WalkArgs<R>& a, int f, int 
       TriGeom<R> g;
       load_walk(a.geom + tri, g);
       load_values(a.geom + tri, g);
-      a.out[o] = eval_value(g, tx, ty);
+      const int64_t oo = (int64_t)(s - a.bs0) * a.out_ld + (f - a.bf0);
+      const R v = eval_value(g, tx, ty);
+      a.out[oo] = v;
+      for (int d = 0; d < a.n_peer; ++d) a.peer_out[d][oo] = v;
     }
     if (a.tri_out) a.tri_out[o] = (inside ? tri : ~tri) + 1;
   }
@@ -484,10 +550,27 @@ __device__ __forceinline__ void publish_target(const WalkArgs<R>& a, int f, int 
 // is unambiguous (any walk finds that one), or to column 0 and the reference's start triangle, then walk forward
 // column by column.
 // ---------------------------------------------------------------------------------------------
+template <class R> struct RawMesh {  // the caller's arrays: what a band-limited pack did not turn into records
+  PointsView<R> pts;
+  TopoView simp;
+  int num_points;
+  int use;  // 1: records may be missing, read the raw arrays
+};
 template <class R>
-__device__ __forceinline__ unsigned long long start_tri_dist(const TriGeom<R>* geom, int i, R opt_x, R opt_y) {
+__device__ __forceinline__ unsigned long long start_tri_dist(const TriGeom<R>* geom, const RawMesh<R>& raw, int i, R opt_x,
+                                                             R opt_y) {
   TriGeom<R> g;
-  load_walk(geom + i, g);
+  if (raw.use) {
+    int a = raw.simp(i, 0), b = raw.simp(i, 1), c = raw.simp(i, 2);
+    if ((unsigned)(a - 1) >= (unsigned)raw.num_points || (unsigned)(b - 1) >= (unsigned)raw.num_points ||
+        (unsigned)(c - 1) >= (unsigned)raw.num_points)
+      a = b = c = 1;  // as pack_mesh_kernel makes an invalid record harmless
+    raw.pts.xy(a - 1, g.x1, g.y1);
+    raw.pts.xy(b - 1, g.x2, g.y2);
+    raw.pts.xy(c - 1, g.x3, g.y3);
+  } else {
+    load_walk(geom + i, g);
+  }
   const R cx = ((g.x1 + g.x2) + g.x3) / R(3), cy = ((g.y1 + g.y2) + g.y3) / R(3);   // :348-349
   const double d = (double)((cx - opt_x) * (cx - opt_x) + (cy - opt_y) * (cy - opt_y));  // :350
   return (unsigned long long)__double_as_longlong(d);  // non-negative doubles order like their bit patterns
@@ -502,7 +585,7 @@ __device__ __forceinline__ unsigned long long start_tri_dist(const TriGeom<R>* g
 constexpr int kStartBlocks = 296;
 template <class R>
 __global__ void __launch_bounds__(256)
-start_tri_kernel(const TriGeom<R>* __restrict__ geom, int n_search, const R* __restrict__ x_axis,
+start_tri_kernel(const TriGeom<R>* __restrict__ geom, const RawMesh<R> raw, int n_search, const R* __restrict__ x_axis,
                  const R* __restrict__ y_axis, int len_y, int64_t* counters, unsigned long long* part, int force) {
   if (counters[5] == 0 && !force) return;
   __shared__ R s_opt_y;
@@ -520,7 +603,7 @@ start_tri_kernel(const TriGeom<R>* __restrict__ geom, int n_search, const R* __r
     if (d < bd || (d == bd && i < bi)) { bd = d; bi = i; }
   };
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_search; i += gridDim.x * blockDim.x)
-    take(start_tri_dist(geom, i, ox, oy), (unsigned long long)i);
+    take(start_tri_dist(geom, raw, i, ox, oy), (unsigned long long)i);
   auto block_reduce = [&]() {
     for (int off = 16; off > 0; off >>= 1)
       take(__shfl_xor_sync(0xffffffffu, bd, off), __shfl_xor_sync(0xffffffffu, bi, off));
@@ -556,12 +639,8 @@ start_tri_kernel(const TriGeom<R>* __restrict__ geom, int n_search, const R* __r
 }
 
 constexpr int kMaxBackup = 256;
-// entries of the fix-up work list (GI_AMB_CAP shrinks it: tests of the overflow path)
-inline int64_t amb_list_limit() {
-  const char* e = getenv("GI_AMB_CAP");
-  const long long v = e ? atoll(e) : 0;
-  return v > 0 ? (int64_t)v : (int64_t)1 << 22;
-}
+// entries of the fix-up work list (gi_set_fixup_list_capacity shrinks it: tests of the overflow path)
+inline int64_t amb_list_limit() { return fixup_list_capacity(); }  // gi_set_fixup_list_capacity (api.cu)
 
 template <class R>
 __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len_x, int len_y) {
@@ -716,7 +795,10 @@ template <class R> struct FillArgs {
   int bf0, bf1, bs0, bs1;  // band B inside E: the cells to fill
   int vf0, vf1, vs0, vs1;  // V, B <= V: the cells whose final value can be read from `out` (out is V-shaped)
   int64_t nz_shift;        // added to the entries of nz_words (they may be relative to another window origin)
-  R* out;
+  R* out;                  // V-shaped, `out_ld` elements from one slow row to the next
+  int64_t out_ld;
+  R* peer_out[kMaxPeers];  // the same cells in the peer fields (filled values are stored there as well)
+  int n_peer;
   int64_t* fill_src;  // optional, band-shaped
   int64_t* counters;  // [1] += masked cells, [2] = max level, [4] = number of nz_words
   int len_x, len_y;
@@ -802,7 +884,7 @@ __global__ void __launch_bounds__(128) fill_kernel(const FillArgs<R> a) {
     const int sf = a.win.fast_is_y ? best_i : best_j, ss = a.win.fast_is_y ? best_j : best_i;
     R v;
     if (sf >= a.vf0 && sf < a.vf1 && ss >= a.vs0 && ss < a.vs1) {
-      v = a.out[(int64_t)(ss - a.vs0) * (a.vf1 - a.vf0) + (sf - a.vf0)];
+      v = a.out[(int64_t)(ss - a.vs0) * a.out_ld + (sf - a.vf0)];
     } else {  // source cell lies in the halo: recompute its (deterministic) value
       const R tx = __ldg((a.win.fast_is_y ? a.win.slow_axis : a.win.fast_axis) + best_j);
       const R ty = __ldg((a.win.fast_is_y ? a.win.fast_axis : a.win.slow_axis) + best_i);
@@ -811,7 +893,9 @@ __global__ void __launch_bounds__(128) fill_kernel(const FillArgs<R> a) {
                            a.iter_cap, inside, iters, g, a.status);
       v = eval_value(g, tx, ty);
     }
-    a.out[(int64_t)(s - a.vs0) * (a.vf1 - a.vf0) + (f - a.vf0)] = v;  // :121
+    const int64_t oo = (int64_t)(s - a.vs0) * a.out_ld + (f - a.vf0);
+    a.out[oo] = v;  // :121
+    for (int d = 0; d < a.n_peer; ++d) a.peer_out[d][oo] = v;
     if (a.fill_src)
       a.fill_src[(int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0)] = (int64_t)best_i * a.len_x + best_j;
   }
@@ -858,24 +942,41 @@ template <class R> struct PackedMesh {
   TriGeom<R>* geom;
   int* seed;
   int ncx, ncy, num_tri;
+  RawMesh<R> raw;  // raw.use = 1: only the triangles near the row window have records
 };
+
+// rows [w0, w1) +- this many rows are packed by a band-limited pack (GI_BARY_BAND_PACK)
+constexpr int kPackMarginRows = 48;
 
 // 1. pack the mesh (device pointers; records and seed grid live in `scr`)
 template <class R>
 int bary_pack(Scratch& scr, const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
               const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours, int num_tri, int flags,
-              int* status, PackedMesh<R>* pm) {
+              int* status, PackedMesh<R>* pm, int w0 = 0, int w1 = -1) {
   cudaStream_t st = scr.stream();
   GI_TRY(scr.alloc(&pm->geom, (size_t)num_tri));
   pm->ncx = (len_x + kSeedCell - 1) / kSeedCell;
   pm->ncy = (len_y + kSeedCell - 1) / kSeedCell;
   pm->num_tri = num_tri;
-  GI_TRY(scr.alloc(&pm->seed, (size_t)pm->ncx * pm->ncy));
-  GI_CUDA(cudaMemsetAsync(pm->seed, 0x7f, sizeof(int) * (size_t)pm->ncx * pm->ncy, st));
+  GI_TRY(scr.alloc(&pm->seed, (size_t)pm->ncx * pm->ncy + 1));  // + the fallback seed
+  GI_CUDA(cudaMemsetAsync(pm->seed, 0x7f, sizeof(int) * ((size_t)pm->ncx * pm->ncy + 1), st));
+  const PointsView<R> pv = points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR);
+  const TopoView sv = topo_t3(simplices, num_tri, flags & GI_TOPO_ROWMAJOR);
+  pm->raw = RawMesh<R>{pv, sv, num_points, 0};
+  uint8_t* need = nullptr;
+  // band-limited pack: rows [w0, w1) +- kPackMarginRows, when that is a real subset of the grid
+  if (w1 < 0) w1 = len_y;
+  const int p0 = std::max(0, w0 - kPackMarginRows), p1 = std::min(len_y, w1 + kPackMarginRows);
+  if ((flags & GI_BARY_BAND_PACK) && (p0 > 0 || p1 < len_y) && p0 < p1) {
+    // (need_kernel takes the row numbers and reads the axis itself: no host copy of the axis, no synchronisation)
+    GI_TRY(scr.alloc(&need, (size_t)num_tri));
+    need_kernel<R><<<div_up(num_tri, 256), 256, 0, st>>>(pv, sv, num_points, num_tri, y_axis, p0, p1 - 1, len_y, need);
+    GI_CUDA(cudaGetLastError());
+    pm->raw.use = 1;
+  }
   pack_mesh_kernel<R><<<div_up(num_tri, 256), 256, 0, st>>>(
-      points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR), data_in,
-      topo_t3(simplices, num_tri, flags & GI_TOPO_ROWMAJOR), topo_t3(neighbours, num_tri, flags & GI_TOPO_ROWMAJOR),
-      num_points, num_tri, pm->geom, pm->seed, x_axis, len_x, y_axis, len_y, status);
+      pv, data_in, sv, topo_t3(neighbours, num_tri, flags & GI_TOPO_ROWMAJOR),
+      num_points, num_tri, pm->geom, pm->seed, x_axis, len_x, y_axis, len_y, need, status);
   GI_CUDA(cudaGetLastError());
   return GI_OK;
 }
@@ -895,7 +996,7 @@ int bary_walk(const WalkArgs<R>& wa, const PackedMesh<R>& pm, const R* x_axis, c
   GI_CUDA(cudaGetLastError());
   // targets inside the margin band of an edge: follow the reference's own path (normally none)
   const int n_search = std::min(num_points, pm.num_tri);  // the reference searches triangles 1..num_points (:347)
-  start_tri_kernel<R><<<kStartBlocks, 256, 0, st>>>(pm.geom, n_search, x_axis, y_axis, len_y, wa.counters,
+  start_tri_kernel<R><<<kStartBlocks, 256, 0, st>>>(pm.geom, pm.raw, n_search, x_axis, y_axis, len_y, wa.counters,
                                                     wa.start_part, wa.reference_rows);
   fixup_kernel<R><<<kNumSMs * 2, 128, 0, st>>>(wa, len_x, len_y);
   // more flagged targets than the list holds, or GI_BARY_REFERENCE_ORDER: the reference's row-sequential walk
@@ -929,7 +1030,7 @@ template <class R>
 int bary_run_window(Scratch& scr, const PackedMesh<R>& pm, const R* x_axis, int len_x, const R* y_axis, int len_y,
                     int num_points, int row_begin, int row_end, int halo, R* data_ip, int32_t* tri_out,
                     uint8_t* mask_out, int64_t* fill_src, int64_t* counters_out, int flags, const StatusSlot& slot,
-                    cudaStream_t st, Phases* ph) {
+                    cudaStream_t st, Phases* ph, const GatherDest<R>* dest = nullptr) {
   const int num_tri = pm.num_tri;
   int64_t* counters; int* nz_words;
   GI_TRY(scr.alloc(&counters, 8));
@@ -963,6 +1064,9 @@ int bary_run_window(Scratch& scr, const PackedMesh<R>& pm, const R* x_axis, int 
   wa.geom = pm.geom; wa.seed = pm.seed; wa.ncx = pm.ncx; wa.ncy = pm.ncy; wa.num_tri = num_tri;
   wa.iter_cap = num_tri + 16;
   wa.out = data_ip; wa.tri_out = tri_out; wa.mask_words = mask_words; wa.counters = counters;
+  wa.out_ld = (dest && dest->ld) ? dest->ld : wa.bf1 - wa.bf0;
+  wa.n_peer = dest ? dest->n_peer : 0;
+  for (int d = 0; d < wa.n_peer; ++d) wa.peer_out[d] = dest->peer[d];
   wa.status = slot.dev;
   GI_TRY(bary_walk<R>(wa, pm, x_axis, y_axis, len_x, len_y, num_points, st));
   if (mask_out || fill_src) {
@@ -978,6 +1082,8 @@ int bary_run_window(Scratch& scr, const PackedMesh<R>& pm, const R* x_axis, int 
   fa.bf0 = wa.bf0; fa.bf1 = wa.bf1; fa.bs0 = wa.bs0; fa.bs1 = wa.bs1;
   fa.vf0 = wa.bf0; fa.vf1 = wa.bf1; fa.vs0 = wa.bs0; fa.vs1 = wa.bs1;
   fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters;
+  fa.out_ld = wa.out_ld; fa.n_peer = wa.n_peer;
+  for (int d = 0; d < wa.n_peer; ++d) fa.peer_out[d] = wa.peer_out[d];
   fill_from_walk(fa, wa, pm, len_x, len_y);
   fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
   GI_CUDA(cudaGetLastError());
@@ -991,12 +1097,13 @@ int bary_run_window(Scratch& scr, const PackedMesh<R>& pm, const R* x_axis, int 
 // ---------------------------------------------------------------------------------------------
 // host-side orchestration (device pointers in, work enqueued on `st`)
 // ---------------------------------------------------------------------------------------------
+namespace {
 template <class R>
-int barycentric_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
-                       const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
-                       int num_tri, int row_begin, int row_end, int halo, R* data_ip, int32_t* tri_out,
-                       uint8_t* mask_out, int64_t* fill_src, int64_t* counters_out, int flags,
-                       cudaStream_t st) {
+int barycentric_device_impl(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                            const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
+                            int num_tri, int row_begin, int row_end, int halo, R* data_ip, int32_t* tri_out,
+                            uint8_t* mask_out, int64_t* fill_src, int64_t* counters_out, int flags,
+                            cudaStream_t st, const GatherDest<R>* dest) {
   GI_REQUIRE(num_points >= 3 && num_tri >= 1, "need at least 3 points and 1 triangle");
   GI_REQUIRE(len_x >= 1 && len_y >= 1, "empty axis");
   GI_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= len_y, "row band out of range");
@@ -1012,12 +1119,46 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
   ph.mark("pack_mesh");
   PackedMesh<R> pm;
   GI_TRY(bary_pack<R>(scr, points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours, num_tri,
-                      flags, slot.dev, &pm));
+                      flags, slot.dev, &pm, std::max(0, row_begin - halo), std::min(len_y, row_end + halo)));
   GI_TRY(bary_run_window<R>(scr, pm, x_axis, len_x, y_axis, len_y, num_points, row_begin, row_end, halo, data_ip,
-                            tri_out, mask_out, fill_src, counters_out, flags, slot, st, &ph));
+                            tri_out, mask_out, fill_src, counters_out, flags, slot, st, &ph, dest));
   ph.finish();
   GI_TRY(flush_status(st, slot));
   return GI_OK;
+}
+}  // namespace
+
+template <class R>
+int barycentric_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                       const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
+                       int num_tri, int row_begin, int row_end, int halo, R* data_ip, int32_t* tri_out,
+                       uint8_t* mask_out, int64_t* fill_src, int64_t* counters_out, int flags,
+                       cudaStream_t st) {
+  return barycentric_device_impl<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
+                                    num_tri, row_begin, row_end, halo, data_ip, tri_out, mask_out, fill_src,
+                                    counters_out, flags, st, nullptr);
+}
+
+// Row band [row_begin, row_end) computed here and stored at its place in `num_fields` full (len_y, len_x) fields:
+// fields[0] is local (the hull fill reads source cells from it), the others are the same field on other GPUs
+// (peer-mapped).  The stores of the walk / fix-up / fill kernels are the gather.
+template <class R>
+int barycentric_gather_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                              const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
+                              int num_tri, int row_begin, int row_end, int halo, R* const* fields, int num_fields,
+                              int flags, cudaStream_t st) {
+  GI_REQUIRE(fields && num_fields >= 1 && num_fields <= GI_MAX_GATHER_FIELDS, "1 .. GI_MAX_GATHER_FIELDS fields");
+  for (int d = 0; d < num_fields; ++d) GI_REQUIRE(fields[d] != nullptr, "null field pointer");
+  const bool rowmajor = flags & GI_FIELD_ROWMAJOR;
+  // element (iy, ix) of a full field: iy*len_x + ix (row-major) or iy + ix*len_y (column-major)
+  const int64_t off = rowmajor ? (int64_t)row_begin * len_x : (int64_t)row_begin;
+  GatherDest<R> dest;
+  dest.ld = rowmajor ? len_x : len_y;
+  dest.n_peer = num_fields - 1;
+  for (int d = 1; d < num_fields; ++d) dest.peer[d - 1] = fields[d] + off;
+  return barycentric_device_impl<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, simplices, neighbours,
+                                    num_tri, row_begin, row_end, halo, fields[0] + off, nullptr, nullptr, nullptr,
+                                    nullptr, flags, st, &dest);
 }
 
 namespace {
@@ -1086,6 +1227,7 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
       // every band cell walked so far holds its final value
       fa.vf0 = bf0; fa.vf1 = bf1; fa.vs0 = bs0; fa.vs1 = (int)std::max<int64_t>(std::min<int64_t>(f1, bs1), bs0);
       fa.out = dout; fa.fill_src = nullptr; fa.counters = counters + 8 * b;
+      fa.out_ld = bnf; fa.n_peer = 0;
       fill_from_walk(fa, was[b], pm, len_x, len_y);
       fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
       GI_CUDA(cudaGetLastError());
@@ -1104,6 +1246,7 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
         wa.geom = pm.geom; wa.seed = pm.seed; wa.ncx = pm.ncx; wa.ncy = pm.ncy; wa.num_tri = num_tri;
         wa.iter_cap = num_tri + 16;
         wa.out = dout + (int64_t)(wa.bs0 - bs0) * bnf; wa.tri_out = nullptr;
+        wa.out_ld = bnf; wa.n_peer = 0;
         wa.mask_words = mask_words + (start[b] - es0) * wpr; wa.nz_words = nz_words + (start[b] - es0) * wpr;
         wa.counters = counters + 8 * b;
         wa.amb_list = amb_list; wa.amb_cap = amb_cap; wa.start_part = start_part;
@@ -1153,14 +1296,25 @@ int barycentric_host(const R* points, int num_points, const R* data_in, const R*
   GI_TRY(to_device(scr, simplices, (size_t)3 * num_tri, &ds));
   GI_TRY(to_device(scr, neighbours, (size_t)3 * num_tri, &dn));
   GI_TRY(scr.alloc(&dout, (size_t)len_x * (row_end - row_begin)));
-  ph.mark("pack_mesh");
-  PackedMesh<R> pm;
-  GI_TRY(bary_pack<R>(scr, dp, num_points, dd, dx, len_x, dy, len_y, ds, dn, num_tri, flags, slot.dev, &pm));
-  ph.mark("walk");
-  const int status = bary_run_banded<R>(pipe, scr, pm, dx, len_x, dy, len_y, num_points, row_begin, row_end, halo,
-                                        dout, data_ip, flags, slot);
-  ph.finish();
-  return status;
+  // a band that is a small part of the grid packs only the triangles near it; a walk that would leave them
+  // (GI_ERR_PACK_WINDOW) makes the call start over with the whole mesh (this path synchronises anyway)
+  const int e0 = std::max(0, row_begin - halo), e1 = std::min(len_y, row_end + halo);
+  int pack_flags = flags & ~GI_BARY_BAND_PACK;
+  if ((int64_t)(e1 - e0 + 2 * kPackMarginRows) * 2 <= len_y) pack_flags |= GI_BARY_BAND_PACK;
+  for (;;) {
+    ph.mark("pack_mesh");
+    PackedMesh<R> pm;
+    GI_TRY(bary_pack<R>(scr, dp, num_points, dd, dx, len_x, dy, len_y, ds, dn, num_tri, pack_flags, slot.dev, &pm, e0, e1));
+    ph.mark("walk");
+    const int status = bary_run_banded<R>(pipe, scr, pm, dx, len_x, dy, len_y, num_points, row_begin, row_end, halo,
+                                          dout, data_ip, flags, slot);
+    if (status == GI_ERR_PACK_WINDOW && (pack_flags & GI_BARY_BAND_PACK)) {
+      pack_flags &= ~GI_BARY_BAND_PACK;
+      continue;
+    }
+    ph.finish();
+    return status;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1287,6 +1441,7 @@ int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* 
   fa.mask_words = words; fa.nz_words = nz_words; fa.nz_shift = 0; fa.bf0 = 0; fa.bf1 = nf; fa.bs0 = 0; fa.bs1 = ns;
   fa.vf0 = 0; fa.vf1 = nf; fa.vs0 = 0; fa.vs1 = ns;
   fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters; fa.len_x = len_x; fa.len_y = len_y;
+  fa.out_ld = nf; fa.n_peer = 0;
   fa.geom = nullptr; fa.seed = nullptr; fa.ncx = fa.ncy = fa.num_tri = fa.iter_cap = 0;
   fa.status = slot.dev;
   fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
@@ -1299,6 +1454,9 @@ int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* 
   template int barycentric_device<R>(const R*, int, const R*, const R*, int, const R*, int, const int32_t*, \
                                      const int32_t*, int, int, int, int, R*, int32_t*, uint8_t*, int64_t*,  \
                                      int64_t*, int, cudaStream_t);                                          \
+  template int barycentric_gather_device<R>(const R*, int, const R*, const R*, int, const R*, int,         \
+                                            const int32_t*, const int32_t*, int, int, int, int, R* const*, \
+                                            int, int, cudaStream_t);                                        \
   template int fill_device<R>(const uint8_t*, int, int, R*, int64_t*, int, cudaStream_t);                   \
   template int barycentric_host<R>(const R*, int, const R*, const R*, int, const R*, int, const int32_t*,   \
                                    const int32_t*, int, int, int, int, R*, int);                            \

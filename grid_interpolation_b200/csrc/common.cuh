@@ -205,6 +205,7 @@ struct HostPipe {
 int host_pipe(HostPipe** out);  // per host thread, created on first use (api.cu)
 // bands of at least ~32 MB of output (a PCIe transfer of that size is near its peak rate), at most kMaxBands
 int64_t pipeline_band_bytes();  // gi_set_pipeline_band_bytes(), default 32 MB (api.cu)
+int64_t fixup_list_capacity();  // gi_set_fixup_list_capacity(), default 4 Mi targets (api.cu)
 inline int plan_bands(int64_t extent, int64_t bytes) {
   int64_t nb = bytes / pipeline_band_bytes();
   if (nb > kMaxBands) nb = kMaxBands;

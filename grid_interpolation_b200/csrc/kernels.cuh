@@ -17,6 +17,13 @@ int barycentric_device(const R* points, int num_points, const R* data_in, const 
                        const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
                        int num_tri, int row_begin, int row_end, int halo, R* data_ip, int32_t* tri_out,
                        uint8_t* mask_out, int64_t* fill_src, int64_t* counters, int flags, cudaStream_t st);
+// multi-GPU form: the band is stored at its place in num_fields full (len_y, len_x) fields (fields[0] local, the
+// others peer-mapped), see barycentric.cu GatherDest
+template <class R>
+int barycentric_gather_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                              const R* y_axis, int len_y, const int32_t* simplices, const int32_t* neighbours,
+                              int num_tri, int row_begin, int row_end, int halo, R* const* fields, int num_fields,
+                              int flags, cudaStream_t st);
 template <class R>
 int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* fill_src, int flags,
                 cudaStream_t st);

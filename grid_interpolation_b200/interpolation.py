@@ -24,6 +24,7 @@ keeps internal (triangle ids, neighbour ids) for parity testing.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from types import SimpleNamespace
 
@@ -36,7 +37,8 @@ from ._lib import (GI_DEVICE, GI_FIELD_ROWMAJOR, GI_HOST, GI_KD_REFERENCE_VISITS
 __all__ = ["bilinear", "idw_kdtree", "idw_esrg_nearest", "barycentric_interpolation",
            "barycentric_interpolation_ex", "idw_kdtree_ex", "idw_esrg_nearest_ex", "kd_build",
            "assign_points_to_cells", "fill_nearest_neighbour", "pinned_empty", "pinned_copy",
-           "set_profiling", "set_pipeline_band_bytes", "last_timings", "BarycentricPlan", "KdTreePlan", "EsrgPlan"]
+           "set_profiling", "set_pipeline_band_bytes", "set_fixup_list_capacity", "release_workspace", "pinned_trim",
+           "last_timings", "BarycentricPlan", "KdTreePlan", "EsrgPlan"]
 
 _F64 = np.dtype(np.float64)
 
@@ -55,7 +57,12 @@ def _real(dtype):
 # pinned host buffers (page-locked: H2D / D2H at PCIe rate), cached because cudaHostAlloc is slow
 # -------------------------------------------------------------------------------------------------
 class _PinnedPool:
-    def __init__(self, cap_bytes=24 << 30):
+    """Cache of page-locked buffers in exact-size buckets.  The cap (default 4 GiB, $GI_PINNED_CACHE_BYTES) bounds
+    what stays cached after the arrays are collected; pinned_trim() releases it."""
+
+    def __init__(self, cap_bytes=None):
+        if cap_bytes is None:
+            cap_bytes = int(os.environ.get("GI_PINNED_CACHE_BYTES", 4 << 30))
         self.free = {}
         self.cached = 0
         self.cap = cap_bytes
@@ -79,6 +86,14 @@ class _PinnedPool:
                 self.cached += nbytes
                 return
         lib().gi_host_free(ptr)
+
+    def trim(self, keep_bytes=0):
+        with self.lock:
+            for nbytes in sorted(self.free, reverse=True):
+                lst = self.free[nbytes]
+                while lst and self.cached > keep_bytes:
+                    lib().gi_host_free(lst.pop())
+                    self.cached -= nbytes
 
 
 _pool = _PinnedPool()
@@ -248,6 +263,13 @@ def _use_out(call, out, shape, dtype, order):
     if out is None:
         return call.out(shape, dtype, order)
     if call.torch:
+        import torch
+        tdtype = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}[np.dtype(dtype)]
+        # the kernels write sizeof(dtype)-byte elements through out.data_ptr(): anything else is a device fault
+        if not _is_torch(out) or not out.is_cuda or out.device != call.device:
+            raise ValueError(f"out must be a torch CUDA tensor on {call.device} (the device of the inputs)")
+        if out.dtype != tdtype:
+            raise ValueError(f"out must have dtype {tdtype}, got {out.dtype}")
         if tuple(out.shape) != tuple(shape):
             raise ValueError(f"out must have shape {shape}")
         if out.is_contiguous():
@@ -255,6 +277,8 @@ def _use_out(call, out, shape, dtype, order):
         if out.dim() == 2 and out.t().is_contiguous():
             return out, out.data_ptr(), False
         raise ValueError("out must be contiguous")
+    if not isinstance(out, np.ndarray):
+        raise ValueError("out must be a numpy array when the inputs are host arrays")
     if out.shape != tuple(shape) or out.dtype != np.dtype(dtype):
         raise ValueError(f"out must have shape {shape} and dtype {np.dtype(dtype)}")
     if out.flags.c_contiguous:
@@ -390,11 +414,13 @@ def idw_esrg_nearest(points, data_in, x_axis, y_axis, grid_spac, num_neighbours,
 
 
 def barycentric_interpolation_ex(points, data_in, x_axis, y_axis, simplices, neighbours, *, rows=None, halo=0,
-                                 order="F", debug=False, reference_order=False, dtype=np.float64, out=None,
-                                 sync=True):
+                                 order="F", debug=False, reference_order=False, band_pack=False, dtype=np.float64,
+                                 out=None, sync=True):
     """barycentric_interpolation on a row band (+ ``halo`` rows for the hull fill); debug=True also returns
     triangle ids (1-based), the outside-hull mask, fill sources and counters.  reference_order=True locates every
-    target by the reference's own row-sequential walk (debug: slow; the default reproduces its result)."""
+    target by the reference's own row-sequential walk (debug: slow; the default reproduces its result).
+    band_pack=True (device tensors; host calls decide by themselves) packs only the triangles near the band
+    (GI_BARY_BAND_PACK): a GiError with status GI_ERR_PACK_WINDOW then asks for a retry without it."""
     rt, suf = _real(dtype)
     with _Call(points) as c:
         x, y, p, d, n = _grid_common(c, points, data_in, x_axis, y_axis, "n2", rt)
@@ -411,7 +437,8 @@ def barycentric_interpolation_ex(points, data_in, x_axis, y_axis, simplices, nei
         r0, r1 = _band(rows, len_y)
         res, res_ptr, rowmajor = _use_out(c, out, (r1 - r0, len_x), rt, order)
         flags = ((GI_FIELD_ROWMAJOR if rowmajor else 0) | (GI_POINTS_ROWMAJOR if p.rowmajor else 0)
-                 | (GI_TOPO_ROWMAJOR if s.rowmajor else 0) | (_lib.GI_BARY_REFERENCE_ORDER if reference_order else 0))
+                 | (GI_TOPO_ROWMAJOR if s.rowmajor else 0) | (_lib.GI_BARY_REFERENCE_ORDER if reference_order else 0)
+                 | (_lib.GI_BARY_BAND_PACK if band_pack else 0))
         tri = mask = src = cnt = None
         tri_ptr = mask_ptr = src_ptr = cnt_ptr = None
         if debug:
@@ -608,6 +635,21 @@ def fill_nearest_neighbour(mask_outside, data_ip):
 
 def set_profiling(on: bool) -> None:
     lib().gi_set_profiling(1 if on else 0)
+
+
+def set_fixup_list_capacity(targets: int) -> None:
+    """Capacity of the barycentric ambiguity fix-up work list (0 = default 4 Mi targets); see gridinterp.h."""
+    lib().gi_set_fixup_list_capacity(int(targets))
+
+
+def release_workspace() -> None:
+    """Return the library's cached device scratch memory (stream-ordered pool) to the driver."""
+    lib().gi_release_workspace()
+
+
+def pinned_trim(keep_bytes: int = 0) -> None:
+    """Free cached page-locked host buffers until at most ``keep_bytes`` stay cached."""
+    _pool.trim(keep_bytes)
 
 
 def set_pipeline_band_bytes(nbytes: int) -> None:

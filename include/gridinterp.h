@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define GI_VERSION 100
+#define GI_VERSION 200
 
 typedef enum {
   GI_OK = 0,
@@ -58,7 +58,9 @@ typedef enum {
   GI_ERR_ITER_CAP = 5,       /* walk / ring search exceeded its cap (reference: infinite loop) */
   GI_ERR_TOO_FEW_POINTS = 6, /* fewer than num_neighbours points (reference: infinite loop, query_esrg.f90:178) */
   GI_ERR_BAD_INDEX = 7,      /* simplices / neighbours id out of range (reference: out-of-bounds read) */
-  GI_ERR_HALO = 8            /* row-band call: hull fill needs rows beyond the supplied halo */
+  GI_ERR_HALO = 8,           /* row-band call: hull fill needs rows beyond the supplied halo */
+  GI_ERR_PACK_WINDOW = 9,    /* GI_BARY_BAND_PACK: a walk left the triangles packed for the band; retry without the flag */
+  GI_ERR_TIMEOUT = 10        /* gi_peer_wait: a peer did not signal within the timeout */
 } gi_status;
 
 #define GI_HOST 0
@@ -84,6 +86,12 @@ typedef enum {
                                        one thread per grid row).  Default: only the targets inside the margin
                                        band of a mesh edge are re-located along that path -- or all of them
                                        when there are more than the fix-up list holds. */
+#define GI_BARY_BAND_PACK 512 /* barycentric row-band calls with GI_DEVICE buffers (multi-GPU sharding): turn only the
+                                 triangles whose y-range meets the walked rows (band + halo + 48 rows) into records
+                                 instead of the whole mesh -- 1/8 of the packing work for one of 8 bands.  Links to
+                                 skipped triangles are marked, and a walk that wants to cross one is reported as
+                                 GI_ERR_PACK_WINDOW by gi_stream_status(): the caller then repeats the call without
+                                 the flag (GI_HOST calls do both by themselves).  Results are identical. */
 #define GI_ESRG_REFERENCE_ORDER 16 /* idw_esrg_nearest: process every target in the reference's candidate order
                                       (debug).  Default: only targets with exactly equal neighbour distances,
                                       the only case in which that order changes the result. */
@@ -103,7 +111,6 @@ void gi_host_free(void* p);
 int gi_stream_status(void* stream);
 /* Environment variables read by the library (debugging aids, none is needed in production):
  *   GI_KD_TRACE=1   print the number of rounds of the quickselect-faithful k-d tree build to stderr
- *   GI_AMB_CAP=n    size of the barycentric fix-up work list (default 4 194 304 targets per window): a smaller
  *                   value forces the row-sequential fallback that runs when the list overflows (tests) */
 /* Phase profiling: gi_set_profiling(1) starts a fresh recording on the calling thread; from then on every
  * call made by that thread records CUDA events around its phases (h2d, pack_mesh, walk, fill, d2h, ...) on
@@ -120,6 +127,34 @@ const char* gi_last_timing_name(int i);
 void gi_set_pipeline_band_bytes(uint64_t bytes);
 /* Return cached scratch memory of the current device to the driver. */
 void gi_release_workspace(void);
+/* Capacity (targets per walked window) of the work list of the barycentric ambiguity fix-up, default 4 194 304;
+ * when more targets lie within the margin band of a mesh edge the window is redone by the row-sequential walk.
+ * A small value forces that path (tests).  <= 0 restores the default.  Process-wide. */
+void gi_set_fixup_list_capacity(int64_t targets);
+
+/* ---- multi-GPU: peer memory and the fused gather (one process per GPU) --------------------------------- */
+/* The reference is a single shared-memory process (4 OpenMP loops, interpolation.f90:62,152,249,362).  Here the
+ * grid targets of interpolation.f90:362-404 are sharded in row bands over the GPUs of one node, and the final
+ * gather of the field is not a separate collective: the kernels store every result into the field of every
+ * destination GPU over NVLink (gi_barycentric_interpolation_gather_*).  The plumbing is CUDA IPC:
+ *   gi_peer_alloc    device memory of the current device that other processes may map (zero-filled)
+ *   gi_peer_export   GI_PEER_HANDLE_BYTES opaque bytes to send to the other ranks (any transport)
+ *   gi_peer_open     map another rank's allocation into this process -> device pointer usable in kernels
+ *   gi_peer_close / gi_peer_free
+ *   gi_peer_signal   after all work enqueued so far on `stream`: flag_arrays[d][slot] = value for d < num
+ *                    (system-scope release store; flag arrays are uint32 peer allocations, slot = this rank)
+ *   gi_peer_wait     enqueue a wait on `stream` until flags[i] >= value for all i < num_slots (this rank's own
+ *                    flag array); bounded by timeout_s (<= 30 s) -> GI_ERR_TIMEOUT via gi_stream_status()
+ * so "all N bands have arrived in my copy of the field" is a stream-ordered event with no host round trip. */
+#define GI_MAX_GATHER_FIELDS 8
+#define GI_PEER_HANDLE_BYTES 64
+void* gi_peer_alloc(uint64_t bytes);
+void gi_peer_free(void* p);
+int gi_peer_export(void* p, void* handle64);
+int gi_peer_open(const void* handle64, void** p);
+int gi_peer_close(void* p);
+int gi_peer_signal(uint32_t* const* flag_arrays, int num, int slot, uint32_t value, void* stream);
+int gi_peer_wait(const uint32_t* flags, int num_slots, uint32_t value, double timeout_s, void* stream);
 
 /* ---- the four drop-in entry points ---------------------------------------------------------- */
 
@@ -176,6 +211,17 @@ int gi_barycentric_interpolation_ex_f64(const double* points, int num_points, co
                                         double* data_ip, int32_t* tri_out, uint8_t* mask_out,
                                         int64_t* fill_src, int64_t* counters, int flags, int mem,
                                         void* stream);
+
+/* Row band [row_begin, row_end) of barycentric_interpolation computed on the current device and stored at its
+ * place in num_fields (<= GI_MAX_GATHER_FIELDS) FULL (len_y, len_x) fields in the layout `flags` selects:
+ * fields[0] must be memory of the current device (the hull fill reads its source cells there), the others are the
+ * same field on other GPUs (gi_peer_open).  All pointers are device pointers, the work is enqueued on `stream`
+ * (GI_DEVICE semantics).  Replaces the OpenMP row loop interpolation.f90:362-404 + the fill :412 for one band. */
+int gi_barycentric_interpolation_gather_f64(const double* points, int num_points, const double* data_in,
+                                            const double* x_axis, int len_x, const double* y_axis, int len_y,
+                                            const int32_t* simplices, const int32_t* neighbours,
+                                            int num_triangles, int row_begin, int row_end, int halo,
+                                            double* const* fields, int num_fields, int flags, void* stream);
 
 /* nn_index (band rows, len_x, k): 1-based ids in ascending-distance order as neighbours_index /
  * index_nn hold them (kd_tree.f90:236, query_esrg.f90:168), k fastest; nn_dist2 squared distances
@@ -254,6 +300,11 @@ int gi_barycentric_interpolation_ex_f32(const float* points, int num_points, con
                                         int row_begin, int row_end, int halo, float* data_ip, int32_t* tri_out,
                                         uint8_t* mask_out, int64_t* fill_src, int64_t* counters, int flags,
                                         int mem, void* stream);
+int gi_barycentric_interpolation_gather_f32(const float* points, int num_points, const float* data_in,
+                                            const float* x_axis, int len_x, const float* y_axis, int len_y,
+                                            const int32_t* simplices, const int32_t* neighbours, int num_triangles,
+                                            int row_begin, int row_end, int halo, float* const* fields,
+                                            int num_fields, int flags, void* stream);
 int gi_idw_kdtree_ex_f32(const float* points, int num_points, const float* data_in, const float* x_axis,
                          int len_x, const float* y_axis, int len_y, int num_neighbours, int row_begin,
                          int row_end, float* data_ip, int32_t* nn_index, float* nn_dist2, int64_t* counters,

@@ -27,7 +27,7 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in gridinterp.h but not exported"
     assert sorted(_lib.SIGNATURES) == names
-    assert _lib.lib().gi_version() == 100
+    assert _lib.lib().gi_version() == 200
 
 
 def test_drop_in_module_name():

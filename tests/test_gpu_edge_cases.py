@@ -177,3 +177,28 @@ def test_bilinear_search_axes_extension(order):
     p2 = np.column_stack([rng.uniform(0, 59, n), rng.uniform(0, 43, n)])
     np.testing.assert_allclose(ip.bilinear(xu, yu, field, p2, search_axes=True), ip.bilinear(xu, yu, field, p2),
                                rtol=1e-12, atol=1e-12)
+
+
+def test_out_tensor_is_validated_before_the_kernel_writes_through_it(c1):
+    """A caller-supplied torch `out` of the wrong dtype / device would make the kernel write 8-byte elements through
+    a foreign pointer: it must be a ValueError, like the numpy branch."""
+    import torch
+    d = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+    args = [d(a) for a in (c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices, c1.neighbours)]
+    shape = (c1.y_axis.size, c1.x_axis.size)
+    good = torch.empty(shape, dtype=torch.float64, device="cuda:0")
+    ip.barycentric_interpolation(*args, out=good)
+    same(good.cpu().numpy(), orc.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis,
+                                                          c1.simplices, c1.neighbours))
+    for bad in (torch.empty(shape, dtype=torch.float32, device="cuda:0"),      # 4-byte elements on the f64 path
+                torch.empty(shape, dtype=torch.int64, device="cuda:0"),
+                torch.empty(shape, dtype=torch.float64),                        # host tensor
+                np.empty(shape)):                                               # numpy out on the device path
+        with pytest.raises(ValueError):
+            ip.barycentric_interpolation(*args, out=bad)
+    with pytest.raises(ValueError):                                             # and through a plan
+        with ip.BarycentricPlan(args[0], args[2], args[3], args[4], args[5]) as plan:
+            plan(args[1], out=torch.empty(shape, dtype=torch.float32, device="cuda:0"))
+    with pytest.raises(ValueError):                                             # torch out on the host path
+        ip.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices, c1.neighbours,
+                                     out=good)

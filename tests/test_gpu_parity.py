@@ -154,12 +154,18 @@ def test_barycentric_reference_order_walk(c1, order):
         assert_values(band, want[r0:r1])
 
 
-def test_barycentric_more_flagged_targets_than_the_fixup_list_holds(monkeypatch):
-    """Every lattice target on an edge or vertex is flagged; with a 64-entry fix-up list (GI_AMB_CAP, normally 4 M)
-    the list overflows and the row-sequential walk takes over -- nothing may be left to phase 1's own path."""
+@pytest.fixture
+def tiny_fixup_list():
+    ip.set_fixup_list_capacity(64)
+    yield
+    ip.set_fixup_list_capacity(0)
+
+
+def test_barycentric_more_flagged_targets_than_the_fixup_list_holds(tiny_fixup_list):
+    """Every lattice target on an edge or vertex is flagged; with a 64-entry fix-up list (normally 4 M) the list
+    overflows and the row-sequential walk takes over -- nothing may be left to phase 1's own path."""
     pts, data, x, y, simp, nbr = _lattice_case()
     want, w = orc.barycentric_interpolation(pts, data, x, y, simp, nbr, debug=True)
-    monkeypatch.setenv("GI_AMB_CAP", "64")
     for order in ("C", "F"):
         got, g = ip.barycentric_interpolation_ex(pts, data, x, y, simp, nbr, debug=True, order=order)
         assert np.array_equal(g.mask, w.mask)
