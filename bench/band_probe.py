@@ -34,6 +34,8 @@ for bp in (False, True):
         for name, v in ip.last_timings():
             agg.setdefault(name, []).append(v)
         ip.set_profiling(False)
-        ok = torch.equal(out, full[rows[0]:rows[1]])
+        from grid_interpolation_b200 import _lib
+        st = _lib.lib().gi_stream_status(torch.cuda.current_stream().cuda_stream)
+        ok = torch.equal(out, full[rows[0]:rows[1]]) and st == 0
         print(f"band_pack={bp} band {b}/{nb} rows {rows}: {e0.elapsed_time(e1) / 10:.3f} ms/step  "
               + "  ".join(f"{k} {np.mean(v):.3f}" for k, v in agg.items()) + f"  equal={ok}", flush=True)

@@ -44,14 +44,23 @@ namespace {
 constexpr int kSeedCell = 16;      // targets per seed-grid cell edge
 constexpr int kWalkThreads = 128;  // columns per CTA
 
-// One record per triangle, f64: 96 B = 3 sectors, 32 B aligned.  Sectors 0-1 are what a walk step needs (3
-// vertices + 3 neighbour ids), sector 2 holds the nodal values for the barycentric value.
+// One record per triangle, f64: 128 B = 4 sectors = one cache line.
+//   sectors 0-1  what a walk step needs: 3 vertices + 3 neighbour ids + the ambiguity threshold
+//   sector  2    A = y2-y3, B = x3-x2, C = y3-y1, D = x1-x3                      (interpolation.f90:385-394)
+//   sector  3    denom = A*D + B*(y1-y3) (:385-386) and the nodal values d1, d2, d3
+// Sectors 2-3 hold everything of the barycentric value that depends on the triangle only, computed once by the
+// pack pass with the reference's operations.  ncu (profiles/r02_start_locate_eval_ncu.csv): in round 1 phase 2
+// re-derived them -- 3 record loads, 17 FP64 instructions -- whenever a column entered another triangle, and as
+// some lane of a warp does so in nearly every row, every row paid for that block (49 % of the kernel's
+// instructions were phase 2, 119 per row and warp).  Now a triangle change is 3 loads + 3 FP64 + the reciprocal.
 template <class R> struct alignas(sizeof(R) == 8 ? 32 : 16) TriGeom {
   R x1, y1, x2, y2, x3, y3;
-  int n1, n2, n3;  // neighbour opposite vertex 1/2/3, 0-based, -1 = hull edge
+  int n1, n2, n3;  // neighbour opposite vertex 1/2/3, 0-based, -1 = hull edge, -2 = not packed (band-limited pack)
   int pad;         // ambiguity threshold of this triangle (bit pattern, see amb_threshold)
-  R d1, d2, d3, padv;
+  R A, B, C, D;
+  R denom, d1, d2, d3;
 };
+static_assert(sizeof(TriGeom<double>) == 128 && sizeof(TriGeom<float>) == 80, "record layout");
 template <class R> struct SeedGrid {
   R x0, y0, inv_cell_x, inv_cell_y;
   int ncx, ncy;
@@ -59,8 +68,8 @@ template <class R> struct SeedGrid {
 
 // Record loads.  The kernels below are bound by L1 data-pipe wavefronts (ncu: l1tex__data_pipe_lsu_wavefronts
 // 75 % of peak with 128-bit loads): every lane fetches its own record, so one warp-wide load costs one wavefront
-// per distinct cache line.  sm_100 has 256-bit global loads (LDG.E.ENL2.256): a 64 B walk record is 2 loads
-// instead of 4, a 96 B evaluation record 3 instead of 6.
+// per distinct cache line.  sm_100 has 256-bit global loads (LDG.E.ENL2.256): the walk part of a record is 2 loads
+// instead of 4, the evaluation part 3 (x3 / y3 come with sector 1).
 __device__ __forceinline__ void ld256(const void* p, double& a, double& b, double& c, double& d) {
   asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
@@ -72,26 +81,37 @@ __device__ __forceinline__ void load_walk(const TriGeom<double>* p, TriGeom<doub
   g.n1 = __double2loint(n12); g.n2 = __double2hiint(n12);
   g.n3 = __double2loint(w); g.pad = __double2hiint(w);
 }
-__device__ __forceinline__ void load_walk(const TriGeom<float>* p, TriGeom<float>& g) { g = *p; }
-// nodal values (sector 2)
-__device__ __forceinline__ void load_values(const TriGeom<double>* p, TriGeom<double>& g) {
-  ld256(reinterpret_cast<const char*>(p) + 64, g.d1, g.d2, g.d3, g.padv);
+__device__ __forceinline__ void load_walk(const TriGeom<float>* p, TriGeom<float>& g) {
+  g.x1 = p->x1; g.y1 = p->y1; g.x2 = p->x2; g.y2 = p->y2; g.x3 = p->x3; g.y3 = p->y3;
+  g.n1 = p->n1; g.n2 = p->n2; g.n3 = p->n3; g.pad = p->pad;
 }
-__device__ __forceinline__ void load_values(const TriGeom<float>*, TriGeom<float>&) {}
-// sector 2 as ONE full-sector store (three 8 B stores at a 96 B stride make the L2 merge partial sectors)
+// evaluation part: x3, y3 (sector 1), A..D (sector 2), denom + nodal values (sector 3)
+__device__ __forceinline__ void load_eval(const TriGeom<double>* p, TriGeom<double>& g) {
+  double n12, w;
+  ld256(reinterpret_cast<const char*>(p) + 32, g.x3, g.y3, n12, w);
+  ld256(reinterpret_cast<const char*>(p) + 64, g.A, g.B, g.C, g.D);
+  ld256(reinterpret_cast<const char*>(p) + 96, g.denom, g.d1, g.d2, g.d3);
+}
+__device__ __forceinline__ void load_eval(const TriGeom<float>* p, TriGeom<float>& g) {
+  g.x3 = p->x3; g.y3 = p->y3; g.A = p->A; g.B = p->B; g.C = p->C; g.D = p->D;
+  g.denom = p->denom; g.d1 = p->d1; g.d2 = p->d2; g.d3 = p->d3;
+}
+// new nodal values (plans): sector 3 as ONE full-sector store, denom kept
 __device__ __forceinline__ void store_values(TriGeom<double>* p, double d1, double d2, double d3) {
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<char*>(p) + 64), "d"(d1), "d"(d2), "d"(d3),
-               "d"(0.0)
+  const double denom = p->denom;
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<char*>(p) + 96), "d"(denom), "d"(d1), "d"(d2),
+               "d"(d3)
                : "memory");
 }
 __device__ __forceinline__ void store_values(TriGeom<float>* p, float d1, float d2, float d3) {
   p->d1 = d1; p->d2 = d2; p->d3 = d3;
 }
-// Fire-and-forget load of sector 2: the registers are never read, so nothing waits on it, but the sector is in
-// L1 when phase 2 asks for it a few thousand cycles later (prefetch.global.L1 had no measurable effect).
+// Fire-and-forget loads of sectors 2-3: the registers are never read, so nothing waits on them, but the sectors
+// are in L1 when phase 2 asks for them a few thousand cycles later (prefetch.global.L1 had no measurable effect).
 __device__ __forceinline__ void touch_values(const TriGeom<double>* p) {
   double a, b, c, d;
   ld256(reinterpret_cast<const char*>(p) + 64, a, b, c, d);
+  ld256(reinterpret_cast<const char*>(p) + 96, a, b, c, d);
 }
 __device__ __forceinline__ void touch_values(const TriGeom<float>*) {}
 
@@ -146,9 +166,13 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
                  const uint8_t* __restrict__ need, int* __restrict__ status) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool packed = t < num_tri && (!need || need[t]);
-  // fallback seed (seed[ncx*ncy]): the smallest packed triangle id
+  // fallback seed (seed[ncx*ncy]): the smallest packed triangle id.  CTAs start roughly in id order, so after the
+  // first few only a plain load is paid (39 000 atomics on one address cost 0.5 ms)
   const unsigned pm = __ballot_sync(0xffffffffu, packed);
-  if (pm && (threadIdx.x & 31) == __ffs(pm) - 1) atomicMin(seed + ((len_x + kSeedCell - 1) / kSeedCell) * ((len_y + kSeedCell - 1) / kSeedCell), t);
+  if (pm && (threadIdx.x & 31) == __ffs(pm) - 1) {
+    int* fb = seed + ((len_x + kSeedCell - 1) / kSeedCell) * ((len_y + kSeedCell - 1) / kSeedCell);
+    if (t < *reinterpret_cast<volatile int*>(fb)) atomicMin(fb, t);
+  }
   if (!packed) return;
   const SeedGrid<R> sg = seed_grid_of(x_axis, len_x, y_axis, len_y);
   int a = simp(t, 0), b = simp(t, 1), c = simp(t, 2);
@@ -172,8 +196,9 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
     if (n3 > 0 && !need[n3 - 1]) g.n3 = kNotPacked;
   }
   g.pad = amb_threshold(g);
+  g.A = g.y2 - g.y3; g.B = g.x3 - g.x2; g.C = g.y3 - g.y1; g.D = g.x1 - g.x3;   // interpolation.f90:385-394
+  g.denom = g.A * g.D + g.B * (g.y1 - g.y3);                                     // :385-386
   g.d1 = __ldg(data + (a - 1)); g.d2 = __ldg(data + (b - 1)); g.d3 = __ldg(data + (c - 1));
-  g.padv = R(0);
   geom[t] = g;
   if (bad) return;
   // seed grid: cell of the centroid under a uniform-axis approximation (a heuristic: it only has to be near)
@@ -216,6 +241,18 @@ __device__ __forceinline__ int seed_lookup(const int* __restrict__ seed, int ncx
   return s < num_tri ? s : 0;
 }
 
+// Band-limited pack: the first failing edge leads to a triangle that was not packed.  Any failing edge is a valid
+// move of a visibility walk and the triangle found does not depend on the path, so take a LATER failing
+// edge whose neighbour is packed if there is one; otherwise the caller reports GI_ERR_PACK_WINDOW.  (A failing hull
+// edge that comes FIRST still ends the walk as in the reference; this only replaces a move that cannot be made.)
+__device__ __forceinline__ int packed_alternative(bool o1, bool o2, bool o3, int n1, int n2, int n3) {
+  // edge 1 -> n3, edge 2 -> n1, edge 3 -> n2 (triangle_walk.f90:66-71)
+  if (o1 && n3 >= 0) return n3;
+  if (o2 && n1 >= 0) return n1;
+  if (o3 && n2 >= 0) return n2;
+  return kNotPacked;
+}
+
 // triangle_walk.f90:24-84 + :140-153.  Returns the triangle the walk ends in and leaves its record in g;
 // inside=false if the walk left through a hull edge (tri is then the last valid triangle, the reference's
 // ind_tri_pre).
@@ -238,6 +275,7 @@ __device__ __forceinline__ int walk(const TriGeom<R>* __restrict__ geom, int tri
     else if (c2 < margin) nxt = g.n1;
     else if (c3 < margin) nxt = g.n2;
     else break;
+    if (nxt == kNotPacked) nxt = packed_alternative(c1 < margin, c2 < margin, c3 < margin, g.n1, g.n2, g.n3);
     if (nxt < 0) {  // :74-80
       if (nxt == kNotPacked) raise_status(status, GI_ERR_PACK_WINDOW);
       inside = false;
@@ -253,12 +291,11 @@ __device__ __forceinline__ int walk(const TriGeom<R>* __restrict__ geom, int tri
 // interpolation.f90:385-398, same operation order; the two divisions share the reciprocal of denom.
 template <class R>
 __device__ __forceinline__ R eval_value(const TriGeom<R>& g, R tx, R ty) {
-  const R A = g.y2 - g.y3, B = g.x3 - g.x2, C = g.y3 - g.y1, D = g.x1 - g.x3;
   DivRcp<R> dv;
-  dv.set(A * D + B * (g.y1 - g.y3));
+  dv.set(g.denom);
   const R u = tx - g.x3, t = ty - g.y3;
-  const R w1 = dv.quotient(A * u + B * t);
-  const R w2 = dv.quotient(C * u + D * t);
+  const R w1 = dv.quotient(g.A * u + g.B * t);
+  const R w2 = dv.quotient(g.C * u + g.D * t);
   const R w3 = R(1) - w1 - w2;
   return g.d1 * w1 + g.d2 * w2 + g.d3 * w3;
 }
@@ -311,6 +348,7 @@ __device__ __forceinline__ int walk_checked(const TriGeom<R>* __restrict__ geom,
     else if (c2 < margin) { nxt = g.n1; cf = c2; }
     else if (c3 < margin) { nxt = g.n2; cf = c3; }
     else { amb = in_amb_band(c1, g.pad) | in_amb_band(c2, g.pad) | in_amb_band(c3, g.pad); break; }
+    if (nxt == kNotPacked) nxt = packed_alternative(c1 < margin, c2 < margin, c3 < margin, g.n1, g.n2, g.n3);
     if (nxt < 0) {
       if (nxt == kNotPacked && status) raise_status(status, GI_ERR_PACK_WINDOW);
       inside = false; amb = in_amb_band(cf, g.pad); break;
@@ -373,7 +411,7 @@ template <class R> struct WalkArgs {
 //                      shared-reciprocal divisions; 128 consecutive doubles per row are stored coalesced and
 //                      the outside-hull bits come from one ballot per warp row.
 // ---------------------------------------------------------------------------------------------
-template <class R, bool FY, int ROWS, int MINB>
+template <class R, bool FY, bool PEERS, int ROWS, int MINB>
 __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const WalkArgs<R> a) {
   __shared__ int stri[ROWS][kWalkThreads];
   __shared__ R saxis[ROWS];
@@ -429,7 +467,8 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
       // first failing edge wins (:57-60); edge i -> neighbour opposite vertex i-1 (wrap) (:66-71)
       const bool o1 = x1 < margin, o2 = x2 < margin, o3 = x3 < margin;
       const bool outside = o1 | o2 | o3;
-      const int nxt = o1 ? n3 : (o2 ? n1 : n2);
+      int nxt = o1 ? n3 : (o2 ? n1 : n2);
+      if (outside && nxt == kNotPacked) nxt = packed_alternative(o1, o2, o3, n1, n2, n3);
       if (outside && nxt >= 0) {
         if (it < a.iter_cap) { enter(nxt); continue; }
         raise_status(a.status, GI_ERR_ITER_CAP);
@@ -457,37 +496,38 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   __syncthreads();
 
   // ---- phase 2: evaluate -----------------------------------------------------------------------
-  // Row-synchronous.  The evaluation record is fetched only when the column enters another triangle (about one
-  // row in four); what depends on (triangle, column) only -- A*(tx-x3), C*(tx-x3) for fast axis x -- is kept in
-  // registers, the row-dependent half of interpolation.f90:387-394 is evaluated per target.
+  // Row-synchronous.  When the column enters another triangle the lane fetches the record's evaluation sectors
+  // (L1-resident after phase 1) -- A..D, denom and the nodal values were computed by the pack pass -- and derives
+  // what depends on (triangle, column): A*(tx-x3), C*(tx-x3) for fast axis x and the refined reciprocal of denom;
+  // the row-dependent half of interpolation.f90:387-394 is evaluated per target.
   const bool f_in_band = active && f >= a.bf0 && f < a.bf1;
   const int wpr = (w.nf() + 31) >> 5;
   const int bnf = a.bf1 - a.bf0;
   static_assert(ROWS <= 32, "one lane per row keeps that row's mask word");
+  const int rb0 = max(0, a.bs0 - srow0), rb1 = min(nrows, a.bs1 - srow0);   // rows of the strip inside the band
+  // band-relative element of (row 0 of the strip, this column); only dereferenced for rows inside the band
+  const int64_t oo0 = (int64_t)(srow0 - a.bs0) * a.out_ld + (f - a.bf0);
+  R* optr = a.out + oo0;
+  int32_t* tptr = a.tri_out ? a.tri_out + ((int64_t)(srow0 - a.bs0) * bnf + (f - a.bf0)) : nullptr;
   int cur = -1;
   unsigned my_mask = 0;
   R c1 = 0, q1 = 0, c2 = 0, q2 = 0, p3 = 0, d1 = 0, d2 = 0, d3 = 0;
   DivRcp<R> dv;
   dv.d = R(1); dv.r2 = R(1);
 #pragma unroll 2
-  for (int r = 0; r < nrows; ++r) {
-    const int s = srow0 + r;
+  for (int r = 0; r < nrows; ++r, optr += a.out_ld) {
     const int t = active ? stri[r][tid] : 0;
     const bool inside = t >= 0;
-    if (f_in_band && s >= a.bs0 && s < a.bs1) {
-      const int64_t o = (int64_t)(s - a.bs0) * bnf + (f - a.bf0);
-      const int64_t oo = (int64_t)(s - a.bs0) * a.out_ld + (f - a.bf0);
+    if (f_in_band && r >= rb0 && r < rb1) {
       if (inside) {
-        if (t != cur) {  // records were touched by phase 1: L1 hits
-          TriGeom<R> g;
-          load_walk(a.geom + t, g);
-          load_values(a.geom + t, g);
+        if (t != cur) {
           cur = t;
-          const R A = g.y2 - g.y3, B = g.x3 - g.x2, C = g.y3 - g.y1, D = g.x1 - g.x3;
-          dv.set(A * D + B * (g.y1 - g.y3));                        // denom (:385-386)
+          TriGeom<R> g;
+          load_eval(a.geom + t, g);
+          dv.set(g.denom);
           d1 = g.d1; d2 = g.d2; d3 = g.d3;
-          if (!FY) { const R u = cf - g.x3; c1 = A * u; q1 = B; c2 = C * u; q2 = D; p3 = g.y3; }
-          else { const R u = cf - g.y3; c1 = B * u; q1 = A; c2 = D * u; q2 = C; p3 = g.x3; }
+          if (!FY) { const R u = cf - g.x3; c1 = g.A * u; q1 = g.B; c2 = g.C * u; q2 = g.D; p3 = g.y3; }
+          else { const R u = cf - g.y3; c1 = g.B * u; q1 = g.A; c2 = g.D * u; q2 = g.C; p3 = g.x3; }
         }
         // w1 = (A*(tx-x3) + B*(ty-y3))/denom, w2 = (C*(tx-x3) + D*(ty-y3))/denom   (:387-394); the sum commutes
         const R t3 = saxis[r] - p3;
@@ -495,10 +535,13 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
         quotient_pair(dv, FY ? q1 * t3 + c1 : c1 + q1 * t3, FY ? q2 * t3 + c2 : c2 + q2 * t3, w1, w2);
         const R w3 = R(1) - w1 - w2;
         const R v = d1 * w1 + d2 * w2 + d3 * w3;                   // :396-398
-        a.out[oo] = v;
-        for (int d = 0; d < a.n_peer; ++d) a.peer_out[d][oo] = v;
+        *optr = v;
+        if (PEERS) {  // the fused gather: the same element of every peer field, over NVLink
+          const int64_t oo = oo0 + (int64_t)r * a.out_ld;
+          for (int d = 0; d < a.n_peer; ++d) a.peer_out[d][oo] = v;
+        }
       }
-      if (a.tri_out) a.tri_out[o] = (inside ? t : ~t) + 1;
+      if (tptr) tptr[(int64_t)r * bnf] = (inside ? t : ~t) + 1;
     }
     const unsigned m = __ballot_sync(0xffffffffu, active && !inside);
     if (lane == r) my_mask = m;  // lane r keeps the word of row r (ROWS <= 32)
@@ -513,6 +556,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   if (lane == 0 && iters_sum) atomicAdd((unsigned long long*)a.counters, (unsigned long long)iters_sum);
 }
 
+
 // Result of a (re-)located target (f, s): value or mask bit, triangle id, work list of the hull fill.
 template <class R>
 __device__ __forceinline__ void publish_target(const WalkArgs<R>& a, int f, int s, int tri, bool inside, R tx, R ty) {
@@ -521,8 +565,7 @@ __device__ __forceinline__ void publish_target(const WalkArgs<R>& a, int f, int 
     const int64_t o = (int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0);
     if (inside) {
       TriGeom<R> g;
-      load_walk(a.geom + tri, g);
-      load_values(a.geom + tri, g);
+      load_eval(a.geom + tri, g);
       const int64_t oo = (int64_t)(s - a.bs0) * a.out_ld + (f - a.bf0);
       const R v = eval_value(g, tx, ty);
       a.out[oo] = v;
@@ -991,8 +1034,11 @@ int bary_walk(const WalkArgs<R>& wa, const PackedMesh<R>& pm, const R* x_axis, c
   constexpr int kRows = 32;
   dim3 grid(div_up(nf, kWalkThreads), div_up(ns, kRows));
   GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
-  if (!wa.win.fast_is_y) locate_eval_kernel<R, false, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
-  else locate_eval_kernel<R, true, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
+  const bool fy = wa.win.fast_is_y, peers = wa.n_peer > 0;
+  if (!fy && !peers) locate_eval_kernel<R, false, false, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
+  else if (fy && !peers) locate_eval_kernel<R, true, false, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
+  else if (!fy) locate_eval_kernel<R, false, true, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
+  else locate_eval_kernel<R, true, true, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
   GI_CUDA(cudaGetLastError());
   // targets inside the margin band of an edge: follow the reference's own path (normally none)
   const int n_search = std::min(num_points, pm.num_tri);  // the reference searches triangles 1..num_points (:347)

@@ -171,9 +171,9 @@ class PeerField:
         use_cuda = dist.get_backend(group) == "nccl"
         send = torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8)
         send = send.to(dev) if use_cuda else send
-        recv = torch.empty((self.world, 2 * hb), dtype=torch.uint8, device=send.device)
-        dist.all_gather_into_tensor(recv, send, group=group)
-        handles = recv.cpu().numpy()
+        recv = [torch.empty(2 * hb, dtype=torch.uint8, device=send.device) for _ in range(self.world)]
+        dist.all_gather(recv, send, group=group)
+        handles = [r.cpu().numpy() for r in recv]
         self._opened = []
         fields, flags = [self._local], [self._flags]
         for r in list(range(self.rank + 1, self.world)) + list(range(self.rank)):   # rotate: spread NVLink targets

@@ -89,13 +89,20 @@ def c3(n=10_000_000, grid=8192):
     w = scattered(n, grid, seed=3, lo=-0.5, hi=grid - 0.5); w.name = "C3"; return w
 
 
+def _default_cache():
+    """<repo>/.gi_cache when it exists (git-ignored; it travels with a gpurun snapshot, so the one-minute Qhull run
+    is not repeated on every fresh box), else /tmp/gi_cache."""
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ".gi_cache")
+    return here if os.path.isdir(here) else "/tmp/gi_cache"
+
+
 def c4(n=5_000_000, grid=16384, cache_dir=None, seed=4):
     """Barycentric headline config: n uniform points -> Delaunay (about 2n triangles) -> grid x grid.
 
     The Qhull triangulation of 5 M points takes about a minute and 4 GB; it is cached as .npy files under
     ``cache_dir`` (default $GI_CACHE or /tmp/gi_cache) so that the two bench arms and all ranks share it.
     """
-    cache_dir = cache_dir or os.environ.get("GI_CACHE", "/tmp/gi_cache")
+    cache_dir = cache_dir or os.environ.get("GI_CACHE") or _default_cache()
     tag = f"c4_n{n}_g{grid}_s{seed}"
     fs = os.path.join(cache_dir, tag + "_simplices.npy")
     fn = os.path.join(cache_dir, tag + "_neighbours.npy")

@@ -65,7 +65,8 @@ def test_band_limited_pack_gives_the_same_band_or_asks_for_a_retry():
     host = ip.barycentric_interpolation_ex(w.points, w.data_pts, w.x_axis, w.y_axis, w.simplices, w.neighbours,
                                            rows=(384, 512), halo=8, order="C")          # decides by itself
     assert np.array_equal(host, full[384:512])
-    # 300 points over the same 1024 x 1024 grid: triangles ~ 80 rows tall, walks cross the 48-row margin
+    # 300 points over the same 1024 x 1024 grid: triangles ~ 80 rows tall, walks cross the 48-row margin and the hull
+    # fill looks further than any small halo: the raw call must report one or the other, the helper retries both
     w = workloads.c4(300, 1024, seed=12)
     d = [dev(a) for a in (w.points, w.data_pts, w.x_axis, w.y_axis, w.simplices, w.neighbours)]
     full = ip.barycentric_interpolation(*d, order="C").cpu().numpy()
@@ -73,16 +74,13 @@ def test_band_limited_pack_gives_the_same_band_or_asks_for_a_retry():
     try:
         band = ip.barycentric_interpolation_ex(*d, rows=rows, halo=8, order="C", band_pack=True).cpu().numpy()
         assert np.array_equal(band, full[rows[0]:rows[1]])       # the walks happened to stay inside: still right
-        reported = False
     except _lib.GiError as e:
-        assert e.status == _lib.GI_ERR_PACK_WINDOW
-        reported = True
+        assert e.status in (_lib.GI_ERR_PACK_WINDOW, _lib.GI_ERR_HALO)
     (lo, hi), band = sharding.barycentric_band(ip, *d, rank=31, world=64, order="C")     # 16-row band, retries
     assert np.array_equal(band.cpu().numpy(), full[lo:hi])
     host = ip.barycentric_interpolation_ex(w.points, w.data_pts, w.x_axis, w.y_axis, w.simplices, w.neighbours,
-                                           rows=rows, halo=8, order="C")
+                                           rows=rows, halo=400, order="C")
     assert np.array_equal(host, full[rows[0]:rows[1]])
-    assert reported or True
 
 
 def _free_port():
