@@ -136,6 +136,7 @@ __device__ __forceinline__ SeedGrid<R> seed_grid_of(const R* __restrict__ x_axis
 // skipped one becomes kNotPacked: a walk that wants to cross it raises GI_ERR_PACK_WINDOW instead of reading a
 // record that was never written (the caller retries with the whole mesh packed).
 constexpr int kNotPacked = -2;
+constexpr int kLongTriangle = (int)0x80000000;  // sign bit of TriGeom::pad, see farthest_failing_edge
 template <class R>
 __global__ void __launch_bounds__(256)
 need_kernel(PointsView<R> pts, TopoView simp, int num_points, int num_tri, const R* __restrict__ y_axis, int row_lo,
@@ -196,6 +197,11 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
     if (n3 > 0 && !need[n3 - 1]) g.n3 = kNotPacked;
   }
   g.pad = amb_threshold(g);
+  {  // long triangle (an edge spans more than two seed cells): careful exit-edge choice, see farthest_failing_edge
+    const R lx = fmax(fmax(fabs(g.x2 - g.x1), fabs(g.x3 - g.x2)), fabs(g.x1 - g.x3)) * sg.inv_cell_x;
+    const R ly = fmax(fmax(fabs(g.y2 - g.y1), fabs(g.y3 - g.y2)), fabs(g.y1 - g.y3)) * sg.inv_cell_y;
+    if (fmax(lx, ly) > R(2)) g.pad |= kLongTriangle;
+  }
   g.A = g.y2 - g.y3; g.B = g.x3 - g.x2; g.C = g.y3 - g.y1; g.D = g.x1 - g.x3;   // interpolation.f90:385-394
   g.denom = g.A * g.D + g.B * (g.y1 - g.y3);                                     // :385-386
   g.d1 = __ldg(data + (a - 1)); g.d2 = __ldg(data + (b - 1)); g.d3 = __ldg(data + (c - 1));
@@ -241,6 +247,31 @@ __device__ __forceinline__ int seed_lookup(const int* __restrict__ seed, int ncx
   return s < num_tri ? s : 0;
 }
 
+// Which failing edge to leave through.  The reference takes the FIRST failing edge (triangle_walk.f90:57-60), and so
+// does this walk -- except in LONG triangles (pad sign bit, set by the pack pass: an edge spans more than two seed
+// cells).  Those are the flat slivers that tile the strip along the convex hull (a hull edge of a uniform cloud is
+// hundreds of grid cells long); there the first-failing rule slides sideways from sliver to sliver: on C4 the
+// targets of grid rows 1..8 needed up to 1 220 dependent moves (mean 10.6; interior rows: mean 4.0, max 14), a
+// serial chain of ~0.6 ms in a kernel that otherwise takes 0.45 ms per 2048-row band (profiles/r02_band_*).
+// Leaving through the failing edge the target is FARTHEST beyond (violation / max-norm length of the edge) brings
+// that to max 15, mean 3.7 moves.  The choice only changes the path: the triangle a walk ends in does not depend
+// on it (targets inside the margin band are re-located along the reference's own path by
+// fixup_kernel), and a target that fails a hull edge is outside the hull whichever edge reports it.
+template <class R>
+__device__ __forceinline__ int farthest_failing_edge(const TriGeom<R>& g, R c1, R c2, R c3, R margin) {
+  const R l1 = fmax(fabs(g.x2 - g.x1), fabs(g.y2 - g.y1));
+  const R l2 = fmax(fabs(g.x3 - g.x2), fabs(g.y3 - g.y2));
+  const R l3 = fmax(fabs(g.x1 - g.x3), fabs(g.y1 - g.y3));
+  // normalised violation of the failing edges (negative; passing edges: +huge).  Only compared with each other.
+  const R v1 = c1 < margin ? c1 / l1 : Consts<R>::huge();
+  const R v2 = c2 < margin ? c2 / l2 : Consts<R>::huge();
+  const R v3 = c3 < margin ? c3 / l3 : Consts<R>::huge();
+  // edge 1 -> n3, edge 2 -> n1, edge 3 -> n2 (triangle_walk.f90:66-71); ties / NaN: the reference's order
+  if (v1 <= v2 && v1 <= v3) return g.n3;
+  if (v2 <= v3) return g.n1;
+  return g.n2;
+}
+
 // Band-limited pack: the first failing edge leads to a triangle that was not packed.  Any failing edge is a valid
 // move of a visibility walk and the triangle found does not depend on the path, so take a LATER failing
 // edge whose neighbour is packed if there is one; otherwise the caller reports GI_ERR_PACK_WINDOW.  (A failing hull
@@ -275,6 +306,8 @@ __device__ __forceinline__ int walk(const TriGeom<R>* __restrict__ geom, int tri
     else if (c2 < margin) nxt = g.n1;
     else if (c3 < margin) nxt = g.n2;
     else break;
+    if (g.pad < 0 && (int)(c1 < margin) + (int)(c2 < margin) + (int)(c3 < margin) > 1)
+      nxt = farthest_failing_edge(g, c1, c2, c3, margin);
     if (nxt == kNotPacked) nxt = packed_alternative(c1 < margin, c2 < margin, c3 < margin, g.n1, g.n2, g.n3);
     if (nxt < 0) {  // :74-80
       if (nxt == kNotPacked) raise_status(status, GI_ERR_PACK_WINDOW);
@@ -286,6 +319,32 @@ __device__ __forceinline__ int walk(const TriGeom<R>* __restrict__ geom, int tri
   }
   iters = it;
   return tri;
+}
+
+// The rest of one target's walk with the farthest-failing-edge rule in EVERY triangle, out of line: phase 1 of
+// locate_eval_kernel calls it when its current triangle is a long one and more than one edge fails, then re-enters
+// the triangle returned (>= 0: every edge passes there; ~id: left the hull / the packed set from triangle id).
+// Everything the caller keeps per triangle is reloaded after the call, so almost nothing is live across it.
+template <class R>
+__device__ __noinline__ int careful_locate(const TriGeom<R>* __restrict__ geom, int tri, R tx, R ty, int iter_cap,
+                                           int* status) {
+  const R margin = Consts<R>::margin();
+  for (int it = 0;; ++it) {
+    TriGeom<R> g;
+    load_walk(geom + tri, g);
+    const R c1 = (g.x2 - g.x1) * (ty - g.y1) - (g.y2 - g.y1) * (tx - g.x1);
+    const R c2 = (g.x3 - g.x2) * (ty - g.y2) - (g.y3 - g.y2) * (tx - g.x2);
+    const R c3 = (g.x1 - g.x3) * (ty - g.y3) - (g.y1 - g.y3) * (tx - g.x3);
+    if (!(c1 < margin) && !(c2 < margin) && !(c3 < margin)) return tri;
+    int nxt = farthest_failing_edge(g, c1, c2, c3, margin);
+    if (nxt == kNotPacked) nxt = packed_alternative(c1 < margin, c2 < margin, c3 < margin, g.n1, g.n2, g.n3);
+    if (nxt < 0) {
+      if (nxt == kNotPacked) raise_status(status, GI_ERR_PACK_WINDOW);
+      return ~tri;
+    }
+    if (it >= iter_cap) { raise_status(status, GI_ERR_ITER_CAP); return ~tri; }
+    tri = nxt;
+  }
 }
 
 // interpolation.f90:385-398, same operation order; the two divisions share the reciprocal of denom.
@@ -325,6 +384,7 @@ template <> __device__ __forceinline__ int amb_threshold<float>(const TriGeom<fl
   return t < 1e37f ? __float_as_int(t) + 1 : 0x7f000000;
 }
 // |x| below the triangle's threshold?  Integer compares on the (high) word: two instructions per cross.
+// (thr = the record's pad without its kLongTriangle bit)
 __device__ __forceinline__ bool in_amb_band(double x, int thr) { return (__double2hiint(x) & 0x7fffffff) < thr; }
 __device__ __forceinline__ bool in_amb_band(float x, int thr) { return (__float_as_int(x) & 0x7fffffff) < thr; }
 
@@ -339,6 +399,7 @@ __device__ __forceinline__ int walk_checked(const TriGeom<R>* __restrict__ geom,
     ++it;
     TriGeom<R> g;
     load_walk(geom + tri, g);
+    g.pad &= 0x7fffffff;  // the reference's path: first failing edge, long triangle or not
     const R c1 = (g.x2 - g.x1) * (ty - g.y1) - (g.y2 - g.y1) * (tx - g.x1);
     const R c2 = (g.x3 - g.x2) * (ty - g.y2) - (g.y3 - g.y2) * (tx - g.x2);
     const R c3 = (g.x1 - g.x3) * (ty - g.y3) - (g.y1 - g.y3) * (tx - g.x3);
@@ -432,13 +493,15 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   if (active) {
     int tri, n1, n2, n3, thr;
     R m1, m2, m3, p1, p2, p3, k1, k2, k3;
-    bool fresh;  // no target resolved in `tri` yet
+    bool fresh;    // no target resolved in `tri` yet
+    bool careful;  // long triangle: see farthest_failing_edge
+    bool forced_out = false;  // careful_locate found this row's target outside the hull at `tri`
     auto enter = [&](int t) {  // make `t` the current triangle: one 64 B load + 12 flops
       tri = t;
       fresh = true;
       TriGeom<R> g;
       load_walk(a.geom + t, g);
-      n1 = g.n1; n2 = g.n2; n3 = g.n3; thr = g.pad;
+      n1 = g.n1; n2 = g.n2; n3 = g.n3; thr = g.pad & 0x7fffffff; careful = g.pad < 0;
       const R ex1 = g.x2 - g.x1, ey1 = g.y2 - g.y1;   // edge (v1,v2)
       const R ex2 = g.x3 - g.x2, ey2 = g.y3 - g.y2;   // edge (v2,v3)
       const R ex3 = g.x1 - g.x3, ey3 = g.y1 - g.y3;   // edge (v3,v1)
@@ -469,10 +532,19 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
       const bool outside = o1 | o2 | o3;
       int nxt = o1 ? n3 : (o2 ? n1 : n2);
       if (outside && nxt == kNotPacked) nxt = packed_alternative(o1, o2, o3, n1, n2, n3);
-      if (outside && nxt >= 0) {
-        if (it < a.iter_cap) { enter(nxt); continue; }
+      if (outside && nxt >= 0 && !forced_out) {
+        if (it < a.iter_cap) {
+          if (careful && (int)o1 + (int)o2 + (int)o3 > 1) {   // rare: see farthest_failing_edge
+            const int res = careful_locate(a.geom, tri, FY ? cv : cf, FY ? cf : cv, a.iter_cap, a.status);
+            forced_out = res < 0;   // a failing hull edge was seen: outside, whichever edge fails first there
+            nxt = forced_out ? ~res : res;
+          }
+          enter(nxt);   // (after careful_locate: the test above is repeated in the triangle that walk ended in)
+          continue;
+        }
         raise_status(a.status, GI_ERR_ITER_CAP);
       }
+      forced_out = false;
       if (outside && nxt == kNotPacked) raise_status(a.status, GI_ERR_PACK_WINDOW);  // band-limited pack too tight
       // resolved: inside `tri`, or outside the hull (:74-80: the last valid triangle is kept).
       // A target within the margin band of an edge is accepted by both adjacent triangles and which one the
