@@ -36,6 +36,7 @@
 
 #include "ieee_div.cuh"
 #include "kernels.cuh"
+#include "scan.cuh"
 
 namespace gi {
 
@@ -452,8 +453,76 @@ template <class R> struct WalkArgs {
   unsigned long long* start_part;  // start_tri_kernel scratch: 2 * kStartBlocks partial results + ticket (zeroed)
   int reference_rows;   // GI_BARY_REFERENCE_ORDER: locate every target by the reference's row-sequential walk
   int* row_todo;        // [len_y], zeroed: grid rows a fix-up handed to row_walk_kernel
+  const int* only_if;   // locate_eval_kernel: run only if this device flag is set (nullptr: always), see raster.cuh
   int* status;
 };
+
+// Phase 2 of the locate / raster kernels: evaluate one strip of ROWS x kWalkThreads targets whose triangles are in
+// the shared-memory tile `stri` (>= 0: inside that triangle; < 0: outside the hull, ~id of the last valid triangle
+// or -1), store the values and the outside-hull mask words.
+template <class R, bool FY, bool PEERS, int ROWS>
+__device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (*stri)[kWalkThreads], const R* saxis,
+                                               int srow0, int nrows, int lane_f, bool active, R cf) {
+  const TargetWindow<R>& w = a.win;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int f = w.f0 + lane_f;
+  // ---- phase 2: evaluate -----------------------------------------------------------------------
+  // Row-synchronous.  When the column enters another triangle the lane fetches the record's evaluation sectors
+  // (L1-resident after phase 1) -- A..D, denom and the nodal values were computed by the pack pass -- and derives
+  // what depends on (triangle, column): A*(tx-x3), C*(tx-x3) for fast axis x and the refined reciprocal of denom;
+  // the row-dependent half of interpolation.f90:387-394 is evaluated per target.
+  const bool f_in_band = active && f >= a.bf0 && f < a.bf1;
+  const int wpr = (w.nf() + 31) >> 5;
+  const int bnf = a.bf1 - a.bf0;
+  static_assert(ROWS <= 32, "one lane per row keeps that row's mask word");
+  const int rb0 = max(0, a.bs0 - srow0), rb1 = min(nrows, a.bs1 - srow0);   // rows of the strip inside the band
+  // band-relative element of (row 0 of the strip, this column); only dereferenced for rows inside the band
+  const int64_t oo0 = (int64_t)(srow0 - a.bs0) * a.out_ld + (f - a.bf0);
+  R* optr = a.out + oo0;
+  int32_t* tptr = a.tri_out ? a.tri_out + ((int64_t)(srow0 - a.bs0) * bnf + (f - a.bf0)) : nullptr;
+  int cur = -1;
+  unsigned my_mask = 0;
+  R c1 = 0, q1 = 0, c2 = 0, q2 = 0, p3 = 0, d1 = 0, d2 = 0, d3 = 0;
+  DivRcp<R> dv;
+  dv.d = R(1); dv.r2 = R(1);
+#pragma unroll 2
+  for (int r = 0; r < nrows; ++r, optr += a.out_ld) {
+    const int t = active ? stri[r][tid] : 0;
+    const bool inside = t >= 0;
+    if (f_in_band && r >= rb0 && r < rb1) {
+      if (inside) {
+        if (t != cur) {
+          cur = t;
+          TriGeom<R> g;
+          load_eval(a.geom + t, g);
+          dv.set(g.denom);
+          d1 = g.d1; d2 = g.d2; d3 = g.d3;
+          if (!FY) { const R u = cf - g.x3; c1 = g.A * u; q1 = g.B; c2 = g.C * u; q2 = g.D; p3 = g.y3; }
+          else { const R u = cf - g.y3; c1 = g.B * u; q1 = g.A; c2 = g.D * u; q2 = g.C; p3 = g.x3; }
+        }
+        // w1 = (A*(tx-x3) + B*(ty-y3))/denom, w2 = (C*(tx-x3) + D*(ty-y3))/denom   (:387-394); the sum commutes
+        const R t3 = saxis[r] - p3;
+        R w1, w2;
+        quotient_pair(dv, FY ? q1 * t3 + c1 : c1 + q1 * t3, FY ? q2 * t3 + c2 : c2 + q2 * t3, w1, w2);
+        const R w3 = R(1) - w1 - w2;
+        const R v = d1 * w1 + d2 * w2 + d3 * w3;                   // :396-398
+        *optr = v;
+        if (PEERS) {  // the fused gather: the same element of every peer field, over NVLink
+          const int64_t oo = oo0 + (int64_t)r * a.out_ld;
+          for (int d = 0; d < a.n_peer; ++d) a.peer_out[d][oo] = v;
+        }
+      }
+      if (tptr) tptr[(int64_t)r * bnf] = (inside ? t : ~t) + 1;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, active && !inside);
+    if (lane == r) my_mask = m;  // lane r keeps the word of row r (ROWS <= 32)
+  }
+  if (lane < nrows && (lane_f >> 5) < wpr) {
+    const int64_t wi = (int64_t)(srow0 + lane - w.s0) * wpr + (lane_f >> 5);
+    a.mask_words[wi] = my_mask;
+    if (my_mask) a.nz_words[atomicAdd((unsigned long long*)(a.counters + 4), 1ull)] = (int)wi;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // The production kernel: locate, then evaluate.
@@ -476,6 +545,7 @@ template <class R, bool FY, bool PEERS, int ROWS, int MINB>
 __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const WalkArgs<R> a) {
   __shared__ int stri[ROWS][kWalkThreads];
   __shared__ R saxis[ROWS];
+  if (a.only_if && !*a.only_if) return;  // the rasteriser did the window
   const TargetWindow<R>& w = a.win;
   const int tid = threadIdx.x, lane = tid & 31;
   const int lane_f = blockIdx.x * kWalkThreads + tid;
@@ -567,67 +637,14 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   }
   __syncthreads();
 
-  // ---- phase 2: evaluate -----------------------------------------------------------------------
-  // Row-synchronous.  When the column enters another triangle the lane fetches the record's evaluation sectors
-  // (L1-resident after phase 1) -- A..D, denom and the nodal values were computed by the pack pass -- and derives
-  // what depends on (triangle, column): A*(tx-x3), C*(tx-x3) for fast axis x and the refined reciprocal of denom;
-  // the row-dependent half of interpolation.f90:387-394 is evaluated per target.
-  const bool f_in_band = active && f >= a.bf0 && f < a.bf1;
-  const int wpr = (w.nf() + 31) >> 5;
-  const int bnf = a.bf1 - a.bf0;
-  static_assert(ROWS <= 32, "one lane per row keeps that row's mask word");
-  const int rb0 = max(0, a.bs0 - srow0), rb1 = min(nrows, a.bs1 - srow0);   // rows of the strip inside the band
-  // band-relative element of (row 0 of the strip, this column); only dereferenced for rows inside the band
-  const int64_t oo0 = (int64_t)(srow0 - a.bs0) * a.out_ld + (f - a.bf0);
-  R* optr = a.out + oo0;
-  int32_t* tptr = a.tri_out ? a.tri_out + ((int64_t)(srow0 - a.bs0) * bnf + (f - a.bf0)) : nullptr;
-  int cur = -1;
-  unsigned my_mask = 0;
-  R c1 = 0, q1 = 0, c2 = 0, q2 = 0, p3 = 0, d1 = 0, d2 = 0, d3 = 0;
-  DivRcp<R> dv;
-  dv.d = R(1); dv.r2 = R(1);
-#pragma unroll 2
-  for (int r = 0; r < nrows; ++r, optr += a.out_ld) {
-    const int t = active ? stri[r][tid] : 0;
-    const bool inside = t >= 0;
-    if (f_in_band && r >= rb0 && r < rb1) {
-      if (inside) {
-        if (t != cur) {
-          cur = t;
-          TriGeom<R> g;
-          load_eval(a.geom + t, g);
-          dv.set(g.denom);
-          d1 = g.d1; d2 = g.d2; d3 = g.d3;
-          if (!FY) { const R u = cf - g.x3; c1 = g.A * u; q1 = g.B; c2 = g.C * u; q2 = g.D; p3 = g.y3; }
-          else { const R u = cf - g.y3; c1 = g.B * u; q1 = g.A; c2 = g.D * u; q2 = g.C; p3 = g.x3; }
-        }
-        // w1 = (A*(tx-x3) + B*(ty-y3))/denom, w2 = (C*(tx-x3) + D*(ty-y3))/denom   (:387-394); the sum commutes
-        const R t3 = saxis[r] - p3;
-        R w1, w2;
-        quotient_pair(dv, FY ? q1 * t3 + c1 : c1 + q1 * t3, FY ? q2 * t3 + c2 : c2 + q2 * t3, w1, w2);
-        const R w3 = R(1) - w1 - w2;
-        const R v = d1 * w1 + d2 * w2 + d3 * w3;                   // :396-398
-        *optr = v;
-        if (PEERS) {  // the fused gather: the same element of every peer field, over NVLink
-          const int64_t oo = oo0 + (int64_t)r * a.out_ld;
-          for (int d = 0; d < a.n_peer; ++d) a.peer_out[d][oo] = v;
-        }
-      }
-      if (tptr) tptr[(int64_t)r * bnf] = (inside ? t : ~t) + 1;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, active && !inside);
-    if (lane == r) my_mask = m;  // lane r keeps the word of row r (ROWS <= 32)
-  }
-  if (lane < nrows && (lane_f >> 5) < wpr) {
-    const int64_t wi = (int64_t)(srow0 + lane - w.s0) * wpr + (lane_f >> 5);
-    a.mask_words[wi] = my_mask;
-    if (my_mask) a.nz_words[atomicAdd((unsigned long long*)(a.counters + 4), 1ull)] = (int)wi;
-  }
+  evaluate_strip<R, FY, PEERS, ROWS>(a, stri, saxis, srow0, nrows, lane_f, active, cf);
   // one atomic per warp for the iteration counter (iters_tot, interpolation.f90:374)
   for (int off = 16; off > 0; off >>= 1) iters_sum += __shfl_down_sync(0xffffffffu, iters_sum, off);
   if (lane == 0 && iters_sum) atomicAdd((unsigned long long*)a.counters, (unsigned long long)iters_sum);
 }
 
+
+#include "raster.cuh"
 
 // Result of a (re-)located target (f, s): value or mask bit, triangle id, work list of the hull fill.
 template <class R>
@@ -1058,6 +1075,7 @@ template <class R> struct PackedMesh {
   int* seed;
   int ncx, ncy, num_tri;
   RawMesh<R> raw;  // raw.use = 1: only the triangles near the row window have records
+  const uint8_t* need;  // band-limited pack: which triangles have records (nullptr: all)
 };
 
 // rows [w0, w1) +- this many rows are packed by a band-limited pack (GI_BARY_BAND_PACK)
@@ -1089,6 +1107,7 @@ int bary_pack(Scratch& scr, const R* points, int num_points, const R* data_in, c
     GI_CUDA(cudaGetLastError());
     pm->raw.use = 1;
   }
+  pm->need = need;
   pack_mesh_kernel<R><<<div_up(num_tri, 256), 256, 0, st>>>(
       pv, data_in, sv, topo_t3(neighbours, num_tri, flags & GI_TOPO_ROWMAJOR),
       num_points, num_tri, pm->geom, pm->seed, x_axis, len_x, y_axis, len_y, need, status);
@@ -1097,16 +1116,37 @@ int bary_pack(Scratch& scr, const R* points, int num_points, const R* data_in, c
 }
 
 // 2. + 2b. locate / evaluate / fix-up over the window wa.win (mask words, work list and counters as set in wa)
+// Rasteriser or walk?  The rasteriser pays two binning passes and tests every node of a triangle's bounding box: it
+// wins where a triangle covers a handful to a few hundred grid nodes and there are enough triangles to fill the
+// GPU; coarse meshes under fine grids (no moves to make) and small calls (launch-bound) keep the walk.
+// GI_BARY_RASTER=0 / 1 forces the choice (tests).
+template <class R> bool use_raster(int num_tri, int64_t nodes) {
+  static const int forced = getenv("GI_BARY_RASTER") ? atoi(getenv("GI_BARY_RASTER")) : -1;
+  if (forced >= 0) return forced != 0;
+  return sizeof(R) == 8 && num_tri >= 4096 && nodes >= (int64_t)num_tri && nodes <= (int64_t)512 * num_tri;
+}
+
 template <class R>
-int bary_walk(const WalkArgs<R>& wa, const PackedMesh<R>& pm, const R* x_axis, const R* y_axis, int len_x, int len_y,
-              int num_points, cudaStream_t st) {
+int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis, const R* y_axis, int len_x, int len_y,
+              int num_points, cudaStream_t st, const TileBins* bins = nullptr, int tile_row0 = 0) {
+  WalkArgs<R> wa = wa_in;
   const int nf = wa.win.nf(), ns = wa.win.ns();
   // 128 columns x 32 rows per CTA, 64 registers, >= 8 CTAs per SM: the best of the shapes measured in round 1
   // (profiles/r01_walk_variants.md)
   constexpr int kRows = 32;
+  static_assert(kRows == kTileH, "the rasteriser's tiles are the walk kernel's strips");
   dim3 grid(div_up(nf, kWalkThreads), div_up(ns, kRows));
   GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
   const bool fy = wa.win.fast_is_y, peers = wa.n_peer > 0;
+  wa.only_if = nullptr;
+  if (bins) {
+    if (!fy && !peers) raster_eval_kernel<R, false, false><<<grid, kWalkThreads, 0, st>>>(wa, *bins, tile_row0);
+    else if (fy && !peers) raster_eval_kernel<R, true, false><<<grid, kWalkThreads, 0, st>>>(wa, *bins, tile_row0);
+    else if (!fy) raster_eval_kernel<R, false, true><<<grid, kWalkThreads, 0, st>>>(wa, *bins, tile_row0);
+    else raster_eval_kernel<R, true, true><<<grid, kWalkThreads, 0, st>>>(wa, *bins, tile_row0);
+    GI_CUDA(cudaGetLastError());
+    wa.only_if = bins->bad;  // descending axes / list overflow: the walk kernel does the window after all
+  }
   if (!fy && !peers) locate_eval_kernel<R, false, false, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
   else if (fy && !peers) locate_eval_kernel<R, true, false, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
   else if (!fy) locate_eval_kernel<R, false, true, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
@@ -1186,7 +1226,14 @@ int bary_run_window(Scratch& scr, const PackedMesh<R>& pm, const R* x_axis, int 
   wa.n_peer = dest ? dest->n_peer : 0;
   for (int d = 0; d < wa.n_peer; ++d) wa.peer_out[d] = dest->peer[d];
   wa.status = slot.dev;
-  GI_TRY(bary_walk<R>(wa, pm, x_axis, y_axis, len_x, len_y, num_points, st));
+  TileBins bins;
+  const bool raster = use_raster<R>(num_tri, (int64_t)nf * ns);
+  if (raster) {
+    ph->mark("bin");
+    GI_TRY(build_tile_bins<R>(scr, pm.geom, pm.need, num_tri, wa.win, &bins));
+    ph->mark("walk");
+  }
+  GI_TRY(bary_walk<R>(wa, pm, x_axis, y_axis, len_x, len_y, num_points, st, raster ? &bins : nullptr, 0));
   if (mask_out || fill_src) {
     expand_mask_kernel<<<kNumSMs * 8, 256, 0, st>>>(mask_words, wpr, wa.win.f0, wa.win.s0, wa.bf0, wa.bf1, wa.bs0,
                                                    wa.bs1, mask_out, fill_src);
@@ -1315,6 +1362,15 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
   GI_TRY(scr.alloc(&row_todo, (size_t)len_y));
   GI_CUDA(cudaMemsetAsync(row_todo, 0, sizeof(int) * (size_t)len_y, st));
 
+  // tile lists of the whole walked window, once: the sub-bands below start at whole tile rows
+  TileBins bins;
+  const bool raster = use_raster<R>(num_tri, (int64_t)nfast * nslow);
+  if (raster) {
+    const TargetWindow<R> we = rowmajor ? TargetWindow<R>{dx, dy, len_x, len_y, ef0, ef1, es0, es1, 0}
+                                        : TargetWindow<R>{dy, dx, len_y, len_x, ef0, ef1, es0, es1, 1};
+    GI_TRY(build_tile_bins<R>(scr, pm.geom, pm.need, num_tri, we, &bins));
+  }
+
   int nb = plan_bands(nslow, (int64_t)(row_end - row_begin) * len_x * sizeof(R));
   for (;;) {
     GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 8 * kMaxBands, st));
@@ -1370,7 +1426,8 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
         wa.amb_list = amb_list; wa.amb_cap = amb_cap; wa.start_part = start_part;
         wa.reference_rows = (flags & GI_BARY_REFERENCE_ORDER) ? 1 : 0; wa.row_todo = row_todo;
         wa.status = slot.dev;
-        GI_TRY(bary_walk<R>(wa, pm, dx, dy, len_x, len_y, num_points, st));
+        GI_TRY(bary_walk<R>(wa, pm, dx, dy, len_x, len_y, num_points, st, raster ? &bins : nullptr,
+                            (int)((start[b] - es0) / kTileH)));
       }
       if (b > 0 && start[b - 1] < start[b]) GI_TRY(fill_band(b - 1));
     }
