@@ -31,6 +31,19 @@ struct TileBins {
   int ntx, nty, cap;
 };
 
+// min / max by compare-and-select (fmin / fmax on doubles expand to ~7 instructions of NaN handling each)
+template <class R> __device__ __forceinline__ R rmin(R a, R b) { return a < b ? a : b; }
+template <class R> __device__ __forceinline__ R rmax(R a, R b) { return a > b ? a : b; }
+
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(unsigned addr, int v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 template <class R> struct Inf;
 template <> struct Inf<double> { __device__ static double v() { return __longlong_as_double(0x7ff0000000000000ll); } };
 template <> struct Inf<float> { __device__ static float v() { return __int_as_float(0x7f800000); } };
@@ -66,7 +79,7 @@ __device__ __forceinline__ int bound_from(Ax ax, int n, R v, int guess) {
 
 template <class R> __device__ __forceinline__ int guess_index(R v, R first, R inv_step, int n) {
   const R g = (v - first) * inv_step;
-  return (int)fmin(fmax(g, R(-1)), R(n + 1));  // (NaN -> -1)
+  return (int)rmin(rmax(g, R(-1)), R(n + 1));  // (NaN -> n + 1: the search starts at the end)
 }
 
 // Bounds of the nodes a triangle can accept, along the fast and the slow axis.  The orientation test passes down
@@ -75,15 +88,15 @@ template <class R> __device__ __forceinline__ int guess_index(R v, R first, R in
 // triangles).
 template <class R>
 __device__ __forceinline__ void tri_bounds(const TriGeom<R>& g, bool fy, R& flo, R& fhi, R& slo, R& shi) {
-  const R xmin = fmin(fmin(g.x1, g.x2), g.x3), xmax = fmax(fmax(g.x1, g.x2), g.x3);
-  const R ymin = fmin(fmin(g.y1, g.y2), g.y3), ymax = fmax(fmax(g.y1, g.y2), g.y3);
-  const R l1 = fmax(fabs(g.x2 - g.x1), fabs(g.y2 - g.y1));
-  const R l2 = fmax(fabs(g.x3 - g.x2), fabs(g.y3 - g.y2));
-  const R l3 = fmax(fabs(g.x1 - g.x3), fabs(g.y1 - g.y3));
-  const R lmin = fmin(fmin(l1, l2), l3), ext = fmax(xmax - xmin, ymax - ymin);
+  const R xmin = rmin(rmin(g.x1, g.x2), g.x3), xmax = rmax(rmax(g.x1, g.x2), g.x3);
+  const R ymin = rmin(rmin(g.y1, g.y2), g.y3), ymax = rmax(rmax(g.y1, g.y2), g.y3);
+  const R l1 = rmax(fabs(g.x2 - g.x1), fabs(g.y2 - g.y1));
+  const R l2 = rmax(fabs(g.x3 - g.x2), fabs(g.y3 - g.y2));
+  const R l3 = rmax(fabs(g.x1 - g.x3), fabs(g.y1 - g.y3));
+  const R lmin = rmin(rmin(l1, l2), l3), ext = rmax(xmax - xmin, ymax - ymin);
   const R eps = sizeof(R) == 8 ? R(1.1102230246251565e-16) : R(5.9604645e-8);
-  const R mag = fmax(fmax(fabs(xmin), fabs(xmax)), fmax(fabs(ymin), fabs(ymax)));
-  R d = lmin > R(0) ? fmin(R(8e-10) / lmin, ext) : ext;
+  const R mag = rmax(rmax(fabs(xmin), fabs(xmax)), rmax(fabs(ymin), fabs(ymax)));
+  R d = lmin > R(0) ? rmin(R(8e-10) / lmin, ext) : ext;
   d = d + R(64) * eps * (ext + mag);
   flo = (fy ? ymin : xmin) - d; fhi = (fy ? ymax : xmax) + d;
   slo = (fy ? xmin : ymin) - d; shi = (fy ? xmax : ymax) + d;
@@ -188,7 +201,9 @@ raster_eval_kernel(const WalkArgs<R> a, const TileBins b, int tile_row0) {
   const R f_first = sfast[0], s_first = saxis[0];
   const R f_span = sfast[ncols - 1] - f_first, s_span = saxis[nrows - 1] - s_first;
   const R inv_f = f_span > R(0) ? R(ncols - 1) / f_span : R(0), inv_s = s_span > R(0) ? R(nrows - 1) / s_span : R(0);
-  const double wq = fmax(sfx[ncols - 1], sfy[nrows - 1]);
+  const double wq = sfx[ncols - 1] + sfy[nrows - 1];
+  const unsigned sfx_s = (unsigned)__cvta_generic_to_shared(sfx), sfy_s = (unsigned)__cvta_generic_to_shared(sfy);
+  const unsigned stri_s = (unsigned)__cvta_generic_to_shared(&stri[0][0]);
   auto fax = [&](int i) { return sfast[i]; };
   auto sax = [&](int i) { return saxis[i]; };
   long long tests = 0;
@@ -253,27 +268,39 @@ raster_eval_kernel(const WalkArgs<R> a, const TileBins b, int tile_row0) {
       const double C3 = __fma_rn(ey3, vx3, __fma_rn(-ex3, vy3, 1e-10));
       const double af1 = FY ? ex1 : -ey1, af2 = FY ? ex2 : -ey2, af3 = FY ? ex3 : -ey3;   // factor of the fast coordinate
       const double as1 = FY ? -ey1 : ex1, as2 = FY ? -ey2 : ex2, as3 = FY ? -ey3 : ex3;   // factor of the slow coordinate
-      const double M = fmax(fmax(fabs(ex1) + fabs(ey1), fabs(ex2) + fabs(ey2)), fabs(ex3) + fabs(ey3));
-      const double Q = fmax(fmax(fmax(fabs(vx1), fabs(vy1)), fmax(fabs(vx2), fabs(vy2))), fmax(fmax(fabs(vx3), fabs(vy3)), wq));
+      // (sums instead of maxima: cheaper, and a larger threshold only sends a few more nodes to the fix-up)
+      const double M = fabs(ex1) + fabs(ey1) + fabs(ex2) + fabs(ey2) + fabs(ex3) + fabs(ey3);
+      const double Q = fabs(vx1) + fabs(vy1) + fabs(vx2) + fabs(vy2) + fabs(vx3) + fabs(vy3) + wq;
       const double t_rec = sizeof(R) == 8 ? __hiloint2double(g.pad & 0x7fffffff, 0)
                                            : (double)__int_as_float(g.pad & 0x7fffffff);
       const double Tr = t_rec + 1e-10 + 32.0 * 1.1102230246251565e-16 * M * Q;
-      const int n = (c1 - c0 + 1) * (r1 - r0 + 1);
+      const int thi = Tr < 1e300 ? __double2hiint(Tr) + 1 : 0x7fe00000;  // |y| < Tr  =>  high word of |y| < thi
+      const int ncol = c1 - c0 + 1, n = ncol * (r1 - r0 + 1);
       tests += n;
-      int c = c0, r = r0;
+      // the node loop, flattened over the box (lanes with boxes of different shapes stay together), on 32-bit
+      // shared-memory addresses
+      const unsigned fa0 = sfx_s + 8u * c0, fa_end = sfx_s + 8u * c1;
+      unsigned fa = fa0, sa = sfy_s + 8u * r0, ta = stri_s + 4u * (r0 * kWalkThreads + c0);
+      const unsigned ta_wrap = 4u * (kWalkThreads - ncol) + 4u;
       for (int i = 0; i < n; ++i) {
-        const double fv = sfx[c], sv = sfy[r];
+        const double fv = lds_f64(fa), sv = lds_f64(sa);
         const double y1 = __fma_rn(as1, sv, __fma_rn(af1, fv, C1));
         const double y2 = __fma_rn(as2, sv, __fma_rn(af2, fv, C2));
         const double y3 = __fma_rn(as3, sv, __fma_rn(af3, fv, C3));
-        const double m = fmin(fmin(y1, y2), y3);
-        if (m >= 0.0) stri[r][c] = id;   // every orientation test passes (:57-60): the node lies in this triangle
-        if (fabs(m) < Tr) {               // too close to an edge to call: the reference's own walk decides
+        const int h1 = __double2hiint(y1), h2 = __double2hiint(y2), h3 = __double2hiint(y3);
+        // every orientation test passes (:57-60; all three y_i >= 0, i.e. no sign bit): the node lies in this triangle
+        if ((h1 | h2 | h3) >= 0) sts_u32(ta, id);
+        // some |y_i| below T_r: too close to an edge('s line) to call, the reference's own walk decides
+        if (min(min(h1 & 0x7fffffff, h2 & 0x7fffffff), h3 & 0x7fffffff) < thi) {
+          const int cell = (int)((ta - stri_s) >> 2);  // r * 128 + c
           const unsigned long long slot2 = atomicAdd((unsigned long long*)(a.counters + 5), 1ull);
           if (slot2 < (unsigned long long)a.amb_cap)
-            a.amb_list[slot2] = (srow0 + r - w.s0) * w.nf() + blockIdx.x * kWalkThreads + c;
+            a.amb_list[slot2] = (srow0 + (cell >> 7) - w.s0) * w.nf() + blockIdx.x * kWalkThreads + (cell & 127);
         }
-        if (++c > c1) { c = c0; ++r; }
+        const bool wrap = fa == fa_end;
+        fa = wrap ? fa0 : fa + 8u;
+        sa += wrap ? 8u : 0u;
+        ta += wrap ? ta_wrap : 4u;
       }
     }
     __syncthreads();
