@@ -45,6 +45,25 @@ namespace {
 constexpr int kSeedCell = 16;      // targets per seed-grid cell edge
 constexpr int kWalkThreads = 128;  // columns per CTA
 
+// tile lists of the rasteriser (raster.cuh); counted by the pack pass
+constexpr int kTileW = kWalkThreads;  // fast-axis nodes per tile
+constexpr int kTileH = 32;            // slow-axis nodes per tile
+
+struct TileBins {
+  int* start;  // [ntx*nty + 1] exclusive offsets into list
+  int* fill;   // [ntx*nty] fill cursors (zeroed between the passes)
+  int* list;   // [cap] triangle ids, tile by tile
+  int* bad;    // device flag: != 0 -> axes not ascending or list overflow: the walk kernel takes over
+  uint2* range;  // [num_tri] tile range of every triangle {tx0 | tx1 << 16, ty0 | ty1 << 16}, written by the pack pass
+  int ntx, nty, cap;
+};
+template <class R> struct TriGeom;
+template <class R>
+__device__ __forceinline__ bool tri_tile_range(const TriGeom<R>& g, const TargetWindow<R>& w, int& tx0, int& tx1, int& ty0, int& ty1);
+template <class R> __device__ __forceinline__ void check_axes(const TargetWindow<R>& w, int t, int* bad);
+
+
+
 // One record per triangle, f64: 128 B = 4 sectors = one cache line.
 //   sectors 0-1  what a walk step needs: 3 vertices + 3 neighbour ids + the ambiguity threshold
 //   sector  2    A = y2-y3, B = x3-x2, C = y3-y1, D = x1-x3                      (interpolation.f90:385-394)
@@ -165,9 +184,14 @@ __global__ void __launch_bounds__(256)
 pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, TopoView nbr, int num_points,
                  int num_tri, TriGeom<R>* __restrict__ geom, int* __restrict__ seed,
                  const R* __restrict__ x_axis, int len_x, const R* __restrict__ y_axis, int len_y,
-                 const uint8_t* __restrict__ need, int* __restrict__ status) {
+                 const uint8_t* __restrict__ need, const TargetWindow<R> bw, const TileBins bb,
+                 int* __restrict__ status) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool packed = t < num_tri && (!need || need[t]);
+  if (bb.start) {  // rasteriser (raster.cuh): axes usable?  A triangle without a record is in no tile.
+    check_axes(bw, t, bb.bad);
+    if (t < num_tri && !packed) bb.range[t] = make_uint2(1u, 1u);  // tx0 = 1 > tx1 = 0: empty
+  }
   // fallback seed (seed[ncx*ncy]): the smallest packed triangle id.  CTAs start roughly in id order, so after the
   // first few only a plain load is paid (39 000 atomics on one address cost 0.5 ms)
   const unsigned pm = __ballot_sync(0xffffffffu, packed);
@@ -207,6 +231,13 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
   g.denom = g.A * g.D + g.B * (g.y1 - g.y3);                                     // :385-386
   g.d1 = __ldg(data + (a - 1)); g.d2 = __ldg(data + (b - 1)); g.d3 = __ldg(data + (c - 1));
   geom[t] = g;
+  if (bb.start) {  // first binning pass: count this triangle in the tiles its bounds meet
+    int tx0 = 1, tx1 = 0, ty0 = 1, ty1 = 0;
+    if (!bad && tri_tile_range(g, bw, tx0, tx1, ty0, ty1))
+      for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(bb.start + ty * bb.ntx + tx, 1);
+    bb.range[t] = make_uint2((unsigned)tx0 | (unsigned)tx1 << 16, (unsigned)ty0 | (unsigned)ty1 << 16);
+  }
   if (bad) return;
   // seed grid: cell of the centroid under a uniform-axis approximation (a heuristic: it only has to be near)
   const R cx = (g.x1 + g.x2 + g.x3) / R(3), cy = (g.y1 + g.y2 + g.y3) / R(3);
@@ -541,17 +572,14 @@ __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (
 //                      shared-reciprocal divisions; 128 consecutive doubles per row are stored coalesced and
 //                      the outside-hull bits come from one ballot per warp row.
 // ---------------------------------------------------------------------------------------------
-template <class R, bool FY, bool PEERS, int ROWS, int MINB>
-__global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const WalkArgs<R> a) {
-  __shared__ int stri[ROWS][kWalkThreads];
-  __shared__ R saxis[ROWS];
-  if (a.only_if && !*a.only_if) return;  // the rasteriser did the window
+template <class R, bool FY, bool PEERS, int ROWS, bool BP>
+__device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, int by, int (*stri)[kWalkThreads], R* saxis) {
   const TargetWindow<R>& w = a.win;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int lane_f = blockIdx.x * kWalkThreads + tid;
+  const int lane_f = bx * kWalkThreads + tid;
   const int f = w.f0 + lane_f;
   const bool active = f < w.f1;
-  const int srow0 = w.s0 + blockIdx.y * ROWS;
+  const int srow0 = w.s0 + by * ROWS;
   const int nrows = min(ROWS, w.s1 - srow0);
   if (tid < nrows) saxis[tid] = __ldg(w.slow_axis + srow0 + tid);
   __syncthreads();
@@ -601,10 +629,11 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
       const bool o1 = x1 < margin, o2 = x2 < margin, o3 = x3 < margin;
       const bool outside = o1 | o2 | o3;
       int nxt = o1 ? n3 : (o2 ? n1 : n2);
-      if (outside && nxt == kNotPacked) nxt = packed_alternative(o1, o2, o3, n1, n2, n3);
+      // (BP: the pack was band-limited, links may lead to triangles without a record)
+      if (BP && outside && nxt == kNotPacked) nxt = packed_alternative(o1, o2, o3, n1, n2, n3);
       if (outside && nxt >= 0 && !forced_out) {
         if (it < a.iter_cap) {
-          if (careful && (int)o1 + (int)o2 + (int)o3 > 1) {   // rare: see farthest_failing_edge
+          if (careful && ((o1 && o2) || (o3 && (o1 || o2)))) {   // long triangle, more than one edge fails (rare)
             const int res = careful_locate(a.geom, tri, FY ? cv : cf, FY ? cf : cv, a.iter_cap, a.status);
             forced_out = res < 0;   // a failing hull edge was seen: outside, whichever edge fails first there
             nxt = forced_out ? ~res : res;
@@ -615,7 +644,7 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
         raise_status(a.status, GI_ERR_ITER_CAP);
       }
       forced_out = false;
-      if (outside && nxt == kNotPacked) raise_status(a.status, GI_ERR_PACK_WINDOW);  // band-limited pack too tight
+      if (BP && outside && nxt == kNotPacked) raise_status(a.status, GI_ERR_PACK_WINDOW);  // band-limited pack too tight
       // resolved: inside `tri`, or outside the hull (:74-80: the last valid triangle is kept).
       // A target within the margin band of an edge is accepted by both adjacent triangles and which one the
       // reference returns depends on its walk path: flag it for fixup_kernel.
@@ -641,6 +670,27 @@ __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const W
   // one atomic per warp for the iteration counter (iters_tot, interpolation.f90:374)
   for (int off = 16; off > 0; off >>= 1) iters_sum += __shfl_down_sync(0xffffffffu, iters_sum, off);
   if (lane == 0 && iters_sum) atomicAdd((unsigned long long*)a.counters, (unsigned long long)iters_sum);
+}
+
+template <class R, bool FY, bool PEERS, int ROWS, int MINB, bool BP>
+__global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const WalkArgs<R> a) {
+  __shared__ int stri[ROWS][kWalkThreads];
+  __shared__ R saxis[ROWS];
+  locate_eval_tile<R, FY, PEERS, ROWS, BP>(a, blockIdx.x, blockIdx.y, stri, saxis);
+}
+
+// The same as a stand-by for the rasteriser (raster.cuh): a small grid that returns at once unless the device
+// flag says the rasteriser could not do the window (an empty launch of the full grid costs 37 us at C4 size), and
+// then loops over the strips.
+template <class R, bool FY, bool PEERS, int ROWS>
+__global__ void __launch_bounds__(kWalkThreads) locate_eval_standby_kernel(const WalkArgs<R> a, int nbx, int nby) {
+  __shared__ int stri[ROWS][kWalkThreads];
+  __shared__ R saxis[ROWS];
+  if (!*a.only_if) return;
+  for (int t = blockIdx.x; t < nbx * nby; t += gridDim.x) {
+    locate_eval_tile<R, FY, PEERS, ROWS, true>(a, t % nbx, t / nbx, stri, saxis);
+    __syncthreads();
+  }
 }
 
 
@@ -1076,7 +1126,19 @@ template <class R> struct PackedMesh {
   int ncx, ncy, num_tri;
   RawMesh<R> raw;  // raw.use = 1: only the triangles near the row window have records
   const uint8_t* need;  // band-limited pack: which triangles have records (nullptr: all)
+  TileBins bins;        // rasteriser: tile lists of the rows [bin_e0, bin_e1) (start == nullptr: none)
+  int bin_e0, bin_e1;
 };
+
+// Rasteriser or walk?  Measured on C4 (profiles/r02_raster_*): the rasteriser needs 3.4 ms where the walk needs
+// 3.1 -- testing every node of every bounding box (2.4 tests per target at 20 of 32 lanes) costs more instructions
+// than the walk's 1.6 iterations per target -- so the walk stays the default and GI_BARY_RASTER=1 selects the
+// rasteriser (the whole GPU test suite passes either way).
+template <class R> bool use_raster(int num_tri, int64_t nodes) {
+  static const int forced = getenv("GI_BARY_RASTER") ? atoi(getenv("GI_BARY_RASTER")) : 0;
+  (void)num_tri; (void)nodes;
+  return forced != 0;
+}
 
 // rows [w0, w1) +- this many rows are packed by a band-limited pack (GI_BARY_BAND_PACK)
 constexpr int kPackMarginRows = 48;
@@ -1108,24 +1170,26 @@ int bary_pack(Scratch& scr, const R* points, int num_points, const R* data_in, c
     pm->raw.use = 1;
   }
   pm->need = need;
-  pack_mesh_kernel<R><<<div_up(num_tri, 256), 256, 0, st>>>(
+  // rasteriser: the tile lists of the walked rows [w0, w1) are counted by the pack pass
+  pm->bins = TileBins{};
+  pm->bin_e0 = w0; pm->bin_e1 = w1;
+  TargetWindow<R> bw{};
+  int n_threads = num_tri;
+  if (w0 < w1 && use_raster<R>(num_tri, (int64_t)len_x * (w1 - w0))) {
+    bw = (flags & GI_FIELD_ROWMAJOR) ? TargetWindow<R>{x_axis, y_axis, len_x, len_y, 0, len_x, w0, w1, 0}
+                                     : TargetWindow<R>{y_axis, x_axis, len_y, len_x, w0, w1, 0, len_x, 1};
+    GI_TRY(alloc_tile_bins<R>(scr, num_tri, bw, &pm->bins));
+    n_threads = std::max(num_tri, std::max(len_x, len_y));
+  }
+  pack_mesh_kernel<R><<<div_up(n_threads, 256), 256, 0, st>>>(
       pv, data_in, sv, topo_t3(neighbours, num_tri, flags & GI_TOPO_ROWMAJOR),
-      num_points, num_tri, pm->geom, pm->seed, x_axis, len_x, y_axis, len_y, need, status);
+      num_points, num_tri, pm->geom, pm->seed, x_axis, len_x, y_axis, len_y, need, bw, pm->bins, status);
   GI_CUDA(cudaGetLastError());
+  if (pm->bins.start) GI_TRY(finish_tile_bins(scr, num_tri, pm->bins));
   return GI_OK;
 }
 
 // 2. + 2b. locate / evaluate / fix-up over the window wa.win (mask words, work list and counters as set in wa)
-// Rasteriser or walk?  The rasteriser pays two binning passes and tests every node of a triangle's bounding box: it
-// wins where a triangle covers a handful to a few hundred grid nodes and there are enough triangles to fill the
-// GPU; coarse meshes under fine grids (no moves to make) and small calls (launch-bound) keep the walk.
-// GI_BARY_RASTER=0 / 1 forces the choice (tests).
-template <class R> bool use_raster(int num_tri, int64_t nodes) {
-  static const int forced = getenv("GI_BARY_RASTER") ? atoi(getenv("GI_BARY_RASTER")) : -1;
-  if (forced >= 0) return forced != 0;
-  return sizeof(R) == 8 && num_tri >= 4096 && nodes >= (int64_t)num_tri && nodes <= (int64_t)512 * num_tri;
-}
-
 template <class R>
 int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis, const R* y_axis, int len_x, int len_y,
               int num_points, cudaStream_t st, const TileBins* bins = nullptr, int tile_row0 = 0) {
@@ -1146,11 +1210,24 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
     else raster_eval_kernel<R, true, true><<<grid, kWalkThreads, 0, st>>>(wa, *bins, tile_row0);
     GI_CUDA(cudaGetLastError());
     wa.only_if = bins->bad;  // descending axes / list overflow: the walk kernel does the window after all
+    const int g = std::min<int64_t>((int64_t)grid.x * grid.y, kNumSMs * 8);
+    if (!fy && !peers) locate_eval_standby_kernel<R, false, false, kRows><<<g, kWalkThreads, 0, st>>>(wa, grid.x, grid.y);
+    else if (fy && !peers) locate_eval_standby_kernel<R, true, false, kRows><<<g, kWalkThreads, 0, st>>>(wa, grid.x, grid.y);
+    else if (!fy) locate_eval_standby_kernel<R, false, true, kRows><<<g, kWalkThreads, 0, st>>>(wa, grid.x, grid.y);
+    else locate_eval_standby_kernel<R, true, true, kRows><<<g, kWalkThreads, 0, st>>>(wa, grid.x, grid.y);
+  } else {
+    const bool bp = pm.need != nullptr;  // band-limited pack: links may lead to triangles without a record
+#define GI_LAUNCH_WALK(FY_, PEERS_)                                                                     \
+  do {                                                                                                  \
+    if (bp) locate_eval_kernel<R, FY_, PEERS_, kRows, 8, true><<<grid, kWalkThreads, 0, st>>>(wa);      \
+    else locate_eval_kernel<R, FY_, PEERS_, kRows, 8, false><<<grid, kWalkThreads, 0, st>>>(wa);        \
+  } while (0)
+    if (!fy && !peers) GI_LAUNCH_WALK(false, false);
+    else if (fy && !peers) GI_LAUNCH_WALK(true, false);
+    else if (!fy) GI_LAUNCH_WALK(false, true);
+    else GI_LAUNCH_WALK(true, true);
+#undef GI_LAUNCH_WALK
   }
-  if (!fy && !peers) locate_eval_kernel<R, false, false, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
-  else if (fy && !peers) locate_eval_kernel<R, true, false, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
-  else if (!fy) locate_eval_kernel<R, false, true, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
-  else locate_eval_kernel<R, true, true, kRows, 8><<<grid, kWalkThreads, 0, st>>>(wa);
   GI_CUDA(cudaGetLastError());
   // targets inside the margin band of an edge: follow the reference's own path (normally none)
   const int n_search = std::min(num_points, pm.num_tri);  // the reference searches triangles 1..num_points (:347)
@@ -1226,14 +1303,8 @@ int bary_run_window(Scratch& scr, const PackedMesh<R>& pm, const R* x_axis, int 
   wa.n_peer = dest ? dest->n_peer : 0;
   for (int d = 0; d < wa.n_peer; ++d) wa.peer_out[d] = dest->peer[d];
   wa.status = slot.dev;
-  TileBins bins;
-  const bool raster = use_raster<R>(num_tri, (int64_t)nf * ns);
-  if (raster) {
-    ph->mark("bin");
-    GI_TRY(build_tile_bins<R>(scr, pm.geom, pm.need, num_tri, wa.win, &bins));
-    ph->mark("walk");
-  }
-  GI_TRY(bary_walk<R>(wa, pm, x_axis, y_axis, len_x, len_y, num_points, st, raster ? &bins : nullptr, 0));
+  const bool raster = pm.bins.start && pm.bin_e0 == e0 && pm.bin_e1 == e1;
+  GI_TRY(bary_walk<R>(wa, pm, x_axis, y_axis, len_x, len_y, num_points, st, raster ? &pm.bins : nullptr, 0));
   if (mask_out || fill_src) {
     expand_mask_kernel<<<kNumSMs * 8, 256, 0, st>>>(mask_words, wpr, wa.win.f0, wa.win.s0, wa.bf0, wa.bf1, wa.bs0,
                                                    wa.bs1, mask_out, fill_src);
@@ -1362,14 +1433,9 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
   GI_TRY(scr.alloc(&row_todo, (size_t)len_y));
   GI_CUDA(cudaMemsetAsync(row_todo, 0, sizeof(int) * (size_t)len_y, st));
 
-  // tile lists of the whole walked window, once: the sub-bands below start at whole tile rows
-  TileBins bins;
-  const bool raster = use_raster<R>(num_tri, (int64_t)nfast * nslow);
-  if (raster) {
-    const TargetWindow<R> we = rowmajor ? TargetWindow<R>{dx, dy, len_x, len_y, ef0, ef1, es0, es1, 0}
-                                        : TargetWindow<R>{dy, dx, len_y, len_x, ef0, ef1, es0, es1, 1};
-    GI_TRY(build_tile_bins<R>(scr, pm.geom, pm.need, num_tri, we, &bins));
-  }
+  // tile lists of the whole walked window (from the pack pass): the sub-bands below start at whole tile rows
+  const bool raster = pm.bins.start && pm.bin_e0 == e0 && pm.bin_e1 == e1;
+  const TileBins& bins = pm.bins;
 
   int nb = plan_bands(nslow, (int64_t)(row_end - row_begin) * len_x * sizeof(R));
   for (;;) {
@@ -1580,7 +1646,7 @@ int barycentric_plan_create(const R* points, int num_points, const R* x_axis, in
     dp = t; dn = tn;
   }
   GI_TRY(bary_pack<R>(plan->keep, dp, num_points, zeros, plan->dx, len_x, plan->dy, len_y, plan->simp, dn, num_tri,
-                      flags, slot.dev, &plan->pm));
+                      flags, slot.dev, &plan->pm, std::max(0, row_begin - halo), std::min(len_y, row_end + halo)));
   GI_TRY(flush_status(st, slot));
   const int status = read_status(st, true);  // invalid ids are reported at creation
   if (status != GI_OK) return status;

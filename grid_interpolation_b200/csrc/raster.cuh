@@ -5,8 +5,9 @@
 // (triangle_walk.f90:140-153); outside the margin band of an edge that triangle is unique and does not depend on
 // the walk, so it can be found from the triangle's side instead of the target's:
 //
-//   bin_tiles_kernel    (two passes: count, fill) every packed triangle is entered in the list of each
-//                       128 x 32-target tile its bounding box meets; bounds come from the axes themselves
+//   pack_mesh_kernel +  (two passes: count -- part of the pack pass, which has the vertices in registers --
+//   bin_fill_kernel     and fill) every packed triangle is entered in the list of each 128 x 32-target tile its
+//                       bounding box meets; bounds come from the axes themselves
 //                       (searched, not assumed uniform), inflated by the reach of the -1e-10 margin.
 //   raster_eval_kernel  one CTA per tile.  Phase A: one thread per listed triangle tests the grid nodes of its
 //                       (tile-clipped) bounding box with the reference's orientation expression -- same operations,
@@ -19,17 +20,6 @@
 //
 // The rasteriser needs ascending axes and a tile list that fits its buffer; both are checked on the device
 // (TileBins::bad) and the walk kernel runs instead when the flag is raised.
-
-constexpr int kTileW = kWalkThreads;  // fast-axis nodes per tile
-constexpr int kTileH = 32;            // slow-axis nodes per tile
-
-struct TileBins {
-  int* start;  // [ntx*nty + 1] exclusive offsets into list
-  int* fill;   // [ntx*nty] fill cursors (zeroed between the passes)
-  int* list;   // [cap] triangle ids, tile by tile
-  int* bad;    // device flag: != 0 -> axes not ascending or list overflow: the walk kernel takes over
-  int ntx, nty, cap;
-};
 
 // min / max by compare-and-select (fmin / fmax on doubles expand to ~7 instructions of NaN handling each)
 template <class R> __device__ __forceinline__ R rmin(R a, R b) { return a < b ? a : b; }
@@ -102,22 +92,10 @@ __device__ __forceinline__ void tri_bounds(const TriGeom<R>& g, bool fy, R& flo,
   slo = (fy ? xmin : ymin) - d; shi = (fy ? xmax : ymax) + d;
 }
 
-// Tile lists.  FILL = false: count the tiles' entries (and check the axes); FILL = true: write them.
-template <class R, bool FILL>
-__global__ void __launch_bounds__(256)
-bin_tiles_kernel(const TriGeom<R>* __restrict__ geom, const uint8_t* __restrict__ need, int num_tri,
-                 const TargetWindow<R> w, const TileBins b) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (!FILL) {  // ascending, finite axes?
-    if (t + 1 < w.nf_full && !(__ldg(w.fast_axis + t) <= __ldg(w.fast_axis + t + 1))) *b.bad = 1;
-    if (t + 1 < w.ns_full && !(__ldg(w.slow_axis + t) <= __ldg(w.slow_axis + t + 1))) *b.bad = 1;
-    if (t == 0 && !(fabs(__ldg(w.fast_axis)) < Inf<R>::v() && fabs(__ldg(w.fast_axis + w.nf_full - 1)) < Inf<R>::v() &&
-                    fabs(__ldg(w.slow_axis)) < Inf<R>::v() && fabs(__ldg(w.slow_axis + w.ns_full - 1)) < Inf<R>::v()))
-      *b.bad = 1;
-  }
-  if (t >= num_tri || (need && !need[t])) return;
-  TriGeom<R> g;
-  load_walk(geom + t, g);
+// Inclusive range of the tiles of window `w` holding nodes inside the triangle's bounds; false if there are none.
+template <class R>
+__device__ __forceinline__ bool tri_tile_range(const TriGeom<R>& g, const TargetWindow<R>& w, int& tx0, int& tx1, int& ty0,
+                                               int& ty1) {
   R flo, fhi, slo, shi;
   tri_bounds(g, w.fast_is_y != 0, flo, fhi, slo, shi);
   const int nf = w.nf(), ns = w.ns();
@@ -131,20 +109,36 @@ bin_tiles_kernel(const TriGeom<R>* __restrict__ geom, const uint8_t* __restrict_
   // nodes [c0, c1] x [r0, r1] of the window lie inside the bounds
   const int c0 = bound_from<false>(fax, nf, flo, guess_index(flo, f_first, inv_f, nf));
   const int c1 = bound_from<true>(fax, nf, fhi, guess_index(fhi, f_first, inv_f, nf) + 1) - 1;
-  if (c0 > c1) return;
+  if (c0 > c1) return false;
   const int r0 = bound_from<false>(sax, ns, slo, guess_index(slo, s_first, inv_s, ns));
   const int r1 = bound_from<true>(sax, ns, shi, guess_index(shi, s_first, inv_s, ns) + 1) - 1;
-  if (r0 > r1) return;
-  for (int ty = r0 / kTileH; ty <= r1 / kTileH; ++ty)
-    for (int tx = c0 / kTileW; tx <= c1 / kTileW; ++tx) {
+  if (r0 > r1) return false;
+  tx0 = c0 / kTileW; tx1 = c1 / kTileW; ty0 = r0 / kTileH; ty1 = r1 / kTileH;
+  return true;
+}
+
+// Ascending, finite axes?  (thread t looks at nodes t, t + 1 of both axes; part of the pack pass)
+template <class R> __device__ __forceinline__ void check_axes(const TargetWindow<R>& w, int t, int* bad) {
+  if (t + 1 < w.nf_full && !(__ldg(w.fast_axis + t) <= __ldg(w.fast_axis + t + 1))) *bad = 1;
+  if (t + 1 < w.ns_full && !(__ldg(w.slow_axis + t) <= __ldg(w.slow_axis + t + 1))) *bad = 1;
+  if (t == 0 && !(fabs(__ldg(w.fast_axis)) < Inf<R>::v() && fabs(__ldg(w.fast_axis + w.nf_full - 1)) < Inf<R>::v() &&
+                  fabs(__ldg(w.slow_axis)) < Inf<R>::v() && fabs(__ldg(w.slow_axis + w.ns_full - 1)) < Inf<R>::v()))
+    *bad = 1;
+}
+
+// Second binning pass (the first, counting, is part of pack_mesh_kernel): every triangle enters the lists of its
+// tiles.  The order inside a list is whatever the atomics make it; nothing depends on it.
+__global__ void __launch_bounds__(256) bin_fill_kernel(int num_tri, const TileBins b) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_tri) return;
+  const uint2 rg = b.range[t];
+  const int tx0 = rg.x & 0xffff, tx1 = rg.x >> 16, ty0 = rg.y & 0xffff, ty1 = rg.y >> 16;
+  for (int ty = ty0; ty <= ty1; ++ty)
+    for (int tx = tx0; tx <= tx1; ++tx) {
       const int tile = ty * b.ntx + tx;
-      if (!FILL) {
-        atomicAdd(b.start + tile, 1);
-      } else {
-        const int pos = __ldg(b.start + tile) + atomicAdd(b.fill + tile, 1);
-        if (pos < b.cap) b.list[pos] = t;
-        else *b.bad = 1;
-      }
+      const int pos = __ldg(b.start + tile) + atomicAdd(b.fill + tile, 1);
+      if (pos < b.cap) b.list[pos] = t;
+      else *b.bad = 1;
     }
 }
 
@@ -156,10 +150,14 @@ bin_tiles_kernel(const TriGeom<R>* __restrict__ geom, const uint8_t* __restrict_
 // the reference's own rounding) + 1e-10 (the shift) + 32 eps M Q, where M bounds |ex| + |ey| of the edges and Q the
 // local coordinates that enter the expression (the error of the two FMAs and of C_i is below 10 eps M Q).
 constexpr int kRasterChunk = 384;   // triangles of a tile processed per pass (a C4 tile lists ~210)
+#ifndef GI_RASTER_MINB
+#define GI_RASTER_MINB 8
+#endif
+constexpr int kRasterMinBlocks = GI_RASTER_MINB;
 constexpr int kRasterBuckets = 64;  // size classes of the per-tile counting sort
 
 template <class R, bool FY, bool PEERS>
-__global__ void __launch_bounds__(kWalkThreads, 6)
+__global__ void __launch_bounds__(kWalkThreads, kRasterMinBlocks)
 raster_eval_kernel(const WalkArgs<R> a, const TileBins b, int tile_row0) {
   __shared__ __align__(16) int stri[kTileH][kWalkThreads];
   __shared__ R sfast[kTileW];
@@ -315,31 +313,33 @@ raster_eval_kernel(const WalkArgs<R> a, const TileBins b, int tile_row0) {
   if ((tid & 31) == 0 && tests) atomicAdd((unsigned long long*)a.counters, (unsigned long long)tests);
 }
 
-// Build the tile lists of window `w` (whole tiles from its origin) on the packed mesh.
+// Tile lists of window `w` (whole tiles from its origin): buffers for the pack pass to count into ...
 template <class R>
-int build_tile_bins(Scratch& scr, const TriGeom<R>* geom, const uint8_t* need, int num_tri, const TargetWindow<R>& w,
-                    TileBins* bins) {
+int alloc_tile_bins(Scratch& scr, int num_tri, const TargetWindow<R>& w, TileBins* bins) {
   cudaStream_t st = scr.stream();
   TileBins b;
   b.ntx = div_up(w.nf(), kTileW);
   b.nty = div_up(w.ns(), kTileH);
   const int64_t ntiles = (int64_t)b.ntx * b.nty;
   const int64_t cap = 2 * (int64_t)num_tri + 4 * ntiles + 1024;
-  GI_REQUIRE(cap < (int64_t)0x7fffffff && ntiles < (int64_t)0x7ffffff0, "tile lists too large");
+  GI_REQUIRE(cap < (int64_t)0x7fffffff && b.ntx < 65536 && b.nty < 65536, "tile lists too large");
   b.cap = (int)cap;
   GI_TRY(scr.alloc(&b.start, (size_t)ntiles + 1));
   GI_TRY(scr.alloc(&b.fill, (size_t)ntiles + 1));
   GI_TRY(scr.alloc(&b.list, (size_t)cap));
   GI_TRY(scr.alloc(&b.bad, 1));
+  GI_TRY(scr.alloc(&b.range, (size_t)num_tri));
   GI_CUDA(cudaMemsetAsync(b.start, 0, sizeof(int) * ((size_t)ntiles + 1), st));
   GI_CUDA(cudaMemsetAsync(b.fill, 0, sizeof(int) * ((size_t)ntiles + 1), st));
   GI_CUDA(cudaMemsetAsync(b.bad, 0, sizeof(int), st));
-  const int n_threads = std::max(num_tri, std::max(w.nf_full, w.ns_full));
-  bin_tiles_kernel<R, false><<<div_up(n_threads, 256), 256, 0, st>>>(geom, need, num_tri, w, b);
-  GI_CUDA(cudaGetLastError());
-  GI_TRY(exclusive_scan_i32(scr, b.start, b.start, ntiles + 1));
-  bin_tiles_kernel<R, true><<<div_up(num_tri, 256), 256, 0, st>>>(geom, need, num_tri, w, b);
-  GI_CUDA(cudaGetLastError());
   *bins = b;
+  return GI_OK;
+}
+// ... and, after the pack pass: offsets, then the lists
+inline int finish_tile_bins(Scratch& scr, int num_tri, const TileBins& b) {
+  cudaStream_t st = scr.stream();
+  GI_TRY(exclusive_scan_i32(scr, b.start, b.start, (int64_t)b.ntx * b.nty + 1));
+  bin_fill_kernel<<<div_up(num_tri, 256), 256, 0, st>>>(num_tri, b);
+  GI_CUDA(cudaGetLastError());
   return GI_OK;
 }
