@@ -179,7 +179,7 @@ need_kernel(PointsView<R> pts, TopoView simp, int num_points, int num_tri, const
   need[t] = (fmax(fmax(ya, yb), yc) >= y_lo && fmin(fmin(ya, yb), yc) <= y_hi) ? 1 : 0;
 }
 
-template <class R>
+template <class R, bool BINS>
 __global__ void __launch_bounds__(256)
 pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, TopoView nbr, int num_points,
                  int num_tri, TriGeom<R>* __restrict__ geom, int* __restrict__ seed,
@@ -188,7 +188,7 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
                  int* __restrict__ status) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool packed = t < num_tri && (!need || need[t]);
-  if (bb.start) {  // rasteriser (raster.cuh): axes usable?  A triangle without a record is in no tile.
+  if (BINS) {  // rasteriser (raster.cuh): axes usable?  A triangle without a record is in no tile.
     check_axes(bw, t, bb.bad);
     if (t < num_tri && !packed) bb.range[t] = make_uint2(1u, 1u);  // tx0 = 1 > tx1 = 0: empty
   }
@@ -231,7 +231,7 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
   g.denom = g.A * g.D + g.B * (g.y1 - g.y3);                                     // :385-386
   g.d1 = __ldg(data + (a - 1)); g.d2 = __ldg(data + (b - 1)); g.d3 = __ldg(data + (c - 1));
   geom[t] = g;
-  if (bb.start) {  // first binning pass: count this triangle in the tiles its bounds meet
+  if (BINS) {  // first binning pass: count this triangle in the tiles its bounds meet
     int tx0 = 1, tx1 = 0, ty0 = 1, ty1 = 0;
     if (!bad && tri_tile_range(g, bw, tx0, tx1, ty0, ty1))
       for (int ty = ty0; ty <= ty1; ++ty)
@@ -1181,9 +1181,15 @@ int bary_pack(Scratch& scr, const R* points, int num_points, const R* data_in, c
     GI_TRY(alloc_tile_bins<R>(scr, num_tri, bw, &pm->bins));
     n_threads = std::max(num_tri, std::max(len_x, len_y));
   }
-  pack_mesh_kernel<R><<<div_up(n_threads, 256), 256, 0, st>>>(
-      pv, data_in, sv, topo_t3(neighbours, num_tri, flags & GI_TOPO_ROWMAJOR),
-      num_points, num_tri, pm->geom, pm->seed, x_axis, len_x, y_axis, len_y, need, bw, pm->bins, status);
+  const TopoView nv = topo_t3(neighbours, num_tri, flags & GI_TOPO_ROWMAJOR);
+  if (pm->bins.start)
+    pack_mesh_kernel<R, true><<<div_up(n_threads, 256), 256, 0, st>>>(pv, data_in, sv, nv, num_points, num_tri, pm->geom,
+                                                                     pm->seed, x_axis, len_x, y_axis, len_y, need, bw,
+                                                                     pm->bins, status);
+  else
+    pack_mesh_kernel<R, false><<<div_up(n_threads, 256), 256, 0, st>>>(pv, data_in, sv, nv, num_points, num_tri, pm->geom,
+                                                                      pm->seed, x_axis, len_x, y_axis, len_y, need, bw,
+                                                                      pm->bins, status);
   GI_CUDA(cudaGetLastError());
   if (pm->bins.start) GI_TRY(finish_tile_bins(scr, num_tri, pm->bins));
   return GI_OK;

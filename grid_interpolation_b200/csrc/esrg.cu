@@ -142,6 +142,9 @@ template <class R> struct EsrgArgs {
   int64_t* todo_count;
   int all_exact;          // debug: the fast kernel hands every target over
   int stats;              // update counters[0..2] (debug: one atomic per target)
+  R* tk_d;                // k > 32: neighbour lists in scratch memory (topk.cuh, KC = 0), k x tk_stride
+  int* tk_id;
+  int64_t tk_stride;
 };
 
 // Smallest level L >= from whose radius is not exceeded by d2, i.e. the first level at which the reference accepts
@@ -173,6 +176,7 @@ __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
   const R cy = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
 
   TopK<R, KC> tk;
+  if constexpr (KC == 0) tk.bind(a.tk_d, a.tk_id, a.tk_stride, blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
   tk.init(a.k, Consts<R>::huge(), -1);                                    // :129-130
   int found = 0;
 
@@ -276,18 +280,21 @@ __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
   // IDW (interpolation.f90:260-274): distances are square-rooted first (query_esrg.f90:247)
   const int64_t o = (int64_t)(s - w.s0) * w.nf() + (f - w.f0);
   R numerator = R(0), denominator = R(0), first_val = R(0), first_dist = R(0);
+  auto take = [&](int rank, int pos, R d2r) {
+    const R dist = sqrt(d2r);
+    const R v = pos >= 0 ? __ldg(a.sval + pos) : R(0);
+    if (rank == 0) { first_val = v; first_dist = dist; }
+    numerator = numerator + (v / dist);
+    denominator = denominator + (R(1) / dist);
+    if (a.nn_index) a.nn_index[o * a.k + rank] = pos >= 0 ? __ldg(a.sid + pos) : -1;
+    if (a.nn_dist2) a.nn_dist2[o * a.k + rank] = d2r;
+  };
+  if constexpr (KC == 0) {
+    for (int j = 0; j < a.k; ++j) take(j, tk.index(j), tk.dist2(j));
+  } else {
 #pragma unroll
-  for (int j = 0; j < KC; ++j) {
-    if (j >= tk.base) {  // rank j - tk.base of the list (topk.cuh)
-      const int pos = tk.id[j];
-      const R dist = sqrt(tk.d[j]);
-      const R v = pos >= 0 ? __ldg(a.sval + pos) : R(0);
-      if (j == tk.base) { first_val = v; first_dist = dist; }
-      numerator = numerator + (v / dist);
-      denominator = denominator + (R(1) / dist);
-      if (a.nn_index) a.nn_index[o * a.k + (j - tk.base)] = pos >= 0 ? __ldg(a.sid + pos) : -1;
-      if (a.nn_dist2) a.nn_dist2[o * a.k + (j - tk.base)] = tk.d[j];
-    }
+    for (int j = 0; j < KC; ++j)
+      if (j >= tk.base) take(j - tk.base, tk.id[j], tk.d[j]);  // rank j - tk.base of the list (topk.cuh)
   }
   a.out[o] = (first_dist <= Consts<R>::tiny_e4()) ? first_val : numerator / denominator;
 
@@ -731,7 +738,8 @@ int esrg_query_window(Scratch& scr, const Binned<R>& b, int num_points, const R*
   GI_REQUIRE(ntargets < (int64_t)0x7fffffff, "window has more than 2^31 targets");
   GI_TRY(scr.alloc(&a.todo, (size_t)ntargets));
   a.todo_count = counters + 3;
-  a.all_exact = (flags & GI_ESRG_REFERENCE_ORDER) ? 1 : 0;
+  a.all_exact = ((flags & GI_ESRG_REFERENCE_ORDER) || k > 32) ? 1 : 0;  // k > 32: only the exact kernel has the any-k list
+  a.tk_d = nullptr; a.tk_id = nullptr; a.tk_stride = 0;
   // first halo level: where the mean point density puts about 1.5k+6 points within r_H = spac*(H+1/2), so
   // that all 32 lanes of a tile find k of them in the first pass with high probability (Poisson tail)
   const double density = (double)num_points / ((double)len_x * (double)len_y);
@@ -753,7 +761,13 @@ int esrg_query_window(Scratch& scr, const Binned<R>& b, int num_points, const R*
   if (k <= 4) esrg_query_kernel<R, 4><<<eg, 128, 0, st>>>(a);
   else if (k <= 8) esrg_query_kernel<R, 8><<<eg, 128, 0, st>>>(a);
   else if (k <= 16) esrg_query_kernel<R, 16><<<eg, 128, 0, st>>>(a);
-  else esrg_query_kernel<R, 32><<<eg, 128, 0, st>>>(a);
+  else if (k <= 32) esrg_query_kernel<R, 32><<<eg, 128, 0, st>>>(a);
+  else {  // any k: the lists live in scratch memory (topk.cuh, KC = 0), one per thread of the grid-stride loop
+    a.tk_stride = (int64_t)eg * 128;
+    GI_TRY(scr.alloc(&a.tk_d, (size_t)a.tk_stride * k));
+    GI_TRY(scr.alloc(&a.tk_id, (size_t)a.tk_stride * k));
+    esrg_query_kernel<R, 0><<<eg, 128, 0, st>>>(a);
+  }
   GI_CUDA(cudaGetLastError());
   return GI_OK;
 }
@@ -764,7 +778,7 @@ template <class R>
 int esrg_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
                 int len_y, R grid_spac, int k, int row_begin, int row_end, R* data_ip, int32_t* nn_index,
                 R* nn_dist2, int64_t* counters_out, int flags, cudaStream_t st) {
-  GI_REQUIRE(k >= 1 && k <= 32, "num_neighbours must be in 1..32");
+  GI_REQUIRE(k >= 1, "num_neighbours must be at least 1");
   GI_REQUIRE(num_points >= k, "fewer points than num_neighbours");
   GI_TRY(ensure_device());
   if (row_begin == row_end) return GI_OK;
@@ -834,7 +848,7 @@ int esrg_run_banded(HostPipe* pipe, Scratch& scr, const Binned<R>& bins, int num
 template <class R>
 int esrg_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
               int len_y, R grid_spac, int k, int row_begin, int row_end, R* data_ip, int flags) {
-  GI_REQUIRE(k >= 1 && k <= 32, "num_neighbours must be in 1..32");
+  GI_REQUIRE(k >= 1, "num_neighbours must be at least 1");
   GI_REQUIRE(num_points >= k, "fewer points than num_neighbours");
   GI_TRY(ensure_device());
   if (row_begin == row_end) return GI_OK;
@@ -919,7 +933,7 @@ template <class R>
 int esrg_plan_create(const R* points, int num_points, const R* x_axis, int len_x, const R* y_axis, int len_y,
                      R grid_spac, int k, int row_begin, int row_end, int flags, int mem, cudaStream_t st_in,
                      PlanBase** out) {
-  GI_REQUIRE(k >= 1 && k <= 32, "num_neighbours must be in 1..32");
+  GI_REQUIRE(k >= 1, "num_neighbours must be at least 1");
   GI_REQUIRE(num_points >= k, "fewer points than num_neighbours");
   GI_TRY(ensure_device());
   cudaStream_t st = st_in;

@@ -413,6 +413,9 @@ template <class R> struct KdArgs {
   R* nn_dist2;         // optional
   int64_t* counters;   // [0] node visits
   int* status;
+  R* tk_d;             // k > 32: neighbour lists in scratch memory (topk.cuh, KC = 0), k x tk_stride
+  int* tk_id;
+  int64_t tk_stride;
 };
 
 template <class R> struct alignas(16) StackEntry {
@@ -467,6 +470,8 @@ __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
     const R tx = __ldg((w.fast_is_y ? w.slow_axis : w.fast_axis) + ix);   // interpolation.f90:158
     const R ty = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
     TopK<R, KC> tk;
+    if constexpr (KC == 0)
+      tk.bind(a.tk_d, a.tk_id, a.tk_stride, ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x);
     tk.init(a.k, Consts<R>::sentinel(), -1);                              // :159
     // Deferred far branches, at most one per tree level.  Measured alternatives (profiles/r01_kd_esrg_variants.md):
     // top entry kept in registers +16 %, 48 registers for 10 CTAs/SM +8 % (spills), two entries per back-up
@@ -512,18 +517,21 @@ __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
     // IDW (interpolation.f90:164-178); rank i of the list lives in slot tk.base + i
     const int64_t o = (int64_t)(s - w.s0) * w.nf() + (f - w.f0);
     R numerator = R(0), denominator = R(0), first_val = R(0), first_d2 = R(0);
+    auto take = [&](int rank, int pos, R d2r) {
+      const R dist = sqrt(d2r);
+      const R v = pos >= 0 ? __ldg(a.nval + pos) : R(0);  // unfilled slot: uninitialised read in the reference
+      if (rank == 0) { first_val = v; first_d2 = d2r; }
+      numerator = numerator + (v / dist);
+      denominator = denominator + (R(1) / dist);
+      if (a.nn_index) a.nn_index[o * a.k + rank] = pos >= 0 ? __ldg(a.order + pos) + 1 : 0;
+      if (a.nn_dist2) a.nn_dist2[o * a.k + rank] = d2r;
+    };
+    if constexpr (KC == 0) {
+      for (int j = 0; j < a.k; ++j) take(j, tk.index(j), tk.dist2(j));
+    } else {
 #pragma unroll
-    for (int j = 0; j < KC; ++j) {
-      if (j >= tk.base) {
-        const int pos = tk.id[j];
-        const R dist = sqrt(tk.d[j]);
-        const R v = pos >= 0 ? __ldg(a.nval + pos) : R(0);  // unfilled slot: uninitialised read in the reference
-        if (j == tk.base) { first_val = v; first_d2 = tk.d[j]; }
-        numerator = numerator + (v / dist);
-        denominator = denominator + (R(1) / dist);
-        if (a.nn_index) a.nn_index[o * a.k + (j - tk.base)] = pos >= 0 ? __ldg(a.order + pos) + 1 : 0;
-        if (a.nn_dist2) a.nn_dist2[o * a.k + (j - tk.base)] = tk.d[j];
-      }
+      for (int j = 0; j < KC; ++j)
+        if (j >= tk.base) take(j - tk.base, tk.id[j], tk.d[j]);
     }
     a.out[o] = (sqrt(first_d2) <= Consts<R>::tiny_e4()) ? first_val : numerator / denominator;
   }
@@ -585,10 +593,33 @@ int kd_query_window(const KdTreeDev<R>& t, const R* x_axis, int len_x, const R* 
   dim3 grid(div_up(a.win.nf(), 32), div_up(a.win.ns(), 4));
   GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
   const int prune = (flags & GI_KD_EXACT_PRUNE) ? 2 : ((flags & GI_KD_REFERENCE_VISITS) ? 1 : 0);
+  a.tk_d = nullptr; a.tk_id = nullptr; a.tk_stride = 0;
   if (k <= 4) launch_query<R, 4>(a, prune, grid, st);
   else if (k <= 8) launch_query<R, 8>(a, prune, grid, st);
   else if (k <= 16) launch_query<R, 16>(a, prune, grid, st);
-  else launch_query<R, 32>(a, prune, grid, st);
+  else if (k <= 32) launch_query<R, 32>(a, prune, grid, st);
+  else {
+    // any k: the lists live in scratch memory (topk.cuh, KC = 0); the window is done in slices of slow rows so
+    // that the scratch stays below ~1 GB
+    Scratch scr(st);
+    const int64_t per_row_block = (int64_t)grid.x * 128;  // threads of one grid row (4 slow rows)
+    const int64_t max_threads = std::max<int64_t>(per_row_block, ((int64_t)1 << 30) / ((int64_t)k * (sizeof(R) + 4)));
+    const int blocks_y = (int)std::min<int64_t>(grid.y, std::max<int64_t>(1, max_threads / per_row_block));
+    a.tk_stride = per_row_block * blocks_y;
+    GI_TRY(scr.alloc(&a.tk_d, (size_t)a.tk_stride * k));
+    GI_TRY(scr.alloc(&a.tk_id, (size_t)a.tk_stride * k));
+    const TargetWindow<R> full = a.win;
+    R* const out0 = a.out; int32_t* const nn0 = a.nn_index; R* const nd0 = a.nn_dist2;
+    for (int by = 0; by < (int)grid.y; by += blocks_y) {
+      const int s_lo = full.s0 + by * 4, s_hi = std::min(full.s1, s_lo + blocks_y * 4);
+      a.win.s0 = s_lo; a.win.s1 = s_hi;
+      const int64_t off = (int64_t)(s_lo - full.s0) * full.nf();
+      a.out = out0 + off;
+      a.nn_index = nn0 ? nn0 + off * k : nullptr;
+      a.nn_dist2 = nd0 ? nd0 + off * k : nullptr;
+      launch_query<R, 0>(a, prune, dim3(grid.x, div_up(s_hi - s_lo, 4)), st);
+    }
+  }
   GI_CUDA(cudaGetLastError());
   return GI_OK;
 }
@@ -599,7 +630,7 @@ template <class R>
 int kdtree_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
                   const R* y_axis, int len_y, int k, int row_begin, int row_end, R* data_ip,
                   int32_t* nn_index, R* nn_dist2, int64_t* counters_out, int flags, cudaStream_t st) {
-  GI_REQUIRE(k >= 1 && k <= 32, "num_neighbours must be in 1..32");
+  GI_REQUIRE(k >= 1, "num_neighbours must be at least 1");
   GI_TRY(ensure_device());
   if (row_begin == row_end) return GI_OK;
   StatusSlot slot;
@@ -665,7 +696,7 @@ int kd_run_banded(HostPipe* pipe, const KdTreeDev<R>& tree, const R* dx, int len
 template <class R>
 int kdtree_host(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
                 int len_y, int k, int row_begin, int row_end, R* data_ip, int flags) {
-  GI_REQUIRE(k >= 1 && k <= 32, "num_neighbours must be in 1..32");
+  GI_REQUIRE(k >= 1, "num_neighbours must be at least 1");
   GI_TRY(ensure_device());
   if (row_begin == row_end) return GI_OK;
   HostPipe* pipe;
@@ -743,7 +774,7 @@ template <class R> struct KdPlan : PlanBase {
 template <class R>
 int kdtree_plan_create(const R* points, int num_points, const R* x_axis, int len_x, const R* y_axis, int len_y, int k,
                        int row_begin, int row_end, int flags, int mem, cudaStream_t st_in, PlanBase** out) {
-  GI_REQUIRE(k >= 1 && k <= 32, "num_neighbours must be in 1..32");
+  GI_REQUIRE(k >= 1, "num_neighbours must be at least 1");
   GI_TRY(ensure_device());
   cudaStream_t st = st_in;
   if (mem == GI_HOST) { HostPipe* pipe; GI_TRY(host_pipe(&pipe)); st = pipe->compute; }

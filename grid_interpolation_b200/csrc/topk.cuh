@@ -44,4 +44,39 @@ template <class R, int KC> struct TopK {
   }
 };
 
+// Any k (the reference takes any num_neighbours, interpolation.f90:107-108,201-202): the same list in global
+// scratch memory, element i of a thread's list `stride` elements after element i-1 (coalesced across a warp).
+// Same interface and the same two insertion rules; an insertion is a shift loop over memory, so this is the
+// slow form -- the kernels instantiate it (KC = 0) only for k > 32.
+template <class R> struct TopK<R, 0> {
+  R* d;
+  int* id;
+  int64_t stride;
+  int k;
+  R dlast;
+  static constexpr int base = 0;
+  __device__ __forceinline__ void bind(R* d_all, int* id_all, int64_t stride_, int64_t thread) {
+    d = d_all + thread; id = id_all + thread; stride = stride_;
+  }
+  __device__ __forceinline__ void init(int k_, R d_init, int id_init) {
+    k = k_;
+    for (int i = 0; i < k; ++i) { d[i * stride] = d_init; id[i * stride] = id_init; }
+    dlast = d_init;
+  }
+  __device__ __forceinline__ R dist2(int rank) const { return d[rank * stride]; }
+  __device__ __forceinline__ int index(int rank) const { return id[rank * stride]; }
+  template <bool BEFORE_EQUAL> __device__ __forceinline__ void insert(R d2, int idx) {  // precondition: d2 < dlast
+    int j = k - 1;
+    for (; j >= 1; --j) {
+      const R prev = d[(j - 1) * stride];
+      if (!(BEFORE_EQUAL ? d2 <= prev : d2 < prev)) break;
+      d[j * stride] = prev;
+      id[j * stride] = id[(j - 1) * stride];
+    }
+    d[j * stride] = d2;
+    id[j * stride] = idx;
+    dlast = d[(k - 1) * stride];
+  }
+};
+
 }  // namespace gi

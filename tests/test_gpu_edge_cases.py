@@ -58,11 +58,27 @@ def test_k_limits(c1, k):
     same(g.nn_index, np.moveaxis(w.nn_index, 0, -1)); same(got, want)
 
 
-def test_k_above_32_is_rejected(c1):
-    with pytest.raises(ValueError):
-        ip.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, 33)
-    with pytest.raises(ValueError):
-        ip.idw_kdtree(c1.points.T, c1.data_pts, c1.x_axis, c1.y_axis, 33)
+@pytest.mark.parametrize("k", [33, 50, 200])
+def test_k_above_32_uses_the_any_k_lists(c1, k):
+    """The reference takes any num_neighbours (interpolation.f90:107-108,201-202); above 32 the neighbour lists
+    live in scratch memory instead of registers (topk.cuh, KC = 0).  Same ids, same order, same bits."""
+    sub = slice(0, 900)
+    pts, dat = c1.points[sub], c1.data_pts[sub]
+    x, y = c1.x_axis[::4], c1.y_axis[::4]
+    spac = c1.grid_spac * 4
+    want, w = orc.idw_esrg_nearest(pts, dat, x, y, spac, k, debug=True)
+    for order in ("F", "C"):
+        got, g = ip.idw_esrg_nearest_ex(pts, dat, x, y, spac, k, debug=True, order=order)
+        same(g.nn_index, np.moveaxis(w.nn_index, 0, -1)); same(got, want)
+    got = ip.idw_esrg_nearest(pts, dat, x, y, spac, k)     # the pipelined host path
+    same(got, want)
+    want, w = orc.idw_kdtree(pts.T, dat, x, y, k, debug=True)
+    got, g = ip.idw_kdtree_ex(pts.T, dat, x, y, k, debug=True)
+    same(g.nn_index, np.moveaxis(w.nn_index, 0, -1)); same(got, want)
+    got = ip.idw_kdtree(pts.T, dat, x, y, k)
+    same(got, want)
+    with ip.KdTreePlan(pts.T, x, y, k) as plan:
+        same(plan(dat), want)
 
 
 def test_esrg_exactly_k_points_and_points_outside_grid():
