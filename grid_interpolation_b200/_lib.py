@@ -18,6 +18,7 @@ GI_BILINEAR_SEARCH_AXES = 64
 GI_KD_FAITHFUL_BUILD = 128
 GI_BARY_REFERENCE_ORDER = 256
 GI_BARY_BAND_PACK = 512
+GI_TARGETS_ROWMAJOR = 1024
 GI_MAX_GATHER_FIELDS, GI_PEER_HANDLE_BYTES = 8, 64
 
 _vp, _i, _i64, _d, _f = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float
@@ -37,6 +38,7 @@ SIGNATURES = {
     "gi_last_timing_name": ([_i], C.c_char_p),
     "gi_release_workspace": ([], None),
     "gi_set_fixup_list_capacity": ([_i64], None),
+    "gi_set_sliver_guard": ([C.c_double], None),
     "gi_peer_alloc": ([C.c_uint64], _vp),
     "gi_peer_free": ([_vp], None),
     "gi_peer_export": ([_vp, _vp], _i),
@@ -66,6 +68,8 @@ for _suf, _real in (("f64", _d), ("f32", _f)):
         f"gi_kd_build_{_suf}": ([_vp, _i, _vp, _i, _i, _vp], _i),
         f"gi_esrg_assign_points_to_cells_{_suf}": ([_vp, _i, _vp, _i, _vp, _i, _real, _vp, _vp, _i, _i, _vp], _i),
         f"gi_fill_nearest_neighbour_{_suf}": ([_vp, _i, _i, _vp, _vp, _i, _i, _vp], _i),
+        f"gi_barycentric_points_{_suf}": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp], _i),
+        f"gi_idw_kdtree_points_{_suf}": ([_vp, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp], _i),
     })
 
 _lib = None

@@ -167,6 +167,8 @@ static int64_t g_band_bytes = (int64_t)32 << 20;
 int64_t pipeline_band_bytes() { return g_band_bytes; }
 static int64_t g_fixup_capacity = (int64_t)1 << 22;
 int64_t fixup_list_capacity() { return g_fixup_capacity; }
+static double g_sliver_quality = 0.0;
+double sliver_guard_quality() { return g_sliver_quality; }
 
 static thread_local HostPipe t_pipe;
 int host_pipe(HostPipe** out) {
@@ -191,7 +193,7 @@ static int host_stream(cudaStream_t* out) {
 }
 
 static bool valid_flags(int flags) {
-  return (flags & ~(GI_POINTS_ROWMAJOR | GI_TOPO_ROWMAJOR | GI_FIELD_ROWMAJOR | GI_KD_REFERENCE_VISITS | GI_ESRG_REFERENCE_ORDER | GI_KD_EXACT_PRUNE | GI_BILINEAR_SEARCH_AXES | GI_KD_FAITHFUL_BUILD | GI_BARY_REFERENCE_ORDER | GI_BARY_BAND_PACK)) == 0;
+  return (flags & ~(GI_POINTS_ROWMAJOR | GI_TOPO_ROWMAJOR | GI_FIELD_ROWMAJOR | GI_KD_REFERENCE_VISITS | GI_ESRG_REFERENCE_ORDER | GI_KD_EXACT_PRUNE | GI_BILINEAR_SEARCH_AXES | GI_KD_FAITHFUL_BUILD | GI_BARY_REFERENCE_ORDER | GI_BARY_BAND_PACK | GI_TARGETS_ROWMAJOR)) == 0;
 }
 #define GI_CHECK_COMMON()                                                 \
   GI_REQUIRE(valid_flags(flags), "unknown bits in flags");                \
@@ -319,6 +321,69 @@ static int fill_api(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64
   GI_TRY(fill_device<R>(dm, len_x, len_y, dd, dsrc, flags, st));
   GI_TRY(to_host(st, data_ip, dd, n));
   GI_TRY(to_host(st, fill_src, dsrc, n));
+  return read_status(st, true);
+}
+
+// scattered targets: host form = copy in, device form, copy out (synchronous)
+template <class R>
+static int barycentric_points_api(const R* points, int num_points, const R* data_in, const int32_t* simplices,
+                                  const int32_t* neighbours, int num_tri, const R* targets, int64_t m, R* data_ip,
+                                  int32_t* tri_out, uint8_t* outside_out, int flags, int mem, void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(points && data_in && simplices && neighbours && (targets || m == 0) && (data_ip || m == 0), "null pointer");
+  GI_REQUIRE(num_points >= 3 && num_tri >= 1 && m >= 0, "bad dimensions");
+  if (mem == GI_DEVICE)
+    return barycentric_points_device<R>(points, num_points, data_in, simplices, neighbours, num_tri, targets, m, data_ip,
+                                        tri_out, outside_out, flags, (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  if (m == 0) return GI_OK;
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  R *dp, *dd, *dt, *dout;
+  int32_t *ds, *dn, *dtri;
+  uint8_t* dmask;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, data_in, (size_t)num_points, &dd));
+  GI_TRY(to_device(scr, simplices, (size_t)3 * num_tri, &ds));
+  GI_TRY(to_device(scr, neighbours, (size_t)3 * num_tri, &dn));
+  GI_TRY(to_device(scr, targets, (size_t)2 * m, &dt));
+  GI_TRY(scr.alloc(&dout, (size_t)m));
+  GI_TRY(out_device(scr, tri_out, (size_t)m, &dtri));
+  GI_TRY(out_device(scr, outside_out, (size_t)m, &dmask));
+  GI_TRY(barycentric_points_device<R>(dp, num_points, dd, ds, dn, num_tri, dt, m, dout, dtri, dmask, flags, st));
+  GI_TRY(to_host(st, data_ip, dout, (size_t)m));
+  GI_TRY(to_host(st, tri_out, dtri, (size_t)m));
+  GI_TRY(to_host(st, outside_out, dmask, (size_t)m));
+  return read_status(st, true);
+}
+
+template <class R>
+static int kdtree_points_api(const R* points, int num_points, const R* data_in, const R* targets, int64_t m, int k,
+                             R* data_ip, int32_t* nn_index, R* nn_dist2, int flags, int mem, void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(points && data_in && (targets || m == 0) && (data_ip || m == 0), "null pointer");
+  GI_REQUIRE(num_points >= 1 && m >= 0 && k >= 1, "bad dimensions");
+  if (mem == GI_DEVICE)
+    return kdtree_points_device<R>(points, num_points, data_in, targets, m, k, data_ip, nn_index, nn_dist2, flags,
+                                   (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  if (m == 0) return GI_OK;
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  R *dp, *dd, *dt, *dout, *dd2;
+  int32_t* dnn;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, data_in, (size_t)num_points, &dd));
+  GI_TRY(to_device(scr, targets, (size_t)2 * m, &dt));
+  GI_TRY(scr.alloc(&dout, (size_t)m));
+  GI_TRY(out_device(scr, nn_index, (size_t)m * k, &dnn));
+  GI_TRY(out_device(scr, nn_dist2, (size_t)m * k, &dd2));
+  GI_TRY(kdtree_points_device<R>(dp, num_points, dd, dt, m, k, dout, dnn, dd2, flags, st));
+  GI_TRY(to_host(st, data_ip, dout, (size_t)m));
+  GI_TRY(to_host(st, nn_index, dnn, (size_t)m * k));
+  GI_TRY(to_host(st, nn_dist2, dd2, (size_t)m * k));
   return read_status(st, true);
 }
 
@@ -501,6 +566,7 @@ GI_API int gi_last_timings(double* ms, int capacity) {
 GI_API const char* gi_last_timing_name(int i) {
   return (i >= 0 && i < (int)t_rec.names.size()) ? t_rec.names[i].c_str() : "";
 }
+GI_API void gi_set_sliver_guard(double min_quality) { g_sliver_quality = min_quality > 0.0 ? min_quality : 0.0; }
 GI_API void gi_set_fixup_list_capacity(int64_t targets) { g_fixup_capacity = targets > 0 ? targets : ((int64_t)1 << 22); }
 
 GI_API void* gi_peer_alloc(uint64_t bytes) {
@@ -701,6 +767,19 @@ GI_API void gi_plan_destroy(gi_plan* plan) {
                                                   int32_t* indptr, int flags, int mem, void* stream) {             \
     return esrg_bin_api<R>(points, num_points, x_axis, len_x, y_axis, len_y, grid_spac, index_of_pts, indptr,      \
                            flags, mem, stream);                                                                     \
+  }                                                                                                                 \
+  GI_API int gi_barycentric_points_##SUF(const R* points, int num_points, const R* data_in,                        \
+                                         const int32_t* simplices, const int32_t* neighbours, int num_triangles,  \
+                                         const R* targets, int64_t num_targets, R* data_ip, int32_t* tri_out,     \
+                                         uint8_t* outside_out, int flags, int mem, void* stream) {                \
+    return barycentric_points_api<R>(points, num_points, data_in, simplices, neighbours, num_triangles, targets,   \
+                                     num_targets, data_ip, tri_out, outside_out, flags, mem, stream);              \
+  }                                                                                                                 \
+  GI_API int gi_idw_kdtree_points_##SUF(const R* points, int num_points, const R* data_in, const R* targets,       \
+                                        int64_t num_targets, int num_neighbours, R* data_ip, int32_t* nn_index,    \
+                                        R* nn_dist2, int flags, int mem, void* stream) {                           \
+    return kdtree_points_api<R>(points, num_points, data_in, targets, num_targets, num_neighbours, data_ip,        \
+                                nn_index, nn_dist2, flags, mem, stream);                                           \
   }                                                                                                                 \
   GI_API int gi_fill_nearest_neighbour_##SUF(const uint8_t* mask_outside, int len_x, int len_y, R* data_ip,        \
                                              int64_t* fill_src, int flags, int mem, void* stream) {                \

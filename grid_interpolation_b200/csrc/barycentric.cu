@@ -32,7 +32,9 @@
 #include <algorithm>
 #include <memory>
 
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "ieee_div.cuh"
 #include "kernels.cuh"
@@ -76,7 +78,8 @@ template <class R> __device__ __forceinline__ void check_axes(const TargetWindow
 template <class R> struct alignas(sizeof(R) == 8 ? 32 : 16) TriGeom {
   R x1, y1, x2, y2, x3, y3;
   int n1, n2, n3;  // neighbour opposite vertex 1/2/3, 0-based, -1 = hull edge, -2 = not packed (band-limited pack)
-  int pad;         // ambiguity threshold of this triangle (bit pattern, see amb_threshold)
+  int pad;         // bits 1-30: ambiguity threshold of this triangle (bit pattern, see amb_threshold); bit 31:
+                   // long triangle (kLongTriangle); bit 0: hull sliver, not to be interpolated in (kSliver)
   R A, B, C, D;
   R denom, d1, d2, d3;
 };
@@ -157,6 +160,8 @@ __device__ __forceinline__ SeedGrid<R> seed_grid_of(const R* __restrict__ x_axis
 // record that was never written (the caller retries with the whole mesh packed).
 constexpr int kNotPacked = -2;
 constexpr int kLongTriangle = (int)0x80000000;  // sign bit of TriGeom::pad, see farthest_failing_edge
+constexpr int kSliver = 1;                      // bit 0 of TriGeom::pad, see sliver_guard
+constexpr int kThrMask = 0x7ffffffe;            // the threshold bits of TriGeom::pad
 template <class R>
 __global__ void __launch_bounds__(256)
 need_kernel(PointsView<R> pts, TopoView simp, int num_points, int num_tri, const R* __restrict__ y_axis, int row_lo,
@@ -179,12 +184,26 @@ need_kernel(PointsView<R> pts, TopoView simp, int num_points, int num_tri, const
   need[t] = (fmax(fmax(ya, yb), yc) >= y_lo && fmin(fmin(ya, yb), yc) <= y_hi) ? 1 : 0;
 }
 
+// Sliver guard (the reference's README to-do: "prohibiting barycentric interpolation for sliver triangles close to
+// the edge (and filling the subsequent missing values from the nearest neighbours)", README.md:41-43).  Opt-in
+// (gi_set_sliver_guard): a triangle with a hull edge whose quality
+//     q = |denom| / max |edge|^2        (denom = twice the signed area, interpolation.f90:385-386; equilateral: 0.87)
+// is below the threshold keeps its place in the mesh -- walks pass through it as before -- but a target found in
+// it is treated like a target outside the hull: masked, then filled by fill_nearest_neighbour.  The oracle has the
+// same switch (orc_set_sliver_guard) with the same expression.
+template <class R> __device__ __forceinline__ R sliver_quality(const TriGeom<R>& g) {
+  const R l1 = (g.x2 - g.x1) * (g.x2 - g.x1) + (g.y2 - g.y1) * (g.y2 - g.y1);
+  const R l2 = (g.x3 - g.x2) * (g.x3 - g.x2) + (g.y3 - g.y2) * (g.y3 - g.y2);
+  const R l3 = (g.x1 - g.x3) * (g.x1 - g.x3) + (g.y1 - g.y3) * (g.y1 - g.y3);
+  return fabs(g.denom) / fmax(fmax(l1, l2), l3);
+}
+
 template <class R, bool BINS>
 __global__ void __launch_bounds__(256)
 pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, TopoView nbr, int num_points,
                  int num_tri, TriGeom<R>* __restrict__ geom, int* __restrict__ seed,
                  const R* __restrict__ x_axis, int len_x, const R* __restrict__ y_axis, int len_y,
-                 const uint8_t* __restrict__ need, const TargetWindow<R> bw, const TileBins bb,
+                 const uint8_t* __restrict__ need, const TargetWindow<R> bw, const TileBins bb, R sliver_q,
                  int* __restrict__ status) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool packed = t < num_tri && (!need || need[t]);
@@ -229,6 +248,7 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
   }
   g.A = g.y2 - g.y3; g.B = g.x3 - g.x2; g.C = g.y3 - g.y1; g.D = g.x1 - g.x3;   // interpolation.f90:385-394
   g.denom = g.A * g.D + g.B * (g.y1 - g.y3);                                     // :385-386
+  if (sliver_q > R(0) && (n1 == 0 || n2 == 0 || n3 == 0) && sliver_quality(g) < sliver_q) g.pad |= kSliver;
   g.d1 = __ldg(data + (a - 1)); g.d2 = __ldg(data + (b - 1)); g.d3 = __ldg(data + (c - 1));
   geom[t] = g;
   if (BINS) {  // first binning pass: count this triangle in the tiles its bounds meet
@@ -406,14 +426,14 @@ template <> __device__ __forceinline__ int amb_threshold<double>(const TriGeom<d
   const double b = (g.x3 - g.x2) * (g.x3 - g.x2) + (g.y3 - g.y2) * (g.y3 - g.y2);
   const double c = (g.x1 - g.x3) * (g.x1 - g.x3) + (g.y1 - g.y3) * (g.y1 - g.y3);
   const double t = 2e-10 + 32.0 * 1.1102230246251565e-16 * fmax(fmax(a, b), c);
-  return t < 1e300 ? __double2hiint(t) + 1 : 0x7fe00000;
+  return t < 1e300 ? (__double2hiint(t) + 2) & kThrMask : 0x7fe00000;  // rounded up, bit 0 left free
 }
 template <> __device__ __forceinline__ int amb_threshold<float>(const TriGeom<float>& g) {
   const float a = (g.x2 - g.x1) * (g.x2 - g.x1) + (g.y2 - g.y1) * (g.y2 - g.y1);
   const float b = (g.x3 - g.x2) * (g.x3 - g.x2) + (g.y3 - g.y2) * (g.y3 - g.y2);
   const float c = (g.x1 - g.x3) * (g.x1 - g.x3) + (g.y1 - g.y3) * (g.y1 - g.y3);
   const float t = 2e-10f + 32.0f * 5.9604645e-8f * fmaxf(fmaxf(a, b), c);
-  return t < 1e37f ? __float_as_int(t) + 1 : 0x7f000000;
+  return t < 1e37f ? (__float_as_int(t) + 2) & kThrMask : 0x7f000000;
 }
 // |x| below the triangle's threshold?  Integer compares on the (high) word: two instructions per cross.
 // (thr = the record's pad without its kLongTriangle bit)
@@ -431,7 +451,7 @@ __device__ __forceinline__ int walk_checked(const TriGeom<R>* __restrict__ geom,
     ++it;
     TriGeom<R> g;
     load_walk(geom + tri, g);
-    g.pad &= 0x7fffffff;  // the reference's path: first failing edge, long triangle or not
+    g.pad &= kThrMask;  // the reference's path: first failing edge, long triangle or not
     const R c1 = (g.x2 - g.x1) * (ty - g.y1) - (g.y2 - g.y1) * (tx - g.x1);
     const R c2 = (g.x3 - g.x2) * (ty - g.y2) - (g.y3 - g.y2) * (tx - g.x2);
     const R c3 = (g.x1 - g.x3) * (ty - g.y3) - (g.y1 - g.y3) * (tx - g.x3);
@@ -593,13 +613,14 @@ __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, i
     R m1, m2, m3, p1, p2, p3, k1, k2, k3;
     bool fresh;    // no target resolved in `tri` yet
     bool careful;  // long triangle: see farthest_failing_edge
+    bool sliver;   // hull sliver: targets found in it are masked (sliver_guard)
     bool forced_out = false;  // careful_locate found this row's target outside the hull at `tri`
     auto enter = [&](int t) {  // make `t` the current triangle: one 64 B load + 12 flops
       tri = t;
       fresh = true;
       TriGeom<R> g;
       load_walk(a.geom + t, g);
-      n1 = g.n1; n2 = g.n2; n3 = g.n3; thr = g.pad & 0x7fffffff; careful = g.pad < 0;
+      n1 = g.n1; n2 = g.n2; n3 = g.n3; thr = g.pad & kThrMask; careful = g.pad < 0; sliver = g.pad & kSliver;
       const R ex1 = g.x2 - g.x1, ey1 = g.y2 - g.y1;   // edge (v1,v2)
       const R ex2 = g.x3 - g.x2, ey2 = g.y3 - g.y2;   // edge (v2,v3)
       const R ex3 = g.x1 - g.x3, ey3 = g.y1 - g.y3;   // edge (v3,v1)
@@ -653,11 +674,11 @@ __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, i
         const unsigned long long slot = atomicAdd((unsigned long long*)(a.counters + 5), 1ull);
         if (slot < (unsigned long long)a.amb_cap) a.amb_list[slot] = (srow0 + r - w.s0) * w.nf() + lane_f;
       }
-      if (fresh && !outside) {  // phase 2 will want this triangle's nodal values: pull the sector into L1 now
+      if (fresh && !outside && !sliver) {  // phase 2 will want this triangle's nodal values: pull the sector into L1 now
         touch_values(a.geom + tri);
         fresh = false;
       }
-      stri[r][tid] = outside ? ~tri : tri;
+      stri[r][tid] = (outside | sliver) ? ~tri : tri;
       iters += it;
       it = 0;
       ++r;
@@ -700,6 +721,7 @@ __global__ void __launch_bounds__(kWalkThreads) locate_eval_standby_kernel(const
 template <class R>
 __device__ __forceinline__ void publish_target(const WalkArgs<R>& a, int f, int s, int tri, bool inside, R tx, R ty) {
   const TargetWindow<R>& w = a.win;
+  if (inside && (a.geom[tri].pad & kSliver)) inside = false;  // sliver_guard
   if (f >= a.bf0 && f < a.bf1 && s >= a.bs0 && s < a.bs1) {
     const int64_t o = (int64_t)(s - a.bs0) * (a.bf1 - a.bf0) + (f - a.bf0);
     if (inside) {
@@ -1185,11 +1207,11 @@ int bary_pack(Scratch& scr, const R* points, int num_points, const R* data_in, c
   if (pm->bins.start)
     pack_mesh_kernel<R, true><<<div_up(n_threads, 256), 256, 0, st>>>(pv, data_in, sv, nv, num_points, num_tri, pm->geom,
                                                                      pm->seed, x_axis, len_x, y_axis, len_y, need, bw,
-                                                                     pm->bins, status);
+                                                                     pm->bins, (R)sliver_guard_quality(), status);
   else
     pack_mesh_kernel<R, false><<<div_up(n_threads, 256), 256, 0, st>>>(pv, data_in, sv, nv, num_points, num_tri, pm->geom,
                                                                       pm->seed, x_axis, len_x, y_axis, len_y, need, bw,
-                                                                      pm->bins, status);
+                                                                      pm->bins, (R)sliver_guard_quality(), status);
   GI_CUDA(cudaGetLastError());
   if (pm->bins.start) GI_TRY(finish_tile_bins(scr, num_tri, pm->bins));
   return GI_OK;
@@ -1697,6 +1719,197 @@ int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* 
   return GI_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Scattered targets (the reference interpolates to the nodes of a regular grid only,
+// interpolation.f90:365-371).  Same search structure -- packed records, a seed grid laid over the bounding box of the
+// mesh -- same visibility walk (triangle_walk.f90:24-84) and the same weights (interpolation.f90:385-398) per target.
+// A target outside the convex hull takes the value of the CLOSEST LOCATION ON THE MESH, which is what the reference's
+// header comment promises (interpolation.f90:292-293) and its grid version approximates by the nearest node inside
+// the hull: from the hull edge the walk left through, the hull is followed edge by edge (rotating about the shared
+// hull vertex through the neighbour links) until the foot of the perpendicular falls on an edge or a vertex is
+// closest; the weights are evaluated there.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ unsigned long long ordered_key(double v) {  // monotone map double -> uint64
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double from_ordered_key(unsigned long long k) {
+  const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  double d;
+#ifdef __CUDA_ARCH__
+  d = __longlong_as_double((long long)u);
+#else
+  memcpy(&d, &u, sizeof d);
+#endif
+  return d;
+}
+// box[0..3] = keys of min x, min y, max x, max y (initialised to ~0, ~0, 0, 0)
+template <class R>
+__global__ void __launch_bounds__(256) points_box_kernel(PointsView<R> pts, int n, unsigned long long* box) {
+  double x0 = 1.7976931348623157e308, y0 = x0, x1 = -x0, y1 = -x0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    R x, y;
+    pts.xy(i, x, y);
+    x0 = fmin(x0, (double)x); x1 = fmax(x1, (double)x); y0 = fmin(y0, (double)y); y1 = fmax(y1, (double)y);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, off)); y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, off));
+    x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, off)); y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, off));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(box + 0, ordered_key(x0)); atomicMin(box + 1, ordered_key(y0));
+    atomicMax(box + 2, ordered_key(x1)); atomicMax(box + 3, ordered_key(y1));
+  }
+}
+// virtual axes over the box: len nodes each (only the seed grid is built on them)
+template <class R>
+__global__ void virtual_axes_kernel(const unsigned long long* box, int len, R* xs, R* ys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  const double x0 = from_ordered_key(box[0]), y0 = from_ordered_key(box[1]);
+  const double x1 = from_ordered_key(box[2]), y1 = from_ordered_key(box[3]);
+  const double f = len > 1 ? (double)i / (double)(len - 1) : 0.0;
+  xs[i] = (R)(x0 + (x1 - x0) * f);
+  ys[i] = (R)(y0 + (y1 - y0) * f);
+}
+
+template <class R> struct TriView {  // vertices and neighbours of a record by index 0..2
+  R x[3], y[3];
+  int nb[3];  // neighbour opposite vertex i
+  __device__ __forceinline__ void load(const TriGeom<R>* p) {
+    TriGeom<R> g;
+    load_walk(p, g);
+    x[0] = g.x1; y[0] = g.y1; x[1] = g.x2; y[1] = g.y2; x[2] = g.x3; y[2] = g.y3;
+    nb[0] = g.n1; nb[1] = g.n2; nb[2] = g.n3;
+  }
+};
+
+// Closest point of the hull to (px, py), which left the mesh through hull edge e (vertices e, e+1) of triangle t.
+template <class R>
+__device__ void closest_on_hull(const TriGeom<R>* __restrict__ geom, int& t, int e, R px, R py, int cap, R& qx, R& qy,
+                                int* status) {
+  int dir = 0;  // +1: moving on past vertex b, -1: moving back past vertex a
+  for (int it = 0;; ++it) {
+    TriView<R> v;
+    v.load(geom + t);
+    const int ia = e, ib = (e + 1) % 3;
+    const R abx = v.x[ib] - v.x[ia], aby = v.y[ib] - v.y[ia];
+    const R len2 = abx * abx + aby * aby;
+    const R tt = len2 > R(0) ? ((px - v.x[ia]) * abx + (py - v.y[ia]) * aby) / len2 : R(0);
+    if (it >= cap) { raise_status(status, GI_ERR_ITER_CAP); qx = v.x[ia]; qy = v.y[ia]; return; }
+    if (tt < R(0)) {
+      if (dir > 0) { qx = v.x[ia]; qy = v.y[ia]; return; }  // the vertex between the two edges is closest
+      dir = -1;
+      const R ax = v.x[ia], ay = v.y[ia];
+      int k = (e + 2) % 3;  // the edge entering a in t
+      while (v.nb[(k + 2) % 3] >= 0) {
+        t = v.nb[(k + 2) % 3];
+        v.load(geom + t);
+        const int j = (v.x[0] == ax && v.y[0] == ay) ? 0 : ((v.x[1] == ax && v.y[1] == ay) ? 1 : 2);
+        k = (j + 2) % 3;
+      }
+      e = k;
+    } else if (tt > R(1)) {
+      if (dir < 0) { qx = v.x[ib]; qy = v.y[ib]; return; }
+      dir = 1;
+      const R bx = v.x[ib], by = v.y[ib];
+      int k = (e + 1) % 3;  // the edge leaving b in t
+      while (v.nb[(k + 2) % 3] >= 0) {
+        t = v.nb[(k + 2) % 3];
+        v.load(geom + t);
+        const int j = (v.x[0] == bx && v.y[0] == by) ? 0 : ((v.x[1] == bx && v.y[1] == by) ? 1 : 2);
+        k = j;
+      }
+      e = k;
+    } else {
+      qx = v.x[ia] + tt * abx; qy = v.y[ia] + tt * aby;
+      return;
+    }
+  }
+}
+
+template <class R>
+__global__ void __launch_bounds__(128)
+bary_points_kernel(const TriGeom<R>* __restrict__ geom, const int* __restrict__ seed, int ncx, int ncy, int num_tri,
+                   const R* __restrict__ xs, const R* __restrict__ ys, int vlen, PointsView<R> targets, int64_t m,
+                   R* __restrict__ out, int32_t* __restrict__ tri_out, uint8_t* __restrict__ outside_out, int* status) {
+  const R margin = Consts<R>::margin();
+  const R x0 = __ldg(xs), y0 = __ldg(ys), ex = __ldg(xs + vlen - 1) - x0, ey = __ldg(ys + vlen - 1) - y0;
+  const R sx = ex > R(0) ? R(vlen - 1) / ex : R(0), sy = ey > R(0) ? R(vlen - 1) / ey : R(0);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    R tx, ty;
+    targets.xy(i, tx, ty);
+    const int ix = (int)fmin(fmax((tx - x0) * sx, R(0)), R(vlen - 1));
+    const int iy = (int)fmin(fmax((ty - y0) * sy, R(0)), R(vlen - 1));
+    int tri = seed_lookup(seed, ncx, ncy, ix, iy, num_tri);
+    int edge = -1;
+    TriGeom<R> g;
+    for (int it = 0;; ++it) {                                            // triangle_walk.f90:44-84
+      load_walk(geom + tri, g);
+      const R c1 = (g.x2 - g.x1) * (ty - g.y1) - (g.y2 - g.y1) * (tx - g.x1);
+      const R c2 = (g.x3 - g.x2) * (ty - g.y2) - (g.y3 - g.y2) * (tx - g.x2);
+      const R c3 = (g.x1 - g.x3) * (ty - g.y3) - (g.y1 - g.y3) * (tx - g.x3);
+      int nxt, e;
+      if (c1 < margin) { nxt = g.n3; e = 0; }
+      else if (c2 < margin) { nxt = g.n1; e = 1; }
+      else if (c3 < margin) { nxt = g.n2; e = 2; }
+      else break;
+      if (nxt < 0) { edge = e; break; }
+      if (it >= num_tri + 16) { raise_status(status, GI_ERR_ITER_CAP); edge = e; break; }
+      tri = nxt;
+    }
+    R qx = tx, qy = ty;
+    if (edge >= 0) closest_on_hull(geom, tri, edge, tx, ty, num_tri + 16, qx, qy, status);
+    load_eval(geom + tri, g);
+    out[i] = eval_value(g, qx, qy);
+    if (tri_out) tri_out[i] = tri + 1;
+    if (outside_out) outside_out[i] = edge >= 0 ? 1 : 0;
+  }
+}
+}  // namespace
+
+template <class R>
+int barycentric_points_device(const R* points, int num_points, const R* data_in, const int32_t* simplices,
+                              const int32_t* neighbours, int num_tri, const R* targets, int64_t num_targets,
+                              R* data_ip, int32_t* tri_out, uint8_t* outside_out, int flags, cudaStream_t st) {
+  GI_REQUIRE(num_points >= 3 && num_tri >= 1, "need at least 3 points and 1 triangle");
+  GI_REQUIRE(num_targets >= 0, "negative number of targets");
+  GI_TRY(ensure_device());
+  if (num_targets == 0) return GI_OK;
+  StatusSlot slot;
+  GI_TRY(get_status_slot(st, &slot));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("pack_mesh");
+  // seed grid: about one cell per four triangles over the bounding box of the mesh
+  const int cells = std::max(1, std::min(4096, (int)std::sqrt((double)num_tri / 4.0)));
+  const int vlen = cells * kSeedCell;
+  unsigned long long* box;
+  R *xs, *ys;
+  GI_TRY(scr.alloc(&box, 4));
+  GI_TRY(scr.alloc(&xs, (size_t)vlen));
+  GI_TRY(scr.alloc(&ys, (size_t)vlen));
+  GI_CUDA(cudaMemsetAsync(box, 0xff, sizeof(unsigned long long) * 2, st));
+  GI_CUDA(cudaMemsetAsync(box + 2, 0, sizeof(unsigned long long) * 2, st));
+  const PointsView<R> pv = points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR);
+  points_box_kernel<R><<<std::min(div_up(num_points, 256), kNumSMs * 8), 256, 0, st>>>(pv, num_points, box);
+  virtual_axes_kernel<R><<<div_up(vlen, 256), 256, 0, st>>>(box, vlen, xs, ys);
+  GI_CUDA(cudaGetLastError());
+  PackedMesh<R> pm;
+  GI_TRY(bary_pack<R>(scr, points, num_points, data_in, xs, vlen, ys, vlen, simplices, neighbours, num_tri,
+                      flags & ~GI_BARY_BAND_PACK, slot.dev, &pm, 0, 0));
+  ph.mark("walk");
+  const PointsView<R> tv = points_n2(targets, num_targets, flags & GI_TARGETS_ROWMAJOR);
+  const int blocks = (int)std::min<int64_t>(div_up(num_targets, 128), (int64_t)kNumSMs * 32);
+  bary_points_kernel<R><<<blocks, 128, 0, st>>>(pm.geom, pm.seed, pm.ncx, pm.ncy, num_tri, xs, ys, vlen, tv, num_targets,
+                                               data_ip, tri_out, outside_out, slot.dev);
+  GI_CUDA(cudaGetLastError());
+  ph.finish();
+  GI_TRY(flush_status(st, slot));
+  return GI_OK;
+}
+
 #define GI_INSTANTIATE(R)                                                                                  \
   template int barycentric_device<R>(const R*, int, const R*, const R*, int, const R*, int, const int32_t*, \
                                      const int32_t*, int, int, int, int, R*, int32_t*, uint8_t*, int64_t*,  \
@@ -1709,7 +1922,9 @@ int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* 
                                    const int32_t*, int, int, int, int, R*, int);                            \
   template int barycentric_plan_create<R>(const R*, int, const R*, int, const R*, int, const int32_t*,      \
                                           const int32_t*, int, int, int, int, int, int, cudaStream_t,       \
-                                          PlanBase**);
+                                          PlanBase**);                                                       \
+  template int barycentric_points_device<R>(const R*, int, const R*, const int32_t*, const int32_t*, int,  \
+                                            const R*, int64_t, R*, int32_t*, uint8_t*, int, cudaStream_t);
 GI_INSTANTIATE(double)
 GI_INSTANTIATE(float)
 

@@ -206,6 +206,7 @@ int host_pipe(HostPipe** out);  // per host thread, created on first use (api.cu
 // bands of at least ~32 MB of output (a PCIe transfer of that size is near its peak rate), at most kMaxBands
 int64_t pipeline_band_bytes();  // gi_set_pipeline_band_bytes(), default 32 MB (api.cu)
 int64_t fixup_list_capacity();  // gi_set_fixup_list_capacity(), default 4 Mi targets (api.cu)
+double sliver_guard_quality();  // gi_set_sliver_guard(), default 0 = off (api.cu, barycentric.cu sliver_quality)
 inline int plan_bands(int64_t extent, int64_t bytes) {
   int64_t nb = bytes / pipeline_band_bytes();
   if (nb > kMaxBands) nb = kMaxBands;

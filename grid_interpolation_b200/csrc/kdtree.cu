@@ -416,6 +416,8 @@ template <class R> struct KdArgs {
   R* tk_d;             // k > 32: neighbour lists in scratch memory (topk.cuh, KC = 0), k x tk_stride
   int* tk_id;
   int64_t tk_stride;
+  PointsView<R> tgt;   // scattered targets (num_tgt > 0): thread i takes target i instead of a grid node
+  int64_t num_tgt;
 };
 
 template <class R> struct alignas(16) StackEntry {
@@ -463,12 +465,19 @@ __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = w.f0 + blockIdx.x * 32 + wid * 8 + (lane & 7);
   const int s = w.s0 + blockIdx.y * 4 + (lane >> 3);
-  const bool active = f < w.f1 && s < w.s1;
+  const bool scattered = a.num_tgt > 0;  // the reference is grid-only (interpolation.f90:154-158); SURVEY 8f
+  const int64_t ti = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool active = scattered ? ti < a.num_tgt : (f < w.f1 && s < w.s1);
   unsigned visits = 0;
   if (active) {
-    const int ix = w.fast_is_y ? s : f, iy = w.fast_is_y ? f : s;
-    const R tx = __ldg((w.fast_is_y ? w.slow_axis : w.fast_axis) + ix);   // interpolation.f90:158
-    const R ty = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
+    R tx, ty;
+    if (scattered) {
+      a.tgt.xy(ti, tx, ty);
+    } else {
+      const int ix = w.fast_is_y ? s : f, iy = w.fast_is_y ? f : s;
+      tx = __ldg((w.fast_is_y ? w.slow_axis : w.fast_axis) + ix);         // interpolation.f90:158
+      ty = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
+    }
     TopK<R, KC> tk;
     if constexpr (KC == 0)
       tk.bind(a.tk_d, a.tk_id, a.tk_stride, ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x);
@@ -515,7 +524,7 @@ __global__ void __launch_bounds__(128) kd_query_kernel(const KdArgs<R> a) {
       }
     }
     // IDW (interpolation.f90:164-178); rank i of the list lives in slot tk.base + i
-    const int64_t o = (int64_t)(s - w.s0) * w.nf() + (f - w.f0);
+    const int64_t o = scattered ? ti : (int64_t)(s - w.s0) * w.nf() + (f - w.f0);
     R numerator = R(0), denominator = R(0), first_val = R(0), first_d2 = R(0);
     auto take = [&](int rank, int pos, R d2r) {
       const R dist = sqrt(d2r);
@@ -594,6 +603,7 @@ int kd_query_window(const KdTreeDev<R>& t, const R* x_axis, int len_x, const R* 
   GI_REQUIRE(grid.y <= 65535, "window too tall for one launch");
   const int prune = (flags & GI_KD_EXACT_PRUNE) ? 2 : ((flags & GI_KD_REFERENCE_VISITS) ? 1 : 0);
   a.tk_d = nullptr; a.tk_id = nullptr; a.tk_stride = 0;
+  a.tgt = PointsView<R>{nullptr, 0, 0}; a.num_tgt = 0;
   if (k <= 4) launch_query<R, 4>(a, prune, grid, st);
   else if (k <= 8) launch_query<R, 8>(a, prune, grid, st);
   else if (k <= 16) launch_query<R, 16>(a, prune, grid, st);
@@ -624,7 +634,69 @@ int kd_query_window(const KdTreeDev<R>& t, const R* x_axis, int len_x, const R* 
   return GI_OK;
 }
 
+// the same query for scattered targets (m, 2): thread i takes target i
+template <class R>
+int kd_query_points(const KdTreeDev<R>& t, const R* targets, int64_t m, int k, R* out, int32_t* nn_index, R* nn_dist2,
+                    int flags, int* status, cudaStream_t st) {
+  if (m <= 0) return GI_OK;
+  KdArgs<R> a;
+  a.win = TargetWindow<R>{nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0};
+  a.nodes = t.nodes; a.nval = t.nval; a.order = t.order; a.n = t.n; a.k = k;
+  a.counters = nullptr; a.status = status;
+  a.tk_d = nullptr; a.tk_id = nullptr; a.tk_stride = 0;
+  const int prune = (flags & GI_KD_EXACT_PRUNE) ? 2 : ((flags & GI_KD_REFERENCE_VISITS) ? 1 : 0);
+  Scratch scr(st);
+  // slices of at most 2^30 / (k * 12) targets when the lists live in scratch memory (k > 32), else 2^30 targets
+  int64_t slice = (int64_t)1 << 30;
+  if (k > 32) {
+    slice = std::max<int64_t>(128, (((int64_t)1 << 30) / ((int64_t)k * (sizeof(R) + 4))) / 128 * 128);
+    a.tk_stride = std::min<int64_t>(slice, (m + 127) / 128 * 128);
+    GI_TRY(scr.alloc(&a.tk_d, (size_t)a.tk_stride * k));
+    GI_TRY(scr.alloc(&a.tk_id, (size_t)a.tk_stride * k));
+  }
+  for (int64_t i0 = 0; i0 < m; i0 += slice) {
+    const int64_t cnt = std::min(slice, m - i0);
+    PointsView<R> tv = points_n2(targets, m, flags & GI_TARGETS_ROWMAJOR);
+    tv.base += i0 * tv.stride;
+    a.tgt = tv; a.num_tgt = cnt;
+    a.out = out + i0;
+    a.nn_index = nn_index ? nn_index + i0 * k : nullptr;
+    a.nn_dist2 = nn_dist2 ? nn_dist2 + i0 * k : nullptr;
+    const dim3 grid((unsigned)div_up(cnt, 128), 1);
+    if (k <= 4) launch_query<R, 4>(a, prune, grid, st);
+    else if (k <= 8) launch_query<R, 8>(a, prune, grid, st);
+    else if (k <= 16) launch_query<R, 16>(a, prune, grid, st);
+    else if (k <= 32) launch_query<R, 32>(a, prune, grid, st);
+    else launch_query<R, 0>(a, prune, grid, st);
+  }
+  GI_CUDA(cudaGetLastError());
+  return GI_OK;
+}
+
 }  // namespace
+
+// IDW from the k nearest neighbours (interpolation.f90:107-194) at scattered targets (m, 2) instead of grid nodes
+// (the reference is grid-only, :154-158): same tree, same traversal, same sums.
+template <class R>
+int kdtree_points_device(const R* points, int num_points, const R* data_in, const R* targets, int64_t num_targets, int k,
+                         R* data_ip, int32_t* nn_index, R* nn_dist2, int flags, cudaStream_t st) {
+  GI_REQUIRE(k >= 1, "num_neighbours must be at least 1");
+  GI_REQUIRE(num_points >= 1 && num_targets >= 0, "bad dimensions");
+  GI_TRY(ensure_device());
+  if (num_targets == 0) return GI_OK;
+  StatusSlot slot;
+  GI_TRY(get_status_slot(st, &slot));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("kd_build");
+  KdTreeDev<R> tree;
+  GI_TRY(kd_prepare<R>(scr, points, num_points, data_in, flags, &tree));
+  ph.mark("kd_query");
+  GI_TRY(kd_query_points<R>(tree, targets, num_targets, k, data_ip, nn_index, nn_dist2, flags, slot.dev, st));
+  ph.finish();
+  GI_TRY(flush_status(st, slot));
+  return GI_OK;
+}
 
 template <class R>
 int kdtree_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
@@ -818,6 +890,8 @@ int kd_build_device(const R* points, int num_points, int32_t* order_out, int fla
   template int kdtree_device<R>(const R*, int, const R*, const R*, int, const R*, int, int, int, int, R*, int32_t*, \
                                 R*, int64_t*, int, cudaStream_t);                                               \
   template int kd_build_device<R>(const R*, int, int32_t*, int, cudaStream_t);                                  \
+  template int kdtree_points_device<R>(const R*, int, const R*, const R*, int64_t, int, R*, int32_t*, R*, int,  \
+                                       cudaStream_t);                                                           \
   template int kdtree_host<R>(const R*, int, const R*, const R*, int, const R*, int, int, int, int, R*, int);    \
   template int kdtree_plan_create<R>(const R*, int, const R*, int, const R*, int, int, int, int, int, int,       \
                                      cudaStream_t, PlanBase**);

@@ -45,6 +45,15 @@ int kdtree_device(const R* points, int num_points, const R* data_in, const R* x_
 template <class R>
 int kd_build_device(const R* points, int num_points, int32_t* order, int flags, cudaStream_t st);
 
+// scattered targets (m, 2) instead of grid nodes; tri_out / outside_out / nn_* optional
+template <class R>
+int barycentric_points_device(const R* points, int num_points, const R* data_in, const int32_t* simplices,
+                              const int32_t* neighbours, int num_tri, const R* targets, int64_t num_targets,
+                              R* data_ip, int32_t* tri_out, uint8_t* outside_out, int flags, cudaStream_t st);
+template <class R>
+int kdtree_points_device(const R* points, int num_points, const R* data_in, const R* targets, int64_t num_targets, int k,
+                         R* data_ip, int32_t* nn_index, R* nn_dist2, int flags, cudaStream_t st);
+
 // GI_HOST forms of the four operators (host pointers in, synchronous): copies and compute are pipelined over
 // output bands / point chunks (common.cuh, HostPipe).  No debug outputs; api.cu falls back to "copy in, *_device,
 // copy out" when those are requested.

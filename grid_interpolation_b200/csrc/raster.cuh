@@ -269,10 +269,11 @@ raster_eval_kernel(const WalkArgs<R> a, const TileBins b, int tile_row0) {
       // (sums instead of maxima: cheaper, and a larger threshold only sends a few more nodes to the fix-up)
       const double M = fabs(ex1) + fabs(ey1) + fabs(ex2) + fabs(ey2) + fabs(ex3) + fabs(ey3);
       const double Q = fabs(vx1) + fabs(vy1) + fabs(vx2) + fabs(vy2) + fabs(vx3) + fabs(vy3) + wq;
-      const double t_rec = sizeof(R) == 8 ? __hiloint2double(g.pad & 0x7fffffff, 0)
-                                           : (double)__int_as_float(g.pad & 0x7fffffff);
+      const double t_rec = sizeof(R) == 8 ? __hiloint2double(g.pad & kThrMask, 0)
+                                           : (double)__int_as_float(g.pad & kThrMask);
       const double Tr = t_rec + 1e-10 + 32.0 * 1.1102230246251565e-16 * M * Q;
       const int thi = Tr < 1e300 ? __double2hiint(Tr) + 1 : 0x7fe00000;  // |y| < Tr  =>  high word of |y| < thi
+      const int sliver = (g.pad & kSliver) ? (int)0x80000000 : 0;  // a hull sliver keeps no node (sliver_guard)
       const int ncol = c1 - c0 + 1, n = ncol * (r1 - r0 + 1);
       tests += n;
       // the node loop, flattened over the box (lanes with boxes of different shapes stay together), on 32-bit
@@ -287,7 +288,7 @@ raster_eval_kernel(const WalkArgs<R> a, const TileBins b, int tile_row0) {
         const double y3 = __fma_rn(as3, sv, __fma_rn(af3, fv, C3));
         const int h1 = __double2hiint(y1), h2 = __double2hiint(y2), h3 = __double2hiint(y3);
         // every orientation test passes (:57-60; all three y_i >= 0, i.e. no sign bit): the node lies in this triangle
-        if ((h1 | h2 | h3) >= 0) sts_u32(ta, id);
+        if (((h1 | h2 | h3) | sliver) >= 0) sts_u32(ta, id);
         // some |y_i| below T_r: too close to an edge('s line) to call, the reference's own walk decides
         if (min(min(h1 & 0x7fffffff, h2 & 0x7fffffff), h3 & 0x7fffffff) < thi) {
           const int cell = (int)((ta - stri_s) >> 2);  // r * 128 + c

@@ -37,7 +37,7 @@ from ._lib import (GI_DEVICE, GI_FIELD_ROWMAJOR, GI_HOST, GI_KD_REFERENCE_VISITS
 __all__ = ["bilinear", "idw_kdtree", "idw_esrg_nearest", "barycentric_interpolation",
            "barycentric_interpolation_ex", "idw_kdtree_ex", "idw_esrg_nearest_ex", "kd_build",
            "assign_points_to_cells", "fill_nearest_neighbour", "pinned_empty", "pinned_copy",
-           "set_profiling", "set_pipeline_band_bytes", "set_fixup_list_capacity", "release_workspace", "pinned_trim",
+           "set_profiling", "set_pipeline_band_bytes", "set_fixup_list_capacity", "set_sliver_guard", "barycentric_points", "idw_kdtree_points", "release_workspace", "pinned_trim",
            "last_timings", "BarycentricPlan", "KdTreePlan", "EsrgPlan"]
 
 _F64 = np.dtype(np.float64)
@@ -465,6 +465,84 @@ def barycentric_interpolation(points, data_in, x_axis, y_axis, simplices, neighb
 
 
 # -------------------------------------------------------------------------------------------------
+# scattered targets: the reference interpolates to grid nodes only
+# -------------------------------------------------------------------------------------------------
+def barycentric_points(points, data_in, simplices, neighbours, targets, *, debug=False, dtype=np.float64, sync=True):
+    """barycentric_interpolation (interpolation.f90:298-416) at scattered ``targets`` (num_targets, 2) instead of
+    grid nodes: same visibility walk, same weights.  A target outside the convex hull takes the value at the closest
+    location on the mesh (interpolation.f90:292-293), found by following the hull.  Returns data_ip (num_targets,);
+    debug=True also returns the 1-based triangle the value was evaluated in and the outside-hull flags."""
+    rt, suf = _real(dtype)
+    with _Call(points) as c:
+        p = c.arg(points, rt, 2, "points"); d = c.arg(data_in, rt, 1, "data_in")
+        s = c.arg(simplices, np.dtype(np.int32), 2, "simplices")
+        nb = c.arg(neighbours, np.dtype(np.int32), 2, "neighbours")
+        tg = c.arg(targets, rt, 2, "targets")
+        if p.shape[1] != 2:
+            raise ValueError(f"points must have shape (num_points, 2), got {p.shape}")
+        n, t = p.shape[0], s.shape[0]
+        if d.shape != (n,):
+            raise ValueError(f"data_in must have shape (num_points,) = {(n,)}, got {d.shape}")
+        if s.shape != (t, 3) or nb.shape != (t, 3):
+            raise ValueError("simplices / neighbours must have shape (num_triangles, 3)")
+        if tg.shape[1] != 2:
+            raise ValueError(f"targets must have shape (num_targets, 2), got {tg.shape}")
+        if s.rowmajor != nb.rowmajor:
+            nb = c.arg(_reorder(nb.keep, s.rowmajor), np.dtype(np.int32), 2, "neighbours")
+        m = tg.shape[0]
+        res, res_ptr, _ = c.out((m,), rt, "C")
+        tri = outside = None
+        tri_ptr = out_ptr = None
+        if debug:
+            tri, tri_ptr, _ = c.out((m,), np.int32, "C")
+            outside, out_ptr, _ = c.out((m,), np.uint8, "C")
+        flags = ((GI_POINTS_ROWMAJOR if p.rowmajor else 0) | (GI_TOPO_ROWMAJOR if s.rowmajor else 0)
+                 | (_lib.GI_TARGETS_ROWMAJOR if tg.rowmajor else 0))
+        st = getattr(lib(), "gi_barycentric_points_" + suf)(p.ptr, n, d.ptr, s.ptr, nb.ptr, t, tg.ptr, m, res_ptr, tri_ptr,
+                                                           out_ptr, flags, c.mem, c.stream)
+        c.finish(st, "barycentric_points", sync)
+        if not debug:
+            return res
+        return res, SimpleNamespace(tri=tri, outside=outside != 0)
+
+
+def idw_kdtree_points(points, data_in, targets, num_neighbours, *, debug=False, exact_prune=False, dtype=np.float64,
+                      sync=True):
+    """idw_kdtree (interpolation.f90:107-194) at scattered ``targets`` (num_targets, 2) instead of grid nodes: same
+    tree, same traversal and prune rule, same sums.  points (2, num_points) as in idw_kdtree.  debug=True also
+    returns neighbour ids (1-based, (num_targets, k)) and squared distances."""
+    rt, suf = _real(dtype)
+    with _Call(points) as c:
+        p = c.arg(points, rt, 2, "points"); d = c.arg(data_in, rt, 1, "data_in")
+        tg = c.arg(targets, rt, 2, "targets")
+        if p.shape[0] != 2:
+            raise ValueError(f"points must have shape (2, num_points), got {p.shape}")
+        n = p.shape[1]
+        if d.shape != (n,):
+            raise ValueError(f"data_in must have shape (num_points,) = {(n,)}, got {d.shape}")
+        if tg.shape[1] != 2:
+            raise ValueError(f"targets must have shape (num_targets, 2), got {tg.shape}")
+        k = int(num_neighbours)
+        if k < 1:
+            raise ValueError("num_neighbours must be at least 1")
+        m = tg.shape[0]
+        res, res_ptr, _ = c.out((m,), rt, "C")
+        nn = d2 = None
+        nn_ptr = d2_ptr = None
+        if debug:
+            nn, nn_ptr, _ = c.out((m, k), np.int32, "C")
+            d2, d2_ptr, _ = c.out((m, k), rt, "C")
+        flags = ((GI_POINTS_ROWMAJOR if p.rowmajor else 0) | (_lib.GI_TARGETS_ROWMAJOR if tg.rowmajor else 0)
+                 | (_lib.GI_KD_EXACT_PRUNE if exact_prune else 0))
+        st = getattr(lib(), "gi_idw_kdtree_points_" + suf)(p.ptr, n, d.ptr, tg.ptr, m, k, res_ptr, nn_ptr, d2_ptr, flags,
+                                                          c.mem, c.stream)
+        c.finish(st, "idw_kdtree_points", sync)
+        if not debug:
+            return res
+        return res, SimpleNamespace(nn_index=nn, nn_dist2=d2)
+
+
+# -------------------------------------------------------------------------------------------------
 # plans: geometry + target grid prepared once on the device, one call per field of nodal values
 # -------------------------------------------------------------------------------------------------
 class _Plan:
@@ -640,6 +718,13 @@ def set_profiling(on: bool) -> None:
 def set_fixup_list_capacity(targets: int) -> None:
     """Capacity of the barycentric ambiguity fix-up work list (0 = default 4 Mi targets); see gridinterp.h."""
     lib().gi_set_fixup_list_capacity(int(targets))
+
+
+def set_sliver_guard(min_quality: float) -> None:
+    """Sliver guard of barycentric_interpolation (the reference's README to-do): triangles with a hull edge whose
+    quality |2 area| / max |edge|^2 is below ``min_quality`` are not interpolated in; their targets are masked and
+    filled from the nearest neighbours.  0 = off (the reference's behaviour); see gridinterp.h."""
+    lib().gi_set_sliver_guard(float(min_quality))
 
 
 def release_workspace() -> None:

@@ -92,6 +92,7 @@ typedef enum {
                                  skipped triangles are marked, and a walk that wants to cross one is reported as
                                  GI_ERR_PACK_WINDOW by gi_stream_status(): the caller then repeats the call without
                                  the flag (GI_HOST calls do both by themselves).  Results are identical. */
+#define GI_TARGETS_ROWMAJOR 1024 /* *_points entry points: the (num_targets, 2) target array is C-order */
 #define GI_ESRG_REFERENCE_ORDER 16 /* idw_esrg_nearest: process every target in the reference's candidate order
                                       (debug).  Default: only targets with exactly equal neighbour distances,
                                       the only case in which that order changes the result. */
@@ -131,6 +132,13 @@ void gi_release_workspace(void);
  * when more targets lie within the margin band of a mesh edge the window is redone by the row-sequential walk.
  * A small value forces that path (tests).  <= 0 restores the default.  Process-wide. */
 void gi_set_fixup_list_capacity(int64_t targets);
+/* Sliver guard for barycentric_interpolation -- the reference's open to-do (README.md:41-43: "prohibiting barycentric
+ * interpolation for sliver triangles close to the edge (and filling the subsequent missing values from the nearest
+ * neighbours)").  A triangle with a hull edge whose quality |2 area| / max |edge|^2 (equilateral: 0.87) is below
+ * min_quality is not interpolated in: its targets are masked like targets outside the hull and filled by
+ * fill_nearest_neighbour (triangle_walk.f90:90-132).  0 (default) = off = the reference's behaviour.  Read when the
+ * mesh is packed (one-shot calls: every call; plans: at creation).  Process-wide. */
+void gi_set_sliver_guard(double min_quality);
 
 /* ---- multi-GPU: peer memory and the fused gather (one process per GPU) --------------------------------- */
 /* The reference is a single shared-memory process (4 OpenMP loops, interpolation.f90:62,152,249,362).  Here the
@@ -211,6 +219,32 @@ int gi_barycentric_interpolation_ex_f64(const double* points, int num_points, co
                                         double* data_ip, int32_t* tri_out, uint8_t* mask_out,
                                         int64_t* fill_src, int64_t* counters, int flags, int mem,
                                         void* stream);
+
+/* ---- scattered targets: the reference interpolates to the nodes of a regular grid only
+ * (interpolation.f90:154-158,365-371); these take any (num_targets, 2) array of target coordinates instead -------- */
+
+/* barycentric_interpolation (interpolation.f90:298-416) at scattered targets: the same visibility walk
+ * (triangle_walk.f90:24-84) from a seed grid laid over the mesh, the same weights (:385-398).  A target outside the
+ * convex hull takes the value at the CLOSEST LOCATION ON THE MESH (the behaviour the reference's header comment
+ * describes, interpolation.f90:292-293; its grid version takes the nearest node inside the hull instead): the hull is
+ * followed from the edge the walk left through until the foot of the perpendicular lies on an edge or a vertex is
+ * closest.  Optional outputs (NULL to skip): tri_out (num_targets) 1-based triangle the value was evaluated in,
+ * outside_out (num_targets) 1 = outside the hull.  flags: GI_POINTS_ROWMAJOR, GI_TOPO_ROWMAJOR, GI_TARGETS_ROWMAJOR. */
+int gi_barycentric_points_f64(const double* points, int num_points, const double* data_in, const int32_t* simplices,
+                              const int32_t* neighbours, int num_triangles, const double* targets,
+                              int64_t num_targets, double* data_ip, int32_t* tri_out, uint8_t* outside_out, int flags,
+                              int mem, void* stream);
+int gi_barycentric_points_f32(const float* points, int num_points, const float* data_in, const int32_t* simplices,
+                              const int32_t* neighbours, int num_triangles, const float* targets, int64_t num_targets,
+                              float* data_ip, int32_t* tri_out, uint8_t* outside_out, int flags, int mem, void* stream);
+/* idw_kdtree (interpolation.f90:107-194 + kd_tree.f90) at scattered targets: same tree, same traversal and prune
+ * rule, same sums.  points (2, num_points) as in gi_idw_kdtree; optional nn_index / nn_dist2 (num_targets, k). */
+int gi_idw_kdtree_points_f64(const double* points, int num_points, const double* data_in, const double* targets,
+                             int64_t num_targets, int num_neighbours, double* data_ip, int32_t* nn_index,
+                             double* nn_dist2, int flags, int mem, void* stream);
+int gi_idw_kdtree_points_f32(const float* points, int num_points, const float* data_in, const float* targets,
+                             int64_t num_targets, int num_neighbours, float* data_ip, int32_t* nn_index, float* nn_dist2,
+                             int flags, int mem, void* stream);
 
 /* Row band [row_begin, row_end) of barycentric_interpolation computed on the current device and stored at its
  * place in num_fields (<= GI_MAX_GATHER_FIELDS) FULL (len_y, len_x) fields in the layout `flags` selects:

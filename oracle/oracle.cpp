@@ -596,6 +596,12 @@ int fill_nearest_neighbour(const uint8_t* mask_outside, int len_x, int len_y, Re
 // debug outputs (all optional, (len_y,len_x) col-major): tri_out (1-based triangle the walk ended in),
 // mask_out (1 = outside hull), fill_src; scalars: ind_tri_start, iters_tot, fill level max
 // ---------------------------------------------------------------------------
+// Sliver guard: NOT in the reference -- its README lists it as a to-do (README.md:41-43).  0 = off.  With a
+// threshold q > 0 a target found in a triangle that has a hull edge and whose quality |denom| / max |edge|^2
+// (denom as in interpolation.f90:385-386) is below q is masked like a target outside the hull and later filled by
+// fill_nearest_neighbour.  The CUDA library has the same switch (gi_set_sliver_guard) and the same expression.
+static double g_sliver_guard = 0.0;
+
 template <class Real>
 int barycentric_interpolation(const Real* points /*(n,2)*/, int num_points, const Real* data_in,
                               const Real* x_axis, int len_x, const Real* y_axis, int len_y,
@@ -659,6 +665,18 @@ int barycentric_interpolation(const Real* points /*(n,2)*/, int num_points, cons
         const Real v2x = px[i2 - 1], v2y = py[i2 - 1];
         const Real v3x = px[i3 - 1], v3y = py[i3 - 1];
         const Real denom = (v2y - v3y) * (v1x - v3x) + (v3x - v2x) * (v1y - v3y);
+        if (g_sliver_guard > 0.0 &&
+            (CM2(neighbours, num_triangles, ind_tri, 1) == neighbour_none ||
+             CM2(neighbours, num_triangles, ind_tri, 2) == neighbour_none ||
+             CM2(neighbours, num_triangles, ind_tri, 3) == neighbour_none)) {
+          const Real l1 = (v2x - v1x) * (v2x - v1x) + (v2y - v1y) * (v2y - v1y);
+          const Real l2 = (v3x - v2x) * (v3x - v2x) + (v3y - v2y) * (v3y - v2y);
+          const Real l3 = (v1x - v3x) * (v1x - v3x) + (v1y - v3y) * (v1y - v3y);
+          if (std::fabs(denom) / std::max(std::max(l1, l2), l3) < (Real)g_sliver_guard) {
+            CM2(mask_outside, len_y, ind_y, ind_x) = 1;
+            continue;
+          }
+        }
         const Real w1 = ((v2y - v3y) * (tx - v3x) + (v3x - v2x) * (ty - v3y)) / denom;
         const Real w2 = ((v3y - v1y) * (tx - v3x) + (v1x - v3x) * (ty - v3y)) / denom;
         const Real w3 = Real(1) - w1 - w2;
@@ -679,6 +697,132 @@ int barycentric_interpolation(const Real* points /*(n,2)*/, int num_points, cons
   return status;
 }
 
+// ===========================================================================
+// Extensions: scattered targets.  NOT in the reference (it interpolates to grid nodes only,
+// interpolation.f90:154-158,365-371); restated here from the library's definition (include/gridinterp.h,
+// gi_barycentric_points / gi_idw_kdtree_points) so that the GPU kernels have an independent checker: the
+// reference's own building blocks (find_triangle's tests, the weights of :385-398, nearest_neighbours and
+// the IDW sums of :164-178) applied to a list of targets instead of the nodes of a grid.
+// ===========================================================================
+template <class Real>
+int barycentric_points(const Real* points /*(n,2)*/, int num_points, const Real* data_in, const int* simplices,
+                       const int* neighbours, int num_triangles, const Real* targets /*(m,2) col-major*/,
+                       int64_t num_targets, Real* data_ip, int* tri_out, uint8_t* outside_out) {
+  if (num_points < 3 || num_triangles < 1 || num_targets < 0) return ORC_BAD_ARG;
+  const Real* px = points;
+  const Real* py = points + num_points;
+  const Real* tgx = targets;
+  const Real* tgy = targets + num_targets;
+  const int iter_cap = 4 * num_triangles + 16;
+  int status = ORC_OK;
+  auto S = [&](int t, int i) { return CM2(simplices, num_triangles, t, i + 1); };   // vertex i (0..2) of triangle t
+  auto N = [&](int t, int i) { return CM2(neighbours, num_triangles, t, i + 1); };  // neighbour opposite vertex i
+#pragma omp parallel for schedule(static) reduction(max : status)
+  for (int64_t it = 0; it < num_targets; ++it) {
+    const Real tx = tgx[it], ty = tgy[it];
+    // visibility walk (triangle_walk.f90:44-84) from triangle 1; the failing hull edge is remembered
+    int t = 1, edge = -1;
+    for (int iters = 1;; ++iters) {
+      if (iters > iter_cap) { status = std::max(status, (int)ORC_ITER_CAP); break; }
+      int i;
+      for (i = 0; i < 3; ++i) {
+        const int v1 = S(t, i), v2 = S(t, (i + 1) % 3);
+        if (triangle_point_outside(px[v1 - 1], py[v1 - 1], px[v2 - 1], py[v2 - 1], tx, ty)) break;
+      }
+      if (i == 3) break;
+      const int nxt = N(t, (i + 2) % 3);                                    // :66-71
+      if (nxt == 0) { edge = i; break; }
+      t = nxt;
+    }
+    // outside the hull: the closest location on the mesh, following the hull from the edge the walk left through
+    Real qx = tx, qy = ty;
+    if (edge >= 0) {
+      int e = edge, dir = 0;
+      for (int iters = 0;; ++iters) {
+        const int a = S(t, e), b = S(t, (e + 1) % 3);
+        const Real abx = px[b - 1] - px[a - 1], aby = py[b - 1] - py[a - 1];
+        const Real len2 = abx * abx + aby * aby;
+        const Real tt = len2 > Real(0) ? ((tx - px[a - 1]) * abx + (ty - py[a - 1]) * aby) / len2 : Real(0);
+        if (iters >= iter_cap) { status = std::max(status, (int)ORC_ITER_CAP); qx = px[a - 1]; qy = py[a - 1]; break; }
+        if (tt < Real(0)) {
+          if (dir > 0) { qx = px[a - 1]; qy = py[a - 1]; break; }
+          dir = -1;
+          int k = (e + 2) % 3;                                              // the edge entering a
+          while (N(t, (k + 2) % 3) != 0) {
+            t = N(t, (k + 2) % 3);
+            const int j = S(t, 0) == a ? 0 : (S(t, 1) == a ? 1 : 2);
+            k = (j + 2) % 3;
+          }
+          e = k;
+        } else if (tt > Real(1)) {
+          if (dir < 0) { qx = px[b - 1]; qy = py[b - 1]; break; }
+          dir = 1;
+          int k = (e + 1) % 3;                                              // the edge leaving b
+          while (N(t, (k + 2) % 3) != 0) {
+            t = N(t, (k + 2) % 3);
+            const int j = S(t, 0) == b ? 0 : (S(t, 1) == b ? 1 : 2);
+            k = j;
+          }
+          e = k;
+        } else {
+          qx = px[a - 1] + tt * abx; qy = py[a - 1] + tt * aby;
+          break;
+        }
+      }
+    }
+    const int i1 = S(t, 0), i2 = S(t, 1), i3 = S(t, 2);                      // interpolation.f90:377-398
+    const Real v1x = px[i1 - 1], v1y = py[i1 - 1], v2x = px[i2 - 1], v2y = py[i2 - 1], v3x = px[i3 - 1], v3y = py[i3 - 1];
+    const Real denom = (v2y - v3y) * (v1x - v3x) + (v3x - v2x) * (v1y - v3y);
+    const Real w1 = ((v2y - v3y) * (qx - v3x) + (v3x - v2x) * (qy - v3y)) / denom;
+    const Real w2 = ((v3y - v1y) * (qx - v3x) + (v1x - v3x) * (qy - v3y)) / denom;
+    const Real w3 = Real(1) - w1 - w2;
+    data_ip[it] = data_in[i1 - 1] * w1 + data_in[i2 - 1] * w2 + data_in[i3 - 1] * w3;
+    if (tri_out) tri_out[it] = t;
+    if (outside_out) outside_out[it] = edge >= 0 ? 1 : 0;
+  }
+  return status;
+}
+
+template <class Real>
+int idw_kdtree_points(const Real* points /*(2,num_points)*/, int num_points, const Real* data_in,
+                      const Real* targets /*(m,2) col-major*/, int64_t num_targets, int num_neighbours, Real* data_ip,
+                      int* nn_index /*(m,k) row-major*/, Real* nn_dist2) {
+  if (num_points < 1 || num_neighbours < 1 || num_targets < 0) return ORC_BAD_ARG;
+  std::vector<int> index(num_points);
+  for (int i = 0; i < num_points; ++i) index[i] = i + 1;
+  KdTree<Real> tree;
+  tree.nodes.reserve(num_points);
+  tree.root = build_kd_tree(tree, points, num_points, 0, index.data());      // interpolation.f90:144
+#pragma omp parallel for schedule(static)
+  for (int64_t it = 0; it < num_targets; ++it) {
+    std::vector<Real> neighbours((size_t)3 * num_neighbours, K<Real>::sentinel());   // :159
+    std::vector<int> neighbours_index(num_neighbours, 0);
+    const Real point_target[2] = {targets[it], targets[num_targets + it]};
+    nearest_neighbours(tree, tree.root, point_target, 0, neighbours.data(), num_neighbours, neighbours_index.data(),
+                       (int64_t*)nullptr);                                    // :160
+    Real out;
+    if (std::sqrt(neighbours[2]) <= K<Real>::tiny_e4()) {                    // :164-169
+      out = data_in[neighbours_index[0] - 1];
+    } else {
+      Real numerator = Real(0), denominator = Real(0);                       // :171-178
+      for (int i = 1; i <= num_neighbours; ++i) {
+        const int id = neighbours_index[i - 1];
+        const Real dist = std::sqrt(neighbours[(size_t)(i - 1) * 3 + 2]);
+        const Real v_i = id >= 1 ? data_in[id - 1] : Real(0);
+        numerator = numerator + (v_i / dist);
+        denominator = denominator + (Real(1) / dist);
+      }
+      out = numerator / denominator;
+    }
+    data_ip[it] = out;
+    if (nn_index)
+      for (int i = 0; i < num_neighbours; ++i) nn_index[(size_t)it * num_neighbours + i] = neighbours_index[i];
+    if (nn_dist2)
+      for (int i = 0; i < num_neighbours; ++i) nn_dist2[(size_t)it * num_neighbours + i] = neighbours[(size_t)i * 3 + 2];
+  }
+  return ORC_OK;
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -689,6 +833,7 @@ int barycentric_interpolation(const Real* points /*(n,2)*/, int num_points, cons
 
 ORC_EXPORT void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 ORC_EXPORT int orc_get_max_threads() { return omp_get_max_threads(); }
+ORC_EXPORT void orc_set_sliver_guard(double q) { g_sliver_guard = q > 0.0 ? q : 0.0; }
 
 #define ORC_DEFINE(SUF, Real)                                                                        \
   ORC_EXPORT int orc_bilinear_##SUF(const Real* x_axis, int len_x, const Real* y_axis, int len_y,    \
@@ -737,6 +882,19 @@ ORC_EXPORT int orc_get_max_threads() { return omp_get_max_threads(); }
                                   grid_spac, num_neighbours, data_ip, nn_index, nn_dist, level_max,  \
                                   list_max, t_build, t_query);                                       \
   }                                                                                                  \
+  ORC_EXPORT int orc_barycentric_points_##SUF(const Real* points, int num_points, const Real* data_in,    \
+                                              const int* simplices, const int* neighbours, int num_triangles, \
+                                              const Real* targets, int64_t num_targets, Real* data_ip,      \
+                                              int* tri_out, uint8_t* outside_out) {                         \
+    return barycentric_points<Real>(points, num_points, data_in, simplices, neighbours, num_triangles,     \
+                                    targets, num_targets, data_ip, tri_out, outside_out);                  \
+  }                                                                                                         \
+  ORC_EXPORT int orc_idw_kdtree_points_##SUF(const Real* points, int num_points, const Real* data_in,       \
+                                             const Real* targets, int64_t num_targets, int num_neighbours, \
+                                             Real* data_ip, int* nn_index, Real* nn_dist2) {               \
+    return idw_kdtree_points<Real>(points, num_points, data_in, targets, num_targets, num_neighbours,      \
+                                   data_ip, nn_index, nn_dist2);                                            \
+  }                                                                                                         \
   ORC_EXPORT int orc_barycentric_interpolation_##SUF(                                                \
       const Real* points, int num_points, const Real* data_in, const Real* x_axis, int len_x,        \
       const Real* y_axis, int len_y, const int* simplices, const int* neighbours, int num_triangles, \

@@ -50,6 +50,11 @@ def set_num_threads(n: int) -> None:
     lib().orc_set_num_threads(int(n))
 
 
+def set_sliver_guard(min_quality: float) -> None:
+    """The library's opt-in sliver guard (NOT in the reference: README.md:41-43 lists it as a to-do), see oracle.cpp."""
+    lib().orc_set_sliver_guard(C.c_double(float(min_quality)))
+
+
 def get_max_threads() -> int:
     return int(lib().orc_get_max_threads())
 
@@ -209,6 +214,36 @@ def barycentric_interpolation(points, data_in, x_axis, y_axis, simplices, neighb
                                     iters_tot=iters.value, fill_level_max=lvl.value, t_start=ts.value,
                                     t_walk=tw.value, t_fill=tf.value)
     return out
+
+
+def barycentric_points(points, data_in, simplices, neighbours, targets, dtype=np.float64, debug=False):
+    """Extension (not in the reference, which is grid-only): barycentric interpolation at scattered targets (m, 2);
+    outside the hull the closest location on the mesh.  See oracle.cpp."""
+    suf, _ = _suffix(dtype)
+    points = _f(points, dtype); data_in = _f(data_in, dtype); targets = _f(targets, dtype)
+    simplices = _f(simplices, np.int32); neighbours = _f(neighbours, np.int32)
+    n, t, m = points.shape[0], simplices.shape[0], targets.shape[0]
+    out = np.empty(m, dtype=dtype)
+    tri = np.empty(m, np.int32) if debug else None
+    outside = np.empty(m, np.uint8) if debug else None
+    st = getattr(lib(), "orc_barycentric_points_" + suf)(_p(points), C.c_int(n), _p(data_in), _p(simplices), _p(neighbours),
+                                                        C.c_int(t), _p(targets), C.c_int64(m), _p(out), _p(tri), _p(outside))
+    _check(st, "barycentric_points")
+    return (out, SimpleNamespace(tri=tri, outside=outside.astype(bool))) if debug else out
+
+
+def idw_kdtree_points(points, data_in, targets, num_neighbours, dtype=np.float64, debug=False):
+    """Extension (not in the reference): idw_kdtree at scattered targets (m, 2); points (2, n).  See oracle.cpp."""
+    suf, _ = _suffix(dtype)
+    points = _f(points, dtype); data_in = _f(data_in, dtype); targets = _f(targets, dtype)
+    n, m, k = points.shape[1], targets.shape[0], int(num_neighbours)
+    out = np.empty(m, dtype=dtype)
+    nn = np.empty((m, k), np.int32) if debug else None
+    d2 = np.empty((m, k), dtype) if debug else None
+    st = getattr(lib(), "orc_idw_kdtree_points_" + suf)(_p(points), C.c_int(n), _p(data_in), _p(targets), C.c_int64(m),
+                                                       C.c_int(k), _p(out), _p(nn), _p(d2))
+    _check(st, "idw_kdtree_points")
+    return (out, SimpleNamespace(nn_index=nn, nn_dist2=d2)) if debug else out
 
 
 def find_triangle(points, simplices, neighbours, target, ind_tri, dtype=np.float64):

@@ -195,6 +195,36 @@ def test_barycentric_grid_rows_along_mesh_edges_for_hundreds_of_columns():
             assert_values(plan(data), want)
 
 
+@pytest.mark.parametrize("q", [0.05, 0.3])
+def test_barycentric_sliver_guard(c1, q):
+    """The reference's README to-do (README.md:41-43), opt-in: hull slivers below the quality threshold are not
+    interpolated in, their targets are masked and filled from the nearest neighbours -- same switch, same
+    expression, same bits in the oracle and the library; every API door."""
+    plain, p = orc.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                             c1.neighbours, debug=True)
+    orc.set_sliver_guard(q); ip.set_sliver_guard(q)
+    try:
+        want, w = orc.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                                c1.neighbours, debug=True)
+        assert w.mask.sum() > p.mask.sum() and (w.mask | ~p.mask).all()      # the guard only adds masked targets
+        assert np.array_equal(want[~w.mask], plain[~w.mask])
+        for order in ("F", "C"):
+            got, g = ip.barycentric_interpolation_ex(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                                     c1.neighbours, order=order, debug=True)
+            assert np.array_equal(g.mask, w.mask) and np.array_equal(g.fill_src, w.fill_src)
+            assert_values(got, want)
+        assert_values(ip.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                                   c1.neighbours), want)
+        with ip.BarycentricPlan(c1.points, c1.x_axis, c1.y_axis, c1.simplices, c1.neighbours) as plan:
+            assert_values(plan(c1.data_pts), want)
+        rows, halo = (0, 40), 12
+        band = ip.barycentric_interpolation_ex(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                               c1.neighbours, rows=rows, halo=halo, order="C")
+        assert_values(band, want[rows[0]:rows[1]])
+    finally:
+        orc.set_sliver_guard(0.0); ip.set_sliver_guard(0.0)
+
+
 def test_barycentric_bad_topology_is_reported(c1):
     bad = c1.simplices.copy(); bad[7, 1] = c1.points.shape[0] + 5
     with pytest.raises(RuntimeError, match="out of range"):

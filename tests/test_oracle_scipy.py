@@ -108,3 +108,75 @@ def test_f32_build_tracks_f64(c1):
     a = orc.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, 6)
     b = orc.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.grid_spac, 6, dtype=np.float32)
     assert b.dtype == np.float32 and np.abs(a - b).max() < 1e-3
+
+
+def test_sliver_guard_extension_masks_hull_slivers_only(c1):
+    """The library's opt-in sliver guard (the reference's README to-do, README.md:41-43) as the oracle states it:
+    off by default; on, it only adds masked targets, all of them in triangles with a hull edge."""
+    plain, p = orc.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                             c1.neighbours, debug=True)
+    orc.set_sliver_guard(0.3)
+    try:
+        got, g = orc.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices,
+                                               c1.neighbours, debug=True)
+    finally:
+        orc.set_sliver_guard(0.0)
+    added = g.mask & ~p.mask
+    assert added.any() and (g.mask | ~p.mask).all()
+    assert np.array_equal(got[~g.mask], plain[~g.mask])
+    hull = (c1.neighbours == 0).any(axis=1)
+    assert hull[g.tri[added] - 1].all()
+    again = orc.barycentric_interpolation(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, c1.simplices, c1.neighbours)
+    assert np.array_equal(again, plain)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# extensions: scattered targets (the reference is grid-only) -- the oracle's restatement against scipy
+# ------------------------------------------------------------------------------------------------------------
+def _closest_on_hull_brute(points, hull_edges, p):
+    best, q = np.inf, None
+    for a, b in hull_edges:
+        ab = points[b] - points[a]
+        t = np.clip(np.dot(p - points[a], ab) / np.dot(ab, ab), 0.0, 1.0)
+        c = points[a] + t * ab
+        d = np.dot(p - c, p - c)
+        if d < best:
+            best, q = d, c
+    return q
+
+
+def test_scattered_barycentric_extension_matches_scipy(c1):
+    from scipy.interpolate import LinearNDInterpolator
+    from scipy.spatial import ConvexHull
+    rng = np.random.default_rng(12)
+    lo, hi = c1.points.min(0), c1.points.max(0)
+    targets = rng.uniform(lo - 0.15 * (hi - lo), hi + 0.15 * (hi - lo), (4000, 2))
+    got, g = orc.barycentric_points(c1.points, c1.data_pts, c1.simplices, c1.neighbours, targets, debug=True)
+    lin = LinearNDInterpolator(c1.points, c1.data_pts)
+    want = lin(targets)
+    inside = ~np.isnan(want)
+    assert inside.sum() > 1000 and (~inside).sum() > 500
+    assert np.array_equal(g.outside, ~inside) or (g.outside != ~inside).sum() <= 2      # margin band only
+    ok = inside & ~g.outside
+    np.testing.assert_allclose(got[ok], want[ok], rtol=1e-9, atol=1e-9)
+    # outside the hull: the value at the closest point of the hull
+    hull = ConvexHull(c1.points)
+    edges = [(s[0], s[1]) for s in hull.simplices]
+    for i in np.flatnonzero(g.outside & ~inside)[:150]:
+        q = _closest_on_hull_brute(c1.points, edges, targets[i])
+        np.testing.assert_allclose(got[i], lin(q[None] * (1 - 1e-13) + c1.points.mean(0) * 1e-13)[0], rtol=1e-6, atol=1e-6)
+
+
+def test_scattered_kdtree_extension_matches_grid_version_and_scipy(c1):
+    from scipy.spatial import cKDTree
+    k = 6
+    scale = 10.0                                         # the regime in which the reference's prune rule is exact
+    pts = np.asfortranarray(c1.points.T * scale)
+    xa, ya = c1.x_axis[::5] * scale, c1.y_axis[::5] * scale
+    grid, w = orc.idw_kdtree(pts, c1.data_pts, xa, ya, k, debug=True)
+    xx, yy = np.meshgrid(xa, ya)
+    targets = np.stack([xx.ravel(), yy.ravel()], 1)
+    got, g = orc.idw_kdtree_points(pts, c1.data_pts, targets, k, debug=True)
+    assert np.array_equal(got.reshape(grid.shape), grid)                       # same targets, same bits
+    d, idx = cKDTree(pts.T).query(targets, k=k)
+    assert np.array_equal(g.nn_index - 1, idx)
