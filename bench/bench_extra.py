@@ -214,6 +214,43 @@ def run(args, rank, world, local_rank):
                      "value": targets_rank * world * args.steps / (float(pms.item()) * 1e-3), "unit": "targets/s"}
         plan.close()
 
+    # C5 with the points in the Morton order of their cells (north_star: Morton-ordered targets, Morton ranges per
+    # GPU).  The order comes from the library (timed); the points are moved once, as an ingest step would (not
+    # timed); the kernel is timed on the ordered points; the un-permutation of the results (torch index_put) is
+    # timed separately.  Not the headline: `value` above is the reference's call on the points as they come.
+    morton = None
+    if wl == "c5":
+        d_all = torch.as_tensor(np.stack([w.px, w.py], 0), device=dev).t()      # every rank orders the whole set
+        def timed(fn, reps):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                r = fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps, r
+        order_ms, order = timed(lambda: ip.bilinear_morton_order(d_x, d_y, d_all, sync=False), 3)
+        mine = order[lo:hi].long()                                               # this rank's Morton range
+        d_pm = d_all[mine].t().contiguous().t()                                  # (n, 2) in the reference's F order
+        del d_all
+        m_out = torch.empty(targets_rank, dtype=torch.float64, device=dev)
+        sync_all()
+        k_ms, _ = timed(lambda: ip.bilinear(d_x, d_y, d_f, d_pm, out=m_out, sync=False), args.steps)
+        kms_t = torch.tensor([k_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(kms_t, op=dist.ReduceOp.MAX)
+        back = torch.empty(n if world == 1 else targets_rank, dtype=torch.float64, device=dev)
+        idx = mine if world == 1 else torch.argsort(mine)
+        u_ms, _ = timed(lambda: back.index_copy_(0, idx, m_out) if world == 1 else back.copy_(m_out[idx]), 3)
+        if world == 1:
+            assert torch.equal(back, d_out), "Morton-ordered run, un-permuted, differs from the direct run"
+        morton = {"order_ms": order_ms, "kernel_ms": float(kms_t.item()), "unpermute_ms": u_ms,
+                  "value_kernel_only": targets_rank * world / (float(kms_t.item()) * 1e-3), "unit": "targets/s",
+                  "note": "points pre-ordered along the Z curve of 16 x 16-node blocks (gi_bilinear_morton_order); "
+                          "ranks take contiguous ranges of that order"}
+        del d_pm, m_out, back, order, mine, idx
+        torch.cuda.empty_cache()
+
     e2e = None
     if not args.no_e2e:
         e_steps = max(2, min(args.steps, 5))
@@ -251,6 +288,7 @@ def run(args, rank, world, local_rank):
                           "config": {"workload": name, "l2": "inputs + outputs per step exceed the 126 MB L2",
                                      "scale": sc},
                           "phase_ms": phase_ms, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "plan": plan_line,
+                          "morton": morton,
                           "clocks": clk, "gpu_launches": launches * args.steps}))
     if world > 1:
         dist.barrier()

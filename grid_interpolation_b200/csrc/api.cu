@@ -324,6 +324,29 @@ static int fill_api(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64
   return read_status(st, true);
 }
 
+template <class R>
+static int bilinear_morton_order_api(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* points,
+                                     int64_t n, int32_t* order, int flags, int mem, void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(x_axis && y_axis && (points || n == 0) && (order || n == 0), "null pointer");
+  if (mem == GI_DEVICE)
+    return bilinear_morton_order_device<R>(x_axis, len_x, y_axis, len_y, points, n, order, flags, (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  if (n == 0) return GI_OK;
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  R *dx, *dy, *dp;
+  int32_t* dorder;
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  GI_TRY(to_device(scr, points, (size_t)2 * n, &dp));
+  GI_TRY(scr.alloc(&dorder, (size_t)n));
+  GI_TRY(bilinear_morton_order_device<R>(dx, len_x, dy, len_y, dp, n, dorder, flags, st));
+  GI_TRY(to_host(st, order, dorder, (size_t)n));
+  return read_status(st, true);
+}
+
 // scattered targets: host form = copy in, device form, copy out (synchronous)
 template <class R>
 static int barycentric_points_api(const R* points, int num_points, const R* data_in, const int32_t* simplices,
@@ -767,6 +790,12 @@ GI_API void gi_plan_destroy(gi_plan* plan) {
                                                   int32_t* indptr, int flags, int mem, void* stream) {             \
     return esrg_bin_api<R>(points, num_points, x_axis, len_x, y_axis, len_y, grid_spac, index_of_pts, indptr,      \
                            flags, mem, stream);                                                                     \
+  }                                                                                                                 \
+  GI_API int gi_bilinear_morton_order_##SUF(const R* x_axis, int len_x, const R* y_axis, int len_y,               \
+                                            const R* points, int64_t num_points, int32_t* order, int flags,      \
+                                            int mem, void* stream) {                                              \
+    return bilinear_morton_order_api<R>(x_axis, len_x, y_axis, len_y, points, num_points, order, flags, mem,     \
+                                        stream);                                                                  \
   }                                                                                                                 \
   GI_API int gi_barycentric_points_##SUF(const R* points, int num_points, const R* data_in,                        \
                                          const int32_t* simplices, const int32_t* neighbours, int num_triangles,  \

@@ -12,7 +12,10 @@
 // (interpolation.f90:49-58) -- floating-point addition is not associative, so the sum is done by a single
 // thread per axis in the reference's order; weights and the final sum follow interpolation.f90:81-93 with
 // FMA contraction disabled.
+#include <algorithm>
+
 #include "kernels.cuh"
+#include "radix.cuh"
 
 namespace gi {
 namespace {
@@ -340,6 +343,77 @@ int bilinear_host(const R* x_axis, int len_x, const R* y_axis, int len_y, const 
   GI_CUDA(cudaStreamSynchronize(st));
   return GI_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Morton order of the points (north_star: "Morton-ordered targets", "Morton ranges" per GPU).  bilinear's gathers
+// are random reads from a field far larger than L2 (8.7 DRAM sectors per point, see above); points that arrive
+// in the Morton order of their cells read each part of the field once, and a contiguous range of that order
+// touches a compact part of the field -- the natural shard for several GPUs.  This entry point only computes
+// the order (cell as interpolation.f90:67,73; 16 x 16-node blocks along a Z curve; stable radix sort): whether
+// the points are moved, and when, is the caller's business (an ingest-time decision; the un-permutation of
+// 1e8 results costs as much as the gathers it saves, profiles/r01_kd_esrg_variants.md).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ unsigned spread_bits16(unsigned v) {  // 16 bits -> every other bit of 32
+  v = (v | (v << 8)) & 0x00ff00ffu;
+  v = (v | (v << 4)) & 0x0f0f0f0fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+template <class R>
+__global__ void __launch_bounds__(256)
+morton_key_kernel(const R* __restrict__ x_axis, int len_x, const R* __restrict__ y_axis, int len_y, PointsView<R> pts,
+                  int n, const R* __restrict__ inv, int shift, unsigned key_oob, unsigned* __restrict__ keys,
+                  int* __restrict__ ids) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const R fx = floor((pts.x(i) - __ldg(x_axis)) * __ldg(inv));            // interpolation.f90:67
+  const R fy = floor((pts.y(i) - __ldg(y_axis)) * __ldg(inv + 1));        // :73
+  const bool ok = fx >= R(0) && fx < R(len_x - 1) && fy >= R(0) && fy < R(len_y - 1);
+  keys[i] = ok ? (spread_bits16((unsigned)fx >> shift) | (spread_bits16((unsigned)fy >> shift) << 1)) : key_oob;
+  ids[i] = i;
+}
+}  // namespace
+
+template <class R>
+int bilinear_morton_order_device(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* points,
+                                 int64_t num_points, int32_t* order, int flags, cudaStream_t st) {
+  GI_REQUIRE(len_x >= 2 && len_y >= 2, "axes need at least 2 nodes");
+  GI_REQUIRE(num_points >= 0 && num_points < (int64_t)0x7fffffff, "num_points must be below 2^31");
+  GI_TRY(ensure_device());
+  if (num_points == 0) return GI_OK;
+  const int n = (int)num_points;
+  Scratch scr(st);
+  R* inv;
+  GI_TRY(scr.alloc(&inv, 2));
+  axis_inv_spacing_kernel<R><<<2, 256, 0, st>>>(x_axis, len_x, y_axis, len_y, inv);
+  // 16 x 16-node blocks, coarser if the Z value of the last block would not fit 31 bits
+  int shift = 4;
+  while ((std::max(len_x, len_y) >> shift) >= (1 << 15)) ++shift;
+  int bits = 0;
+  while (((std::max(len_x, len_y) - 1) >> shift) >> bits) ++bits;
+  const unsigned key_oob = 1u << (2 * bits);              // points outside the grid sort last
+  const int passes = (2 * bits + 1 + 7) / 8;
+  unsigned *keys, *keys_tmp, *keys_sorted;
+  int *ids, *ids_tmp, *ids_sorted, *hist;
+  GI_TRY(scr.alloc(&keys, (size_t)n));
+  GI_TRY(scr.alloc(&keys_tmp, (size_t)n));
+  GI_TRY(scr.alloc(&ids, (size_t)n));
+  GI_TRY(scr.alloc(&ids_tmp, (size_t)n));
+  GI_TRY(scr.alloc(&hist, radix_hist_size<unsigned>(n)));
+  morton_key_kernel<R><<<div_up(n, 256), 256, 0, st>>>(x_axis, len_x, y_axis, len_y,
+                                                     points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR), n, inv,
+                                                     shift, key_oob, keys, ids);
+  GI_CUDA(cudaGetLastError());
+  GI_TRY(radix_sort<unsigned>(keys, ids, keys_tmp, ids_tmp, hist, n, passes, st, &keys_sorted, &ids_sorted));
+  GI_CUDA(cudaMemcpyAsync(order, ids_sorted, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  return GI_OK;
+}
+template int bilinear_morton_order_device<double>(const double*, int, const double*, int, const double*, int64_t,
+                                                  int32_t*, int, cudaStream_t);
+template int bilinear_morton_order_device<float>(const float*, int, const float*, int, const float*, int64_t, int32_t*,
+                                                 int, cudaStream_t);
 
 template int bilinear_device<double>(const double*, int, const double*, int, const double*, const double*, int64_t,
                                      double*, int, cudaStream_t);

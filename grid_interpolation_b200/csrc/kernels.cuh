@@ -10,6 +10,11 @@ template <class R>
 int bilinear_device(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* data_in, const R* points,
                     int64_t num_points, R* data_ip, int flags, cudaStream_t st);
 
+// order[j] = 0-based index of the j-th point along the Z curve of the field's 16 x 16-node blocks (device pointers)
+template <class R>
+int bilinear_morton_order_device(const R* x_axis, int len_x, const R* y_axis, int len_y, const R* points,
+                                 int64_t num_points, int32_t* order, int flags, cudaStream_t st);
+
 // barycentric.cu -- interpolation.f90:298-416 + triangle_walk.f90
 // counters (device, optional): int64[4] = walk iterations, masked cells, max fill level, fix-ups
 template <class R>

@@ -37,7 +37,7 @@ from ._lib import (GI_DEVICE, GI_FIELD_ROWMAJOR, GI_HOST, GI_KD_REFERENCE_VISITS
 __all__ = ["bilinear", "idw_kdtree", "idw_esrg_nearest", "barycentric_interpolation",
            "barycentric_interpolation_ex", "idw_kdtree_ex", "idw_esrg_nearest_ex", "kd_build",
            "assign_points_to_cells", "fill_nearest_neighbour", "pinned_empty", "pinned_copy",
-           "set_profiling", "set_pipeline_band_bytes", "set_fixup_list_capacity", "set_sliver_guard", "barycentric_points", "idw_kdtree_points", "release_workspace", "pinned_trim",
+           "set_profiling", "set_pipeline_band_bytes", "set_fixup_list_capacity", "set_sliver_guard", "barycentric_points", "idw_kdtree_points", "bilinear_morton_order", "release_workspace", "pinned_trim",
            "last_timings", "BarycentricPlan", "KdTreePlan", "EsrgPlan"]
 
 _F64 = np.dtype(np.float64)
@@ -314,6 +314,26 @@ def bilinear(x_axis, y_axis, data_in, points, *, search_axes=False, dtype=np.flo
         flags |= _lib.GI_BILINEAR_SEARCH_AXES if search_axes else 0
         st = getattr(lib(), "gi_bilinear_" + suf)(x.ptr, len_x, y.ptr, len_y, d.ptr, p.ptr, n, res_ptr, flags, c.mem, c.stream)
         c.finish(st, "bilinear", sync)
+        return res
+
+
+def bilinear_morton_order(x_axis, y_axis, points, *, dtype=np.float64, sync=True):
+    """Order of bilinear's ``points`` (num_points, 2) along the Z curve of the field's 16 x 16-node blocks (0-based
+    int32 permutation, points outside the grid last).  ``bilinear(x, y, field, points[order])`` reads every part of
+    the field once instead of gathering at random, and ``order[a:b]`` is a spatially compact shard (one GPU's share);
+    un-permute with ``out[order] = result``.  See gridinterp.h."""
+    rt, suf = _real(dtype)
+    with _Call(points) as c:
+        x = c.arg(x_axis, rt, 1, "x_axis"); y = c.arg(y_axis, rt, 1, "y_axis")
+        p = c.arg(points, rt, 2, "points")
+        if p.shape[1] != 2:
+            raise ValueError(f"points must have shape (num_points, 2), got {p.shape}")
+        n = p.shape[0]
+        res, res_ptr, _ = c.out((n,), np.int32, "C")
+        flags = GI_POINTS_ROWMAJOR if p.rowmajor else 0
+        st = getattr(lib(), "gi_bilinear_morton_order_" + suf)(x.ptr, x.shape[0], y.ptr, y.shape[0], p.ptr, n, res_ptr, flags,
+                                                              c.mem, c.stream)
+        c.finish(st, "bilinear_morton_order", sync)
         return res
 
 

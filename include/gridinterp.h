@@ -220,6 +220,18 @@ int gi_barycentric_interpolation_ex_f64(const double* points, int num_points, co
                                         int64_t* fill_src, int64_t* counters, int flags, int mem,
                                         void* stream);
 
+/* Morton order of bilinear's points (north_star: Morton-ordered targets / Morton ranges per GPU): order[j] = 0-based
+ * index of the j-th point along the Z curve of the field's 16 x 16-node blocks (cell of a point as
+ * interpolation.f90:67,73; points outside the grid last; stable).  bilinear's field reads are random gathers
+ * (interpolation.f90:62-96): points taken in this order read each part of the field once, and a contiguous range
+ * of the order touches a compact part of the field -- the shard for one of several GPUs.  Only the order is
+ * computed; moving the points (and the results back) is left to the caller. */
+int gi_bilinear_morton_order_f64(const double* x_axis, int len_x, const double* y_axis, int len_y,
+                                 const double* points, int64_t num_points, int32_t* order, int flags, int mem,
+                                 void* stream);
+int gi_bilinear_morton_order_f32(const float* x_axis, int len_x, const float* y_axis, int len_y, const float* points,
+                                 int64_t num_points, int32_t* order, int flags, int mem, void* stream);
+
 /* ---- scattered targets: the reference interpolates to the nodes of a regular grid only
  * (interpolation.f90:154-158,365-371); these take any (num_targets, 2) array of target coordinates instead -------- */
 

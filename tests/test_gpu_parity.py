@@ -471,3 +471,39 @@ def test_bilinear_sector_load_path(order):
     f = np.ascontiguousarray(field) if order == "C" else np.asfortranarray(field)
     p = np.ascontiguousarray(pts) if order == "C" else np.asfortranarray(pts)
     assert_values(ip.bilinear(x, y, f, p), want)
+
+
+def test_bilinear_morton_order_is_a_spatial_permutation():
+    """gi_bilinear_morton_order: a permutation that sorts the points by the Z value of their 16 x 16-node block
+    (points outside the grid last); bilinear on the ordered points, un-permuted, equals the direct call."""
+    rng = np.random.default_rng(21)
+    lx, ly, n = 1024, 768, 300_000
+    x = np.arange(float(lx)) * 0.5 + 3.0; y = np.arange(float(ly)) * 0.25 - 10.0
+    field = rng.normal(size=(ly, lx))
+    pts = np.column_stack([rng.uniform(x[0] - 5, x[-1] + 5, n), rng.uniform(y[0] - 5, y[-1] + 5, n)])
+    order = ip.bilinear_morton_order(x, y, pts)
+    assert order.dtype == np.int32 and np.array_equal(np.sort(order), np.arange(n))
+    ix = np.floor((pts[:, 0] - x[0]) / 0.5); iy = np.floor((pts[:, 1] - y[0]) / 0.25)
+    inside = (ix >= 0) & (ix < lx - 1) & (iy >= 0) & (iy < ly - 1)
+    def spread(v):
+        v = v.astype(np.uint32)
+        v = (v | (v << 8)) & 0x00ff00ff; v = (v | (v << 4)) & 0x0f0f0f0f
+        v = (v | (v << 2)) & 0x33333333; v = (v | (v << 1)) & 0x55555555
+        return v
+    key = np.where(inside, spread(np.clip(ix, 0, lx).astype(np.int64) >> 4) | (spread(np.clip(iy, 0, ly).astype(np.int64) >> 4) << 1),
+                   np.uint32(1 << 12))
+    ks = key[order]
+    assert (np.diff(ks.astype(np.int64)) >= 0).all()
+    assert (np.diff(order)[np.diff(ks.astype(np.int64)) == 0] > 0).all()         # stable
+    direct = ip.bilinear(x, y, field, pts)
+    back = np.empty(n)
+    back[order] = ip.bilinear(x, y, field, pts[order])
+    assert np.array_equal(back, direct)
+    # a contiguous eighth of the order is spatially compact: the shard of one of 8 GPUs touches ~1/8 of the field
+    part = pts[order[:n // 8]]
+    part = part[inside[order[:n // 8]]]
+    bbox = np.ptp(part[:, 0]) * np.ptp(part[:, 1])
+    assert bbox < 0.3 * np.ptp(x) * np.ptp(y)
+    import torch
+    d = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+    assert np.array_equal(ip.bilinear_morton_order(d(x), d(y), d(pts)).cpu().numpy(), order)
