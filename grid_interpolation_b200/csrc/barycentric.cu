@@ -66,24 +66,21 @@ template <class R> __device__ __forceinline__ void check_axes(const TargetWindow
 
 
 
-// One record per triangle, f64: 128 B = 4 sectors = one cache line.
-//   sectors 0-1  what a walk step needs: 3 vertices + 3 neighbour ids + the ambiguity threshold
-//   sector  2    A = y2-y3, B = x3-x2, C = y3-y1, D = x1-x3                      (interpolation.f90:385-394)
-//   sector  3    denom = A*D + B*(y1-y3) (:385-386) and the nodal values d1, d2, d3
-// Sectors 2-3 hold everything of the barycentric value that depends on the triangle only, computed once by the
-// pack pass with the reference's operations.  ncu (profiles/r02_start_locate_eval_ncu.csv): in round 1 phase 2
-// re-derived them -- 3 record loads, 17 FP64 instructions -- whenever a column entered another triangle, and as
-// some lane of a warp does so in nearly every row, every row paid for that block (49 % of the kernel's
-// instructions were phase 2, 119 per row and warp).  Now a triangle change is 3 loads + 3 FP64 + the reciprocal.
+// One record per triangle, f64: 96 B = 3 sectors.
+//   sectors 0-1  what a walk step needs: 3 vertices + 3 neighbour ids + the ambiguity threshold / flags word
+//   sector  2    denom = (y2-y3)*(x1-x3) + (x3-x2)*(y1-y3) (interpolation.f90:385-386) and the nodal values d1, d2, d3
+// Measured alternatives (same box, profiles/r02_walk_variants.md): round 1's record without denom (phase 2 re-derives
+// it: 4 FP64 more per triangle change) and a 128 B record that also holds A = y2-y3 .. D = x1-x3 (8 FP64 fewer per
+// triangle change, but a fourth sector per triangle to fetch and one more load to warm it: the kernel is bound by
+// latency and L1 wavefronts, not by FP64 -- 2.99 ms against 2.84 ms, and the pack pass writes 1.28 GB instead of 0.96).
 template <class R> struct alignas(sizeof(R) == 8 ? 32 : 16) TriGeom {
   R x1, y1, x2, y2, x3, y3;
   int n1, n2, n3;  // neighbour opposite vertex 1/2/3, 0-based, -1 = hull edge, -2 = not packed (band-limited pack)
   int pad;         // bits 1-30: ambiguity threshold of this triangle (bit pattern, see amb_threshold); bit 31:
                    // long triangle (kLongTriangle); bit 0: hull sliver, not to be interpolated in (kSliver)
-  R A, B, C, D;
   R denom, d1, d2, d3;
 };
-static_assert(sizeof(TriGeom<double>) == 128 && sizeof(TriGeom<float>) == 80, "record layout");
+static_assert(sizeof(TriGeom<double>) == 96 && sizeof(TriGeom<float>) == 64, "record layout");
 template <class R> struct SeedGrid {
   R x0, y0, inv_cell_x, inv_cell_y;
   int ncx, ncy;
@@ -108,33 +105,27 @@ __device__ __forceinline__ void load_walk(const TriGeom<float>* p, TriGeom<float
   g.x1 = p->x1; g.y1 = p->y1; g.x2 = p->x2; g.y2 = p->y2; g.x3 = p->x3; g.y3 = p->y3;
   g.n1 = p->n1; g.n2 = p->n2; g.n3 = p->n3; g.pad = p->pad;
 }
-// evaluation part: x3, y3 (sector 1), A..D (sector 2), denom + nodal values (sector 3)
+// evaluation part: all three sectors (A..D of interpolation.f90:385-394 are differences of the vertices)
 __device__ __forceinline__ void load_eval(const TriGeom<double>* p, TriGeom<double>& g) {
-  double n12, w;
-  ld256(reinterpret_cast<const char*>(p) + 32, g.x3, g.y3, n12, w);
-  ld256(reinterpret_cast<const char*>(p) + 64, g.A, g.B, g.C, g.D);
-  ld256(reinterpret_cast<const char*>(p) + 96, g.denom, g.d1, g.d2, g.d3);
+  load_walk(p, g);
+  ld256(reinterpret_cast<const char*>(p) + 64, g.denom, g.d1, g.d2, g.d3);
 }
-__device__ __forceinline__ void load_eval(const TriGeom<float>* p, TriGeom<float>& g) {
-  g.x3 = p->x3; g.y3 = p->y3; g.A = p->A; g.B = p->B; g.C = p->C; g.D = p->D;
-  g.denom = p->denom; g.d1 = p->d1; g.d2 = p->d2; g.d3 = p->d3;
-}
-// new nodal values (plans): sector 3 as ONE full-sector store, denom kept
+__device__ __forceinline__ void load_eval(const TriGeom<float>* p, TriGeom<float>& g) { g = *p; }
+// new nodal values (plans): sector 2 as ONE full-sector store, denom kept
 __device__ __forceinline__ void store_values(TriGeom<double>* p, double d1, double d2, double d3) {
   const double denom = p->denom;
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<char*>(p) + 96), "d"(denom), "d"(d1), "d"(d2),
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<char*>(p) + 64), "d"(denom), "d"(d1), "d"(d2),
                "d"(d3)
                : "memory");
 }
 __device__ __forceinline__ void store_values(TriGeom<float>* p, float d1, float d2, float d3) {
   p->d1 = d1; p->d2 = d2; p->d3 = d3;
 }
-// Fire-and-forget loads of sectors 2-3: the registers are never read, so nothing waits on them, but the sectors
-// are in L1 when phase 2 asks for them a few thousand cycles later (prefetch.global.L1 had no measurable effect).
+// Fire-and-forget load of sector 2: the registers are never read, so nothing waits on them, but the sector
+// is in L1 when phase 2 asks for it a few thousand cycles later (prefetch.global.L1 had no measurable effect).
 __device__ __forceinline__ void touch_values(const TriGeom<double>* p) {
   double a, b, c, d;
   ld256(reinterpret_cast<const char*>(p) + 64, a, b, c, d);
-  ld256(reinterpret_cast<const char*>(p) + 96, a, b, c, d);
 }
 __device__ __forceinline__ void touch_values(const TriGeom<float>*) {}
 
@@ -246,8 +237,10 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
     const R ly = fmax(fmax(fabs(g.y2 - g.y1), fabs(g.y3 - g.y2)), fabs(g.y1 - g.y3)) * sg.inv_cell_y;
     if (fmax(lx, ly) > R(2)) g.pad |= kLongTriangle;
   }
-  g.A = g.y2 - g.y3; g.B = g.x3 - g.x2; g.C = g.y3 - g.y1; g.D = g.x1 - g.x3;   // interpolation.f90:385-394
-  g.denom = g.A * g.D + g.B * (g.y1 - g.y3);                                     // :385-386
+  {
+    const R A = g.y2 - g.y3, B = g.x3 - g.x2, D = g.x1 - g.x3;                     // interpolation.f90:385-394
+    g.denom = A * D + B * (g.y1 - g.y3);                                           // :385-386
+  }
   if (sliver_q > R(0) && (n1 == 0 || n2 == 0 || n3 == 0) && sliver_quality(g) < sliver_q) g.pad |= kSliver;
   g.d1 = __ldg(data + (a - 1)); g.d2 = __ldg(data + (b - 1)); g.d3 = __ldg(data + (c - 1));
   geom[t] = g;
@@ -405,8 +398,9 @@ __device__ __forceinline__ R eval_value(const TriGeom<R>& g, R tx, R ty) {
   DivRcp<R> dv;
   dv.set(g.denom);
   const R u = tx - g.x3, t = ty - g.y3;
-  const R w1 = dv.quotient(g.A * u + g.B * t);
-  const R w2 = dv.quotient(g.C * u + g.D * t);
+  const R A = g.y2 - g.y3, B = g.x3 - g.x2, C = g.y3 - g.y1, D = g.x1 - g.x3;
+  const R w1 = dv.quotient(A * u + B * t);
+  const R w2 = dv.quotient(C * u + D * t);
   const R w3 = R(1) - w1 - w2;
   return g.d1 * w1 + g.d2 * w2 + g.d3 * w3;
 }
@@ -527,17 +521,13 @@ __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (
   const int bnf = a.bf1 - a.bf0;
   static_assert(ROWS <= 32, "one lane per row keeps that row's mask word");
   const int rb0 = max(0, a.bs0 - srow0), rb1 = min(nrows, a.bs1 - srow0);   // rows of the strip inside the band
-  // band-relative element of (row 0 of the strip, this column); only dereferenced for rows inside the band
-  const int64_t oo0 = (int64_t)(srow0 - a.bs0) * a.out_ld + (f - a.bf0);
-  R* optr = a.out + oo0;
-  int32_t* tptr = a.tri_out ? a.tri_out + ((int64_t)(srow0 - a.bs0) * bnf + (f - a.bf0)) : nullptr;
   int cur = -1;
   unsigned my_mask = 0;
   R c1 = 0, q1 = 0, c2 = 0, q2 = 0, p3 = 0, d1 = 0, d2 = 0, d3 = 0;
   DivRcp<R> dv;
   dv.d = R(1); dv.r2 = R(1);
 #pragma unroll 2
-  for (int r = 0; r < nrows; ++r, optr += a.out_ld) {
+  for (int r = 0; r < nrows; ++r) {
     const int t = active ? stri[r][tid] : 0;
     const bool inside = t >= 0;
     if (f_in_band && r >= rb0 && r < rb1) {
@@ -548,8 +538,9 @@ __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (
           load_eval(a.geom + t, g);
           dv.set(g.denom);
           d1 = g.d1; d2 = g.d2; d3 = g.d3;
-          if (!FY) { const R u = cf - g.x3; c1 = g.A * u; q1 = g.B; c2 = g.C * u; q2 = g.D; p3 = g.y3; }
-          else { const R u = cf - g.y3; c1 = g.B * u; q1 = g.A; c2 = g.D * u; q2 = g.C; p3 = g.x3; }
+          const R A = g.y2 - g.y3, B = g.x3 - g.x2, C = g.y3 - g.y1, D = g.x1 - g.x3;
+          if (!FY) { const R u = cf - g.x3; c1 = A * u; q1 = B; c2 = C * u; q2 = D; p3 = g.y3; }
+          else { const R u = cf - g.y3; c1 = B * u; q1 = A; c2 = D * u; q2 = C; p3 = g.x3; }
         }
         // w1 = (A*(tx-x3) + B*(ty-y3))/denom, w2 = (C*(tx-x3) + D*(ty-y3))/denom   (:387-394); the sum commutes
         const R t3 = saxis[r] - p3;
@@ -557,13 +548,14 @@ __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (
         quotient_pair(dv, FY ? q1 * t3 + c1 : c1 + q1 * t3, FY ? q2 * t3 + c2 : c2 + q2 * t3, w1, w2);
         const R w3 = R(1) - w1 - w2;
         const R v = d1 * w1 + d2 * w2 + d3 * w3;                   // :396-398
-        *optr = v;
+        // band-relative element (computed per row: pointers carried through the loop cost registers, and spills)
+        const int64_t oo = (int64_t)(srow0 + r - a.bs0) * a.out_ld + (f - a.bf0);
+        a.out[oo] = v;
         if (PEERS) {  // the fused gather: the same element of every peer field, over NVLink
-          const int64_t oo = oo0 + (int64_t)r * a.out_ld;
           for (int d = 0; d < a.n_peer; ++d) a.peer_out[d][oo] = v;
         }
       }
-      if (tptr) tptr[(int64_t)r * bnf] = (inside ? t : ~t) + 1;
+      if (a.tri_out) a.tri_out[(int64_t)(srow0 + r - a.bs0) * bnf + (f - a.bf0)] = (inside ? t : ~t) + 1;
     }
     const unsigned m = __ballot_sync(0xffffffffu, active && !inside);
     if (lane == r) my_mask = m;  // lane r keeps the word of row r (ROWS <= 32)
@@ -592,7 +584,7 @@ __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (
 //                      shared-reciprocal divisions; 128 consecutive doubles per row are stored coalesced and
 //                      the outside-hull bits come from one ballot per warp row.
 // ---------------------------------------------------------------------------------------------
-template <class R, bool FY, bool PEERS, int ROWS, bool BP>
+template <class R, bool FY, bool PEERS, int ROWS, bool BP, bool CF>
 __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, int by, int (*stri)[kWalkThreads], R* saxis) {
   const TargetWindow<R>& w = a.win;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -609,18 +601,16 @@ __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, i
   // ---- phase 1: locate -------------------------------------------------------------------------
   long long iters_sum = 0;
   if (active) {
-    int tri, n1, n2, n3, thr;
+    int tri, n1, n2, n3, pad;  // pad: the record's threshold + flags word (kLongTriangle, kSliver), kept whole
     R m1, m2, m3, p1, p2, p3, k1, k2, k3;
     bool fresh;    // no target resolved in `tri` yet
-    bool careful;  // long triangle: see farthest_failing_edge
-    bool sliver;   // hull sliver: targets found in it are masked (sliver_guard)
     bool forced_out = false;  // careful_locate found this row's target outside the hull at `tri`
     auto enter = [&](int t) {  // make `t` the current triangle: one 64 B load + 12 flops
       tri = t;
       fresh = true;
       TriGeom<R> g;
       load_walk(a.geom + t, g);
-      n1 = g.n1; n2 = g.n2; n3 = g.n3; thr = g.pad & kThrMask; careful = g.pad < 0; sliver = g.pad & kSliver;
+      n1 = g.n1; n2 = g.n2; n3 = g.n3; pad = g.pad;
       const R ex1 = g.x2 - g.x1, ey1 = g.y2 - g.y1;   // edge (v1,v2)
       const R ex2 = g.x3 - g.x2, ey2 = g.y3 - g.y2;   // edge (v2,v3)
       const R ex3 = g.x1 - g.x3, ey3 = g.y1 - g.y3;   // edge (v3,v1)
@@ -652,9 +642,11 @@ __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, i
       int nxt = o1 ? n3 : (o2 ? n1 : n2);
       // (BP: the pack was band-limited, links may lead to triangles without a record)
       if (BP && outside && nxt == kNotPacked) nxt = packed_alternative(o1, o2, o3, n1, n2, n3);
-      if (outside && nxt >= 0 && !forced_out) {
+      if (outside && nxt >= 0 && !(CF && forced_out)) {
         if (it < a.iter_cap) {
-          if (careful && ((o1 && o2) || (o3 && (o1 || o2)))) {   // long triangle, more than one edge fails (rare)
+          // (CF: careful exit-edge choice in long triangles, see farthest_failing_edge; compiled in for windows of few
+          // strips, where the hull strip's walks are the critical path)
+          if (CF && pad < 0 && ((o1 && o2) || (o3 && (o1 || o2)))) {   // long triangle, more than one edge fails (rare)
             const int res = careful_locate(a.geom, tri, FY ? cv : cf, FY ? cf : cv, a.iter_cap, a.status);
             forced_out = res < 0;   // a failing hull edge was seen: outside, whichever edge fails first there
             nxt = forced_out ? ~res : res;
@@ -664,12 +656,14 @@ __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, i
         }
         raise_status(a.status, GI_ERR_ITER_CAP);
       }
-      forced_out = false;
+      if (CF) forced_out = false;
       if (BP && outside && nxt == kNotPacked) raise_status(a.status, GI_ERR_PACK_WINDOW);  // band-limited pack too tight
       // resolved: inside `tri`, or outside the hull (:74-80: the last valid triangle is kept).
       // A target within the margin band of an edge is accepted by both adjacent triangles and which one the
       // reference returns depends on its walk path: flag it for fixup_kernel.
       // (any |cross| below twice the margin: a superset of the truly ambiguous cases, three compares)
+      const int thr = pad & kThrMask;
+      const bool sliver = pad & kSliver;   // hull sliver: targets found in it are masked (sliver_guard)
       if (in_amb_band(x1, thr) | in_amb_band(x2, thr) | in_amb_band(x3, thr)) {
         const unsigned long long slot = atomicAdd((unsigned long long*)(a.counters + 5), 1ull);
         if (slot < (unsigned long long)a.amb_cap) a.amb_list[slot] = (srow0 + r - w.s0) * w.nf() + lane_f;
@@ -693,11 +687,11 @@ __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, i
   if (lane == 0 && iters_sum) atomicAdd((unsigned long long*)a.counters, (unsigned long long)iters_sum);
 }
 
-template <class R, bool FY, bool PEERS, int ROWS, int MINB, bool BP>
+template <class R, bool FY, bool PEERS, int ROWS, int MINB, bool BP, bool CF>
 __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const WalkArgs<R> a) {
   __shared__ int stri[ROWS][kWalkThreads];
   __shared__ R saxis[ROWS];
-  locate_eval_tile<R, FY, PEERS, ROWS, BP>(a, blockIdx.x, blockIdx.y, stri, saxis);
+  locate_eval_tile<R, FY, PEERS, ROWS, BP, CF>(a, blockIdx.x, blockIdx.y, stri, saxis);
 }
 
 // The same as a stand-by for the rasteriser (raster.cuh): a small grid that returns at once unless the device
@@ -709,7 +703,7 @@ __global__ void __launch_bounds__(kWalkThreads) locate_eval_standby_kernel(const
   __shared__ R saxis[ROWS];
   if (!*a.only_if) return;
   for (int t = blockIdx.x; t < nbx * nby; t += gridDim.x) {
-    locate_eval_tile<R, FY, PEERS, ROWS, true>(a, t % nbx, t / nbx, stri, saxis);
+    locate_eval_tile<R, FY, PEERS, ROWS, true, true>(a, t % nbx, t / nbx, stri, saxis);
     __syncthreads();
   }
 }
@@ -1245,16 +1239,26 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
     else locate_eval_standby_kernel<R, true, true, kRows><<<g, kWalkThreads, 0, st>>>(wa, grid.x, grid.y);
   } else {
     const bool bp = pm.need != nullptr;  // band-limited pack: links may lead to triangles without a record
-#define GI_LAUNCH_WALK(FY_, PEERS_)                                                                     \
-  do {                                                                                                  \
-    if (bp) locate_eval_kernel<R, FY_, PEERS_, kRows, 8, true><<<grid, kWalkThreads, 0, st>>>(wa);      \
-    else locate_eval_kernel<R, FY_, PEERS_, kRows, 8, false><<<grid, kWalkThreads, 0, st>>>(wa);        \
+    // careful exit-edge choice (CF): the sliver triangles along the hull cost the first / last strips of a window long
+    // dependent walks without it (band of 2048 rows: 1.25 instead of 0.43 ms); in a window of many CTA waves those
+    // strips are not the critical path and the test is 2 % of the kernel, so it is compiled out there
+    const bool cf = (int64_t)grid.x * grid.y < (int64_t)kNumSMs * 8 * 24;
+#define GI_LAUNCH_WALK2(FY_, PEERS_, BP_)                                                                \
+  do {                                                                                                   \
+    if (cf) locate_eval_kernel<R, FY_, PEERS_, kRows, 8, BP_, true><<<grid, kWalkThreads, 0, st>>>(wa);    \
+    else locate_eval_kernel<R, FY_, PEERS_, kRows, 8, BP_, false><<<grid, kWalkThreads, 0, st>>>(wa);      \
+  } while (0)
+#define GI_LAUNCH_WALK(FY_, PEERS_)                     \
+  do {                                                  \
+    if (bp) GI_LAUNCH_WALK2(FY_, PEERS_, true);         \
+    else GI_LAUNCH_WALK2(FY_, PEERS_, false);           \
   } while (0)
     if (!fy && !peers) GI_LAUNCH_WALK(false, false);
     else if (fy && !peers) GI_LAUNCH_WALK(true, false);
     else if (!fy) GI_LAUNCH_WALK(false, true);
     else GI_LAUNCH_WALK(true, true);
 #undef GI_LAUNCH_WALK
+#undef GI_LAUNCH_WALK2
   }
   GI_CUDA(cudaGetLastError());
   // targets inside the margin band of an edge: follow the reference's own path (normally none)
