@@ -13,11 +13,12 @@ packing + seed grid + walk / barycentric + hull fill), as the reference's routin
             ranks.  N = 1: one call.  N > 1 (torchrun, one rank per GPU; "scaling": "strong"): the SAME 16384^2 grid
             in N row bands (BASELINE.json: "row-band sharded over 8 GPUs"), mesh replicated, every rank packs only
             the triangles near its band, and the final gather of the field is INSIDE the timed step: the kernels
-            store every result into the field of every rank over NVLink (peer stores, grid_interpolation_b200.
-            sharding.PeerField), followed by a stream-ordered signal / wait so that a step ends when all N bands
-            have arrived in this rank's copy.  Extra keys at N > 1: "bands_only" (no gather), "gather_nccl" (band
-            + ncclAllGather, the plain-collective form), "weak" (round 1's headline: one 16384-row band per rank of
-            a 16384 x 16384N grid), "nvlink_floor_ms" (bytes every rank must receive / 900 GB/s).
+            store every result into the rank's own field and into rank 0's over NVLink (peer stores,
+            grid_interpolation_b200.sharding.PeerField), followed by a stream-ordered signal; rank 0's step ends
+            when all N bands have arrived in its copy.  Extra keys at N > 1: "gather_all" (the field gathered on
+            EVERY rank), "bands_only" (no gather), "gather_nccl" (band + ncclAllGather, the plain-collective
+            form), "weak" (round 1's headline: one 16384-row band per rank of a 16384 x 16384N grid),
+            "nvlink_floor_ms" (bytes rank 0 must receive / 900 GB/s).
   parity    the run checks itself: N = 1 compares the whole field, the triangle ids, the outside-hull mask and the
             fill sources with the CPU oracle (the restatement of the Fortran, oracle/); N > 1 compares every
             rank's gathered field with a one-shot single-GPU run of the whole grid.
@@ -286,7 +287,12 @@ def main():
         field = sharding.PeerField(grid, len_x, order="C")
         d_out = field.tensor
 
-        def step_dev():       # band -> every rank's field (peer stores), signal, wait for all bands
+        def step_dev():       # the final gather: band -> this rank's field and rank 0's (peer stores); rank 0 waits
+            sharding.barycentric_gather(field, *mesh, halo=halo, dest=0)
+            if rank == 0:
+                field.wait()
+
+        def step_all():       # band -> EVERY rank's field, signal, every rank waits for all bands
             sharding.barycentric_gather(field, *mesh, halo=halo)
             field.wait()
     else:
@@ -315,11 +321,22 @@ def main():
     parity = None
     if world > 1 and not weak:
         one = ip.barycentric_interpolation(*mesh, order="C")
+        # rank 0 holds the gathered field; the other ranks hold (at least) their own band
+        sel = slice(0, grid) if rank == 0 else slice(band[0], band[1])
+        bad = int((one[sel] != d_out[sel]).sum().item())
+        cnt = torch.tensor([bad], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        parity = {"against": "a one-shot single-GPU run of the whole grid: the gathered field on rank 0, the own "
+                             "band on the other ranks", "targets": targets_total, "value_mismatches": int(cnt.item())}
+        # the all-to-all form: the field complete on EVERY rank
+        ms_a = tm.run(step_all, args.steps, warm)
+        status("gather_all")
         bad = int((one != d_out).sum().item())
         cnt = torch.tensor([bad], dtype=torch.int64, device=dev)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        parity = {"against": "a one-shot single-GPU run of the whole grid, on every rank", "targets": targets_total,
-                  "value_mismatches": int(cnt.item())}
+        extras["gather_all"] = {"ms_per_step": ms_a, "value": targets_total / (ms_a * 1e-3), "unit": "targets/s",
+                                "value_mismatches": int(cnt.item()),
+                                "note": "the field gathered on every rank (each receives (N-1)/N of it over NVLink)"}
         del one
 
     # ------------------------------------------------------------------ N > 1 extras
@@ -477,7 +494,7 @@ def main():
     # kernels of ours per step: pack (+ need), locate/evaluate, start triangle, fix-up, row walk, fill, status
     # flush (+ signal, wait and its flush in the gather form)
     launches = 7 + ((1 + 3) if field is not None else 0)
-    band_txt = (f"{world} row bands, the field gathered on every rank by peer stores inside the step"
+    band_txt = (f"{world} row bands, the field gathered on rank 0 by peer stores inside the step"
                 if world > 1 and not weak else f"{world} row band(s) of {rows} rows")
     out = {
         "metric": "target points interpolated/sec", "value": value, "unit": "targets/s", "n_gpus": world,

@@ -185,17 +185,25 @@ class PeerField:
             fields.append(fp.value); flags.append(gp.value)
         self.ptrs = (C.c_void_p * self.world)(*fields)
         self.flag_ptrs = (C.c_void_p * self.world)(*flags)
+        order_r = [self.rank] + list(range(self.rank + 1, self.world)) + list(range(self.rank))
+        self.ptr_of = {r: fields[i] for i, r in enumerate(order_r)}     # rank -> its field / flags as mapped here
+        self.flag_of = {r: flags[i] for i, r in enumerate(order_r)}
         self._seq = 0
         shape = self.shape if order == "C" else self.shape[::-1]
         t = torch.as_tensor(_DeviceView(self._local, shape, self.dtype.str), device=dev)
         self.tensor = t if order == "C" else t.t()
         dist.barrier(group)
 
-    def signal(self, stream=None):
-        """After everything enqueued so far on ``stream``: tell every rank that this rank's band is in its field."""
+    def signal(self, stream=None, dest=None):
+        """After everything enqueued so far on ``stream``: tell every rank (``dest=None``) or rank ``dest`` only that
+        this rank's band is in its field."""
         self._seq += 1
-        self._check(self._lib.gi_peer_signal(self.flag_ptrs, self.world, self.rank, self._seq, _stream(stream)),
-                    "gi_peer_signal")
+        if dest is None:
+            self._check(self._lib.gi_peer_signal(self.flag_ptrs, self.world, self.rank, self._seq, _stream(stream)),
+                        "gi_peer_signal")
+        else:
+            one = (C.c_void_p * 1)(self.flag_of[dest])
+            self._check(self._lib.gi_peer_signal(one, 1, self.rank, self._seq, _stream(stream)), "gi_peer_signal")
         return self._seq
 
     def wait(self, seq=None, stream=None, timeout_s: float = 10.0):
@@ -232,12 +240,13 @@ def _stream(stream):
 
 
 def barycentric_gather(field: PeerField, points, data_in, x_axis, y_axis, simplices, neighbours, *, halo=None,
-                       band_pack=True, signal=True, stream=None):
+                       band_pack=True, signal=True, stream=None, dest=None):
     """This rank's row band of ``barycentric_interpolation`` (interpolation.f90:362-404,412), stored by the kernels
-    into ``field`` on every rank (the fused final gather).  Inputs are torch CUDA tensors in C order (points (n, 2),
-    simplices / neighbours (t, 3) int32); asynchronous on the current torch stream.  Check
-    ``lib().gi_stream_status`` (or call ``field.wait()`` + synchronize) before trusting the result: GI_ERR_HALO /
-    GI_ERR_PACK_WINDOW ask for a retry with a larger halo / ``band_pack=False``."""
+    into ``field`` on every rank (``dest=None``: the field ends up complete everywhere) or into this rank's own copy
+    and rank ``dest``'s (the final gather of the field onto one rank: 1/N of the NVLink traffic per sender).  Inputs
+    are torch CUDA tensors in C order (points (n, 2), simplices / neighbours (t, 3) int32); asynchronous on the
+    current torch stream.  Check ``lib().gi_stream_status`` (or call ``field.wait()`` + synchronize) before trusting
+    the result: GI_ERR_HALO / GI_ERR_PACK_WINDOW ask for a retry with a larger halo / ``band_pack=False``."""
     from . import _lib
     lib = _lib.lib()
     suf = "f64" if field.dtype == np.float64 else "f32"
@@ -249,11 +258,16 @@ def barycentric_gather(field: PeerField, points, data_in, x_axis, y_axis, simpli
     for t in (points, data_in, x_axis, y_axis, simplices, neighbours):
         if not (hasattr(t, "is_cuda") and t.is_cuda and t.is_contiguous()):
             raise ValueError("barycentric_gather takes contiguous torch CUDA tensors")
+    if dest is None:
+        ptrs, n_fields = field.ptrs, field.world
+    else:
+        dst = [field.ptr_of[field.rank]] + ([field.ptr_of[dest]] if dest != field.rank else [])
+        ptrs, n_fields = (C.c_void_p * len(dst))(*dst), len(dst)
     st = getattr(lib, "gi_barycentric_interpolation_gather_" + suf)(
         points.data_ptr(), points.shape[0], data_in.data_ptr(), x_axis.data_ptr(), x_axis.shape[0], y_axis.data_ptr(),
-        y_axis.shape[0], simplices.data_ptr(), neighbours.data_ptr(), simplices.shape[0], r0, r1, h, field.ptrs,
-        field.world, flags, _stream(stream))
+        y_axis.shape[0], simplices.data_ptr(), neighbours.data_ptr(), simplices.shape[0], r0, r1, h, ptrs,
+        n_fields, flags, _stream(stream))
     _lib.check(st, "barycentric_gather")
     if signal:
-        field.signal(stream)
+        field.signal(stream, dest=dest)
     return r0, r1

@@ -111,6 +111,17 @@ def _worker(rank, world, port, order, ret):
                 field.tensor.zero_()
                 torch.cuda.synchronize()
                 dist.barrier()
+            # the gather onto ONE rank: every rank stores into its own copy and rank 1's; only rank 1 waits
+            root = 1
+            r0, r1 = sharding.barycentric_gather(field, *d, dest=root)
+            if rank == root:
+                field.wait()
+            torch.cuda.synchronize()
+            _lib.check(_lib.lib().gi_stream_status(torch.cuda.current_stream().cuda_stream), "gather to one rank")
+            got = field.tensor.cpu().numpy()
+            ok = ok and (np.array_equal(got, want) if rank == root else
+                         (np.array_equal(got[r0:r1], want[r0:r1]) and not got[:r0].any() and not got[r1:].any()))
+            dist.barrier()
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
