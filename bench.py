@@ -49,7 +49,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from grid_interpolation_b200 import workloads  # noqa: E402
+import workloads  # noqa: E402
 
 ALG_BYTES = {"c2": 9.43, "c3": 11.58, "c4": 9.34, "c5": 45.48}       # SURVEY.md section 8(d), FP64 + int32
 DOMINANT = {"c4": "walk", "c5": "bilinear", "c3": "esrg_query", "c2": "kd_query"}

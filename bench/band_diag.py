@@ -2,7 +2,8 @@
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from grid_interpolation_b200 import interpolation as ip, workloads, _lib
+from grid_interpolation_b200 import interpolation as ip, _lib
+import workloads
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 grid = int(16384 * scale) // 128 * 128
 w = workloads.c4(int(5_000_000 * scale ** 2), grid)

@@ -7,7 +7,8 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from grid_interpolation_b200 import interpolation as ip, workloads  # noqa: E402
+from grid_interpolation_b200 import interpolation as ip  # noqa: E402
+import workloads
 
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0

@@ -13,7 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from grid_interpolation_b200 import workloads  # noqa: E402
+import workloads  # noqa: E402
 
 
 def _kd_launches(n):

@@ -3,7 +3,8 @@ entry points through the numpy API (host buffers, H2D/D2H included) next to the 
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from grid_interpolation_b200 import interpolation as ip, workloads
+from grid_interpolation_b200 import interpolation as ip
+import workloads
 from oracle import oracle as orc
 w = workloads.c1()
 def t(fn, n=50):

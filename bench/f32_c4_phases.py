@@ -1,5 +1,6 @@
 import numpy as np, torch
-from grid_interpolation_b200 import interpolation as ip, workloads
+from grid_interpolation_b200 import interpolation as ip
+import workloads
 dev = torch.device("cuda:0")
 w = workloads.c4(); g = 16384
 for R, dt in ((np.float32, torch.float32), (np.float64, torch.float64)):

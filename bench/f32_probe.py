@@ -2,7 +2,8 @@
 sizes, device-resident, next to double precision (the graded kind): ms per call, mean of 5 after 2 warm-ups."""
 import sys, time
 import numpy as np, torch
-from grid_interpolation_b200 import interpolation as ip, workloads
+from grid_interpolation_b200 import interpolation as ip
+import workloads
 
 dev = torch.device("cuda:0")
 def t(a, dt): return torch.as_tensor(np.ascontiguousarray(a), device=dev).to(dt)

@@ -3,7 +3,8 @@ are the walks of the rows outside / near the hull?"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from grid_interpolation_b200 import interpolation as ip, workloads
+from grid_interpolation_b200 import interpolation as ip
+import workloads
 w = workloads.c4()
 t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
 mesh = [t(a) for a in (w.points, w.data_pts, w.x_axis, w.y_axis, w.simplices, w.neighbours)]

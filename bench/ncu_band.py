@@ -3,7 +3,8 @@
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from grid_interpolation_b200 import interpolation as ip, workloads
+from grid_interpolation_b200 import interpolation as ip
+import workloads
 b, nb = int(sys.argv[1]), int(sys.argv[2])
 grid = 16384
 w = workloads.c4()

@@ -2,7 +2,8 @@
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from grid_interpolation_b200 import interpolation as ip, workloads
+from grid_interpolation_b200 import interpolation as ip
+import workloads
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 row_tests = len(sys.argv) > 2 and sys.argv[2] == "1"
 grid = int(16384 * scale) // 128 * 128

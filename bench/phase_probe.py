@@ -2,7 +2,8 @@
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from grid_interpolation_b200 import interpolation as ip, workloads
+from grid_interpolation_b200 import interpolation as ip
+import workloads
 which = sys.argv[1]; scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 dev = torch.device("cuda:0"); t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
 if which == "c3":

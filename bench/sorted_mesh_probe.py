@@ -4,7 +4,8 @@ kept, so every value keeps its bits).  Host-side numpy re-ordering: a probe for 
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from grid_interpolation_b200 import interpolation as ip, workloads
+from grid_interpolation_b200 import interpolation as ip
+import workloads
 
 def zkey(x, y, cell):
     def spread(v):

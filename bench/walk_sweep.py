@@ -9,7 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from grid_interpolation_b200 import interpolation as ip  # noqa: E402
-from grid_interpolation_b200 import workloads  # noqa: E402
+import workloads  # noqa: E402
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 n = int(5_000_000 * scale ** 2); grid = int(16384 * scale) // 128 * 128

@@ -30,6 +30,7 @@
 // All index decisions (orientation signs, first failing edge) and all values use the reference's operations
 // in the reference's order with FMA contraction disabled (-fmad=false): bit-identical to the oracle.
 #include <algorithm>
+#include <atomic>
 #include <memory>
 
 #include <cmath>
@@ -1270,13 +1271,16 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
   {
     const int cols = wa.win.fast_is_y ? wa.win.s1 : wa.win.f1;            // a row is walked from column 0
     const int spec_cols = cols <= kRowSpecMaxCols ? cols : 0;
-    static bool configured[64] = {};  // per device (the attribute belongs to the device's copy of the kernel)
+    // the attribute belongs to the device's copy of the kernel: set once per device (bit mask, race-free; a second
+    // thread that sets it again does no harm)
+    static std::atomic<unsigned long long> configured{0ull};
     int dev = 0;
     GI_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
+    const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (!bit || !(configured.load(std::memory_order_acquire) & bit)) {
       GI_CUDA(cudaFuncSetAttribute(row_walk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kRowSpecMaxCols * (int)sizeof(int)));
-      if (dev >= 0 && dev < 64) configured[dev] = true;
+      configured.fetch_or(bit, std::memory_order_release);
     }
     row_walk_kernel<R><<<std::min(wa.win.fast_is_y ? nf : ns, kNumSMs * 16), 32, (size_t)spec_cols * sizeof(int), st>>>(
         wa, spec_cols);

@@ -14,7 +14,7 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def c1():
-    from grid_interpolation_b200 import workloads
+    import workloads
     return workloads.c1()
 
 

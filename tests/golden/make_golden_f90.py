@@ -27,7 +27,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from grid_interpolation_b200 import workloads  # noqa: E402  (host-side input generation only)
+import workloads  # noqa: E402  (host-side input generation only)
 from oracle.f90interp import Cell, Interpreter  # noqa: E402
 
 REF = os.environ.get("GI_REFERENCE", "/root/reference")

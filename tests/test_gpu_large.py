@@ -17,7 +17,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from grid_interpolation_b200 import interpolation as ip  # noqa: E402
-from grid_interpolation_b200 import workloads  # noqa: E402
+import workloads  # noqa: E402
 
 
 def dev(a):

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 from grid_interpolation_b200 import _lib, sharding  # noqa: E402
 from grid_interpolation_b200 import interpolation as ip  # noqa: E402
-from grid_interpolation_b200 import workloads  # noqa: E402
+import workloads  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from grid_interpolation_b200 import interpolation as ip  # noqa: E402
-from grid_interpolation_b200 import workloads  # noqa: E402
+import workloads  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
 RTOL = 1e-12  # north_star: FP64 values within 1e-12 relative (we additionally assert bit equality)

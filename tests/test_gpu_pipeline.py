@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from grid_interpolation_b200 import interpolation as ip  # noqa: E402
-from grid_interpolation_b200 import workloads  # noqa: E402
+import workloads  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
 

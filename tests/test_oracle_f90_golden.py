@@ -65,7 +65,7 @@ def test_barycentric_matches_fortran_source(g):
 def test_reference_test_case_at_full_size(golden_dir):
     """The reference's own test case at its own size (test_interpolation.py:54-93: 5 000 points -> 132 x 79 grid,
     num_nn = 6), Fortran source interpreted end to end (make_golden_f90.py --c1): the four fields bit for bit."""
-    from grid_interpolation_b200 import workloads
+    import workloads
     z = np.load(os.path.join(golden_dir, "f90_c1_f64.npz"))
     w = workloads.c1()
     assert workloads.digest(w) == str(z["inputs_sha256"]), "seeded inputs differ from the ones the vectors were made from"

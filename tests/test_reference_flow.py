@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("num_points", [5_000, 100_000, 500_000])   # 500 000 = the script's default (:54)
 def test_test_interpolation_flow(num_points):
     from interpolation import interpolation as ip_fortran          # test_interpolation.py:27
-    from grid_interpolation_b200 import workloads
+    import workloads
     w = workloads.c1(num_points=num_points)                         # :54-93 (seed 33, sine mountains, grid)
     points, data_pts, x_axis, y_axis, grid_spac = w.points, w.data_pts, w.x_axis, w.y_axis, w.grid_spac
 

@@ -38,7 +38,7 @@ def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from grid_interpolation_b200 import workloads
+        import workloads
         from oracle import oracle as orc
         w = workloads.c1(num_points=1500)
         ly = w.y_axis.size

@@ -92,7 +92,7 @@ def c3(n=10_000_000, grid=8192):
 def _default_cache():
     """<repo>/.gi_cache when it exists (git-ignored; it travels with a gpurun snapshot, so the one-minute Qhull run
     is not repeated on every fresh box), else /tmp/gi_cache."""
-    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ".gi_cache")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), ".gi_cache")
     return here if os.path.isdir(here) else "/tmp/gi_cache"
 
 
