@@ -55,7 +55,8 @@ ALG_BYTES = {"c2": 9.43, "c3": 11.58, "c4": 9.34, "c5": 45.48}
 DOMINANT = {"c4": "walk", "c5": "bilinear", "c3": "esrg_query", "c2": "kd_query"}
 NVLINK_GBS = 900.0                                                     # per direction and GPU (NVLink 5)
 # what limits locate_eval_kernel according to the committed ncu capture (profiles/r02_locate_eval_ncu.csv)
-C4_LIMITER = {"unit": "instruction issue + FP64 pipe (not HBM)", "source": "ncu --set full, profiles/"}
+C4_LIMITER = {"unit": "dependent walk chain at 8 CTAs/SM: issue slots 55-60 %, L1 wavefronts 62 %, FP64 pipe 33 % (not HBM: DRAM 13 %)",
+              "source": "ncu --set full, profiles/r02_final_locate_eval_ncu.csv"}
 
 
 def parse():

@@ -411,6 +411,43 @@ static int kdtree_points_api(const R* points, int num_points, const R* data_in, 
 }
 
 template <class R>
+static int esrg_points_api(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
+                           const R* y_axis, int len_y, R grid_spac, const R* targets, int64_t m, int k, R* data_ip,
+                           int32_t* nn_index, R* nn_dist2, int flags, int mem, void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(points && data_in && x_axis && y_axis && (targets || m == 0) && (data_ip || m == 0), "null pointer");
+  GI_REQUIRE(num_points >= 1 && len_x >= 1 && len_y >= 1 && m >= 0 && k >= 1, "bad dimensions");
+  GI_REQUIRE(grid_spac > R(0), "grid_spac must be positive");
+  if (num_points < k) {
+    set_error("fewer source points than num_neighbours (the reference loops forever, query_esrg.f90:178)");
+    return GI_ERR_TOO_FEW_POINTS;
+  }
+  if (mem == GI_DEVICE)
+    return esrg_points_device<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, targets, m, k,
+                                 data_ip, nn_index, nn_dist2, flags, (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  if (m == 0) return GI_OK;
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  R *dp, *dd, *dx, *dy, *dt, *dout, *dd2;
+  int32_t* dnn;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, data_in, (size_t)num_points, &dd));
+  GI_TRY(to_device(scr, x_axis, (size_t)len_x, &dx));
+  GI_TRY(to_device(scr, y_axis, (size_t)len_y, &dy));
+  GI_TRY(to_device(scr, targets, (size_t)2 * m, &dt));
+  GI_TRY(scr.alloc(&dout, (size_t)m));
+  GI_TRY(out_device(scr, nn_index, (size_t)m * k, &dnn));
+  GI_TRY(out_device(scr, nn_dist2, (size_t)m * k, &dd2));
+  GI_TRY(esrg_points_device<R>(dp, num_points, dd, dx, len_x, dy, len_y, grid_spac, dt, m, k, dout, dnn, dd2, flags, st));
+  GI_TRY(to_host(st, data_ip, dout, (size_t)m));
+  GI_TRY(to_host(st, nn_index, dnn, (size_t)m * k));
+  GI_TRY(to_host(st, nn_dist2, dd2, (size_t)m * k));
+  return read_status(st, true);
+}
+
+template <class R>
 static int kdtree_api(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x,
                       const R* y_axis, int len_y, int k, int row_begin, int row_end, R* data_ip,
                       int32_t* nn_index, R* nn_dist2, int64_t* counters, int flags, int mem, void* stream) {
@@ -809,6 +846,13 @@ GI_API void gi_plan_destroy(gi_plan* plan) {
                                         R* nn_dist2, int flags, int mem, void* stream) {                           \
     return kdtree_points_api<R>(points, num_points, data_in, targets, num_targets, num_neighbours, data_ip,        \
                                 nn_index, nn_dist2, flags, mem, stream);                                           \
+  }                                                                                                                 \
+  GI_API int gi_idw_esrg_nearest_points_##SUF(const R* points, int num_points, const R* data_in, const R* x_axis,  \
+                                              int len_x, const R* y_axis, int len_y, R grid_spac, const R* targets, \
+                                              int64_t num_targets, int num_neighbours, R* data_ip,                 \
+                                              int32_t* nn_index, R* nn_dist2, int flags, int mem, void* stream) {  \
+    return esrg_points_api<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, targets,       \
+                              num_targets, num_neighbours, data_ip, nn_index, nn_dist2, flags, mem, stream);       \
   }                                                                                                                 \
   GI_API int gi_fill_nearest_neighbour_##SUF(const uint8_t* mask_outside, int len_x, int len_y, R* data_ip,        \
                                              int64_t* fill_src, int flags, int mem, void* stream) {                \

@@ -145,6 +145,10 @@ template <class R> struct EsrgArgs {
   R* tk_d;                // k > 32: neighbour lists in scratch memory (topk.cuh, KC = 0), k x tk_stride
   int* tk_id;
   int64_t tk_stride;
+  PointsView<R> tgt;      // scattered targets (num_tgt > 0, esrg_query_kernel only): target i instead of a grid node
+  int64_t num_tgt;
+  const R* x_axis;        // (scattered targets: the cell of a target is computed like a point's)
+  const R* y_axis;
 };
 
 // Smallest level L >= from whose radius is not exceeded by d2, i.e. the first level at which the reference accepts
@@ -152,11 +156,11 @@ template <class R> struct EsrgArgs {
 // (query_esrg.f90:141,181,230).  Used once a target's frames have left the grid: no cell is added any more and
 // nothing changes until the growing radius reaches the nearest deferred point (points clamped into the border
 // cells from far outside the grid), so the levels in between are skipped instead of iterated.
-template <class R> __device__ __forceinline__ int esrg_level_reaching(R spac, R d2, int from) {
-  const double est = sqrt((double)d2) / (double)spac - 0.5;
+template <class R> __device__ __forceinline__ int esrg_level_reaching(R spac, R d2, int from, R half = R(0.5)) {
+  const double est = sqrt((double)d2) / (double)spac - (double)half;
   int L = est > 2.0e9 ? 2000000000 : (est > 0.0 ? (int)est : 0);
   L = max(L - 1, from);
-  auto r2 = [&](int l) { const R rad = spac * (R(l) + R(0.5)); return rad * rad; };
+  auto r2 = [&](int l) { const R rad = spac * (R(l) + half); return rad * rad; };
   while (L > from && !(d2 > r2(L - 1))) --L;
   while (d2 > r2(L) && L < 2000000000) ++L;
   return L;
@@ -165,15 +169,28 @@ template <class R> __device__ __forceinline__ int esrg_level_reaching(R spac, R 
 template <class R, int KC>
 __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
   const TargetWindow<R>& w = a.win;
-  const int64_t n_todo = *a.todo_count;
+  // Scattered targets (the reference's targets are the cell centres, query_esrg.f90:133-134): the ring
+  // search runs around the target's cell, and a level's radius is spac * L instead of spac * (L + 1/2) -- a target
+  // anywhere in its cell is at least L cells away from everything outside the (2L+1)^2 block.
+  const bool scattered = a.num_tgt > 0;
+  const R half = scattered ? R(0) : R(0.5);
+  const int64_t n_todo = scattered ? a.num_tgt : *a.todo_count;
   for (int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; li < n_todo; li += (int64_t)gridDim.x * blockDim.x) {
-  const int lin = a.todo[li];
-  const int f = w.f0 + lin % w.nf();
-  const int s = w.s0 + lin / w.nf();
-  const int ix = w.fast_is_y ? s : f, iy = w.fast_is_y ? f : s;
   const int len_x = a.len_x, len_y = a.len_y;
-  const R cx = __ldg((w.fast_is_y ? w.slow_axis : w.fast_axis) + ix);     // query_esrg.f90:133-134
-  const R cy = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
+  int f = 0, s = 0, ix, iy;
+  R cx, cy;
+  if (scattered) {
+    a.tgt.xy(li, cx, cy);
+    ix = cell_index(cx, __ldg(a.x_axis), a.spac, len_x);
+    iy = cell_index(cy, __ldg(a.y_axis), a.spac, len_y);
+  } else {
+    const int lin = a.todo[li];
+    f = w.f0 + lin % w.nf();
+    s = w.s0 + lin / w.nf();
+    ix = w.fast_is_y ? s : f; iy = w.fast_is_y ? f : s;
+    cx = __ldg((w.fast_is_y ? w.slow_axis : w.fast_axis) + ix);           // query_esrg.f90:133-134
+    cy = __ldg((w.fast_is_y ? w.fast_axis : w.slow_axis) + iy);
+  }
 
   TopK<R, KC> tk;
   if constexpr (KC == 0) tk.bind(a.tk_d, a.tk_id, a.tk_stride, blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
@@ -245,7 +262,7 @@ __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
   // beyond this level the frame lies outside the grid: every cell has been scanned
   const int level_full = max(max(ix, len_x - 1 - ix), max(iy, len_y - 1 - iy));
   for (;;) {
-    const R rad = a.spac * (R(level) + R(0.5));                           // :141,:181
+    const R rad = a.spac * (R(level) + half);                             // :141,:181
     radius_sq_prev = radius_sq;
     radius_sq = rad * rad;
     dmin_deferred = Consts<R>::huge();
@@ -273,12 +290,12 @@ __global__ void __launch_bounds__(128) esrg_query_kernel(const EsrgArgs<R> a) {
       // The reference keeps incrementing the level (:178-181) until the radius reaches its deferred points; the
       // host checked num_points >= k, so that happens.  (No deferred point at all: NaN coordinates -- stop.)
       if (!(dmin_deferred < Consts<R>::huge())) { raise_status(a.status, GI_ERR_TOO_FEW_POINTS); break; }
-      level = esrg_level_reaching(a.spac, dmin_deferred, level);
+      level = esrg_level_reaching(a.spac, dmin_deferred, level, half);
     }
   }
 
   // IDW (interpolation.f90:260-274): distances are square-rooted first (query_esrg.f90:247)
-  const int64_t o = (int64_t)(s - w.s0) * w.nf() + (f - w.f0);
+  const int64_t o = scattered ? li : (int64_t)(s - w.s0) * w.nf() + (f - w.f0);
   R numerator = R(0), denominator = R(0), first_val = R(0), first_dist = R(0);
   auto take = [&](int rank, int pos, R d2r) {
     const R dist = sqrt(d2r);
@@ -378,7 +395,7 @@ __global__ void __launch_bounds__(128) esrg_fast_kernel(const EsrgArgs<R> a) {
         }
       }
     }
-    const R rad = a.spac * (R(level) + R(0.5));                           // :141,:181
+    const R rad = a.spac * (R(level) + R(0.5));                             // :141,:181
     if (!(dmax > rad * rad)) break;                                       // k points within r_L: :178,:243
     ++level;
     if (level > level_full) {  // every cell scanned: the k smallest are final, the reference only grows its radius
@@ -740,6 +757,7 @@ int esrg_query_window(Scratch& scr, const Binned<R>& b, int num_points, const R*
   a.todo_count = counters + 3;
   a.all_exact = ((flags & GI_ESRG_REFERENCE_ORDER) || k > 32) ? 1 : 0;  // k > 32: only the exact kernel has the any-k list
   a.tk_d = nullptr; a.tk_id = nullptr; a.tk_stride = 0;
+  a.tgt = PointsView<R>{nullptr, 0, 0}; a.num_tgt = 0; a.x_axis = x_axis; a.y_axis = y_axis;
   // first halo level: where the mean point density puts about 1.5k+6 points within r_H = spac*(H+1/2), so
   // that all 32 lanes of a tile find k of them in the first pass with high probability (Poisson tail)
   const double density = (double)num_points / ((double)len_x * (double)len_y);
@@ -773,6 +791,55 @@ int esrg_query_window(Scratch& scr, const Binned<R>& b, int num_points, const R*
 }
 
 }  // namespace
+
+// idw_esrg_nearest (interpolation.f90:201-288 + query_esrg.f90) at scattered targets (m, 2) instead of the nodes of
+// the grid: the grid only defines the cell list; every target goes through the frame-by-frame kernel.
+template <class R>
+int esrg_points_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+                       int len_y, R grid_spac, const R* targets, int64_t num_targets, int k, R* data_ip,
+                       int32_t* nn_index, R* nn_dist2, int flags, cudaStream_t st) {
+  GI_REQUIRE(k >= 1, "num_neighbours must be at least 1");
+  GI_REQUIRE(num_points >= k, "fewer points than num_neighbours");
+  GI_REQUIRE(num_targets >= 0, "negative number of targets");
+  GI_TRY(ensure_device());
+  if (num_targets == 0) return GI_OK;
+  StatusSlot slot;
+  GI_TRY(get_status_slot(st, &slot));
+  Scratch scr(st);
+  Phases ph(st);
+  ph.mark("esrg_bin");
+  Binned<R> b;
+  GI_TRY(esrg_bin<R>(scr, points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, flags, &b));
+  ph.mark("esrg_query");
+  EsrgArgs<R> a;
+  a.win = TargetWindow<R>{nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0};
+  a.table = b.table; a.sxy = b.sxy; a.sval = b.sval; a.sid = b.sid; a.scell = b.scell;
+  a.len_x = len_x; a.len_y = len_y; a.k = k; a.spac = grid_spac;
+  a.out = data_ip; a.nn_index = nn_index; a.nn_dist2 = nn_dist2;
+  int64_t* counters;
+  GI_TRY(scr.alloc(&counters, 4));
+  GI_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t) * 4, st));
+  a.counters = counters; a.stats = 0; a.status = slot.dev;
+  a.todo = nullptr; a.todo_count = counters + 3; a.all_exact = 1;
+  a.tk_d = nullptr; a.tk_id = nullptr; a.tk_stride = 0;
+  a.tgt = points_n2(targets, num_targets, flags & GI_TARGETS_ROWMAJOR); a.num_tgt = num_targets;
+  a.x_axis = x_axis; a.y_axis = y_axis;
+  const int eg = kNumSMs * 8;
+  if (k <= 4) esrg_query_kernel<R, 4><<<eg, 128, 0, st>>>(a);
+  else if (k <= 8) esrg_query_kernel<R, 8><<<eg, 128, 0, st>>>(a);
+  else if (k <= 16) esrg_query_kernel<R, 16><<<eg, 128, 0, st>>>(a);
+  else if (k <= 32) esrg_query_kernel<R, 32><<<eg, 128, 0, st>>>(a);
+  else {
+    a.tk_stride = (int64_t)eg * 128;
+    GI_TRY(scr.alloc(&a.tk_d, (size_t)a.tk_stride * k));
+    GI_TRY(scr.alloc(&a.tk_id, (size_t)a.tk_stride * k));
+    esrg_query_kernel<R, 0><<<eg, 128, 0, st>>>(a);
+  }
+  GI_CUDA(cudaGetLastError());
+  ph.finish();
+  GI_TRY(flush_status(st, slot));
+  return GI_OK;
+}
 
 template <class R>
 int esrg_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
@@ -978,6 +1045,8 @@ int esrg_bin_device(const R* points, int num_points, const R* x_axis, int len_x,
 #define GI_INSTANTIATE(R)                                                                                        \
   template int esrg_device<R>(const R*, int, const R*, const R*, int, const R*, int, R, int, int, int, R*, int32_t*, \
                               R*, int64_t*, int, cudaStream_t);                                                  \
+  template int esrg_points_device<R>(const R*, int, const R*, const R*, int, const R*, int, R, const R*, int64_t,  \
+                                     int, R*, int32_t*, R*, int, cudaStream_t);                                   \
   template int esrg_bin_device<R>(const R*, int, const R*, int, const R*, int, R, int32_t*, int32_t*, int,        \
                                   cudaStream_t);                                                                  \
   template int esrg_host<R>(const R*, int, const R*, const R*, int, const R*, int, R, int, int, int, R*, int);  \

@@ -59,6 +59,11 @@ template <class R>
 int kdtree_points_device(const R* points, int num_points, const R* data_in, const R* targets, int64_t num_targets, int k,
                          R* data_ip, int32_t* nn_index, R* nn_dist2, int flags, cudaStream_t st);
 
+template <class R>
+int esrg_points_device(const R* points, int num_points, const R* data_in, const R* x_axis, int len_x, const R* y_axis,
+                       int len_y, R grid_spac, const R* targets, int64_t num_targets, int k, R* data_ip,
+                       int32_t* nn_index, R* nn_dist2, int flags, cudaStream_t st);
+
 // GI_HOST forms of the four operators (host pointers in, synchronous): copies and compute are pipelined over
 // output bands / point chunks (common.cuh, HostPipe).  No debug outputs; api.cu falls back to "copy in, *_device,
 // copy out" when those are requested.

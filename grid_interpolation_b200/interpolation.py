@@ -37,7 +37,7 @@ from ._lib import (GI_DEVICE, GI_FIELD_ROWMAJOR, GI_HOST, GI_KD_REFERENCE_VISITS
 __all__ = ["bilinear", "idw_kdtree", "idw_esrg_nearest", "barycentric_interpolation",
            "barycentric_interpolation_ex", "idw_kdtree_ex", "idw_esrg_nearest_ex", "kd_build",
            "assign_points_to_cells", "fill_nearest_neighbour", "pinned_empty", "pinned_copy",
-           "set_profiling", "set_pipeline_band_bytes", "set_fixup_list_capacity", "set_sliver_guard", "barycentric_points", "idw_kdtree_points", "bilinear_morton_order", "release_workspace", "pinned_trim",
+           "set_profiling", "set_pipeline_band_bytes", "set_fixup_list_capacity", "set_sliver_guard", "barycentric_points", "idw_kdtree_points", "idw_esrg_nearest_points", "bilinear_morton_order", "release_workspace", "pinned_trim",
            "last_timings", "BarycentricPlan", "KdTreePlan", "EsrgPlan"]
 
 _F64 = np.dtype(np.float64)
@@ -557,6 +557,37 @@ def idw_kdtree_points(points, data_in, targets, num_neighbours, *, debug=False, 
         st = getattr(lib(), "gi_idw_kdtree_points_" + suf)(p.ptr, n, d.ptr, tg.ptr, m, k, res_ptr, nn_ptr, d2_ptr, flags,
                                                           c.mem, c.stream)
         c.finish(st, "idw_kdtree_points", sync)
+        if not debug:
+            return res
+        return res, SimpleNamespace(nn_index=nn, nn_dist2=d2)
+
+
+def idw_esrg_nearest_points(points, data_in, x_axis, y_axis, grid_spac, targets, num_neighbours, *, debug=False,
+                            dtype=np.float64, sync=True):
+    """idw_esrg_nearest (interpolation.f90:201-288) at scattered ``targets`` (num_targets, 2): the grid only defines
+    the cell list; the ring search runs around each target's own cell with radius grid_spac * L per level (the exact
+    k nearest points, ascending).  debug=True also returns neighbour ids (1-based) and squared distances."""
+    rt, suf = _real(dtype)
+    with _Call(points) as c:
+        x, y, p, d, n = _grid_common(c, points, data_in, x_axis, y_axis, "n2", rt)
+        tg = c.arg(targets, rt, 2, "targets")
+        if tg.shape[1] != 2:
+            raise ValueError(f"targets must have shape (num_targets, 2), got {tg.shape}")
+        k = int(num_neighbours)
+        if k < 1:
+            raise ValueError("num_neighbours must be at least 1")
+        m = tg.shape[0]
+        res, res_ptr, _ = c.out((m,), rt, "C")
+        nn = d2 = None
+        nn_ptr = d2_ptr = None
+        if debug:
+            nn, nn_ptr, _ = c.out((m, k), np.int32, "C")
+            d2, d2_ptr, _ = c.out((m, k), rt, "C")
+        flags = (GI_POINTS_ROWMAJOR if p.rowmajor else 0) | (_lib.GI_TARGETS_ROWMAJOR if tg.rowmajor else 0)
+        st = getattr(lib(), "gi_idw_esrg_nearest_points_" + suf)(p.ptr, n, d.ptr, x.ptr, x.shape[0], y.ptr, y.shape[0],
+                                                                float(grid_spac), tg.ptr, m, k, res_ptr, nn_ptr, d2_ptr,
+                                                                flags, c.mem, c.stream)
+        c.finish(st, "idw_esrg_nearest_points", sync)
         if not debug:
             return res
         return res, SimpleNamespace(nn_index=nn, nn_dist2=d2)

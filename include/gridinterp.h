@@ -257,6 +257,19 @@ int gi_idw_kdtree_points_f64(const double* points, int num_points, const double*
 int gi_idw_kdtree_points_f32(const float* points, int num_points, const float* data_in, const float* targets,
                              int64_t num_targets, int num_neighbours, float* data_ip, int32_t* nn_index, float* nn_dist2,
                              int flags, int mem, void* stream);
+/* idw_esrg_nearest (interpolation.f90:201-288 + query_esrg.f90) at scattered targets: the grid (x_axis, y_axis,
+ * grid_spac) only defines the cell list the points are binned into; the ring search runs around the target's own
+ * cell and a level's radius is grid_spac * L instead of grid_spac * (L + 1/2) (the reference's targets sit at the
+ * cell centres, query_esrg.f90:133-134,141; a target anywhere in its cell is at least L cells from everything
+ * outside the (2L+1)^2 block) -> the exact k nearest points in ascending order, ties in the reference's order. */
+int gi_idw_esrg_nearest_points_f64(const double* points, int num_points, const double* data_in, const double* x_axis,
+                                   int len_x, const double* y_axis, int len_y, double grid_spac,
+                                   const double* targets, int64_t num_targets, int num_neighbours, double* data_ip,
+                                   int32_t* nn_index, double* nn_dist2, int flags, int mem, void* stream);
+int gi_idw_esrg_nearest_points_f32(const float* points, int num_points, const float* data_in, const float* x_axis,
+                                   int len_x, const float* y_axis, int len_y, float grid_spac, const float* targets,
+                                   int64_t num_targets, int num_neighbours, float* data_ip, int32_t* nn_index,
+                                   float* nn_dist2, int flags, int mem, void* stream);
 
 /* Row band [row_begin, row_end) of barycentric_interpolation computed on the current device and stored at its
  * place in num_fields (<= GI_MAX_GATHER_FIELDS) FULL (len_y, len_x) fields in the layout `flags` selects:

@@ -91,3 +91,51 @@ def test_idw_kdtree_points(c1, k):
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
     got_d = ip.idw_kdtree_points(dev(pts), dev(c1.data_pts), dev(targets), k)
     assert np.array_equal(got_d.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("k", [1, 6, 40])
+def test_idw_esrg_nearest_points(c1, k):
+    """Scattered targets through the cell list: the exact k nearest points in ascending order, i.e. what the k-d tree
+    oracle finds for the same targets (continuous random coordinates: no distance ties), and the same IDW sums
+    (interpolation.f90:260-274 == :164-178 on an ascending neighbour list)."""
+    targets = _targets(c1.points, 30_000, 7)
+    spac = float(c1.x_axis[1] - c1.x_axis[0])
+    want, w = orc.idw_kdtree_points(np.asfortranarray(c1.points.T), c1.data_pts, targets, k, debug=True)
+    got, g = ip.idw_esrg_nearest_points(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac, targets, k, debug=True)
+    assert np.array_equal(g.nn_index, w.nn_index) and np.array_equal(g.nn_dist2, w.nn_dist2)
+    assert np.array_equal(got, want)
+    # grid nodes as scattered targets: the grid entry point's bits
+    xx, yy = np.meshgrid(c1.x_axis, c1.y_axis)
+    nodes = np.stack([xx.ravel(), yy.ravel()], 1)
+    field = ip.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac, k, order="C")
+    assert np.array_equal(ip.idw_esrg_nearest_points(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac, nodes, k),
+                          field.ravel())
+    # device tensors, Fortran-ordered targets, single precision against the f32 oracle
+    import torch
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+    got_d = ip.idw_esrg_nearest_points(dev(c1.points), dev(c1.data_pts), dev(c1.x_axis), dev(c1.y_axis), spac,
+                                       dev(targets), k)
+    assert np.array_equal(got_d.cpu().numpy(), want)
+    assert np.array_equal(ip.idw_esrg_nearest_points(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac,
+                                                     np.asfortranarray(targets), k), want)
+    assert ip.idw_esrg_nearest_points(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac, np.zeros((0, 2)), k).shape == (0,)
+    f32 = np.float32
+    t32 = targets[:5000].astype(f32)
+    want32, w32 = orc.idw_kdtree_points(np.asfortranarray(c1.points.T.astype(f32)), c1.data_pts.astype(f32), t32, k,
+                                        dtype=f32, debug=True)
+    got32, g32 = ip.idw_esrg_nearest_points(c1.points.astype(f32), c1.data_pts.astype(f32), c1.x_axis.astype(f32),
+                                            c1.y_axis.astype(f32), f32(spac), t32, k, dtype=f32, debug=True)
+    assert np.array_equal(g32.nn_dist2, w32.nn_dist2)          # (ids may differ where two f32 distances tie)
+    same = (g32.nn_index == w32.nn_index).all(1)
+    assert same.mean() > 0.99 and np.array_equal(got32[same], want32[same])
+
+
+def test_idw_esrg_nearest_points_targets_far_outside_the_grid(c1):
+    rng = np.random.default_rng(11)
+    lo, hi = c1.points.min(0), c1.points.max(0)
+    targets = np.concatenate([rng.uniform(lo - 5 * (hi - lo), hi + 5 * (hi - lo), (5000, 2)),
+                              rng.uniform(lo - 1e4 * (hi - lo), hi + 1e4 * (hi - lo), (500, 2))])
+    spac = float(c1.x_axis[1] - c1.x_axis[0])
+    want, w = orc.idw_kdtree_points(np.asfortranarray(c1.points.T), c1.data_pts, targets, 6, debug=True)
+    got, g = ip.idw_esrg_nearest_points(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac, targets, 6, debug=True)
+    assert np.array_equal(g.nn_index, w.nn_index) and np.array_equal(got, want)
