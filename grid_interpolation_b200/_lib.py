@@ -18,6 +18,7 @@ GI_BILINEAR_SEARCH_AXES = 64
 GI_KD_FAITHFUL_BUILD = 128
 GI_BARY_REFERENCE_ORDER = 256
 GI_BARY_BAND_PACK = 512
+GI_BARY_PLANE_VALUES = 2048
 GI_TARGETS_ROWMAJOR = 1024
 GI_MAX_GATHER_FIELDS, GI_PEER_HANDLE_BYTES = 8, 64
 

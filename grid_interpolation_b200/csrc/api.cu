@@ -193,7 +193,7 @@ static int host_stream(cudaStream_t* out) {
 }
 
 static bool valid_flags(int flags) {
-  return (flags & ~(GI_POINTS_ROWMAJOR | GI_TOPO_ROWMAJOR | GI_FIELD_ROWMAJOR | GI_KD_REFERENCE_VISITS | GI_ESRG_REFERENCE_ORDER | GI_KD_EXACT_PRUNE | GI_BILINEAR_SEARCH_AXES | GI_KD_FAITHFUL_BUILD | GI_BARY_REFERENCE_ORDER | GI_BARY_BAND_PACK | GI_TARGETS_ROWMAJOR)) == 0;
+  return (flags & ~(GI_POINTS_ROWMAJOR | GI_TOPO_ROWMAJOR | GI_FIELD_ROWMAJOR | GI_KD_REFERENCE_VISITS | GI_ESRG_REFERENCE_ORDER | GI_KD_EXACT_PRUNE | GI_BILINEAR_SEARCH_AXES | GI_KD_FAITHFUL_BUILD | GI_BARY_REFERENCE_ORDER | GI_BARY_BAND_PACK | GI_TARGETS_ROWMAJOR | GI_BARY_PLANE_VALUES)) == 0;
 }
 #define GI_CHECK_COMMON()                                                 \
   GI_REQUIRE(valid_flags(flags), "unknown bits in flags");                \

@@ -64,6 +64,7 @@ template <class R> struct TriGeom;
 template <class R>
 __device__ __forceinline__ bool tri_tile_range(const TriGeom<R>& g, const TargetWindow<R>& w, int& tx0, int& tx1, int& ty0, int& ty1);
 template <class R> __device__ __forceinline__ void check_axes(const TargetWindow<R>& w, int t, int* bad);
+template <class R> __device__ __forceinline__ void plane_of(TriGeom<R>& g);
 
 
 
@@ -77,8 +78,10 @@ template <class R> __device__ __forceinline__ void check_axes(const TargetWindow
 template <class R> struct alignas(sizeof(R) == 8 ? 32 : 16) TriGeom {
   R x1, y1, x2, y2, x3, y3;
   int n1, n2, n3;  // neighbour opposite vertex 1/2/3, 0-based, -1 = hull edge, -2 = not packed (band-limited pack)
-  int pad;         // bits 1-30: ambiguity threshold of this triangle (bit pattern, see amb_threshold); bit 31:
-                   // long triangle (kLongTriangle); bit 0: hull sliver, not to be interpolated in (kSliver)
+  int pad;         // bits 2-30: ambiguity threshold of this triangle (bit pattern, see amb_threshold); bit 31:
+                   // long triangle (kLongTriangle); bit 0: hull sliver, not to be interpolated in (kSliver);
+                   // bit 1: sector 2 holds the triangle's plane instead (kPlane, GI_BARY_PLANE_VALUES):
+                   // denom = gx, d1 = gy, d2 = d3 of the text, d3 unused
   R denom, d1, d2, d3;
 };
 static_assert(sizeof(TriGeom<double>) == 96 && sizeof(TriGeom<float>) == 64, "record layout");
@@ -112,6 +115,18 @@ __device__ __forceinline__ void load_eval(const TriGeom<double>* p, TriGeom<doub
   ld256(reinterpret_cast<const char*>(p) + 64, g.denom, g.d1, g.d2, g.d3);
 }
 __device__ __forceinline__ void load_eval(const TriGeom<float>* p, TriGeom<float>& g) { g = *p; }
+// plane evaluation (GI_BARY_PLANE_VALUES): sectors 1 and 2 only
+__device__ __forceinline__ void load_plane(const TriGeom<double>* p, double& x3, double& y3, int& pad, double& s0,
+                                           double& s1, double& s2, double& s3) {
+  double n12, w;
+  ld256(reinterpret_cast<const char*>(p) + 32, x3, y3, n12, w);
+  ld256(reinterpret_cast<const char*>(p) + 64, s0, s1, s2, s3);
+  pad = __double2hiint(w);
+}
+__device__ __forceinline__ void load_plane(const TriGeom<float>* p, float& x3, float& y3, int& pad, float& s0, float& s1,
+                                           float& s2, float& s3) {
+  x3 = p->x3; y3 = p->y3; pad = p->pad; s0 = p->denom; s1 = p->d1; s2 = p->d2; s3 = p->d3;
+}
 // new nodal values (plans): sector 2 as ONE full-sector store; denom comes from the plan's own copy (reading it
 // back from the record is a 32 B read-modify-write per 96 B record: 0.33 ms instead of 0.2 ms at C4)
 __device__ __forceinline__ void store_values(TriGeom<double>* p, double denom, double d1, double d2, double d3) {
@@ -122,6 +137,17 @@ __device__ __forceinline__ void store_values(TriGeom<double>* p, double denom, d
 __device__ __forceinline__ void store_values(TriGeom<float>* p, float denom, float d1, float d2, float d3) {
   p->denom = denom; p->d1 = d1; p->d2 = d2; p->d3 = d3;
 }
+// a whole record, written once and not read again by the writing pass: three full-sector stores, evict_first in L2
+__device__ __forceinline__ void store_record(TriGeom<double>* p, const TriGeom<double>& g, unsigned long long pol) {
+  const double n12 = __hiloint2double(g.n2, g.n1), w = __hiloint2double(g.pad, g.n3);
+  asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(g.x1), "d"(g.y1), "d"(g.x2),
+               "d"(g.y2), "l"(pol) : "memory");
+  asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(reinterpret_cast<char*>(p) + 32),
+               "d"(g.x3), "d"(g.y3), "d"(n12), "d"(w), "l"(pol) : "memory");
+  asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(reinterpret_cast<char*>(p) + 64),
+               "d"(g.denom), "d"(g.d1), "d"(g.d2), "d"(g.d3), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void store_record(TriGeom<float>* p, const TriGeom<float>& g, unsigned long long) { *p = g; }
 // Fire-and-forget load of sector 2: the registers are never read, so nothing waits on them, but the sector
 // is in L1 when phase 2 asks for it a few thousand cycles later (prefetch.global.L1 had no measurable effect).
 __device__ __forceinline__ void touch_values(const TriGeom<double>* p) {
@@ -153,7 +179,8 @@ __device__ __forceinline__ SeedGrid<R> seed_grid_of(const R* __restrict__ x_axis
 constexpr int kNotPacked = -2;
 constexpr int kLongTriangle = (int)0x80000000;  // sign bit of TriGeom::pad, see farthest_failing_edge
 constexpr int kSliver = 1;                      // bit 0 of TriGeom::pad, see sliver_guard
-constexpr int kThrMask = 0x7ffffffe;            // the threshold bits of TriGeom::pad
+constexpr int kPlane = 2;                       // bit 1 of TriGeom::pad, see plane_of
+constexpr int kThrMask = 0x7ffffffc;            // the threshold bits of TriGeom::pad
 template <class R>
 __global__ void __launch_bounds__(256)
 need_kernel(PointsView<R> pts, TopoView simp, int num_points, int num_tri, const R* __restrict__ y_axis, int row_lo,
@@ -196,7 +223,7 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
                  int num_tri, TriGeom<R>* __restrict__ geom, int* __restrict__ seed,
                  const R* __restrict__ x_axis, int len_x, const R* __restrict__ y_axis, int len_y,
                  const uint8_t* __restrict__ need, const TargetWindow<R> bw, const TileBins bb, R sliver_q,
-                 int* __restrict__ status) {
+                 int plane, int* __restrict__ status) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool packed = t < num_tri && (!need || need[t]);
   if (BINS) {  // rasteriser (raster.cuh): axes usable?  A triangle without a record is in no tile.
@@ -212,8 +239,11 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
   }
   if (!packed) return;
   const SeedGrid<R> sg = seed_grid_of(x_axis, len_x, y_axis, len_y);
-  int a = simp(t, 0), b = simp(t, 1), c = simp(t, 2);
-  int n1 = nbr(t, 0), n2 = nbr(t, 1), n3 = nbr(t, 2);
+  // L2 residency (common.cuh): ids and records stream through once (evict_first), vertices and nodal values are
+  // gathered three to six times each from arrays that fit the L2 (evict_last)
+  const unsigned long long keep = l2_evict_last(), once = l2_evict_first();
+  int a = simp(t, 0, once), b = simp(t, 1, once), c = simp(t, 2, once);
+  int n1 = nbr(t, 0, once), n2 = nbr(t, 1, once), n3 = nbr(t, 2, once);
   const bool bad = (unsigned)(a - 1) >= (unsigned)num_points || (unsigned)(b - 1) >= (unsigned)num_points ||
                    (unsigned)(c - 1) >= (unsigned)num_points || (unsigned)n1 > (unsigned)num_tri ||
                    (unsigned)n2 > (unsigned)num_tri || (unsigned)n3 > (unsigned)num_tri;
@@ -223,9 +253,9 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
     n1 = n2 = n3 = 0;
   }
   TriGeom<R> g;
-  pts.xy(a - 1, g.x1, g.y1);
-  pts.xy(b - 1, g.x2, g.y2);
-  pts.xy(c - 1, g.x3, g.y3);
+  pts.xy(a - 1, g.x1, g.y1, keep);
+  pts.xy(b - 1, g.x2, g.y2, keep);
+  pts.xy(c - 1, g.x3, g.y3, keep);
   g.n1 = n1 - 1; g.n2 = n2 - 1; g.n3 = n3 - 1;
   if (need) {
     if (n1 > 0 && !need[n1 - 1]) g.n1 = kNotPacked;
@@ -243,8 +273,9 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
     g.denom = A * D + B * (g.y1 - g.y3);                                           // :385-386
   }
   if (sliver_q > R(0) && (n1 == 0 || n2 == 0 || n3 == 0) && sliver_quality(g) < sliver_q) g.pad |= kSliver;
-  g.d1 = __ldg(data + (a - 1)); g.d2 = __ldg(data + (b - 1)); g.d3 = __ldg(data + (c - 1));
-  geom[t] = g;
+  g.d1 = ldg_hint(data + (a - 1), keep); g.d2 = ldg_hint(data + (b - 1), keep); g.d3 = ldg_hint(data + (c - 1), keep);
+  if (plane) plane_of(g);
+  store_record(geom + t, g, once);
   if (BINS) {  // first binning pass: count this triangle in the tiles its bounds meet
     int tx0 = 1, tx1 = 0, ty0 = 1, ty1 = 0;
     if (!bad && tri_tile_range(g, bw, tx0, tx1, ty0, ty1))
@@ -260,18 +291,34 @@ pack_mesh_kernel(PointsView<R> pts, const R* __restrict__ data, TopoView simp, T
     atomicMin(seed + (int)fy * sg.ncx + (int)fx, t);
 }
 
-// plans: new nodal values into sector 2 of the existing records (ids were validated by pack_mesh_kernel)
+// plans: new nodal values into sector 2 of the existing records (ids were validated by pack_mesh_kernel).
+// plane != 0 (GI_BARY_PLANE_VALUES): the record's vertices are read back and the plane recomputed where the record
+// is a plane record (the choice is geometric, see plane_of).
 template <class R>
 __global__ void __launch_bounds__(256)
 pack_values_kernel(const R* __restrict__ data, TopoView simp, int num_points, int num_tri, const R* __restrict__ denom,
-                   TriGeom<R>* __restrict__ geom) {
+                   TriGeom<R>* __restrict__ geom, int plane) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= num_tri) return;
   int a = simp(t, 0), b = simp(t, 1), c = simp(t, 2);
   if ((unsigned)(a - 1) >= (unsigned)num_points || (unsigned)(b - 1) >= (unsigned)num_points ||
       (unsigned)(c - 1) >= (unsigned)num_points)
     a = b = c = 1;
-  store_values(geom + t, __ldg(denom + t), __ldg(data + (a - 1)), __ldg(data + (b - 1)), __ldg(data + (c - 1)));
+  const R d1 = __ldg(data + (a - 1)), d2 = __ldg(data + (b - 1)), d3 = __ldg(data + (c - 1));
+  if (plane) {
+    TriGeom<R> g;
+    load_walk(geom + t, g);
+    if (g.pad & kPlane) {
+      const R A = g.y2 - g.y3, B = g.x3 - g.x2, D = g.x1 - g.x3;
+      g.denom = A * D + B * (g.y1 - g.y3);
+      g.d1 = d1; g.d2 = d2; g.d3 = d3;
+      g.pad &= ~kPlane;
+      plane_of(g);   // same geometry, same answer: a plane record again
+      store_values(geom + t, g.denom, g.d1, g.d2, g.d3);
+      return;
+    }
+  }
+  store_values(geom + t, __ldg(denom + t), d1, d2, d3);
 }
 
 // plans: the records' denominators as an array of their own (see store_values)
@@ -414,6 +461,44 @@ __device__ __forceinline__ R eval_value(const TriGeom<R>& g, R tx, R ty) {
   return g.d1 * w1 + g.d2 * w2 + g.d3 * w3;
 }
 
+// GI_BARY_PLANE_VALUES (opt-in): the value as the triangle's plane through its three nodal values,
+//     v = d3 + gx*(tx - x3) + gy*(ty - y3),   gx = ((d1-d3)*A + (d2-d3)*C)/denom,  gy = ((d1-d3)*B + (d2-d3)*D)/denom
+// (A..D, denom of interpolation.f90:385-394; the same affine function the reference evaluates through its weights),
+// computed as fma(gy, ty - y3, d3 + gx*(tx - x3)) by every path that produces a value, so that bands, fix-ups and the
+// hull fill agree bit for bit among themselves.  Against the reference's expression the two roundings differ by at
+// most ~16 eps * cond * max|d| with cond = max|edge|^2 / |denom|; triangles with cond > kPlaneCond (needles: a few in
+// 10^5 of a random Delaunay mesh, and the slivers along the hull) keep the exact record and the reference's
+// expression, which bounds the difference by ~1e-12 * max|d| in double precision (north_star's tolerance; tested in
+// tests/test_gpu_plane.py).  What it saves: 18 FP64 operations + the division guards per target become 2.
+constexpr int kPlaneCond = 128;
+template <class R> __device__ __forceinline__ void plane_of(TriGeom<R>& g) {
+  const R A = g.y2 - g.y3, B = g.x3 - g.x2, C = g.y3 - g.y1, D = g.x1 - g.x3;
+  const R l1 = (g.x2 - g.x1) * (g.x2 - g.x1) + (g.y2 - g.y1) * (g.y2 - g.y1);
+  const R l2 = B * B + A * A;
+  const R l3 = D * D + C * C;
+  const R lmax = fmax(fmax(l1, l2), l3);
+  // (written so that a NaN or zero denom, or an overflowing edge length, fails the test)
+  if (!(fabs(g.denom) * R(kPlaneCond) >= lmax) || !(lmax < Consts<R>::huge()) || !(fabs(g.denom) > R(0))) return;
+  const R e1 = g.d1 - g.d3, e2 = g.d2 - g.d3;
+  const R gx = (e1 * A + e2 * C) / g.denom, gy = (e1 * B + e2 * D) / g.denom;
+  g.denom = gx; g.d1 = gy; g.d2 = g.d3; g.d3 = R(0);
+  g.pad |= kPlane;
+}
+template <class R> __device__ __forceinline__ R eval_plane(R gx, R gy, R d3, R x3, R y3, R tx, R ty) {
+  return fma(gy, ty - y3, d3 + gx * (tx - x3));
+}
+// the value of a target in the triangle of record g, whichever form the record has
+template <class R> __device__ __forceinline__ R eval_any(const TriGeom<R>& g, R tx, R ty) {
+  if (g.pad & kPlane) return eval_plane(g.denom, g.d1, g.d2, g.x3, g.y3, tx, ty);
+  return eval_value(g, tx, ty);
+}
+// out of line: the rare exact record met by the plane instantiation of evaluate_strip
+template <class R> __device__ __noinline__ R eval_exact_record(const TriGeom<R>* p, R tx, R ty) {
+  TriGeom<R> g;
+  load_eval(p, g);
+  return eval_value(g, tx, ty);
+}
+
 // When is a located target path-dependent?  A target accepted by this triangle (every cross >= -1e-10,
 // triangle_walk.f90:148-151) is ALSO accepted by the neighbour behind edge i iff that neighbour's own evaluation of
 // the shared edge, cross' = -cross + delta, is >= -1e-10, i.e. iff cross <= 1e-10 + delta.  delta is the rounding
@@ -429,14 +514,14 @@ template <> __device__ __forceinline__ int amb_threshold<double>(const TriGeom<d
   const double b = (g.x3 - g.x2) * (g.x3 - g.x2) + (g.y3 - g.y2) * (g.y3 - g.y2);
   const double c = (g.x1 - g.x3) * (g.x1 - g.x3) + (g.y1 - g.y3) * (g.y1 - g.y3);
   const double t = 2e-10 + 32.0 * 1.1102230246251565e-16 * fmax(fmax(a, b), c);
-  return t < 1e300 ? (__double2hiint(t) + 2) & kThrMask : 0x7fe00000;  // rounded up, bit 0 left free
+  return t < 1e300 ? (__double2hiint(t) + 4) & kThrMask : 0x7fe00000;  // rounded up, bits 0-1 left free
 }
 template <> __device__ __forceinline__ int amb_threshold<float>(const TriGeom<float>& g) {
   const float a = (g.x2 - g.x1) * (g.x2 - g.x1) + (g.y2 - g.y1) * (g.y2 - g.y1);
   const float b = (g.x3 - g.x2) * (g.x3 - g.x2) + (g.y3 - g.y2) * (g.y3 - g.y2);
   const float c = (g.x1 - g.x3) * (g.x1 - g.x3) + (g.y1 - g.y3) * (g.y1 - g.y3);
   const float t = 2e-10f + 32.0f * 5.9604645e-8f * fmaxf(fmaxf(a, b), c);
-  return t < 1e37f ? (__float_as_int(t) + 2) & kThrMask : 0x7f000000;
+  return t < 1e37f ? (__float_as_int(t) + 4) & kThrMask : 0x7f000000;
 }
 // |x| below the triangle's threshold?  Integer compares on the (high) word: two instructions per cross.
 // (thr = the record's pad without its kLongTriangle bit)
@@ -514,7 +599,7 @@ template <class R> struct WalkArgs {
 // Phase 2 of the locate / raster kernels: evaluate one strip of ROWS x kWalkThreads targets whose triangles are in
 // the shared-memory tile `stri` (>= 0: inside that triangle; < 0: outside the hull, ~id of the last valid triangle
 // or -1), store the values and the outside-hull mask words.
-template <class R, bool FY, bool PEERS, int ROWS>
+template <class R, bool FY, bool PEERS, int ROWS, bool PLANE = false>
 __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (*stri)[kWalkThreads], const R* saxis,
                                                int srow0, int nrows, int lane_f, bool active, R cf) {
   const TargetWindow<R>& w = a.win;
@@ -531,6 +616,7 @@ __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (
   static_assert(ROWS <= 32, "one lane per row keeps that row's mask word");
   const int rb0 = max(0, a.bs0 - srow0), rb1 = min(nrows, a.bs1 - srow0);   // rows of the strip inside the band
   int cur = -1;
+  bool cur_exact = false;
   unsigned my_mask = 0;
   R c1 = 0, q1 = 0, c2 = 0, q2 = 0, p3 = 0, d1 = 0, d2 = 0, d3 = 0;
   DivRcp<R> dv;
@@ -541,6 +627,24 @@ __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (
     const bool inside = t >= 0;
     if (f_in_band && r >= rb0 && r < rb1) {
       if (inside) {
+        R v;
+        if (PLANE) {
+          // GI_BARY_PLANE_VALUES (see plane_of): two record sectors per triangle change, 2 (fast axis x) or 4 FP64
+          // operations per target; c1 = the row-independent part, q1 / q2 = gx / gy, d3 = the text's d3.
+          // cur_exact: this triangle kept the exact record (a needle): the reference's expression, out of line.
+          if (t != cur) {
+            cur = t;
+            R x3, y3, gx, gy, g3, unused;
+            int plane_pad;
+            load_plane(a.geom + t, x3, y3, plane_pad, gx, gy, g3, unused);
+            cur_exact = !(plane_pad & kPlane);
+            if (!FY) { c1 = g3 + gx * (cf - x3); q2 = gy; p3 = y3; }
+            else { c1 = cf - y3; q1 = gx; q2 = gy; d3 = g3; p3 = x3; }
+          }
+          if (cur_exact) v = eval_exact_record(a.geom + t, FY ? saxis[r] : cf, FY ? cf : saxis[r]);
+          else if (!FY) v = fma(q2, saxis[r] - p3, c1);
+          else v = fma(q2, c1, d3 + q1 * (saxis[r] - p3));
+        } else {
         if (t != cur) {
           cur = t;
           TriGeom<R> g;
@@ -556,7 +660,8 @@ __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (
         R w1, w2;
         quotient_pair(dv, FY ? q1 * t3 + c1 : c1 + q1 * t3, FY ? q2 * t3 + c2 : c2 + q2 * t3, w1, w2);
         const R w3 = R(1) - w1 - w2;
-        const R v = d1 * w1 + d2 * w2 + d3 * w3;                   // :396-398
+        v = d1 * w1 + d2 * w2 + d3 * w3;                           // :396-398
+        }
         // band-relative element (computed per row: pointers carried through the loop cost registers, and spills)
         const int64_t oo = (int64_t)(srow0 + r - a.bs0) * a.out_ld + (f - a.bf0);
         a.out[oo] = v;
@@ -593,7 +698,7 @@ __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (
 //                      shared-reciprocal divisions; 128 consecutive doubles per row are stored coalesced and
 //                      the outside-hull bits come from one ballot per warp row.
 // ---------------------------------------------------------------------------------------------
-template <class R, bool FY, bool PEERS, int ROWS, bool BP, bool CF>
+template <class R, bool FY, bool PEERS, int ROWS, bool BP, bool CF, bool PLANE = false>
 __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, int by, int (*stri)[kWalkThreads], R* saxis) {
   const TargetWindow<R>& w = a.win;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -690,17 +795,17 @@ __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, i
   }
   __syncthreads();
 
-  evaluate_strip<R, FY, PEERS, ROWS>(a, stri, saxis, srow0, nrows, lane_f, active, cf);
+  evaluate_strip<R, FY, PEERS, ROWS, PLANE>(a, stri, saxis, srow0, nrows, lane_f, active, cf);
   // one atomic per warp for the iteration counter (iters_tot, interpolation.f90:374)
   for (int off = 16; off > 0; off >>= 1) iters_sum += __shfl_down_sync(0xffffffffu, iters_sum, off);
   if (lane == 0 && iters_sum) atomicAdd((unsigned long long*)a.counters, (unsigned long long)iters_sum);
 }
 
-template <class R, bool FY, bool PEERS, int ROWS, int MINB, bool BP, bool CF>
+template <class R, bool FY, bool PEERS, int ROWS, int MINB, bool BP, bool CF, bool PLANE = false>
 __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const WalkArgs<R> a) {
   __shared__ int stri[ROWS][kWalkThreads];
   __shared__ R saxis[ROWS];
-  locate_eval_tile<R, FY, PEERS, ROWS, BP, CF>(a, blockIdx.x, blockIdx.y, stri, saxis);
+  locate_eval_tile<R, FY, PEERS, ROWS, BP, CF, PLANE>(a, blockIdx.x, blockIdx.y, stri, saxis);
 }
 
 // The same as a stand-by for the rasteriser (raster.cuh): a small grid that returns at once unless the device
@@ -731,7 +836,7 @@ __device__ __forceinline__ void publish_target(const WalkArgs<R>& a, int f, int 
       TriGeom<R> g;
       load_eval(a.geom + tri, g);
       const int64_t oo = (int64_t)(s - a.bs0) * a.out_ld + (f - a.bf0);
-      const R v = eval_value(g, tx, ty);
+      const R v = eval_any(g, tx, ty);
       a.out[oo] = v;
       for (int d = 0; d < a.n_peer; ++d) a.peer_out[d][oo] = v;
     }
@@ -1098,7 +1203,7 @@ __global__ void __launch_bounds__(128) fill_kernel(const FillArgs<R> a) {
       bool inside; int iters; TriGeom<R> g;
       const int tri = walk(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, best_j, best_i, a.num_tri), tx, ty,
                            a.iter_cap, inside, iters, g, a.status);
-      v = eval_value(g, tx, ty);
+      v = eval_any(g, tx, ty);
     }
     const int64_t oo = (int64_t)(s - a.vs0) * a.out_ld + (f - a.vf0);
     a.out[oo] = v;  // :121
@@ -1153,6 +1258,7 @@ template <class R> struct PackedMesh {
   const uint8_t* need;  // band-limited pack: which triangles have records (nullptr: all)
   TileBins bins;        // rasteriser: tile lists of the rows [bin_e0, bin_e1) (start == nullptr: none)
   int bin_e0, bin_e1;
+  int plane;            // GI_BARY_PLANE_VALUES: records hold planes (kPlane) where the triangle's shape allows
 };
 
 // Rasteriser or walk?  Measured on C4 (profiles/r02_raster_*): the rasteriser needs 3.4 ms where the walk needs
@@ -1183,6 +1289,7 @@ int bary_pack(Scratch& scr, const R* points, int num_points, const R* data_in, c
   const PointsView<R> pv = points_n2(points, num_points, flags & GI_POINTS_ROWMAJOR);
   const TopoView sv = topo_t3(simplices, num_tri, flags & GI_TOPO_ROWMAJOR);
   pm->raw = RawMesh<R>{pv, sv, num_points, 0};
+  pm->plane = (flags & GI_BARY_PLANE_VALUES) ? 1 : 0;
   uint8_t* need = nullptr;
   // band-limited pack: rows [w0, w1) +- kPackMarginRows, when that is a real subset of the grid
   if (w1 < 0) w1 = len_y;
@@ -1200,7 +1307,7 @@ int bary_pack(Scratch& scr, const R* points, int num_points, const R* data_in, c
   pm->bin_e0 = w0; pm->bin_e1 = w1;
   TargetWindow<R> bw{};
   int n_threads = num_tri;
-  if (w0 < w1 && use_raster<R>(num_tri, (int64_t)len_x * (w1 - w0))) {
+  if (w0 < w1 && !pm->plane && use_raster<R>(num_tri, (int64_t)len_x * (w1 - w0))) {
     bw = (flags & GI_FIELD_ROWMAJOR) ? TargetWindow<R>{x_axis, y_axis, len_x, len_y, 0, len_x, w0, w1, 0}
                                      : TargetWindow<R>{y_axis, x_axis, len_y, len_x, w0, w1, 0, len_x, 1};
     GI_TRY(alloc_tile_bins<R>(scr, num_tri, bw, &pm->bins));
@@ -1210,11 +1317,11 @@ int bary_pack(Scratch& scr, const R* points, int num_points, const R* data_in, c
   if (pm->bins.start)
     pack_mesh_kernel<R, true><<<div_up(n_threads, 256), 256, 0, st>>>(pv, data_in, sv, nv, num_points, num_tri, pm->geom,
                                                                      pm->seed, x_axis, len_x, y_axis, len_y, need, bw,
-                                                                     pm->bins, (R)sliver_guard_quality(), status);
+                                                                     pm->bins, (R)sliver_guard_quality(), pm->plane, status);
   else
     pack_mesh_kernel<R, false><<<div_up(n_threads, 256), 256, 0, st>>>(pv, data_in, sv, nv, num_points, num_tri, pm->geom,
                                                                       pm->seed, x_axis, len_x, y_axis, len_y, need, bw,
-                                                                      pm->bins, (R)sliver_guard_quality(), status);
+                                                                      pm->bins, (R)sliver_guard_quality(), pm->plane, status);
   GI_CUDA(cudaGetLastError());
   if (pm->bins.start) GI_TRY(finish_tile_bins(scr, num_tri, pm->bins));
   return GI_OK;
@@ -1252,10 +1359,15 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
     // dependent walks without it (band of 2048 rows: 1.25 instead of 0.43 ms); in a window of many CTA waves those
     // strips are not the critical path and the test is 2 % of the kernel, so it is compiled out there
     const bool cf = (int64_t)grid.x * grid.y < (int64_t)kNumSMs * 8 * 24;
-#define GI_LAUNCH_WALK2(FY_, PEERS_, BP_)                                                                \
-  do {                                                                                                   \
-    if (cf) locate_eval_kernel<R, FY_, PEERS_, kRows, 8, BP_, true><<<grid, kWalkThreads, 0, st>>>(wa);    \
-    else locate_eval_kernel<R, FY_, PEERS_, kRows, 8, BP_, false><<<grid, kWalkThreads, 0, st>>>(wa);      \
+#define GI_LAUNCH_WALK3(FY_, PEERS_, BP_, CF_)                                                                  \
+  do {                                                                                                          \
+    if (pm.plane) locate_eval_kernel<R, FY_, PEERS_, kRows, 8, BP_, CF_, true><<<grid, kWalkThreads, 0, st>>>(wa); \
+    else locate_eval_kernel<R, FY_, PEERS_, kRows, 8, BP_, CF_, false><<<grid, kWalkThreads, 0, st>>>(wa);         \
+  } while (0)
+#define GI_LAUNCH_WALK2(FY_, PEERS_, BP_)           \
+  do {                                              \
+    if (cf) GI_LAUNCH_WALK3(FY_, PEERS_, BP_, true);  \
+    else GI_LAUNCH_WALK3(FY_, PEERS_, BP_, false);    \
   } while (0)
 #define GI_LAUNCH_WALK(FY_, PEERS_)                     \
   do {                                                  \
@@ -1268,6 +1380,7 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
     else GI_LAUNCH_WALK(true, true);
 #undef GI_LAUNCH_WALK
 #undef GI_LAUNCH_WALK2
+#undef GI_LAUNCH_WALK3
   }
   GI_CUDA(cudaGetLastError());
   // targets inside the margin band of an edge: follow the reference's own path (normally none)
@@ -1637,7 +1750,7 @@ template <class R> struct BaryPlan : PlanBase {
     }
     ph.mark("pack_values");
     pack_values_kernel<R><<<div_up(pm.num_tri, 256), 256, 0, st>>>(dd, topo_t3(simp, pm.num_tri, flags & GI_TOPO_ROWMAJOR),
-                                                                  num_points, pm.num_tri, denom, pm.geom);
+                                                                  num_points, pm.num_tri, denom, pm.geom, pm.plane);
     GI_CUDA(cudaGetLastError());
     ph.mark("walk");
     if (mem == GI_HOST) {
@@ -1672,6 +1785,9 @@ int barycentric_plan_create(const R* points, int num_points, const R* x_axis, in
   plan->num_points = num_points; plan->len_x = len_x; plan->len_y = len_y;
   plan->row_begin = row_begin; plan->row_end = row_end; plan->halo = halo; plan->flags = flags;
   Scratch tmp(st);
+  // bary_pack launches on its scratch's stream: the plan's creation stream, not the legacy default stream (the
+  // pipeline streams are non-blocking, so work on stream 0 is not ordered with them)
+  plan->keep.set_stream(st);
   const cudaMemcpyKind kind = mem == GI_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   GI_TRY(plan->keep.alloc(&plan->dx, (size_t)len_x));
   GI_TRY(plan->keep.alloc(&plan->dy, (size_t)len_y));
@@ -1882,7 +1998,7 @@ bary_points_kernel(const TriGeom<R>* __restrict__ geom, const int* __restrict__ 
     R qx = tx, qy = ty;
     if (edge >= 0) closest_on_hull(geom, tri, edge, tx, ty, num_tri + 16, qx, qy, status);
     load_eval(geom + tri, g);
-    out[i] = eval_value(g, qx, qy);
+    out[i] = eval_any(g, qx, qy);
     if (tri_out) tri_out[i] = tri + 1;
     if (outside_out) outside_out[i] = edge >= 0 ? 1 : 0;
   }

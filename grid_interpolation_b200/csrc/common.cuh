@@ -59,6 +59,47 @@ template <> struct Consts<float> {
 };
 
 // ---------------------------------------------------------------------------------------------
+// L2 residency hints (createpolicy + .L2::cache_hint).  For passes that stream large arrays once while gathering
+// from arrays that fit the 126 MB L2: the streams are marked evict_first so that they do not push the gathered
+// lines out (pack_mesh_kernel: 1.2 GB of index / record traffic against 120 MB of vertices and nodal values).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long l2_evict_last() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_evict_first() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ int ldg_hint(const int* p, unsigned long long pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double ldg_hint(const double* p, unsigned long long pol) {
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ldg_hint(const float* p, unsigned long long pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double2 ldg_hint(const double2* p, unsigned long long pol) {
+  double2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_hint(const float2* p, unsigned long long pol) {
+  float2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // stride-generic views
 // ---------------------------------------------------------------------------------------------
 template <class R> struct PointsView {  // x(i) = base[i*stride], y(i) = base[i*stride + yoff]
@@ -80,6 +121,20 @@ template <class R> struct PointsView {  // x(i) = base[i*stride], y(i) = base[i*
       px = x(i); py = y(i);
     }
   }
+  // the same with an L2 cache policy (see l2_evict_last)
+  __device__ __forceinline__ void xy(int64_t i, R& px, R& py, unsigned long long pol) const {
+    if (stride == 2 && yoff == 1 && (reinterpret_cast<uintptr_t>(base) & (2 * sizeof(R) - 1)) == 0) {
+      if (sizeof(R) == 8) {
+        const double2 v = ldg_hint(reinterpret_cast<const double2*>(base) + i, pol);
+        px = (R)v.x; py = (R)v.y;
+      } else {
+        const float2 v = ldg_hint(reinterpret_cast<const float2*>(base) + i, pol);
+        px = (R)v.x; py = (R)v.y;
+      }
+    } else {
+      px = ldg_hint(base + i * stride, pol); py = ldg_hint(base + i * stride + yoff, pol);
+    }
+  }
 };
 // (n,2) array: Fortran order = SoA, C order = interleaved
 template <class R> inline PointsView<R> points_n2(const R* p, int64_t n, bool rowmajor) {
@@ -93,6 +148,9 @@ struct TopoView {  // a(t,c) = base[t*st + c*sc], t 0-based triangle, c in 0..2
   const int32_t* base;
   int64_t st, sc;
   __device__ __forceinline__ int operator()(int64_t t, int c) const { return __ldg(base + t * st + c * sc); }
+  __device__ __forceinline__ int operator()(int64_t t, int c, unsigned long long pol) const {
+    return ldg_hint(base + t * st + c * sc, pol);
+  }
 };
 inline TopoView topo_t3(const int32_t* p, int64_t t, bool rowmajor) {
   return rowmajor ? TopoView{p, 3, 1} : TopoView{p, 1, t};
@@ -148,6 +206,7 @@ class Scratch {
     ptrs_.clear();
   }
   cudaStream_t stream() const { return stream_; }
+  void set_stream(cudaStream_t s) { stream_ = s; }   // persistent scratch: the stream its owner's kernels run on
 
  private:
   cudaStream_t stream_;

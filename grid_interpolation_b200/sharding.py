@@ -36,6 +36,43 @@ def row_band(len_y: int, rank: int, world: int) -> Tuple[int, int]:
     return split_range(len_y, world)[rank]
 
 
+def gather_bands(len_y: int, world: int, dest: int, dest_share: float, align: int = 32) -> List[Tuple[int, int]]:
+    """Row bands for a gather onto rank ``dest``: that rank computes ``dest_share`` of the rows, the others split the
+    rest evenly (band heights are multiples of ``align`` rows, the strip height of the locate / evaluate kernel,
+    except for one remainder band).
+
+    Why uneven: when the field is gathered onto ONE rank, that rank's NVLink ingress carries (1 - share) of the field
+    (2.1 GB at 16384 x 16384 doubles: 2.1 ms at 900 GB/s for 7/8 of it) while its SMs finish a 1/N band in a fraction
+    of that.  Peer stores need no SM on the receiving side, so the gathering rank can compute a larger band while the
+    rest arrives: the step is shortest where compute(share) = ingress(1 - share)."""
+    if not 0 <= dest < world:
+        raise ValueError("dest must be a rank of the group")
+    if world == 1:
+        return [(0, len_y)]
+    if len_y < 4 * align * world:      # small fields: no point in aligning, and no rank should end up empty
+        align = 1
+    share = min(max(float(dest_share), 0.0), 1.0)
+    n_dest = int(round(share * len_y / align)) * align
+    n_dest = min(max(n_dest, min(align, len_y)), len_y)
+    rest_rows = len_y - n_dest
+    units = split_range((rest_rows + align - 1) // align, world - 1)        # the other ranks, in units of `align` rows
+    other, used = [], 0
+    for lo_u, hi_u in units:                                               # the last of them absorbs the remainder
+        sz = min((hi_u - lo_u) * align, rest_rows - used)
+        other.append(sz)
+        used += sz
+    out, lo, j = [], 0, 0
+    for r in range(world):
+        if r == dest:
+            sz = n_dest
+        else:
+            sz = other[j]
+            j += 1
+        out.append((lo, lo + sz))
+        lo += sz
+    return out
+
+
 def halo_for_fill(default: int = 8) -> int:
     """Extra rows walked on each side of a band so the hull fill sees neighbouring bands (GI_ERR_HALO if too
     small).  8 covers every mesh whose hull leaves less than 8 empty grid rows inside a band boundary."""
@@ -240,17 +277,25 @@ def _stream(stream):
 
 
 def barycentric_gather(field: PeerField, points, data_in, x_axis, y_axis, simplices, neighbours, *, halo=None,
-                       band_pack=True, signal=True, stream=None, dest=None):
+                       band_pack=True, signal=True, stream=None, dest=None, bands=None):
     """This rank's row band of ``barycentric_interpolation`` (interpolation.f90:362-404,412), stored by the kernels
     into ``field`` on every rank (``dest=None``: the field ends up complete everywhere) or into this rank's own copy
     and rank ``dest``'s (the final gather of the field onto one rank: 1/N of the NVLink traffic per sender).  Inputs
     are torch CUDA tensors in C order (points (n, 2), simplices / neighbours (t, 3) int32); asynchronous on the
     current torch stream.  Check ``lib().gi_stream_status`` (or call ``field.wait()`` + synchronize) before trusting
-    the result: GI_ERR_HALO / GI_ERR_PACK_WINDOW ask for a retry with a larger halo / ``band_pack=False``."""
+    the result: GI_ERR_HALO / GI_ERR_PACK_WINDOW ask for a retry with a larger halo / ``band_pack=False``.
+    ``bands``: the (begin, end) rows of every rank (default: ``row_band``, even); see ``gather_bands`` for the uneven
+    split that suits a gather onto one rank."""
     from . import _lib
     lib = _lib.lib()
     suf = "f64" if field.dtype == np.float64 else "f32"
-    r0, r1 = row_band(field.shape[0], field.rank, field.world)
+    if bands is None:
+        r0, r1 = row_band(field.shape[0], field.rank, field.world)
+    else:
+        if len(bands) != field.world or bands[0][0] != 0 or bands[-1][1] != field.shape[0] or any(
+                bands[i][1] != bands[i + 1][0] for i in range(field.world - 1)):
+            raise ValueError("bands must be one contiguous (begin, end) row range per rank covering the field")
+        r0, r1 = bands[field.rank]
     h = (halo_for_fill() if halo is None else halo) if field.world > 1 else 0
     flags = _lib.GI_POINTS_ROWMAJOR | _lib.GI_TOPO_ROWMAJOR | (_lib.GI_FIELD_ROWMAJOR if field.order == "C" else 0)
     if band_pack and field.world > 1:

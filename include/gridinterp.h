@@ -92,6 +92,13 @@ typedef enum {
                                  skipped triangles are marked, and a walk that wants to cross one is reported as
                                  GI_ERR_PACK_WINDOW by gi_stream_status(): the caller then repeats the call without
                                  the flag (GI_HOST calls do both by themselves).  Results are identical. */
+#define GI_BARY_PLANE_VALUES 2048 /* barycentric entry points and plans (opt-in): evaluate a target's value as the
+                                     plane through its triangle's three nodal values, d3 + gx*(x-x3) + gy*(y-y3) with
+                                     the gradient precomputed per triangle, instead of through the reference's weight
+                                     expressions (interpolation.f90:385-398).  Triangle ids, the outside-hull mask and
+                                     fill sources stay bit-identical; values agree with the reference's to
+                                     1e-12 * max|data_in| in double precision (needle triangles, max|edge|^2 >
+                                     128 |denom|, keep the exact expression).  The default is the bit-identical form. */
 #define GI_TARGETS_ROWMAJOR 1024 /* *_points entry points: the (num_targets, 2) target array is C-order */
 #define GI_ESRG_REFERENCE_ORDER 16 /* idw_esrg_nearest: process every target in the reference's candidate order
                                       (debug).  Default: only targets with exactly equal neighbour distances,

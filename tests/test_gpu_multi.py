@@ -122,6 +122,20 @@ def _worker(rank, world, port, order, ret):
             ok = ok and (np.array_equal(got, want) if rank == root else
                          (np.array_equal(got[r0:r1], want[r0:r1]) and not got[:r0].any() and not got[r1:].any()))
             dist.barrier()
+            # the same with uneven bands: the gathering rank computes 60 % of the rows (sharding.gather_bands)
+            field.tensor.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            bands = sharding.gather_bands(want.shape[0], world, root, 0.6)
+            r0, r1 = sharding.barycentric_gather(field, *d, dest=root, bands=bands)
+            assert (r0, r1) == bands[rank] and bands[root][1] - bands[root][0] > want.shape[0] // world
+            if rank == root:
+                field.wait()
+            torch.cuda.synchronize()
+            _lib.check(_lib.lib().gi_stream_status(torch.cuda.current_stream().cuda_stream), "uneven gather")
+            got = field.tensor.cpu().numpy()
+            ok = ok and (np.array_equal(got, want) if rank == root else np.array_equal(got[r0:r1], want[r0:r1]))
+            dist.barrier()
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

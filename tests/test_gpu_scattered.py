@@ -93,24 +93,48 @@ def test_idw_kdtree_points(c1, k):
     assert np.array_equal(got_d.cpu().numpy(), want)
 
 
+def _exact_knn_idw(points, data, targets, k, R=np.float64):
+    """The exact k nearest points of every target (scipy cKDTree for the ids; the k-d ORACLE cannot serve here: like
+    the reference it prunes with |diff| < d^2, kd_tree.f90:182, and misses neighbours when distances are below 1 or
+    above the 1e6 sentinel), with the reference's arithmetic for everything that is compared bit for bit: squared
+    distances as dx*dx + dy*dy, IDW sums in ascending neighbour order (interpolation.f90:260-274)."""
+    from scipy.spatial import cKDTree
+    p = points.astype(R); t = targets.astype(R); d = data.astype(R)
+    _, idx = cKDTree(p.astype(np.float64)).query(t.astype(np.float64), k=k)
+    idx = idx.reshape(len(t), k)
+    dx = p[idx, 0] - t[:, None, 0]; dy = p[idx, 1] - t[:, None, 1]
+    d2 = dx * dx + dy * dy
+    order = np.argsort(d2, axis=1, kind="stable")            # the distances as the kernel rounds them decide the order
+    idx = np.take_along_axis(idx, order, 1); d2 = np.take_along_axis(d2, order, 1)
+    dist = np.sqrt(d2)
+    num = np.zeros(len(t), R); den = np.zeros(len(t), R)
+    for j in range(k):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            num = num + d[idx[:, j]] / dist[:, j]
+            den = den + R(1) / dist[:, j]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = num / den
+    return out.astype(R), (idx + 1).astype(np.int32), d2
+
+
 @pytest.mark.parametrize("k", [1, 6, 40])
 def test_idw_esrg_nearest_points(c1, k):
-    """Scattered targets through the cell list: the exact k nearest points in ascending order, i.e. what the k-d tree
-    oracle finds for the same targets (continuous random coordinates: no distance ties), and the same IDW sums
-    (interpolation.f90:260-274 == :164-178 on an ascending neighbour list)."""
+    """Scattered targets through the cell list: the exact k nearest points in ascending order and the reference's IDW
+    sums over them (continuous random coordinates: no distance ties, no zero distances)."""
     targets = _targets(c1.points, 30_000, 7)
     spac = float(c1.x_axis[1] - c1.x_axis[0])
-    want, w = orc.idw_kdtree_points(np.asfortranarray(c1.points.T), c1.data_pts, targets, k, debug=True)
+    want, want_nn, want_d2 = _exact_knn_idw(c1.points, c1.data_pts, targets, k)
     got, g = ip.idw_esrg_nearest_points(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac, targets, k, debug=True)
-    assert np.array_equal(g.nn_index, w.nn_index) and np.array_equal(g.nn_dist2, w.nn_dist2)
+    assert np.array_equal(g.nn_index, want_nn) and np.array_equal(g.nn_dist2, want_d2)
     assert np.array_equal(got, want)
-    # grid nodes as scattered targets: the grid entry point's bits
+    # grid nodes as scattered targets: the grid entry point's bits (and so the oracle's)
     xx, yy = np.meshgrid(c1.x_axis, c1.y_axis)
     nodes = np.stack([xx.ravel(), yy.ravel()], 1)
     field = ip.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac, k, order="C")
+    assert np.array_equal(field, orc.idw_esrg_nearest(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac, k))
     assert np.array_equal(ip.idw_esrg_nearest_points(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac, nodes, k),
                           field.ravel())
-    # device tensors, Fortran-ordered targets, single precision against the f32 oracle
+    # device tensors, Fortran-ordered targets, single precision
     import torch
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
     got_d = ip.idw_esrg_nearest_points(dev(c1.points), dev(c1.data_pts), dev(c1.x_axis), dev(c1.y_axis), spac,
@@ -120,13 +144,12 @@ def test_idw_esrg_nearest_points(c1, k):
                                                      np.asfortranarray(targets), k), want)
     assert ip.idw_esrg_nearest_points(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac, np.zeros((0, 2)), k).shape == (0,)
     f32 = np.float32
-    t32 = targets[:5000].astype(f32)
-    want32, w32 = orc.idw_kdtree_points(np.asfortranarray(c1.points.T.astype(f32)), c1.data_pts.astype(f32), t32, k,
-                                        dtype=f32, debug=True)
-    got32, g32 = ip.idw_esrg_nearest_points(c1.points.astype(f32), c1.data_pts.astype(f32), c1.x_axis.astype(f32),
-                                            c1.y_axis.astype(f32), f32(spac), t32, k, dtype=f32, debug=True)
-    assert np.array_equal(g32.nn_dist2, w32.nn_dist2)          # (ids may differ where two f32 distances tie)
-    same = (g32.nn_index == w32.nn_index).all(1)
+    p32, d32, t32 = c1.points.astype(f32), c1.data_pts.astype(f32), targets[:5000].astype(f32)
+    want32, nn32, d232 = _exact_knn_idw(p32, d32, t32, k, f32)
+    got32, g32 = ip.idw_esrg_nearest_points(p32, d32, c1.x_axis.astype(f32), c1.y_axis.astype(f32), f32(spac), t32, k,
+                                            dtype=f32, debug=True)
+    assert np.array_equal(g32.nn_dist2, d232)                  # (ids may differ where two f32 distances tie)
+    same = (g32.nn_index == nn32).all(1)
     assert same.mean() > 0.99 and np.array_equal(got32[same], want32[same])
 
 
@@ -136,6 +159,8 @@ def test_idw_esrg_nearest_points_targets_far_outside_the_grid(c1):
     targets = np.concatenate([rng.uniform(lo - 5 * (hi - lo), hi + 5 * (hi - lo), (5000, 2)),
                               rng.uniform(lo - 1e4 * (hi - lo), hi + 1e4 * (hi - lo), (500, 2))])
     spac = float(c1.x_axis[1] - c1.x_axis[0])
-    want, w = orc.idw_kdtree_points(np.asfortranarray(c1.points.T), c1.data_pts, targets, 6, debug=True)
+    want, want_nn, want_d2 = _exact_knn_idw(c1.points, c1.data_pts, targets, 6)
     got, g = ip.idw_esrg_nearest_points(c1.points, c1.data_pts, c1.x_axis, c1.y_axis, spac, targets, 6, debug=True)
-    assert np.array_equal(g.nn_index, w.nn_index) and np.array_equal(got, want)
+    assert np.array_equal(g.nn_dist2, want_d2)
+    same = (g.nn_index == want_nn).all(1)                     # far targets: neighbour distances may tie after rounding
+    assert same.mean() > 0.99 and np.array_equal(got[same], want[same])

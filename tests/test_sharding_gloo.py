@@ -29,6 +29,31 @@ def test_split_range_properties():
         sharding.split_range(5, 0)
 
 
+def test_gather_bands_properties():
+    """Uneven row bands for a gather onto one rank: contiguous, ordered, covering, the destination's share honoured,
+    the others balanced, edges on strip boundaries for large fields and no empty band for small ones."""
+    for len_y in (79, 1000, 16384):
+        for world in (1, 2, 3, 8):
+            for dest in range(world):
+                for share in (0.0, 1.0 / world, 0.36, 0.5, 1.0):
+                    b = sharding.gather_bands(len_y, world, dest, share)
+                    assert len(b) == world and b[0][0] == 0 and b[-1][1] == len_y
+                    assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
+                    sizes = [hi - lo for lo, hi in b]
+                    assert all(sz >= 0 for sz in sizes)
+                    if world > 1 and 0.0 < share < 1.0:
+                        assert abs(sizes[dest] - share * len_y) <= 32
+                        others = [sz for r, sz in enumerate(sizes) if r != dest]
+                        assert max(others) - min(others) <= 64
+                        if len_y >= 4 * 32 * world:
+                            assert sum(sz % 32 != 0 for sz in sizes) <= 1     # whole strips, one remainder
+                        else:
+                            assert min(sizes) > 0
+    assert sharding.gather_bands(16384, 8, 0, 0.125) == sharding.split_range(16384, 8)
+    with pytest.raises(ValueError):
+        sharding.gather_bands(10, 2, 2, 0.5)
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
