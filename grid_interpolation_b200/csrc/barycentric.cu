@@ -571,6 +571,25 @@ template <class R> struct GatherDest {
   int64_t ld;  // 0 = band-shaped contiguous
 };
 
+// Values of halo targets (walked rows outside the band) that a fix-up re-located.  The hull fill re-evaluates a
+// source cell that lies in the halo on the fly (nothing is stored for halo rows), which finds the right triangle
+// for every target except those inside the margin band of an edge, where the reference's choice depends on its
+// walk path: those were re-located by the fix-up paths, and publish_target leaves their value here so that a band
+// fills from exactly the value a one-shot run of the whole grid would have read.  Dense over the halo rows
+// (2 * halo * len_x values), initialised to an all-ones bit pattern = "no fix-up here".
+template <class R> struct HaloFix {
+  R* vals;              // nullptr: no halo
+  int y_e0, y_b0, y_b1; // walked rows start at y_e0, the band is [y_b0, y_b1)
+  int len_x;
+  __device__ __forceinline__ int64_t index(int ix, int iy) const {
+    if (!vals || (iy >= y_b0 && iy < y_b1)) return -1;
+    const int hr = iy < y_b0 ? iy - y_e0 : (iy - y_b1) + (y_b0 - y_e0);
+    return (int64_t)hr * len_x + ix;
+  }
+};
+__device__ __forceinline__ bool is_no_fix(double v) { return __double_as_longlong(v) == -1ll; }
+__device__ __forceinline__ bool is_no_fix(float v) { return __float_as_int(v) == -1; }
+
 template <class R> struct WalkArgs {
   TargetWindow<R> win;   // walked window E (band + halo)
   int bf0, bf1, bs0, bs1;  // band B inside E: the part that is written to `out`
@@ -593,6 +612,7 @@ template <class R> struct WalkArgs {
   int reference_rows;   // GI_BARY_REFERENCE_ORDER: locate every target by the reference's row-sequential walk
   int* row_todo;        // [len_y], zeroed: grid rows a fix-up handed to row_walk_kernel
   const int* only_if;   // locate_eval_kernel: run only if this device flag is set (nullptr: always), see raster.cuh
+  HaloFix<R> hfix;      // where fix-ups leave the values of halo targets (see HaloFix)
   int* status;
 };
 
@@ -841,6 +861,13 @@ __device__ __forceinline__ void publish_target(const WalkArgs<R>& a, int f, int 
       for (int d = 0; d < a.n_peer; ++d) a.peer_out[d][oo] = v;
     }
     if (a.tri_out) a.tri_out[o] = (inside ? tri : ~tri) + 1;
+  } else if (inside) {  // a halo target: the hull fill may take it as a source cell
+    const int64_t hi = a.hfix.index(w.fast_is_y ? s : f, w.fast_is_y ? f : s);
+    if (hi >= 0) {
+      TriGeom<R> g;
+      load_eval(a.geom + tri, g);
+      a.hfix.vals[hi] = eval_any(g, tx, ty);
+    }
   }
   const int lf = f - w.f0, wpr = (w.nf() + 31) >> 5;
   uint32_t* word = a.mask_words + (int64_t)(s - w.s0) * wpr + (lf >> 5);
@@ -1119,6 +1146,7 @@ template <class R> struct FillArgs {
   const TriGeom<R>* geom;
   const int* seed;
   int ncx, ncy, num_tri, iter_cap;
+  HaloFix<R> hfix;    // values of halo cells that a fix-up re-located (see HaloFix)
   int* status;
 };
 
@@ -1198,12 +1226,17 @@ __global__ void __launch_bounds__(128) fill_kernel(const FillArgs<R> a) {
     if (sf >= a.vf0 && sf < a.vf1 && ss >= a.vs0 && ss < a.vs1) {
       v = a.out[(int64_t)(ss - a.vs0) * a.out_ld + (sf - a.vf0)];
     } else {  // source cell lies in the halo: recompute its (deterministic) value
-      const R tx = __ldg((a.win.fast_is_y ? a.win.slow_axis : a.win.fast_axis) + best_j);
-      const R ty = __ldg((a.win.fast_is_y ? a.win.fast_axis : a.win.slow_axis) + best_i);
-      bool inside; int iters; TriGeom<R> g;
-      const int tri = walk(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, best_j, best_i, a.num_tri), tx, ty,
-                           a.iter_cap, inside, iters, g, a.status);
-      v = eval_any(g, tx, ty);
+      const int64_t hi = a.hfix.index(best_j, best_i);
+      v = hi >= 0 ? a.hfix.vals[hi] : R(0);
+      if (hi < 0 || is_no_fix(v)) {   // (a fix-up left no value: any walk finds this target's triangle)
+        const R tx = __ldg((a.win.fast_is_y ? a.win.slow_axis : a.win.fast_axis) + best_j);
+        const R ty = __ldg((a.win.fast_is_y ? a.win.fast_axis : a.win.slow_axis) + best_i);
+        bool inside; int iters; TriGeom<R> g;
+        const int tri = walk(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, best_j, best_i, a.num_tri), tx, ty,
+                             a.iter_cap, inside, iters, g, a.status);
+        (void)tri;
+        v = eval_any(g, tx, ty);
+      }
     }
     const int64_t oo = (int64_t)(s - a.vs0) * a.out_ld + (f - a.vf0);
     a.out[oo] = v;  // :121
@@ -1414,7 +1447,18 @@ template <class R> void fill_from_walk(FillArgs<R>& fa, const WalkArgs<R>& wa, c
                                        int len_y) {
   fa.len_x = len_x; fa.len_y = len_y;
   fa.geom = pm.geom; fa.seed = pm.seed; fa.ncx = pm.ncx; fa.ncy = pm.ncy; fa.num_tri = pm.num_tri;
-  fa.iter_cap = wa.iter_cap; fa.status = wa.status;
+  fa.iter_cap = wa.iter_cap; fa.status = wa.status; fa.hfix = wa.hfix;
+}
+
+// the HaloFix store of a band [row_begin,row_end) walked as [e0,e1): allocated only when there are halo rows
+template <class R>
+int alloc_halo_fix(Scratch& scr, int e0, int e1, int row_begin, int row_end, int len_x, HaloFix<R>* h) {
+  *h = HaloFix<R>{nullptr, e0, row_begin, row_end, len_x};
+  const int64_t rows = (int64_t)(e1 - e0) - (row_end - row_begin);
+  if (rows <= 0) return GI_OK;
+  GI_TRY(scr.alloc(&h->vals, (size_t)rows * len_x));
+  GI_CUDA(cudaMemsetAsync(h->vals, 0xff, sizeof(R) * (size_t)rows * len_x, scr.stream()));
+  return GI_OK;
 }
 
 // 2. + 3. for the row band [row_begin,row_end) with `halo` extra rows walked on each side, on a packed mesh
@@ -1453,6 +1497,7 @@ int bary_run_window(Scratch& scr, const PackedMesh<R>& pm, const R* x_axis, int 
   GI_CUDA(cudaMemsetAsync(wa.start_part, 0, sizeof(unsigned long long) * (2 * kStartBlocks + 1), st));
   GI_TRY(scr.alloc(&wa.row_todo, (size_t)len_y));
   GI_CUDA(cudaMemsetAsync(wa.row_todo, 0, sizeof(int) * (size_t)len_y, st));
+  GI_TRY(alloc_halo_fix<R>(scr, e0, e1, row_begin, row_end, len_x, &wa.hfix));
   wa.geom = pm.geom; wa.seed = pm.seed; wa.ncx = pm.ncx; wa.ncy = pm.ncy; wa.num_tri = num_tri;
   wa.iter_cap = num_tri + 16;
   wa.out = data_ip; wa.tri_out = tri_out; wa.mask_words = mask_words; wa.counters = counters;
@@ -1590,6 +1635,9 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
   GI_TRY(scr.alloc(&row_todo, (size_t)len_y));
   GI_CUDA(cudaMemsetAsync(row_todo, 0, sizeof(int) * (size_t)len_y, st));
 
+  HaloFix<R> hfix;
+  GI_TRY(alloc_halo_fix<R>(scr, e0, e1, row_begin, row_end, len_x, &hfix));
+
   // tile lists of the whole walked window (from the pack pass): the sub-bands below start at whole tile rows
   const bool raster = pm.bins.start && pm.bin_e0 == e0 && pm.bin_e1 == e1;
   const TileBins& bins = pm.bins;
@@ -1648,6 +1696,7 @@ int bary_run_banded(HostPipe* pipe, Scratch& scr, const PackedMesh<R>& pm, const
         wa.counters = counters + 8 * b;
         wa.amb_list = amb_list; wa.amb_cap = amb_cap; wa.start_part = start_part;
         wa.reference_rows = (flags & GI_BARY_REFERENCE_ORDER) ? 1 : 0; wa.row_todo = row_todo;
+        wa.hfix = hfix;
         wa.status = slot.dev;
         GI_TRY(bary_walk<R>(wa, pm, dx, dy, len_x, len_y, num_points, st, raster ? &bins : nullptr,
                             (int)((start[b] - es0) / kTileH)));
@@ -1848,6 +1897,7 @@ int fill_device(const uint8_t* mask, int len_x, int len_y, R* data_ip, int64_t* 
   fa.out = data_ip; fa.fill_src = fill_src; fa.counters = counters; fa.len_x = len_x; fa.len_y = len_y;
   fa.out_ld = nf; fa.n_peer = 0;
   fa.geom = nullptr; fa.seed = nullptr; fa.ncx = fa.ncy = fa.num_tri = fa.iter_cap = 0;
+  fa.hfix = HaloFix<R>{nullptr, 0, 0, 0, 0};
   fa.status = slot.dev;
   fill_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(fa);
   GI_CUDA(cudaGetLastError());

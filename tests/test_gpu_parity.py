@@ -126,6 +126,42 @@ def test_barycentric_targets_on_mesh_edges():
         assert_values(got, want)
 
 
+@pytest.mark.parametrize("cols,halo", [((-4, 70), 17), ((13, 51), 4)])
+def test_band_fill_reads_fixed_up_halo_sources(cols, halo):
+    """Row bands whose hull fill takes its source cells from HALO rows that lie exactly on mesh edges (a sheared,
+    scaled lattice: coordinates are not exactly representable, so the two triangles sharing an edge give values that
+    differ in the last bit).  The band must read the value of the triangle the reference's row-wise walk chooses --
+    the fix-up paths leave it in the HaloFix store -- i.e. equal the one-shot field and the oracle bit for bit.
+    Columns (-4, 70) cross the sheared hull on both sides (the nearest source of a corner target is ~16 cells away,
+    hence the wide halo); columns (13, 51) stay inside the x-range every lattice row covers (sources 3 rows away)."""
+    import torch
+    gx, gy = np.meshgrid(np.arange(0.0, 14.0), np.arange(0.0, 11.0))
+    pts = np.stack([0.37 * gx.ravel() + 0.11 * gy.ravel() + 0.1, 0.29 * gy.ravel() + 0.2], 1)
+    simp, nbr = workloads.delaunay(pts)
+    data = np.sin(3.0 * pts[:, 0]) + 0.3 * pts[:, 1] ** 2 + 7.0
+    # target rows ON the lattice rows y = 0.29 j + 0.2 (and between them)
+    x = 0.1 + 0.0925 * np.arange(*cols)
+    y = 0.2 + 0.145 * np.arange(-3, 24)
+    want, w = orc.barycentric_interpolation(pts, data, x, y, simp, nbr, debug=True)
+    assert w.mask[:3].all() and not w.mask[3].all()          # rows 0..2 lie below the hull: filled from row 3 upwards
+    ly = y.size
+    for order in ("C", "F"):
+        full, g = ip.barycentric_interpolation_ex(pts, data, x, y, simp, nbr, debug=True, order=order)
+        assert g.fixups > 50
+        assert_values(full, want)
+        for bands in ([(0, 3), (3, 4), (4, 21), (21, ly)], [(0, 2), (2, 23), (23, ly)]):
+            parts = [ip.barycentric_interpolation_ex(pts, data, x, y, simp, nbr, rows=b, halo=halo, order=order)
+                     for b in bands]
+            assert_values(np.concatenate(parts, 0), want)
+            dev = [torch.as_tensor(np.ascontiguousarray(a), device="cuda:0") for a in (pts, data, x, y, simp, nbr)]
+            parts = [ip.barycentric_interpolation_ex(*dev, rows=b, halo=halo, order=order).cpu().numpy() for b in bands]
+            assert_values(np.concatenate(parts, 0), want)
+            parts = [ip.barycentric_interpolation_ex(pts, data, x, y, simp, nbr, rows=b, halo=halo, order=order,
+                                                     plane_values=True) for b in bands]
+            assert np.array_equal(np.concatenate(parts, 0),
+                                  ip.barycentric_interpolation_ex(pts, data, x, y, simp, nbr, order=order, plane_values=True))
+
+
 def _lattice_case():
     gx, gy = np.meshgrid(np.arange(0.0, 12.0), np.arange(0.0, 9.0))
     pts = np.stack([gx.ravel(), gy.ravel()], 1)
