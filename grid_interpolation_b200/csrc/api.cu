@@ -49,6 +49,56 @@ int ensure_device() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// per-(device, stream) scratch arenas (see Scratch in common.cuh)
+// ---------------------------------------------------------------------------------------------
+struct ScratchArena {
+  char* base = nullptr;
+  size_t cap = 0, offset = 0;
+  int live = 0;  // Scratch objects holding it
+};
+constexpr size_t kArenaBytes = (size_t)8 << 20;
+static std::map<std::pair<int, cudaStream_t>, ScratchArena> g_arenas;
+
+ScratchArena* arena_acquire(cudaStream_t s) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lock(g_mutex);
+  ScratchArena& a = g_arenas[std::make_pair(dev, s)];
+  if (!a.base) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, kArenaBytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    a.base = static_cast<char*>(p);
+    a.cap = kArenaBytes;
+  }
+  ++a.live;
+  return &a;   // (std::map never moves its nodes)
+}
+void* arena_alloc(ScratchArena* a, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (a->offset + need > a->cap) return nullptr;
+  void* p = a->base + a->offset;
+  a->offset += need;
+  return p;
+}
+void arena_release(ScratchArena* a) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (--a->live == 0) a->offset = 0;
+}
+void arena_trim() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+  std::lock_guard<std::mutex> lock(g_mutex);
+  for (auto& kv : g_arenas) {
+    ScratchArena& a = kv.second;
+    if (kv.first.first == dev && a.live == 0 && a.base) {
+      cudaFree(a.base);
+      a.base = nullptr; a.cap = 0; a.offset = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-(device, stream) status slots
 // ---------------------------------------------------------------------------------------------
 static std::map<std::pair<int, cudaStream_t>, StatusSlot> g_slots;
@@ -689,6 +739,7 @@ GI_API void gi_release_workspace(void) {
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     cudaDeviceSynchronize();
     cudaMemPoolTrimTo(pool, 0);
+    gi::arena_trim();
   }
 }
 

@@ -1036,25 +1036,30 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
 // range (a grid row along mesh edges, or along the hull: every target of the row is flagged), (b) for the whole
 // window when more targets were flagged than the fix-up list holds (a structured mesh whose edges run along the
 // grid lines of a multi-million-node grid), so that nothing is silently left to phase 1's path, and (c) for
-// all targets with GI_BARY_REFERENCE_ORDER (debug).  Rows are independent but each is serial:
-// 16384 threads at C4 size, tens of milliseconds -- a fallback, not the production path.
+// all targets with GI_BARY_REFERENCE_ORDER (debug).  Rows are independent; within a row the chain of dependent walks
+// is cut into speculative pieces (below) -- a fallback, not the production path.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowChunk = 1024;
 constexpr int kRowSpecMaxCols = 50 * 1024;  // speculative form: one int of shared memory per column (200 KB)
-// One warp per grid row.
-//   serial form       lane 0 walks a chunk of columns (the chain of dependent walks, nothing else in it), then all
-//                     lanes publish the chunk (values, mask bits, work list) in parallel.
-//   speculative form  (rows of up to kRowSpecMaxCols columns) the chain is cut into 32 pieces: lane L walks piece
-//                     L from a GUESSED state (the triangle a walk from the seed grid finds for the column before
-//                     the piece) and records the state after every column; then lane 0 repairs the pieces in
-//                     order -- it continues the TRUE chain into piece L only until its state equals the recorded
-//                     one (the state after a column depends on nothing but the state before it and the column,
-//                     so from there on the recorded chain is the true chain).  Exact, and 512 instead of 16 384
-//                     dependent walks per row at C4 size.
+constexpr int kRowThreads = 256;
+// One CTA per grid row.
+//   serial form       thread 0 walks a chunk of columns (the chain of dependent walks, nothing else in it), then all
+//                     threads publish the chunk (values, mask bits, work list) in parallel.
+//   speculative form  (rows of up to kRowSpecMaxCols columns) the chain is cut into one piece per thread: thread L
+//                     walks piece L from a GUESSED state (the triangle a walk from the seed grid finds for the
+//                     column before the piece) and records the state after every column.  The state after a
+//                     column depends on nothing but the state before it and the column, so piece L is the true
+//                     chain iff its guess equals the true state after the last column of piece L-1.  Thread 0 then
+//                     goes through the pieces in order: a piece whose guess equals the (by then true) recorded
+//                     state before it costs one comparison; otherwise the true chain is continued into the piece
+//                     until its state equals the recorded one.  Exact -- and, since a guess is wrong only where the
+//                     located triangle depends on the path, 64 + a few dependent walks per row at C4 size instead
+//                     of 16 384 (round 2 had 32 pieces per row and one repair walk per piece: 544).
 template <class R>
-__global__ void __launch_bounds__(32) row_walk_kernel(const WalkArgs<R> a, int spec_cols) {
-  __shared__ int s_tri[kRowChunk];   // found triangle, ~id = left through a hull edge
-  extern __shared__ int s_state[];   // speculative form: the same per column of the row
+__global__ void __launch_bounds__(kRowThreads) row_walk_kernel(const WalkArgs<R> a, int spec_cols) {
+  __shared__ int s_tri[kRowChunk];      // found triangle, ~id = left through a hull edge
+  __shared__ int s_guess[kRowThreads];  // speculative form: the state each piece started from
+  extern __shared__ int s_state[];      // speculative form: the state after every column of the row
   const bool all_rows = a.reference_rows || a.counters[5] > (int64_t)a.amb_cap;
   if (!all_rows && a.counters[6] == 0) return;
   const TargetWindow<R>& w = a.win;
@@ -1062,31 +1067,35 @@ __global__ void __launch_bounds__(32) row_walk_kernel(const WalkArgs<R> a, int s
   const R* y_axis = w.fast_is_y ? w.fast_axis : w.slow_axis;
   const int ix0 = w.fast_is_y ? w.s0 : w.f0, ix1 = w.fast_is_y ? w.s1 : w.f1;
   const int iy0 = w.fast_is_y ? w.f0 : w.s0, iy1 = w.fast_is_y ? w.f1 : w.s1;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x;
   for (int iy = iy0 + blockIdx.x; iy < iy1; iy += gridDim.x) {
-    if (!all_rows && !a.row_todo[iy]) continue;
-    __syncwarp();
-    if (lane == 0) a.row_todo[iy] = 0;
+    if (!all_rows && !a.row_todo[iy]) continue;   // (the same for every thread of the CTA)
+    __syncthreads();
+    if (tid == 0) a.row_todo[iy] = 0;
     const R ty = __ldg(y_axis + iy);
     const int start = (int)a.counters[7];                                  // ind_tri = ind_tri_start   (:366)
     bool inside, amb;
     if (ix1 <= spec_cols && ix1 >= 64) {
-      const int piece = (ix1 + 31) >> 5, c_lo = lane * piece, c_hi = min(c_lo + piece, ix1);
+      // pieces of at least 8 columns: the seed walk of a piece must not outweigh the piece
+      const int piece = max((ix1 + kRowThreads - 1) / kRowThreads, 8), c_lo = tid * piece, c_hi = min(c_lo + piece, ix1);
       if (c_lo < ix1) {
         int tri = start;
-        if (lane > 0)  // any valid triangle may be guessed; a good guess makes the repair short
+        if (tid > 0) {  // any valid triangle may be guessed; a good guess makes the repair short
           tri = walk_checked(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, c_lo - 1, iy, a.num_tri), __ldg(x_axis + c_lo - 1),
                              ty, a.iter_cap, inside, amb, (int*)nullptr);
+          s_guess[tid] = inside ? tri : ~tri;
+        }
         for (int ix = c_lo; ix < c_hi; ++ix) {
-          tri = walk_checked(a.geom, tri, __ldg(x_axis + ix), ty, a.iter_cap, inside, amb, lane ? (int*)nullptr : a.status);
+          tri = walk_checked(a.geom, tri, __ldg(x_axis + ix), ty, a.iter_cap, inside, amb, tid ? (int*)nullptr : a.status);
           s_state[ix] = inside ? tri : ~tri;
         }
       }
-      __syncwarp();
-      if (lane == 0) {
+      __syncthreads();
+      if (tid == 0) {
         for (int c = piece; c < ix1; c += piece) {
-          const int prev = s_state[c - 1];
-          int tri = prev >= 0 ? prev : ~prev;                              // the true state after column c - 1
+          const int prev = s_state[c - 1];                                 // the true state after column c - 1
+          if (prev == s_guess[c / piece]) continue;                        // the piece started from it: true as recorded
+          int tri = prev >= 0 ? prev : ~prev;
           const int end = min(c + piece, ix1);
           for (int ix = c; ix < end; ++ix) {
             tri = walk_checked(a.geom, tri, __ldg(x_axis + ix), ty, a.iter_cap, inside, amb, a.status);   // :372-373
@@ -1096,30 +1105,29 @@ __global__ void __launch_bounds__(32) row_walk_kernel(const WalkArgs<R> a, int s
           }
         }
       }
-      __syncwarp();
-      for (int ix = ix0 + lane; ix < ix1; ix += 32) {
+      __syncthreads();
+      for (int ix = ix0 + tid; ix < ix1; ix += kRowThreads) {
         const int t = s_state[ix];
         publish_target(a, w.fast_is_y ? iy : ix, w.fast_is_y ? ix : iy, t >= 0 ? t : ~t, t >= 0, __ldg(x_axis + ix), ty);
       }
-      __syncwarp();
       continue;
     }
     int tri = start;
     for (int c0 = 0; c0 < ix1; c0 += kRowChunk) {                          // :367
       const int cn = min(kRowChunk, ix1 - c0);
-      if (lane == 0) {
+      if (tid == 0) {
         for (int i = 0; i < cn; ++i) {
           tri = walk_checked(a.geom, tri, __ldg(x_axis + c0 + i), ty, a.iter_cap, inside, amb, a.status);  // :372-373
           s_tri[i] = inside ? tri : ~tri;
         }
       }
-      __syncwarp();
-      for (int i = lane; i < cn; i += 32) {
+      __syncthreads();
+      for (int i = tid; i < cn; i += kRowThreads) {
         const int ix = c0 + i, t = s_tri[i];
         if (ix >= ix0)
           publish_target(a, w.fast_is_y ? iy : ix, w.fast_is_y ? ix : iy, t >= 0 ? t : ~t, t >= 0, __ldg(x_axis + ix), ty);
       }
-      __syncwarp();
+      __syncthreads();
     }
   }
 }
@@ -1392,6 +1400,26 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
     // dependent walks without it (band of 2048 rows: 1.25 instead of 0.43 ms); in a window of many CTA waves those
     // strips are not the critical path and the test is 2 % of the kernel, so it is compiled out there
     const bool cf = (int64_t)grid.x * grid.y < (int64_t)kNumSMs * 8 * 24;
+    // Small windows (the reference's own test size: 132 x 79 targets on 10 k triangles) are a handful of CTAs whose
+    // threads each walk a dependent chain of 32 rows -- ~1.5 record fetches per row at L2 latency.  Shorter strips
+    // give more, shorter chains (each pays its own seed walk): 132 x 79 targets 0.135 -> 0.082 ms for walk + fill +
+    // copy-out with strips of 4 rows, 586 x 347 targets 0.19 -> 0.13 ms (bench/c1_rows_probe.py, profiles/r02_c1_*).
+    int small_rows = 0;
+    if (!peers && !bp) {
+      if ((int64_t)grid.x * div_up(ns, 8) <= kNumSMs * 4) small_rows = 4;
+      else if ((int64_t)grid.x * div_up(ns, 16) <= kNumSMs * 4) small_rows = 8;
+    }
+#define GI_LAUNCH_SMALL(FY_, ROWS_)                                                                                  \
+  do {                                                                                                               \
+    dim3 g2(grid.x, div_up(ns, ROWS_));                                                                              \
+    if (pm.plane) locate_eval_kernel<R, FY_, false, ROWS_, 4, false, true, true><<<g2, kWalkThreads, 0, st>>>(wa);  \
+    else locate_eval_kernel<R, FY_, false, ROWS_, 4, false, true, false><<<g2, kWalkThreads, 0, st>>>(wa);          \
+  } while (0)
+    if (small_rows == 4 && !peers && !bp) {
+      if (fy) GI_LAUNCH_SMALL(true, 4); else GI_LAUNCH_SMALL(false, 4);
+    } else if (small_rows == 8 && !peers && !bp) {
+      if (fy) GI_LAUNCH_SMALL(true, 8); else GI_LAUNCH_SMALL(false, 8);
+    } else {
 #define GI_LAUNCH_WALK3(FY_, PEERS_, BP_, CF_)                                                                  \
   do {                                                                                                          \
     if (pm.plane) locate_eval_kernel<R, FY_, PEERS_, kRows, 8, BP_, CF_, true><<<grid, kWalkThreads, 0, st>>>(wa); \
@@ -1411,6 +1439,8 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
     else if (fy && !peers) GI_LAUNCH_WALK(true, false);
     else if (!fy) GI_LAUNCH_WALK(false, true);
     else GI_LAUNCH_WALK(true, true);
+    }
+#undef GI_LAUNCH_SMALL
 #undef GI_LAUNCH_WALK
 #undef GI_LAUNCH_WALK2
 #undef GI_LAUNCH_WALK3
@@ -1436,8 +1466,8 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
                                    kRowSpecMaxCols * (int)sizeof(int)));
       configured.fetch_or(bit, std::memory_order_release);
     }
-    row_walk_kernel<R><<<std::min(wa.win.fast_is_y ? nf : ns, kNumSMs * 16), 32, (size_t)spec_cols * sizeof(int), st>>>(
-        wa, spec_cols);
+    row_walk_kernel<R><<<std::min(wa.win.fast_is_y ? nf : ns, kNumSMs * 16), kRowThreads, (size_t)spec_cols * sizeof(int),
+                         st>>>(wa, spec_cols);
   }
   GI_CUDA(cudaGetLastError());
   return GI_OK;
