@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgridinterp.so")
+# GI_LIBRARY: another build of the same library (A/B variants from `python -m grid_interpolation_b200.build --variant`)
+LIB_PATH = os.environ.get("GI_LIBRARY") or os.path.join(_HERE, "libgridinterp.so")
 
 GI_OK, GI_ERR_BAD_ARG, GI_ERR_NO_DEVICE, GI_ERR_OOM, GI_ERR_CUDA = 0, 1, 2, 3, 4
 GI_ERR_ITER_CAP, GI_ERR_TOO_FEW_POINTS, GI_ERR_BAD_INDEX, GI_ERR_HALO = 5, 6, 7, 8

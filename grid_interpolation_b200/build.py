@@ -46,16 +46,24 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out_dir: str | None = None) -> str:
+    """Build the library.  ``defines`` / ``out_dir``: an A/B variant (extra -D flags, objects and .so under
+    ``out_dir``; load it with GI_LIBRARY=<out_dir>/libgridinterp.so)."""
+    if out_dir:
+        return _build(tuple(defines), os.path.join(out_dir, "build"), os.path.join(out_dir, "libgridinterp.so"), verbose)
     if not force and not needs_build():
         return LIB
+    return _build((), BUILD, LIB, verbose)
+
+
+def _build(defines, BUILD, LIB, verbose) -> str:
     nvcc = _nvcc()
     os.makedirs(BUILD, exist_ok=True)
     ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
 
     def compile_one(src):
         obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-        cmd = [nvcc, *ccbin, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *ccbin, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
@@ -78,4 +86,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m grid_interpolation_b200.build [--force] [-v] [--variant DIR -DNAME=VALUE ...]
+    if "--variant" in sys.argv:
+        d = sys.argv[sys.argv.index("--variant") + 1]
+        print(build(defines=[a[2:] for a in sys.argv if a.startswith("-D")], out_dir=d, verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -156,6 +156,21 @@ __device__ __forceinline__ void touch_values(const TriGeom<double>* p) {
 }
 __device__ __forceinline__ void touch_values(const TriGeom<float>*) {}
 
+// Warm the walk part (sectors 0-1) of a record the walk will probably move to: two one-word loads whose results are
+// never read, so no register waits on them.  (A/B on C4, same box: this form 2.844 -> 2.800 ms; prefetch.global.L1
+// 2.996 ms; cp.async.ca into a dummy shared slot 3.071 ms -- profiles/r02_walk_variants.md.)  GI_WALK_PREFETCH=0
+// compiles the prediction out.
+#ifndef GI_WALK_PREFETCH
+#define GI_WALK_PREFETCH 1
+#endif
+__device__ __forceinline__ void touch_walk(const TriGeom<double>* p) {
+  const char* c = reinterpret_cast<const char*>(p);
+  int u, v;
+  asm volatile("ld.global.b32 %0, [%1];" : "=r"(u) : "l"(c));
+  asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(c + 32));
+}
+__device__ __forceinline__ void touch_walk(const TriGeom<float>*) {}
+
 // seed-grid geometry from the axes (a uniform-axis approximation: seeds only have to be near)
 template <class R>
 __device__ __forceinline__ SeedGrid<R> seed_grid_of(const R* __restrict__ x_axis, int len_x,
@@ -440,10 +455,10 @@ __device__ __noinline__ int careful_locate(const TriGeom<R>* __restrict__ geom, 
     int nxt = farthest_failing_edge(g, c1, c2, c3, margin);
     if (nxt == kNotPacked) nxt = packed_alternative(c1 < margin, c2 < margin, c3 < margin, g.n1, g.n2, g.n3);
     if (nxt < 0) {
-      if (nxt == kNotPacked) raise_status(status, GI_ERR_PACK_WINDOW);
+      if (nxt == kNotPacked && status) raise_status(status, GI_ERR_PACK_WINDOW);
       return ~tri;
     }
-    if (it >= iter_cap) { raise_status(status, GI_ERR_ITER_CAP); return ~tri; }
+    if (it >= iter_cap) { if (status) raise_status(status, GI_ERR_ITER_CAP); return ~tri; }
     tri = nxt;
   }
 }
@@ -528,18 +543,24 @@ template <> __device__ __forceinline__ int amb_threshold<float>(const TriGeom<fl
 __device__ __forceinline__ bool in_amb_band(double x, int thr) { return (__double2hiint(x) & 0x7fffffff) < thr; }
 __device__ __forceinline__ bool in_amb_band(float x, int thr) { return (__float_as_int(x) & 0x7fffffff) < thr; }
 
-// walk() that also reports whether the accepting (or hull-exit) test was inside the margin band
+// walk() that also reports whether the accepting (or hull-exit) test was inside the margin band.
+// `g` / `have`: the walk part of record `have` (-1: none) kept by the caller from one walk to the next -- a chain of
+// walks along a grid row (fix-up, row walk) mostly starts in the triangle the previous one ended in, and the record
+// load is the longest link of its dependent chain.
 template <class R>
-__device__ __forceinline__ int walk_checked(const TriGeom<R>* __restrict__ geom, int tri, R tx, R ty, int iter_cap,
-                                            bool& inside, bool& amb, int* status) {
+__device__ __forceinline__ int walk_checked_cached(const TriGeom<R>* __restrict__ geom, int tri, TriGeom<R>& g, int& have,
+                                                   R tx, R ty, int iter_cap, bool& inside, bool& amb, int* status,
+                                                   int* iters_out = nullptr) {
   const R margin = Consts<R>::margin();
   inside = true;
   int it = 0;
   for (;;) {
     ++it;
-    TriGeom<R> g;
-    load_walk(geom + tri, g);
-    g.pad &= kThrMask;  // the reference's path: first failing edge, long triangle or not
+    if (tri != have) {
+      load_walk(geom + tri, g);
+      g.pad &= kThrMask;  // the reference's path: first failing edge, long triangle or not
+      have = tri;
+    }
     const R c1 = (g.x2 - g.x1) * (ty - g.y1) - (g.y2 - g.y1) * (tx - g.x1);
     const R c2 = (g.x3 - g.x2) * (ty - g.y2) - (g.y3 - g.y2) * (tx - g.x2);
     const R c3 = (g.x1 - g.x3) * (ty - g.y3) - (g.y1 - g.y3) * (tx - g.x3);
@@ -557,7 +578,29 @@ __device__ __forceinline__ int walk_checked(const TriGeom<R>* __restrict__ geom,
     tri = nxt;
     if (it >= iter_cap) { if (status) raise_status(status, GI_ERR_ITER_CAP); inside = false; amb = false; break; }
   }
+  if (iters_out) *iters_out += it;
   return tri;
+}
+template <class R>
+__device__ __forceinline__ int walk_checked(const TriGeom<R>* __restrict__ geom, int tri, R tx, R ty, int iter_cap,
+                                            bool& inside, bool& amb, int* status, int* iters_out = nullptr) {
+  TriGeom<R> g;
+  int have = -1;
+  return walk_checked_cached(geom, tri, g, have, tx, ty, iter_cap, inside, amb, status, iters_out);
+}
+// The same result for a walk that starts at a seed triangle, where no path is prescribed: the located triangle does
+// not depend on the path (outside the margin band, which `amb` reports), so the moves are made with the careful
+// exit-edge choice (at most ~15 of them through the sliver triangles along the hull, where the reference's
+// first-failing-edge rule needs up to 1 220) and only the final test is the reference's.
+template <class R>
+__device__ __forceinline__ int locate_checked(const TriGeom<R>* __restrict__ geom, int seed_tri, R tx, R ty, int iter_cap,
+                                              bool& inside, bool& amb, int* status) {
+  const int res = careful_locate(geom, seed_tri, tx, ty, iter_cap, status);
+  if (res < 0) {  // left through a hull edge of triangle ~res (callers want certain INSIDE starts, or a guess)
+    inside = false; amb = false;
+    return ~res;
+  }
+  return walk_checked(geom, res, tx, ty, iter_cap, inside, amb, status);   // one test: every edge passes in `res`
 }
 
 // Multi-GPU gather fused into the kernels (north_star "final gather of the output field"): every store
@@ -731,6 +774,9 @@ __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, i
   __syncthreads();
   const R cf = active ? __ldg(w.fast_axis + f) : R(0);
   const R margin = Consts<R>::margin();
+#if GI_WALK_PREFETCH
+  const bool descending = saxis[nrows - 1] < saxis[0];
+#endif
 
   // ---- phase 1: locate -------------------------------------------------------------------------
   long long iters_sum = 0;
@@ -755,6 +801,22 @@ __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, i
         m1 = ey1; m2 = ey2; m3 = ey3; p1 = g.x1; p2 = g.x2; p3 = g.x3;
         k1 = ex1 * (cf - g.y1); k2 = ex2 * (cf - g.y2); k3 = ex3 * (cf - g.y3);
       }
+#if GI_WALK_PREFETCH
+      {
+        // The edge this column will leave the triangle through on its way along the slow axis: the cross product of
+        // edge i changes by m_i (fast axis x) or -m_i (fast axis y) per unit of the slow coordinate, so only edges
+        // with a falling cross can be crossed; two of them meet in the vertex between them, and the column passes
+        // that vertex on one side.  A prediction only (margins, descending axes): the neighbour's record is warmed.
+        const bool s1 = (FY ? m1 > R(0) : m1 < R(0)) != descending, s2 = (FY ? m2 > R(0) : m2 < R(0)) != descending,
+                   s3 = (FY ? m3 > R(0) : m3 < R(0)) != descending;
+        int pn;
+        if (s1 && s2) pn = ((FY ? cf < g.y2 : cf > g.x2) != descending) ? n3 : n1;       // edge 1 -> n3, edge 2 -> n1
+        else if (s2 && s3) pn = ((FY ? cf < g.y3 : cf > g.x3) != descending) ? n1 : n2;  // edge 3 -> n2
+        else if (s3 && s1) pn = ((FY ? cf < g.y1 : cf > g.x1) != descending) ? n2 : n3;
+        else pn = s1 ? n3 : (s2 ? n1 : n2);
+        if (pn >= 0) touch_walk(a.geom + pn);
+      }
+#endif
     };
     const int ix = FY ? srow0 : f, iy = FY ? f : srow0;
     enter(seed_lookup(a.seed, a.ncx, a.ncy, ix, iy, a.num_tri));
@@ -1005,8 +1067,8 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
         if ((mw >> ((jf - w.f0) & 31)) & 1u) continue;
       }
       bool inside, amb;
-      const int t = walk_checked(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, j, iy, a.num_tri), __ldg(x_axis + j), ty,
-                                 a.iter_cap, inside, amb, a.status);
+      const int t = locate_checked(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, j, iy, a.num_tri), __ldg(x_axis + j), ty,
+                                   a.iter_cap, inside, amb, a.status);
       if (inside && !amb) { tri = t; j0 = j; break; }
     }
     if (tri < 0) {
@@ -1021,8 +1083,10 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
     }
     // forward along the row exactly as the reference does (:367-373)
     bool inside = true, amb;
+    TriGeom<R> g;
+    int have = -1;
     for (int j = j0 + 1; j <= ix; ++j)
-      tri = walk_checked(a.geom, tri, __ldg(x_axis + j), ty, a.iter_cap, inside, amb, a.status);
+      tri = walk_checked_cached(a.geom, tri, g, have, __ldg(x_axis + j), ty, a.iter_cap, inside, amb, a.status);
     publish_target(a, f, s, tri, inside, __ldg(x_axis + ix), ty);
     atomicAdd((unsigned long long*)(a.counters + 3), 1ull);
   }
@@ -1055,6 +1119,8 @@ constexpr int kRowThreads = 256;
 //                     until its state equals the recorded one.  Exact -- and, since a guess is wrong only where the
 //                     located triangle depends on the path, 64 + a few dependent walks per row at C4 size instead
 //                     of 16 384 (round 2 had 32 pieces per row and one repair walk per piece: 544).
+// GI_BARY_TRACE: rows walked, pieces whose guess was wrong, repair walks, their iterations, iterations of the pieces
+__device__ unsigned long long g_row_walk_stats[10];  // + cycles: longest piece, repair, whole row; rounds; longest guess
 template <class R>
 __global__ void __launch_bounds__(kRowThreads) row_walk_kernel(const WalkArgs<R> a, int spec_cols) {
   __shared__ int s_tri[kRowChunk];      // found triangle, ~id = left through a hull edge
@@ -1075,49 +1141,92 @@ __global__ void __launch_bounds__(kRowThreads) row_walk_kernel(const WalkArgs<R>
     const R ty = __ldg(y_axis + iy);
     const int start = (int)a.counters[7];                                  // ind_tri = ind_tri_start   (:366)
     bool inside, amb;
+    const long long t_row0 = clock64();
     if (ix1 <= spec_cols && ix1 >= 64) {
       // pieces of at least 8 columns: the seed walk of a piece must not outweigh the piece
       const int piece = max((ix1 + kRowThreads - 1) / kRowThreads, 8), c_lo = tid * piece, c_hi = min(c_lo + piece, ix1);
       if (c_lo < ix1) {
         int tri = start;
         if (tid > 0) {  // any valid triangle may be guessed; a good guess makes the repair short
-          tri = walk_checked(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, c_lo - 1, iy, a.num_tri), __ldg(x_axis + c_lo - 1),
-                             ty, a.iter_cap, inside, amb, (int*)nullptr);
+          tri = locate_checked(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, c_lo - 1, iy, a.num_tri), __ldg(x_axis + c_lo - 1),
+                               ty, a.iter_cap, inside, amb, (int*)nullptr);
           s_guess[tid] = inside ? tri : ~tri;
+          atomicMax(&g_row_walk_stats[9], (unsigned long long)(clock64() - t_row0));
         }
+        int its = 0, have = -1;
+        TriGeom<R> g;
+        R tx = __ldg(x_axis + c_lo);
         for (int ix = c_lo; ix < c_hi; ++ix) {
-          tri = walk_checked(a.geom, tri, __ldg(x_axis + ix), ty, a.iter_cap, inside, amb, tid ? (int*)nullptr : a.status);
+          const R tx_next = __ldg(x_axis + min(ix + 1, ix1 - 1));   // (off the dependent chain)
+          tri = walk_checked_cached(a.geom, tri, g, have, tx, ty, a.iter_cap, inside, amb, tid ? (int*)nullptr : a.status,
+                                    &its);
           s_state[ix] = inside ? tri : ~tri;
+          tx = tx_next;
         }
+        atomicAdd(&g_row_walk_stats[4], (unsigned long long)its);
+        atomicMax(&g_row_walk_stats[5], (unsigned long long)(clock64() - t_row0));
       }
-      __syncthreads();
-      if (tid == 0) {
-        for (int c = piece; c < ix1; c += piece) {
-          const int prev = s_state[c - 1];                                 // the true state after column c - 1
-          if (prev == s_guess[c / piece]) continue;                        // the piece started from it: true as recorded
-          int tri = prev >= 0 ? prev : ~prev;
-          const int end = min(c + piece, ix1);
-          for (int ix = c; ix < end; ++ix) {
-            tri = walk_checked(a.geom, tri, __ldg(x_axis + ix), ty, a.iter_cap, inside, amb, a.status);   // :372-373
+      // Repair in rounds, every piece at once: a piece whose start state differs from the state recorded after the
+      // column before it is walked again from that state (until it meets its own recorded chain).  Piece 0 is true
+      // from the start, so after round r the first r pieces are -- at most one round per piece, in practice as many
+      // as a wrong state survives (a row outside the hull, where the reference keeps the hull triangle it left
+      // through until that edge no longer sees the target: ~16 pieces at C4 size).
+      const long long t_rep0 = clock64();
+      int wrong = 0, repairs = 0, its2 = 0, rounds = 0;
+      for (;;) {
+        __syncthreads();
+        int prev = 0;
+        bool redo = false;
+        if (tid > 0 && c_lo < ix1) {
+          prev = s_state[c_lo - 1];
+          redo = prev != s_guess[tid];
+        }
+        if (!__syncthreads_or(redo)) break;   // (also orders the reads above before the writes below)
+        ++rounds;
+        if (redo) {
+          ++wrong;
+          s_guess[tid] = prev;
+          int tri = prev >= 0 ? prev : ~prev, have = -1;
+          TriGeom<R> g;
+          R tx = __ldg(x_axis + c_lo);
+          for (int ix = c_lo; ix < c_hi; ++ix) {
+            const R tx_next = __ldg(x_axis + min(ix + 1, ix1 - 1));
+            const int recorded = s_state[ix];
+            tri = walk_checked_cached(a.geom, tri, g, have, tx, ty, a.iter_cap, inside, amb, a.status, &its2);   // :372-373
+            ++repairs;
             const int st = inside ? tri : ~tri;
-            if (st == s_state[ix]) break;                                  // met the recorded chain
+            if (st == recorded) break;                                     // met the recorded chain
             s_state[ix] = st;
+            tx = tx_next;
           }
         }
+      }
+      if (tid == 0) {
+        atomicAdd(&g_row_walk_stats[0], 1ull);
+        atomicMax(&g_row_walk_stats[6], (unsigned long long)(clock64() - t_rep0));
+        atomicAdd(&g_row_walk_stats[8], (unsigned long long)rounds);
+      }
+      if (wrong) {
+        atomicAdd(&g_row_walk_stats[1], (unsigned long long)wrong);
+        atomicAdd(&g_row_walk_stats[2], (unsigned long long)repairs);
+        atomicAdd(&g_row_walk_stats[3], (unsigned long long)its2);
       }
       __syncthreads();
       for (int ix = ix0 + tid; ix < ix1; ix += kRowThreads) {
         const int t = s_state[ix];
         publish_target(a, w.fast_is_y ? iy : ix, w.fast_is_y ? ix : iy, t >= 0 ? t : ~t, t >= 0, __ldg(x_axis + ix), ty);
       }
+      atomicMax(&g_row_walk_stats[7], (unsigned long long)(clock64() - t_row0));
       continue;
     }
     int tri = start;
     for (int c0 = 0; c0 < ix1; c0 += kRowChunk) {                          // :367
       const int cn = min(kRowChunk, ix1 - c0);
       if (tid == 0) {
+        TriGeom<R> g;
+        int have = -1;
         for (int i = 0; i < cn; ++i) {
-          tri = walk_checked(a.geom, tri, __ldg(x_axis + c0 + i), ty, a.iter_cap, inside, amb, a.status);  // :372-373
+          tri = walk_checked_cached(a.geom, tri, g, have, __ldg(x_axis + c0 + i), ty, a.iter_cap, inside, amb, a.status);  // :372-373
           s_tri[i] = inside ? tri : ~tri;
         }
       }
@@ -1470,6 +1579,21 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
                          st>>>(wa, spec_cols);
   }
   GI_CUDA(cudaGetLastError());
+  static const bool trace = getenv("GI_BARY_TRACE") != nullptr;
+  if (trace) {  // debugging aid (synchronises): what the fix-up paths had to do in this window
+    int64_t c[8];
+    unsigned long long rs[10], zero[10] = {};
+    GI_CUDA(cudaMemcpyAsync(c, wa.counters, sizeof(c), cudaMemcpyDeviceToHost, st));
+    GI_CUDA(cudaMemcpyFromSymbolAsync(rs, g_row_walk_stats, sizeof(rs), 0, cudaMemcpyDeviceToHost, st));
+    GI_CUDA(cudaMemcpyToSymbolAsync(g_row_walk_stats, zero, sizeof(zero), 0, cudaMemcpyHostToDevice, st));
+    GI_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "[gridinterp] walk window %d x %d: iterations %lld, flagged %lld (list %d), fixed up %lld, start "
+                    "triangle %lld; row walk: %llu rows, %llu pieces with a wrong guess, %llu repair walks (%llu "
+                    "iterations) in %llu rounds, %llu iterations in the pieces; cycles: longest guess %llu, longest piece "
+                    "%llu, repair %llu, row %llu\n",
+            nf, ns, (long long)c[0], (long long)c[5], wa.amb_cap, (long long)c[3], (long long)c[7], rs[0], rs[1], rs[2],
+            rs[3], rs[8], rs[4], rs[9], rs[5], rs[6], rs[7]);
+  }
   return GI_OK;
 }
 
