@@ -1043,6 +1043,10 @@ constexpr int kMaxBackup = 256;
 // entries of the fix-up work list (gi_set_fixup_list_capacity shrinks it: tests of the overflow path)
 inline int64_t amb_list_limit() { return fixup_list_capacity(); }  // gi_set_fixup_list_capacity (api.cu)
 
+// Thread per flagged target for the usual case (the column before it is a certain start: one seed walk, one step);
+// a target whose back-up has to go further is taken by its whole warp, 32 candidate columns at a time -- in single
+// precision, or on a lattice, whole stretches of a row are ambiguous, and 256 candidates tested one after the other
+// by one thread (each a seed walk of ~10 dependent record loads) made the kernel's tail (f32 C4: 1.2 ms).
 template <class R>
 __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len_x, int len_y) {
   const TargetWindow<R>& w = a.win;
@@ -1050,38 +1054,25 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
   const int nf = w.nf(), wpr = (nf + 31) >> 5;
   const R* x_axis = w.fast_is_y ? w.slow_axis : w.fast_axis;
   const R* y_axis = w.fast_is_y ? w.fast_axis : w.slow_axis;
-  for (int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; li < n; li += (int64_t)gridDim.x * blockDim.x) {
-    const int lin = a.amb_list[li];
-    const int s = w.s0 + lin / nf, f = w.f0 + lin % nf;
-    const int ix = w.fast_is_y ? s : f, iy = w.fast_is_y ? f : s;
-    const R ty = __ldg(y_axis + iy);
-    // back up to the nearest column of this row whose triangle does not depend on the path
-    int tri = -1, j0 = -1;
-    const int j_stop = max(ix - kMaxBackup, 0);
-    for (int j = ix - 1; j >= j_stop; --j) {
-      // phase 1 has classified column j already: one it found outside the hull cannot be the certain INSIDE start
-      // looked for here (passing over a candidate is always safe; a row outside the hull costs 256 loads, not walks)
-      const int jf = w.fast_is_y ? iy : j, js = w.fast_is_y ? j : iy;
-      if (jf >= w.f0 && jf < w.f1 && js >= w.s0 && js < w.s1) {
-        const uint32_t mw = a.mask_words[(int64_t)(js - w.s0) * wpr + ((jf - w.f0) >> 5)];
-        if ((mw >> ((jf - w.f0) & 31)) & 1u) continue;
-      }
-      bool inside, amb;
-      const int t = locate_checked(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, j, iy, a.num_tri), __ldg(x_axis + j), ty,
-                                   a.iter_cap, inside, amb, a.status);
-      if (inside && !amb) { tri = t; j0 = j; break; }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // is column j of row iy a certain start?  (inside, and not within the margin band of an edge: any walk finds it)
+  auto certain = [&](int j, int iy, R ty, int& tri) -> bool {
+    // phase 1 has classified column j already: one it found outside the hull cannot be the certain INSIDE start
+    // looked for here (passing over a candidate is always safe; a row outside the hull costs loads, not walks)
+    const int jf = w.fast_is_y ? iy : j, js = w.fast_is_y ? j : iy;
+    if (jf >= w.f0 && jf < w.f1 && js >= w.s0 && js < w.s1) {
+      const uint32_t mw = a.mask_words[(int64_t)(js - w.s0) * wpr + ((jf - w.f0) >> 5)];
+      if ((mw >> ((jf - w.f0) & 31)) & 1u) return false;
     }
-    if (tri < 0) {
-      // no path-independent column within kMaxBackup (a grid row running along mesh edges): only column 0 (the
-      // reference's ind_tri_start, :366) is another certain starting point
-      if (j_stop > 0) {  // leave the row to row_walk_kernel, which redoes it along the reference's own path
-        a.row_todo[iy] = 1;
-        a.counters[6] = 1;
-        continue;
-      }
-      tri = (int)a.counters[7];
-    }
-    // forward along the row exactly as the reference does (:367-373)
+    bool inside, amb;
+    tri = locate_checked(a.geom, seed_lookup(a.seed, a.ncx, a.ncy, j, iy, a.num_tri), __ldg(x_axis + j), ty, a.iter_cap,
+                         inside, amb, a.status);
+    return inside && !amb;
+  };
+  // forward along the row from the state after column j0 exactly as the reference does (:367-373), then publish
+  auto finish = [&](int tri, int j0, int ix, int iy, int f, int s, R ty) {
     bool inside = true, amb;
     TriGeom<R> g;
     int have = -1;
@@ -1089,6 +1080,54 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
       tri = walk_checked_cached(a.geom, tri, g, have, __ldg(x_axis + j), ty, a.iter_cap, inside, amb, a.status);
     publish_target(a, f, s, tri, inside, __ldg(x_axis + ix), ty);
     atomicAdd((unsigned long long*)(a.counters + 3), 1ull);
+  };
+  for (int64_t base = warp * 32; base < n; base += nwarps * 32) {   // (warp-uniform trip count)
+    const int64_t li = base + lane;
+    bool far = false;
+    int f = 0, s = 0, ix = 0, iy = 0;
+    R ty = R(0);
+    if (li < n) {
+      const int lin = a.amb_list[li];
+      s = w.s0 + lin / nf; f = w.f0 + lin % nf;
+      ix = w.fast_is_y ? s : f; iy = w.fast_is_y ? f : s;
+      ty = __ldg(y_axis + iy);
+      int tri = -1;
+      if (ix == 0) finish((int)a.counters[7], -1, ix, iy, f, s, ty);     // column 0 starts at ind_tri_start (:366)
+      else if (certain(ix - 1, iy, ty, tri)) finish(tri, ix - 1, ix, iy, f, s, ty);
+      else far = true;
+    }
+    // back up to the nearest column of this row whose triangle does not depend on the path
+    unsigned todo = __ballot_sync(0xffffffffu, far);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int t_ix = __shfl_sync(0xffffffffu, ix, src), t_iy = __shfl_sync(0xffffffffu, iy, src);
+      const R t_ty = __ldg(y_axis + t_iy);
+      const int j_stop = max(t_ix - kMaxBackup, 0);
+      int tri = -1, j0 = -1;
+      for (int jb = t_ix - 2; jb >= j_stop && tri < 0; jb -= 32) {
+        const int j = jb - lane;
+        int t = -1;
+        const bool ok = j >= j_stop && certain(j, t_iy, t_ty, t);
+        const unsigned hit = __ballot_sync(0xffffffffu, ok);
+        if (hit) {
+          const int l = __ffs(hit) - 1;   // the nearest one
+          tri = __shfl_sync(0xffffffffu, t, l);
+          j0 = jb - l;
+        }
+      }
+      if (lane == src) {
+        if (tri < 0 && j_stop > 0) {
+          // no path-independent column within kMaxBackup (a grid row running along mesh edges): only column 0 (the
+          // reference's ind_tri_start, :366) is another certain starting point -- leave the row to row_walk_kernel,
+          // which redoes it along the reference's own path
+          a.row_todo[iy] = 1;
+          a.counters[6] = 1;
+        } else {
+          finish(tri < 0 ? (int)a.counters[7] : tri, j0, ix, iy, f, s, ty);
+        }
+      }
+    }
   }
 }
 
@@ -1559,7 +1598,7 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
   const int n_search = std::min(num_points, pm.num_tri);  // the reference searches triangles 1..num_points (:347)
   start_tri_kernel<R><<<kStartBlocks, 256, 0, st>>>(pm.geom, pm.raw, n_search, x_axis, y_axis, len_y, wa.counters,
                                                     wa.start_part, wa.reference_rows);
-  fixup_kernel<R><<<kNumSMs * 2, 128, 0, st>>>(wa, len_x, len_y);
+  fixup_kernel<R><<<kNumSMs * 8, 128, 0, st>>>(wa, len_x, len_y);
   // more flagged targets than the list holds, or GI_BARY_REFERENCE_ORDER: the reference's row-sequential walk
   {
     const int cols = wa.win.fast_is_y ? wa.win.s1 : wa.win.f1;            // a row is walked from column 0
