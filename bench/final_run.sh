@@ -2,7 +2,7 @@
 # reference arm, ncu launch lists of the same commands, ncu --set full captures of the dominant kernels.
 set -x
 cd $GRAFT_REPO_ROOT
-T=${1:-fin2}
+T=${1:-fin3}
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/${T}_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1
 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_c4.json 2> gpurun_out/${T}_c4.err
@@ -15,3 +15,5 @@ ncu --set full --clock-control none --import-source on -k regex:pack_mesh_kernel
 ncu --set full --clock-control none --import-source on -k regex:bilinear_sector_kernel -s 2 -c 1 -o gpurun_out/${T}_bilinear -f python bench/phase_probe.py c5 1.0 > gpurun_out/${T}_ncu_bil.log 2>&1
 cat gpurun_out/${T}_pytest.log gpurun_out/${T}_smoke.log gpurun_out/${T}_c1.log
 tail -c 600 gpurun_out/${T}_c4.json
+PYTHONPATH=. python bench/f32_probe.py > gpurun_out/${T}_f32.log 2>&1
+tail -8 gpurun_out/${T}_f32.log
