@@ -73,6 +73,7 @@ for _suf, _real in (("f64", _d), ("f32", _f)):
         f"gi_bilinear_morton_order_{_suf}": ([_vp, _i, _vp, _i, _vp, _i64, _vp, _i, _i, _vp], _i),
         f"gi_barycentric_points_{_suf}": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp], _i),
         f"gi_idw_esrg_nearest_points_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _i, _real, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp], _i),
+        f"gi_mesh_reorder_{_suf}": ([_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp], _i),
         f"gi_idw_kdtree_points_{_suf}": ([_vp, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp], _i),
     })
 

@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgridinterp.so")
-SOURCES = ["api.cu", "bilinear.cu", "barycentric.cu", "esrg.cu", "kdtree.cu"]
+SOURCES = ["api.cu", "bilinear.cu", "barycentric.cu", "esrg.cu", "kdtree.cu", "mesh.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3", "-Xptxas", "-v"]
 

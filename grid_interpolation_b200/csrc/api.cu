@@ -397,6 +397,40 @@ static int bilinear_morton_order_api(const R* x_axis, int len_x, const R* y_axis
   return read_status(st, true);
 }
 
+template <class R>
+static int mesh_reorder_api(const R* points, int num_points, const int32_t* simplices, const int32_t* neighbours,
+                            int num_tri, R* points_out, int32_t* point_order, int32_t* simplices_out,
+                            int32_t* neighbours_out, int32_t* triangle_order, int flags, int mem, void* stream) {
+  GI_CHECK_COMMON();
+  GI_REQUIRE(points && simplices && neighbours && simplices_out && neighbours_out, "null pointer");
+  GI_REQUIRE(num_points >= 3 && num_tri >= 1, "need at least 3 points and 1 triangle");
+  GI_REQUIRE((points_out == nullptr) == (point_order == nullptr), "points_out and point_order come together");
+  if (mem == GI_DEVICE)
+    return mesh_reorder_device<R>(points, num_points, simplices, neighbours, num_tri, points_out, point_order,
+                                  simplices_out, neighbours_out, triangle_order, flags, (cudaStream_t)stream);
+  GI_TRY(ensure_device());
+  cudaStream_t st;
+  GI_TRY(host_stream(&st));
+  Scratch scr(st);
+  R *dp, *dpo;
+  int32_t *ds, *dn, *dso, *dno, *dto, *dporder;
+  GI_TRY(to_device(scr, points, (size_t)2 * num_points, &dp));
+  GI_TRY(to_device(scr, simplices, (size_t)3 * num_tri, &ds));
+  GI_TRY(to_device(scr, neighbours, (size_t)3 * num_tri, &dn));
+  GI_TRY(out_device(scr, points_out, (size_t)2 * num_points, &dpo));
+  GI_TRY(out_device(scr, point_order, (size_t)num_points, &dporder));
+  GI_TRY(scr.alloc(&dso, (size_t)3 * num_tri));
+  GI_TRY(scr.alloc(&dno, (size_t)3 * num_tri));
+  GI_TRY(out_device(scr, triangle_order, (size_t)num_tri, &dto));
+  GI_TRY(mesh_reorder_device<R>(dp, num_points, ds, dn, num_tri, dpo, dporder, dso, dno, dto, flags, st));
+  GI_TRY(to_host(st, points_out, dpo, (size_t)2 * num_points));
+  GI_TRY(to_host(st, point_order, dporder, (size_t)num_points));
+  GI_TRY(to_host(st, simplices_out, dso, (size_t)3 * num_tri));
+  GI_TRY(to_host(st, neighbours_out, dno, (size_t)3 * num_tri));
+  GI_TRY(to_host(st, triangle_order, dto, (size_t)num_tri));
+  return read_status(st, true);
+}
+
 // scattered targets: host form = copy in, device form, copy out (synchronous)
 template <class R>
 static int barycentric_points_api(const R* points, int num_points, const R* data_in, const int32_t* simplices,
@@ -904,6 +938,13 @@ GI_API void gi_plan_destroy(gi_plan* plan) {
                                               int32_t* nn_index, R* nn_dist2, int flags, int mem, void* stream) {  \
     return esrg_points_api<R>(points, num_points, data_in, x_axis, len_x, y_axis, len_y, grid_spac, targets,       \
                               num_targets, num_neighbours, data_ip, nn_index, nn_dist2, flags, mem, stream);       \
+  }                                                                                                                 \
+  GI_API int gi_mesh_reorder_##SUF(const R* points, int num_points, const int32_t* simplices,                      \
+                                   const int32_t* neighbours, int num_triangles, R* points_out,                   \
+                                   int32_t* point_order, int32_t* simplices_out, int32_t* neighbours_out,         \
+                                   int32_t* triangle_order, int flags, int mem, void* stream) {                   \
+    return mesh_reorder_api<R>(points, num_points, simplices, neighbours, num_triangles, points_out, point_order,  \
+                               simplices_out, neighbours_out, triangle_order, flags, mem, stream);                 \
   }                                                                                                                 \
   GI_API int gi_fill_nearest_neighbour_##SUF(const uint8_t* mask_outside, int len_x, int len_y, R* data_ip,        \
                                              int64_t* fill_src, int flags, int mem, void* stream) {                \

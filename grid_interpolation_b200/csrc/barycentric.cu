@@ -656,8 +656,21 @@ template <class R> struct WalkArgs {
   int* row_todo;        // [len_y], zeroed: grid rows a fix-up handed to row_walk_kernel
   const int* only_if;   // locate_eval_kernel: run only if this device flag is set (nullptr: always), see raster.cuh
   HaloFix<R> hfix;      // where fix-ups leave the values of halo targets (see HaloFix)
+  const uint8_t* need;  // band-limited pack: which triangles have records (nullptr: all); set by bary_walk
   int* status;
 };
+
+// The reference's start triangle (ind_tri_start, counters[7]) as the start of a walk.  After a band-limited pack it
+// may have no record (it lies near the first column at the MIDDLE row of the grid, wherever the band is): the call
+// is then repeated with the whole mesh, like any walk that would leave the packed set (GI_ERR_PACK_WINDOW).
+template <class R> __device__ __forceinline__ int start_triangle(const WalkArgs<R>& a) {
+  const int t = (int)a.counters[7];
+  if (a.need && !a.need[t]) {
+    raise_status(a.status, GI_ERR_PACK_WINDOW);
+    return -1;
+  }
+  return t;
+}
 
 // Phase 2 of the locate / raster kernels: evaluate one strip of ROWS x kWalkThreads targets whose triangles are in
 // the shared-memory tile `stri` (>= 0: inside that triangle; < 0: outside the hull, ~id of the last valid triangle
@@ -1092,7 +1105,10 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
       ix = w.fast_is_y ? s : f; iy = w.fast_is_y ? f : s;
       ty = __ldg(y_axis + iy);
       int tri = -1;
-      if (ix == 0) finish((int)a.counters[7], -1, ix, iy, f, s, ty);     // column 0 starts at ind_tri_start (:366)
+      if (ix == 0) {                                                     // column 0 starts at ind_tri_start (:366)
+        const int t0 = start_triangle(a);
+        if (t0 >= 0) finish(t0, -1, ix, iy, f, s, ty);
+      }
       else if (certain(ix - 1, iy, ty, tri)) finish(tri, ix - 1, ix, iy, f, s, ty);
       else far = true;
     }
@@ -1124,7 +1140,8 @@ __global__ void __launch_bounds__(128) fixup_kernel(const WalkArgs<R> a, int len
           a.row_todo[iy] = 1;
           a.counters[6] = 1;
         } else {
-          finish(tri < 0 ? (int)a.counters[7] : tri, j0, ix, iy, f, s, ty);
+          if (tri < 0) tri = start_triangle(a);
+          if (tri >= 0) finish(tri, j0, ix, iy, f, s, ty);
         }
       }
     }
@@ -1178,7 +1195,8 @@ __global__ void __launch_bounds__(kRowThreads) row_walk_kernel(const WalkArgs<R>
     __syncthreads();
     if (tid == 0) a.row_todo[iy] = 0;
     const R ty = __ldg(y_axis + iy);
-    const int start = (int)a.counters[7];                                  // ind_tri = ind_tri_start   (:366)
+    const int start = start_triangle(a);                                   // ind_tri = ind_tri_start   (:366)
+    if (start < 0) continue;   // (no record for it: GI_ERR_PACK_WINDOW raised, the caller repeats with the whole mesh)
     bool inside, amb;
     const long long t_row0 = clock64();
     if (ix1 <= spec_cols && ix1 >= 64) {
@@ -1521,6 +1539,7 @@ template <class R>
 int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis, const R* y_axis, int len_x, int len_y,
               int num_points, cudaStream_t st, const TileBins* bins = nullptr, int tile_row0 = 0) {
   WalkArgs<R> wa = wa_in;
+  wa.need = pm.need;
   const int nf = wa.win.nf(), ns = wa.win.ns();
   // 128 columns x 32 rows per CTA, 64 registers, >= 8 CTAs per SM: the best of the shapes measured in round 1
   // (profiles/r01_walk_variants.md)

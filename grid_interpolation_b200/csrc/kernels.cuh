@@ -64,6 +64,12 @@ int esrg_points_device(const R* points, int num_points, const R* data_in, const 
                        int len_y, R grid_spac, const R* targets, int64_t num_targets, int k, R* data_ip,
                        int32_t* nn_index, R* nn_dist2, int flags, cudaStream_t st);
 
+// mesh.cu -- mesh ingest: triangles (and optionally points) renumbered along the Z curve of their position
+template <class R>
+int mesh_reorder_device(const R* points, int num_points, const int32_t* simplices, const int32_t* neighbours,
+                        int num_tri, R* points_out, int32_t* point_order, int32_t* simplices_out,
+                        int32_t* neighbours_out, int32_t* triangle_order, int flags, cudaStream_t st);
+
 // GI_HOST forms of the four operators (host pointers in, synchronous): copies and compute are pipelined over
 // output bands / point chunks (common.cuh, HostPipe).  No debug outputs; api.cu falls back to "copy in, *_device,
 // copy out" when those are requested.

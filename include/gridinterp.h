@@ -278,6 +278,26 @@ int gi_idw_esrg_nearest_points_f32(const float* points, int num_points, const fl
                                    int64_t num_targets, int num_neighbours, float* data_ip, int32_t* nn_index,
                                    float* nn_dist2, int flags, int mem, void* stream);
 
+/* Mesh ingest ("GPU Delaunay / mesh ingest"; no counterpart in the reference, which takes simplices and
+ * neighbours in Qhull's facet order and the points in the caller's order, test_interpolation.py:64-67): the same
+ * mesh renumbered along the Z curve of position, so that every kernel that follows a link reads nearby memory.
+ *   triangle_order[j] = 1-based input id of the triangle that becomes triangle j+1: triangles sorted (stable) by the
+ *     Z value of their centroid ((x1+x2+x3)/3, (y1+y2+y3)/3); Z value of a position = 16 bits per axis,
+ *     q = trunc((v - v_min) * (65535 / (v_max - v_min))) over the points' bounding box, x in the even bits;
+ *   simplices_out / neighbours_out: row j = the input row of that triangle (vertex order and neighbour columns
+ *     kept, so every interpolated value is computed from the same operands), triangle ids renumbered, 0 = none;
+ *   points_out / point_order (both or neither): the points sorted (stable) by their own Z value, point_order[j] =
+ *     1-based input id of the point that becomes point j+1, simplices_out then holds the new vertex ids and the
+ *     caller permutes its nodal values the same way (data_in[point_order - 1]).
+ * Layouts as `flags` says for the inputs (GI_POINTS_ROWMAJOR, GI_TOPO_ROWMAJOR); outputs in the same layouts.
+ * An id out of range raises GI_ERR_BAD_INDEX. */
+int gi_mesh_reorder_f64(const double* points, int num_points, const int32_t* simplices, const int32_t* neighbours,
+                        int num_triangles, double* points_out, int32_t* point_order, int32_t* simplices_out,
+                        int32_t* neighbours_out, int32_t* triangle_order, int flags, int mem, void* stream);
+int gi_mesh_reorder_f32(const float* points, int num_points, const int32_t* simplices, const int32_t* neighbours,
+                        int num_triangles, float* points_out, int32_t* point_order, int32_t* simplices_out,
+                        int32_t* neighbours_out, int32_t* triangle_order, int flags, int mem, void* stream);
+
 /* Row band [row_begin, row_end) of barycentric_interpolation computed on the current device and stored at its
  * place in num_fields (<= GI_MAX_GATHER_FIELDS) FULL (len_y, len_x) fields in the layout `flags` selects:
  * fields[0] must be memory of the current device (the hull fill reads its source cells there), the others are the
