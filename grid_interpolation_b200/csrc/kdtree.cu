@@ -121,6 +121,108 @@ kd_partition_kernel(const int* __restrict__ split, const int* __restrict__ other
   else { seg_lo_new[p] = m + 1; seg_hi_new[p] = hi; }
 }
 
+// The last levels in shared memory: once every segment has at most kFinishMax points (n >> d0 <= kFinishMax), one
+// CTA per segment runs the remaining levels of the same algorithm -- flag, prefix sum, stable partition of the other
+// list around the median of the split list -- on local positions, with barriers instead of launches: 1 launch
+// instead of 5 per level for the lower half of the tree (1 M points: levels 10..19, 0.45 of the build's 1.35 ms;
+// 5 000 points: 2 levels by launches instead of 13).  CTA b finds its segment by descending d0 levels along the bits
+// of b -- the segment bounds are pure arithmetic (kd_tree.f90:54).
+constexpr int kFinishMax = 1024;
+constexpr int kFinishItems = kFinishMax / 256;
+__global__ void __launch_bounds__(256)
+kd_finish_kernel(int* __restrict__ list_x, const int* __restrict__ list_y, const int* __restrict__ pos_x,
+                 const int* __restrict__ pos_y, int n, int d0, int levels) {
+  __shared__ int L[3][kFinishMax];     // point ids by position: two lists + the partition's destination
+  __shared__ short X[3][kFinishMax];   // X[a][i]: position in the OTHER list of the point at position i of list a
+  __shared__ short slo[kFinishMax], shi[kFinishMax];
+  __shared__ int scan[kFinishMax];
+  int lo = 0, hi = n;
+  for (int j = d0 - 1; j >= 0 && lo < hi; --j) {
+    const int m = lo + ((hi - lo + 1) >> 1) - 1;   // ind_median = (num_points + 1) / 2   (kd_tree.f90:54)
+    if ((blockIdx.x >> j) & 1) lo = m + 1; else hi = m;
+  }
+  const int M = hi - lo;
+  if (M <= 0) return;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < M; i += 256) {
+    const int px = list_x[lo + i], py = list_y[lo + i];
+    L[0][i] = px; L[1][i] = py;
+    X[0][i] = (short)(pos_y[px] - lo);
+    X[1][i] = (short)(pos_x[py] - lo);
+    slo[i] = 0; shi[i] = (short)M;
+  }
+  int buf[2] = {0, 1}, spare = 2;   // which of L / X holds list x, list y
+  __syncthreads();
+  for (int d = d0; d < levels; ++d) {
+    const int ax = d & 1, ot = ax ^ 1;  // axis = mod(depth, 2)   (kd_tree.f90:45)
+    const int bs = buf[ax], bo = buf[ot];
+    int l[kFinishItems], m[kFinishItems], f[kFinishItems];
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < kFinishItems; ++i) {
+      const int p = tid * kFinishItems + i;
+      l[i] = -1; m[i] = 0; f[i] = 0;
+      if (p < M) {
+        l[i] = slo[p];
+        if (l[i] >= 0) {
+          const int h = shi[p];
+          m[i] = l[i] + ((h - l[i] + 1) >> 1) - 1;
+          f[i] = X[bo][p] < m[i] ? 1 : 0;      // the point at position p of the other list goes left
+        }
+      }
+      acc += f[i];
+    }
+    int total;
+    int run = block_exclusive_scan_256(acc, &total);
+#pragma unroll
+    for (int i = 0; i < kFinishItems; ++i) {
+      const int p = tid * kFinishItems + i;
+      if (p < M) scan[p] = run;
+      run += f[i];
+    }
+    __syncthreads();
+    int newp[kFinishItems], ps[kFinishItems];
+#pragma unroll
+    for (int i = 0; i < kFinishItems; ++i) {
+      const int p = tid * kFinishItems + i;
+      newp[i] = p; ps[i] = 0;
+      if (p < M) {
+        ps[i] = X[bo][p];
+        if (l[i] >= 0) {
+          const int left_before = scan[p] - scan[l[i]];
+          if (ps[i] < m[i]) newp[i] = l[i] + left_before;          // left subtree keeps its relative order
+          else if (ps[i] == m[i]) newp[i] = m[i];                  // the node
+          else {
+            const int node_pos = X[bs][m[i]];
+            newp[i] = m[i] + 1 + ((p - l[i]) - left_before - (node_pos < p ? 1 : 0));
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kFinishItems; ++i) {
+      const int p = tid * kFinishItems + i;
+      if (p < M) {
+        L[spare][newp[i]] = L[bo][p];
+        X[spare][newp[i]] = (short)ps[i];
+        if (l[i] >= 0) {
+          X[bs][ps[i]] = (short)newp[i];
+          // the segment bookkeeping is per POSITION
+          const int h = shi[p];
+          if (p < m[i]) { shi[p] = (short)m[i]; }
+          else if (p == m[i]) { slo[p] = -1; shi[p] = -1; }
+          else { slo[p] = (short)(m[i] + 1); shi[p] = (short)h; }
+        }
+      }
+    }
+    __syncthreads();
+    buf[ot] = spare;
+    spare = bo;
+  }
+  for (int i = tid; i < M; i += 256) list_x[lo + i] = L[buf[0]][i];   // both lists are the tree order now
+}
+
 template <class R> struct alignas(16) XY { R x, y; };
 
 template <class R>
@@ -383,7 +485,11 @@ int kd_build(Scratch& scr, PointsView<R> pv, int n, int flags, int** order_dev) 
   kd_init_kernel<<<blocks, 256, 0, st>>>(list[0], list[1], n, pos[0], pos[1], seg_lo, seg_hi);
   int levels = 0;
   while ((1ll << levels) <= (long long)n) ++levels;  // floor(log2 n) + 1
-  for (int d = 0; d < levels; ++d) {
+  int d0 = 0;   // levels done by launches: until every segment fits a CTA's shared memory (kd_finish_kernel)
+  while ((n >> d0) > kFinishMax) ++d0;
+  static const bool no_finish = getenv("GI_KD_NO_SMEM_FINISH") != nullptr;   // A/B and tests
+  if (no_finish) d0 = levels;
+  for (int d = 0; d < d0; ++d) {
     const int ax = d & 1, ot = ax ^ 1;  // axis = mod(depth, 2)   (kd_tree.f90:45)
     kd_flag_kernel<<<blocks, 256, 0, st>>>(list[ot], pos[ax], seg_lo, seg_hi, n, flag);
     GI_TRY(exclusive_scan_i32(scr, flag, flag, n));
@@ -394,6 +500,7 @@ int kd_build(Scratch& scr, PointsView<R> pv, int n, int flags, int** order_dev) 
     std::swap(seg_lo, seg_lo_new);
     std::swap(seg_hi, seg_hi_new);
   }
+  if (d0 < levels) kd_finish_kernel<<<1u << d0, 256, 0, st>>>(list[0], list[1], pos[0], pos[1], n, d0, levels);
   GI_CUDA(cudaGetLastError());
   *order_dev = list[0];  // both lists are identical once every position is a node
   return GI_OK;
