@@ -266,6 +266,64 @@ struct alignas(16) KdfNode {
   int depth;
 };
 
+// Sub-arrays of at most kSerialMax points do not take part in the rounds: a round costs ~100 us whatever the size of
+// the ranges, and half of the few hundred rounds of a 1 M-point build belong to the lowest ten levels.  One warp per
+// such sub-array copies it to shared memory and lane 0 runs the reference's recursion on it as written
+// (build_kd_tree / partition_iter, kd_tree.f90:30-155, in place): a thousand serial builds side by side, ~1.4 ms.
+constexpr int kSerialMax = 1024;
+struct KdfSmall { int lo, hi, depth; };   // positions [lo, hi] of the array, depth of the sub-tree's root
+
+template <class R>
+__global__ void __launch_bounds__(32)
+kdf_serial_kernel(R* __restrict__ X, R* __restrict__ Y, int* __restrict__ ID, const KdfSmall* __restrict__ work,
+                  const int* __restrict__ count) {
+  __shared__ R sx[kSerialMax], sy[kSerialMax];
+  __shared__ int sid[kSerialMax];
+  const int lane = threadIdx.x;
+  const int nwork = *count;
+  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const KdfSmall it = work[wi];
+    const int m = it.hi - it.lo + 1;
+    for (int i = lane; i < m; i += 32) { sx[i] = X[it.lo + i]; sy[i] = Y[it.lo + i]; sid[i] = ID[it.lo + i]; }
+    __syncwarp();
+    if (lane == 0) {
+      auto swap3 = [&](int a, int b) {
+        const R tx = sx[a], ty = sy[a]; const int ti = sid[a];
+        sx[a] = sx[b]; sy[a] = sy[b]; sid[a] = sid[b];
+        sx[b] = tx; sy[b] = ty; sid[b] = ti;
+      };
+      int s_lo[32], s_hi[32], s_d[32];   // sub-arrays still to be built (the recursion of :64-68)
+      int sp = 1;
+      s_lo[0] = 0; s_hi[0] = m - 1; s_d[0] = it.depth;
+      while (sp > 0) {
+        --sp;
+        const int lo = s_lo[sp], hi = s_hi[sp], d = s_d[sp];
+        const int k = lo + ((hi - lo + 2) >> 1) - 1;           // ind_median = (num_points + 1) / 2   (:54)
+        const R* K = (d & 1) ? sy : sx;                        // axis = mod(depth, 2)   (:45)
+        int a = lo, b = hi;
+        while (a != b) {                                       // partition_iter (:112)
+          const int pidx = (a + b) >> 1;                       // :115
+          const R pivot = K[pidx];
+          swap3(pidx, b);                                      // :119-124
+          int store = a;
+          for (int i = a; i < b; ++i) {                        // :128-138
+            if (K[i] < pivot) { swap3(store, i); ++store; }
+          }
+          swap3(store, b);                                     // :141-146
+          if (k < store) b = store - 1;                        // :149-153
+          else if (k > store) a = store + 1;
+          else break;
+        }
+        if (k > lo && sp < 32) { s_lo[sp] = lo; s_hi[sp] = k - 1; s_d[sp] = d + 1; ++sp; }
+        if (k < hi && sp < 32) { s_lo[sp] = k + 1; s_hi[sp] = hi; s_d[sp] = d + 1; ++sp; }
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) { X[it.lo + i] = sx[i]; Y[it.lo + i] = sy[i]; ID[it.lo + i] = sid[i]; }
+    __syncwarp();
+  }
+}
+
 // position i of the array as the pass sees it, i.e. after pivot and last element were exchanged (:119-124)
 __device__ __forceinline__ int kdf_virt(int i, int pidx, int hi) { return i == pidx ? hi : (i == hi ? pidx : i); }
 
@@ -323,7 +381,8 @@ __global__ void __launch_bounds__(256)
 kdf_pass_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __restrict__ ID, int* __restrict__ nid,
                 const KdfNode* __restrict__ nodes, const int* __restrict__ flag, const int* __restrict__ F,
                 const int* __restrict__ first_ge, int n, R* __restrict__ X2, R* __restrict__ Y2,
-                int* __restrict__ ID2, KdfNode* __restrict__ nodes_next, int* __restrict__ alive) {
+                int* __restrict__ ID2, KdfNode* __restrict__ nodes_next, int* __restrict__ alive,
+                KdfSmall* __restrict__ small, int* __restrict__ small_count, int serial_max) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const int node = nid[p];
@@ -364,16 +423,25 @@ kdf_pass_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __r
       }
     }
   }
+  // a child of at most kSerialMax points leaves the rounds: kdf_serial_kernel finishes its whole sub-tree
+  const bool left_small = k - node <= serial_max, right_small = nd.n_hi - k <= serial_max;   // (0: none)
   if (p == hi) {  // one thread per node writes the next state(s)
     if (!fin) { nodes_next[node] = KdfNode{nlo, nhi, nd.n_hi, nd.depth}; *alive = 1; }
     else {
-      if (k > node) { nodes_next[node] = KdfNode{node, k - 1, k - 1, nd.depth + 1}; *alive = 1; }          // :64-65
-      if (k < nd.n_hi) { nodes_next[k + 1] = KdfNode{k + 1, nd.n_hi, nd.n_hi, nd.depth + 1}; *alive = 1; }  // :66-68
+      if (k > node) {                                                                                        // :64-65
+        if (left_small) small[atomicAdd(small_count, 1)] = KdfSmall{node, k - 1, nd.depth + 1};
+        else { nodes_next[node] = KdfNode{node, k - 1, k - 1, nd.depth + 1}; *alive = 1; }
+      }
+      if (k < nd.n_hi) {                                                                                     // :66-68
+        if (right_small) small[atomicAdd(small_count, 1)] = KdfSmall{k + 1, nd.n_hi, nd.depth + 1};
+        else { nodes_next[k + 1] = KdfNode{k + 1, nd.n_hi, nd.n_hi, nd.depth + 1}; *alive = 1; }
+      }
     }
   }
   if (fin) {
     if (p == k) nid[p] = -1;      // :59-61 the node
-    else if (p > k) nid[p] = k + 1;
+    else if (p > k) nid[p] = right_small ? -2 : k + 1;
+    else if (left_small) nid[p] = -2;
   }
 }
 
@@ -417,10 +485,23 @@ int kd_build_faithful(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
   GI_TRY(scr.alloc(&nodes, (size_t)n)); GI_TRY(scr.alloc(&nodes_next, (size_t)n));
   GI_TRY(scr.alloc(&sums, (size_t)div_up(n, kScanTile)));
   GI_TRY(scr.alloc(&alive, 1));
+  KdfSmall* small;
+  int* small_count;
+  GI_TRY(scr.alloc(&small, (size_t)n));
+  GI_TRY(scr.alloc(&small_count, 1));
+  GI_CUDA(cudaMemsetAsync(small_count, 0, sizeof(int), st));
   const int blocks = div_up(n, 256);
   kdf_init_kernel<R><<<blocks, 256, 0, st>>>(pv, n, X, Y, ID, nid, nodes);
+  static const bool no_serial = getenv("GI_KD_NO_SERIAL_FINISH") != nullptr;   // A/B and tests: rounds down to the leaves
   constexpr int kBatch = 8;  // rounds between two looks at the `alive` word
-  for (int64_t round = 0;; round += kBatch) {
+  if (n <= kSerialMax && !no_serial) {   // the whole tree is one small sub-array
+    const KdfSmall whole{0, n - 1, 0};
+    const int one = 1;
+    GI_CUDA(cudaMemcpyAsync(small, &whole, sizeof(whole), cudaMemcpyHostToDevice, st));
+    GI_CUDA(cudaMemcpyAsync(small_count, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    GI_CUDA(cudaStreamSynchronize(st));   // (the two host words go out of scope)
+  }
+  for (int64_t round = 0; n > kSerialMax || no_serial; round += kBatch) {
     GI_REQUIRE(round <= 4 * (int64_t)n + 64, "k-d build did not converge");
     GI_CUDA(cudaMemsetAsync(alive, 0, sizeof(int), st));
     for (int b = 0; b < kBatch; ++b) {
@@ -429,7 +510,7 @@ int kd_build_faithful(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
       kdf_first_ge_kernel<<<blocks, 256, 0, st>>>(nid, nodes, F, n, first_ge);
       if (b == kBatch - 1) GI_CUDA(cudaMemsetAsync(alive, 0, sizeof(int), st));  // what the LAST round leaves
       kdf_pass_kernel<R><<<blocks, 256, 0, st>>>(X, Y, ID, nid, nodes, flag, F, first_ge, n, X2, Y2, ID2,
-                                                 nodes_next, alive);
+                                                 nodes_next, alive, small, small_count, no_serial ? 0 : kSerialMax);
       std::swap(X, X2); std::swap(Y, Y2); std::swap(ID, ID2); std::swap(nodes, nodes_next);
     }
     int h_alive = 0;
@@ -440,6 +521,7 @@ int kd_build_faithful(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
       break;
     }
   }
+  kdf_serial_kernel<R><<<kNumSMs * 8, 32, 0, st>>>(X, Y, ID, small, small_count);
   GI_CUDA(cudaGetLastError());
   *order_dev = ID;
   return GI_OK;
