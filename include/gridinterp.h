@@ -118,8 +118,11 @@ void gi_host_free(void* p);
 /* cudaStreamSynchronize(stream) + the first device-side error recorded on it since the last call. */
 int gi_stream_status(void* stream);
 /* Environment variables read by the library (debugging aids, none is needed in production):
- *   GI_KD_TRACE=1   print the number of rounds of the quickselect-faithful k-d tree build to stderr
- *                   value forces the row-sequential fallback that runs when the list overflows (tests) */
+ *   GI_KD_TRACE=1            print the number of rounds of the quickselect-faithful k-d tree build to stderr
+ *   GI_BARY_TRACE=1          print, per walked window, what the barycentric fix-up paths had to do (flagged targets,
+ *                            fix-ups, rows redone along the reference's path, repair rounds); synchronises
+ *   GI_BARY_RASTER=1         the tile rasteriser instead of the walk for locate / evaluate (same results)
+ *   GI_KD_NO_SMEM_FINISH=1, GI_KD_NO_SERIAL_FINISH=1   k-d builds by launches / rounds down to the leaves (A/B) */
 /* Phase profiling: gi_set_profiling(1) starts a fresh recording on the calling thread; from then on every
  * call made by that thread records CUDA events around its phases (h2d, pack_mesh, walk, fill, d2h, ...) on
  * the stream it runs on, without synchronising.  gi_last_timings() waits for the last recorded event and
@@ -133,7 +136,8 @@ const char* gi_last_timing_name(int i);
  * chunks (results are identical to a one-shot call).  A band / chunk holds about `bytes` of output (default
  * 32 MB, at most 16 bands per call); 0 restores the default.  Process-wide tuning knob. */
 void gi_set_pipeline_band_bytes(uint64_t bytes);
-/* Return cached scratch memory of the current device to the driver. */
+/* Return cached scratch memory of the current device to the driver: the stream-ordered pool and the 8 MB arenas
+ * (one per stream a call ran on) that serve the small allocations of every call. */
 void gi_release_workspace(void);
 /* Capacity (targets per walked window) of the work list of the barycentric ambiguity fix-up, default 4 194 304;
  * when more targets lie within the margin band of a mesh edge the window is redone by the row-sequential walk.
