@@ -24,6 +24,8 @@
 //           none could be inserted (insertion needs d2 < max d2, which only shrinks), so the neighbour
 //           list after the skipped visit is bit-identical to the reference's; it cuts node visits ~14x when
 //           the k-th d2 is > 1.  GI_KD_REFERENCE_VISITS turns it off (visit-count parity with the oracle).
+#include <cooperative_groups.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -35,6 +37,7 @@
 
 namespace gi {
 namespace {
+namespace cg = cooperative_groups;
 
 // ---------------------------------------------------------------------------------------------
 // sort keys: both coordinate orders are produced by radix.cuh's stable sort on an order-preserving 64-bit image
@@ -339,11 +342,8 @@ kdf_init_kernel(PointsView<R> pts, int n, R* __restrict__ X, R* __restrict__ Y, 
 }
 
 template <class R>
-__global__ void __launch_bounds__(256)
-kdf_flag_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __restrict__ nid,
-                const KdfNode* __restrict__ nodes, int n, int* __restrict__ flag) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
+__device__ __forceinline__ int kdf_flag_at(int p, const R* __restrict__ X, const R* __restrict__ Y,
+                                           const int* __restrict__ nid, const KdfNode* __restrict__ nodes) {
   int f = 0;
   const int node = nid[p];
   if (node >= 0) {
@@ -354,15 +354,20 @@ kdf_flag_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __r
       f = K[p == pidx ? nd.a_hi : p] < K[pidx] ? 1 : 0;    // :129 (strict)
     }
   }
-  flag[p] = f;
+  return f;
+}
+template <class R>
+__global__ void __launch_bounds__(256)
+kdf_flag_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __restrict__ nid,
+                const KdfNode* __restrict__ nodes, int n, int* __restrict__ flag) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  flag[p] = kdf_flag_at<R>(p, X, Y, nid, nodes);
 }
 
 // per node: i0 = first position of the pass whose element is not "<" (a_hi if there is none)
-__global__ void __launch_bounds__(256)
-kdf_first_ge_kernel(const int* __restrict__ nid, const KdfNode* __restrict__ nodes, const int* __restrict__ F, int n,
-                    int* __restrict__ first_ge) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
+__device__ __forceinline__ void kdf_first_ge_at(int p, const int* __restrict__ nid, const KdfNode* __restrict__ nodes,
+                                                const int* __restrict__ F, int* __restrict__ first_ge) {
   const int node = nid[p];
   if (node < 0) return;
   const KdfNode nd = nodes[node];
@@ -375,16 +380,21 @@ kdf_first_ge_kernel(const int* __restrict__ nid, const KdfNode* __restrict__ nod
   }
   first_ge[node] = l;
 }
-
-template <class R>
 __global__ void __launch_bounds__(256)
-kdf_pass_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __restrict__ ID, int* __restrict__ nid,
-                const KdfNode* __restrict__ nodes, const int* __restrict__ flag, const int* __restrict__ F,
-                const int* __restrict__ first_ge, int n, R* __restrict__ X2, R* __restrict__ Y2,
-                int* __restrict__ ID2, KdfNode* __restrict__ nodes_next, int* __restrict__ alive,
-                KdfSmall* __restrict__ small, int* __restrict__ small_count, int serial_max) {
+kdf_first_ge_kernel(const int* __restrict__ nid, const KdfNode* __restrict__ nodes, const int* __restrict__ F, int n,
+                    int* __restrict__ first_ge) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
+  kdf_first_ge_at(p, nid, nodes, F, first_ge);
+}
+
+template <class R>
+__device__ __forceinline__ void
+kdf_pass_at(int p, const R* __restrict__ X, const R* __restrict__ Y, const int* __restrict__ ID, int* __restrict__ nid,
+            const KdfNode* __restrict__ nodes, const int* __restrict__ flag, const int* __restrict__ F,
+            const int* __restrict__ first_ge, R* __restrict__ X2, R* __restrict__ Y2,
+            int* __restrict__ ID2, KdfNode* __restrict__ nodes_next, int* __restrict__ alive,
+            KdfSmall* __restrict__ small, int* __restrict__ small_count, int serial_max) {
   const int node = nid[p];
   if (node < 0) { X2[p] = X[p]; Y2[p] = Y[p]; ID2[p] = ID[p]; return; }
   const KdfNode nd = nodes[node];
@@ -444,6 +454,79 @@ kdf_pass_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __r
     else if (left_small) nid[p] = -2;
   }
 }
+template <class R>
+__global__ void __launch_bounds__(256)
+kdf_pass_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __restrict__ ID, int* __restrict__ nid,
+                const KdfNode* __restrict__ nodes, const int* __restrict__ flag, const int* __restrict__ F,
+                const int* __restrict__ first_ge, int n, R* __restrict__ X2, R* __restrict__ Y2,
+                int* __restrict__ ID2, KdfNode* __restrict__ nodes_next, int* __restrict__ alive,
+                KdfSmall* __restrict__ small, int* __restrict__ small_count, int serial_max) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  kdf_pass_at<R>(p, X, Y, ID, nid, nodes, flag, F, first_ge, X2, Y2, ID2, nodes_next, alive, small, small_count,
+                 serial_max);
+}
+
+// All rounds in ONE cooperative launch (arrays of up to one element per resident thread, ~150 000 points): a round of
+// the host-driven form is eight sweeps over the array (flag, three scan kernels, first ">=", pass, two memsets) of
+// ~10 us each however small the array.  Here every CTA owns a contiguous chunk of the array and the phases of a round are separated by grid-wide
+// barriers: flags + chunk-local prefix | chunk offsets | first ">=" per node | pass.  Same device functions, same
+// arithmetic, same result.  `alive` has three slots: round r reports in slot r % 3 and clears slot (r + 1) % 3, which
+// nobody reads before the next barrier.
+template <class R> struct KdfRounds {
+  R *X, *Y, *X2, *Y2;
+  int *ID, *ID2, *nid, *flag, *F, *first_ge, *totals, *alive, *small_count, *rounds;
+  KdfNode *nodes, *nodes_next;
+  KdfSmall* small;
+  int n, serial_max, max_rounds;
+};
+template <class R>
+__global__ void __launch_bounds__(256) kdf_rounds_kernel(KdfRounds<R> a) {
+  cg::grid_group grid = cg::this_grid();
+  const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+  const int chunk = (a.n + nb - 1) / nb, per = (chunk + 255) >> 8;
+  const int c0 = min(a.n, b * chunk), c1 = min(a.n, c0 + chunk);
+  const int t0 = min(c1, c0 + tid * per), t1 = min(c1, t0 + per);   // this thread's elements (contiguous)
+  R *X = a.X, *Y = a.Y, *X2 = a.X2, *Y2 = a.Y2;
+  int *ID = a.ID, *ID2 = a.ID2;
+  KdfNode *nodes = a.nodes, *nodes_next = a.nodes_next;
+  int round = 0;
+  for (;; ++round) {
+    int* alive = a.alive + round % 3;
+    if (b == 0 && tid == 0) a.alive[(round + 1) % 3] = 0;
+    int acc = 0;
+    for (int p = t0; p < t1; ++p) {
+      const int f = kdf_flag_at<R>(p, X, Y, a.nid, nodes);
+      a.flag[p] = f;
+      acc += f;
+    }
+    int total;
+    int run = block_exclusive_scan_256(acc, &total);
+    for (int p = t0; p < t1; ++p) { a.F[p] = run; run += a.flag[p]; }
+    if (tid == 0) a.totals[b] = total;
+    grid.sync();
+    int part = 0;
+    for (int i = tid; i < b; i += 256) part += a.totals[i];
+    int offset;
+    block_exclusive_scan_256(part, &offset);
+    if (offset)
+      for (int p = t0; p < t1; ++p) a.F[p] += offset;
+    grid.sync();
+    for (int p = t0; p < t1; ++p) kdf_first_ge_at(p, a.nid, nodes, a.F, a.first_ge);
+    grid.sync();
+    for (int p = t0; p < t1; ++p)
+      kdf_pass_at<R>(p, X, Y, ID, a.nid, nodes, a.flag, a.F, a.first_ge, X2, Y2, ID2, nodes_next, alive, a.small,
+                     a.small_count, a.serial_max);
+    grid.sync();
+    { R* t = X; X = X2; X2 = t; t = Y; Y = Y2; Y2 = t; }
+    { int* t = ID; ID = ID2; ID2 = t; }
+    { KdfNode* t = nodes; nodes = nodes_next; nodes_next = t; }
+    if (!*(volatile int*)alive || round + 1 >= a.max_rounds) break;
+  }
+  if (X != a.X)   // an odd number of rounds: the result goes back to the caller's first set of arrays
+    for (int p = t0; p < t1; ++p) { a.X[p] = X[p]; a.Y[p] = Y[p]; a.ID[p] = ID[p]; }
+  if (b == 0 && tid == 0) *a.rounds = round + 1;
+}
 
 // 1 iff two neighbours of a sorted key list are equal (-0.0 and +0.0 count as equal, as `<` sees them)
 __global__ void __launch_bounds__(256)
@@ -501,7 +584,44 @@ int kd_build_faithful(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
     GI_CUDA(cudaMemcpyAsync(small_count, &one, sizeof(int), cudaMemcpyHostToDevice, st));
     GI_CUDA(cudaStreamSynchronize(st));   // (the two host words go out of scope)
   }
-  for (int64_t round = 0; n > kSerialMax || no_serial; round += kBatch) {
+  // all rounds in one cooperative launch where the device allows it (every CTA resident at once)
+  static const bool no_coop = getenv("GI_KD_NO_COOP") != nullptr;   // A/B and tests: the host-driven rounds
+  bool rounds_done = false;
+  if ((n > kSerialMax || no_serial) && !no_coop) {
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    GI_CUDA(cudaGetDevice(&dev));
+    GI_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    GI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kdf_rounds_kernel<R>, 256, 0));
+    // (one element per resident thread: with several, every thread's dependent loads -- node record, prefix sums, hop
+    //  chain -- queue up behind each other and a round of 1 M points takes 360 us instead of the launches' 110 us;
+    //  measured: 10 000 points 8.5 -> 4.2 ms, 100 000 points 28 -> 16.5 ms, 1 M points 27 -> 86 ms)
+    if (coop && per_sm > 0 && (int64_t)n <= (int64_t)sms * std::min(per_sm, 4) * 256) {
+      const int grid = std::max(1, std::min(sms * std::min(per_sm, 4), div_up(n, 256)));
+      int *totals, *alive3, *rounds;
+      GI_TRY(scr.alloc(&totals, (size_t)grid));
+      GI_TRY(scr.alloc(&alive3, 3));
+      GI_TRY(scr.alloc(&rounds, 1));
+      GI_CUDA(cudaMemsetAsync(alive3, 0, 3 * sizeof(int), st));
+      KdfRounds<R> ra;
+      ra.X = X; ra.Y = Y; ra.X2 = X2; ra.Y2 = Y2; ra.ID = ID; ra.ID2 = ID2; ra.nid = nid; ra.flag = flag; ra.F = F;
+      ra.first_ge = first_ge; ra.totals = totals; ra.alive = alive3; ra.small_count = small_count; ra.rounds = rounds;
+      ra.nodes = nodes; ra.nodes_next = nodes_next; ra.small = small;
+      ra.n = n; ra.serial_max = no_serial ? 0 : kSerialMax;
+      ra.max_rounds = (int)std::min<int64_t>(4 * (int64_t)n + 64, 0x7fffffff);
+      void* kargs[] = {&ra};
+      GI_CUDA(cudaLaunchCooperativeKernel((const void*)kdf_rounds_kernel<R>, dim3(grid), dim3(256), kargs, 0, st));
+      rounds_done = true;
+      if (getenv("GI_KD_TRACE")) {
+        int h_rounds = 0;
+        GI_CUDA(cudaMemcpyAsync(&h_rounds, rounds, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GI_CUDA(cudaStreamSynchronize(st));
+        fprintf(stderr, "[gridinterp] quickselect-faithful k-d build: n = %d, %d rounds (one cooperative launch, %d CTAs)\n",
+                n, h_rounds, grid);
+      }
+    }
+  }
+  for (int64_t round = 0; (n > kSerialMax || no_serial) && !rounds_done; round += kBatch) {
     GI_REQUIRE(round <= 4 * (int64_t)n + 64, "k-d build did not converge");
     GI_CUDA(cudaMemsetAsync(alive, 0, sizeof(int), st));
     for (int b = 0; b < kBatch; ++b) {
