@@ -333,12 +333,12 @@ __device__ __forceinline__ int kdf_virt(int i, int pidx, int hi) { return i == p
 template <class R>
 __global__ void __launch_bounds__(256)
 kdf_init_kernel(PointsView<R> pts, int n, R* __restrict__ X, R* __restrict__ Y, int* __restrict__ ID,
-                int* __restrict__ nid, KdfNode* __restrict__ nodes) {
+                int* __restrict__ nid, KdfNode* __restrict__ nodes, int* __restrict__ first_ge) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   X[p] = pts.x(p); Y[p] = pts.y(p); ID[p] = p;
   nid[p] = 0;
-  if (p == 0) nodes[0] = KdfNode{0, n - 1, n - 1, 0};
+  if (p == 0) { nodes[0] = KdfNode{0, n - 1, n - 1, 0}; first_ge[0] = n - 1; }
 }
 
 template <class R>
@@ -394,7 +394,10 @@ kdf_pass_at(int p, const R* __restrict__ X, const R* __restrict__ Y, const int* 
             const KdfNode* __restrict__ nodes, const int* __restrict__ flag, const int* __restrict__ F,
             const int* __restrict__ first_ge, R* __restrict__ X2, R* __restrict__ Y2,
             int* __restrict__ ID2, KdfNode* __restrict__ nodes_next, int* __restrict__ alive,
-            KdfSmall* __restrict__ small, int* __restrict__ small_count, int serial_max) {
+            KdfSmall* __restrict__ small, int* __restrict__ small_count, int serial_max,
+            int* __restrict__ first_ge_next = nullptr) {
+  // (first_ge_next: the fused flag / scan kernel finds a node's first ">=" position with atomicMin and needs the
+  //  word preset to the range's last position; whoever writes a node's next state presets it)
   const int node = nid[p];
   if (node < 0) { X2[p] = X[p]; Y2[p] = Y[p]; ID2[p] = ID[p]; return; }
   const KdfNode nd = nodes[node];
@@ -436,15 +439,23 @@ kdf_pass_at(int p, const R* __restrict__ X, const R* __restrict__ Y, const int* 
   // a child of at most kSerialMax points leaves the rounds: kdf_serial_kernel finishes its whole sub-tree
   const bool left_small = k - node <= serial_max, right_small = nd.n_hi - k <= serial_max;   // (0: none)
   if (p == hi) {  // one thread per node writes the next state(s)
-    if (!fin) { nodes_next[node] = KdfNode{nlo, nhi, nd.n_hi, nd.depth}; *alive = 1; }
-    else {
+    if (!fin) {
+      nodes_next[node] = KdfNode{nlo, nhi, nd.n_hi, nd.depth}; *alive = 1;
+      if (first_ge_next) first_ge_next[node] = nhi;
+    } else {
       if (k > node) {                                                                                        // :64-65
         if (left_small) small[atomicAdd(small_count, 1)] = KdfSmall{node, k - 1, nd.depth + 1};
-        else { nodes_next[node] = KdfNode{node, k - 1, k - 1, nd.depth + 1}; *alive = 1; }
+        else {
+          nodes_next[node] = KdfNode{node, k - 1, k - 1, nd.depth + 1}; *alive = 1;
+          if (first_ge_next) first_ge_next[node] = k - 1;
+        }
       }
       if (k < nd.n_hi) {                                                                                     // :66-68
         if (right_small) small[atomicAdd(small_count, 1)] = KdfSmall{k + 1, nd.n_hi, nd.depth + 1};
-        else { nodes_next[k + 1] = KdfNode{k + 1, nd.n_hi, nd.n_hi, nd.depth + 1}; *alive = 1; }
+        else {
+          nodes_next[k + 1] = KdfNode{k + 1, nd.n_hi, nd.n_hi, nd.depth + 1}; *alive = 1;
+          if (first_ge_next) first_ge_next[k + 1] = nd.n_hi;
+        }
       }
     }
   }
@@ -460,11 +471,93 @@ kdf_pass_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __r
                 const KdfNode* __restrict__ nodes, const int* __restrict__ flag, const int* __restrict__ F,
                 const int* __restrict__ first_ge, int n, R* __restrict__ X2, R* __restrict__ Y2,
                 int* __restrict__ ID2, KdfNode* __restrict__ nodes_next, int* __restrict__ alive,
-                KdfSmall* __restrict__ small, int* __restrict__ small_count, int serial_max) {
+                KdfSmall* __restrict__ small, int* __restrict__ small_count, int serial_max,
+                int* __restrict__ first_ge_next) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   kdf_pass_at<R>(p, X, Y, ID, nid, nodes, flag, F, first_ge, X2, Y2, ID2, nodes_next, alive, small, small_count,
-                 serial_max);
+                 serial_max, first_ge_next);
+}
+
+// Flags, their prefix sums and every node's first ">=" position in ONE sweep (instead of flag kernel + three scan
+// kernels + binary searches): a single-pass scan with decoupled look-back.  A tile (256 threads x 8 elements) takes
+// its number from a ticket counter, publishes its aggregate, then walks back over its predecessors' words until one
+// holds an inclusive prefix.  A word is stamped with the round it belongs to, so nothing is reset between rounds.
+constexpr int kFusedItems = 8;
+constexpr int kFusedTile = 256 * kFusedItems;
+template <class R>
+__global__ void __launch_bounds__(256)
+kdf_flag_scan_kernel(const R* __restrict__ X, const R* __restrict__ Y, const int* __restrict__ nid,
+                     const KdfNode* __restrict__ nodes, int n, int* __restrict__ flag, int* __restrict__ F,
+                     int* __restrict__ first_ge, unsigned long long* state, unsigned* ticket, unsigned round,
+                     int num_tiles) {
+  __shared__ int s_tile, s_prefix;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_tile = (int)(atomicAdd(ticket, 1u) - round * (unsigned)num_tiles);
+  __syncthreads();
+  const int tile = s_tile;
+  // flags are computed with coalesced accesses (element j * 256 + tid of the tile) and handed through shared memory to
+  // the thread that scans them (elements tid * 8 .. tid * 8 + 7)
+  __shared__ int s_f[kFusedTile];
+  const int tile0 = tile * kFusedTile;
+#pragma unroll
+  for (int j = 0; j < kFusedItems; ++j) {
+    const int p = tile0 + j * 256 + tid;
+    int fl = 0;
+    if (p < n) {
+      const int node = nid[p];
+      if (node >= 0) {
+        const KdfNode nd = nodes[node];
+        if (p >= nd.a_lo && p < nd.a_hi) {
+          const R* K = (nd.depth & 1) ? Y : X;                 // axis = mod(depth, 2)   (kd_tree.f90:45)
+          const int pidx = (nd.a_lo + nd.a_hi) >> 1;           // :115
+          fl = K[p == pidx ? nd.a_hi : p] < K[pidx] ? 1 : 0;   // :129 (strict)
+          // i0 = first position of the pass whose element is not "<" (preset to a_hi by the previous pass)
+          if (!fl && p < *(volatile int*)(first_ge + node)) atomicMin(first_ge + node, p);
+        }
+      }
+      flag[p] = fl;
+    }
+    s_f[j * 256 + tid] = fl;
+  }
+  __syncthreads();
+  int f[kFusedItems];
+  int acc = 0;
+#pragma unroll
+  for (int i = 0; i < kFusedItems; ++i) { f[i] = s_f[tid * kFusedItems + i]; acc += f[i]; }
+  int total;
+  int run = block_exclusive_scan_256(acc, &total);
+  if (tid == 0) {
+    const unsigned long long stamp = (unsigned long long)(round & 0x3fffffffu) << 34;
+    volatile unsigned long long* vs = state;
+    if (tile == 0) {
+      vs[0] = stamp | (2ull << 32) | (unsigned)total;
+      s_prefix = 0;
+    } else {
+      vs[tile] = stamp | (1ull << 32) | (unsigned)total;       // my aggregate
+      int excl = 0;
+      for (int t = tile - 1;;) {
+        const unsigned long long v = vs[t];
+        const unsigned st = (unsigned)(v >> 32) & 3u;
+        if ((v >> 34) != (stamp >> 34) || st == 0u) continue;  // not published in this round yet
+        excl += (int)(unsigned)v;
+        if (st == 2u) break;
+        --t;
+      }
+      vs[tile] = stamp | (2ull << 32) | (unsigned)(excl + total);
+      s_prefix = excl;
+    }
+  }
+  __syncthreads();
+  run += s_prefix;
+#pragma unroll
+  for (int i = 0; i < kFusedItems; ++i) { s_f[tid * kFusedItems + i] = run; run += f[i]; }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kFusedItems; ++j) {
+    const int p = tile0 + j * 256 + tid;
+    if (p < n) F[p] = s_f[j * 256 + tid];
+  }
 }
 
 // All rounds in ONE cooperative launch (arrays of up to one element per resident thread, ~150 000 points): a round of
@@ -574,7 +667,7 @@ int kd_build_faithful(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
   GI_TRY(scr.alloc(&small_count, 1));
   GI_CUDA(cudaMemsetAsync(small_count, 0, sizeof(int), st));
   const int blocks = div_up(n, 256);
-  kdf_init_kernel<R><<<blocks, 256, 0, st>>>(pv, n, X, Y, ID, nid, nodes);
+  kdf_init_kernel<R><<<blocks, 256, 0, st>>>(pv, n, X, Y, ID, nid, nodes, first_ge);
   static const bool no_serial = getenv("GI_KD_NO_SERIAL_FINISH") != nullptr;   // A/B and tests: rounds down to the leaves
   constexpr int kBatch = 8;  // rounds between two looks at the `alive` word
   if (n <= kSerialMax && !no_serial) {   // the whole tree is one small sub-array
@@ -621,17 +714,37 @@ int kd_build_faithful(Scratch& scr, PointsView<R> pv, int n, int** order_dev) {
       }
     }
   }
+  // host-driven rounds: two launches per round (flags + prefix sums + first ">=" in one sweep, then the pass)
+  static const bool no_fused = getenv("GI_KD_NO_FUSED_SCAN") != nullptr;   // A/B and tests: six launches per round
+  const int fused_tiles = div_up(n, kFusedTile);
+  int* first_ge_next = nullptr;
+  unsigned long long* tile_state = nullptr;
+  unsigned* ticket = nullptr;
+  if (!rounds_done && !no_fused) {
+    GI_TRY(scr.alloc(&first_ge_next, (size_t)n));
+    GI_TRY(scr.alloc(&tile_state, (size_t)fused_tiles));
+    GI_TRY(scr.alloc(&ticket, 1));
+    GI_CUDA(cudaMemsetAsync(tile_state, 0xff, sizeof(unsigned long long) * (size_t)fused_tiles, st));
+    GI_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+  }
   for (int64_t round = 0; (n > kSerialMax || no_serial) && !rounds_done; round += kBatch) {
     GI_REQUIRE(round <= 4 * (int64_t)n + 64, "k-d build did not converge");
     GI_CUDA(cudaMemsetAsync(alive, 0, sizeof(int), st));
     for (int b = 0; b < kBatch; ++b) {
-      kdf_flag_kernel<R><<<blocks, 256, 0, st>>>(X, Y, nid, nodes, n, flag);
-      GI_TRY(kdf_scan(flag, F, n, sums, st));
-      kdf_first_ge_kernel<<<blocks, 256, 0, st>>>(nid, nodes, F, n, first_ge);
+      if (no_fused) {
+        kdf_flag_kernel<R><<<blocks, 256, 0, st>>>(X, Y, nid, nodes, n, flag);
+        GI_TRY(kdf_scan(flag, F, n, sums, st));
+        kdf_first_ge_kernel<<<blocks, 256, 0, st>>>(nid, nodes, F, n, first_ge);
+      } else {
+        kdf_flag_scan_kernel<R><<<fused_tiles, 256, 0, st>>>(X, Y, nid, nodes, n, flag, F, first_ge, tile_state, ticket,
+                                                            (unsigned)(round + b), fused_tiles);
+      }
       if (b == kBatch - 1) GI_CUDA(cudaMemsetAsync(alive, 0, sizeof(int), st));  // what the LAST round leaves
       kdf_pass_kernel<R><<<blocks, 256, 0, st>>>(X, Y, ID, nid, nodes, flag, F, first_ge, n, X2, Y2, ID2,
-                                                 nodes_next, alive, small, small_count, no_serial ? 0 : kSerialMax);
+                                                 nodes_next, alive, small, small_count, no_serial ? 0 : kSerialMax,
+                                                 no_fused ? nullptr : first_ge_next);
       std::swap(X, X2); std::swap(Y, Y2); std::swap(ID, ID2); std::swap(nodes, nodes_next);
+      if (!no_fused) std::swap(first_ge, first_ge_next);
     }
     int h_alive = 0;
     GI_CUDA(cudaMemcpyAsync(&h_alive, alive, sizeof(int), cudaMemcpyDeviceToHost, st));
