@@ -1587,10 +1587,13 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
     } else if (small_rows == 8 && !peers && !bp) {
       if (fy) GI_LAUNCH_SMALL(true, 8); else GI_LAUNCH_SMALL(false, 8);
     } else {
+#ifndef GI_WALK_MINB
+#define GI_WALK_MINB 8   // CTAs per SM the full-grid kernel is compiled for (64 registers); A/B: profiles/r02_walk_variants.md
+#endif
 #define GI_LAUNCH_WALK3(FY_, PEERS_, BP_, CF_)                                                                  \
   do {                                                                                                          \
-    if (pm.plane) locate_eval_kernel<R, FY_, PEERS_, kRows, 8, BP_, CF_, true><<<grid, kWalkThreads, 0, st>>>(wa); \
-    else locate_eval_kernel<R, FY_, PEERS_, kRows, 8, BP_, CF_, false><<<grid, kWalkThreads, 0, st>>>(wa);         \
+    if (pm.plane) locate_eval_kernel<R, FY_, PEERS_, kRows, GI_WALK_MINB, BP_, CF_, true><<<grid, kWalkThreads, 0, st>>>(wa); \
+    else locate_eval_kernel<R, FY_, PEERS_, kRows, GI_WALK_MINB, BP_, CF_, false><<<grid, kWalkThreads, 0, st>>>(wa); \
   } while (0)
 #define GI_LAUNCH_WALK2(FY_, PEERS_, BP_)           \
   do {                                              \
