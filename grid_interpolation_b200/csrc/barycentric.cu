@@ -675,7 +675,7 @@ template <class R> __device__ __forceinline__ int start_triangle(const WalkArgs<
 // Phase 2 of the locate / raster kernels: evaluate one strip of ROWS x kWalkThreads targets whose triangles are in
 // the shared-memory tile `stri` (>= 0: inside that triangle; < 0: outside the hull, ~id of the last valid triangle
 // or -1), store the values and the outside-hull mask words.
-template <class R, bool FY, bool PEERS, int ROWS, bool PLANE = false>
+template <class R, bool FY, bool PEERS, int ROWS, bool PLANE = false, bool LEAN = false>
 __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (*stri)[kWalkThreads], const R* saxis,
                                                int srow0, int nrows, int lane_f, bool active, R cf) {
   const TargetWindow<R>& w = a.win;
@@ -697,7 +697,8 @@ __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (
   R c1 = 0, q1 = 0, c2 = 0, q2 = 0, p3 = 0, d1 = 0, d2 = 0, d3 = 0;
   DivRcp<R> dv;
   dv.d = R(1); dv.r2 = R(1);
-#pragma unroll 2
+  // (LEAN: the 56-register instantiation, see walk_lean(); two rows in flight cost it registers it does not have)
+#pragma unroll(LEAN ? 1 : 2)
   for (int r = 0; r < nrows; ++r) {
     const int t = active ? stri[r][tid] : 0;
     const bool inside = t >= 0;
@@ -774,7 +775,12 @@ __device__ __forceinline__ void evaluate_strip(const WalkArgs<R>& a, const int (
 //                      shared-reciprocal divisions; 128 consecutive doubles per row are stored coalesced and
 //                      the outside-hull bits come from one ballot per warp row.
 // ---------------------------------------------------------------------------------------------
-template <class R, bool FY, bool PEERS, int ROWS, bool BP, bool CF, bool PLANE = false>
+// The full-grid kernel of the headline layout runs at 9 CTAs per SM instead of 8 (+3.6 %, profiles/r02_walk_variants.md)
+// if it fits 56 registers without spilling into the walk loop, which it does once the iteration counter (iters_tot,
+// a diagnostic) and the second in-flight row of phase 2 (-1.6 %) are gone.  The y-fast instantiation still spills at
+// 56 registers and loses (2.78 -> 2.92 ms), so only x-fast, whole-mesh, many-wave windows are "lean" (and not the plane form, which spills there too).
+constexpr bool walk_lean(bool fy, bool peers, bool bp, bool cf) { return !fy && !peers && !bp && !cf; }
+template <class R, bool FY, bool PEERS, int ROWS, bool BP, bool CF, bool PLANE = false, bool LEAN = false>
 __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, int by, int (*stri)[kWalkThreads], R* saxis) {
   const TargetWindow<R>& w = a.win;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -882,7 +888,7 @@ __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, i
         fresh = false;
       }
       stri[r][tid] = (outside | sliver) ? ~tri : tri;
-      iters += it;
+      if (!LEAN) iters += it;   // (iters_tot: not counted by the lean instantiation)
       it = 0;
       ++r;
     }
@@ -890,7 +896,7 @@ __device__ __forceinline__ void locate_eval_tile(const WalkArgs<R>& a, int bx, i
   }
   __syncthreads();
 
-  evaluate_strip<R, FY, PEERS, ROWS, PLANE>(a, stri, saxis, srow0, nrows, lane_f, active, cf);
+  evaluate_strip<R, FY, PEERS, ROWS, PLANE, LEAN>(a, stri, saxis, srow0, nrows, lane_f, active, cf);
   // one atomic per warp for the iteration counter (iters_tot, interpolation.f90:374)
   for (int off = 16; off > 0; off >>= 1) iters_sum += __shfl_down_sync(0xffffffffu, iters_sum, off);
   if (lane == 0 && iters_sum) atomicAdd((unsigned long long*)a.counters, (unsigned long long)iters_sum);
@@ -900,7 +906,7 @@ template <class R, bool FY, bool PEERS, int ROWS, int MINB, bool BP, bool CF, bo
 __global__ void __launch_bounds__(kWalkThreads, MINB) locate_eval_kernel(const WalkArgs<R> a) {
   __shared__ int stri[ROWS][kWalkThreads];
   __shared__ R saxis[ROWS];
-  locate_eval_tile<R, FY, PEERS, ROWS, BP, CF, PLANE>(a, blockIdx.x, blockIdx.y, stri, saxis);
+  locate_eval_tile<R, FY, PEERS, ROWS, BP, CF, PLANE, (MINB > 8)>(a, blockIdx.x, blockIdx.y, stri, saxis);
 }
 
 // The same as a stand-by for the rasteriser (raster.cuh): a small grid that returns at once unless the device
@@ -1587,13 +1593,20 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
     } else if (small_rows == 8 && !peers && !bp) {
       if (fy) GI_LAUNCH_SMALL(true, 8); else GI_LAUNCH_SMALL(false, 8);
     } else {
-#ifndef GI_WALK_MINB
-#define GI_WALK_MINB 8   // CTAs per SM the full-grid kernel is compiled for (64 registers); A/B: profiles/r02_walk_variants.md
-#endif
-#define GI_LAUNCH_WALK3(FY_, PEERS_, BP_, CF_)                                                                  \
-  do {                                                                                                          \
-    if (pm.plane) locate_eval_kernel<R, FY_, PEERS_, kRows, GI_WALK_MINB, BP_, CF_, true><<<grid, kWalkThreads, 0, st>>>(wa); \
-    else locate_eval_kernel<R, FY_, PEERS_, kRows, GI_WALK_MINB, BP_, CF_, false><<<grid, kWalkThreads, 0, st>>>(wa); \
+#define GI_LAUNCH_WALK3(FY_, PEERS_, BP_, CF_)                                                                    \
+  do {                                                                                                            \
+    if (pm.plane) {                                                                                               \
+      locate_eval_kernel<R, FY_, PEERS_, kRows, 8, BP_, CF_, true><<<grid, kWalkThreads, 0, st>>>(wa);            \
+    } else {                                                                                                      \
+      bool launched = false;                                                                                      \
+      if constexpr (walk_lean(FY_, PEERS_, BP_, CF_)) {   /* (not with debug outputs: they include iters_tot) */  \
+        if (wa.tri_out == nullptr) {                                                                              \
+          locate_eval_kernel<R, FY_, PEERS_, kRows, 9, BP_, CF_, false><<<grid, kWalkThreads, 0, st>>>(wa);       \
+          launched = true;                                                                                        \
+        }                                                                                                         \
+      }                                                                                                           \
+      if (!launched) locate_eval_kernel<R, FY_, PEERS_, kRows, 8, BP_, CF_, false><<<grid, kWalkThreads, 0, st>>>(wa); \
+    }                                                                                                             \
   } while (0)
 #define GI_LAUNCH_WALK2(FY_, PEERS_, BP_)           \
   do {                                              \
