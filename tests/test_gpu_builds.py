@@ -87,3 +87,31 @@ def test_esrg_binning_sizes(n, lx, ly):
     same(idx, oi)
     same(ptr[:-1].reshape(ly, lx) + 1, op)
     assert ptr[-1] == n
+
+
+@pytest.mark.parametrize("switch", ["GI_KD_NO_SMEM_FINISH", "GI_KD_NO_SERIAL_FINISH", "GI_KD_NO_COOP",
+                                    "GI_KD_NO_COOP,GI_KD_NO_FUSED_SCAN"])
+def test_kd_build_alternative_paths(switch, tmp_path):
+    """The A/B switches of the k-d builds (launch-per-level canonical build, rounds down to the leaves, host-driven
+    rounds, six-launch rounds) are read once per process: each is exercised in a child process on a random set (distinct
+    coordinates and a forced faithful build), a lattice (ties) and a set large enough for the host-driven rounds, and
+    must give the oracle's tree node by node."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import test_gpu_builds as t
+        rng = np.random.default_rng(3)
+        gx, gy = np.meshgrid(np.arange(60.0), np.arange(45.0))
+        lattice = np.stack([gx.ravel(), gy.ravel()])[:, rng.permutation(2700)]
+        t.check_tree(rng.uniform(0, 100, (2, 5000)))
+        t.check_tree(rng.uniform(0, 100, (2, 5000)), faithful=True)
+        t.check_tree(lattice)
+        t.check_tree(np.round(rng.uniform(0, 50, (2, 200_000)), 2))
+        print("ok")
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    for name in switch.split(","):
+        env[name] = "1"
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
