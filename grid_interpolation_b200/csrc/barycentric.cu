@@ -1576,7 +1576,7 @@ int bary_walk(const WalkArgs<R>& wa_in, const PackedMesh<R>& pm, const R* x_axis
     // Small windows (the reference's own test size: 132 x 79 targets on 10 k triangles) are a handful of CTAs whose
     // threads each walk a dependent chain of 32 rows -- ~1.5 record fetches per row at L2 latency.  Shorter strips
     // give more, shorter chains (each pays its own seed walk): 132 x 79 targets 0.135 -> 0.082 ms for walk + fill +
-    // copy-out with strips of 4 rows, 586 x 347 targets 0.19 -> 0.13 ms (bench/c1_rows_probe.py, profiles/r02_c1_*).
+    // copy-out with strips of 4 rows, 586 x 347 targets 0.19 -> 0.13 ms (profiles/r02_c1_rows_probe.txt).
     int small_rows = 0;
     if (!peers && !bp) {
       if ((int64_t)grid.x * div_up(ns, 8) <= kNumSMs * 4) small_rows = 4;
