@@ -63,6 +63,21 @@ def test_shape_errors_raise_value_error_like_f2py():
         ip.barycentric_interpolation(pts, np.zeros(10), x, y, np.ones((3, 3), int), np.ones((4, 3), int))
     with pytest.raises(ValueError):
         ip.idw_esrg_nearest_ex(pts, np.zeros(10), x, y, 1.0, 3, rows=(3, 9))
+    simp = np.ones((4, 3), np.int32)
+    with pytest.raises(ValueError):
+        ip.mesh_reorder(pts[:, :1], simp, simp)                       # points must be (n, 2)
+    with pytest.raises(ValueError):
+        ip.mesh_reorder(pts, simp[:, :2], simp)                       # simplices must be (t, 3)
+    with pytest.raises(ValueError):
+        ip.mesh_reorder(pts, simp, np.ones((5, 3), np.int32))         # neighbours must match simplices
+
+
+def test_mesh_reorder_fails_loudly_without_a_gpu():
+    if _lib.lib().gi_device_count() > 0:
+        pytest.skip("a GPU is present")
+    simp = np.array([[1, 2, 3]], np.int32)
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        ip.mesh_reorder(np.random.rand(3, 2), simp, np.zeros((1, 3), np.int32))
 
 
 def test_no_silent_cpu_fallback():
